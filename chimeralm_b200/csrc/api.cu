@@ -1,0 +1,698 @@
+// C-ABI implementation: context, weights, workspaces and the launch sequence of the predict
+// forward.  See include/chimeralm_b200.h for the contract of every export.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/chimeralm_b200.h"
+#include "gemm_tcgen05.cuh"
+#include "kernels.cuh"
+#include "longconv.cuh"
+
+using namespace clm;
+
+namespace {
+
+struct Tensor {
+  float* d = nullptr;
+  std::vector<int64_t> shape;
+  int64_t numel = 0;
+};
+
+struct LayerW {
+  const float *ln1_g, *ln1_b, *ln2_g, *ln2_b;
+  const float *in_b, *out_b, *fc1_b, *fc2_b;
+  const float *sc_w, *sc_b, *fbias;
+  __nv_bfloat16 *in_w, *out_w, *fc1_w, *fc2_w;
+  CUtensorMap tm_in, tm_out, tm_fc1, tm_fc2;
+  float* k = nullptr;                               // [D][Lk]
+  float2* gspec[LONGCONV_MAX_LOGN + 1] = {nullptr};  // per LOGN: [n_seg][D][N]
+};
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+constexpr int MIN_LOGN = 8;
+
+}  // namespace
+
+struct clm_ctx {
+  clm_config cfg;
+  int device = 0;
+  int num_sms = 148;
+  bool finalized = false;
+  std::string err;
+  std::map<std::string, Tensor> w;
+  std::vector<LayerW> layers;
+  long long Lk = 0;  // padded filter row length
+  // head / final
+  const float *lnf_g, *lnf_b, *emb;
+  __nv_bfloat16* att0_w = nullptr;
+  CUtensorMap tm_att0;
+  const float *att0_b, *att2_w;
+  float att2_b = 0.f;
+  HeadParams head{};
+  // workspaces
+  int max_B = 0, max_T = 0, Tp_max = 0;
+  float* R = nullptr;
+  __nv_bfloat16 *XN = nullptr, *U = nullptr, *VX = nullptr, *X0 = nullptr, *Y = nullptr, *YT = nullptr;
+  float *score = nullptr, *part = nullptr, *pooled = nullptr;
+  float2* scratch = nullptr;
+  size_t scratch_bytes = 0;
+  int* d_err = nullptr;
+  int n_split = 1;
+  // e2e staging
+  cudaStream_t own_stream = nullptr;
+  uint8_t* st_bases = nullptr;
+  size_t st_bases_cap = 0;
+  int64_t* st_offsets = nullptr;
+  uint8_t* st_ids = nullptr;
+  float* st_logits = nullptr;
+  uint8_t* st_labels = nullptr;
+  // debug
+  int dbg_layer = -1, dbg_stage = -1;
+  long long launches = 0;
+  EncodeTiledFn encode_tiled = nullptr;
+  std::vector<void*> owned;  // device allocations freed at destroy
+};
+
+namespace {
+
+int fail(clm_ctx* c, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (c) c->err = buf;
+  return code;
+}
+
+#define CLM_CUDA(ctx, expr)                                                                          \
+  do {                                                                                               \
+    cudaError_t e_ = (expr);                                                                         \
+    if (e_ != cudaSuccess)                                                                           \
+      return fail(ctx, CLM_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+#define CLM_LAUNCH_CHECK(ctx, what)                                                                  \
+  do {                                                                                               \
+    cudaError_t e_ = cudaGetLastError();                                                             \
+    if (e_ != cudaSuccess) return fail(ctx, CLM_ERR_CUDA, "launch %s failed: %s", what, cudaGetErrorString(e_)); \
+    (ctx)->launches++;                                                                               \
+  } while (0)
+
+template <typename T>
+int dev_alloc(clm_ctx* c, T** p, size_t count) {
+  void* q = nullptr;
+  cudaError_t e = cudaMalloc(&q, count * sizeof(T) + 256);
+  if (e != cudaSuccess) return fail(c, CLM_ERR_NOMEM, "cudaMalloc(%zu bytes) failed: %s", count * sizeof(T), cudaGetErrorString(e));
+  c->owned.push_back(q);
+  *p = reinterpret_cast<T*>(q);
+  return 0;
+}
+
+void dev_free(clm_ctx* c, void* p) {
+  if (!p) return;
+  for (auto& q : c->owned)
+    if (q == p) {
+      cudaFree(q);
+      q = nullptr;
+    }
+}
+
+__global__ void f32_to_bf16_kernel(const float* __restrict__ s, __nv_bfloat16* __restrict__ d, long long n) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) d[i] = __float2bfloat16(s[i]);
+}
+
+int make_tmap_bf16_2d(clm_ctx* c, CUtensorMap* tm, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {cols * 2};
+  cuuint32_t box[2] = {(cuuint32_t)GEMM_BK, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = c->encode_tiled(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box,
+                               estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(c, CLM_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d (rows=%llu cols=%llu)", (int)r, (unsigned long long)rows, (unsigned long long)cols);
+  return 0;
+}
+
+const Tensor* find(clm_ctx* c, const std::string& name) {
+  auto it = c->w.find(name);
+  return it == c->w.end() ? nullptr : &it->second;
+}
+
+int need(clm_ctx* c, const std::string& name, int64_t numel, const float** out) {
+  const Tensor* t = find(c, name);
+  if (!t) return fail(c, CLM_ERR_MISSING, "weight '%s' was not loaded", name.c_str());
+  if (t->numel != numel) return fail(c, CLM_ERR_INVALID, "weight '%s' has %lld elements, expected %lld", name.c_str(), (long long)t->numel, (long long)numel);
+  *out = t->d;
+  return 0;
+}
+
+int to_bf16(clm_ctx* c, const float* src, int64_t n, __nv_bfloat16** out) {
+  int rc = dev_alloc(c, out, (size_t)n);
+  if (rc) return rc;
+  f32_to_bf16_kernel<<<(unsigned)((n + 255) / 256), 256>>>(src, *out, n);
+  CLM_LAUNCH_CHECK(c, "f32_to_bf16");
+  return 0;
+}
+
+template <int BN, int STAGES, int EPI>
+int launch_gemm_t(clm_ctx* c, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t st) {
+  using S = GemmSmem<BN, STAGES>;
+  static bool attr_set = false;
+  auto kern = gemm_bf16_tn_kernel<BN, STAGES, EPI>;
+  if (!attr_set) {
+    CLM_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
+    attr_set = true;
+  }
+  dim3 grid((p.M + GEMM_BM - 1) / GEMM_BM, p.N / BN);
+  kern<<<grid, GEMM_THREADS, S::kTotal, st>>>(tmA, tmB, p);
+  CLM_LAUNCH_CHECK(c, "gemm_bf16_tn");
+  return 0;
+}
+
+int launch_gemm(clm_ctx* c, const void* A, const CUtensorMap& tmB, const GemmParams& p, int epi, cudaStream_t st) {
+  if (p.K % GEMM_BK != 0 || p.K <= 0) return fail(c, CLM_ERR_INVALID, "gemm: K=%d must be a positive multiple of %d", p.K, GEMM_BK);
+  if (p.M <= 0) return fail(c, CLM_ERR_INVALID, "gemm: M=%d", p.M);
+  CUtensorMap tmA;
+  int rc = make_tmap_bf16_2d(c, &tmA, A, (uint64_t)p.M, (uint64_t)p.K, GEMM_BM);
+  if (rc) return rc;
+  if (epi == EPI_SCORE) {
+    if (p.N != 256) return fail(c, CLM_ERR_INVALID, "gemm: scorer epilogue needs N == 256 (got %d)", p.N);
+    return launch_gemm_t<256, 2, EPI_SCORE>(c, tmA, tmB, p, st);
+  }
+  if (p.N % 128 != 0) return fail(c, CLM_ERR_INVALID, "gemm: N=%d must be a multiple of 128", p.N);
+  switch (epi) {
+    case EPI_BIAS_BF16: return launch_gemm_t<128, 3, EPI_BIAS_BF16>(c, tmA, tmB, p, st);
+    case EPI_BIAS_GELU_TANH: return launch_gemm_t<128, 3, EPI_BIAS_GELU_TANH>(c, tmA, tmB, p, st);
+    case EPI_BIAS_RES_F32: return launch_gemm_t<128, 3, EPI_BIAS_RES_F32>(c, tmA, tmB, p, st);
+    default: return fail(c, CLM_ERR_INVALID, "gemm: unknown epilogue %d", epi);
+  }
+}
+
+// ---- long convolution dispatch -------------------------------------------------------------
+struct ConvPlan {
+  int logn, n_chunks;
+};
+
+ConvPlan plan_conv(int T) {
+  for (int logn = MIN_LOGN; logn <= LONGCONV_MAX_LOGN; ++logn) {
+    const int C = 1 << (logn - 1);
+    if (T <= C + LONGCONV_TAIL_MAX) return {logn, 1};
+  }
+  const int C = 1 << (LONGCONV_MAX_LOGN - 1);
+  int n = T / C;
+  if (T % C > LONGCONV_TAIL_MAX) n += 1;
+  return {LONGCONV_MAX_LOGN, n};
+}
+
+int n_segments(const clm_ctx* c, int logn) {
+  if (logn < LONGCONV_MAX_LOGN) return 1;
+  const int C = 1 << (logn - 1);
+  return (c->cfg.max_seq_len + C - 1) / C;
+}
+
+template <int LOGN>
+int spectrum_t(clm_ctx* c, LayerW& L) {
+  using Cfg = ConvCfg<LOGN>;
+  const int D = c->cfg.d_model, nseg = n_segments(c, LOGN);
+  int rc = dev_alloc(c, &L.gspec[LOGN], (size_t)nseg * D * Cfg::N);
+  if (rc) return rc;
+  auto kern = filter_spectrum_kernel<LOGN>;
+  CLM_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+  kern<<<dim3(D, nseg), Cfg::THREADS, Cfg::SMEM>>>(L.k, c->Lk, c->cfg.max_seq_len, L.gspec[LOGN], D);
+  CLM_LAUNCH_CHECK(c, "filter_spectrum");
+  return 0;
+}
+
+template <int LOGN>
+int conv_t(clm_ctx* c, const LongConvParams& p, int grid, cudaStream_t st) {
+  using Cfg = ConvCfg<LOGN>;
+  static bool attr_set = false;
+  auto kern = longconv_kernel<LOGN>;
+  if (!attr_set) {
+    CLM_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+    attr_set = true;
+  }
+  kern<<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(p);
+  CLM_LAUNCH_CHECK(c, "longconv");
+  return 0;
+}
+
+size_t conv_scratch_bytes(const clm_ctx* c, int T) {
+  ConvPlan pl = plan_conv(T);
+  if (pl.n_chunks <= 1) return 0;
+  return (size_t)c->num_sms * pl.n_chunks * ((size_t)1 << pl.logn) * sizeof(float2);
+}
+
+int launch_longconv(clm_ctx* c, int layer, const __nv_bfloat16* vx, const __nv_bfloat16* x0, __nv_bfloat16* out, int B,
+                    int T, int Tp, float2* scratch, size_t scratch_bytes, cudaStream_t st) {
+  if (T > c->cfg.max_seq_len) return fail(c, CLM_ERR_INVALID, "longconv: T=%d exceeds max_seq_len=%d", T, c->cfg.max_seq_len);
+  const ConvPlan pl = plan_conv(T);
+  LayerW& L = c->layers[layer];
+  LongConvParams p{};
+  p.vx = vx; p.x0 = x0; p.out = out;
+  p.gspec = L.gspec[pl.logn];
+  p.k = L.k; p.dbias = L.fbias; p.scratch = scratch; p.Lk = c->Lk;
+  p.B = B; p.D = c->cfg.d_model; p.T = T; p.Tp = Tp;
+  p.n_chunks = pl.n_chunks;
+  p.n_items = c->cfg.d_model * ((B + 1) / 2);
+  int grid = p.n_items;
+  if (pl.logn == LONGCONV_MAX_LOGN) grid = std::min(grid, c->num_sms);  // 1 CTA/SM (139 KB smem), persistent
+  else grid = std::min(grid, c->num_sms * 8);
+  if (pl.n_chunks > 1) {
+    const size_t needb = (size_t)grid * pl.n_chunks * ((size_t)1 << pl.logn) * sizeof(float2);
+    if (needb > scratch_bytes) return fail(c, CLM_ERR_STATE, "longconv: scratch too small (%zu < %zu); call clm_reserve with max_T >= %d", scratch_bytes, needb, T);
+  }
+  switch (pl.logn) {
+    case 8: return conv_t<8>(c, p, grid, st);
+    case 9: return conv_t<9>(c, p, grid, st);
+    case 10: return conv_t<10>(c, p, grid, st);
+    case 11: return conv_t<11>(c, p, grid, st);
+    case 12: return conv_t<12>(c, p, grid, st);
+    case 13: return conv_t<13>(c, p, grid, st);
+    case 14: return conv_t<14>(c, p, grid, st);
+  }
+  return fail(c, CLM_ERR_INVALID, "longconv: no plan for T=%d", T);
+}
+
+int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+}  // namespace
+
+// =============================================================================================
+extern "C" {
+
+void clm_default_config(clm_config* cfg) {
+  cfg->d_model = 256; cfg->n_layer = 4; cfg->d_inner = 1024; cfg->vocab_rows = 16; cfg->max_seq_len = 32770;
+  cfg->filter_order = 64; cfg->emb_dim = 5; cfg->short_filter_order = 3; cfg->num_inner_mlps = 2;
+  cfg->head_hidden = 512; cfg->num_classes = 2;
+  cfg->layer_norm_eps = 1e-5f; cfg->filter_shift = 0.05f;
+}
+
+const char* clm_version(void) { return "chimeralm_b200 0.1 (sm_100a)"; }
+
+const char* clm_last_error(const clm_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+long long clm_launch_count(const clm_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int clm_create(const clm_config* cfg, int device, clm_ctx** out) {
+  if (!cfg || !out) return CLM_ERR_INVALID;
+  *out = nullptr;
+  // The kernels are specialised for the named architecture; refuse anything else loudly.
+  if (cfg->d_model != 256 || cfg->d_inner != 1024 || cfg->head_hidden != 512 || cfg->num_classes != 2 ||
+      cfg->short_filter_order != 3 || cfg->filter_order > 64 || cfg->num_inner_mlps != 2 || cfg->n_layer < 1)
+    return CLM_ERR_INVALID;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return CLM_ERR_CUDA;
+  clm_ctx* c = new (std::nothrow) clm_ctx();
+  if (!c) return CLM_ERR_NOMEM;
+  c->cfg = *cfg;
+  c->device = device;
+  *out = c;
+  CLM_CUDA(c, cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CLM_CUDA(c, cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) return fail(c, CLM_ERR_CUDA, "device %d is sm_%d%d; this library contains sm_100a code only", device, prop.major, prop.minor);
+  c->num_sms = prop.multiProcessorCount;
+  cudaDriverEntryPointQueryResult qres;
+  void* fn = nullptr;
+  CLM_CUDA(c, cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+  if (!fn || qres != cudaDriverEntryPointSuccess) return fail(c, CLM_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+  c->encode_tiled = reinterpret_cast<EncodeTiledFn>(fn);
+  CLM_CUDA(c, cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+  uint8_t lut[256];
+  memset(lut, 6, sizeof lut);  // [UNK]
+  lut['A'] = 7; lut['C'] = 8; lut['G'] = 9; lut['T'] = 10; lut['N'] = 11;
+  CLM_CUDA(c, cudaMemcpyToSymbol(c_base_lut, lut, sizeof lut));
+  int rc = dev_alloc(c, &c->d_err, 1);
+  if (rc) return rc;
+  CLM_CUDA(c, cudaMemset(c->d_err, 0, sizeof(int)));
+  c->layers.resize(cfg->n_layer);
+  return 0;
+}
+
+void clm_destroy(clm_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaDeviceSynchronize();
+  for (void* p : c->owned)
+    if (p) cudaFree(p);
+  if (c->own_stream) cudaStreamDestroy(c->own_stream);
+  delete c;
+}
+
+int clm_load_tensor(clm_ctx* c, const char* name, const void* data, int dtype, const int64_t* shape, int ndim) {
+  if (!c || !name || !data || ndim < 0 || ndim > 8) return fail(c, CLM_ERR_INVALID, "clm_load_tensor: bad argument");
+  if (dtype != CLM_F32) return fail(c, CLM_ERR_INVALID, "clm_load_tensor('%s'): only float32 host tensors are accepted", name);
+  if (c->finalized) return fail(c, CLM_ERR_STATE, "clm_load_tensor after clm_finalize");
+  const std::string n(name);
+  if (n.rfind("net.", 0) != 0) return 1;  // not a model weight: ignored
+  CLM_CUDA(c, cudaSetDevice(c->device));
+  Tensor t;
+  t.numel = 1;
+  for (int i = 0; i < ndim; ++i) {
+    t.shape.push_back(shape[i]);
+    t.numel *= shape[i];
+  }
+  if (t.numel <= 0) return fail(c, CLM_ERR_INVALID, "clm_load_tensor('%s'): empty tensor", name);
+  int rc = dev_alloc(c, &t.d, (size_t)t.numel);
+  if (rc) return rc;
+  CLM_CUDA(c, cudaMemcpy(t.d, data, (size_t)t.numel * sizeof(float), cudaMemcpyHostToDevice));
+  c->w[n] = t;
+  return 0;
+}
+
+int clm_finalize(clm_ctx* c) {
+  if (!c) return CLM_ERR_INVALID;
+  if (c->finalized) return 0;
+  CLM_CUDA(c, cudaSetDevice(c->device));
+  const clm_config& g = c->cfg;
+  const int D = g.d_model, F = g.filter_order, E = g.emb_dim, Lmax = g.max_seq_len;
+  const std::string BB = "net.backbone.backbone.", HD = "net.head.";
+  int rc;
+#define NEED(name, numel, dst)                         \
+  if ((rc = need(c, name, numel, dst)) != 0) return rc
+  NEED(BB + "embeddings.word_embeddings.weight", (int64_t)g.vocab_rows * D, &c->emb);
+  NEED(BB + "ln_f.weight", D, &c->lnf_g);
+  NEED(BB + "ln_f.bias", D, &c->lnf_b);
+  c->Lk = round_up(Lmax, 64);
+  for (int l = 0; l < g.n_layer; ++l) {
+    LayerW& L = c->layers[l];
+    const std::string P = BB + "layers." + std::to_string(l) + ".";
+    const float *in_w, *out_w, *fc1_w, *fc2_w;
+    NEED(P + "norm1.weight", D, &L.ln1_g);
+    NEED(P + "norm1.bias", D, &L.ln1_b);
+    NEED(P + "norm2.weight", D, &L.ln2_g);
+    NEED(P + "norm2.bias", D, &L.ln2_b);
+    NEED(P + "mixer.in_proj.weight", 3LL * D * D, &in_w);
+    NEED(P + "mixer.in_proj.bias", 3LL * D, &L.in_b);
+    NEED(P + "mixer.out_proj.weight", (int64_t)D * D, &out_w);
+    NEED(P + "mixer.out_proj.bias", D, &L.out_b);
+    NEED(P + "mixer.short_filter.weight", 3LL * D * 3, &L.sc_w);
+    NEED(P + "mixer.short_filter.bias", 3LL * D, &L.sc_b);
+    NEED(P + "mixer.filter_fn.bias", D, &L.fbias);
+    NEED(P + "mlp.fc1.weight", (int64_t)g.d_inner * D, &fc1_w);
+    NEED(P + "mlp.fc1.bias", g.d_inner, &L.fc1_b);
+    NEED(P + "mlp.fc2.weight", (int64_t)g.d_inner * D, &fc2_w);
+    NEED(P + "mlp.fc2.bias", D, &L.fc2_b);
+    if ((rc = to_bf16(c, in_w, 3LL * D * D, &L.in_w))) return rc;
+    if ((rc = to_bf16(c, out_w, (int64_t)D * D, &L.out_w))) return rc;
+    if ((rc = to_bf16(c, fc1_w, (int64_t)g.d_inner * D, &L.fc1_w))) return rc;
+    if ((rc = to_bf16(c, fc2_w, (int64_t)g.d_inner * D, &L.fc2_w))) return rc;
+    if ((rc = make_tmap_bf16_2d(c, &L.tm_in, L.in_w, 3 * D, D, 128))) return rc;
+    if ((rc = make_tmap_bf16_2d(c, &L.tm_out, L.out_w, D, D, 128))) return rc;
+    if ((rc = make_tmap_bf16_2d(c, &L.tm_fc1, L.fc1_w, g.d_inner, D, 128))) return rc;
+    if ((rc = make_tmap_bf16_2d(c, &L.tm_fc2, L.fc2_w, D, g.d_inner, 128))) return rc;
+    // implicit filter k[l] = HyenaFilter.filter(Lmax)
+    FilterGenParams fp{};
+    const std::string Q = P + "mixer.filter_fn.";
+    NEED(Q + "pos_emb.z", (int64_t)Lmax * E, &fp.z);
+    NEED(Q + "pos_emb.t", Lmax, &fp.tpos);
+    NEED(Q + "implicit_filter.0.weight", (int64_t)F * E, &fp.w[0]);
+    NEED(Q + "implicit_filter.0.bias", F, &fp.b[0]);
+    NEED(Q + "implicit_filter.1.freq", F, &fp.freq[0]);
+    NEED(Q + "implicit_filter.2.weight", (int64_t)F * F, &fp.w[1]);
+    NEED(Q + "implicit_filter.2.bias", F, &fp.b[1]);
+    NEED(Q + "implicit_filter.3.freq", F, &fp.freq[1]);
+    NEED(Q + "implicit_filter.4.weight", (int64_t)F * F, &fp.w[2]);
+    NEED(Q + "implicit_filter.4.bias", F, &fp.b[2]);
+    NEED(Q + "implicit_filter.5.freq", F, &fp.freq[2]);
+    NEED(Q + "implicit_filter.6.weight", (int64_t)D * F, &fp.w[3]);
+    NEED(Q + "modulation.deltas", D, &fp.deltas);
+    fp.shift = g.filter_shift; fp.E = E; fp.F = F; fp.D = D; fp.L = Lmax; fp.Lk = c->Lk;
+    if ((rc = dev_alloc(c, &L.k, (size_t)D * c->Lk))) return rc;
+    CLM_CUDA(c, cudaMemset(L.k, 0, (size_t)D * c->Lk * sizeof(float)));
+    fp.k_out = L.k;
+    filter_gen_kernel<<<Lmax, 256>>>(fp);
+    CLM_LAUNCH_CHECK(c, "filter_gen");
+    if ((rc = spectrum_t<8>(c, L))) return rc;
+    if ((rc = spectrum_t<9>(c, L))) return rc;
+    if ((rc = spectrum_t<10>(c, L))) return rc;
+    if ((rc = spectrum_t<11>(c, L))) return rc;
+    if ((rc = spectrum_t<12>(c, L))) return rc;
+    if ((rc = spectrum_t<13>(c, L))) return rc;
+    if ((rc = spectrum_t<14>(c, L))) return rc;
+  }
+  // head
+  const float *a0w, *a2b;
+  NEED(HD + "attention.0.weight", (int64_t)D * D, &a0w);
+  NEED(HD + "attention.0.bias", D, &c->att0_b);
+  NEED(HD + "attention.2.weight", D, &c->att2_w);
+  NEED(HD + "attention.2.bias", 1, &a2b);
+  CLM_CUDA(c, cudaMemcpy(&c->att2_b, a2b, sizeof(float), cudaMemcpyDeviceToHost));
+  if ((rc = to_bf16(c, a0w, (int64_t)D * D, &c->att0_w))) return rc;
+  if ((rc = make_tmap_bf16_2d(c, &c->tm_att0, c->att0_w, D, D, 256))) return rc;
+  const int H = g.head_hidden;
+  NEED(HD + "classifier.0.weight", (int64_t)H * D, &c->head.w0);
+  NEED(HD + "classifier.0.bias", H, &c->head.b0);
+  NEED(HD + "classifier.3.weight", (int64_t)H * H, &c->head.w1);
+  NEED(HD + "classifier.3.bias", H, &c->head.b1);
+  NEED(HD + "classifier.6.layers.0.weight", (int64_t)H * H, &c->head.wr0);
+  NEED(HD + "classifier.6.layers.0.bias", H, &c->head.br0);
+  NEED(HD + "classifier.6.layers.3.weight", (int64_t)H * H, &c->head.wr1);
+  NEED(HD + "classifier.6.layers.3.bias", H, &c->head.br1);
+  NEED(HD + "output_layer.weight", 2LL * H, &c->head.wo);
+  NEED(HD + "output_layer.bias", 2, &c->head.bo);
+#undef NEED
+  CLM_CUDA(c, cudaDeviceSynchronize());
+  c->finalized = true;
+  return 0;
+}
+
+int clm_reserve(clm_ctx* c, int max_B, int max_T) {
+  if (!c || max_B <= 0 || max_T <= 0) return fail(c, CLM_ERR_INVALID, "clm_reserve: bad sizes");
+  if (max_T > c->cfg.max_seq_len) return fail(c, CLM_ERR_INVALID, "clm_reserve: max_T=%d exceeds max_seq_len=%d", max_T, c->cfg.max_seq_len);
+  CLM_CUDA(c, cudaSetDevice(c->device));
+  CLM_CUDA(c, cudaDeviceSynchronize());
+  void* olds[] = {c->R, c->XN, c->U, c->VX, c->X0, c->Y, c->YT, c->score, c->part, c->pooled, c->scratch,
+                  c->st_offsets, c->st_ids, c->st_logits, c->st_labels};
+  for (void* p : olds) dev_free(c, p);
+  const int D = c->cfg.d_model;
+  const size_t M = (size_t)max_B * max_T;
+  const int Tp = round_up(max_T, 64);
+  const size_t CT = (size_t)max_B * D * Tp;
+  int rc;
+  if ((rc = dev_alloc(c, &c->R, M * D))) return rc;
+  if ((rc = dev_alloc(c, &c->XN, M * D))) return rc;
+  if ((rc = dev_alloc(c, &c->U, M * (size_t)c->cfg.d_inner))) return rc;  // in_proj out (3D) and fc1 out (d_inner)
+  if ((rc = dev_alloc(c, &c->VX, CT))) return rc;
+  if ((rc = dev_alloc(c, &c->X0, CT))) return rc;
+  if ((rc = dev_alloc(c, &c->Y, CT))) return rc;
+  if ((rc = dev_alloc(c, &c->YT, M * D))) return rc;
+  if ((rc = dev_alloc(c, &c->score, M))) return rc;
+  c->n_split = std::max(1, std::min(64, (2 * c->num_sms + max_B - 1) / max_B));
+  if ((rc = dev_alloc(c, &c->part, (size_t)max_B * c->n_split * (2 + D)))) return rc;
+  if ((rc = dev_alloc(c, &c->pooled, (size_t)max_B * D))) return rc;
+  c->scratch_bytes = conv_scratch_bytes(c, max_T);
+  c->scratch = nullptr;
+  if (c->scratch_bytes) {
+    // any T <= max_T that takes the chunked path needs at most this much
+    const int C = 1 << (LONGCONV_MAX_LOGN - 1);
+    const size_t worst = (size_t)c->num_sms * ((max_T + C - 1) / C) * ((size_t)1 << LONGCONV_MAX_LOGN) * sizeof(float2);
+    c->scratch_bytes = std::max(c->scratch_bytes, worst);
+    if ((rc = dev_alloc(c, reinterpret_cast<uint8_t**>(&c->scratch), c->scratch_bytes))) return rc;
+  }
+  if ((rc = dev_alloc(c, &c->st_offsets, (size_t)max_B + 1))) return rc;
+  if ((rc = dev_alloc(c, &c->st_ids, M))) return rc;
+  if ((rc = dev_alloc(c, &c->st_logits, (size_t)max_B * 2))) return rc;
+  if ((rc = dev_alloc(c, &c->st_labels, (size_t)max_B))) return rc;
+  c->max_B = max_B; c->max_T = max_T; c->Tp_max = Tp;
+  return 0;
+}
+
+int clm_encode_batch(clm_ctx* c, const uint8_t* d_bases, const int64_t* d_offsets, int B, int T_pad, int add_cls,
+                     int add_sep, int pad_left, int max_bases, uint8_t* d_ids_out, int32_t* d_lens_out,
+                     void* stream) {
+  if (!c || !d_bases || !d_offsets || !d_ids_out || B <= 0 || T_pad <= 0 || max_bases < 0)
+    return fail(c, CLM_ERR_INVALID, "clm_encode_batch: bad argument");
+  EncodeParams p{d_bases, d_offsets, d_ids_out, d_lens_out, B, T_pad, add_cls ? 1 : 0, add_sep ? 1 : 0, pad_left ? 1 : 0, max_bases};
+  dim3 grid(std::min(64, (T_pad + 255) / 256), B);
+  encode_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p);
+  CLM_LAUNCH_CHECK(c, "encode");
+  return 0;
+}
+
+int clm_set_debug_stop(clm_ctx* c, int layer, int stage) {
+  if (!c) return CLM_ERR_INVALID;
+  c->dbg_layer = layer;
+  c->dbg_stage = stage;
+  return 0;
+}
+
+int clm_forward(clm_ctx* c, const void* d_ids, int ids_dtype, int B, int T, float* d_logits, uint8_t* d_labels,
+                void* stream) {
+  if (!c) return CLM_ERR_INVALID;
+  if (!c->finalized) return fail(c, CLM_ERR_STATE, "clm_forward before clm_finalize");
+  if (!d_ids || !d_logits || B <= 0 || T <= 0) return fail(c, CLM_ERR_INVALID, "clm_forward: bad argument");
+  if (B > c->max_B || T > c->max_T || (size_t)B * T > (size_t)c->max_B * c->max_T)
+    return fail(c, CLM_ERR_STATE, "clm_forward: batch %dx%d exceeds reserved %dx%d; call clm_reserve", B, T, c->max_B, c->max_T);
+  cudaStream_t st = (cudaStream_t)stream;
+  const clm_config& g = c->cfg;
+  const int D = g.d_model;
+  const long long M = (long long)B * T;
+  if (M > 0x7fffffffLL) return fail(c, CLM_ERR_INVALID, "clm_forward: B*T too large");
+  const int Tp = round_up(T, 64);
+  const unsigned rows8 = (unsigned)((M + 7) / 8);
+  int rc;
+#define STOP_AFTER(layer, stage) \
+  if (c->dbg_layer == (layer) && c->dbg_stage == (stage)) return 0
+
+  switch (ids_dtype) {
+    case CLM_U8: embed_kernel<uint8_t><<<rows8, 256, 0, st>>>((const uint8_t*)d_ids, c->emb, c->R, M, D, g.vocab_rows, c->d_err); break;
+    case CLM_I32: embed_kernel<int32_t><<<rows8, 256, 0, st>>>((const int32_t*)d_ids, c->emb, c->R, M, D, g.vocab_rows, c->d_err); break;
+    case CLM_I64: embed_kernel<int64_t><<<rows8, 256, 0, st>>>((const int64_t*)d_ids, c->emb, c->R, M, D, g.vocab_rows, c->d_err); break;
+    default: return fail(c, CLM_ERR_INVALID, "clm_forward: ids dtype %d not supported", ids_dtype);
+  }
+  CLM_LAUNCH_CHECK(c, "embed");
+  STOP_AFTER(0, 0);
+
+  for (int l = 0; l < g.n_layer; ++l) {
+    LayerW& L = c->layers[l];
+    layernorm_bf16_kernel<<<rows8, 256, 0, st>>>(c->R, L.ln1_g, L.ln1_b, c->XN, M, g.layer_norm_eps);
+    CLM_LAUNCH_CHECK(c, "ln1");
+    STOP_AFTER(l, 1);
+    GemmParams p{};
+    p.M = (int)M; p.N = 3 * D; p.K = D; p.bias = L.in_b; p.out = c->U; p.ldo = 3 * D;
+    if ((rc = launch_gemm(c, c->XN, L.tm_in, p, EPI_BIAS_BF16, st))) return rc;
+    STOP_AFTER(l, 2);
+    shortconv_gate_kernel<<<dim3((Tp + 63) / 64, D / 32, B), 256, 0, st>>>(c->U, L.sc_w, L.sc_b, c->VX, c->X0, T, Tp, D);
+    CLM_LAUNCH_CHECK(c, "shortconv_gate");
+    STOP_AFTER(l, 3);
+    if ((rc = launch_longconv(c, l, c->VX, c->X0, c->Y, B, T, Tp, c->scratch, c->scratch_bytes, st))) return rc;
+    STOP_AFTER(l, 4);
+    transpose_ct_kernel<<<dim3((T + 63) / 64, D / 64, B), 256, 0, st>>>(c->Y, c->YT, T, Tp, D);
+    CLM_LAUNCH_CHECK(c, "transpose_ct");
+    STOP_AFTER(l, 5);
+    p = GemmParams{};
+    p.M = (int)M; p.N = D; p.K = D; p.bias = L.out_b; p.out = c->R; p.res = c->R; p.ldo = D;
+    if ((rc = launch_gemm(c, c->YT, L.tm_out, p, EPI_BIAS_RES_F32, st))) return rc;
+    STOP_AFTER(l, 6);
+    layernorm_bf16_kernel<<<rows8, 256, 0, st>>>(c->R, L.ln2_g, L.ln2_b, c->XN, M, g.layer_norm_eps);
+    CLM_LAUNCH_CHECK(c, "ln2");
+    STOP_AFTER(l, 7);
+    p = GemmParams{};
+    p.M = (int)M; p.N = g.d_inner; p.K = D; p.bias = L.fc1_b; p.out = c->U; p.ldo = g.d_inner;
+    if ((rc = launch_gemm(c, c->XN, L.tm_fc1, p, EPI_BIAS_GELU_TANH, st))) return rc;
+    STOP_AFTER(l, 8);
+    p = GemmParams{};
+    p.M = (int)M; p.N = D; p.K = g.d_inner; p.bias = L.fc2_b; p.out = c->R; p.res = c->R; p.ldo = D;
+    if ((rc = launch_gemm(c, c->U, L.tm_fc2, p, EPI_BIAS_RES_F32, st))) return rc;
+    STOP_AFTER(l, 9);
+  }
+  const int NL = g.n_layer;
+  layernorm_bf16_kernel<<<rows8, 256, 0, st>>>(c->R, c->lnf_g, c->lnf_b, c->XN, M, g.layer_norm_eps);
+  CLM_LAUNCH_CHECK(c, "ln_f");
+  STOP_AFTER(NL, 10);
+  {
+    GemmParams p{};
+    p.M = (int)M; p.N = D; p.K = D; p.bias = c->att0_b; p.w2 = c->att2_w; p.b2 = c->att2_b; p.score = c->score; p.ldo = D;
+    if ((rc = launch_gemm(c, c->XN, c->tm_att0, p, EPI_SCORE, st))) return rc;
+  }
+  STOP_AFTER(NL, 11);
+  pool_partial_kernel<<<dim3(c->n_split, B), 256, 0, st>>>(c->R, c->score, c->lnf_g, c->lnf_b, c->part, T, c->n_split, g.layer_norm_eps);
+  CLM_LAUNCH_CHECK(c, "pool_partial");
+  STOP_AFTER(NL, 12);
+  HeadParams hp = c->head;
+  hp.part = c->part; hp.n_split = c->n_split; hp.logits = d_logits; hp.labels = d_labels; hp.pooled_out = c->pooled;
+  head_kernel<<<B, 512, 0, st>>>(hp);
+  CLM_LAUNCH_CHECK(c, "head");
+#undef STOP_AFTER
+  return 0;
+}
+
+int clm_predict_host(clm_ctx* c, const uint8_t* h_bases, const int64_t* h_offsets, int B, int T_pad, int add_cls,
+                     int add_sep, int pad_left, int max_bases, float* h_logits, uint8_t* h_labels) {
+  if (!c || !h_bases || !h_offsets || !h_logits || B <= 0) return fail(c, CLM_ERR_INVALID, "clm_predict_host: bad argument");
+  if (B > c->max_B || T_pad > c->max_T) return fail(c, CLM_ERR_STATE, "clm_predict_host: batch %dx%d exceeds reserved %dx%d", B, T_pad, c->max_B, c->max_T);
+  CLM_CUDA(c, cudaSetDevice(c->device));
+  const size_t nbytes = (size_t)h_offsets[B];
+  if (nbytes > c->st_bases_cap) {
+    dev_free(c, c->st_bases);
+    const size_t cap = std::max(nbytes, (size_t)c->max_B * c->max_T);
+    int rc = dev_alloc(c, &c->st_bases, cap);
+    if (rc) return rc;
+    c->st_bases_cap = cap;
+  }
+  cudaStream_t st = c->own_stream;
+  CLM_CUDA(c, cudaMemcpyAsync(c->st_bases, h_bases, nbytes, cudaMemcpyHostToDevice, st));
+  CLM_CUDA(c, cudaMemcpyAsync(c->st_offsets, h_offsets, (size_t)(B + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+  int rc = clm_encode_batch(c, c->st_bases, c->st_offsets, B, T_pad, add_cls, add_sep, pad_left, max_bases, c->st_ids, nullptr, st);
+  if (rc) return rc;
+  rc = clm_forward(c, c->st_ids, CLM_U8, B, T_pad, c->st_logits, c->st_labels, st);
+  if (rc) return rc;
+  CLM_CUDA(c, cudaMemcpyAsync(h_logits, c->st_logits, (size_t)B * 2 * sizeof(float), cudaMemcpyDeviceToHost, st));
+  if (h_labels) CLM_CUDA(c, cudaMemcpyAsync(h_labels, c->st_labels, (size_t)B, cudaMemcpyDeviceToHost, st));
+  CLM_CUDA(c, cudaStreamSynchronize(st));
+  return 0;
+}
+
+int clm_gemm(clm_ctx* c, const void* d_A, const void* d_W, const float* d_bias, int M, int N, int K, int epi,
+             void* d_out, const float* d_res, const float* d_w2, float b2, float* d_score, void* stream) {
+  if (!c || !d_A || !d_W || !d_bias) return fail(c, CLM_ERR_INVALID, "clm_gemm: bad argument");
+  CUtensorMap tmB;
+  int rc = make_tmap_bf16_2d(c, &tmB, d_W, (uint64_t)N, (uint64_t)K, epi == EPI_SCORE ? 256 : 128);
+  if (rc) return rc;
+  GemmParams p{};
+  p.M = M; p.N = N; p.K = K; p.bias = d_bias; p.out = d_out; p.res = d_res; p.w2 = d_w2; p.b2 = b2; p.score = d_score; p.ldo = N;
+  return launch_gemm(c, d_A, tmB, p, epi, (cudaStream_t)stream);
+}
+
+int clm_longconv(clm_ctx* c, int layer, const void* d_vx, const void* d_x0, void* d_out, int B, int T, int Tp,
+                 void* stream) {
+  if (!c || !c->finalized) return fail(c, CLM_ERR_STATE, "clm_longconv before clm_finalize");
+  if (layer < 0 || layer >= c->cfg.n_layer || B <= 0 || T <= 0 || Tp < T) return fail(c, CLM_ERR_INVALID, "clm_longconv: bad argument");
+  const size_t needb = conv_scratch_bytes(c, T);
+  if (needb > c->scratch_bytes) {
+    CLM_CUDA(c, cudaDeviceSynchronize());
+    dev_free(c, c->scratch);
+    int rc = dev_alloc(c, reinterpret_cast<uint8_t**>(&c->scratch), needb);
+    if (rc) return rc;
+    c->scratch_bytes = needb;
+  }
+  return launch_longconv(c, layer, (const __nv_bfloat16*)d_vx, (const __nv_bfloat16*)d_x0, (__nv_bfloat16*)d_out, B, T, Tp,
+                         c->scratch, c->scratch_bytes, (cudaStream_t)stream);
+}
+
+int clm_get_filter(clm_ctx* c, int layer, float* d_out, int L, void* stream) {
+  if (!c || !c->finalized) return fail(c, CLM_ERR_STATE, "clm_get_filter before clm_finalize");
+  if (layer < 0 || layer >= c->cfg.n_layer || L <= 0 || L > c->cfg.max_seq_len) return fail(c, CLM_ERR_INVALID, "clm_get_filter: bad argument");
+  CLM_CUDA(c, cudaMemcpy2DAsync(d_out, (size_t)L * sizeof(float), c->layers[layer].k, (size_t)c->Lk * sizeof(float),
+                                (size_t)L * sizeof(float), c->cfg.d_model, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return 0;
+}
+
+int clm_debug_copy(clm_ctx* c, const char* what, void* d_dst, size_t max_bytes, void* stream) {
+  if (!c || !what || !d_dst) return fail(c, CLM_ERR_INVALID, "clm_debug_copy: bad argument");
+  const size_t M = (size_t)c->max_B * c->max_T, D = c->cfg.d_model;
+  const size_t CT = (size_t)c->max_B * D * c->Tp_max;
+  const void* src = nullptr;
+  size_t bytes = 0;
+  const std::string w(what);
+  if (w == "resid") { src = c->R; bytes = M * D * 4; }
+  else if (w == "xn") { src = c->XN; bytes = M * D * 2; }
+  else if (w == "u") { src = c->U; bytes = M * c->cfg.d_inner * 2; }
+  else if (w == "vx") { src = c->VX; bytes = CT * 2; }
+  else if (w == "x0") { src = c->X0; bytes = CT * 2; }
+  else if (w == "y") { src = c->Y; bytes = CT * 2; }
+  else if (w == "yt") { src = c->YT; bytes = M * D * 2; }
+  else if (w == "score") { src = c->score; bytes = M * 4; }
+  else if (w == "pooled") { src = c->pooled; bytes = (size_t)c->max_B * D * 4; }
+  else return fail(c, CLM_ERR_INVALID, "clm_debug_copy: unknown buffer '%s'", what);
+  if (!src) return fail(c, CLM_ERR_STATE, "clm_debug_copy: workspaces not reserved");
+  CLM_CUDA(c, cudaMemcpyAsync(d_dst, src, std::min(bytes, max_bytes), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return 0;
+}
+
+}  // extern "C"

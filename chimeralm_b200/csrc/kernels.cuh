@@ -1,0 +1,305 @@
+// Bandwidth-bound kernels of the predict path: token encoding, embedding gather, LayerNorm,
+// depthwise short conv + first gate (with the token-major -> channel-major transpose the long
+// convolution wants), the inverse transpose, attention pooling and the classifier head.
+#pragma once
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+namespace clm {
+
+// ---------------------------------------------------------------------------------------------
+// Character tokenisation.  Reference: chimeralm/data/tokenizer.py:264-268 (char -> id, unknown
+// -> [UNK]=6), :297-306 ([CLS] + ids + [SEP]; Hub flavour ids + [SEP]), truncation keeps the
+// first bases, DataCollator pads with [PAD]=4 on `padding_side` (:152-159).
+__constant__ uint8_t c_base_lut[256];
+
+struct EncodeParams {
+  const uint8_t* bases;     // concatenated ASCII reads
+  const int64_t* offsets;   // [B+1]
+  uint8_t* ids;             // [B, T_pad]
+  int32_t* lens;            // [B] token count incl. specials (may be null)
+  int B, T_pad, add_cls, add_sep, pad_left, max_bases;
+};
+
+__global__ void __launch_bounds__(256) encode_kernel(EncodeParams p) {
+  const int b = blockIdx.y;
+  const int64_t beg = p.offsets[b];
+  int64_t nb = p.offsets[b + 1] - beg;
+  if (nb > p.max_bases) nb = p.max_bases;
+  const int ntok = (int)nb + p.add_cls + p.add_sep;
+  const int start = p.pad_left ? (p.T_pad - ntok) : 0;
+  if (blockIdx.x == 0 && threadIdx.x == 0 && p.lens) p.lens[b] = ntok;
+  uint8_t* row = p.ids + (int64_t)b * p.T_pad;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < p.T_pad; t += gridDim.x * blockDim.x) {
+    const int j = t - start;  // index inside the token sequence
+    uint8_t id = 4;           // [PAD]
+    if (j >= 0 && j < ntok) {
+      if (p.add_cls && j == 0) id = 0;
+      else if (p.add_sep && j == ntok - 1) id = 1;
+      else id = c_base_lut[p.bases[beg + j - p.add_cls]];
+    }
+    row[t] = id;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Embedding gather (HyenaEmbeddings.word_embeddings, A.2): one warp per token, fp32 residual out.
+template <typename IdT>
+__global__ void __launch_bounds__(256) embed_kernel(const IdT* __restrict__ ids, const float* __restrict__ E,
+                                                    float* __restrict__ R, long long M, int D, int vocab_rows,
+                                                    int* __restrict__ err) {
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= M) return;
+  long long id = (long long)ids[row];
+  if (id < 0 || id >= vocab_rows) {
+    if (lane == 0) atomicExch(err, 1);
+    id = 0;
+  }
+  const float4* src = reinterpret_cast<const float4*>(E + id * D);
+  float4* dst = reinterpret_cast<float4*>(R + row * D);
+  for (int i = lane; i < D / 4; i += 32) dst[i] = __ldg(src + i);
+}
+
+// ---------------------------------------------------------------------------------------------
+// LayerNorm over D=256 (eps inside rsqrt, biased variance, as torch.nn.LayerNorm): one warp per
+// row, fp32 in, bf16 out (GEMM operand).
+__global__ void __launch_bounds__(256) layernorm_bf16_kernel(const float* __restrict__ X, const float* __restrict__ g,
+                                                             const float* __restrict__ bta,
+                                                             __nv_bfloat16* __restrict__ Y, long long M, float eps) {
+  constexpr int D = 256;
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= M) return;
+  const float4* x4 = reinterpret_cast<const float4*>(X + row * D);
+  float4 a = x4[lane], b = x4[lane + 32];
+  float s = a.x + a.y + a.z + a.w + b.x + b.y + b.z + b.w;
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s * (1.0f / D);
+  float v[8] = {a.x - mean, a.y - mean, a.z - mean, a.w - mean, b.x - mean, b.y - mean, b.z - mean, b.w - mean};
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) ss += v[i] * v[i];
+  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  const float rstd = rsqrtf(ss * (1.0f / D) + eps);
+  const float4 g0 = __ldg(reinterpret_cast<const float4*>(g) + lane), g1 = __ldg(reinterpret_cast<const float4*>(g) + lane + 32);
+  const float4 b0 = __ldg(reinterpret_cast<const float4*>(bta) + lane), b1 = __ldg(reinterpret_cast<const float4*>(bta) + lane + 32);
+  __nv_bfloat162 o0 = __floats2bfloat162_rn(v[0] * rstd * g0.x + b0.x, v[1] * rstd * g0.y + b0.y);
+  __nv_bfloat162 o1 = __floats2bfloat162_rn(v[2] * rstd * g0.z + b0.z, v[3] * rstd * g0.w + b0.w);
+  __nv_bfloat162 o2 = __floats2bfloat162_rn(v[4] * rstd * g1.x + b1.x, v[5] * rstd * g1.y + b1.y);
+  __nv_bfloat162 o3 = __floats2bfloat162_rn(v[6] * rstd * g1.z + b1.z, v[7] * rstd * g1.w + b1.w);
+  uint2* y2 = reinterpret_cast<uint2*>(Y + row * D);
+  y2[lane] = make_uint2(*reinterpret_cast<uint32_t*>(&o0), *reinterpret_cast<uint32_t*>(&o1));
+  y2[lane + 32] = make_uint2(*reinterpret_cast<uint32_t*>(&o2), *reinterpret_cast<uint32_t*>(&o3));
+}
+
+// ---------------------------------------------------------------------------------------------
+// Depthwise causal short conv (k=3, Conv1d padding=2 truncated to T) + first gate, A.3:
+//   uc[ch,t] = w[ch,0] u[ch,t-2] + w[ch,1] u[ch,t-1] + w[ch,2] u[ch,t] + b[ch]   (u = 0 for t < 0)
+//   x0 = uc[0:D], x1 = uc[D:2D], v = uc[2D:3D];   vx = v * x1
+// Input U token-major bf16 [B*T, 3D]; outputs channel-major bf16 [B][D][Tp].
+// Block = 64 tokens x 32 channels (x3 groups), transposed through shared memory.
+__global__ void __launch_bounds__(256) shortconv_gate_kernel(const __nv_bfloat16* __restrict__ U,
+                                                             const float* __restrict__ w,   // [3D,3]
+                                                             const float* __restrict__ bias,  // [3D]
+                                                             __nv_bfloat16* __restrict__ VX,
+                                                             __nv_bfloat16* __restrict__ X0, int T, int Tp, int D) {
+  constexpr int TT = 64, TC = 32;
+  __shared__ float su[3][TT + 2][TC + 1];
+  const int b = blockIdx.z, t0 = blockIdx.x * TT, c0 = blockIdx.y * TC;
+  const int tid = threadIdx.x;
+  const long long rowbase = (long long)b * T;
+  // load: (TT+2) tokens x 3 groups x TC channels, 2 channels (one bf16x2) per thread-iteration
+  for (int i = tid; i < (TT + 2) * 3 * (TC / 2); i += 256) {
+    const int cp = i % (TC / 2);
+    const int g = (i / (TC / 2)) % 3;
+    const int tt = i / (3 * TC / 2);
+    const int t = t0 - 2 + tt;
+    float2 f = make_float2(0.f, 0.f);
+    if (t >= 0 && t < T) {
+      const __nv_bfloat162 v =
+          *reinterpret_cast<const __nv_bfloat162*>(U + (rowbase + t) * (3LL * D) + g * D + c0 + 2 * cp);
+      f = __bfloat1622float2(v);
+    }
+    su[g][tt][2 * cp] = f.x;
+    su[g][tt][2 * cp + 1] = f.y;
+  }
+  __syncthreads();
+  // compute + transposed store: thread handles channel cl, tokens (tl, tl+1)
+  for (int i = tid; i < TC * (TT / 2); i += 256) {
+    const int tl = (i % (TT / 2)) * 2;
+    const int cl = i / (TT / 2);
+    const int c = c0 + cl;
+    float uc[3][2];
+#pragma unroll
+    for (int g = 0; g < 3; ++g) {
+      const int ch = g * D + c;
+      const float w0 = __ldg(w + ch * 3), w1 = __ldg(w + ch * 3 + 1), w2 = __ldg(w + ch * 3 + 2), bb = __ldg(bias + ch);
+#pragma unroll
+      for (int k = 0; k < 2; ++k)
+        uc[g][k] = w0 * su[g][tl + k][cl] + w1 * su[g][tl + k + 1][cl] + w2 * su[g][tl + k + 2][cl] + bb;
+    }
+    const int t = t0 + tl;
+    if (t < Tp) {
+      const long long o = ((long long)b * D + c) * Tp + t;
+      const float vx0 = (t < T) ? uc[2][0] * uc[1][0] : 0.f, vx1 = (t + 1 < T) ? uc[2][1] * uc[1][1] : 0.f;
+      const float x00 = (t < T) ? uc[0][0] : 0.f, x01 = (t + 1 < T) ? uc[0][1] : 0.f;
+      *reinterpret_cast<__nv_bfloat162*>(VX + o) = __floats2bfloat162_rn(vx0, vx1);
+      *reinterpret_cast<__nv_bfloat162*>(X0 + o) = __floats2bfloat162_rn(x00, x01);
+    }
+  }
+}
+
+// Channel-major bf16 [B][D][Tp] -> token-major bf16 [B*T, D] (out_proj's A operand).
+__global__ void __launch_bounds__(256) transpose_ct_kernel(const __nv_bfloat16* __restrict__ Y,
+                                                           __nv_bfloat16* __restrict__ YT, int T, int Tp, int D) {
+  constexpr int TT = 64, TC = 64;
+  __shared__ __nv_bfloat16 s[TC][TT + 2];
+  const int b = blockIdx.z, t0 = blockIdx.x * TT, c0 = blockIdx.y * TC;
+  const int tid = threadIdx.x;
+  for (int i = tid; i < TC * TT; i += 256) {
+    const int tl = i % TT, cl = i / TT;
+    const int t = t0 + tl;
+    s[cl][tl] = (t < T) ? Y[((long long)b * D + c0 + cl) * Tp + t] : __float2bfloat16(0.f);
+  }
+  __syncthreads();
+  for (int i = tid; i < TT * TC; i += 256) {
+    const int cl = i % TC, tl = i / TC;
+    const int t = t0 + tl;
+    if (t < T) YT[((long long)b * T + t) * D + c0 + cl] = s[cl][tl];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Attention pooling (chimeralm/models/components/hyena.py:117-132, mask == None):
+//   w = softmax_t(score[b,:]) over ALL T positions;  pooled[b,:] = sum_t w_t * ln_f(R[b,t,:])
+// Split over the sequence: each block reduces a slice with a running max (online softmax) and
+// writes (max, sum, acc[D]); the head kernel merges slices.  ln_f is recomputed from the fp32
+// residual so the pooled features never pass through bf16.
+__global__ void __launch_bounds__(256) pool_partial_kernel(const float* __restrict__ R, const float* __restrict__ score,
+                                                           const float* __restrict__ g, const float* __restrict__ bta,
+                                                           float* __restrict__ part,  // [B][S][2+D]
+                                                           int T, int n_split, float eps) {
+  constexpr int D = 256;
+  __shared__ float sm_m[8], sm_l[8];
+  __shared__ float sm_acc[8][D];
+  const int b = blockIdx.y, sp = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int per = (T + n_split - 1) / n_split;
+  const int tb = sp * per, te = min(T, tb + per);
+  const float4 g0 = __ldg(reinterpret_cast<const float4*>(g) + lane), g1 = __ldg(reinterpret_cast<const float4*>(g) + lane + 32);
+  const float4 b0 = __ldg(reinterpret_cast<const float4*>(bta) + lane), b1 = __ldg(reinterpret_cast<const float4*>(bta) + lane + 32);
+  float m = -INFINITY, l = 0.f;
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int t = tb + warp; t < te; t += 8) {
+    const long long row = (long long)b * T + t;
+    const float4* x4 = reinterpret_cast<const float4*>(R + row * D);
+    float4 a = x4[lane], c = x4[lane + 32];
+    float s = a.x + a.y + a.z + a.w + c.x + c.y + c.z + c.w;
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s * (1.0f / D);
+    float v[8] = {a.x - mean, a.y - mean, a.z - mean, a.w - mean, c.x - mean, c.y - mean, c.z - mean, c.w - mean};
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) ss += v[i] * v[i];
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    const float rstd = rsqrtf(ss * (1.0f / D) + eps);
+    const float sc = score[row];
+    const float mn = fmaxf(m, sc);
+    const float corr = __expf(m - mn);  // exp(-inf) = 0 on the first step
+    const float pw = __expf(sc - mn);
+    l = l * corr + pw;
+    const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = acc[i] * corr + pw * (v[i] * rstd * gg[i] + bb[i]);
+    m = mn;
+  }
+  if (lane == 0) { sm_m[warp] = m; sm_l[warp] = l; }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { sm_acc[warp][lane * 4 + i] = acc[i]; sm_acc[warp][128 + lane * 4 + i] = acc[4 + i]; }
+  __syncthreads();
+  float M = -INFINITY;
+  for (int w = 0; w < 8; ++w) M = fmaxf(M, sm_m[w]);
+  float* out = part + ((long long)b * n_split + sp) * (2 + D);
+  const int d = threadIdx.x;  // 256 threads == D
+  float a = 0.f, L = 0.f;
+  for (int w = 0; w < 8; ++w) {
+    const float f = (sm_m[w] == -INFINITY) ? 0.f : __expf(sm_m[w] - M);
+    a += sm_acc[w][d] * f;
+    L += sm_l[w] * f;
+  }
+  out[2 + d] = a;
+  if (d == 0) { out[0] = M; out[1] = L; }
+}
+
+// Classifier head (components/hyena.py:55-74,142-146,149-180): merge pooling slices, then
+//   Lin(256,512) GELU Lin(512,512) GELU [Lin(512,512) GELU Lin(512,512)] + skip, Lin(512,2);
+//   label = argmax(logits) with ties -> 0 (chimeralm/models/callbacks.py:107).  One block per read.
+struct HeadParams {
+  const float* part; int n_split;
+  const float *w0, *b0, *w1, *b1, *wr0, *br0, *wr1, *br1, *wo, *bo;
+  float* logits;      // [B,2]
+  uint8_t* labels;    // [B] (may be null)
+  float* pooled_out;  // [B,256] (may be null; debug / attention export)
+};
+
+__device__ __forceinline__ float gelu_erf_h(float x) { return 0.5f * x * (1.0f + erff(x * 0.7071067811865476f)); }
+
+// y[o] = act(b[o] + sum_i W[o,i] x[i]) for o in [0,OUT): one warp per output row, coalesced W reads.
+template <int IN, int OUT, bool GELU>
+__device__ __forceinline__ void head_linear(const float* __restrict__ W, const float* __restrict__ bias,
+                                            const float* x, float* y) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (int o = warp; o < OUT; o += nw) {
+    const float* wr = W + (long long)o * IN;
+    float a = 0.f;
+    for (int i = lane; i < IN; i += 32) a += __ldg(wr + i) * x[i];
+    for (int s = 16; s > 0; s >>= 1) a += __shfl_xor_sync(0xffffffffu, a, s);
+    if (lane == 0) {
+      a += bias[o];
+      y[o] = GELU ? gelu_erf_h(a) : a;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(512) head_kernel(HeadParams p) {
+  constexpr int D = 256, H = 512;
+  __shared__ float pooled[D], h1[H], h2[H], h3[H];
+  __shared__ float s_lg[2];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const float* part = p.part + (long long)b * p.n_split * (2 + D);
+  float M = -INFINITY;
+  for (int s = 0; s < p.n_split; ++s) M = fmaxf(M, part[s * (2 + D)]);
+  if (tid < D) {
+    float a = 0.f, L = 0.f;
+    for (int s = 0; s < p.n_split; ++s) {
+      const float ms = part[s * (2 + D)];
+      const float f = (ms == -INFINITY) ? 0.f : __expf(ms - M);
+      a += part[s * (2 + D) + 2 + tid] * f;
+      L += part[s * (2 + D) + 1] * f;
+    }
+    pooled[tid] = a / L;
+    if (p.pooled_out) p.pooled_out[(long long)b * D + tid] = a / L;
+  }
+  __syncthreads();
+  head_linear<D, H, true>(p.w0, p.b0, pooled, h1);
+  __syncthreads();
+  head_linear<H, H, true>(p.w1, p.b1, h1, h2);
+  __syncthreads();
+  head_linear<H, H, true>(p.wr0, p.br0, h2, h3);
+  __syncthreads();
+  head_linear<H, H, false>(p.wr1, p.br1, h3, h1);
+  __syncthreads();
+  for (int i = tid; i < H; i += blockDim.x) h1[i] += h2[i];
+  __syncthreads();
+  head_linear<H, 2, false>(p.wo, p.bo, h1, s_lg);
+  __syncthreads();
+  if (tid == 0) {
+    p.logits[b * 2 + 0] = s_lg[0];
+    p.logits[b * 2 + 1] = s_lg[1];
+    if (p.labels) p.labels[b] = (s_lg[1] > s_lg[0]) ? 1 : 0;
+  }
+}
+
+}  // namespace clm

@@ -1,0 +1,198 @@
+"""Python handle on one native context (one per GPU).
+
+PyTorch is used here only for device memory, streams and tensors handed to the C-ABI as raw
+pointers; every computation happens in the CUDA library.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from .config import DEFAULT_CONFIG, HyenaConfig
+
+_IDS_DTYPES = {torch.uint8: _lib.CLM_U8, torch.int32: _lib.CLM_I32, torch.int64: _lib.CLM_I64}
+
+
+def _stream_ptr(device) -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+class Engine:
+    """Owns a `clm_ctx`: weights, filter tables, workspaces (include/chimeralm_b200.h)."""
+
+    def __init__(self, state_dict, device: int | str | torch.device = 0, cfg: HyenaConfig = DEFAULT_CONFIG,
+                 max_batch: int = 32, max_tokens: int = 8193):
+        self.lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise _lib.ChimeraLMNativeError("no CUDA device: chimeralm_b200 has no CPU path")
+        self.device = torch.device("cuda", device) if isinstance(device, int) else torch.device(device)
+        self.cfg = cfg
+        torch.cuda.set_device(self.device)
+        torch.zeros(1, device=self.device)  # make sure the primary context exists
+        ccfg = _lib.clm_config()
+        self.lib.clm_default_config(C.byref(ccfg))
+        ccfg.d_model, ccfg.n_layer, ccfg.d_inner = cfg.d_model, cfg.n_layer, cfg.d_inner
+        ccfg.vocab_rows, ccfg.max_seq_len = cfg.vocab_rows, cfg.max_seq_len
+        ccfg.filter_order, ccfg.emb_dim = cfg.filter_order, cfg.emb_dim
+        ccfg.short_filter_order, ccfg.num_inner_mlps = cfg.short_filter_order, cfg.num_inner_mlps
+        ccfg.head_hidden, ccfg.num_classes = cfg.head_hidden, cfg.num_classes
+        ccfg.layer_norm_eps, ccfg.filter_shift = cfg.layer_norm_epsilon, cfg.shift
+        self.ctx = C.c_void_p()
+        rc = self.lib.clm_create(C.byref(ccfg), self.device.index or 0, C.byref(self.ctx))
+        if rc < 0:
+            msg = self.lib.clm_last_error(self.ctx).decode() if self.ctx else "clm_create rejected the configuration"
+            raise _lib.ChimeraLMNativeError(f"clm_create failed (status {rc}): {msg}")
+        self.load_state_dict(state_dict)
+        self._check(self.lib.clm_finalize(self.ctx), "clm_finalize")
+        self.max_batch = self.max_tokens = 0
+        self.reserve(max_batch, max_tokens)
+
+    # ------------------------------------------------------------------ plumbing
+    def _check(self, rc, what):
+        _lib.check(self.ctx, rc, what)
+
+    def close(self):
+        if getattr(self, "ctx", None):
+            self.lib.clm_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def load_state_dict(self, sd) -> None:
+        for name, t in sd.items():
+            if not name.startswith("net."):
+                name = "net." + name
+            a = t.detach().to(torch.float32).cpu().contiguous().numpy()
+            shape = (C.c_int64 * max(a.ndim, 1))(*a.shape) if a.ndim else (C.c_int64 * 1)(1)
+            rc = self.lib.clm_load_tensor(self.ctx, name.encode(), a.ctypes.data_as(C.c_void_p), _lib.CLM_F32,
+                                          shape, a.ndim)
+            self._check(rc, f"clm_load_tensor({name})")
+
+    def reserve(self, max_batch: int, max_tokens: int) -> None:
+        if max_batch <= self.max_batch and max_tokens <= self.max_tokens:
+            return
+        max_batch, max_tokens = max(max_batch, self.max_batch), max(max_tokens, self.max_tokens)
+        self._check(self.lib.clm_reserve(self.ctx, max_batch, max_tokens), "clm_reserve")
+        self.max_batch, self.max_tokens = max_batch, max_tokens
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.clm_launch_count(self.ctx))
+
+    # ------------------------------------------------------------------ hot path
+    def forward(self, input_ids: torch.Tensor, return_labels: bool = False):
+        """ClassificationLit.forward: int ids [B,T] on this device -> float32 logits [B,2]."""
+        if input_ids.dim() != 2:
+            raise ValueError("input_ids must be [B, T]")
+        if input_ids.dtype not in _IDS_DTYPES:
+            raise TypeError(f"input_ids dtype {input_ids.dtype} not supported (uint8/int32/int64)")
+        ids = input_ids.to(self.device).contiguous()
+        B, T = ids.shape
+        self.reserve(B, T)
+        logits = torch.empty(B, 2, dtype=torch.float32, device=self.device)
+        labels = torch.empty(B, dtype=torch.uint8, device=self.device)
+        rc = self.lib.clm_forward(self.ctx, C.c_void_p(ids.data_ptr()), _IDS_DTYPES[ids.dtype], B, T,
+                                  C.c_void_p(logits.data_ptr()), C.c_void_p(labels.data_ptr()),
+                                  _stream_ptr(self.device))
+        self._check(rc, "clm_forward")
+        return (logits, labels) if return_labels else logits
+
+    def encode(self, bases: torch.Tensor, offsets: torch.Tensor, T_pad: int, *, add_cls: bool, add_sep: bool,
+               pad_left: bool, max_bases: int):
+        """Device tokenisation + padding: uint8 ASCII bases, int64 offsets[B+1] -> uint8 ids [B,T_pad], int32 lens."""
+        B = offsets.numel() - 1
+        bases = bases.to(self.device, torch.uint8).contiguous()
+        offsets = offsets.to(self.device, torch.int64).contiguous()
+        if bases.numel() == 0:
+            bases = torch.zeros(1, dtype=torch.uint8, device=self.device)
+        ids = torch.empty(B, T_pad, dtype=torch.uint8, device=self.device)
+        lens = torch.empty(B, dtype=torch.int32, device=self.device)
+        rc = self.lib.clm_encode_batch(self.ctx, C.c_void_p(bases.data_ptr()), C.c_void_p(offsets.data_ptr()), B, T_pad,
+                                       int(add_cls), int(add_sep), int(pad_left), int(max_bases),
+                                       C.c_void_p(ids.data_ptr()), C.c_void_p(lens.data_ptr()), _stream_ptr(self.device))
+        self._check(rc, "clm_encode_batch")
+        return ids, lens
+
+    def predict_host(self, bases: torch.Tensor, offsets: torch.Tensor, T_pad: int, *, add_cls: bool, add_sep: bool,
+                     pad_left: bool, max_bases: int, logits_out: torch.Tensor | None = None,
+                     labels_out: torch.Tensor | None = None):
+        """End-to-end with HOST tensors (pinned recommended): H2D, encode, forward, D2H, sync."""
+        B = offsets.numel() - 1
+        self.reserve(B, T_pad)
+        if logits_out is None:
+            logits_out = torch.empty(B, 2, dtype=torch.float32).pin_memory()
+        if labels_out is None:
+            labels_out = torch.empty(B, dtype=torch.uint8).pin_memory()
+        rc = self.lib.clm_predict_host(self.ctx, C.c_void_p(bases.data_ptr()), C.c_void_p(offsets.data_ptr()), B, T_pad,
+                                       int(add_cls), int(add_sep), int(pad_left), int(max_bases),
+                                       C.c_void_p(logits_out.data_ptr()), C.c_void_p(labels_out.data_ptr()))
+        self._check(rc, "clm_predict_host")
+        return logits_out, labels_out
+
+    # ------------------------------------------------------------------ unit-level access (tests)
+    def gemm(self, A, W, bias, epi, res=None, w2=None, b2=0.0):
+        M, K = A.shape
+        N = W.shape[0]
+        st = _stream_ptr(self.device)
+        null = C.c_void_p(0)
+        if epi == _lib.EPI_SCORE:
+            score = torch.empty(M, dtype=torch.float32, device=self.device)
+            rc = self.lib.clm_gemm(self.ctx, C.c_void_p(A.data_ptr()), C.c_void_p(W.data_ptr()), C.c_void_p(bias.data_ptr()),
+                                   M, N, K, epi, null, null, C.c_void_p(w2.data_ptr()), float(b2),
+                                   C.c_void_p(score.data_ptr()), st)
+            self._check(rc, "clm_gemm")
+            return score
+        if epi == _lib.EPI_BIAS_RES_F32:
+            out = torch.empty(M, N, dtype=torch.float32, device=self.device)
+            rc = self.lib.clm_gemm(self.ctx, C.c_void_p(A.data_ptr()), C.c_void_p(W.data_ptr()), C.c_void_p(bias.data_ptr()),
+                                   M, N, K, epi, C.c_void_p(out.data_ptr()), C.c_void_p(res.data_ptr()), null, 0.0, null, st)
+        else:
+            out = torch.empty(M, N, dtype=torch.bfloat16, device=self.device)
+            rc = self.lib.clm_gemm(self.ctx, C.c_void_p(A.data_ptr()), C.c_void_p(W.data_ptr()), C.c_void_p(bias.data_ptr()),
+                                   M, N, K, epi, C.c_void_p(out.data_ptr()), null, null, 0.0, null, st)
+        self._check(rc, "clm_gemm")
+        return out
+
+    def longconv(self, layer: int, vx: torch.Tensor, x0: torch.Tensor, T: int):
+        B, D, Tp = vx.shape
+        out = torch.zeros_like(vx)
+        rc = self.lib.clm_longconv(self.ctx, layer, C.c_void_p(vx.data_ptr()), C.c_void_p(x0.data_ptr()),
+                                   C.c_void_p(out.data_ptr()), B, T, Tp, _stream_ptr(self.device))
+        self._check(rc, "clm_longconv")
+        return out
+
+    def get_filter(self, layer: int, L: int) -> torch.Tensor:
+        out = torch.empty(self.cfg.d_model, L, dtype=torch.float32, device=self.device)
+        self._check(self.lib.clm_get_filter(self.ctx, layer, C.c_void_p(out.data_ptr()), L, _stream_ptr(self.device)),
+                    "clm_get_filter")
+        return out
+
+    def set_debug_stop(self, layer: int = -1, stage: int = -1) -> None:
+        self._check(self.lib.clm_set_debug_stop(self.ctx, layer, stage), "clm_set_debug_stop")
+
+    def debug_copy(self, what: str, shape, dtype) -> torch.Tensor:
+        out = torch.empty(shape, dtype=dtype, device=self.device)
+        rc = self.lib.clm_debug_copy(self.ctx, what.encode(), C.c_void_p(out.data_ptr()), out.numel() * out.element_size(),
+                                     _stream_ptr(self.device))
+        self._check(rc, "clm_debug_copy")
+        return out
+
+
+def pack_reads(seqs: list[str] | list[bytes], pinned: bool = False):
+    """Concatenate reads into one uint8 buffer + int64 offsets (the C-ABI's input layout)."""
+    bs = [s.encode("ascii", "replace") if isinstance(s, str) else bytes(s) for s in seqs]
+    offsets = np.zeros(len(bs) + 1, dtype=np.int64)
+    np.cumsum([len(b) for b in bs], out=offsets[1:])
+    flat = np.frombuffer(b"".join(bs), dtype=np.uint8).copy() if offsets[-1] else np.zeros(1, dtype=np.uint8)
+    tb, to = torch.from_numpy(flat), torch.from_numpy(offsets)
+    if pinned:
+        tb, to = tb.pin_memory(), to.pin_memory()
+    return tb, to

@@ -1,0 +1,118 @@
+/* chimeralm_b200 — C ABI of the B200-native `chimeralm predict` hot path.
+ *
+ * Plain C, no torch types: pointers, sizes and an opaque context.  One context per device;
+ * calls on a context are serialised by the caller and are asynchronous on the given CUDA
+ * stream unless stated otherwise.  Every function returns 0 on success or a negative
+ * clm_status; clm_last_error() gives the message.  No C++ exception crosses this boundary and
+ * the library never calls exit().
+ *
+ * Each entry point names the reference interface it replaces (paths relative to the
+ * ylab-hi/ChimeraLM tree).  INTEGRATION.md shows the ctypes binding a maintainer would add.
+ */
+#ifndef CHIMERALM_B200_H_
+#define CHIMERALM_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct clm_ctx clm_ctx;
+
+typedef enum {
+  CLM_OK = 0,
+  CLM_ERR_INVALID = -1,   /* bad argument / shape */
+  CLM_ERR_CUDA = -2,      /* CUDA runtime or driver error (message has the detail) */
+  CLM_ERR_STATE = -3,     /* call order violated (e.g. forward before finalize) */
+  CLM_ERR_MISSING = -4,   /* a required weight tensor was never loaded */
+  CLM_ERR_NOMEM = -5
+} clm_status;
+
+typedef enum { CLM_F32 = 0, CLM_BF16 = 1, CLM_U8 = 2, CLM_I32 = 3, CLM_I64 = 4 } clm_dtype;
+
+/* Architecture constants; defaults = LongSafari/hyenadna-small-32k-seqlen-hf config.json +
+ * chimeralm/models/lm.py:46-55 (head).  clm_default_config() fills them in. */
+typedef struct {
+  int d_model, n_layer, d_inner, vocab_rows, max_seq_len;
+  int filter_order, emb_dim, short_filter_order, num_inner_mlps;
+  int head_hidden, num_classes;
+  float layer_norm_eps, filter_shift;
+} clm_config;
+
+void clm_default_config(clm_config* cfg);
+const char* clm_version(void);
+
+/* Lifetime.  Replaces model construction: ChimeraLM.new()/from_pretrained()
+ * (chimeralm/models/lm.py:12-61) + Lightning's module-to-device move. */
+int clm_create(const clm_config* cfg, int device, clm_ctx** out);
+void clm_destroy(clm_ctx* ctx);
+const char* clm_last_error(const clm_ctx* ctx);
+
+/* Weights.  `name` is the reference state-dict key (e.g.
+ * "net.backbone.backbone.layers.0.mixer.in_proj.weight", "net.head.output_layer.bias";
+ * layout probed from ClassificationLit(net=HyenaDna(...)), chimeralm/models/basic_module.py:39).
+ * `data` is a HOST pointer, copied; the caller keeps ownership.  Unknown names are ignored
+ * (returns 1) so a whole checkpoint can be streamed in.  Replaces load_state_dict /
+ * trainer.predict(ckpt_path=...) (chimeralm/__main__.py:317). */
+int clm_load_tensor(clm_ctx* ctx, const char* name, const void* data, int dtype, const int64_t* shape, int ndim);
+/* Converts GEMM weights to bf16, generates the implicit long filters for all layers
+ * (HyenaFilter.filter, recomputed on every forward in the reference) and their spectra. */
+int clm_finalize(clm_ctx* ctx);
+/* Sizes the activation workspaces for batches up to max_B reads of max_T tokens.  No
+ * allocation happens inside clm_forward. */
+int clm_reserve(clm_ctx* ctx, int max_B, int max_T);
+
+/* Tokenisation + collation on the device.  Replaces tokenizer(seq, truncation=True,
+ * max_length=...) (chimeralm/data/tokenizer.py:97, CharacterTokenizer :264-306) and
+ * DataCollator.torch_call's padding (:152-159).
+ *   d_bases   : device, concatenated ASCII bases of B reads
+ *   d_offsets : device, int64[B+1] start offsets into d_bases
+ *   max_bases : truncation (first max_bases bases are kept)
+ *   d_ids_out : device, uint8[B, T_pad]; T_pad >= min(len,max_bases)+add_cls+add_sep for all reads
+ *   d_lens_out: device, int32[B] token counts incl. specials (may be NULL) */
+int clm_encode_batch(clm_ctx* ctx, const uint8_t* d_bases, const int64_t* d_offsets, int B, int T_pad, int add_cls,
+                     int add_sep, int pad_left, int max_bases, uint8_t* d_ids_out, int32_t* d_lens_out,
+                     void* stream);
+
+/* The model forward.  Replaces ClassificationLit.forward / predict_step
+ * (chimeralm/models/basic_module.py:67-77,177-187) = HyenaDna.forward
+ * (chimeralm/models/components/hyena.py:244-256) and PredictionWriter's argmax
+ * (chimeralm/models/callbacks.py:107).
+ *   d_ids    : device, [B, T] token ids of dtype ids_dtype (CLM_U8, CLM_I32 or CLM_I64)
+ *   d_logits : device, float32[B, 2]
+ *   d_labels : device, uint8[B] = argmax(logits) with ties -> 0 (may be NULL) */
+int clm_forward(clm_ctx* ctx, const void* d_ids, int ids_dtype, int B, int T, float* d_logits, uint8_t* d_labels,
+                void* stream);
+
+/* End-to-end convenience with HOST buffers (pinned recommended): H2D copy of bases/offsets,
+ * encode, forward, D2H copy of logits/labels, stream synchronise.  This is what bench.py's
+ * `e2e` figure and the Python predict loop time. */
+int clm_predict_host(clm_ctx* ctx, const uint8_t* h_bases, const int64_t* h_offsets, int B, int T_pad, int add_cls,
+                     int add_sep, int pad_left, int max_bases, float* h_logits, uint8_t* h_labels);
+
+/* Number of kernel launches issued by this context since creation (bench.py's gpu_launches). */
+long long clm_launch_count(const clm_ctx* ctx);
+
+/* ---- unit-level entry points (parity tests call the kernels one by one through these) ---- */
+/* out = epilogue(A[M,K] (bf16) * W[N,K]^T (bf16)); epi: 0 bias->bf16, 1 bias+gelu_tanh->bf16,
+ * 2 bias+res->f32, 3 scorer (score[m] = sum_n gelu_erf(.)*w2[n] + b2, needs N == 256). */
+int clm_gemm(clm_ctx* ctx, const void* d_A, const void* d_W, const float* d_bias, int M, int N, int K, int epi,
+             void* d_out, const float* d_res, const float* d_w2, float b2, float* d_score, void* stream);
+/* out = (causal_long_conv(vx, k_layer) + bias_layer * vx) * x0 on channel-major bf16 [B][D][Tp]. */
+int clm_longconv(clm_ctx* ctx, int layer, const void* d_vx, const void* d_x0, void* d_out, int B, int T, int Tp,
+                 void* stream);
+/* Copies the generated time-domain filter k[layer][:, :L] (float32 [D, L]) to a device buffer. */
+int clm_get_filter(clm_ctx* ctx, int layer, float* d_out, int L, void* stream);
+/* Forward stops after (layer, stage); layer == n_layer addresses the final stages; -1 disables.
+ * Stages: 0 embed | per layer 1 ln1 2 in_proj 3 shortconv+gate 4 longconv 5 transpose 6 out_proj
+ * 7 ln2 8 fc1 9 fc2 | final 10 ln_f 11 scores 12 pooling 13 head. */
+int clm_set_debug_stop(clm_ctx* ctx, int layer, int stage);
+/* Copies a named workspace ("resid","xn","u","vx","x0","y","yt","score","pooled") to d_dst. */
+int clm_debug_copy(clm_ctx* ctx, const char* what, void* d_dst, size_t max_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CHIMERALM_B200_H_ */

@@ -1,0 +1,82 @@
+"""End-to-end parity of the CUDA forward against the CPU oracle (-m gpu), stage by stage and on
+final logits, on identical padded input_ids and identical seeded weights.
+
+Tolerances: bf16 GEMM operands / bf16 inter-kernel activations with fp32 accumulation, fp32
+residual stream, fp32 FFT and fp32 pooling/head.  Residual stream |err| <= 5e-2 (values ~ N(0,1)
+scaled by the block outputs), logits |err| <= 5e-3 (north_star: "stated bf16 tolerance";
+SURVEY.md 8(d) allows up to 2e-2), labels must agree wherever |oracle margin| > 2 * 5e-3."""
+
+import pytest
+import torch
+
+from chimeralm_b200.config import DEFAULT_CONFIG as CFG
+
+pytestmark = pytest.mark.gpu
+
+LOGIT_TOL = 5e-3
+
+
+def _ids(B, T, seed, pad_left=0):
+    g = torch.Generator().manual_seed(seed)
+    ids = torch.randint(7, 11, (B, T), generator=g)
+    ids[:, -1] = 1
+    for b in range(B):
+        n = int(torch.randint(0, pad_left + 1, (1,), generator=g)) if pad_left else 0
+        ids[b, :n] = 4
+    return ids
+
+
+def _oracle_states(sd, ids):
+    """Residual stream after every block + final hidden + logits, from the oracle."""
+    import torch.nn.functional as F
+    from oracle import hyena_oracle as O
+
+    with torch.inference_mode():
+        h = F.embedding(ids, sd[O.BB + "embeddings.word_embeddings.weight"])
+        states = [h.clone()]
+        for i in range(CFG.n_layer):
+            h = O.block(sd, i, h, CFG)
+            states.append(h.clone())
+        hf = F.layer_norm(h, (CFG.d_model,), sd[O.BB + "ln_f.weight"], sd[O.BB + "ln_f.bias"], CFG.layer_norm_epsilon)
+        logits, attn = O.head(sd, hf, return_attention=True)
+    return states, hf, logits, attn
+
+
+@pytest.mark.parametrize("B,T", [(2, 301), (3, 1025)])
+def test_stagewise_residual_stream(engine, state_dict, B, T):
+    ids = _ids(B, T, seed=B * 1000 + T, pad_left=40)
+    states, hf, logits_ref, _ = _oracle_states(state_dict, ids)
+    engine.reserve(B, T)
+    try:
+        engine.set_debug_stop(0, 0)
+        engine.forward(ids.cuda())
+        got = engine.debug_copy("resid", (B, T, CFG.d_model), torch.float32).cpu()
+        assert torch.equal(got, states[0]), "embedding gather must be exact"
+        for l in range(CFG.n_layer):
+            engine.set_debug_stop(l, 9)
+            engine.forward(ids.cuda())
+            got = engine.debug_copy("resid", (B, T, CFG.d_model), torch.float32).cpu()
+            err = (got - states[l + 1]).abs().max().item()
+            assert err <= 5e-2, (l, err)
+    finally:
+        engine.set_debug_stop(-1, -1)
+    logits = engine.forward(ids.cuda()).cpu()
+    assert (logits - logits_ref).abs().max().item() <= LOGIT_TOL
+
+
+@pytest.mark.parametrize("B,T", [(1, 64), (4, 2049), (2, 8193)])
+def test_logits_and_labels(engine, state_dict, B, T):
+    from oracle import hyena_oracle as O
+
+    ids = _ids(B, T, seed=T, pad_left=T // 3)
+    ref = O.forward(state_dict, ids, CFG)
+    logits, labels = engine.forward(ids.to(torch.uint8).cuda(), return_labels=True)
+    logits, labels = logits.cpu(), labels.cpu()
+    err = (logits - ref).abs().max().item()
+    assert err <= LOGIT_TOL, err
+    margin = ref[:, 1] - ref[:, 0]
+    decided = margin.abs() > 2 * LOGIT_TOL
+    assert torch.equal(labels[decided].long(), ref.argmax(1)[decided])
+    # int64 ids (the reference's dtype) take the same path
+    logits64 = engine.forward(ids.cuda()).cpu()
+    assert torch.equal(logits64, logits)

@@ -1,0 +1,101 @@
+"""Kernel-level parity on the B200 (-m gpu): every CUDA kernel is called through the C-ABI and
+compared with a plain PyTorch fp32 statement of the same op (or the oracle's function)."""
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from chimeralm_b200 import _lib
+from chimeralm_b200.config import DEFAULT_CONFIG as CFG
+
+pytestmark = pytest.mark.gpu
+
+
+def _rand_bf16(shape, gen, scale=1.0):
+    return (torch.randn(shape, generator=gen) * scale).to(torch.bfloat16)
+
+
+@pytest.mark.parametrize("M", [1, 128, 1000, 8193])
+@pytest.mark.parametrize("NK", [(768, 256), (256, 256), (1024, 256), (256, 1024)])
+def test_gemm_bias(engine, M, NK):
+    N, K = NK
+    g = torch.Generator().manual_seed(M * 7 + N + K)
+    A, W = _rand_bf16((M, K), g), _rand_bf16((N, K), g, 0.05)
+    bias = torch.randn(N, generator=g) * 0.1
+    ref = A.float() @ W.float().T + bias
+    out = engine.gemm(A.cuda(), W.cuda(), bias.cuda(), _lib.EPI_BIAS_BF16)
+    torch.cuda.synchronize()
+    err = (out.float().cpu() - ref).abs().max().item()
+    # bf16 output rounding: |ref| ~ 1 -> half-ulp 2^-9 relative
+    assert err <= 1e-2 * max(1.0, ref.abs().max().item()), err
+
+
+def test_gemm_epilogues(engine):
+    g = torch.Generator().manual_seed(3)
+    M, K = 777, 256
+    A = _rand_bf16((M, K), g)
+    W1, b1 = _rand_bf16((1024, K), g, 0.05), torch.randn(1024, generator=g) * 0.1
+    ref = F.gelu(A.float() @ W1.float().T + b1, approximate="tanh")
+    out = engine.gemm(A.cuda(), W1.cuda(), b1.cuda(), _lib.EPI_BIAS_GELU_TANH)
+    assert (out.float().cpu() - ref).abs().max().item() <= 1e-2 * max(1.0, ref.abs().max().item())
+
+    W2, b2 = _rand_bf16((256, K), g, 0.05), torch.randn(256, generator=g) * 0.1
+    res = torch.randn(M, 256, generator=g)
+    ref = A.float() @ W2.float().T + b2 + res
+    out = engine.gemm(A.cuda(), W2.cuda(), b2.cuda(), _lib.EPI_BIAS_RES_F32, res=res.cuda())
+    assert (out.cpu() - ref).abs().max().item() <= 2e-5 * max(1.0, ref.abs().max().item())
+
+    w2, bb = torch.randn(256, generator=g) * 0.1, 0.37
+    ref = F.gelu(A.float() @ W2.float().T + b2) @ w2 + bb
+    out = engine.gemm(A.cuda(), W2.cuda(), b2.cuda(), _lib.EPI_SCORE, w2=w2.cuda(), b2=bb)
+    assert (out.cpu() - ref).abs().max().item() <= 1e-4 * max(1.0, ref.abs().max().item())
+
+
+def test_implicit_filter(engine, state_dict):
+    from oracle import hyena_oracle as O
+
+    for layer in (0, 3):
+        L = CFG.max_seq_len
+        ref = O.implicit_filter(state_dict, layer, L, CFG).T  # [D, L]
+        got = engine.get_filter(layer, L).cpu()
+        err = (got - ref).abs().max().item()
+        assert err <= 2e-5, (layer, err)
+
+
+@pytest.mark.parametrize("T", [1, 37, 128, 131, 1000, 2049, 4096, 8193, 8292, 20000, 32769])
+def test_longconv(engine, state_dict, T):
+    from oracle import hyena_oracle as O
+
+    B, D = 3, CFG.d_model
+    Tp = (T + 63) // 64 * 64
+    g = torch.Generator().manual_seed(T)
+    vx = torch.zeros(B, D, Tp, dtype=torch.bfloat16)
+    x0 = torch.zeros(B, D, Tp, dtype=torch.bfloat16)
+    vx[..., :T] = _rand_bf16((B, D, T), g)
+    x0[..., :T] = _rand_bf16((B, D, T), g)
+    vx[..., T:] = 7.0  # garbage in the pad region must not leak into the result
+    layer = 1
+    k = O.implicit_filter(state_dict, layer, T, CFG).T
+    bias = state_dict[f"{O.BB}layers.{layer}.mixer.filter_fn.bias"]
+    ref = O.fftconv(vx[..., :T].float(), k, bias) * x0[..., :T].float()  # CPU fp32 (the oracle's op)
+    out = engine.longconv(layer, vx.cuda(), x0.cuda(), T)
+    torch.cuda.synchronize()
+    err = (out[..., :T].float().cpu() - ref).abs().max().item()
+    scale = ref.abs().max().item()
+    assert err <= 1e-2 * max(1.0, scale), (T, err, scale)
+
+
+def test_encode(engine):
+    from chimeralm_b200.engine import pack_reads
+    from oracle import tokenizer_oracle as TO
+
+    seqs = ["ATCG", "", "ACGTNXacgt", "N" * 50, "ACGT" * 40, "G"]
+    for add_cls, pad_left, max_len in ((True, False, 34), (False, True, 100), (True, True, 16), (False, False, 7)):
+        ids_ref = [TO.encode(s, max_length=max_len, add_cls=add_cls) for s in seqs]
+        padded = TO.collate(ids_ref, padding_side="left" if pad_left else "right")
+        T_pad = len(padded[0])
+        bases, offs = pack_reads(seqs)
+        ids, lens = engine.encode(bases, offs, T_pad, add_cls=add_cls, add_sep=True, pad_left=pad_left,
+                                  max_bases=max_len - 1 - int(add_cls))
+        assert ids.cpu().tolist() == padded
+        assert lens.cpu().tolist() == [len(x) for x in ids_ref]
