@@ -44,6 +44,11 @@ _SIGNATURES = {
     "clm_predict_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                    C.c_int, C.c_void_p, C.c_void_p]),
     "clm_launch_count": (C.c_longlong, [C.c_void_p]),
+    "clm_profile_enable": (C.c_int, [C.c_void_p, C.c_int]),
+    "clm_profile_reset": (C.c_int, [C.c_void_p]),
+    "clm_profile_num": (C.c_int, []),
+    "clm_profile_name": (C.c_char_p, [C.c_int]),
+    "clm_profile_get": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
     "clm_gemm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p]),
     "clm_longconv": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,

@@ -77,6 +77,13 @@ struct clm_ctx {
   uint8_t* st_ids = nullptr;
   float* st_logits = nullptr;
   uint8_t* st_labels = nullptr;
+  // per-kernel-class device timing (CUDA events on the launching stream)
+  bool prof_on = false;
+  std::vector<cudaEvent_t> prof_pool;
+  std::vector<int> prof_cat;      // category of event pair i (events 2i, 2i+1)
+  size_t prof_used = 0;           // event pairs in flight
+  double prof_ms[32] = {0};
+  long long prof_n[32] = {0};
   // debug
   int dbg_layer = -1, dbg_stage = -1;
   long long launches = 0;
@@ -289,6 +296,46 @@ int launch_longconv(clm_ctx* c, int layer, const __nv_bfloat16* vx, const __nv_b
 
 int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
+enum ProfCat { PC_ENCODE = 0, PC_EMBED, PC_LN, PC_GEMM_IN, PC_SHORTCONV, PC_LONGCONV, PC_TRANSPOSE, PC_GEMM_OUT,
+               PC_GEMM_FC1, PC_GEMM_FC2, PC_SCORE, PC_POOL, PC_HEAD, PC_COUNT };
+const char* kProfNames[PC_COUNT] = {"encode", "embed", "layernorm", "gemm_in_proj", "shortconv_gate", "longconv",
+                                    "transpose", "gemm_out_proj", "gemm_fc1", "gemm_fc2", "gemm_score", "pool",
+                                    "head"};
+
+struct ProfScope {
+  clm_ctx* c;
+  cudaStream_t st;
+  size_t idx = (size_t)-1;
+  ProfScope(clm_ctx* c_, int cat, cudaStream_t st_) : c(c_), st(st_) {
+    if (!c->prof_on) return;
+    if (c->prof_used * 2 + 2 > c->prof_pool.size()) {
+      cudaEvent_t a, b;
+      if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) return;
+      c->prof_pool.push_back(a);
+      c->prof_pool.push_back(b);
+      c->prof_cat.push_back(cat);
+    }
+    idx = c->prof_used++;
+    c->prof_cat[idx] = cat;
+    cudaEventRecord(c->prof_pool[2 * idx], st);
+  }
+  ~ProfScope() {
+    if (idx != (size_t)-1) cudaEventRecord(c->prof_pool[2 * idx + 1], st);
+  }
+};
+
+void prof_collect(clm_ctx* c) {
+  for (size_t i = 0; i < c->prof_used; ++i) {
+    float ms = 0.f;
+    if (cudaEventSynchronize(c->prof_pool[2 * i + 1]) == cudaSuccess &&
+        cudaEventElapsedTime(&ms, c->prof_pool[2 * i], c->prof_pool[2 * i + 1]) == cudaSuccess) {
+      c->prof_ms[c->prof_cat[i]] += ms;
+      c->prof_n[c->prof_cat[i]] += 1;
+    }
+  }
+  c->prof_used = 0;
+}
+
 }  // namespace
 
 // =============================================================================================
@@ -349,6 +396,7 @@ void clm_destroy(clm_ctx* c) {
   cudaDeviceSynchronize();
   for (void* p : c->owned)
     if (p) cudaFree(p);
+  for (cudaEvent_t e : c->prof_pool) cudaEventDestroy(e);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
   delete c;
 }
@@ -518,6 +566,7 @@ int clm_encode_batch(clm_ctx* c, const uint8_t* d_bases, const int64_t* d_offset
   if (!c || !d_bases || !d_offsets || !d_ids_out || B <= 0 || T_pad <= 0 || max_bases < 0)
     return fail(c, CLM_ERR_INVALID, "clm_encode_batch: bad argument");
   EncodeParams p{d_bases, d_offsets, d_ids_out, d_lens_out, B, T_pad, add_cls ? 1 : 0, add_sep ? 1 : 0, pad_left ? 1 : 0, max_bases};
+  ProfScope ps_(c, PC_ENCODE, (cudaStream_t)stream);
   dim3 grid(std::min(64, (T_pad + 255) / 256), B);
   encode_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p);
   CLM_LAUNCH_CHECK(c, "encode");
@@ -549,65 +598,79 @@ int clm_forward(clm_ctx* c, const void* d_ids, int ids_dtype, int B, int T, floa
 #define STOP_AFTER(layer, stage) \
   if (c->dbg_layer == (layer) && c->dbg_stage == (stage)) return 0
 
+  { ProfScope ps_(c, PC_EMBED, st);
   switch (ids_dtype) {
     case CLM_U8: embed_kernel<uint8_t><<<rows8, 256, 0, st>>>((const uint8_t*)d_ids, c->emb, c->R, M, D, g.vocab_rows, c->d_err); break;
     case CLM_I32: embed_kernel<int32_t><<<rows8, 256, 0, st>>>((const int32_t*)d_ids, c->emb, c->R, M, D, g.vocab_rows, c->d_err); break;
     case CLM_I64: embed_kernel<int64_t><<<rows8, 256, 0, st>>>((const int64_t*)d_ids, c->emb, c->R, M, D, g.vocab_rows, c->d_err); break;
     default: return fail(c, CLM_ERR_INVALID, "clm_forward: ids dtype %d not supported", ids_dtype);
   }
-  CLM_LAUNCH_CHECK(c, "embed");
+  CLM_LAUNCH_CHECK(c, "embed"); }
   STOP_AFTER(0, 0);
 
   for (int l = 0; l < g.n_layer; ++l) {
     LayerW& L = c->layers[l];
+    { ProfScope ps_(c, PC_LN, st);
     layernorm_bf16_kernel<<<rows8, 256, 0, st>>>(c->R, L.ln1_g, L.ln1_b, c->XN, M, g.layer_norm_eps);
-    CLM_LAUNCH_CHECK(c, "ln1");
+    CLM_LAUNCH_CHECK(c, "ln1"); }
     STOP_AFTER(l, 1);
     GemmParams p{};
     p.M = (int)M; p.N = 3 * D; p.K = D; p.bias = L.in_b; p.out = c->U; p.ldo = 3 * D;
-    if ((rc = launch_gemm(c, c->XN, L.tm_in, p, EPI_BIAS_BF16, st))) return rc;
+    { ProfScope ps_(c, PC_GEMM_IN, st);
+    if ((rc = launch_gemm(c, c->XN, L.tm_in, p, EPI_BIAS_BF16, st))) return rc; }
     STOP_AFTER(l, 2);
+    { ProfScope ps_(c, PC_SHORTCONV, st);
     shortconv_gate_kernel<<<dim3((Tp + 63) / 64, D / 32, B), 256, 0, st>>>(c->U, L.sc_w, L.sc_b, c->VX, c->X0, T, Tp, D);
-    CLM_LAUNCH_CHECK(c, "shortconv_gate");
+    CLM_LAUNCH_CHECK(c, "shortconv_gate"); }
     STOP_AFTER(l, 3);
-    if ((rc = launch_longconv(c, l, c->VX, c->X0, c->Y, B, T, Tp, c->scratch, c->scratch_bytes, st))) return rc;
+    { ProfScope ps_(c, PC_LONGCONV, st);
+    if ((rc = launch_longconv(c, l, c->VX, c->X0, c->Y, B, T, Tp, c->scratch, c->scratch_bytes, st))) return rc; }
     STOP_AFTER(l, 4);
+    { ProfScope ps_(c, PC_TRANSPOSE, st);
     transpose_ct_kernel<<<dim3((T + 63) / 64, D / 64, B), 256, 0, st>>>(c->Y, c->YT, T, Tp, D);
-    CLM_LAUNCH_CHECK(c, "transpose_ct");
+    CLM_LAUNCH_CHECK(c, "transpose_ct"); }
     STOP_AFTER(l, 5);
     p = GemmParams{};
     p.M = (int)M; p.N = D; p.K = D; p.bias = L.out_b; p.out = c->R; p.res = c->R; p.ldo = D;
-    if ((rc = launch_gemm(c, c->YT, L.tm_out, p, EPI_BIAS_RES_F32, st))) return rc;
+    { ProfScope ps_(c, PC_GEMM_OUT, st);
+    if ((rc = launch_gemm(c, c->YT, L.tm_out, p, EPI_BIAS_RES_F32, st))) return rc; }
     STOP_AFTER(l, 6);
+    { ProfScope ps_(c, PC_LN, st);
     layernorm_bf16_kernel<<<rows8, 256, 0, st>>>(c->R, L.ln2_g, L.ln2_b, c->XN, M, g.layer_norm_eps);
-    CLM_LAUNCH_CHECK(c, "ln2");
+    CLM_LAUNCH_CHECK(c, "ln2"); }
     STOP_AFTER(l, 7);
     p = GemmParams{};
     p.M = (int)M; p.N = g.d_inner; p.K = D; p.bias = L.fc1_b; p.out = c->U; p.ldo = g.d_inner;
-    if ((rc = launch_gemm(c, c->XN, L.tm_fc1, p, EPI_BIAS_GELU_TANH, st))) return rc;
+    { ProfScope ps_(c, PC_GEMM_FC1, st);
+    if ((rc = launch_gemm(c, c->XN, L.tm_fc1, p, EPI_BIAS_GELU_TANH, st))) return rc; }
     STOP_AFTER(l, 8);
     p = GemmParams{};
     p.M = (int)M; p.N = D; p.K = g.d_inner; p.bias = L.fc2_b; p.out = c->R; p.res = c->R; p.ldo = D;
-    if ((rc = launch_gemm(c, c->U, L.tm_fc2, p, EPI_BIAS_RES_F32, st))) return rc;
+    { ProfScope ps_(c, PC_GEMM_FC2, st);
+    if ((rc = launch_gemm(c, c->U, L.tm_fc2, p, EPI_BIAS_RES_F32, st))) return rc; }
     STOP_AFTER(l, 9);
   }
   const int NL = g.n_layer;
+  { ProfScope ps_(c, PC_LN, st);
   layernorm_bf16_kernel<<<rows8, 256, 0, st>>>(c->R, c->lnf_g, c->lnf_b, c->XN, M, g.layer_norm_eps);
-  CLM_LAUNCH_CHECK(c, "ln_f");
+  CLM_LAUNCH_CHECK(c, "ln_f"); }
   STOP_AFTER(NL, 10);
   {
     GemmParams p{};
     p.M = (int)M; p.N = D; p.K = D; p.bias = c->att0_b; p.w2 = c->att2_w; p.b2 = c->att2_b; p.score = c->score; p.ldo = D;
+    ProfScope ps_(c, PC_SCORE, st);
     if ((rc = launch_gemm(c, c->XN, c->tm_att0, p, EPI_SCORE, st))) return rc;
   }
   STOP_AFTER(NL, 11);
+  { ProfScope ps_(c, PC_POOL, st);
   pool_partial_kernel<<<dim3(c->n_split, B), 256, 0, st>>>(c->R, c->score, c->lnf_g, c->lnf_b, c->part, T, c->n_split, g.layer_norm_eps);
-  CLM_LAUNCH_CHECK(c, "pool_partial");
+  CLM_LAUNCH_CHECK(c, "pool_partial"); }
   STOP_AFTER(NL, 12);
   HeadParams hp = c->head;
   hp.part = c->part; hp.n_split = c->n_split; hp.logits = d_logits; hp.labels = d_labels; hp.pooled_out = c->pooled;
+  { ProfScope ps_(c, PC_HEAD, st);
   head_kernel<<<B, 512, 0, st>>>(hp);
-  CLM_LAUNCH_CHECK(c, "head");
+  CLM_LAUNCH_CHECK(c, "head"); }
 #undef STOP_AFTER
   return 0;
 }
@@ -670,6 +733,32 @@ int clm_get_filter(clm_ctx* c, int layer, float* d_out, int L, void* stream) {
   if (layer < 0 || layer >= c->cfg.n_layer || L <= 0 || L > c->cfg.max_seq_len) return fail(c, CLM_ERR_INVALID, "clm_get_filter: bad argument");
   CLM_CUDA(c, cudaMemcpy2DAsync(d_out, (size_t)L * sizeof(float), c->layers[layer].k, (size_t)c->Lk * sizeof(float),
                                 (size_t)L * sizeof(float), c->cfg.d_model, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return 0;
+}
+
+int clm_profile_enable(clm_ctx* c, int on) {
+  if (!c) return CLM_ERR_INVALID;
+  if (!on && c->prof_on) prof_collect(c);
+  c->prof_on = on != 0;
+  return 0;
+}
+
+int clm_profile_reset(clm_ctx* c) {
+  if (!c) return CLM_ERR_INVALID;
+  prof_collect(c);
+  for (int i = 0; i < 32; ++i) { c->prof_ms[i] = 0; c->prof_n[i] = 0; }
+  return 0;
+}
+
+int clm_profile_num(void) { return PC_COUNT; }
+
+const char* clm_profile_name(int cat) { return (cat >= 0 && cat < PC_COUNT) ? kProfNames[cat] : ""; }
+
+int clm_profile_get(clm_ctx* c, int cat, double* total_ms, long long* launches) {
+  if (!c || cat < 0 || cat >= PC_COUNT || !total_ms || !launches) return fail(c, CLM_ERR_INVALID, "clm_profile_get: bad argument");
+  prof_collect(c);
+  *total_ms = c->prof_ms[cat];
+  *launches = c->prof_n[cat];
   return 0;
 }
 

@@ -87,6 +87,22 @@ class Engine:
     def launch_count(self) -> int:
         return int(self.lib.clm_launch_count(self.ctx))
 
+    def profile(self, on: bool) -> None:
+        self._check(self.lib.clm_profile_enable(self.ctx, int(on)), "clm_profile_enable")
+
+    def profile_reset(self) -> None:
+        self._check(self.lib.clm_profile_reset(self.ctx), "clm_profile_reset")
+
+    def profile_read(self) -> dict:
+        """{kernel class: (total device ms, launches)} accumulated while profiling was on."""
+        out = {}
+        for cat in range(self.lib.clm_profile_num()):
+            ms, n = C.c_double(), C.c_longlong()
+            self._check(self.lib.clm_profile_get(self.ctx, cat, C.byref(ms), C.byref(n)), "clm_profile_get")
+            if n.value:
+                out[self.lib.clm_profile_name(cat).decode()] = (ms.value, n.value)
+        return out
+
     # ------------------------------------------------------------------ hot path
     def forward(self, input_ids: torch.Tensor, return_labels: bool = False):
         """ClassificationLit.forward: int ids [B,T] on this device -> float32 logits [B,2]."""

@@ -95,6 +95,15 @@ int clm_predict_host(clm_ctx* ctx, const uint8_t* h_bases, const int64_t* h_offs
 /* Number of kernel launches issued by this context since creation (bench.py's gpu_launches). */
 long long clm_launch_count(const clm_ctx* ctx);
 
+/* Per-kernel-class device timing: while enabled, every launch is bracketed by CUDA events on
+ * its own stream; clm_profile_get synchronises on them and returns the accumulated time and
+ * launch count of one class (names from clm_profile_name, 0 <= cat < clm_profile_num()). */
+int clm_profile_enable(clm_ctx* ctx, int on);
+int clm_profile_reset(clm_ctx* ctx);
+int clm_profile_num(void);
+const char* clm_profile_name(int cat);
+int clm_profile_get(clm_ctx* ctx, int cat, double* total_ms, long long* launches);
+
 /* ---- unit-level entry points (parity tests call the kernels one by one through these) ---- */
 /* out = epilogue(A[M,K] (bf16) * W[N,K]^T (bf16)); epi: 0 bias->bf16, 1 bias+gelu_tanh->bf16,
  * 2 bias+res->f32, 3 scorer (score[m] = sum_n gelu_erf(.)*w2[n] + b2, needs N == 256). */
