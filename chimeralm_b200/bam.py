@@ -1,0 +1,184 @@
+"""Self-contained BAM reading/writing for the predict and filter commands (no pysam/htslib).
+
+Mirrors `chimeralm/data/bam.py:21-38` (reference): `is_chimeric` keeps records that are
+mapped, carry an `SA` aux tag and are neither secondary nor supplementary; `parse_bam_file`
+yields `{"id": query_name, "seq": query_sequence}` in file order (the sequence as stored in
+the BAM, i.e. already reverse-complemented for reverse-strand records, like pysam's
+`query_sequence`).
+
+BGZF is a series of gzip members, which `gzip`/`zlib` read back to back; records follow the
+SAM/BAM spec section 4.2.
+"""
+
+from __future__ import annotations
+
+import gzip
+import struct
+import zlib
+from collections.abc import Iterator
+from dataclasses import dataclass
+from pathlib import Path
+
+import numpy as np
+
+FLAG_UNMAPPED, FLAG_SECONDARY, FLAG_SUPPLEMENTARY = 0x4, 0x100, 0x800
+_NIB = np.frombuffer(b"=ACMGRSVTWYHKDBN", dtype=np.uint8)
+_AUX_FIXED = {b"A": 1, b"c": 1, b"C": 1, b"s": 2, b"S": 2, b"i": 4, b"I": 4, b"f": 4}
+
+
+@dataclass
+class BamRecord:
+    ref_id: int
+    pos: int
+    flag: int
+    name: str
+    l_seq: int
+    raw: bytes          # the whole record after the block_size field
+    seq_off: int        # offset of the 4-bit sequence inside raw
+    aux_off: int        # offset of the aux area inside raw
+
+    @property
+    def is_unmapped(self) -> bool:
+        return bool(self.flag & FLAG_UNMAPPED)
+
+    @property
+    def is_secondary(self) -> bool:
+        return bool(self.flag & FLAG_SECONDARY)
+
+    @property
+    def is_supplementary(self) -> bool:
+        return bool(self.flag & FLAG_SUPPLEMENTARY)
+
+    def sequence_bytes(self) -> np.ndarray:
+        """ASCII bases (uint8) decoded from the 4-bit packing."""
+        packed = np.frombuffer(self.raw, dtype=np.uint8, count=(self.l_seq + 1) // 2, offset=self.seq_off)
+        out = np.empty(packed.size * 2, dtype=np.uint8)
+        out[0::2] = _NIB[packed >> 4]
+        out[1::2] = _NIB[packed & 15]
+        return out[: self.l_seq]
+
+    @property
+    def query_sequence(self) -> str:
+        return self.sequence_bytes().tobytes().decode("ascii")
+
+    def has_tag(self, tag: str) -> bool:
+        want = tag.encode()
+        raw, p, n = self.raw, self.aux_off, len(self.raw)
+        while p + 3 <= n:
+            t, ty = raw[p : p + 2], raw[p + 2 : p + 3]
+            if t == want:
+                return True
+            p += 3
+            if ty in _AUX_FIXED:
+                p += _AUX_FIXED[ty]
+            elif ty in (b"Z", b"H"):
+                p = raw.index(b"\0", p) + 1
+            elif ty == b"B":
+                sub, cnt = raw[p : p + 1], struct.unpack_from("<i", raw, p + 1)[0]
+                p += 5 + cnt * _AUX_FIXED[sub]
+            else:
+                raise ValueError(f"bad aux type {ty!r} in record {self.name}")
+        return False
+
+
+def is_chimeric(read: BamRecord) -> bool:
+    """Reference `is_chimeric` (chimeralm/data/bam.py:21-23)."""
+    return not read.is_unmapped and read.has_tag("SA") and not read.is_secondary and not read.is_supplementary
+
+
+class BamReader:
+    """Sequential BAM reader: header text, reference list, then records."""
+
+    def __init__(self, path: str | Path):
+        self.f = gzip.open(str(path), "rb")
+        if self.f.read(4) != b"BAM\1":
+            raise ValueError(f"{path}: not a BAM file")
+        (l_text,) = struct.unpack("<i", self.f.read(4))
+        self.header_text = self.f.read(l_text)
+        (n_ref,) = struct.unpack("<i", self.f.read(4))
+        self.references = []
+        for _ in range(n_ref):
+            (l_name,) = struct.unpack("<i", self.f.read(4))
+            name = self.f.read(l_name)[:-1].decode()
+            (l_ref,) = struct.unpack("<i", self.f.read(4))
+            self.references.append((name, l_ref))
+
+    def header_bytes(self) -> bytes:
+        out = [b"BAM\1", struct.pack("<i", len(self.header_text)), self.header_text, struct.pack("<i", len(self.references))]
+        for name, l_ref in self.references:
+            nm = name.encode() + b"\0"
+            out += [struct.pack("<i", len(nm)), nm, struct.pack("<i", l_ref)]
+        return b"".join(out)
+
+    def __iter__(self) -> Iterator[BamRecord]:
+        f = self.f
+        while True:
+            head = f.read(4)
+            if len(head) < 4:
+                return
+            (block_size,) = struct.unpack("<i", head)
+            raw = f.read(block_size)
+            if len(raw) < block_size:
+                raise ValueError("truncated BAM record")
+            ref_id, pos, l_read_name, _mapq, _bin, n_cigar, flag, l_seq = struct.unpack_from("<iiBBHHHi", raw, 0)
+            name = raw[32 : 32 + l_read_name - 1].decode("ascii", "replace")
+            seq_off = 32 + l_read_name + 4 * n_cigar
+            aux_off = seq_off + (l_seq + 1) // 2 + l_seq
+            yield BamRecord(ref_id, pos, flag, name, l_seq, raw, seq_off, aux_off)
+
+    def close(self):
+        self.f.close()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+
+def parse_bam_file(file_path: str | Path) -> Iterator[dict]:
+    """Reference `parse_bam_file` (chimeralm/data/bam.py:26-38)."""
+    with BamReader(file_path) as bam:
+        for read in bam:
+            if is_chimeric(read):
+                yield {"id": read.name, "seq": read.query_sequence}
+
+
+def parse_bam_file_bytes(file_path: str | Path):
+    """Same records as `parse_bam_file` but bases stay uint8 arrays (feeds the CUDA encoder)."""
+    with BamReader(file_path) as bam:
+        for read in bam:
+            if is_chimeric(read):
+                yield read.name, read.sequence_bytes()
+
+
+# ---------------------------------------------------------------------------------- writing
+_BGZF_EOF = bytes.fromhex("1f8b08040000000000ff0600424302001b0003000000000000000000")
+
+
+def _bgzf_block(data: bytes, level: int = 6) -> bytes:
+    co = zlib.compressobj(level, zlib.DEFLATED, -15)
+    comp = co.compress(data) + co.flush()
+    bsize = len(comp) + 25
+    return (b"\x1f\x8b\x08\x04\0\0\0\0\0\xff\x06\0BC\x02\0" + struct.pack("<H", bsize) + comp +
+            struct.pack("<II", zlib.crc32(data) & 0xFFFFFFFF, len(data)))
+
+
+class BamWriter:
+    """Minimal BGZF BAM writer (records are copied byte-for-byte from the input)."""
+
+    def __init__(self, path: str | Path, header_bytes: bytes):
+        self.f = open(str(path), "wb")
+        self.buf = bytearray(header_bytes)
+
+    def write(self, rec: BamRecord) -> None:
+        self.buf += struct.pack("<i", len(rec.raw)) + rec.raw
+        while len(self.buf) >= 0xFF00:
+            self.f.write(_bgzf_block(bytes(self.buf[:0xFF00])))
+            del self.buf[:0xFF00]
+
+    def close(self) -> None:
+        if self.buf:
+            self.f.write(_bgzf_block(bytes(self.buf)))
+        self.f.write(_BGZF_EOF)
+        self.f.close()

@@ -183,7 +183,7 @@ int launch_gemm_t(clm_ctx* c, const CUtensorMap& tmA, const CUtensorMap& tmB, co
     CLM_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
     attr_set = true;
   }
-  dim3 grid((p.M + GEMM_BM - 1) / GEMM_BM, p.N / BN);
+  dim3 grid((unsigned)(((p.M + GEMM_BM - 1) / GEMM_BM) * (p.N / BN)));
   kern<<<grid, GEMM_THREADS, S::kTotal, st>>>(tmA, tmB, p);
   CLM_LAUNCH_CHECK(c, "gemm_bf16_tn");
   return 0;
@@ -715,7 +715,7 @@ int clm_gemm(clm_ctx* c, const void* d_A, const void* d_W, const float* d_bias, 
 int clm_longconv(clm_ctx* c, int layer, const void* d_vx, const void* d_x0, void* d_out, int B, int T, int Tp,
                  void* stream) {
   if (!c || !c->finalized) return fail(c, CLM_ERR_STATE, "clm_longconv before clm_finalize");
-  if (layer < 0 || layer >= c->cfg.n_layer || B <= 0 || T <= 0 || Tp < T) return fail(c, CLM_ERR_INVALID, "clm_longconv: bad argument");
+  if (layer < 0 || layer >= c->cfg.n_layer || B <= 0 || T <= 0 || Tp < T || Tp % 64 != 0) return fail(c, CLM_ERR_INVALID, "clm_longconv: bad argument (Tp must be a multiple of 64 and >= T)");
   const size_t needb = conv_scratch_bytes(c, T);
   if (needb > c->scratch_bytes) {
     CLM_CUDA(c, cudaDeviceSynchronize());

@@ -76,8 +76,11 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * GEMM_BM;
-  const int n0 = blockIdx.y * BN;
+  // 1-D grid, N-tile fastest: the CTAs that share an A tile are launched back to back, so the
+  // tile is fetched from HBM once and served from L2 to the other N-tiles.
+  const int n_tiles = p.N / BN;
+  const int m0 = (blockIdx.x / n_tiles) * GEMM_BM;
+  const int n0 = (blockIdx.x % n_tiles) * BN;
   const int num_k = p.K / GEMM_BK;
 
   if (warp == 0 && lane == 0) {

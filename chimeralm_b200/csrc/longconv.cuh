@@ -125,6 +125,31 @@ struct LongConvParams {
 };
 
 __device__ __forceinline__ float bf16_ld(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+// streaming 16-byte load (8 bf16), bypassing L1 allocation
+__device__ __forceinline__ uint4 ld_nc_16(const __nv_bfloat16* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void unpack_bf16x8(const uint4& r, float (&f)[8]) {
+  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    f[2 * i] = __uint_as_float(w[i] << 16);
+    f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+  }
+}
+__device__ __forceinline__ uint4 pack_bf16x8(const float (&f)[8]) {
+  uint32_t w[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+    w[i] = *reinterpret_cast<uint32_t*>(&v);
+  }
+  return make_uint4(w[0], w[1], w[2], w[3]);
+}
 
 template <int LOGN>
 __global__ void __launch_bounds__(ConvCfg<LOGN>::THREADS, 1) longconv_kernel(LongConvParams p) {
@@ -148,47 +173,83 @@ __global__ void __launch_bounds__(ConvCfg<LOGN>::THREADS, 1) longconv_kernel(Lon
 
     for (int ch = 0; ch < p.n_chunks; ++ch) {
       const int tbase = ch * C;
-      // ---- load chunk (zero beyond T), upper half zero
-      for (int i = tid; i < C; i += TH) {
+      // ---- load chunk (zero beyond T), upper half zero.  8 bf16 (16 B) per sequence per step;
+      //      row starts are 128 B aligned (Tp % 64 == 0) and Tp >= any t touched here.
+#pragma unroll 2
+      for (int i = tid * 8; i < C; i += TH * 8) {
         const int t = tbase + i;
-        float a = 0.f, b = 0.f;
+        uint4 ra = make_uint4(0, 0, 0, 0), rb = make_uint4(0, 0, 0, 0);
         if (t < p.T) {
-          a = bf16_ld(va + t);
-          if (has_b1) b = bf16_ld(vb + t);
+          ra = ld_nc_16(va + t);
+          if (has_b1) rb = ld_nc_16(vb + t);
         }
-        zs[fft::pad_idx(i)] = make_float2(a, b);
-        zs[fft::pad_idx(C + i)] = make_float2(0.f, 0.f);
+        float fa[8], fb[8];
+        unpack_bf16x8(ra, fa);
+        unpack_bf16x8(rb, fb);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const bool ok = (t + j) < p.T;
+          zs[fft::pad_idx(i + j)] = make_float2(ok ? fa[j] : 0.f, ok ? fb[j] : 0.f);
+          zs[fft::pad_idx(C + i + j)] = make_float2(0.f, 0.f);
+        }
       }
       __syncthreads();
       fft::fft_forward<LOGN, TH>(zs, tid);
-      // ---- frequency domain: Y = sum_{j<=ch} U_j . G_{ch-j}
+      // ---- frequency domain: Y = sum_{j<=ch} U_j . G_{ch-j}; two bins (one float4) per step
       float2* my_scratch = p.scratch + (long long)blockIdx.x * p.n_chunks * N;
       const float2* g0 = p.gspec + (long long)c * N;
       const long long gstride = (long long)p.D * N;
-      for (int i = tid; i < N; i += TH) {
-        const float2 u = zs[fft::pad_idx(i)];
-        if (p.n_chunks > 1 && ch + 1 < p.n_chunks) my_scratch[(long long)ch * N + i] = u;
-        float2 acc = fft::cmul(u, g0[i]);
+      const bool park = p.n_chunks > 1 && ch + 1 < p.n_chunks;
+#pragma unroll 4
+      for (int i = tid * 2; i < N; i += TH * 2) {
+        const float4 g = __ldg(reinterpret_cast<const float4*>(g0 + i));
+        const int zi = fft::pad_idx(i);
+        const float2 u0 = zs[zi], u1 = zs[zi + 1];
+        if (park) *reinterpret_cast<float4*>(my_scratch + (long long)ch * N + i) = make_float4(u0.x, u0.y, u1.x, u1.y);
+        float2 a0 = fft::cmul(u0, make_float2(g.x, g.y)), a1 = fft::cmul(u1, make_float2(g.z, g.w));
         for (int j = 0; j < ch; ++j) {
-          const float2 uj = my_scratch[(long long)j * N + i];
-          const float2 g = g0[(long long)(ch - j) * gstride + i];
-          acc.x += uj.x * g.x - uj.y * g.y;
-          acc.y += uj.x * g.y + uj.y * g.x;
+          const float4 uj = *reinterpret_cast<const float4*>(my_scratch + (long long)j * N + i);
+          const float4 gj = __ldg(reinterpret_cast<const float4*>(g0 + (long long)(ch - j) * gstride + i));
+          a0.x += uj.x * gj.x - uj.y * gj.y;
+          a0.y += uj.x * gj.y + uj.y * gj.x;
+          a1.x += uj.z * gj.z - uj.w * gj.w;
+          a1.y += uj.z * gj.w + uj.w * gj.z;
         }
-        zs[fft::pad_idx(i)] = acc;
+        zs[zi] = a0;
+        zs[zi + 1] = a1;
       }
       __syncthreads();
       fft::fft_inverse<LOGN, TH>(zs, tid);
-      // ---- outputs y[tbase + r] = z[C + r]; add bias skip, apply x0 gate, store bf16
-      for (int r = tid; r < C; r += TH) {
+      // ---- outputs y[tbase + r] = z[C + r]; add bias skip, apply x0 gate, store bf16 (8 per step)
+#pragma unroll 2
+      for (int r = tid * 8; r < C; r += TH * 8) {
         const int t = tbase + r;
         if (t < t_fft) {
-          const float2 y = zs[fft::pad_idx(C + r)];
-          const float oa = (y.x + dc * bf16_ld(va + t)) * bf16_ld(p.x0 + off0 + t);
-          p.out[off0 + t] = __float2bfloat16(oa);
+          const uint4 rva = ld_nc_16(va + t), rxa = ld_nc_16(p.x0 + off0 + t);
+          uint4 rvb = make_uint4(0, 0, 0, 0), rxb = make_uint4(0, 0, 0, 0);
           if (has_b1) {
-            const float ob = (y.y + dc * bf16_ld(vb + t)) * bf16_ld(p.x0 + off1 + t);
-            p.out[off1 + t] = __float2bfloat16(ob);
+            rvb = ld_nc_16(vb + t);
+            rxb = ld_nc_16(p.x0 + off1 + t);
+          }
+          float fva[8], fxa[8], fvb[8], fxb[8], oa[8], ob[8];
+          unpack_bf16x8(rva, fva);
+          unpack_bf16x8(rxa, fxa);
+          unpack_bf16x8(rvb, fvb);
+          unpack_bf16x8(rxb, fxb);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float2 y = zs[fft::pad_idx(C + r + j)];
+            oa[j] = (y.x + dc * fva[j]) * fxa[j];
+            ob[j] = (y.y + dc * fvb[j]) * fxb[j];
+          }
+          if (t + 8 <= t_fft) {
+            *reinterpret_cast<uint4*>(p.out + off0 + t) = pack_bf16x8(oa);
+            if (has_b1) *reinterpret_cast<uint4*>(p.out + off1 + t) = pack_bf16x8(ob);
+          } else {
+            for (int j = 0; j < 8 && t + j < t_fft; ++j) {
+              p.out[off0 + t + j] = __float2bfloat16(oa[j]);
+              if (has_b1) p.out[off1 + t + j] = __float2bfloat16(ob[j]);
+            }
           }
         }
       }

@@ -1,0 +1,160 @@
+"""Predict-side data module: mirror of `chimeralm/data/bam.py::BamDataModule` (reference
+:78-109,129-174,287-299) without Lightning / HF datasets / pysam.
+
+Batching policy is the reference's: file order, `batch_size // world_size` reads per device,
+`shuffle=False`, last batch short, every batch padded to its longest member on the
+tokenizer's `padding_side`.  Under data parallelism rank r takes samples r, r+W, r+2W, ...
+(Lightning's unrepeated distributed sampler in predict mode).  `bucket_by_length=True` is the
+B200-side option that sorts reads by length first so batches carry little padding.
+
+When an `Engine` is attached the batch's `input_ids` are produced on the GPU by
+`clm_encode_batch` from raw bases staged in pinned memory (uint8 ids, device tensor);
+without one the module collates on the host exactly like `DataCollator.torch_call`.
+"""
+
+from __future__ import annotations
+
+from pathlib import Path
+
+import numpy as np
+import torch
+
+from .bam import parse_bam_file_bytes
+from .tokenizer import DataCollator, encode_read_name
+
+
+class PredictDataset:
+    """Reads kept as (name, uint8 bases) in file order, already truncated to `max_bases`."""
+
+    def __init__(self, names: list[str], seqs: list[np.ndarray]):
+        self.names, self.seqs = names, seqs
+
+    def __len__(self):
+        return len(self.names)
+
+
+def read_fastq_bytes(path):
+    import gzip
+
+    op = gzip.open if str(path).endswith(".gz") else open
+    with op(str(path), "rb") as f:
+        while True:
+            h = f.readline()
+            if not h:
+                return
+            s = f.readline().rstrip(b"\r\n")
+            f.readline()
+            f.readline()
+            yield h[1:].split()[0].decode("ascii", "replace"), np.frombuffer(s, dtype=np.uint8)
+
+
+class BamDataModule:
+    def __init__(self, tokenizer, train_data_path=None, batch_size: int = 12, val_data_path=None, test_data_path=None,
+                 predict_data_path=None, num_workers: int = 1, max_train_samples=None, max_val_samples=None,
+                 max_test_samples=None, max_predict_samples=None, *, pin_memory: bool = False, engine=None,
+                 bucket_by_length: bool = False, rank: int = 0, world_size: int = 1):
+        self.tokenizer = tokenizer
+        self.batch_size = batch_size
+        self.predict_data_path = predict_data_path
+        self.max_predict_samples = max_predict_samples
+        self.engine = engine
+        self.bucket_by_length = bucket_by_length
+        self.rank, self.world_size = rank, world_size
+        self.batch_size_per_device = batch_size
+        self.data_collator = DataCollator(tokenizer)
+        self.data_predict: PredictDataset | None = None
+
+    @property
+    def num_classes(self) -> int:
+        return 2
+
+    def setup(self, stage: str | None = None) -> None:
+        if self.batch_size % self.world_size != 0:
+            raise RuntimeError(f"Batch size ({self.batch_size}) is not divisible by the number of devices ({self.world_size}).")
+        self.batch_size_per_device = self.batch_size // self.world_size
+        if stage != "predict":
+            raise NotImplementedError("chimeralm_b200 implements the predict stage only (training is out of scope)")
+        if not self.predict_data_path:
+            raise ValueError("Predict data path is required for prediction stage.")
+        path = Path(self.predict_data_path)
+        max_bases = self.tokenizer.max_len_single_sentence - self.tokenizer.num_special_tokens
+        it = read_fastq_bytes(path) if path.suffix in (".fq", ".fastq", ".gz") else parse_bam_file_bytes(path)
+        names, seqs = [], []
+        for name, seq in it:
+            names.append(name)
+            seqs.append(seq[:max_bases])
+            if self.max_predict_samples is not None and len(names) >= self.max_predict_samples:
+                break
+        self.data_predict = PredictDataset(names, seqs)
+
+    # -------------------------------------------------------------------------------------
+    def _rank_indices(self) -> list[int]:
+        n = len(self.data_predict)
+        idx = list(range(n))
+        if self.bucket_by_length:
+            idx.sort(key=lambda i: len(self.data_predict.seqs[i]))
+        return idx[self.rank :: self.world_size]
+
+    def predict_dataloader(self):
+        ds = self.data_predict
+        idx = self._rank_indices()
+        bs = self.batch_size_per_device
+        tok = self.tokenizer
+        for b0 in range(0, len(idx), bs):
+            sel = idx[b0 : b0 + bs]
+            names = [ds.names[i] for i in sel]
+            seqs = [ds.seqs[i] for i in sel]
+            ns = tok.num_special_tokens
+            T = max(len(s) for s in seqs) + ns
+            id_rows = np.array([encode_read_name(n) for n in names], dtype=np.int64).astype(np.int8)
+            batch = {"id": torch.from_numpy(id_rows), "labels": torch.full((len(sel),), -1, dtype=torch.int64),
+                     "names": names, "indices": sel}
+            if self.engine is not None:
+                offsets = np.zeros(len(seqs) + 1, dtype=np.int64)
+                np.cumsum([len(s) for s in seqs], out=offsets[1:])
+                flat = np.concatenate(seqs) if offsets[-1] else np.zeros(1, np.uint8)
+                bases = torch.from_numpy(flat).pin_memory()
+                offs = torch.from_numpy(offsets).pin_memory()
+                ids, _ = self.engine.encode(bases.to(self.engine.device, non_blocking=True),
+                                            offs.to(self.engine.device, non_blocking=True), T, add_cls=tok.add_cls,
+                                            add_sep=tok.add_sep, pad_left=tok.padding_side == "left",
+                                            max_bases=tok.max_len_single_sentence - ns)
+                batch["input_ids"] = ids
+            else:
+                feats = [{"input_ids": tok.encode_array(s.tobytes(), max_length=tok.max_len_single_sentence)} for s in seqs]
+                batch["input_ids"] = tok.pad(feats, return_tensors="pt")["input_ids"]
+            yield batch
+
+
+class Trainer:
+    """The slice of `lightning.Trainer` that `chimeralm predict` uses (chimeralm/__main__.py:307-317)."""
+
+    def __init__(self, accelerator="gpu", devices=1, callbacks=None, deterministic=True, logger=False, rank: int = 0,
+                 world_size: int = 1):
+        self.callbacks = list(callbacks or [])
+        self.global_rank, self.world_size = rank, world_size
+
+    def predict(self, model, dataloaders=None, return_predictions: bool = False, ckpt_path=None):
+        from .weights import load_checkpoint
+
+        if ckpt_path is not None:
+            model.load_state_dict(load_checkpoint(ckpt_path))
+            if hasattr(dataloaders, "engine") and dataloaders.engine is not None:
+                dataloaders.engine = model.engine
+        dm = dataloaders
+        if hasattr(dm, "setup"):
+            dm.rank, dm.world_size = self.global_rank, self.world_size
+            dm.setup("predict")
+            loader = dm.predict_dataloader()
+        else:
+            loader = dm
+        model.eval()
+        results = []
+        for batch_idx, batch in enumerate(loader):
+            pred = model.predict_step(batch, batch_idx)
+            for cb in self.callbacks:
+                cb.write_on_batch_end(self, model, pred, None, batch, batch_idx, 0)
+            if return_predictions or self.world_size > 1:
+                results.append((batch.get("indices"), pred[2].cpu() if len(pred) > 2 else pred[0].argmax(1).cpu()))
+        self.last_results = results
+        return results if return_predictions else None
