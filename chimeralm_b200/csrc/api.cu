@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "../../include/chimeralm_b200.h"
+#include "block_mlp.cuh"
 #include "gemm_tcgen05.cuh"
 #include "kernels.cuh"
 #include "longconv.cuh"
@@ -84,6 +85,7 @@ struct clm_ctx {
   size_t prof_used = 0;           // event pairs in flight
   double prof_ms[32] = {0};
   long long prof_n[32] = {0};
+  bool fused_mlp = true;  // out_proj+res+LN2+fc1+gelu+fc2+res in one kernel
   // debug
   int dbg_layer = -1, dbg_stage = -1;
   long long launches = 0;
@@ -208,6 +210,26 @@ int launch_gemm(clm_ctx* c, const void* A, const CUtensorMap& tmB, const GemmPar
   }
 }
 
+int launch_block_mlp(clm_ctx* c, int layer, const __nv_bfloat16* y, float* res, int M, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    CLM_CUDA(c, cudaFuncSetAttribute(block_mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bm::SMEM_TOTAL));
+    attr_set = true;
+  }
+  LayerW& L = c->layers[layer];
+  CUtensorMap tmY;
+  int rc = make_tmap_bf16_2d(c, &tmY, y, (uint64_t)M, (uint64_t)c->cfg.d_model, 128);
+  if (rc) return rc;
+  BlockMlpParams p{};
+  p.M = M; p.res = res; p.b_out = L.out_b; p.ln_g = L.ln2_g; p.ln_b = L.ln2_b; p.b1 = L.fc1_b; p.b2 = L.fc2_b;
+  p.eps = c->cfg.layer_norm_eps;
+  p.num_tiles = (M + bm::BM - 1) / bm::BM;
+  const int grid = std::min(p.num_tiles, c->num_sms);
+  block_mlp_kernel<<<grid, bm::THREADS, bm::SMEM_TOTAL, st>>>(tmY, L.tm_out, L.tm_fc1, L.tm_fc2, p);
+  CLM_LAUNCH_CHECK(c, "block_mlp");
+  return 0;
+}
+
 // ---- long convolution dispatch -------------------------------------------------------------
 struct ConvPlan {
   int logn, n_chunks;
@@ -297,10 +319,10 @@ int launch_longconv(clm_ctx* c, int layer, const __nv_bfloat16* vx, const __nv_b
 int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
 enum ProfCat { PC_ENCODE = 0, PC_EMBED, PC_LN, PC_GEMM_IN, PC_SHORTCONV, PC_LONGCONV, PC_TRANSPOSE, PC_GEMM_OUT,
-               PC_GEMM_FC1, PC_GEMM_FC2, PC_SCORE, PC_POOL, PC_HEAD, PC_COUNT };
+               PC_GEMM_FC1, PC_GEMM_FC2, PC_SCORE, PC_POOL, PC_HEAD, PC_BLOCK_MLP, PC_COUNT };
 const char* kProfNames[PC_COUNT] = {"encode", "embed", "layernorm", "gemm_in_proj", "shortconv_gate", "longconv",
                                     "transpose", "gemm_out_proj", "gemm_fc1", "gemm_fc2", "gemm_score", "pool",
-                                    "head"};
+                                    "head", "block_mlp"};
 
 struct ProfScope {
   clm_ctx* c;
@@ -630,24 +652,29 @@ int clm_forward(clm_ctx* c, const void* d_ids, int ids_dtype, int B, int T, floa
     transpose_ct_kernel<<<dim3((T + 63) / 64, D / 64, B), 256, 0, st>>>(c->Y, c->YT, T, Tp, D);
     CLM_LAUNCH_CHECK(c, "transpose_ct"); }
     STOP_AFTER(l, 5);
+    if (c->fused_mlp && c->dbg_layer != l) {
+      ProfScope ps_(c, PC_BLOCK_MLP, st);
+      if ((rc = launch_block_mlp(c, l, c->YT, c->R, (int)M, st))) return rc;
+    } else {
     p = GemmParams{};
-    p.M = (int)M; p.N = D; p.K = D; p.bias = L.out_b; p.out = c->R; p.res = c->R; p.ldo = D;
-    { ProfScope ps_(c, PC_GEMM_OUT, st);
-    if ((rc = launch_gemm(c, c->YT, L.tm_out, p, EPI_BIAS_RES_F32, st))) return rc; }
-    STOP_AFTER(l, 6);
-    { ProfScope ps_(c, PC_LN, st);
-    layernorm_bf16_kernel<<<rows8, 256, 0, st>>>(c->R, L.ln2_g, L.ln2_b, c->XN, M, g.layer_norm_eps);
-    CLM_LAUNCH_CHECK(c, "ln2"); }
-    STOP_AFTER(l, 7);
-    p = GemmParams{};
-    p.M = (int)M; p.N = g.d_inner; p.K = D; p.bias = L.fc1_b; p.out = c->U; p.ldo = g.d_inner;
-    { ProfScope ps_(c, PC_GEMM_FC1, st);
-    if ((rc = launch_gemm(c, c->XN, L.tm_fc1, p, EPI_BIAS_GELU_TANH, st))) return rc; }
-    STOP_AFTER(l, 8);
-    p = GemmParams{};
-    p.M = (int)M; p.N = D; p.K = g.d_inner; p.bias = L.fc2_b; p.out = c->R; p.res = c->R; p.ldo = D;
-    { ProfScope ps_(c, PC_GEMM_FC2, st);
-    if ((rc = launch_gemm(c, c->U, L.tm_fc2, p, EPI_BIAS_RES_F32, st))) return rc; }
+      p.M = (int)M; p.N = D; p.K = D; p.bias = L.out_b; p.out = c->R; p.res = c->R; p.ldo = D;
+      { ProfScope ps_(c, PC_GEMM_OUT, st);
+      if ((rc = launch_gemm(c, c->YT, L.tm_out, p, EPI_BIAS_RES_F32, st))) return rc; }
+      STOP_AFTER(l, 6);
+      { ProfScope ps_(c, PC_LN, st);
+      layernorm_bf16_kernel<<<rows8, 256, 0, st>>>(c->R, L.ln2_g, L.ln2_b, c->XN, M, g.layer_norm_eps);
+      CLM_LAUNCH_CHECK(c, "ln2"); }
+      STOP_AFTER(l, 7);
+      p = GemmParams{};
+      p.M = (int)M; p.N = g.d_inner; p.K = D; p.bias = L.fc1_b; p.out = c->U; p.ldo = g.d_inner;
+      { ProfScope ps_(c, PC_GEMM_FC1, st);
+      if ((rc = launch_gemm(c, c->XN, L.tm_fc1, p, EPI_BIAS_GELU_TANH, st))) return rc; }
+      STOP_AFTER(l, 8);
+      p = GemmParams{};
+      p.M = (int)M; p.N = D; p.K = g.d_inner; p.bias = L.fc2_b; p.out = c->R; p.res = c->R; p.ldo = D;
+      { ProfScope ps_(c, PC_GEMM_FC2, st);
+      if ((rc = launch_gemm(c, c->U, L.tm_fc2, p, EPI_BIAS_RES_F32, st))) return rc; }
+    }
     STOP_AFTER(l, 9);
   }
   const int NL = g.n_layer;
@@ -710,6 +737,20 @@ int clm_gemm(clm_ctx* c, const void* d_A, const void* d_W, const float* d_bias, 
   GemmParams p{};
   p.M = M; p.N = N; p.K = K; p.bias = d_bias; p.out = d_out; p.res = d_res; p.w2 = d_w2; p.b2 = b2; p.score = d_score; p.ldo = N;
   return launch_gemm(c, d_A, tmB, p, epi, (cudaStream_t)stream);
+}
+
+int clm_set_option(clm_ctx* c, const char* name, int value) {
+  if (!c || !name) return CLM_ERR_INVALID;
+  const std::string n(name);
+  if (n == "fused_mlp") c->fused_mlp = value != 0;
+  else return fail(c, CLM_ERR_INVALID, "clm_set_option: unknown option '%s'", name);
+  return 0;
+}
+
+int clm_block_mlp(clm_ctx* c, int layer, const void* d_y, float* d_res, int M, void* stream) {
+  if (!c || !c->finalized) return fail(c, CLM_ERR_STATE, "clm_block_mlp before clm_finalize");
+  if (layer < 0 || layer >= c->cfg.n_layer || !d_y || !d_res || M <= 0) return fail(c, CLM_ERR_INVALID, "clm_block_mlp: bad argument");
+  return launch_block_mlp(c, layer, (const __nv_bfloat16*)d_y, d_res, M, (cudaStream_t)stream);
 }
 
 int clm_longconv(clm_ctx* c, int layer, const void* d_vx, const void* d_x0, void* d_out, int B, int T, int Tp,

@@ -1,0 +1,390 @@
+// Fused second half of a HyenaDNA block, one persistent kernel (SURVEY.md A.3 tail + A.6):
+//
+//   r1  = y * Wout^T + b_out + res                 (HyenaOperator.out_proj + residual)
+//   xn  = LayerNorm2(r1)
+//   h   = gelu_tanh(xn * W1^T + b1)                (HyenaMlp.fc1)
+//   out = h * W2^T + b2 + r1                       (HyenaMlp.fc2 + residual)       -> res (fp32)
+//
+// Replaces 4 reference ops (nn.Linear x3, nn.LayerNorm, F.gelu) and keeps r1, xn and the
+// 1024-wide hidden activations on chip: per token the kernel reads 512 B (y, bf16) + 1 KB
+// (res) and writes 1 KB (res), instead of ~9.2 KB for the unfused sequence.
+//
+// One CTA per SM loops over tiles of 128 tokens.  All three GEMMs run on tcgen05 with the
+// accumulators in TMEM:
+//   cols [0,256)    R : out_proj accumulator, rewritten in place by the epilogue as r1 + b2 and
+//                       then used as the fc2 accumulator (so the fc2 result already carries the
+//                       residual and bias)
+//   cols [256,512)  H0/H1 : fc1 output in two 128-column buffers, double-buffered against the
+//                       GELU epilogue
+// Shared memory (224 KB): X (64 KB: y tile, later xn in the same UMMA layout), HB (2 x 32 KB:
+// gelu(h) chunks as the A operand of fc2), W ring (3 x 32 KB weight tiles streamed by TMA from
+// L2 in exactly the order the MMA thread consumes them).
+//
+// Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc), warps 2..9 = epilogue
+// (TMEM lane quarter = warp % 4, column half = (warp - 2) / 4).
+#pragma once
+#include <cuda_bf16.h>
+
+#include "gemm_tcgen05.cuh"
+#include "ptx.cuh"
+
+namespace clm {
+
+struct BlockMlpParams {
+  int M;                 // tokens
+  float* res;            // [M,256] fp32, read and overwritten
+  const float* b_out;    // [256]
+  const float* ln_g;     // [256]
+  const float* ln_b;     // [256]
+  const float* b1;       // [1024]
+  const float* b2;       // [256]
+  float eps;
+  int num_tiles;
+};
+
+namespace bm {
+constexpr int D = 256, DI = 1024, BM = 128, BK = 64;
+constexpr int KB_BYTES = BM * BK * 2;            // 16 KB: one [128 x 64] bf16 tile
+constexpr int X_BYTES = 4 * KB_BYTES;            // 64 KB
+constexpr int HB_BYTES = 2 * KB_BYTES;           // 32 KB per buffer
+constexpr int SLOT_BYTES = 2 * KB_BYTES;         // 32 KB
+constexpr int NSLOT = 3;
+constexpr int OFF_X = 0;
+constexpr int OFF_HB = OFF_X + X_BYTES;
+constexpr int OFF_W = OFF_HB + 2 * HB_BYTES;
+constexpr int OFF_BAR = OFF_W + NSLOT * SLOT_BYTES;   // 229376
+constexpr int OFF_PART = OFF_BAR + 256;               // LayerNorm partial sums [2][2][128] fp32
+constexpr int SMEM_TOTAL = OFF_PART + 2 * 2 * BM * 4; // 231680 <= 232448 (227 KB)
+constexpr int THREADS = 320;
+constexpr int EPI_THREADS = 256;
+constexpr int NCHUNK = DI / 128;                 // 8 fc1 column chunks
+constexpr uint32_t TM_R = 0, TM_H = 256;
+
+__device__ __forceinline__ float gelu_tanh_fast(float x) {
+  // x * sigmoid(2u), u = sqrt(2/pi) (x + 0.044715 x^3)  ==  0.5 x (1 + tanh(u))
+  const float u2 = 1.5957691216057308f * (x + 0.044715f * x * x * x);
+  return __fdividef(x, 1.0f + __expf(-u2));
+}
+}  // namespace bm
+
+__global__ void __launch_bounds__(bm::THREADS, 1)
+block_mlp_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmWout,
+                 const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2, BlockMlpParams p) {
+  using namespace bm;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((ptx::smem_u32(smem) & 1023u) != 0) __trap();  // swizzled UMMA/TMA tiles need 1 KB alignment
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
+  uint64_t* w_full = bars;                 // [3]
+  uint64_t* w_empty = bars + 3;            // [3]
+  uint64_t* x_full = bars + 6;             // y tile landed in X
+  uint64_t* x_free = bars + 7;             // X no longer read by the tensor core (after fc1 chunk 7)
+  uint64_t* g1_done = bars + 8;            // out_proj accumulator complete
+  uint64_t* xn_full = bars + 9;            // epilogue wrote xn into X and r1+b2 into R
+  uint64_t* hacc_full = bars + 10;         // [2] fc1 chunk accumulator complete
+  uint64_t* hacc_free = bars + 12;         // [2] epilogue drained the fc1 chunk accumulator
+  uint64_t* hbuf_full = bars + 14;         // [2] gelu(h) chunk written to HB
+  uint64_t* hbuf_free = bars + 16;         // [2] fc2 finished reading HB
+  uint64_t* out_full = bars + 18;          // fc2 accumulator complete
+  uint64_t* r_free = bars + 19;            // epilogue drained R
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 20);
+  float (*s_part)[2][BM] = reinterpret_cast<float (*)[2][BM]>(smem + OFF_PART);  // [half][sum|sumsq][row]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmY); ptx::prefetch_tmap(&tmWout); ptx::prefetch_tmap(&tmW1); ptx::prefetch_tmap(&tmW2);
+    for (int i = 0; i < NSLOT; ++i) { ptx::mbar_init(&w_full[i], 1); ptx::mbar_init(&w_empty[i], 1); }
+    ptx::mbar_init(x_full, 1); ptx::mbar_init(x_free, 1); ptx::mbar_init(g1_done, 1);
+    ptx::mbar_init(xn_full, 8);
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&hacc_full[i], 1); ptx::mbar_init(&hacc_free[i], 8);
+      ptx::mbar_init(&hbuf_full[i], 8); ptx::mbar_init(&hbuf_free[i], 1);
+    }
+    ptx::mbar_init(out_full, 1); ptx::mbar_init(r_free, 8);
+    ptx::fence_mbar_init();
+  } else if (warp == 1) {
+    ptx::tmem_alloc<512>(tmem_ptr);
+  }
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  ptx::tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // =========================== TMA producer ===========================
+    if (lane == 0) {
+      uint32_t wi = 0;  // running weight-slot counter
+      auto slot_acquire = [&]() -> uint8_t* {
+        const uint32_t s = wi % NSLOT, ph = (wi / NSLOT) & 1;
+        ptx::mbar_wait(&w_empty[s], ph ^ 1);
+        ptx::mbar_expect_tx(&w_full[s], SLOT_BYTES);
+        return smem + OFF_W + s * SLOT_BYTES;
+      };
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+        const int m0 = tile * BM;
+        ptx::mbar_wait(x_free, (it & 1) ^ 1);
+        ptx::mbar_expect_tx(x_full, X_BYTES);
+        for (int kb = 0; kb < 4; ++kb) ptx::tma_load_2d(smem + OFF_X + kb * KB_BYTES, &tmY, x_full, kb * BK, m0);
+        // out_proj weights: 4 k-blocks of [256 x 64]
+        for (int kb = 0; kb < 4; ++kb) {
+          uint8_t* s = slot_acquire();
+          const uint32_t sl = wi % NSLOT;
+          ptx::tma_load_2d(s, &tmWout, &w_full[sl], kb * BK, 0);
+          ptx::tma_load_2d(s + KB_BYTES, &tmWout, &w_full[sl], kb * BK, 128);
+          ++wi;
+        }
+        for (int j = 0; j <= NCHUNK; ++j) {
+          if (j < NCHUNK) {  // fc1 chunk j: rows [128 j, +128), 4 k-blocks, two per slot
+            for (int h2 = 0; h2 < 2; ++h2) {
+              uint8_t* s = slot_acquire();
+              const uint32_t sl = wi % NSLOT;
+              ptx::tma_load_2d(s, &tmW1, &w_full[sl], (2 * h2) * BK, j * 128);
+              ptx::tma_load_2d(s + KB_BYTES, &tmW1, &w_full[sl], (2 * h2 + 1) * BK, j * 128);
+              ++wi;
+            }
+          }
+          if (j >= 1) {  // fc2 K-chunk j-1: columns [128 (j-1), +128) = 2 k-blocks of [256 x 64]
+            const int jj = j - 1;
+            for (int kb = 0; kb < 2; ++kb) {
+              uint8_t* s = slot_acquire();
+              const uint32_t sl = wi % NSLOT;
+              ptx::tma_load_2d(s, &tmW2, &w_full[sl], jj * 128 + kb * BK, 0);
+              ptx::tma_load_2d(s + KB_BYTES, &tmW2, &w_full[sl], jj * 128 + kb * BK, 128);
+              ++wi;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =========================== MMA issuer ===========================
+    if (lane == 0) {
+      constexpr uint32_t idesc256 = ptx::idesc_bf16_f32(BM, 256);
+      constexpr uint32_t idesc128 = ptx::idesc_bf16_f32(BM, 128);
+      const uint32_t sX = ptx::smem_u32(smem + OFF_X);
+      const uint32_t sHB = ptx::smem_u32(smem + OFF_HB);
+      const uint32_t sW = ptx::smem_u32(smem + OFF_W);
+      uint32_t wi = 0;
+      auto slot_wait = [&]() -> uint32_t {
+        const uint32_t s = wi % NSLOT, ph = (wi / NSLOT) & 1;
+        ptx::mbar_wait(&w_full[s], ph);
+        ptx::tc_fence_after_sync();
+        return sW + s * SLOT_BYTES;
+      };
+      auto slot_release = [&]() {
+        ptx::umma_commit(&w_empty[wi % NSLOT]);
+        ++wi;
+      };
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+        const uint32_t tph = it & 1;
+        // ---- G1: R = y * Wout^T
+        ptx::mbar_wait(r_free, tph ^ 1);     // previous tile's output drained from R
+        ptx::mbar_wait(x_full, tph);
+        ptx::tc_fence_after_sync();
+        for (int kb = 0; kb < 4; ++kb) {
+          const uint32_t sw = slot_wait();
+          const uint64_t da = ptx::smem_desc_k_sw128(sX + kb * KB_BYTES);
+          const uint64_t db = ptx::smem_desc_k_sw128(sw);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) ptx::umma_f16(tmem_base + TM_R, da + 2 * k, db + 2 * k, idesc256, (kb | k) != 0);
+          slot_release();
+        }
+        ptx::umma_commit(g1_done);
+        // ---- fc1 / fc2 software pipeline
+        for (int j = 0; j <= NCHUNK; ++j) {
+          if (j < NCHUNK) {
+            const uint32_t b = j & 1, u = it * 4 + (j >> 1);
+            if (j == 0) { ptx::mbar_wait(xn_full, tph); }
+            ptx::mbar_wait(&hacc_free[b], (u & 1) ^ 1);
+            ptx::tc_fence_after_sync();
+            for (int h2 = 0; h2 < 2; ++h2) {
+              const uint32_t sw = slot_wait();
+#pragma unroll
+              for (int q = 0; q < 2; ++q) {
+                const int kb = 2 * h2 + q;
+                const uint64_t da = ptx::smem_desc_k_sw128(sX + kb * KB_BYTES);
+                const uint64_t db = ptx::smem_desc_k_sw128(sw + q * KB_BYTES);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                  ptx::umma_f16(tmem_base + TM_H + b * 128, da + 2 * k, db + 2 * k, idesc128, (kb | k) != 0);
+              }
+              slot_release();
+            }
+            ptx::umma_commit(&hacc_full[b]);
+            if (j == NCHUNK - 1) ptx::umma_commit(x_free);  // X (xn) not needed by later MMAs of this tile
+          }
+          if (j >= 1) {
+            const int jj = j - 1;
+            const uint32_t b = jj & 1, u = it * 4 + (jj >> 1);
+            ptx::mbar_wait(&hbuf_full[b], u & 1);
+            ptx::tc_fence_after_sync();
+            for (int kb = 0; kb < 2; ++kb) {
+              const uint32_t sw = slot_wait();
+              const uint64_t da = ptx::smem_desc_k_sw128(sHB + b * HB_BYTES + kb * KB_BYTES);
+              const uint64_t db = ptx::smem_desc_k_sw128(sw);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) ptx::umma_f16(tmem_base + TM_R, da + 2 * k, db + 2 * k, idesc256, 1u);
+              slot_release();
+            }
+            ptx::umma_commit(&hbuf_free[b]);
+          }
+        }
+        ptx::umma_commit(out_full);
+      }
+    }
+  } else {
+    // =========================== epilogue warps ===========================
+    const int e = warp - 2;
+    const int q = warp & 3;          // TMEM lane quarter this warp may access
+    const int hf = e >> 2;           // column half
+    const int r = q * 32 + lane;     // row inside the tile
+    const uint32_t lane_addr = tmem_base + (uint32_t(q * 32) << 16);
+    const uint32_t sX = ptx::smem_u32(smem + OFF_X);
+    const uint32_t sHB = ptx::smem_u32(smem + OFF_HB);
+    const uint32_t swz = uint32_t(r & 7);
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      const uint32_t tph = it & 1;
+      const long long row = (long long)tile * BM + r;
+      const bool row_ok = row < p.M;
+      float* res_row = p.res + row * D;
+      // ------------------------------------------------ E1: r1, LayerNorm2 -> xn
+      ptx::mbar_wait(g1_done, tph);
+      ptx::tc_fence_after_sync();
+      float s1 = 0.f, s2 = 0.f;
+#pragma unroll 1
+      for (int c0 = 0; c0 < 128; c0 += 32) {
+        const int col = hf * 128 + c0;
+        uint32_t a[32];
+        ptx::tmem_ld_32x32b_x32(lane_addr + TM_R + col, a);
+        float4 rs[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          rs[j] = row_ok ? *reinterpret_cast<const float4*>(res_row + col + 4 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 bo = __ldg(reinterpret_cast<const float4*>(p.b_out + col) + j);
+          const float4 b2 = __ldg(reinterpret_cast<const float4*>(p.b2 + col) + j);
+          const float v0 = __uint_as_float(a[4 * j + 0]) + bo.x + rs[j].x;
+          const float v1 = __uint_as_float(a[4 * j + 1]) + bo.y + rs[j].y;
+          const float v2 = __uint_as_float(a[4 * j + 2]) + bo.z + rs[j].z;
+          const float v3 = __uint_as_float(a[4 * j + 3]) + bo.w + rs[j].w;
+          s1 += (v0 + v1) + (v2 + v3);
+          s2 += (v0 * v0 + v1 * v1) + (v2 * v2 + v3 * v3);
+          a[4 * j + 0] = __float_as_uint(v0 + b2.x);
+          a[4 * j + 1] = __float_as_uint(v1 + b2.y);
+          a[4 * j + 2] = __float_as_uint(v2 + b2.z);
+          a[4 * j + 3] = __float_as_uint(v3 + b2.w);
+        }
+        ptx::tmem_st_32x32b_x32(lane_addr + TM_R + col, a);
+      }
+      ptx::tmem_st_wait();
+      s_part[hf][0][r] = s1;
+      s_part[hf][1][r] = s2;
+      ptx::bar_sync(1, EPI_THREADS);
+      const float ts1 = s_part[0][0][r] + s_part[1][0][r];
+      const float ts2 = s_part[0][1][r] + s_part[1][1][r];
+      const float mean = ts1 * (1.0f / D);
+      const float var = fmaxf(ts2 * (1.0f / D) - mean * mean, 0.f);
+      const float rstd = rsqrtf(var + p.eps);
+#pragma unroll 1
+      for (int c0 = 0; c0 < 128; c0 += 32) {
+        const int col = hf * 128 + c0;
+        uint32_t a[32];
+        ptx::tmem_ld_32x32b_x32(lane_addr + TM_R + col, a);
+        ptx::tmem_ld_wait();
+        const int kb = col >> 6;
+        const uint32_t rowaddr = sX + kb * KB_BYTES + r * 128;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {  // 4 chunks of 8 columns = 16 bytes each
+          float x[8];
+#pragma unroll
+          for (int j = 0; j < 8; j += 4) {
+            const int cc = col + g * 8 + j;
+            const float4 b2 = __ldg(reinterpret_cast<const float4*>(p.b2 + cc));
+            const float4 gg = __ldg(reinterpret_cast<const float4*>(p.ln_g + cc));
+            const float4 bb = __ldg(reinterpret_cast<const float4*>(p.ln_b + cc));
+            x[j + 0] = (__uint_as_float(a[g * 8 + j + 0]) - b2.x - mean) * rstd * gg.x + bb.x;
+            x[j + 1] = (__uint_as_float(a[g * 8 + j + 1]) - b2.y - mean) * rstd * gg.y + bb.y;
+            x[j + 2] = (__uint_as_float(a[g * 8 + j + 2]) - b2.z - mean) * rstd * gg.z + bb.z;
+            x[j + 3] = (__uint_as_float(a[g * 8 + j + 3]) - b2.w - mean) * rstd * gg.w + bb.w;
+          }
+          const uint32_t chunk = uint32_t(((col & 63) >> 3) + g) ^ swz;
+          ptx::st_shared_v4(rowaddr + chunk * 16, pack_bf16(x[0], x[1]), pack_bf16(x[2], x[3]), pack_bf16(x[4], x[5]),
+                            pack_bf16(x[6], x[7]));
+        }
+      }
+      ptx::fence_proxy_async_smem();
+      ptx::tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(xn_full);
+      // ------------------------------------------------ E2: gelu(fc1 chunk) -> HB
+#pragma unroll 1
+      for (int j = 0; j < NCHUNK; ++j) {
+        const uint32_t b = j & 1, u = it * 4 + (j >> 1);
+        ptx::mbar_wait(&hacc_full[b], u & 1);
+        ptx::tc_fence_after_sync();
+        uint32_t a0[32], a1[32];
+        ptx::tmem_ld_32x32b_x32(lane_addr + TM_H + b * 128 + hf * 64, a0);
+        ptx::tmem_ld_32x32b_x32(lane_addr + TM_H + b * 128 + hf * 64 + 32, a1);
+        ptx::tmem_ld_wait();
+        ptx::tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&hacc_free[b]);
+        ptx::mbar_wait(&hbuf_free[b], (u & 1) ^ 1);
+        const float* b1p = p.b1 + j * 128 + hf * 64;
+        const uint32_t rowaddr = sHB + b * HB_BYTES + hf * KB_BYTES + r * 128;
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          const uint32_t* src = (g < 4) ? &a0[g * 8] : &a1[(g - 4) * 8];
+          float x[8];
+#pragma unroll
+          for (int jj = 0; jj < 8; jj += 4) {
+            const float4 bv = __ldg(reinterpret_cast<const float4*>(b1p + g * 8 + jj));
+            x[jj + 0] = gelu_tanh_fast(__uint_as_float(src[jj + 0]) + bv.x);
+            x[jj + 1] = gelu_tanh_fast(__uint_as_float(src[jj + 1]) + bv.y);
+            x[jj + 2] = gelu_tanh_fast(__uint_as_float(src[jj + 2]) + bv.z);
+            x[jj + 3] = gelu_tanh_fast(__uint_as_float(src[jj + 3]) + bv.w);
+          }
+          const uint32_t chunk = uint32_t(g) ^ swz;
+          ptx::st_shared_v4(rowaddr + chunk * 16, pack_bf16(x[0], x[1]), pack_bf16(x[2], x[3]), pack_bf16(x[4], x[5]),
+                            pack_bf16(x[6], x[7]));
+        }
+        ptx::fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&hbuf_full[b]);
+      }
+      // ------------------------------------------------ E3: out = R -> res
+      ptx::mbar_wait(out_full, tph);
+      ptx::tc_fence_after_sync();
+#pragma unroll 1
+      for (int c0 = 0; c0 < 128; c0 += 32) {
+        const int col = hf * 128 + c0;
+        uint32_t a[32];
+        ptx::tmem_ld_32x32b_x32(lane_addr + TM_R + col, a);
+        ptx::tmem_ld_wait();
+        if (row_ok) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<float4*>(res_row + col + 4 * j) =
+                make_float4(__uint_as_float(a[4 * j]), __uint_as_float(a[4 * j + 1]), __uint_as_float(a[4 * j + 2]),
+                            __uint_as_float(a[4 * j + 3]));
+        }
+      }
+      ptx::tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(r_free);
+    }
+  }
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after_sync();
+    ptx::tmem_dealloc<512>(tmem_base);
+  }
+}
+
+}  // namespace clm

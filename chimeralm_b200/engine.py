@@ -177,6 +177,17 @@ class Engine:
         self._check(rc, "clm_gemm")
         return out
 
+    def block_mlp(self, layer: int, y: torch.Tensor, res: torch.Tensor) -> torch.Tensor:
+        """In-place fused block tail on `res` (fp32 [M,256]) from y (bf16 [M,256])."""
+        M = y.shape[0]
+        rc = self.lib.clm_block_mlp(self.ctx, layer, C.c_void_p(y.data_ptr()), C.c_void_p(res.data_ptr()), M,
+                                    _stream_ptr(self.device))
+        self._check(rc, "clm_block_mlp")
+        return res
+
+    def set_option(self, name: str, value: int) -> None:
+        self._check(self.lib.clm_set_option(self.ctx, name.encode(), int(value)), "clm_set_option")
+
     def longconv(self, layer: int, vx: torch.Tensor, x0: torch.Tensor, T: int):
         B, D, Tp = vx.shape
         out = torch.zeros_like(vx)

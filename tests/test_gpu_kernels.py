@@ -99,3 +99,25 @@ def test_encode(engine):
                                   max_bases=max_len - 1 - int(add_cls))
         assert ids.cpu().tolist() == padded
         assert lens.cpu().tolist() == [len(x) for x in ids_ref]
+
+
+@pytest.mark.parametrize("M", [128, 1000, 148 * 128 * 2 + 77])
+def test_block_mlp_fused(engine, state_dict, M):
+    """Fused out_proj+res+LN2+fc1+gelu+fc2+res kernel vs the same ops in fp32 torch (bf16 weights)."""
+    from oracle import hyena_oracle as O
+
+    layer = 2
+    p = f"{O.BB}layers.{layer}."
+    g = torch.Generator().manual_seed(M)
+    y = _rand_bf16((M, 256), g)
+    res = torch.randn(M, 256, generator=g)
+    q = lambda w: w.to(torch.bfloat16).float()
+    sd = state_dict
+    r1 = y.float() @ q(sd[p + "mixer.out_proj.weight"]).T + sd[p + "mixer.out_proj.bias"] + res
+    xn = F.layer_norm(r1, (256,), sd[p + "norm2.weight"], sd[p + "norm2.bias"], 1e-5).to(torch.bfloat16).float()
+    h = F.gelu(xn @ q(sd[p + "mlp.fc1.weight"]).T + sd[p + "mlp.fc1.bias"], approximate="tanh").to(torch.bfloat16).float()
+    ref = h @ q(sd[p + "mlp.fc2.weight"]).T + sd[p + "mlp.fc2.bias"] + r1
+    out = engine.block_mlp(layer, y.cuda(), res.cuda().clone())
+    torch.cuda.synchronize()
+    err = (out.cpu() - ref).abs().max().item()
+    assert err <= 2e-2, (M, err)
