@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "../../include/chimeralm_b200.h"
+#include "block_in.cuh"
 #include "block_mlp.cuh"
 #include "gemm_tcgen05.cuh"
 #include "kernels.cuh"
@@ -33,6 +34,10 @@ struct LayerW {
   const float *sc_w, *sc_b, *fbias;
   __nv_bfloat16 *in_w, *out_w, *fc1_w, *fc2_w;
   CUtensorMap tm_in, tm_out, tm_fc1, tm_fc2;
+  // LayerNorm1 affine folded into in_proj (block_in kernel): W' = W diag(gamma), b' = b + W beta
+  __nv_bfloat16* in_wf = nullptr;
+  float* in_bf = nullptr;
+  CUtensorMap tm_inf;
   float* k = nullptr;                               // [D][Lk]
   float2* gspec[LONGCONV_MAX_LOGN + 1] = {nullptr};  // per LOGN: [n_seg][D][N]
 };
@@ -86,6 +91,7 @@ struct clm_ctx {
   double prof_ms[32] = {0};
   long long prof_n[32] = {0};
   bool fused_mlp = true;  // out_proj+res+LN2+fc1+gelu+fc2+res in one kernel
+  bool fused_in = true;   // LN1+in_proj+short conv+gate in one kernel
   // debug
   int dbg_layer = -1, dbg_stage = -1;
   long long launches = 0;
@@ -210,7 +216,43 @@ int launch_gemm(clm_ctx* c, const void* A, const CUtensorMap& tmB, const GemmPar
   }
 }
 
-int launch_block_mlp(clm_ctx* c, int layer, const __nv_bfloat16* y, float* res, int M, cudaStream_t st) {
+int make_tmap_ct_bf16_3d(clm_ctx* c, CUtensorMap* tm, const void* base, int B, int D, int Tp) {
+  cuuint64_t dims[3] = {(cuuint64_t)Tp, (cuuint64_t)D, (cuuint64_t)B};
+  cuuint64_t strides[2] = {(cuuint64_t)Tp * 2, (cuuint64_t)Tp * D * 2};
+  cuuint32_t box[3] = {64, 128, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = c->encode_tiled(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box,
+                               estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(c, CLM_ERR_CUDA, "cuTensorMapEncodeTiled(3d) failed with CUresult %d", (int)r);
+  return 0;
+}
+
+int launch_block_in(clm_ctx* c, int layer, const float* res, int B, int T, int Tp, __nv_bfloat16* vx,
+                    __nv_bfloat16* x0, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    CLM_CUDA(c, cudaFuncSetAttribute(block_in_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bi::SMEM_TOTAL));
+    attr_set = true;
+  }
+  LayerW& L = c->layers[layer];
+  CUtensorMap tmVX, tmX0;
+  int rc;
+  if ((rc = make_tmap_ct_bf16_3d(c, &tmVX, vx, B, c->cfg.d_model, Tp))) return rc;
+  if ((rc = make_tmap_ct_bf16_3d(c, &tmX0, x0, B, c->cfg.d_model, Tp))) return rc;
+  BlockInParams p{};
+  p.res = res; p.b_in = L.in_bf; p.cw = L.sc_w; p.cb = L.sc_b; p.eps = c->cfg.layer_norm_eps;
+  p.B = B; p.T = T;
+  p.tiles_per_seq = (T + bi::BT - 1) / bi::BT;
+  p.num_tiles = B * p.tiles_per_seq;
+  const int grid = std::min(p.num_tiles, c->num_sms);
+  block_in_kernel<<<grid, bi::THREADS, bi::SMEM_TOTAL, st>>>(L.tm_inf, tmVX, tmX0, p);
+  CLM_LAUNCH_CHECK(c, "block_in");
+  return 0;
+}
+
+int launch_block_mlp(clm_ctx* c, int layer, const __nv_bfloat16* y, float* res, int M, cudaStream_t st,
+                     long long* trace = nullptr) {
   static bool attr_set = false;
   if (!attr_set) {
     CLM_CUDA(c, cudaFuncSetAttribute(block_mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bm::SMEM_TOTAL));
@@ -224,6 +266,7 @@ int launch_block_mlp(clm_ctx* c, int layer, const __nv_bfloat16* y, float* res, 
   p.M = M; p.res = res; p.b_out = L.out_b; p.ln_g = L.ln2_g; p.ln_b = L.ln2_b; p.b1 = L.fc1_b; p.b2 = L.fc2_b;
   p.eps = c->cfg.layer_norm_eps;
   p.num_tiles = (M + bm::BM - 1) / bm::BM;
+  p.trace = trace;
   const int grid = std::min(p.num_tiles, c->num_sms);
   block_mlp_kernel<<<grid, bm::THREADS, bm::SMEM_TOTAL, st>>>(tmY, L.tm_out, L.tm_fc1, L.tm_fc2, p);
   CLM_LAUNCH_CHECK(c, "block_mlp");
@@ -319,10 +362,10 @@ int launch_longconv(clm_ctx* c, int layer, const __nv_bfloat16* vx, const __nv_b
 int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
 enum ProfCat { PC_ENCODE = 0, PC_EMBED, PC_LN, PC_GEMM_IN, PC_SHORTCONV, PC_LONGCONV, PC_TRANSPOSE, PC_GEMM_OUT,
-               PC_GEMM_FC1, PC_GEMM_FC2, PC_SCORE, PC_POOL, PC_HEAD, PC_BLOCK_MLP, PC_COUNT };
+               PC_GEMM_FC1, PC_GEMM_FC2, PC_SCORE, PC_POOL, PC_HEAD, PC_BLOCK_MLP, PC_BLOCK_IN, PC_COUNT };
 const char* kProfNames[PC_COUNT] = {"encode", "embed", "layernorm", "gemm_in_proj", "shortconv_gate", "longconv",
                                     "transpose", "gemm_out_proj", "gemm_fc1", "gemm_fc2", "gemm_score", "pool",
-                                    "head", "block_mlp"};
+                                    "head", "block_mlp", "block_in"};
 
 struct ProfScope {
   clm_ctx* c;
@@ -482,6 +525,15 @@ int clm_finalize(clm_ctx* c) {
     if ((rc = to_bf16(c, fc1_w, (int64_t)g.d_inner * D, &L.fc1_w))) return rc;
     if ((rc = to_bf16(c, fc2_w, (int64_t)g.d_inner * D, &L.fc2_w))) return rc;
     if ((rc = make_tmap_bf16_2d(c, &L.tm_in, L.in_w, 3 * D, D, 128))) return rc;
+    {
+      float* wf = nullptr;
+      if ((rc = dev_alloc(c, &wf, (size_t)3 * D * D))) return rc;
+      if ((rc = dev_alloc(c, &L.in_bf, (size_t)3 * D))) return rc;
+      fold_ln_kernel<<<3 * D, 256>>>(in_w, L.in_b, L.ln1_g, L.ln1_b, wf, L.in_bf, D);
+      CLM_LAUNCH_CHECK(c, "fold_ln");
+      if ((rc = to_bf16(c, wf, 3LL * D * D, &L.in_wf))) return rc;
+      if ((rc = make_tmap_bf16_2d(c, &L.tm_inf, L.in_wf, 3 * D, D, 128))) return rc;
+    }
     if ((rc = make_tmap_bf16_2d(c, &L.tm_out, L.out_w, D, D, 128))) return rc;
     if ((rc = make_tmap_bf16_2d(c, &L.tm_fc1, L.fc1_w, g.d_inner, D, 128))) return rc;
     if ((rc = make_tmap_bf16_2d(c, &L.tm_fc2, L.fc2_w, D, g.d_inner, 128))) return rc;
@@ -554,7 +606,7 @@ int clm_reserve(clm_ctx* c, int max_B, int max_T) {
   const int Tp = round_up(max_T, 64);
   const size_t CT = (size_t)max_B * D * Tp;
   int rc;
-  if ((rc = dev_alloc(c, &c->R, M * D))) return rc;
+  if ((rc = dev_alloc(c, &c->R, (M + 160) * D))) return rc;  // R32 layout: whole 32-row groups + tile overhang
   if ((rc = dev_alloc(c, &c->XN, M * D))) return rc;
   if ((rc = dev_alloc(c, &c->U, M * (size_t)c->cfg.d_inner))) return rc;  // in_proj out (3D) and fc1 out (d_inner)
   if ((rc = dev_alloc(c, &c->VX, CT))) return rc;
@@ -616,6 +668,7 @@ int clm_forward(clm_ctx* c, const void* d_ids, int ids_dtype, int B, int T, floa
   if (M > 0x7fffffffLL) return fail(c, CLM_ERR_INVALID, "clm_forward: B*T too large");
   const int Tp = round_up(T, 64);
   const unsigned rows8 = (unsigned)((M + 7) / 8);
+  const unsigned rows32 = (unsigned)((M + 31) / 32);
   int rc;
 #define STOP_AFTER(layer, stage) \
   if (c->dbg_layer == (layer) && c->dbg_stage == (stage)) return 0
@@ -632,18 +685,23 @@ int clm_forward(clm_ctx* c, const void* d_ids, int ids_dtype, int B, int T, floa
 
   for (int l = 0; l < g.n_layer; ++l) {
     LayerW& L = c->layers[l];
+    if (c->fused_in && c->dbg_layer != l) {
+      ProfScope ps_(c, PC_BLOCK_IN, st);
+      if ((rc = launch_block_in(c, l, c->R, B, T, Tp, c->VX, c->X0, st))) return rc;
+    } else {
     { ProfScope ps_(c, PC_LN, st);
-    layernorm_bf16_kernel<<<rows8, 256, 0, st>>>(c->R, L.ln1_g, L.ln1_b, c->XN, M, g.layer_norm_eps);
-    CLM_LAUNCH_CHECK(c, "ln1"); }
-    STOP_AFTER(l, 1);
-    GemmParams p{};
-    p.M = (int)M; p.N = 3 * D; p.K = D; p.bias = L.in_b; p.out = c->U; p.ldo = 3 * D;
-    { ProfScope ps_(c, PC_GEMM_IN, st);
-    if ((rc = launch_gemm(c, c->XN, L.tm_in, p, EPI_BIAS_BF16, st))) return rc; }
-    STOP_AFTER(l, 2);
-    { ProfScope ps_(c, PC_SHORTCONV, st);
-    shortconv_gate_kernel<<<dim3((Tp + 63) / 64, D / 32, B), 256, 0, st>>>(c->U, L.sc_w, L.sc_b, c->VX, c->X0, T, Tp, D);
-    CLM_LAUNCH_CHECK(c, "shortconv_gate"); }
+      layernorm_bf16_kernel<<<rows32, 256, 0, st>>>(c->R, L.ln1_g, L.ln1_b, c->XN, M, g.layer_norm_eps);
+      CLM_LAUNCH_CHECK(c, "ln1"); }
+      STOP_AFTER(l, 1);
+      GemmParams p{};
+      p.M = (int)M; p.N = 3 * D; p.K = D; p.bias = L.in_b; p.out = c->U; p.ldo = 3 * D;
+      { ProfScope ps_(c, PC_GEMM_IN, st);
+      if ((rc = launch_gemm(c, c->XN, L.tm_in, p, EPI_BIAS_BF16, st))) return rc; }
+      STOP_AFTER(l, 2);
+      { ProfScope ps_(c, PC_SHORTCONV, st);
+      shortconv_gate_kernel<<<dim3((Tp + 63) / 64, D / 32, B), 256, 0, st>>>(c->U, L.sc_w, L.sc_b, c->VX, c->X0, T, Tp, D);
+      CLM_LAUNCH_CHECK(c, "shortconv_gate"); }
+    }
     STOP_AFTER(l, 3);
     { ProfScope ps_(c, PC_LONGCONV, st);
     if ((rc = launch_longconv(c, l, c->VX, c->X0, c->Y, B, T, Tp, c->scratch, c->scratch_bytes, st))) return rc; }
@@ -656,13 +714,13 @@ int clm_forward(clm_ctx* c, const void* d_ids, int ids_dtype, int B, int T, floa
       ProfScope ps_(c, PC_BLOCK_MLP, st);
       if ((rc = launch_block_mlp(c, l, c->YT, c->R, (int)M, st))) return rc;
     } else {
-    p = GemmParams{};
-      p.M = (int)M; p.N = D; p.K = D; p.bias = L.out_b; p.out = c->R; p.res = c->R; p.ldo = D;
+      GemmParams p{};
+      p.M = (int)M; p.N = D; p.K = D; p.bias = L.out_b; p.out = c->R; p.res = c->R; p.ldo = D; p.r32 = 1;
       { ProfScope ps_(c, PC_GEMM_OUT, st);
       if ((rc = launch_gemm(c, c->YT, L.tm_out, p, EPI_BIAS_RES_F32, st))) return rc; }
       STOP_AFTER(l, 6);
       { ProfScope ps_(c, PC_LN, st);
-      layernorm_bf16_kernel<<<rows8, 256, 0, st>>>(c->R, L.ln2_g, L.ln2_b, c->XN, M, g.layer_norm_eps);
+      layernorm_bf16_kernel<<<rows32, 256, 0, st>>>(c->R, L.ln2_g, L.ln2_b, c->XN, M, g.layer_norm_eps);
       CLM_LAUNCH_CHECK(c, "ln2"); }
       STOP_AFTER(l, 7);
       p = GemmParams{};
@@ -671,7 +729,7 @@ int clm_forward(clm_ctx* c, const void* d_ids, int ids_dtype, int B, int T, floa
       if ((rc = launch_gemm(c, c->XN, L.tm_fc1, p, EPI_BIAS_GELU_TANH, st))) return rc; }
       STOP_AFTER(l, 8);
       p = GemmParams{};
-      p.M = (int)M; p.N = D; p.K = g.d_inner; p.bias = L.fc2_b; p.out = c->R; p.res = c->R; p.ldo = D;
+      p.M = (int)M; p.N = D; p.K = g.d_inner; p.bias = L.fc2_b; p.out = c->R; p.res = c->R; p.ldo = D; p.r32 = 1;
       { ProfScope ps_(c, PC_GEMM_FC2, st);
       if ((rc = launch_gemm(c, c->U, L.tm_fc2, p, EPI_BIAS_RES_F32, st))) return rc; }
     }
@@ -679,7 +737,7 @@ int clm_forward(clm_ctx* c, const void* d_ids, int ids_dtype, int B, int T, floa
   }
   const int NL = g.n_layer;
   { ProfScope ps_(c, PC_LN, st);
-  layernorm_bf16_kernel<<<rows8, 256, 0, st>>>(c->R, c->lnf_g, c->lnf_b, c->XN, M, g.layer_norm_eps);
+  layernorm_bf16_kernel<<<rows32, 256, 0, st>>>(c->R, c->lnf_g, c->lnf_b, c->XN, M, g.layer_norm_eps);
   CLM_LAUNCH_CHECK(c, "ln_f"); }
   STOP_AFTER(NL, 10);
   {
@@ -743,14 +801,28 @@ int clm_set_option(clm_ctx* c, const char* name, int value) {
   if (!c || !name) return CLM_ERR_INVALID;
   const std::string n(name);
   if (n == "fused_mlp") c->fused_mlp = value != 0;
+  else if (n == "fused_in") c->fused_in = value != 0;
   else return fail(c, CLM_ERR_INVALID, "clm_set_option: unknown option '%s'", name);
   return 0;
+}
+
+int clm_block_in(clm_ctx* c, int layer, const float* d_res, int B, int T, int Tp, void* d_vx, void* d_x0, void* stream) {
+  if (!c || !c->finalized) return fail(c, CLM_ERR_STATE, "clm_block_in before clm_finalize");
+  if (layer < 0 || layer >= c->cfg.n_layer || !d_res || !d_vx || !d_x0 || B <= 0 || T <= 0 || Tp < T || Tp % 64 != 0)
+    return fail(c, CLM_ERR_INVALID, "clm_block_in: bad argument");
+  return launch_block_in(c, layer, d_res, B, T, Tp, (__nv_bfloat16*)d_vx, (__nv_bfloat16*)d_x0, (cudaStream_t)stream);
 }
 
 int clm_block_mlp(clm_ctx* c, int layer, const void* d_y, float* d_res, int M, void* stream) {
   if (!c || !c->finalized) return fail(c, CLM_ERR_STATE, "clm_block_mlp before clm_finalize");
   if (layer < 0 || layer >= c->cfg.n_layer || !d_y || !d_res || M <= 0) return fail(c, CLM_ERR_INVALID, "clm_block_mlp: bad argument");
   return launch_block_mlp(c, layer, (const __nv_bfloat16*)d_y, d_res, M, (cudaStream_t)stream);
+}
+
+int clm_block_mlp_trace(clm_ctx* c, int layer, const void* d_y, float* d_res, int M, long long* d_trace, void* stream) {
+  if (!c || !c->finalized) return fail(c, CLM_ERR_STATE, "clm_block_mlp_trace before clm_finalize");
+  if (layer < 0 || layer >= c->cfg.n_layer || !d_y || !d_res || M <= 0 || !d_trace) return fail(c, CLM_ERR_INVALID, "clm_block_mlp_trace: bad argument");
+  return launch_block_mlp(c, layer, (const __nv_bfloat16*)d_y, d_res, M, (cudaStream_t)stream, d_trace);
 }
 
 int clm_longconv(clm_ctx* c, int layer, const void* d_vx, const void* d_x0, void* d_out, int B, int T, int Tp,
@@ -810,7 +882,7 @@ int clm_debug_copy(clm_ctx* c, const char* what, void* d_dst, size_t max_bytes, 
   const void* src = nullptr;
   size_t bytes = 0;
   const std::string w(what);
-  if (w == "resid") { src = c->R; bytes = M * D * 4; }
+  if (w == "resid") { src = c->R; bytes = (M + 128) * D * 4; }  // R32 blocked layout
   else if (w == "xn") { src = c->XN; bytes = M * D * 2; }
   else if (w == "u") { src = c->U; bytes = M * c->cfg.d_inner * 2; }
   else if (w == "vx") { src = c->VX; bytes = CT * 2; }

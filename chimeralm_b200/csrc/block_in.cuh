@@ -1,0 +1,322 @@
+// Fused first half of a HyenaDNA block, one persistent kernel (SURVEY.md A.6 head + A.3):
+//
+//   xn      = LayerNorm1(res)                                  (affine folded into W'/b', see below)
+//   u       = xn * W_in^T + b_in                               (HyenaOperator.in_proj, 256 -> 768)
+//   uc[c,t] = w[c,0] u[c,t-2] + w[c,1] u[c,t-1] + w[c,2] u[c,t] + cb[c]      (short_filter, causal k=3)
+//   x0, x1, v = uc[0:256], uc[256:512], uc[512:768];   vx = v * x1            (first gate)
+//   outputs : vx, x0 as channel-major bf16 [B][256][Tp]  (what the long convolution consumes)
+//
+// Replaces nn.LayerNorm + nn.Linear + nn.Conv1d(groups=768) + split + mul of the reference and
+// the transpose between them: per token the kernel reads 1 KB (res) and writes 1 KB (vx, x0);
+// the 768-wide in_proj output never leaves the SM.
+//
+// The GEMM is computed TRANSPOSED: D[channel, token] = W'[channel,:] . xn[token,:], so that in
+// TMEM a lane is a channel and a column is a token.  The epilogue thread that owns a channel
+// then runs the 3-tap causal filter along its own registers and emits time-contiguous rows.
+// A tile is 128 new tokens of one read plus a 16-token halo on the left (N = 144 columns; only
+// the last two halo columns are used, 16 keeps N a legal UMMA shape), so tiles are independent.
+// Per tile two passes (channel halves); each pass accumulates the x0/x1/v blocks of the same
+// 128 channels in TMEM columns [0,144) [144,288) [288,432).
+//
+// LayerNorm's affine is folded offline (clm_finalize): W' = W_in * diag(gamma),
+// b' = b_in + W_in beta, so the kernel only normalises.
+//
+// Warp roles: warp 0 = TMA producer (weight k-blocks, 4 x 16 KB ring), warp 1 = MMA issuer,
+// warps 2..9 = LayerNorm producers of the B operand, then epilogue (conv + gate + TMA store).
+#pragma once
+#include <cuda_bf16.h>
+
+#include "gemm_tcgen05.cuh"
+#include "ptx.cuh"
+
+namespace clm {
+
+struct BlockInParams {
+  const float* res;     // residual stream, R32 layout
+  const float* b_in;    // [768] folded bias
+  const float* cw;      // [768][3] short filter taps
+  const float* cb;      // [768]   short filter bias
+  float eps;
+  int B, T;
+  int tiles_per_seq, num_tiles;
+};
+
+namespace bi {
+constexpr int D = 256, BT = 128, HALO = 16, NCOL = BT + HALO;   // 144 token columns per tile
+constexpr int KB_ROWS_BYTES = NCOL * 128;                       // one k-block of xn: 144 rows x 128 B
+constexpr int XN_BYTES = 4 * KB_ROWS_BYTES;                     // 73728
+constexpr int SLOT_BYTES = 128 * 64 * 2;                        // 16 KB: [128 channels x 64 k]
+constexpr int NSLOT = 4;
+constexpr int STAGE_BOX = 128 * 128;                            // 16 KB: [128 channels x 64 tokens] bf16
+constexpr int OFF_XN = 0;
+constexpr int OFF_W = OFF_XN + XN_BYTES;                        // 73728 (multiple of 1024)
+constexpr int OFF_STAGE = OFF_W + NSLOT * SLOT_BYTES;           // 139264
+constexpr int OFF_BAR = OFF_STAGE + 4 * STAGE_BOX;              // 204800
+constexpr int OFF_PART = OFF_BAR + 256;                         // LN partials [2][2][128] fp32
+constexpr int SMEM_TOTAL = OFF_PART + 2 * 2 * 128 * 4;          // 207104
+constexpr int THREADS = 320, EPI_THREADS = 256;
+constexpr int GCOLS = NCOL;                                     // TMEM columns per channel group
+}  // namespace bi
+
+__device__ __forceinline__ void tmem_ld_32x32b_x2(uint32_t taddr, uint32_t& a, uint32_t& b) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(a), "=r"(b) : "r"(taddr) : "memory");
+}
+
+__global__ void __launch_bounds__(bi::THREADS, 1)
+block_in_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmVX,
+                const __grid_constant__ CUtensorMap tmX0, BlockInParams p) {
+  using namespace bi;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((ptx::smem_u32(smem) & 1023u) != 0) __trap();
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
+  uint64_t* w_full = bars;          // [4]
+  uint64_t* w_empty = bars + 4;     // [4]
+  uint64_t* xn_full = bars + 8;     // LN warps wrote the B operand
+  uint64_t* xn_free = bars + 9;     // both passes' MMAs finished reading it
+  uint64_t* acc_full = bars + 10;   // one pass accumulated
+  uint64_t* acc_free = bars + 11;   // epilogue drained TMEM
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 12);
+  float (*s_part)[2][128] = reinterpret_cast<float (*)[2][128]>(smem + OFF_PART);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmW); ptx::prefetch_tmap(&tmVX); ptx::prefetch_tmap(&tmX0);
+    for (int i = 0; i < NSLOT; ++i) { ptx::mbar_init(&w_full[i], 1); ptx::mbar_init(&w_empty[i], 1); }
+    ptx::mbar_init(xn_full, 8); ptx::mbar_init(xn_free, 1);
+    ptx::mbar_init(acc_full, 1); ptx::mbar_init(acc_free, 8);
+    ptx::fence_mbar_init();
+  } else if (warp == 1) {
+    ptx::tmem_alloc<512>(tmem_ptr);
+  }
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  ptx::tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // =========================== TMA producer: 24 weight k-blocks per tile ===========================
+    if (lane == 0) {
+      uint32_t wi = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        for (int h = 0; h < 2; ++h)
+          for (int g = 0; g < 3; ++g)
+            for (int kb = 0; kb < 4; ++kb) {
+              const uint32_t s = wi % NSLOT, ph = (wi / NSLOT) & 1;
+              ptx::mbar_wait(&w_empty[s], ph ^ 1);
+              ptx::mbar_expect_tx(&w_full[s], SLOT_BYTES);
+              ptx::tma_load_2d(smem + OFF_W + s * SLOT_BYTES, &tmW, &w_full[s], kb * 64, g * 256 + h * 128);
+              ++wi;
+            }
+      }
+    }
+  } else if (warp == 1) {
+    // =========================== MMA issuer ===========================
+    if (lane == 0) {
+      constexpr uint32_t idesc = ptx::idesc_bf16_f32(128, NCOL);
+      const uint32_t sXN = ptx::smem_u32(smem + OFF_XN), sW = ptx::smem_u32(smem + OFF_W);
+      uint32_t wi = 0, it = 0, pass = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+        ptx::mbar_wait(xn_full, it & 1);
+        for (int h = 0; h < 2; ++h, ++pass) {
+          ptx::mbar_wait(acc_free, (pass & 1) ^ 1);
+          ptx::tc_fence_after_sync();
+          for (int g = 0; g < 3; ++g)
+            for (int kb = 0; kb < 4; ++kb) {
+              const uint32_t s = wi % NSLOT, ph = (wi / NSLOT) & 1;
+              ptx::mbar_wait(&w_full[s], ph);
+              ptx::tc_fence_after_sync();
+              const uint64_t da = ptx::smem_desc_k_sw128(sW + s * SLOT_BYTES);
+              const uint64_t db = ptx::smem_desc_k_sw128(sXN + kb * KB_ROWS_BYTES);
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                ptx::umma_f16(tmem_base + g * GCOLS, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+              ptx::umma_commit(&w_empty[s]);
+              ++wi;
+            }
+          ptx::umma_commit(acc_full);
+          if (h == 1) ptx::umma_commit(xn_free);
+        }
+      }
+    }
+  } else {
+    // =========================== LayerNorm producers + epilogue ===========================
+    const int e = warp - 2;
+    const int q = warp & 3;            // TMEM lane quarter
+    const int hf = e >> 2;             // LN: column half of the row; epilogue: token half of the tile
+    const int r = q * 32 + lane;       // LN: row 0..127 of the tile; epilogue: channel inside the pass
+    const uint32_t lane_addr = tmem_base + (uint32_t(q * 32) << 16);
+    const uint32_t sXN = ptx::smem_u32(smem + OFF_XN);
+    const uint32_t sST = ptx::smem_u32(smem + OFF_STAGE);
+    const bool issuer = (threadIdx.x == 64);
+    uint32_t it = 0, pass = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      const int b = tile / p.tiles_per_seq;
+      const int t0 = (tile % p.tiles_per_seq) * BT;
+      const long long seq_row0 = (long long)b * p.T;
+      // ------------------------------------------------ LayerNorm -> B operand (xn, bf16, SW128 K-major)
+      ptx::mbar_wait(xn_free, (it & 1) ^ 1);
+      // round 0: tile rows 0..127 (thread = row r, column half hf); round 1: rows 128..143 (warp 2 only:
+      // lanes 0-15 take the low half, lanes 16-31 the high half of row 128 + lane % 16)
+#pragma unroll 1
+      for (int round = 0; round < 2; ++round) {
+        if (round == 1 && e != 0) break;
+        const int trow = (round == 0) ? r : (128 + (lane & 15));
+        const int half = (round == 0) ? hf : (lane >> 4);
+        const int t = t0 - HALO + trow;
+        const bool ok = (t >= 0);      // t < 0: left of the read (conv zero padding; value unused)
+        const long long grow = seq_row0 + t;
+        float4 x[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          x[j] = ok ? *reinterpret_cast<const float4*>(p.res + ptx::r32_off(grow, half * 128 + 4 * j))
+                    : make_float4(0.f, 0.f, 0.f, 0.f);
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          s1 += (x[j].x + x[j].y) + (x[j].z + x[j].w);
+          s2 += (x[j].x * x[j].x + x[j].y * x[j].y) + (x[j].z * x[j].z + x[j].w * x[j].w);
+        }
+        float ts1, ts2;
+        if (round == 0) {
+          s_part[hf][0][r] = s1;
+          s_part[hf][1][r] = s2;
+          ptx::bar_sync(1, EPI_THREADS);
+          ts1 = s_part[0][0][r] + s_part[1][0][r];
+          ts2 = s_part[0][1][r] + s_part[1][1][r];
+        } else {
+          ts1 = s1 + __shfl_xor_sync(0xffffffffu, s1, 16);
+          ts2 = s2 + __shfl_xor_sync(0xffffffffu, s2, 16);
+        }
+        const float mean = ts1 * (1.0f / D);
+        const float rstd = rsqrtf(fmaxf(ts2 * (1.0f / D) - mean * mean, 0.f) + p.eps);
+        const uint32_t swz = uint32_t(trow & 7);
+#pragma unroll
+        for (int c8 = 0; c8 < 16; ++c8) {   // 16 chunks of 8 columns in this half
+          const int col = half * 128 + c8 * 8;
+          const float4 a = x[2 * c8], c4 = x[2 * c8 + 1];
+          const uint32_t w0 = pack_bf16((a.x - mean) * rstd, (a.y - mean) * rstd);
+          const uint32_t w1 = pack_bf16((a.z - mean) * rstd, (a.w - mean) * rstd);
+          const uint32_t w2 = pack_bf16((c4.x - mean) * rstd, (c4.y - mean) * rstd);
+          const uint32_t w3 = pack_bf16((c4.z - mean) * rstd, (c4.w - mean) * rstd);
+          const uint32_t addr = sXN + (col >> 6) * KB_ROWS_BYTES + trow * 128 + ((uint32_t((col & 63) >> 3) ^ swz) << 4);
+          ptx::st_shared_v4(addr, w0, w1, w2, w3);
+        }
+      }
+      ptx::fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(xn_full);
+      // ------------------------------------------------ two passes of conv + gate epilogue
+#pragma unroll 1
+      for (int h = 0; h < 2; ++h, ++pass) {
+        // per-thread channel constants (thread = channel h*128 + r of each group)
+        float bia[3], w0[3], w1[3], w2[3], cbv[3];
+#pragma unroll
+        for (int g = 0; g < 3; ++g) {
+          const int ch = g * 256 + h * 128 + r;
+          bia[g] = __ldg(p.b_in + ch);
+          w0[g] = __ldg(p.cw + ch * 3);
+          w1[g] = __ldg(p.cw + ch * 3 + 1);
+          w2[g] = __ldg(p.cw + ch * 3 + 2);
+          cbv[g] = __ldg(p.cb + ch);
+        }
+        // staging buffers may still be read by the previous pass's TMA stores
+        if (issuer) ptx::tma_store_wait_read<0>();
+        ptx::bar_sync(1, EPI_THREADS);
+        ptx::mbar_wait(acc_full, pass & 1);
+        ptx::tc_fence_after_sync();
+        const int cbase = HALO + hf * 64;   // first output column of this thread
+        float hm2[3], hm1[3];               // u[j-2], u[j-1] carried along the columns
+#pragma unroll
+        for (int g = 0; g < 3; ++g) {
+          uint32_t a, c2;
+          tmem_ld_32x32b_x2(lane_addr + g * GCOLS + cbase - 2, a, c2);
+          ptx::tmem_ld_wait();
+          const int tm2 = t0 - HALO + cbase - 2;
+          hm2[g] = (tm2 >= 0) ? __uint_as_float(a) + bia[g] : 0.f;
+          hm1[g] = (tm2 + 1 >= 0) ? __uint_as_float(c2) + bia[g] : 0.f;
+        }
+#pragma unroll 1
+        for (int s = 0; s < 2; ++s) {       // two sub-blocks of 32 token columns
+          float uc[3][32];
+#pragma unroll
+          for (int g = 0; g < 3; ++g) {
+            uint32_t a[32];
+            ptx::tmem_ld_32x32b_x32(lane_addr + g * GCOLS + cbase + s * 32, a);
+            ptx::tmem_ld_wait();
+            float um2 = hm2[g], um1 = hm1[g];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float u = __uint_as_float(a[j]) + bia[g];   // cbase + s*32 + j >= HALO -> t >= 0
+              uc[g][j] = fmaf(w0[g], um2, fmaf(w1[g], um1, fmaf(w2[g], u, cbv[g])));
+              um2 = um1;
+              um1 = u;
+            }
+            hm2[g] = um2;
+            hm1[g] = um1;
+          }
+          if (s == 1) {                      // all TMEM reads of this pass are done
+            ptx::tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(acc_free);
+          }
+          const uint32_t swz = uint32_t(r & 7);
+          const uint32_t rowoff = uint32_t(r) * 128;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {     // 4 chunks of 8 tokens
+            const float* x0p = &uc[0][k * 8];
+            const float* x1p = &uc[1][k * 8];
+            const float* vp = &uc[2][k * 8];
+            const uint32_t chunk = (uint32_t(s * 4 + k) ^ swz) << 4;
+            ptx::st_shared_v4(sST + (0 * 2 + hf) * STAGE_BOX + rowoff + chunk, pack_bf16(vp[0] * x1p[0], vp[1] * x1p[1]),
+                              pack_bf16(vp[2] * x1p[2], vp[3] * x1p[3]), pack_bf16(vp[4] * x1p[4], vp[5] * x1p[5]),
+                              pack_bf16(vp[6] * x1p[6], vp[7] * x1p[7]));
+            ptx::st_shared_v4(sST + (1 * 2 + hf) * STAGE_BOX + rowoff + chunk, pack_bf16(x0p[0], x0p[1]),
+                              pack_bf16(x0p[2], x0p[3]), pack_bf16(x0p[4], x0p[5]), pack_bf16(x0p[6], x0p[7]));
+          }
+        }
+        ptx::fence_proxy_async_smem();
+        ptx::bar_sync(2, EPI_THREADS);
+        if (issuer) {
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            ptx::tma_store_3d(&tmVX, smem + OFF_STAGE + (0 * 2 + hh) * STAGE_BOX, t0 + hh * 64, h * 128, b);
+            ptx::tma_store_3d(&tmX0, smem + OFF_STAGE + (1 * 2 + hh) * STAGE_BOX, t0 + hh * 64, h * 128, b);
+          }
+          ptx::tma_store_commit();
+        }
+      }
+    }
+    if (issuer) ptx::tma_store_wait<0>();
+  }
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after_sync();
+    ptx::tmem_dealloc<512>(tmem_base);
+  }
+}
+
+// W'[n,k] = W[n,k] * gamma[k];  b'[n] = b[n] + sum_k W[n,k] * beta[k]   (one block per output row n)
+__global__ void __launch_bounds__(256) fold_ln_kernel(const float* __restrict__ W, const float* __restrict__ bias,
+                                                      const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                      float* __restrict__ Wf, float* __restrict__ bf, int K) {
+  __shared__ float red[8];
+  const int n = blockIdx.x;
+  float acc = 0.f;
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    const float w = W[(long long)n * K + k];
+    Wf[(long long)n * K + k] = w * gamma[k];
+    acc += w * beta[k];
+  }
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += red[i];
+    bf[n] = bias[n] + t;
+  }
+}
+
+}  // namespace clm

@@ -3,7 +3,7 @@
 //   r1  = y * Wout^T + b_out + res                 (HyenaOperator.out_proj + residual)
 //   xn  = LayerNorm2(r1)
 //   h   = gelu_tanh(xn * W1^T + b1)                (HyenaMlp.fc1)
-//   out = h * W2^T + b2 + r1                       (HyenaMlp.fc2 + residual)       -> res (fp32)
+//   out = h * W2^T + b2 + r1                       (HyenaMlp.fc2 + residual)       -> res (fp32, R32 layout)
 //
 // Replaces 4 reference ops (nn.Linear x3, nn.LayerNorm, F.gelu) and keeps r1, xn and the
 // 1024-wide hidden activations on chip: per token the kernel reads 512 B (y, bf16) + 1 KB
@@ -40,6 +40,7 @@ struct BlockMlpParams {
   const float* b2;       // [256]
   float eps;
   int num_tiles;
+  long long* trace;      // optional [3][64] clock64 stamps written by CTA 0 (null in production)
 };
 
 namespace bm {
@@ -61,9 +62,15 @@ constexpr int NCHUNK = DI / 128;                 // 8 fc1 column chunks
 constexpr uint32_t TM_R = 0, TM_H = 256;
 
 __device__ __forceinline__ float gelu_tanh_fast(float x) {
-  // x * sigmoid(2u), u = sqrt(2/pi) (x + 0.044715 x^3)  ==  0.5 x (1 + tanh(u))
-  const float u2 = 1.5957691216057308f * (x + 0.044715f * x * x * x);
-  return __fdividef(x, 1.0f + __expf(-u2));
+  // 0.5 x (1 + tanh(u)), u = sqrt(2/pi) (x + 0.044715 x^3); tanh.approx is ONE MUFU op (the
+  // exp + rcp formulation needs two and made the GELU epilogue MUFU-bound at the MMA's pace).
+  // |tanh.approx error| <= 2^-10.987, well below the bf16 rounding applied to the result.
+  const float x2 = x * x;
+  const float u = x * fmaf(0.035677408136300125f, x2, 0.7978845608028654f);
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(u));
+  const float hx = 0.5f * x;
+  return fmaf(hx, t, hx);
 }
 }  // namespace bm
 
@@ -90,6 +97,15 @@ block_mlp_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
   float (*s_part)[2][BM] = reinterpret_cast<float (*)[2][BM]>(smem + OFF_PART);  // [half][sum|sumsq][row]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // Each CTA walks the 8 fc1/fc2 hidden chunks starting at a different one, so the 148 CTAs do
+  // not all pull the same weight tile out of the same L2 slices at the same moment.
+  const int rot = blockIdx.x & (NCHUNK - 1);
+  // trace rows: 0 = producer, 1 = MMA issuer, 2 = epilogue warp 2; first two tiles of CTA 0
+  long long* trace = (p.trace && blockIdx.x == 0) ? p.trace : nullptr;
+  int trace_n = 0;
+  auto stamp = [&](int role) {
+    if (trace && trace_n < 64) trace[role * 64 + trace_n++] = clock64();
+  };
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmY); ptx::prefetch_tmap(&tmWout); ptx::prefetch_tmap(&tmW1); ptx::prefetch_tmap(&tmW2);
@@ -126,6 +142,7 @@ block_mlp_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
         ptx::mbar_wait(x_free, (it & 1) ^ 1);
         ptx::mbar_expect_tx(x_full, X_BYTES);
         for (int kb = 0; kb < 4; ++kb) ptx::tma_load_2d(smem + OFF_X + kb * KB_BYTES, &tmY, x_full, kb * BK, m0);
+        stamp(0);
         // out_proj weights: 4 k-blocks of [256 x 64]
         for (int kb = 0; kb < 4; ++kb) {
           uint8_t* s = slot_acquire();
@@ -139,13 +156,14 @@ block_mlp_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
             for (int h2 = 0; h2 < 2; ++h2) {
               uint8_t* s = slot_acquire();
               const uint32_t sl = wi % NSLOT;
-              ptx::tma_load_2d(s, &tmW1, &w_full[sl], (2 * h2) * BK, j * 128);
-              ptx::tma_load_2d(s + KB_BYTES, &tmW1, &w_full[sl], (2 * h2 + 1) * BK, j * 128);
+              const int jc = (j + rot) & (NCHUNK - 1);
+              ptx::tma_load_2d(s, &tmW1, &w_full[sl], (2 * h2) * BK, jc * 128);
+              ptx::tma_load_2d(s + KB_BYTES, &tmW1, &w_full[sl], (2 * h2 + 1) * BK, jc * 128);
               ++wi;
             }
           }
           if (j >= 1) {  // fc2 K-chunk j-1: columns [128 (j-1), +128) = 2 k-blocks of [256 x 64]
-            const int jj = j - 1;
+            const int jj = (j - 1 + rot) & (NCHUNK - 1);
             for (int kb = 0; kb < 2; ++kb) {
               uint8_t* s = slot_acquire();
               const uint32_t sl = wi % NSLOT;
@@ -180,9 +198,11 @@ block_mlp_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
         const uint32_t tph = it & 1;
         // ---- G1: R = y * Wout^T
+        stamp(1);
         ptx::mbar_wait(r_free, tph ^ 1);     // previous tile's output drained from R
         ptx::mbar_wait(x_full, tph);
         ptx::tc_fence_after_sync();
+        stamp(1);
         for (int kb = 0; kb < 4; ++kb) {
           const uint32_t sw = slot_wait();
           const uint64_t da = ptx::smem_desc_k_sw128(sX + kb * KB_BYTES);
@@ -192,6 +212,7 @@ block_mlp_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
           slot_release();
         }
         ptx::umma_commit(g1_done);
+        stamp(1);
         // ---- fc1 / fc2 software pipeline
         for (int j = 0; j <= NCHUNK; ++j) {
           if (j < NCHUNK) {
@@ -199,6 +220,7 @@ block_mlp_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
             if (j == 0) { ptx::mbar_wait(xn_full, tph); }
             ptx::mbar_wait(&hacc_free[b], (u & 1) ^ 1);
             ptx::tc_fence_after_sync();
+            stamp(1);
             for (int h2 = 0; h2 < 2; ++h2) {
               const uint32_t sw = slot_wait();
 #pragma unroll
@@ -220,6 +242,7 @@ block_mlp_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
             const uint32_t b = jj & 1, u = it * 4 + (jj >> 1);
             ptx::mbar_wait(&hbuf_full[b], u & 1);
             ptx::tc_fence_after_sync();
+            stamp(1);
             for (int kb = 0; kb < 2; ++kb) {
               const uint32_t sw = slot_wait();
               const uint64_t da = ptx::smem_desc_k_sw128(sHB + b * HB_BYTES + kb * KB_BYTES);
@@ -232,6 +255,7 @@ block_mlp_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
           }
         }
         ptx::umma_commit(out_full);
+        stamp(1);
       }
     }
   } else {
@@ -249,29 +273,34 @@ block_mlp_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
       const uint32_t tph = it & 1;
       const long long row = (long long)tile * BM + r;
       const bool row_ok = row < p.M;
-      float* res_row = p.res + row * D;
       // ------------------------------------------------ E1: r1, LayerNorm2 -> xn
+      // The residual half-row (128 fp32) is fetched into registers BEFORE waiting for the
+      // out_proj accumulator, so its DRAM latency hides behind the y-tile load and G1.
+      float4 rs[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        rs[j] = row_ok ? *reinterpret_cast<const float4*>(p.res + ptx::r32_off(row, hf * 128 + 4 * j))
+                       : make_float4(0.f, 0.f, 0.f, 0.f);
+      const bool tr = trace && warp == 2 && lane == 0;
       ptx::mbar_wait(g1_done, tph);
       ptx::tc_fence_after_sync();
+      if (tr) stamp(2);
       float s1 = 0.f, s2 = 0.f;
-#pragma unroll 1
-      for (int c0 = 0; c0 < 128; c0 += 32) {
-        const int col = hf * 128 + c0;
+#pragma unroll
+      for (int ci = 0; ci < 4; ++ci) {
+        const int col = hf * 128 + ci * 32;
         uint32_t a[32];
         ptx::tmem_ld_32x32b_x32(lane_addr + TM_R + col, a);
-        float4 rs[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          rs[j] = row_ok ? *reinterpret_cast<const float4*>(res_row + col + 4 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
         ptx::tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float4 bo = __ldg(reinterpret_cast<const float4*>(p.b_out + col) + j);
           const float4 b2 = __ldg(reinterpret_cast<const float4*>(p.b2 + col) + j);
-          const float v0 = __uint_as_float(a[4 * j + 0]) + bo.x + rs[j].x;
-          const float v1 = __uint_as_float(a[4 * j + 1]) + bo.y + rs[j].y;
-          const float v2 = __uint_as_float(a[4 * j + 2]) + bo.z + rs[j].z;
-          const float v3 = __uint_as_float(a[4 * j + 3]) + bo.w + rs[j].w;
+          const float4 rr = rs[ci * 8 + j];
+          const float v0 = __uint_as_float(a[4 * j + 0]) + bo.x + rr.x;
+          const float v1 = __uint_as_float(a[4 * j + 1]) + bo.y + rr.y;
+          const float v2 = __uint_as_float(a[4 * j + 2]) + bo.z + rr.z;
+          const float v3 = __uint_as_float(a[4 * j + 3]) + bo.w + rr.w;
           s1 += (v0 + v1) + (v2 + v3);
           s2 += (v0 * v0 + v1 * v1) + (v2 * v2 + v3 * v3);
           a[4 * j + 0] = __float_as_uint(v0 + b2.x);
@@ -321,12 +350,14 @@ block_mlp_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
       ptx::tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(xn_full);
+      if (tr) stamp(2);
       // ------------------------------------------------ E2: gelu(fc1 chunk) -> HB
 #pragma unroll 1
       for (int j = 0; j < NCHUNK; ++j) {
         const uint32_t b = j & 1, u = it * 4 + (j >> 1);
         ptx::mbar_wait(&hacc_full[b], u & 1);
         ptx::tc_fence_after_sync();
+        if (tr) stamp(2);
         uint32_t a0[32], a1[32];
         ptx::tmem_ld_32x32b_x32(lane_addr + TM_H + b * 128 + hf * 64, a0);
         ptx::tmem_ld_32x32b_x32(lane_addr + TM_H + b * 128 + hf * 64 + 32, a1);
@@ -335,7 +366,7 @@ block_mlp_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&hacc_free[b]);
         ptx::mbar_wait(&hbuf_free[b], (u & 1) ^ 1);
-        const float* b1p = p.b1 + j * 128 + hf * 64;
+        const float* b1p = p.b1 + ((j + rot) & (NCHUNK - 1)) * 128 + hf * 64;
         const uint32_t rowaddr = sHB + b * HB_BYTES + hf * KB_BYTES + r * 128;
 #pragma unroll
         for (int g = 0; g < 8; ++g) {
@@ -356,10 +387,12 @@ block_mlp_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
         ptx::fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&hbuf_full[b]);
+        if (tr) stamp(2);
       }
       // ------------------------------------------------ E3: out = R -> res
       ptx::mbar_wait(out_full, tph);
       ptx::tc_fence_after_sync();
+      if (tr) stamp(2);
 #pragma unroll 1
       for (int c0 = 0; c0 < 128; c0 += 32) {
         const int col = hf * 128 + c0;
@@ -369,7 +402,7 @@ block_mlp_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
         if (row_ok) {
 #pragma unroll
           for (int j = 0; j < 8; ++j)
-            *reinterpret_cast<float4*>(res_row + col + 4 * j) =
+            *reinterpret_cast<float4*>(p.res + ptx::r32_off(row, col + 4 * j)) =
                 make_float4(__uint_as_float(a[4 * j]), __uint_as_float(a[4 * j + 1]), __uint_as_float(a[4 * j + 2]),
                             __uint_as_float(a[4 * j + 3]));
         }
@@ -377,6 +410,7 @@ block_mlp_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
       ptx::tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(r_free);
+      if (tr) stamp(2);
     }
   }
   ptx::tc_fence_before_sync();

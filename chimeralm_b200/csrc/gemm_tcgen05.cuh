@@ -36,6 +36,7 @@ struct GemmParams {
   float b2;            // EPI_SCORE
   float* score;        // EPI_SCORE: [M]
   long long ldo;
+  int r32;             // EPI_BIAS_RES_F32: res/out use the R32 blocked layout (N must be 256)
 };
 
 constexpr int GEMM_BM = 128;
@@ -175,13 +176,13 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
       } else if constexpr (EPI == EPI_BIAS_RES_F32) {
         if (row_ok) {
-          const float* rs = p.res + row * p.ldo + n;
-          float* o = reinterpret_cast<float*>(p.out) + row * p.ldo + n;
+          // res/out: row-major when p.r32 == 0, the blocked residual layout (ptx::r32_off) otherwise
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
-            float4 r4 = *reinterpret_cast<const float4*>(rs + j);
+            const long long off = p.r32 ? ptx::r32_off(row, n + j) : row * p.ldo + n + j;
+            float4 r4 = *reinterpret_cast<const float4*>(p.res + off);
             float4 w = make_float4(v[j] + r4.x, v[j + 1] + r4.y, v[j + 2] + r4.z, v[j + 3] + r4.w);
-            *reinterpret_cast<float4*>(o + j) = w;
+            *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + off) = w;
           }
         }
       } else {  // EPI_SCORE

@@ -5,6 +5,8 @@
 #include <cuda_bf16.h>
 #include <stdint.h>
 
+#include "ptx.cuh"
+
 namespace clm {
 
 // ---------------------------------------------------------------------------------------------
@@ -43,7 +45,8 @@ __global__ void __launch_bounds__(256) encode_kernel(EncodeParams p) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// Embedding gather (HyenaEmbeddings.word_embeddings, A.2): one warp per token, fp32 residual out.
+// Embedding gather (HyenaEmbeddings.word_embeddings, A.2): one warp per token, fp32 residual out
+// in the R32 blocked layout (ptx::r32_off).
 template <typename IdT>
 __global__ void __launch_bounds__(256) embed_kernel(const IdT* __restrict__ ids, const float* __restrict__ E,
                                                     float* __restrict__ R, long long M, int D, int vocab_rows,
@@ -57,40 +60,49 @@ __global__ void __launch_bounds__(256) embed_kernel(const IdT* __restrict__ ids,
     id = 0;
   }
   const float4* src = reinterpret_cast<const float4*>(E + id * D);
-  float4* dst = reinterpret_cast<float4*>(R + row * D);
-  for (int i = lane; i < D / 4; i += 32) dst[i] = __ldg(src + i);
+  for (int i = lane; i < D / 4; i += 32) *reinterpret_cast<float4*>(R + ptx::r32_off(row, 4 * i)) = __ldg(src + i);
 }
 
 // ---------------------------------------------------------------------------------------------
-// LayerNorm over D=256 (eps inside rsqrt, biased variance, as torch.nn.LayerNorm): one warp per
-// row, fp32 in, bf16 out (GEMM operand).
+// LayerNorm over D=256 (eps inside rsqrt, biased variance, as torch.nn.LayerNorm).  Input: fp32
+// residual in the R32 blocked layout; output: bf16 token-major (GEMM operand).  One block per
+// 32-row group: the group's 32 KB are contiguous in R32 and are copied to shared memory with
+// fully coalesced 16-byte loads, then each warp normalises 4 rows.
 __global__ void __launch_bounds__(256) layernorm_bf16_kernel(const float* __restrict__ X, const float* __restrict__ g,
                                                              const float* __restrict__ bta,
                                                              __nv_bfloat16* __restrict__ Y, long long M, float eps) {
-  constexpr int D = 256;
-  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (row >= M) return;
-  const float4* x4 = reinterpret_cast<const float4*>(X + row * D);
-  float4 a = x4[lane], b = x4[lane + 32];
-  float s = a.x + a.y + a.z + a.w + b.x + b.y + b.z + b.w;
-  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  const float mean = s * (1.0f / D);
-  float v[8] = {a.x - mean, a.y - mean, a.z - mean, a.w - mean, b.x - mean, b.y - mean, b.z - mean, b.w - mean};
-  float ss = 0.f;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) ss += v[i] * v[i];
-  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-  const float rstd = rsqrtf(ss * (1.0f / D) + eps);
+  constexpr int D = 256, CH = 64, CS = 33;  // 64 column chunks; chunk stride 33 float4 (pad 1) against bank conflicts
+  __shared__ float4 sx[CH * CS];
+  const long long row0 = (long long)blockIdx.x * 32;
+  const float4* src = reinterpret_cast<const float4*>(X + row0 * D);  // r32_off(row0, 0) == row0 * 256
+  for (int i = threadIdx.x; i < CH * 32; i += 256) sx[(i >> 5) * CS + (i & 31)] = src[i];
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float4 g0 = __ldg(reinterpret_cast<const float4*>(g) + lane), g1 = __ldg(reinterpret_cast<const float4*>(g) + lane + 32);
   const float4 b0 = __ldg(reinterpret_cast<const float4*>(bta) + lane), b1 = __ldg(reinterpret_cast<const float4*>(bta) + lane + 32);
-  __nv_bfloat162 o0 = __floats2bfloat162_rn(v[0] * rstd * g0.x + b0.x, v[1] * rstd * g0.y + b0.y);
-  __nv_bfloat162 o1 = __floats2bfloat162_rn(v[2] * rstd * g0.z + b0.z, v[3] * rstd * g0.w + b0.w);
-  __nv_bfloat162 o2 = __floats2bfloat162_rn(v[4] * rstd * g1.x + b1.x, v[5] * rstd * g1.y + b1.y);
-  __nv_bfloat162 o3 = __floats2bfloat162_rn(v[6] * rstd * g1.z + b1.z, v[7] * rstd * g1.w + b1.w);
-  uint2* y2 = reinterpret_cast<uint2*>(Y + row * D);
-  y2[lane] = make_uint2(*reinterpret_cast<uint32_t*>(&o0), *reinterpret_cast<uint32_t*>(&o1));
-  y2[lane + 32] = make_uint2(*reinterpret_cast<uint32_t*>(&o2), *reinterpret_cast<uint32_t*>(&o3));
+#pragma unroll
+  for (int rr = 0; rr < 4; ++rr) {
+    const int r = warp * 4 + rr;
+    const long long row = row0 + r;
+    if (row >= M) break;
+    const float4 a = sx[lane * CS + r], b = sx[(lane + 32) * CS + r];
+    float s = a.x + a.y + a.z + a.w + b.x + b.y + b.z + b.w;
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s * (1.0f / D);
+    float v[8] = {a.x - mean, a.y - mean, a.z - mean, a.w - mean, b.x - mean, b.y - mean, b.z - mean, b.w - mean};
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) ss += v[i] * v[i];
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    const float rstd = rsqrtf(ss * (1.0f / D) + eps);
+    __nv_bfloat162 o0 = __floats2bfloat162_rn(v[0] * rstd * g0.x + b0.x, v[1] * rstd * g0.y + b0.y);
+    __nv_bfloat162 o1 = __floats2bfloat162_rn(v[2] * rstd * g0.z + b0.z, v[3] * rstd * g0.w + b0.w);
+    __nv_bfloat162 o2 = __floats2bfloat162_rn(v[4] * rstd * g1.x + b1.x, v[5] * rstd * g1.y + b1.y);
+    __nv_bfloat162 o3 = __floats2bfloat162_rn(v[6] * rstd * g1.z + b1.z, v[7] * rstd * g1.w + b1.w);
+    uint2* y2 = reinterpret_cast<uint2*>(Y + row * D);
+    y2[lane] = make_uint2(*reinterpret_cast<uint32_t*>(&o0), *reinterpret_cast<uint32_t*>(&o1));
+    y2[lane + 32] = make_uint2(*reinterpret_cast<uint32_t*>(&o2), *reinterpret_cast<uint32_t*>(&o3));
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -193,8 +205,8 @@ __global__ void __launch_bounds__(256) pool_partial_kernel(const float* __restri
   float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   for (int t = tb + warp; t < te; t += 8) {
     const long long row = (long long)b * T + t;
-    const float4* x4 = reinterpret_cast<const float4*>(R + row * D);
-    float4 a = x4[lane], c = x4[lane + 32];
+    const float4 a = *reinterpret_cast<const float4*>(R + ptx::r32_off(row, 4 * lane));
+    const float4 c = *reinterpret_cast<const float4*>(R + ptx::r32_off(row, 128 + 4 * lane));
     float s = a.x + a.y + a.z + a.w + c.x + c.y + c.z + c.w;
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     const float mean = s * (1.0f / D);

@@ -208,6 +208,15 @@ __device__ __forceinline__ void tmem_st_32x32b_x32(uint32_t taddr, const uint32_
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+// Residual-stream layout "R32": rows are grouped by 32 and, inside a group, the 16-byte column
+// chunks of the 32 rows are contiguous:  off(row, col) = ((row/32)*64 + col/4)*128 + (row%32)*4 + col%4
+// (in floats, 256 columns).  A warp whose lanes own consecutive rows (the TMEM epilogue's
+// natural mapping: lane == accumulator row) then reads or writes 512 contiguous bytes per
+// 128-bit instruction instead of touching 32 different cache lines.
+__host__ __device__ __forceinline__ long long r32_off(long long row, int col) {
+  return (((row >> 5) * 64 + (col >> 2)) << 7) + ((row & 31) << 2) + (col & 3);
+}
+
 // named barrier among a subset of the CTA's warps
 __device__ __forceinline__ void bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");

@@ -177,13 +177,26 @@ class Engine:
         self._check(rc, "clm_gemm")
         return out
 
+    def block_in(self, layer: int, res_rows: torch.Tensor, B: int, T: int):
+        """Fused LN1+in_proj+short conv+gate: res_rows fp32 [B*T,256] (row-major here) -> (vx, x0) bf16 [B,256,Tp]."""
+        Tp = (T + 63) // 64 * 64
+        blocked = rows_to_r32(torch.cat([res_rows, torch.zeros(160, 256, dtype=res_rows.dtype, device=res_rows.device)]))
+        vx = torch.zeros(B, 256, Tp, dtype=torch.bfloat16, device=self.device)
+        x0 = torch.zeros_like(vx)
+        rc = self.lib.clm_block_in(self.ctx, layer, C.c_void_p(blocked.data_ptr()), B, T, Tp, C.c_void_p(vx.data_ptr()),
+                                   C.c_void_p(x0.data_ptr()), _stream_ptr(self.device))
+        self._check(rc, "clm_block_in")
+        return vx, x0
+
     def block_mlp(self, layer: int, y: torch.Tensor, res: torch.Tensor) -> torch.Tensor:
-        """In-place fused block tail on `res` (fp32 [M,256]) from y (bf16 [M,256])."""
+        """Fused block tail: y (bf16 [M,256]), res (fp32 [M,256], row-major here; converted to the
+        device's blocked layout and back) -> block output [M,256]."""
         M = y.shape[0]
-        rc = self.lib.clm_block_mlp(self.ctx, layer, C.c_void_p(y.data_ptr()), C.c_void_p(res.data_ptr()), M,
+        blocked = rows_to_r32(res)
+        rc = self.lib.clm_block_mlp(self.ctx, layer, C.c_void_p(y.data_ptr()), C.c_void_p(blocked.data_ptr()), M,
                                     _stream_ptr(self.device))
         self._check(rc, "clm_block_mlp")
-        return res
+        return r32_to_rows(blocked, M)
 
     def set_option(self, name: str, value: int) -> None:
         self._check(self.lib.clm_set_option(self.ctx, name.encode(), int(value)), "clm_set_option")
@@ -211,6 +224,21 @@ class Engine:
                                      _stream_ptr(self.device))
         self._check(rc, "clm_debug_copy")
         return out
+
+
+def r32_to_rows(blocked: torch.Tensor, M: int) -> torch.Tensor:
+    """Undo the residual stream's blocked device layout (csrc/ptx.cuh r32_off): -> [M, 256]."""
+    G = (M + 31) // 32
+    return blocked.reshape(-1)[: G * 32 * 256].reshape(G, 64, 32, 4).permute(0, 2, 1, 3).reshape(G * 32, 256)[:M]
+
+
+def rows_to_r32(rows: torch.Tensor) -> torch.Tensor:
+    """[M, 256] -> the blocked layout, padded to whole 32-row groups."""
+    M = rows.shape[0]
+    G = (M + 31) // 32
+    pad = torch.zeros(G * 32, 256, dtype=rows.dtype, device=rows.device)
+    pad[:M] = rows
+    return pad.reshape(G, 32, 64, 4).permute(0, 2, 1, 3).contiguous().reshape(-1)
 
 
 def pack_reads(seqs: list[str] | list[bytes], pinned: bool = False):

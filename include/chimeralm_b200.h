@@ -109,11 +109,19 @@ int clm_profile_get(clm_ctx* ctx, int cat, double* total_ms, long long* launches
  * 2 bias+res->f32, 3 scorer (score[m] = sum_n gelu_erf(.)*w2[n] + b2, needs N == 256). */
 int clm_gemm(clm_ctx* ctx, const void* d_A, const void* d_W, const float* d_bias, int M, int N, int K, int epi,
              void* d_out, const float* d_res, const float* d_w2, float b2, float* d_score, void* stream);
+/* Fused first half of block `layer` (LayerNorm1 + in_proj + causal short conv + first gate; HF
+ * HyenaBlock/HyenaOperator.forward): d_res fp32 residual stream of B*T tokens in
+ * the blocked R32 layout (with >= 160 rows of slack after the last token); outputs vx = v*x1 and
+ * x0 as channel-major bf16 [B][256][Tp], Tp % 64 == 0. */
+int clm_block_in(clm_ctx* ctx, int layer, const float* d_res, int B, int T, int Tp, void* d_vx, void* d_x0, void* stream);
 /* Fused second half of block `layer` (out_proj + residual + LayerNorm2 + fc1 + GELU + fc2 +
  * residual; HF HyenaBlock.forward): d_y bf16 [M,256] token-major, d_res fp32
  * [M,256] read and overwritten with the block output. */
 int clm_block_mlp(clm_ctx* ctx, int layer, const void* d_y, float* d_res, int M, void* stream);
-/* Runtime switches: "fused_mlp" (default 1) selects the fused block kernel in clm_forward. */
+/* Same, and CTA 0 records clock64() stamps of its producer / MMA / epilogue roles into
+ * d_trace (int64 [3][64], zero-filled by the caller) - a timeline for tuning, not a product path. */
+int clm_block_mlp_trace(clm_ctx* ctx, int layer, const void* d_y, float* d_res, int M, long long* d_trace, void* stream);
+/* Runtime switches: "fused_mlp" / "fused_in" (default 1) select the fused block kernels in clm_forward. */
 int clm_set_option(clm_ctx* ctx, const char* name, int value);
 /* out = (causal_long_conv(vx, k_layer) + bias_layer * vx) * x0 on channel-major bf16 [B][D][Tp]. */
 int clm_longconv(clm_ctx* ctx, int layer, const void* d_vx, const void* d_x0, void* d_out, int B, int T, int Tp,

@@ -26,6 +26,15 @@ def _ids(B, T, seed, pad_left=0):
     return ids
 
 
+def _resid(engine, B, T):
+    """Residual stream from the device's blocked (R32) layout -> [B, T, D]."""
+    from chimeralm_b200.engine import r32_to_rows
+
+    M = B * T
+    raw = engine.debug_copy("resid", ((M + 31) // 32 * 32 * CFG.d_model,), torch.float32)
+    return r32_to_rows(raw, M).reshape(B, T, CFG.d_model).cpu()
+
+
 def _oracle_states(sd, ids):
     """Residual stream after every block + final hidden + logits, from the oracle."""
     import torch.nn.functional as F
@@ -50,12 +59,12 @@ def test_stagewise_residual_stream(engine, state_dict, B, T):
     try:
         engine.set_debug_stop(0, 0)
         engine.forward(ids.cuda())
-        got = engine.debug_copy("resid", (B, T, CFG.d_model), torch.float32).cpu()
+        got = _resid(engine, B, T)
         assert torch.equal(got, states[0]), "embedding gather must be exact"
         for l in range(CFG.n_layer):
             engine.set_debug_stop(l, 9)
             engine.forward(ids.cuda())
-            got = engine.debug_copy("resid", (B, T, CFG.d_model), torch.float32).cpu()
+            got = _resid(engine, B, T)
             err = (got - states[l + 1]).abs().max().item()
             assert err <= 5e-2, (l, err)
     finally:

@@ -121,3 +121,27 @@ def test_block_mlp_fused(engine, state_dict, M):
     torch.cuda.synchronize()
     err = (out.cpu() - ref).abs().max().item()
     assert err <= 2e-2, (M, err)
+
+
+@pytest.mark.parametrize("B,T", [(1, 70), (2, 300), (3, 1025), (2, 8193)])
+def test_block_in_fused(engine, state_dict, B, T):
+    """Fused LN1+in_proj+short conv+gate vs fp32 torch (oracle ops), channel-major outputs."""
+    from oracle import hyena_oracle as O
+
+    layer = 1
+    p = f"{O.BB}layers.{layer}."
+    sd = state_dict
+    g = torch.Generator().manual_seed(B * 10000 + T)
+    res = torch.randn(B, T, 256, generator=g) * 1.5 + 0.3
+    x = F.layer_norm(res, (256,), sd[p + "norm1.weight"], sd[p + "norm1.bias"], 1e-5)
+    u = F.linear(x, sd[p + "mixer.in_proj.weight"], sd[p + "mixer.in_proj.bias"]).transpose(1, 2)
+    uc = F.conv1d(u, sd[p + "mixer.short_filter.weight"], sd[p + "mixer.short_filter.bias"], padding=2, groups=768)[..., :T]
+    x0_ref, x1_ref, v_ref = uc.split(256, dim=1)
+    vx_ref = v_ref * x1_ref
+    vx, x0 = engine.block_in(layer, res.reshape(B * T, 256).cuda(), B, T)
+    torch.cuda.synchronize()
+    e_vx = (vx[..., :T].float().cpu() - vx_ref).abs().max().item()
+    e_x0 = (x0[..., :T].float().cpu() - x0_ref).abs().max().item()
+    # bf16 operands (K=256) + bf16 output rounding; |u| ~ 0.3, |vx| ~ 0.1
+    assert e_x0 <= 2e-2 * max(1.0, x0_ref.abs().max().item()), (e_x0, x0_ref.abs().max().item())
+    assert e_vx <= 2e-2 * max(1.0, vx_ref.abs().max().item()), (e_vx, vx_ref.abs().max().item())

@@ -1,0 +1,177 @@
+"""CPU tests (-m "not gpu") of the host-side mirror of the reference interface, the BAM
+reader/writer, the C-ABI surface and the FFT plan."""
+
+import ctypes
+import json
+import re
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+from chimeralm_b200 import _lib, tokenizer as T
+from chimeralm_b200.bam import BamReader, BamWriter, is_chimeric, parse_bam_file
+from chimeralm_b200.callbacks import PredictionWriter, load_predictions_from_folder, resume_read_name
+from oracle import tokenizer_oracle as TO
+
+ROOT = Path(__file__).resolve().parents[1]
+GOLD = ROOT / "tests" / "golden"
+BAM = GOLD / "test_chimric_reads.bam"
+
+
+@pytest.fixture(scope="module")
+def tok_gold():
+    return json.loads((GOLD / "tokenizer_golden.json").read_text())
+
+
+def test_character_tokenizer_mirror_matches_reference(tok_gold):
+    seqs = tok_gold["seqs"]
+    for case in tok_gold["cases"]:
+        mml = case["model_max_length"]
+        tok = T.CharacterTokenizer(model_max_length=mml, padding_side=case["padding_side"])
+        if mml is None:
+            got = [tok(s)["input_ids"] for s in seqs]
+        else:
+            assert tok.max_len_single_sentence == case["max_len_single_sentence"]
+            got = [tok(s, truncation=True, max_length=tok.max_len_single_sentence, padding=True)["input_ids"] for s in seqs]
+        assert got == case["input_ids"]
+        assert tok.pad_token_id == case["pad_token_id"]
+        if mml is not None:
+            feats = [T.tokenize_and_align_labels_and_quals_ids({"seq": s, "id": f"read-{i}/{len(s)}"}, tok, tok.max_len_single_sentence)
+                     for i, s in enumerate(seqs)]
+            batch = T.DataCollator(tok).torch_call(feats)
+            assert batch["input_ids"].tolist() == case["collated_input_ids"]
+            assert batch["id"].tolist() == case["collated_id"] and batch["id"].dtype == torch.int8
+            assert batch["labels"].tolist() == case["collated_labels"]
+
+
+def test_reference_kats_on_mirror():
+    tok = T.CharacterTokenizer()
+    enc = tok.encode("ATCG")
+    assert enc == [0, 7, 10, 8, 9, 1]
+    assert tok.convert_ids_to_tokens(enc) == ["[CLS]", "A", "T", "C", "G", "[SEP]"]
+    assert tok.decode(enc) == "ATCG"
+
+
+def test_hub_flavour_tokenizer():
+    tok = T.load_tokenizer_from_hyena_model("hyenadna-small-32k-seqlen")
+    assert tok.padding_side == "left" and tok.max_len_single_sentence == 32769
+    assert tok("ATCGCGTG")["input_ids"] == [7, 10, 8, 9, 8, 9, 10, 9, 1]  # notebooks/attention.ipynb:502: 8 bases + 1 special
+    long = tok("A" * 40000, truncation=True, max_length=tok.max_len_single_sentence)["input_ids"]
+    assert len(long) == 32769 and long[-1] == 1
+    with pytest.raises(ValueError):
+        T.load_tokenizer_from_hyena_model("nope")
+
+
+def test_bam_reader_matches_survey_probe():
+    recs = list(parse_bam_file(BAM))
+    lens = [len(r["seq"]) for r in recs]
+    assert len(recs) == 100 and min(lens) == 524 and max(lens) == 137138 and sum(lens) == 1223444
+    assert sum(1 for x in lens if x > 32768) == 11
+    assert set("".join(r["seq"][:2000] for r in recs)) <= set("ACGT")
+    with BamReader(BAM) as bam:
+        flags = {}
+        for r in bam:
+            assert is_chimeric(r)
+            flags[r.flag] = flags.get(r.flag, 0) + 1
+    assert flags == {0: 60, 16: 40}
+
+
+def test_bam_write_roundtrip(tmp_path):
+    out = tmp_path / "copy.bam"
+    with BamReader(BAM) as bam:
+        w = BamWriter(out, bam.header_bytes())
+        recs = [r for _, r in zip(range(20), bam)]
+        for r in recs:
+            w.write(r)
+        w.close()
+    with BamReader(out) as again:
+        back = list(again)
+    assert [r.raw for r in back] == [r.raw for r in recs]
+    assert out.read_bytes().endswith(bytes.fromhex("1f8b08040000000000ff0600424302001b0003000000000000000000"))
+
+
+def test_prediction_writer_and_loader(tmp_path):
+    class Tr:
+        global_rank = 3
+
+    names = ["read/1", "m64011_190830_220126/1/ccs", "x"]
+    ids = torch.tensor([T.encode_read_name(n) for n in names], dtype=torch.int8)
+    logits = torch.tensor([[0.2, 0.1], [0.0, 3.0], [1.0, 1.0]])
+    w = PredictionWriter(tmp_path / "pred", "batch")
+    w.write_on_batch_end(Tr(), None, (logits, torch.full((3,), -1)), None, {"id": ids}, 7, 0)
+    f = tmp_path / "pred" / "3_7.txt"
+    assert f.read_text() == "read/1\t0\nm64011_190830_220126/1/ccs\t1\nx\t0\n"
+    assert f.read_text().splitlines(keepends=True) == TO.prediction_lines(names, [0, 1, 0])
+    assert load_predictions_from_folder(tmp_path / "pred") == {"read/1": 0, "m64011_190830_220126/1/ccs": 1, "x": 0}
+    assert [resume_read_name(r) for r in ids] == names
+    with pytest.raises(TypeError):
+        PredictionWriter(None)  # reference behaviour when -o is omitted
+
+
+def test_c_abi_library_exports_every_declared_symbol():
+    header = (ROOT / "include" / "chimeralm_b200.h").read_text()
+    declared = set(re.findall(r"\b(clm_[a-z0-9_]+)\s*\(", header))
+    declared -= {"clm_ctx", "clm_status", "clm_dtype", "clm_config"}
+    assert declared, "no declarations parsed"
+    lib = ctypes.CDLL(str(_lib.LIB_PATH))
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in include/chimeralm_b200.h but not exported"
+    assert declared == set(_lib.EXPORTED_SYMBOLS), declared ^ set(_lib.EXPORTED_SYMBOLS)
+    handle = _lib.load()
+    assert handle.clm_version().decode().startswith("chimeralm_b200")
+    cfg = _lib.clm_config()
+    handle.clm_default_config(ctypes.byref(cfg))
+    assert (cfg.d_model, cfg.n_layer, cfg.d_inner, cfg.vocab_rows, cfg.max_seq_len) == (256, 4, 1024, 16, 32770)
+
+
+def test_engine_fails_loudly_without_gpu():
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from chimeralm_b200.engine import Engine
+    from chimeralm_b200.weights import make_state_dict
+
+    with pytest.raises(_lib.ChimeraLMNativeError):
+        Engine(make_state_dict(0))
+
+
+def test_fft_plan_on_host():
+    exe = ROOT / "oracle" / "_build" / "fft_host_test"
+    if not exe.exists():
+        import __graft_entry__ as g
+
+        g.build()
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "OK" in r.stdout, r.stdout + r.stderr
+
+
+def test_weight_factory_is_deterministic_and_ckpt_roundtrip(tmp_path):
+    from chimeralm_b200.weights import load_checkpoint, make_state_dict, save_lightning_ckpt
+
+    a, b = make_state_dict(5), make_state_dict(5)
+    assert all(torch.equal(a[k], b[k]) for k in a)
+    save_lightning_ckpt(a, tmp_path / "m.ckpt")
+    c = load_checkpoint(tmp_path / "m.ckpt")
+    assert list(c) == list(a) and all(torch.equal(a[k], c[k]) for k in a)
+
+
+def test_data_module_reference_batching():
+    from chimeralm_b200.data import BamDataModule
+
+    tok = T.load_tokenizer_from_hyena_model("hyenadna-small-32k-seqlen")
+    dm = BamDataModule(tok, batch_size=12, predict_data_path=BAM)
+    dm.setup("predict")
+    shapes = [tuple(b["input_ids"].shape) for b in dm.predict_dataloader()]
+    # 9 batches (8 x 12 + 4) with these padded lengths
+    assert [s[0] for s in shapes] == [12] * 8 + [4]
+    assert [s[1] for s in shapes] == [32769, 32769, 22074, 32769, 32769, 32769, 26141, 32769, 31855]
+    first = next(iter(dm.predict_dataloader()))
+    assert first["input_ids"].dtype == torch.int64 and first["id"].dtype == torch.int8
+    assert first["labels"].tolist() == [-1] * 12
+    # rank sharding (Lightning's unrepeated sampler): rank r takes samples r, r+W, ...
+    dm2 = BamDataModule(tok, batch_size=12, predict_data_path=BAM, rank=1, world_size=2)
+    dm2.setup("predict")
+    assert dm2.batch_size_per_device == 6
+    assert sum(b["input_ids"].shape[0] for b in dm2.predict_dataloader()) == 50
