@@ -17,6 +17,7 @@
 #include "gemm_tcgen05.cuh"
 #include "kernels.cuh"
 #include "longconv.cuh"
+#include "longconv_fast.cuh"
 
 using namespace clm;
 
@@ -40,6 +41,7 @@ struct LayerW {
   CUtensorMap tm_inf;
   float* k = nullptr;                               // [D][Lk]
   float2* gspec[LONGCONV_MAX_LOGN + 1] = {nullptr};  // per LOGN: [n_seg][D][N]
+  float2* gspecT[LONGCONV_MAX_LOGN + 1] = {nullptr}; // per LOGN: [D][16][N/16], bias folded (longconv_fast)
 };
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -92,6 +94,7 @@ struct clm_ctx {
   long long prof_n[32] = {0};
   bool fused_mlp = true;  // out_proj+res+LN2+fc1+gelu+fc2+res in one kernel
   bool fused_in = true;   // LN1+in_proj+short conv+gate in one kernel
+  bool fast_conv = true;  // tuned single-chunk long convolution
   // debug
   int dbg_layer = -1, dbg_stage = -1;
   long long launches = 0;
@@ -309,6 +312,39 @@ int spectrum_t(clm_ctx* c, LayerW& L) {
 }
 
 template <int LOGN>
+int spectrum_fast_t(clm_ctx* c, LayerW& L) {
+  if constexpr (FastCfg<LOGN>::kSupported) {
+    using Cfg = ConvCfg<LOGN>;
+    const int D = c->cfg.d_model;
+    int rc = dev_alloc(c, &L.gspecT[LOGN], (size_t)D * Cfg::N);
+    if (rc) return rc;
+    auto kern = filter_spectrum_fast_kernel<LOGN>;
+    CLM_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+    kern<<<D, Cfg::THREADS, Cfg::SMEM>>>(L.k, c->Lk, c->cfg.max_seq_len, L.fbias, L.gspecT[LOGN], D);
+    CLM_LAUNCH_CHECK(c, "filter_spectrum_fast");
+  }
+  return 0;
+}
+
+template <int LOGN>
+int conv_fast_t(clm_ctx* c, const LongConvFastParams& p, int grid, cudaStream_t st) {
+  if constexpr (FastCfg<LOGN>::kSupported) {
+    using F = FastCfg<LOGN>;
+    static bool attr_set = false;
+    auto kern = longconv_fast_kernel<LOGN>;
+    if (!attr_set) {
+      CLM_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, F::SMEM));
+      attr_set = true;
+    }
+    kern<<<grid, F::THREADS, F::SMEM, st>>>(p);
+    CLM_LAUNCH_CHECK(c, "longconv_fast");
+    return 0;
+  } else {
+    return fail(c, CLM_ERR_INVALID, "longconv_fast: unsupported size");
+  }
+}
+
+template <int LOGN>
 int conv_t(clm_ctx* c, const LongConvParams& p, int grid, cudaStream_t st) {
   using Cfg = ConvCfg<LOGN>;
   static bool attr_set = false;
@@ -333,6 +369,22 @@ int launch_longconv(clm_ctx* c, int layer, const __nv_bfloat16* vx, const __nv_b
   if (T > c->cfg.max_seq_len) return fail(c, CLM_ERR_INVALID, "longconv: T=%d exceeds max_seq_len=%d", T, c->cfg.max_seq_len);
   const ConvPlan pl = plan_conv(T);
   LayerW& L = c->layers[layer];
+  if (c->fast_conv && pl.n_chunks == 1 && L.gspecT[pl.logn] != nullptr) {
+    LongConvFastParams f{};
+    f.vx = vx; f.x0 = x0; f.out = out; f.gT = L.gspecT[pl.logn]; f.k = L.k; f.dbias = L.fbias; f.Lk = c->Lk;
+    f.B = B; f.D = c->cfg.d_model; f.T = T; f.Tp = Tp;
+    f.n_items = c->cfg.d_model * ((B + 1) / 2);
+    int grid = f.n_items;
+    if (pl.logn >= 13) grid = std::min(grid, c->num_sms);
+    else grid = std::min(grid, c->num_sms * 4);
+    switch (pl.logn) {
+      case 9: return conv_fast_t<9>(c, f, grid, st);
+      case 10: return conv_fast_t<10>(c, f, grid, st);
+      case 11: return conv_fast_t<11>(c, f, grid, st);
+      case 13: return conv_fast_t<13>(c, f, grid, st);
+      case 14: return conv_fast_t<14>(c, f, grid, st);
+    }
+  }
   LongConvParams p{};
   p.vx = vx; p.x0 = x0; p.out = out;
   p.gspec = L.gspec[pl.logn];
@@ -566,6 +618,11 @@ int clm_finalize(clm_ctx* c) {
     if ((rc = spectrum_t<12>(c, L))) return rc;
     if ((rc = spectrum_t<13>(c, L))) return rc;
     if ((rc = spectrum_t<14>(c, L))) return rc;
+    if ((rc = spectrum_fast_t<9>(c, L))) return rc;
+    if ((rc = spectrum_fast_t<10>(c, L))) return rc;
+    if ((rc = spectrum_fast_t<11>(c, L))) return rc;
+    if ((rc = spectrum_fast_t<13>(c, L))) return rc;
+    if ((rc = spectrum_fast_t<14>(c, L))) return rc;
   }
   // head
   const float *a0w, *a2b;
@@ -802,6 +859,7 @@ int clm_set_option(clm_ctx* c, const char* name, int value) {
   const std::string n(name);
   if (n == "fused_mlp") c->fused_mlp = value != 0;
   else if (n == "fused_in") c->fused_in = value != 0;
+  else if (n == "fast_conv") c->fast_conv = value != 0;
   else return fail(c, CLM_ERR_INVALID, "clm_set_option: unknown option '%s'", name);
   return 0;
 }

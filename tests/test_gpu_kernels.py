@@ -62,7 +62,7 @@ def test_implicit_filter(engine, state_dict):
         assert err <= 2e-5, (layer, err)
 
 
-@pytest.mark.parametrize("T", [1, 37, 128, 131, 1000, 2049, 4096, 8193, 8292, 20000, 32769])
+@pytest.mark.parametrize("T", [1, 37, 128, 131, 200, 515, 1000, 2049, 4096, 4100, 8193, 8292, 20000, 32769])
 def test_longconv(engine, state_dict, T):
     from oracle import hyena_oracle as O
 
