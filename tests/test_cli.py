@@ -1,0 +1,56 @@
+"""CPU tests (-m "not gpu") of the command line surface (chimeralm/__main__.py:248-333 mirror)."""
+
+import subprocess
+import sys
+from pathlib import Path
+
+from typer.testing import CliRunner
+
+ROOT = Path(__file__).resolve().parents[1]
+BAM = ROOT / "tests" / "golden" / "test_chimric_reads.bam"
+
+
+def test_help_lists_reference_commands_and_flags():
+    from chimeralm_b200.__main__ import app
+
+    r = CliRunner().invoke(app, ["--help"])
+    assert r.exit_code == 0 and "predict" in r.output and "filter" in r.output
+    r = CliRunner().invoke(app, ["predict", "--help"])
+    for flag in ("--gpus", "-g", "--output", "-o", "--batch-size", "-b", "--workers", "-w", "--random", "-r", "--verbose", "-v",
+                 "--ckpt", "--max-sample"):
+        assert flag in r.output, flag
+    r = CliRunner().invoke(app, ["--version"])
+    assert r.exit_code == 0 and "chimeralm-b200" in r.output
+
+
+def test_predict_without_gpu_fails_loudly(tmp_path):
+    import torch
+
+    if torch.cuda.is_available():
+        return
+    r = subprocess.run([sys.executable, "-m", "chimeralm_b200", "predict", str(BAM), "-o", str(tmp_path / "o")], cwd=ROOT,
+                       capture_output=True, text=True)
+    assert r.returncode == 2 and "no CPU fallback" in (r.stdout + r.stderr)
+
+
+def test_filter_drops_label1_and_keeps_unknown(tmp_path):
+    from chimeralm_b200.__main__ import app
+    from chimeralm_b200.bam import BamReader, parse_bam_file
+
+    bam = tmp_path / "in.bam"
+    bam.write_bytes(BAM.read_bytes())
+    names = [r["id"] for r in parse_bam_file(bam)]
+    pred = tmp_path / "pred"
+    pred.mkdir()
+    (pred / "0_0.txt").write_text("".join(f"{n}\t{i % 3 == 0 and 1 or 0}\n" for i, n in enumerate(names[:60])))
+    r = CliRunner().invoke(app, ["filter", str(bam), str(pred), "-p"])
+    assert r.exit_code == 0, r.output
+    out = tmp_path / "in.filtered.bam"
+    with BamReader(out) as f:
+        kept = [rec.name for rec in f]
+    dropped = {n for i, n in enumerate(names[:60]) if i % 3 == 0}
+    assert kept == [n for n in names if n not in dropped]          # reads without a prediction are kept
+    assert (pred / "predictions.txt").exists()
+    with BamReader(tmp_path / "in.filtered.sorted.bam") as f:
+        keys = [((rec.ref_id & 0xFFFFFFFF), rec.pos) for rec in f]
+    assert keys == sorted(keys) and len(keys) == len(kept)

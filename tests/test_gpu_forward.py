@@ -89,3 +89,65 @@ def test_logits_and_labels(engine, state_dict, B, T):
     # int64 ids (the reference's dtype) take the same path
     logits64 = engine.forward(ids.cuda()).cpu()
     assert torch.equal(logits64, logits)
+
+
+def test_k1_bam_anchor_end_to_end(tmp_path, state_dict):
+    """K1 (BASELINE.json configs[0]): `predict` on the reference's test BAM, batch 12, file order,
+    Hub-flavour tokens, through the mirrored Trainer/BamDataModule/PredictionWriter stack.  The
+    first batch (12 reads padded to 32 769 tokens: chunked FFT path, 11x left padding) is
+    checked against the oracle on identical padded ids; every read must get a prediction line."""
+    from pathlib import Path
+
+    from chimeralm_b200.callbacks import PredictionWriter, load_predictions_from_folder
+    from chimeralm_b200.data import BamDataModule, Trainer
+    from chimeralm_b200.model import ClassificationLit
+    from chimeralm_b200.tokenizer import load_tokenizer_from_hyena_model
+    from oracle import hyena_oracle as O
+    from oracle import tokenizer_oracle as TO
+    from chimeralm_b200.bam import parse_bam_file
+
+    bam = Path(__file__).parent / "golden" / "test_chimric_reads.bam"
+    tok = load_tokenizer_from_hyena_model("hyenadna-small-32k-seqlen")
+    model = ClassificationLit(state_dict, device=0, max_batch=12, max_tokens=32769)
+    dm = BamDataModule(tok, batch_size=12, predict_data_path=bam, engine=model.engine)
+    out = tmp_path / "pred"
+    trainer = Trainer(callbacks=[PredictionWriter(out, "batch")])
+    res = trainer.predict(model, dataloaders=dm, return_predictions=True)
+    preds = load_predictions_from_folder(out)
+    recs = list(parse_bam_file(bam))
+    assert len(preds) == 100 and set(preds) == {r["id"] for r in recs}
+    assert sorted(p.name for p in out.glob("*.txt")) == sorted(f"0_{i}.txt" for i in range(9))
+    # first batch vs oracle (token ids from the oracle tokenizer: bit-exact check of the GPU encoder too)
+    ids_ref = TO.collate([TO.encode(r["seq"], max_length=32769, add_cls=False) for r in recs[:12]], padding_side="left")
+    dm.setup("predict")
+    first = next(iter(dm.predict_dataloader()))
+    assert first["input_ids"].cpu().tolist() == ids_ref
+    logits = model.forward(first["input_ids"]).cpu()
+    ref = O.forward(state_dict, torch.tensor(ids_ref), CFG)
+    err = (logits - ref).abs().max().item()
+    assert err <= LOGIT_TOL, err
+    margin = ref[:, 1] - ref[:, 0]
+    decided = margin.abs() > 2 * LOGIT_TOL
+    got = torch.tensor([preds[r["id"]] for r in recs[:12]])
+    assert torch.equal(got[decided], ref.argmax(1)[decided])
+    model.engine.close()
+
+
+def test_mixed_lengths_bucketed(engine, state_dict):
+    """K3-style ragged batch: reads of different lengths, left-padded to the batch maximum by the GPU
+    encoder; logits vs oracle on the same padded ids."""
+    from chimeralm_b200.engine import pack_reads
+    from oracle import hyena_oracle as O
+    from oracle import tokenizer_oracle as TO
+
+    g = torch.Generator().manual_seed(11)
+    lens = [1000, 1733, 2950, 400, 2999, 1, 0, 2048]
+    seqs = ["".join("ACGT"[int(x)] for x in torch.randint(0, 4, (n,), generator=g)) for n in lens]
+    ids_ref = TO.collate([TO.encode(s, max_length=32769, add_cls=False) for s in seqs], padding_side="left")
+    T = len(ids_ref[0])
+    bases, offs = pack_reads(seqs)
+    ids, lens_dev = engine.encode(bases, offs, T, add_cls=False, add_sep=True, pad_left=True, max_bases=32768)
+    assert ids.cpu().tolist() == ids_ref and lens_dev.cpu().tolist() == [n + 1 for n in lens]
+    logits = engine.forward(ids).cpu()
+    ref = O.forward(state_dict, torch.tensor(ids_ref), CFG)
+    assert (logits - ref).abs().max().item() <= LOGIT_TOL
