@@ -95,6 +95,7 @@ struct clm_ctx {
   bool fused_mlp = true;  // out_proj+res+LN2+fc1+gelu+fc2+res in one kernel
   bool fused_in = true;   // LN1+in_proj+short conv+gate in one kernel
   bool fast_conv = true;  // tuned single-chunk long convolution
+  bool y_channel_major = true;  // block_mlp reads the conv output channel-major (MN-major UMMA operand): no transpose
   // debug
   int dbg_layer = -1, dbg_stage = -1;
   long long launches = 0;
@@ -254,8 +255,9 @@ int launch_block_in(clm_ctx* c, int layer, const float* res, int B, int T, int T
   return 0;
 }
 
+// y token-major [M,256] when B == 0; channel-major [B][256][Tp] (M == B*T) otherwise
 int launch_block_mlp(clm_ctx* c, int layer, const __nv_bfloat16* y, float* res, int M, cudaStream_t st,
-                     long long* trace = nullptr) {
+                     long long* trace = nullptr, int B = 0, int T = 0, int Tp = 0) {
   static bool attr_set = false;
   if (!attr_set) {
     CLM_CUDA(c, cudaFuncSetAttribute(block_mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bm::SMEM_TOTAL));
@@ -263,13 +265,26 @@ int launch_block_mlp(clm_ctx* c, int layer, const __nv_bfloat16* y, float* res, 
   }
   LayerW& L = c->layers[layer];
   CUtensorMap tmY;
-  int rc = make_tmap_bf16_2d(c, &tmY, y, (uint64_t)M, (uint64_t)c->cfg.d_model, 128);
-  if (rc) return rc;
+  int rc;
+  if (B > 0) {
+    cuuint64_t dims[3] = {(cuuint64_t)Tp, (cuuint64_t)c->cfg.d_model, (cuuint64_t)B};
+    cuuint64_t strides[2] = {(cuuint64_t)Tp * 2, (cuuint64_t)Tp * c->cfg.d_model * 2};
+    cuuint32_t box[3] = {64, 64, 1}, estr[3] = {1, 1, 1};
+    CUresult r = c->encode_tiled(&tmY, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<__nv_bfloat16*>(y), dims, strides, box,
+                                 estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(c, CLM_ERR_CUDA, "cuTensorMapEncodeTiled(y channel-major) failed with CUresult %d", (int)r);
+  } else if ((rc = make_tmap_bf16_2d(c, &tmY, y, (uint64_t)M, (uint64_t)c->cfg.d_model, 128))) {
+    return rc;
+  }
   BlockMlpParams p{};
   p.M = M; p.res = res; p.b_out = L.out_b; p.ln_g = L.ln2_g; p.ln_b = L.ln2_b; p.b1 = L.fc1_b; p.b2 = L.fc2_b;
   p.eps = c->cfg.layer_norm_eps;
   p.num_tiles = (M + bm::BM - 1) / bm::BM;
   p.trace = trace;
+  if (B > 0) {
+    p.y_cm = 1; p.T = T; p.tiles_per_seq = (T + bm::BM - 1) / bm::BM; p.num_tiles = B * p.tiles_per_seq;
+  }
   const int grid = std::min(p.num_tiles, c->num_sms);
   block_mlp_kernel<<<grid, bm::THREADS, bm::SMEM_TOTAL, st>>>(tmY, L.tm_out, L.tm_fc1, L.tm_fc2, p);
   CLM_LAUNCH_CHECK(c, "block_mlp");
@@ -763,13 +778,18 @@ int clm_forward(clm_ctx* c, const void* d_ids, int ids_dtype, int B, int T, floa
     { ProfScope ps_(c, PC_LONGCONV, st);
     if ((rc = launch_longconv(c, l, c->VX, c->X0, c->Y, B, T, Tp, c->scratch, c->scratch_bytes, st))) return rc; }
     STOP_AFTER(l, 4);
-    { ProfScope ps_(c, PC_TRANSPOSE, st);
-    transpose_ct_kernel<<<dim3((T + 63) / 64, D / 64, B), 256, 0, st>>>(c->Y, c->YT, T, Tp, D);
-    CLM_LAUNCH_CHECK(c, "transpose_ct"); }
+    const bool mlp_fused = c->fused_mlp && c->dbg_layer != l;
+    if (!(mlp_fused && c->y_channel_major)) {
+      ProfScope ps_(c, PC_TRANSPOSE, st);
+      transpose_ct_kernel<<<dim3((T + 63) / 64, D / 64, B), 256, 0, st>>>(c->Y, c->YT, T, Tp, D);
+      CLM_LAUNCH_CHECK(c, "transpose_ct");
+    }
     STOP_AFTER(l, 5);
-    if (c->fused_mlp && c->dbg_layer != l) {
+    if (mlp_fused) {
       ProfScope ps_(c, PC_BLOCK_MLP, st);
-      if ((rc = launch_block_mlp(c, l, c->YT, c->R, (int)M, st))) return rc;
+      if (c->y_channel_major) rc = launch_block_mlp(c, l, c->Y, c->R, (int)M, st, nullptr, B, T, Tp);
+      else rc = launch_block_mlp(c, l, c->YT, c->R, (int)M, st);
+      if (rc) return rc;
     } else {
       GemmParams p{};
       p.M = (int)M; p.N = D; p.K = D; p.bias = L.out_b; p.out = c->R; p.res = c->R; p.ldo = D; p.r32 = 1;
@@ -860,6 +880,7 @@ int clm_set_option(clm_ctx* c, const char* name, int value) {
   if (n == "fused_mlp") c->fused_mlp = value != 0;
   else if (n == "fused_in") c->fused_in = value != 0;
   else if (n == "fast_conv") c->fast_conv = value != 0;
+  else if (n == "y_channel_major") c->y_channel_major = value != 0;
   else return fail(c, CLM_ERR_INVALID, "clm_set_option: unknown option '%s'", name);
   return 0;
 }
@@ -875,6 +896,13 @@ int clm_block_mlp(clm_ctx* c, int layer, const void* d_y, float* d_res, int M, v
   if (!c || !c->finalized) return fail(c, CLM_ERR_STATE, "clm_block_mlp before clm_finalize");
   if (layer < 0 || layer >= c->cfg.n_layer || !d_y || !d_res || M <= 0) return fail(c, CLM_ERR_INVALID, "clm_block_mlp: bad argument");
   return launch_block_mlp(c, layer, (const __nv_bfloat16*)d_y, d_res, M, (cudaStream_t)stream);
+}
+
+int clm_block_mlp_cm(clm_ctx* c, int layer, const void* d_y_cm, float* d_res, int B, int T, int Tp, void* stream) {
+  if (!c || !c->finalized) return fail(c, CLM_ERR_STATE, "clm_block_mlp_cm before clm_finalize");
+  if (layer < 0 || layer >= c->cfg.n_layer || !d_y_cm || !d_res || B <= 0 || T <= 0 || Tp < T || Tp % 64 != 0)
+    return fail(c, CLM_ERR_INVALID, "clm_block_mlp_cm: bad argument");
+  return launch_block_mlp(c, layer, (const __nv_bfloat16*)d_y_cm, d_res, B * T, (cudaStream_t)stream, nullptr, B, T, Tp);
 }
 
 int clm_block_mlp_trace(clm_ctx* c, int layer, const void* d_y, float* d_res, int M, long long* d_trace, void* stream) {

@@ -40,6 +40,10 @@ struct BlockMlpParams {
   const float* b2;       // [256]
   float eps;
   int num_tiles;
+  // y_cm == 0: y is token-major [M,256] (tmY 2-D, tiles of 128 consecutive rows).
+  // y_cm == 1: y is channel-major [B][256][Tp] (tmY 3-D {t, c, b}); tiles are 128 tokens of ONE read,
+  //            fed to out_proj as an MN-major A operand, so no transpose pass is needed.
+  int y_cm, T, tiles_per_seq;
   long long* trace;      // optional [3][64] clock64 stamps written by CTA 0 (null in production)
 };
 
@@ -141,7 +145,14 @@ block_mlp_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
         const int m0 = tile * BM;
         ptx::mbar_wait(x_free, (it & 1) ^ 1);
         ptx::mbar_expect_tx(x_full, X_BYTES);
-        for (int kb = 0; kb < 4; ++kb) ptx::tma_load_2d(smem + OFF_X + kb * KB_BYTES, &tmY, x_full, kb * BK, m0);
+        if (p.y_cm) {
+          const int b = tile / p.tiles_per_seq, t0 = (tile % p.tiles_per_seq) * BM;
+          for (int kb = 0; kb < 4; ++kb)    // k-block = 64 channels; two 64-token halves of 8 KB each
+            for (int hh = 0; hh < 2; ++hh)
+              ptx::tma_load_3d(smem + OFF_X + kb * KB_BYTES + hh * (KB_BYTES / 2), &tmY, x_full, t0 + hh * 64, kb * BK, b);
+        } else {
+          for (int kb = 0; kb < 4; ++kb) ptx::tma_load_2d(smem + OFF_X + kb * KB_BYTES, &tmY, x_full, kb * BK, m0);
+        }
         stamp(0);
         // out_proj weights: 4 k-blocks of [256 x 64]
         for (int kb = 0; kb < 4; ++kb) {
@@ -179,6 +190,7 @@ block_mlp_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
     // =========================== MMA issuer ===========================
     if (lane == 0) {
       constexpr uint32_t idesc256 = ptx::idesc_bf16_f32(BM, 256);
+      constexpr uint32_t idesc256_amn = ptx::idesc_bf16_f32_amn(BM, 256);
       constexpr uint32_t idesc128 = ptx::idesc_bf16_f32(BM, 128);
       const uint32_t sX = ptx::smem_u32(smem + OFF_X);
       const uint32_t sHB = ptx::smem_u32(smem + OFF_HB);
@@ -205,10 +217,18 @@ block_mlp_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
         stamp(1);
         for (int kb = 0; kb < 4; ++kb) {
           const uint32_t sw = slot_wait();
-          const uint64_t da = ptx::smem_desc_k_sw128(sX + kb * KB_BYTES);
           const uint64_t db = ptx::smem_desc_k_sw128(sw);
+          if (p.y_cm) {
+            // A = y^T tile: MN(token)-major, 2 atoms of 64 tokens 8 KB apart, K rows of 128 B; 16 K-rows per step
+            const uint64_t da = ptx::smem_desc_mn_sw128(sX + kb * KB_BYTES, KB_BYTES / 2, 1024);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) ptx::umma_f16(tmem_base + TM_R, da + 2 * k, db + 2 * k, idesc256, (kb | k) != 0);
+            for (int k = 0; k < 4; ++k)
+              ptx::umma_f16(tmem_base + TM_R, da + (2048 >> 4) * k, db + 2 * k, idesc256_amn, (kb | k) != 0);
+          } else {
+            const uint64_t da = ptx::smem_desc_k_sw128(sX + kb * KB_BYTES);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) ptx::umma_f16(tmem_base + TM_R, da + 2 * k, db + 2 * k, idesc256, (kb | k) != 0);
+          }
           slot_release();
         }
         ptx::umma_commit(g1_done);
@@ -271,8 +291,16 @@ block_mlp_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
       const uint32_t tph = it & 1;
-      const long long row = (long long)tile * BM + r;
-      const bool row_ok = row < p.M;
+      long long row;
+      bool row_ok;
+      if (p.y_cm) {
+        const int b = tile / p.tiles_per_seq, t = (tile % p.tiles_per_seq) * BM + r;
+        row = (long long)b * p.T + t;
+        row_ok = t < p.T;
+      } else {
+        row = (long long)tile * BM + r;
+        row_ok = row < p.M;
+      }
       // ------------------------------------------------ E1: r1, LayerNorm2 -> xn
       // The residual half-row (128 fp32) is fetched into registers BEFORE waiting for the
       // out_proj accumulator, so its DRAM latency hides behind the y-tile load and G1.

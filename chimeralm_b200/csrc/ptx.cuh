@@ -176,6 +176,26 @@ __device__ __forceinline__ uint64_t smem_desc_k_sw128(uint32_t saddr) {
   return d;
 }
 
+// Shared-memory matrix descriptor for an MN-major bf16 operand tile laid out (as TMA writes a
+// {64 MN-elements, R K-rows} box with the 128-byte swizzle) as atoms of 8 K-rows x 128 bytes:
+//   MN index: 8 x 16-byte chunks inside a row, then 64-element atoms `lbo_bytes` apart;
+//   K  index: 8 rows 128 B apart, then 8-row groups `sbo_bytes` apart (1024 when rows are contiguous).
+// (cute/atom/mma_traits_sm100.hpp make_umma_desc<Major::MN>: ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16 B units.)
+__device__ __forceinline__ uint64_t smem_desc_mn_sw128(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((saddr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+
+// Same as idesc_bf16_f32 but the A operand is MN-major (bit 15).
+__host__ __device__ constexpr uint32_t idesc_bf16_f32_amn(uint32_t M, uint32_t N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+
 // Instruction descriptor, kind::f16, bf16 x bf16 -> fp32, both operands K-major
 // (cute/arch/mma_sm100_desc.hpp InstrDescriptor).
 __host__ __device__ constexpr uint32_t idesc_bf16_f32(uint32_t M, uint32_t N) {

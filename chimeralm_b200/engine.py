@@ -198,6 +198,15 @@ class Engine:
         self._check(rc, "clm_block_mlp")
         return r32_to_rows(blocked, M)
 
+    def block_mlp_cm(self, layer: int, y_cm: torch.Tensor, res: torch.Tensor, T: int) -> torch.Tensor:
+        """Fused block tail from the channel-major conv output y_cm bf16 [B,256,Tp]; res fp32 [B*T,256]."""
+        B, _, Tp = y_cm.shape
+        blocked = rows_to_r32(torch.cat([res, torch.zeros(160, 256, dtype=res.dtype, device=res.device)]))
+        rc = self.lib.clm_block_mlp_cm(self.ctx, layer, C.c_void_p(y_cm.data_ptr()), C.c_void_p(blocked.data_ptr()), B, T, Tp,
+                                       _stream_ptr(self.device))
+        self._check(rc, "clm_block_mlp_cm")
+        return r32_to_rows(blocked, B * T)
+
     def set_option(self, name: str, value: int) -> None:
         self._check(self.lib.clm_set_option(self.ctx, name.encode(), int(value)), "clm_set_option")
 

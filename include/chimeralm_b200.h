@@ -118,6 +118,9 @@ int clm_block_in(clm_ctx* ctx, int layer, const float* d_res, int B, int T, int 
  * residual; HF HyenaBlock.forward): d_y bf16 [M,256] token-major, d_res fp32
  * [M,256] read and overwritten with the block output. */
 int clm_block_mlp(clm_ctx* ctx, int layer, const void* d_y, float* d_res, int M, void* stream);
+/* Same block tail, but y is the long convolution's channel-major output bf16 [B][256][Tp] (consumed as
+ * an MN-major tensor-core operand, no transpose); d_res holds B*T rows in the R32 layout. */
+int clm_block_mlp_cm(clm_ctx* ctx, int layer, const void* d_y_cm, float* d_res, int B, int T, int Tp, void* stream);
 /* Same, and CTA 0 records clock64() stamps of its producer / MMA / epilogue roles into
  * d_trace (int64 [3][64], zero-filled by the caller) - a timeline for tuning, not a product path. */
 int clm_block_mlp_trace(clm_ctx* ctx, int layer, const void* d_y, float* d_res, int M, long long* d_trace, void* stream);

@@ -145,3 +145,29 @@ def test_block_in_fused(engine, state_dict, B, T):
     # bf16 operands (K=256) + bf16 output rounding; |u| ~ 0.3, |vx| ~ 0.1
     assert e_x0 <= 2e-2 * max(1.0, x0_ref.abs().max().item()), (e_x0, x0_ref.abs().max().item())
     assert e_vx <= 2e-2 * max(1.0, vx_ref.abs().max().item()), (e_vx, vx_ref.abs().max().item())
+
+
+@pytest.mark.parametrize("B,T", [(1, 128), (2, 300), (3, 1025)])
+def test_block_mlp_channel_major_operand(engine, state_dict, B, T):
+    """Same fused block tail, fed the conv output channel-major (MN-major UMMA A operand)."""
+    from oracle import hyena_oracle as O
+
+    layer = 0
+    p = f"{O.BB}layers.{layer}."
+    Tp = (T + 63) // 64 * 64
+    g = torch.Generator().manual_seed(B * 977 + T)
+    y_cm = torch.zeros(B, 256, Tp, dtype=torch.bfloat16)
+    y_cm[..., :T] = _rand_bf16((B, 256, T), g)
+    y_cm[..., T:] = 3.0  # pad region must not matter
+    res = torch.randn(B * T, 256, generator=g)
+    q = lambda w: w.to(torch.bfloat16).float()
+    sd = state_dict
+    y = y_cm[..., :T].float().transpose(1, 2).reshape(B * T, 256)
+    r1 = y @ q(sd[p + "mixer.out_proj.weight"]).T + sd[p + "mixer.out_proj.bias"] + res
+    xn = F.layer_norm(r1, (256,), sd[p + "norm2.weight"], sd[p + "norm2.bias"], 1e-5).to(torch.bfloat16).float()
+    h = F.gelu(xn @ q(sd[p + "mlp.fc1.weight"]).T + sd[p + "mlp.fc1.bias"], approximate="tanh").to(torch.bfloat16).float()
+    ref = h @ q(sd[p + "mlp.fc2.weight"]).T + sd[p + "mlp.fc2.bias"] + r1
+    out = engine.block_mlp_cm(layer, y_cm.cuda(), res.cuda(), T)
+    torch.cuda.synchronize()
+    err = (out.cpu() - ref).abs().max().item()
+    assert err <= 2e-2, (B, T, err)
