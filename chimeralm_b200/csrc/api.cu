@@ -39,6 +39,9 @@ struct LayerW {
   __nv_bfloat16* in_wf = nullptr;
   float* in_bf = nullptr;
   CUtensorMap tm_inf;
+  // block_mlp operands, pre-tiled [N/rt][K/64][rt][64] so that every 32 KB ring slot is one TMA box
+  __nv_bfloat16 *out_wt = nullptr, *fc1_wt = nullptr, *fc2_wt = nullptr;
+  CUtensorMap tm_out_t, tm_fc1_t, tm_fc2_t;
   float* k = nullptr;                               // [D][Lk]
   float2* gspec[LONGCONV_MAX_LOGN + 1] = {nullptr};  // per LOGN: [n_seg][D][N]
   float2* gspecT[LONGCONV_MAX_LOGN + 1] = {nullptr}; // per LOGN: [D][16][N/16], bias folded (longconv_fast)
@@ -148,6 +151,15 @@ void dev_free(clm_ctx* c, void* p) {
     }
 }
 
+// dst[(((n/rt)*(K/64) + k/64)*rt + n%rt)*64 + k%64] = bf16(src[n][k])
+__global__ void retile_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int N, int K, int rt) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)N * K) return;
+  const int n = (int)(i / K), k = (int)(i % K);
+  const long long o = ((((long long)(n / rt) * (K / 64) + k / 64) * rt + n % rt) << 6) + (k & 63);
+  dst[o] = __float2bfloat16(src[i]);
+}
+
 __global__ void f32_to_bf16_kernel(const float* __restrict__ s, __nv_bfloat16* __restrict__ d, long long n) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) d[i] = __float2bfloat16(s[i]);
@@ -175,6 +187,21 @@ int need(clm_ctx* c, const std::string& name, int64_t numel, const float** out) 
   if (!t) return fail(c, CLM_ERR_MISSING, "weight '%s' was not loaded", name.c_str());
   if (t->numel != numel) return fail(c, CLM_ERR_INVALID, "weight '%s' has %lld elements, expected %lld", name.c_str(), (long long)t->numel, (long long)numel);
   *out = t->d;
+  return 0;
+}
+
+int retile(clm_ctx* c, const float* src, int N, int K, int rt, __nv_bfloat16** out, CUtensorMap* tm) {
+  int rc = dev_alloc(c, out, (size_t)N * K);
+  if (rc) return rc;
+  retile_bf16_kernel<<<(unsigned)(((long long)N * K + 255) / 256), 256>>>(src, *out, N, K, rt);
+  CLM_LAUNCH_CHECK(c, "retile_bf16");
+  cuuint64_t dims[2] = {64, (cuuint64_t)((long long)N * K / 64)};
+  cuuint64_t strides[1] = {128};
+  cuuint32_t box[2] = {64, 256}, estr[2] = {1, 1};
+  CUresult r = c->encode_tiled(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, *out, dims, strides, box, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(c, CLM_ERR_CUDA, "cuTensorMapEncodeTiled(retiled weight) failed with CUresult %d", (int)r);
   return 0;
 }
 
@@ -278,7 +305,7 @@ int launch_block_mlp(clm_ctx* c, int layer, const __nv_bfloat16* y, float* res, 
     return rc;
   }
   BlockMlpParams p{};
-  p.M = M; p.res = res; p.b_out = L.out_b; p.ln_g = L.ln2_g; p.ln_b = L.ln2_b; p.b1 = L.fc1_b; p.b2 = L.fc2_b;
+  p.M = M; p.res = res; p.layer = layer;
   p.eps = c->cfg.layer_norm_eps;
   p.num_tiles = (M + bm::BM - 1) / bm::BM;
   p.trace = trace;
@@ -286,7 +313,7 @@ int launch_block_mlp(clm_ctx* c, int layer, const __nv_bfloat16* y, float* res, 
     p.y_cm = 1; p.T = T; p.tiles_per_seq = (T + bm::BM - 1) / bm::BM; p.num_tiles = B * p.tiles_per_seq;
   }
   const int grid = std::min(p.num_tiles, c->num_sms);
-  block_mlp_kernel<<<grid, bm::THREADS, bm::SMEM_TOTAL, st>>>(tmY, L.tm_out, L.tm_fc1, L.tm_fc2, p);
+  block_mlp_kernel<<<grid, bm::THREADS, bm::SMEM_TOTAL, st>>>(tmY, L.tm_out_t, L.tm_fc1_t, L.tm_fc2_t, p);
   CLM_LAUNCH_CHECK(c, "block_mlp");
   return 0;
 }
@@ -604,6 +631,23 @@ int clm_finalize(clm_ctx* c) {
     if ((rc = make_tmap_bf16_2d(c, &L.tm_out, L.out_w, D, D, 128))) return rc;
     if ((rc = make_tmap_bf16_2d(c, &L.tm_fc1, L.fc1_w, g.d_inner, D, 128))) return rc;
     if ((rc = make_tmap_bf16_2d(c, &L.tm_fc2, L.fc2_w, D, g.d_inner, 128))) return rc;
+    {
+      if (l >= bm::MAX_LAYERS) return fail(c, CLM_ERR_INVALID, "n_layer > %d not supported by the fused block kernel", bm::MAX_LAYERS);
+      // LayerNorm2 affine folded into fc1: W1' = W1 diag(gamma2), b1' = b1 + W1 beta2
+      float *w1f = nullptr, *b1f = nullptr;
+      if ((rc = dev_alloc(c, &w1f, (size_t)g.d_inner * D))) return rc;
+      if ((rc = dev_alloc(c, &b1f, (size_t)g.d_inner))) return rc;
+      fold_ln_kernel<<<g.d_inner, 256>>>(fc1_w, L.fc1_b, L.ln2_g, L.ln2_b, w1f, b1f, D);
+      CLM_LAUNCH_CHECK(c, "fold_ln2");
+      if ((rc = retile(c, out_w, D, D, 256, &L.out_wt, &L.tm_out_t))) return rc;
+      if ((rc = retile(c, w1f, g.d_inner, D, 128, &L.fc1_wt, &L.tm_fc1_t))) return rc;
+      if ((rc = retile(c, fc2_w, D, g.d_inner, 256, &L.fc2_wt, &L.tm_fc2_t))) return rc;
+      static bm::LayerConsts hc;
+      CLM_CUDA(c, cudaMemcpy(hc.b_out, L.out_b, sizeof hc.b_out, cudaMemcpyDeviceToHost));
+      CLM_CUDA(c, cudaMemcpy(hc.b2, L.fc2_b, sizeof hc.b2, cudaMemcpyDeviceToHost));
+      CLM_CUDA(c, cudaMemcpy(hc.b1, b1f, sizeof hc.b1, cudaMemcpyDeviceToHost));
+      CLM_CUDA(c, cudaMemcpyToSymbol(bm::c_mlp, &hc, sizeof hc, (size_t)l * sizeof(bm::LayerConsts)));
+    }
     // implicit filter k[l] = HyenaFilter.filter(Lmax)
     FilterGenParams fp{};
     const std::string Q = P + "mixer.filter_fn.";

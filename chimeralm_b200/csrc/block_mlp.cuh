@@ -11,7 +11,7 @@
 //
 // One CTA per SM loops over tiles of 128 tokens.  All three GEMMs run on tcgen05 with the
 // accumulators in TMEM:
-//   cols [0,256)    R : out_proj accumulator, rewritten in place by the epilogue as r1 + b2 and
+//   256 cols        R : out_proj accumulator, rewritten in place by the epilogue as r1 and
 //                       then used as the fc2 accumulator (so the fc2 result already carries the
 //                       residual and bias)
 //   cols [256,512)  H0/H1 : fc1 output in two 128-column buffers, double-buffered against the
@@ -32,12 +32,8 @@ namespace clm {
 
 struct BlockMlpParams {
   int M;                 // tokens
-  float* res;            // [M,256] fp32, read and overwritten
-  const float* b_out;    // [256]
-  const float* ln_g;     // [256]
-  const float* ln_b;     // [256]
-  const float* b1;       // [1024]
-  const float* b2;       // [256]
+  float* res;            // [M,256] fp32 (R32 layout), read and overwritten
+  int layer;             // index into bm::c_mlp (biases; LayerNorm2 affine is folded into W1/b1)
   float eps;
   int num_tiles;
   // y_cm == 0: y is token-major [M,256] (tmY 2-D, tiles of 128 consecutive rows).
@@ -48,6 +44,16 @@ struct BlockMlpParams {
 };
 
 namespace bm {
+constexpr int MAX_LAYERS = 8;
+// Per-layer bias vectors, read with warp-uniform addresses in the epilogues -> constant cache
+// (with 226 KB of shared memory per CTA only ~4 KB of L1 is left, so __ldg thrashed).
+struct LayerConsts {
+  float b_out[256];
+  float b2[256];
+  float b1[1024];   // fc1 bias with LayerNorm2's beta folded in
+};
+__constant__ LayerConsts c_mlp[MAX_LAYERS];
+
 constexpr int D = 256, DI = 1024, BM = 128, BK = 64;
 constexpr int KB_BYTES = BM * BK * 2;            // 16 KB: one [128 x 64] bf16 tile
 constexpr int X_BYTES = 4 * KB_BYTES;            // 64 KB
@@ -63,7 +69,6 @@ constexpr int SMEM_TOTAL = OFF_PART + 2 * 2 * BM * 4; // 231680 <= 232448 (227 K
 constexpr int THREADS = 320;
 constexpr int EPI_THREADS = 256;
 constexpr int NCHUNK = DI / 128;                 // 8 fc1 column chunks
-constexpr uint32_t TM_R = 0, TM_H = 256;
 
 __device__ __forceinline__ float gelu_tanh_fast(float x) {
   // 0.5 x (1 + tanh(u)), u = sqrt(2/pi) (x + 0.044715 x^3); tanh.approx is ONE MUFU op (the
@@ -154,32 +159,27 @@ block_mlp_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
           for (int kb = 0; kb < 4; ++kb) ptx::tma_load_2d(smem + OFF_X + kb * KB_BYTES, &tmY, x_full, kb * BK, m0);
         }
         stamp(0);
-        // out_proj weights: 4 k-blocks of [256 x 64]
-        for (int kb = 0; kb < 4; ++kb) {
+        // Weights are pre-tiled at finalize as [N/rt][K/64][rt][64] (rt = 256 for Wout/W2, 128 for W1), so
+        // every 32 KB slot is ONE TMA instruction (a single thread issues ~1 TMA per 240 cycles).
+        for (int kb = 0; kb < 4; ++kb) {               // out_proj: k-block kb = rows [256 kb, +256)
           uint8_t* s = slot_acquire();
-          const uint32_t sl = wi % NSLOT;
-          ptx::tma_load_2d(s, &tmWout, &w_full[sl], kb * BK, 0);
-          ptx::tma_load_2d(s + KB_BYTES, &tmWout, &w_full[sl], kb * BK, 128);
+          ptx::tma_load_2d(s, &tmWout, &w_full[wi % NSLOT], 0, kb * 256);
           ++wi;
         }
         for (int j = 0; j <= NCHUNK; ++j) {
-          if (j < NCHUNK) {  // fc1 chunk j: rows [128 j, +128), 4 k-blocks, two per slot
+          if (j < NCHUNK) {  // fc1 chunk jc: k-blocks (2 h2, 2 h2 + 1) = rows [(4 jc + 2 h2) 128, +256)
+            const int jc = (j + rot) & (NCHUNK - 1);
             for (int h2 = 0; h2 < 2; ++h2) {
               uint8_t* s = slot_acquire();
-              const uint32_t sl = wi % NSLOT;
-              const int jc = (j + rot) & (NCHUNK - 1);
-              ptx::tma_load_2d(s, &tmW1, &w_full[sl], (2 * h2) * BK, jc * 128);
-              ptx::tma_load_2d(s + KB_BYTES, &tmW1, &w_full[sl], (2 * h2 + 1) * BK, jc * 128);
+              ptx::tma_load_2d(s, &tmW1, &w_full[wi % NSLOT], 0, (jc * 4 + 2 * h2) * 128);
               ++wi;
             }
           }
-          if (j >= 1) {  // fc2 K-chunk j-1: columns [128 (j-1), +128) = 2 k-blocks of [256 x 64]
+          if (j >= 1) {  // fc2 K-chunk jj: k-blocks 2 jj + kb = rows [(2 jj + kb) 256, +256)
             const int jj = (j - 1 + rot) & (NCHUNK - 1);
             for (int kb = 0; kb < 2; ++kb) {
               uint8_t* s = slot_acquire();
-              const uint32_t sl = wi % NSLOT;
-              ptx::tma_load_2d(s, &tmW2, &w_full[sl], jj * 128 + kb * BK, 0);
-              ptx::tma_load_2d(s + KB_BYTES, &tmW2, &w_full[sl], jj * 128 + kb * BK, 128);
+              ptx::tma_load_2d(s, &tmW2, &w_full[wi % NSLOT], 0, (jj * 2 + kb) * 256);
               ++wi;
             }
           }
@@ -209,9 +209,14 @@ block_mlp_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
       uint32_t it = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
         const uint32_t tph = it & 1;
+        // R and H swap TMEM halves every tile: this tile's out_proj accumulates into the columns the
+        // previous tile used for H (drained long ago), so it does not wait for the previous tile's
+        // output epilogue, which is still reading the other half.
+        const uint32_t TM_R = tph ? 256u : 0u, TM_H = tph ? 0u : 256u;
         // ---- G1: R = y * Wout^T
         stamp(1);
-        ptx::mbar_wait(r_free, tph ^ 1);     // previous tile's output drained from R
+        ptx::mbar_wait(&hacc_free[0], ((it * 4) & 1) ^ 1);   // previous tile's fc1 buffers drained (already true)
+        ptx::mbar_wait(&hacc_free[1], ((it * 4) & 1) ^ 1);
         ptx::mbar_wait(x_full, tph);
         ptx::tc_fence_after_sync();
         stamp(1);
@@ -237,7 +242,10 @@ block_mlp_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
         for (int j = 0; j <= NCHUNK; ++j) {
           if (j < NCHUNK) {
             const uint32_t b = j & 1, u = it * 4 + (j >> 1);
-            if (j == 0) { ptx::mbar_wait(xn_full, tph); }
+            if (j == 0) {
+              ptx::mbar_wait(xn_full, tph);
+              ptx::mbar_wait(r_free, tph ^ 1);   // previous tile's output drained from what is now H
+            }
             ptx::mbar_wait(&hacc_free[b], (u & 1) ^ 1);
             ptx::tc_fence_after_sync();
             stamp(1);
@@ -291,6 +299,8 @@ block_mlp_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
       const uint32_t tph = it & 1;
+      const uint32_t TM_R = tph ? 256u : 0u, TM_H = tph ? 0u : 256u;
+      const LayerConsts& lc = c_mlp[p.layer];
       long long row;
       bool row_ok;
       if (p.y_cm) {
@@ -322,19 +332,18 @@ block_mlp_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
         ptx::tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const float4 bo = __ldg(reinterpret_cast<const float4*>(p.b_out + col) + j);
-          const float4 b2 = __ldg(reinterpret_cast<const float4*>(p.b2 + col) + j);
           const float4 rr = rs[ci * 8 + j];
-          const float v0 = __uint_as_float(a[4 * j + 0]) + bo.x + rr.x;
-          const float v1 = __uint_as_float(a[4 * j + 1]) + bo.y + rr.y;
-          const float v2 = __uint_as_float(a[4 * j + 2]) + bo.z + rr.z;
-          const float v3 = __uint_as_float(a[4 * j + 3]) + bo.w + rr.w;
+          const int cc = col + 4 * j;
+          const float v0 = __uint_as_float(a[4 * j + 0]) + lc.b_out[cc + 0] + rr.x;
+          const float v1 = __uint_as_float(a[4 * j + 1]) + lc.b_out[cc + 1] + rr.y;
+          const float v2 = __uint_as_float(a[4 * j + 2]) + lc.b_out[cc + 2] + rr.z;
+          const float v3 = __uint_as_float(a[4 * j + 3]) + lc.b_out[cc + 3] + rr.w;
           s1 += (v0 + v1) + (v2 + v3);
           s2 += (v0 * v0 + v1 * v1) + (v2 * v2 + v3 * v3);
-          a[4 * j + 0] = __float_as_uint(v0 + b2.x);
-          a[4 * j + 1] = __float_as_uint(v1 + b2.y);
-          a[4 * j + 2] = __float_as_uint(v2 + b2.z);
-          a[4 * j + 3] = __float_as_uint(v3 + b2.w);
+          a[4 * j + 0] = __float_as_uint(v0);   // r1 stays in TMEM as the fc2 accumulator's initial value
+          a[4 * j + 1] = __float_as_uint(v1);
+          a[4 * j + 2] = __float_as_uint(v2);
+          a[4 * j + 3] = __float_as_uint(v3);
         }
         ptx::tmem_st_32x32b_x32(lane_addr + TM_R + col, a);
       }
@@ -356,19 +365,10 @@ block_mlp_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
         const int kb = col >> 6;
         const uint32_t rowaddr = sX + kb * KB_BYTES + r * 128;
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {  // 4 chunks of 8 columns = 16 bytes each
+        for (int g = 0; g < 4; ++g) {  // 4 chunks of 8 columns = 16 bytes each (gamma/beta are folded into W1/b1)
           float x[8];
 #pragma unroll
-          for (int j = 0; j < 8; j += 4) {
-            const int cc = col + g * 8 + j;
-            const float4 b2 = __ldg(reinterpret_cast<const float4*>(p.b2 + cc));
-            const float4 gg = __ldg(reinterpret_cast<const float4*>(p.ln_g + cc));
-            const float4 bb = __ldg(reinterpret_cast<const float4*>(p.ln_b + cc));
-            x[j + 0] = (__uint_as_float(a[g * 8 + j + 0]) - b2.x - mean) * rstd * gg.x + bb.x;
-            x[j + 1] = (__uint_as_float(a[g * 8 + j + 1]) - b2.y - mean) * rstd * gg.y + bb.y;
-            x[j + 2] = (__uint_as_float(a[g * 8 + j + 2]) - b2.z - mean) * rstd * gg.z + bb.z;
-            x[j + 3] = (__uint_as_float(a[g * 8 + j + 3]) - b2.w - mean) * rstd * gg.w + bb.w;
-          }
+          for (int j = 0; j < 8; ++j) x[j] = (__uint_as_float(a[g * 8 + j]) - mean) * rstd;
           const uint32_t chunk = uint32_t(((col & 63) >> 3) + g) ^ swz;
           ptx::st_shared_v4(rowaddr + chunk * 16, pack_bf16(x[0], x[1]), pack_bf16(x[2], x[3]), pack_bf16(x[4], x[5]),
                             pack_bf16(x[6], x[7]));
@@ -394,20 +394,14 @@ block_mlp_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&hacc_free[b]);
         ptx::mbar_wait(&hbuf_free[b], (u & 1) ^ 1);
-        const float* b1p = p.b1 + ((j + rot) & (NCHUNK - 1)) * 128 + hf * 64;
+        const float* b1p = lc.b1 + ((j + rot) & (NCHUNK - 1)) * 128 + hf * 64;
         const uint32_t rowaddr = sHB + b * HB_BYTES + hf * KB_BYTES + r * 128;
 #pragma unroll
         for (int g = 0; g < 8; ++g) {
           const uint32_t* src = (g < 4) ? &a0[g * 8] : &a1[(g - 4) * 8];
           float x[8];
 #pragma unroll
-          for (int jj = 0; jj < 8; jj += 4) {
-            const float4 bv = __ldg(reinterpret_cast<const float4*>(b1p + g * 8 + jj));
-            x[jj + 0] = gelu_tanh_fast(__uint_as_float(src[jj + 0]) + bv.x);
-            x[jj + 1] = gelu_tanh_fast(__uint_as_float(src[jj + 1]) + bv.y);
-            x[jj + 2] = gelu_tanh_fast(__uint_as_float(src[jj + 2]) + bv.z);
-            x[jj + 3] = gelu_tanh_fast(__uint_as_float(src[jj + 3]) + bv.w);
-          }
+          for (int jj = 0; jj < 8; ++jj) x[jj] = gelu_tanh_fast(__uint_as_float(src[jj]) + b1p[g * 8 + jj]);
           const uint32_t chunk = uint32_t(g) ^ swz;
           ptx::st_shared_v4(rowaddr + chunk * 16, pack_bf16(x[0], x[1]), pack_bf16(x[2], x[3]), pack_bf16(x[4], x[5]),
                             pack_bf16(x[6], x[7]));
@@ -431,8 +425,8 @@ block_mlp_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
 #pragma unroll
           for (int j = 0; j < 8; ++j)
             *reinterpret_cast<float4*>(p.res + ptx::r32_off(row, col + 4 * j)) =
-                make_float4(__uint_as_float(a[4 * j]), __uint_as_float(a[4 * j + 1]), __uint_as_float(a[4 * j + 2]),
-                            __uint_as_float(a[4 * j + 3]));
+                make_float4(__uint_as_float(a[4 * j]) + lc.b2[col + 4 * j], __uint_as_float(a[4 * j + 1]) + lc.b2[col + 4 * j + 1],
+                            __uint_as_float(a[4 * j + 2]) + lc.b2[col + 4 * j + 2], __uint_as_float(a[4 * j + 3]) + lc.b2[col + 4 * j + 3]);
         }
       }
       ptx::tc_fence_before_sync();
