@@ -625,8 +625,7 @@ int clm_finalize(clm_ctx* c) {
       if ((rc = dev_alloc(c, &L.in_bf, (size_t)3 * D))) return rc;
       fold_ln_kernel<<<3 * D, 256>>>(in_w, L.in_b, L.ln1_g, L.ln1_b, wf, L.in_bf, D);
       CLM_LAUNCH_CHECK(c, "fold_ln");
-      if ((rc = to_bf16(c, wf, 3LL * D * D, &L.in_wf))) return rc;
-      if ((rc = make_tmap_bf16_2d(c, &L.tm_inf, L.in_wf, 3 * D, D, 128))) return rc;
+      if ((rc = retile(c, wf, 3 * D, D, 128, &L.in_wf, &L.tm_inf))) return rc;
     }
     if ((rc = make_tmap_bf16_2d(c, &L.tm_out, L.out_w, D, D, 128))) return rc;
     if ((rc = make_tmap_bf16_2d(c, &L.tm_fc1, L.fc1_w, g.d_inner, D, 128))) return rc;

@@ -21,8 +21,10 @@
 // LayerNorm's affine is folded offline (clm_finalize): W' = W_in * diag(gamma),
 // b' = b_in + W_in beta, so the kernel only normalises.
 //
-// Warp roles: warp 0 = TMA producer (weight k-blocks, 4 x 16 KB ring), warp 1 = MMA issuer,
+// Warp roles: warp 0 = TMA producer (weight ring, 2 x 32 KB), warp 1 = MMA issuer,
 // warps 2..9 = LayerNorm producers of the B operand, then epilogue (conv + gate + TMA store).
+// Weight slots are 32 KB single-TMA boxes (a single thread issues only ~1 TMA per 240 cycles,
+// profiles/probes/tma_stream_probe.cu).
 #pragma once
 #include <cuda_bf16.h>
 
@@ -45,8 +47,8 @@ namespace bi {
 constexpr int D = 256, BT = 128, HALO = 16, NCOL = BT + HALO;   // 144 token columns per tile
 constexpr int KB_ROWS_BYTES = NCOL * 128;                       // one k-block of xn: 144 rows x 128 B
 constexpr int XN_BYTES = 4 * KB_ROWS_BYTES;                     // 73728
-constexpr int SLOT_BYTES = 128 * 64 * 2;                        // 16 KB: [128 channels x 64 k]
-constexpr int NSLOT = 4;
+constexpr int SLOT_BYTES = 2 * 128 * 64 * 2;                    // 32 KB: two k-blocks of [128 channels x 64 k], ONE TMA box
+constexpr int NSLOT = 2;
 constexpr int STAGE_BOX = 128 * 128;                            // 16 KB: [128 channels x 64 tokens] bf16
 constexpr int OFF_XN = 0;
 constexpr int OFF_W = OFF_XN + XN_BYTES;                        // 73728 (multiple of 1024)
@@ -69,8 +71,8 @@ block_in_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((ptx::smem_u32(smem) & 1023u) != 0) __trap();
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
-  uint64_t* w_full = bars;          // [4]
-  uint64_t* w_empty = bars + 4;     // [4]
+  uint64_t* w_full = bars;          // [NSLOT]
+  uint64_t* w_empty = bars + 4;     // [NSLOT]
   uint64_t* xn_full = bars + 8;     // LN warps wrote the B operand
   uint64_t* xn_free = bars + 9;     // both passes' MMAs finished reading it
   uint64_t* acc_full = bars + 10;   // one pass accumulated
@@ -95,17 +97,19 @@ block_in_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
   const uint32_t tmem_base = *tmem_ptr;
 
   if (warp == 0) {
-    // =========================== TMA producer: 24 weight k-blocks per tile ===========================
+    // =========================== TMA producer: 12 weight slots (2 k-blocks each) per tile ===========
+    // W' is pre-tiled at finalize as [n/128][kb][128][64]: k-blocks (2kp, 2kp+1) of one 128-channel block
+    // are 256 consecutive rows of a [.. x 64] matrix, i.e. one 32 KB TMA box per slot.
     if (lane == 0) {
       uint32_t wi = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         for (int h = 0; h < 2; ++h)
           for (int g = 0; g < 3; ++g)
-            for (int kb = 0; kb < 4; ++kb) {
+            for (int kp = 0; kp < 2; ++kp) {
               const uint32_t s = wi % NSLOT, ph = (wi / NSLOT) & 1;
               ptx::mbar_wait(&w_empty[s], ph ^ 1);
               ptx::mbar_expect_tx(&w_full[s], SLOT_BYTES);
-              ptx::tma_load_2d(smem + OFF_W + s * SLOT_BYTES, &tmW, &w_full[s], kb * 64, g * 256 + h * 128);
+              ptx::tma_load_2d(smem + OFF_W + s * SLOT_BYTES, &tmW, &w_full[s], 0, ((g * 2 + h) * 4 + 2 * kp) * 128);
               ++wi;
             }
       }
@@ -122,15 +126,19 @@ block_in_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
           ptx::mbar_wait(acc_free, (pass & 1) ^ 1);
           ptx::tc_fence_after_sync();
           for (int g = 0; g < 3; ++g)
-            for (int kb = 0; kb < 4; ++kb) {
+            for (int kp = 0; kp < 2; ++kp) {
               const uint32_t s = wi % NSLOT, ph = (wi / NSLOT) & 1;
               ptx::mbar_wait(&w_full[s], ph);
               ptx::tc_fence_after_sync();
-              const uint64_t da = ptx::smem_desc_k_sw128(sW + s * SLOT_BYTES);
-              const uint64_t db = ptx::smem_desc_k_sw128(sXN + kb * KB_ROWS_BYTES);
 #pragma unroll
-              for (int k = 0; k < 4; ++k)
-                ptx::umma_f16(tmem_base + g * GCOLS, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+              for (int q2 = 0; q2 < 2; ++q2) {
+                const int kb = 2 * kp + q2;
+                const uint64_t da = ptx::smem_desc_k_sw128(sW + s * SLOT_BYTES + q2 * (SLOT_BYTES / 2));
+                const uint64_t db = ptx::smem_desc_k_sw128(sXN + kb * KB_ROWS_BYTES);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                  ptx::umma_f16(tmem_base + g * GCOLS, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+              }
               ptx::umma_commit(&w_empty[s]);
               ++wi;
             }

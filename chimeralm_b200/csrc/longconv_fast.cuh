@@ -14,7 +14,8 @@
 //   * radix-16 twiddles come from shared-memory tables instead of sincospif + a power chain,
 //   * complex add/sub use packed fp32x2 instructions (FADD2 on sm_100),
 //   * the bias skip is folded into filter tap 0 (k'[0] = k[0] + bias), so the output pass does
-//     not re-read vx; the next item's rows are prefetched into L2 while this item is transformed.
+//     not re-read vx; the next item's vx rows are copied into a shared-memory staging buffer with
+//     cp.async (and its x0 rows prefetched into L2) while this item is transformed.
 // Barriers per item: 7 (was 11); shared-memory round trips: 6 (was 11).
 #pragma once
 #include <cuda_bf16.h>
@@ -98,17 +99,14 @@ __device__ __forceinline__ void dft16(cx (&x)[16]) {
 #undef CLM_SWAP
 }
 
-// Twiddle tables: tA[e] = W_4096^e for e < 2048 (W^(e+2048) = -W^e), tB[e] = W_256^e for e < 256.
-constexpr int TA = 2048, TB = 256;
+// Twiddle tables, laid out so that a warp (consecutive j) reads consecutive addresses:
+//   tA[(q-1)*256 + j] = W_4096^(j q), j < 256, q = 1..15;   tB[(q-1)*16 + j] = W_256^(j q), j < 16.
+constexpr int TA = 15 * 256, TB = 15 * 16;
 
 template <int NB>
-__device__ __forceinline__ float2 tw_lookup(const float2* tA, const float2* tB, int e) {
-  if constexpr (NB == 256) {
-    return tB[e];
-  } else {  // NB == 4096
-    const float2 w = tA[e & (TA - 1)];
-    return (e & TA) ? make_float2(-w.x, -w.y) : w;
-  }
+__device__ __forceinline__ float2 tw_lookup(const float2* tA, const float2* tB, int j, int q) {
+  if constexpr (NB == 256) return tB[(q - 1) * 16 + j];
+  else return tA[(q - 1) * 256 + j];
 }
 
 // in-place radix-16 pass over blocks of NB (4096 or 256), twiddles from the tables
@@ -125,10 +123,10 @@ __device__ __forceinline__ void pass16(cx* z, const float2* tA, const float2* tB
     if constexpr (!INV) {
       dft16<false>(x);
 #pragma unroll
-      for (int q = 1; q < 16; ++q) x[q] = cmul(x[q], tw_lookup<NB>(tA, tB, j * q));
+      for (int q = 1; q < 16; ++q) x[q] = cmul(x[q], tw_lookup<NB>(tA, tB, j, q));
     } else {
 #pragma unroll
-      for (int q = 1; q < 16; ++q) x[q] = cmulc(x[q], tw_lookup<NB>(tA, tB, j * q));
+      for (int q = 1; q < 16; ++q) x[q] = cmulc(x[q], tw_lookup<NB>(tA, tB, j, q));
       dft16<true>(x);
     }
 #pragma unroll
@@ -146,7 +144,8 @@ struct FastCfg {
   static constexpr int THREADS = ConvCfg<LOGN>::THREADS;
   static constexpr int OFF_TA = fft::padded_size(N) * 8;
   static constexpr int OFF_TB = OFF_TA + f2::TA * 8;
-  static constexpr int SMEM = OFF_TB + f2::TB * 8;
+  static constexpr int OFF_STG = (OFF_TB + f2::TB * 8 + 15) / 16 * 16;   // bf16 staging of the NEXT item's vx rows: [2][C]
+  static constexpr int SMEM = OFF_STG + 2 * C * 2;
 };
 
 // Spectrum in the layout the fused middle pass wants: gT[c][q][b] = G_c[16 b + q], b < N/16.
@@ -203,14 +202,31 @@ __global__ void __launch_bounds__(FastCfg<LOGN>::THREADS, 1) longconv_fast_kerne
   const int tid = threadIdx.x;
   for (int e = tid; e < f2::TA; e += TH) {
     float sn, cs;
-    sincospif((float)e / 2048.0f, &sn, &cs);   // 2*pi*e/4096
+    sincospif((float)((e & 255) * ((e >> 8) + 1)) / 2048.0f, &sn, &cs);   // 2*pi*(j q)/4096
     tA[e] = make_float2(cs, -sn);
   }
   for (int e = tid; e < f2::TB; e += TH) {
     float sn, cs;
-    sincospif((float)e / 128.0f, &sn, &cs);    // 2*pi*e/256
+    sincospif((float)((e & 15) * ((e >> 4) + 1)) / 128.0f, &sn, &cs);     // 2*pi*(j q)/256
     tB[e] = make_float2(cs, -sn);
   }
+  __nv_bfloat16* stg = reinterpret_cast<__nv_bfloat16*>(smem_f + F::OFF_STG);
+  // asynchronous copy of one item's vx rows (both reads, first min(C, Tp) tokens) into the staging buffer
+  auto stage_item = [&](int it_) {
+    const int c_ = it_ / ((p.B + 1) / 2), b_ = (it_ % ((p.B + 1) / 2)) * 2;
+    const long long o0 = ((long long)b_ * p.D + c_) * p.Tp;
+    const int ncopy = min(C, p.Tp) / 8;   // 16-byte pieces per read
+    const int nseq = (b_ + 1 < p.B) ? 2 : 1;
+    for (int i = tid; i < nseq * ncopy; i += TH) {
+      const int sq = i / ncopy, pc = i % ncopy;
+      const __nv_bfloat16* src = p.vx + o0 + (long long)sq * p.D * p.Tp + pc * 8;
+      const uint32_t dst = static_cast<uint32_t>(__cvta_generic_to_shared(stg + sq * C + pc * 8));
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  if ((int)blockIdx.x < p.n_items) stage_item(blockIdx.x);
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
   const int n_pairs = (p.B + 1) / 2;
   const int t_fft = min(C, p.T);
   __syncthreads();
@@ -223,7 +239,7 @@ __global__ void __launch_bounds__(FastCfg<LOGN>::THREADS, 1) longconv_fast_kerne
     const long long off1 = has_b1 ? off0 + (long long)p.D * p.Tp : off0;
     const __nv_bfloat16* va = p.vx + off0;
     const __nv_bfloat16* vb = p.vx + off1;
-    // ---- L2 prefetch of the next item's rows (vx and x0 of both reads)
+    // ---- L2 prefetch of the next item's x0 rows
     {
       const int nitem = item + gridDim.x;
       if (nitem < p.n_items) {
@@ -231,10 +247,9 @@ __global__ void __launch_bounds__(FastCfg<LOGN>::THREADS, 1) longconv_fast_kerne
         const long long no0 = ((long long)nb0 * p.D + nc) * p.Tp;
         const long long no1 = (nb0 + 1 < p.B) ? no0 + (long long)p.D * p.Tp : no0;
         const int lines = (min(p.T, C) * 2 + 127) / 128;
-        for (int l = tid; l < 4 * lines; l += TH) {
+        for (int l = tid; l < 2 * lines; l += TH) {     // x0 rows only: vx is staged through shared memory
           const int which = l / lines, ln = l % lines;
-          const __nv_bfloat16* base = (which & 1) ? p.x0 : p.vx;
-          prefetch_l2(base + ((which & 2) ? no1 : no0) + ln * 64);
+          prefetch_l2(p.x0 + (which ? no1 : no0) + ln * 64);
         }
       }
     }
@@ -249,9 +264,9 @@ __global__ void __launch_bounds__(FastCfg<LOGN>::THREADS, 1) longconv_fast_kerne
         for (int r = 0; r < HALF; ++r) {
           const int t = j + r * S0;
           uint32_t wa = 0, wb = 0;
-          if (t < p.T) {  // t even, Tp even: the pair (t, t+1) is in bounds
-            wa = *reinterpret_cast<const uint32_t*>(va + t);
-            if (has_b1) wb = *reinterpret_cast<const uint32_t*>(vb + t);
+          if (t < p.T) {  // t even: the pair (t, t+1) was staged (t + 1 < min(C, Tp))
+            wa = *reinterpret_cast<const uint32_t*>(stg + t);
+            if (has_b1) wb = *reinterpret_cast<const uint32_t*>(stg + C + t);
           }
           xa[r][0] = __uint_as_float(wa << 16);
           xa[r][1] = (t + 1 < p.T) ? __uint_as_float(wa & 0xffff0000u) : 0.f;
@@ -297,6 +312,7 @@ __global__ void __launch_bounds__(FastCfg<LOGN>::THREADS, 1) longconv_fast_kerne
       }
     }
     __syncthreads();
+    if (item + (int)gridDim.x < p.n_items) stage_item(item + gridDim.x);   // overlaps the whole transform
     // ---- forward radix-16 passes down to blocks of 256
     if constexpr (S0 >= 4096) {
       f2::pass16<N, 4096, false, TH>(z, tA, tB, tid);
@@ -440,7 +456,8 @@ __global__ void __launch_bounds__(FastCfg<LOGN>::THREADS, 1) longconv_fast_kerne
       }
       __syncthreads();
     }
-    __syncthreads();   // phase Z reads of z complete before the next item's phase A overwrites it
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();   // phase Z reads of z complete and the next item's staged rows have landed
   }
 }
 
