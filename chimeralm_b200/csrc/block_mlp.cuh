@@ -11,11 +11,11 @@
 //
 // One CTA per SM loops over tiles of 128 tokens.  All three GEMMs run on tcgen05 with the
 // accumulators in TMEM:
-//   256 cols        R : out_proj accumulator, rewritten in place by the epilogue as r1 and
-//                       then used as the fc2 accumulator (so the fc2 result already carries the
-//                       residual and bias)
-//   cols [256,512)  H0/H1 : fc1 output in two 128-column buffers, double-buffered against the
-//                       GELU epilogue
+//   cols [0,256)    R  : out_proj accumulator, rewritten in place by the epilogue as r1 and then used as
+//                        the fc2 accumulator (so the fc2 result already carries the residual)
+//   cols [256,384)  XN : LayerNorm2 output as packed bf16 - the A operand of fc1 read from TMEM
+//                        (tcgen05.mma TS form), so fc1 streams only its weights from shared memory
+//   cols [384,512)  H  : fc1 chunk accumulator (drained into registers before the GELU math)
 // Shared memory (224 KB): X (64 KB: y tile, later xn in the same UMMA layout), HB (2 x 32 KB:
 // gelu(h) chunks as the A operand of fc2), W ring (3 x 32 KB weight tiles streamed by TMA from
 // L2 in exactly the order the MMA thread consumes them).
@@ -69,6 +69,7 @@ constexpr int SMEM_TOTAL = OFF_PART + 2 * 2 * BM * 4; // 231680 <= 232448 (227 K
 constexpr int THREADS = 320;
 constexpr int EPI_THREADS = 256;
 constexpr int NCHUNK = DI / 128;                 // 8 fc1 column chunks
+constexpr uint32_t TM_R = 0, TM_XN = 256, TM_H = 384;
 
 __device__ __forceinline__ float gelu_tanh_fast(float x) {
   // 0.5 x (1 + tanh(u)), u = sqrt(2/pi) (x + 0.044715 x^3); tanh.approx is ONE MUFU op (the
@@ -93,23 +94,23 @@ block_mlp_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
   uint64_t* w_full = bars;                 // [3]
   uint64_t* w_empty = bars + 3;            // [3]
   uint64_t* x_full = bars + 6;             // y tile landed in X
-  uint64_t* x_free = bars + 7;             // X no longer read by the tensor core (after fc1 chunk 7)
+  uint64_t* x_free = bars + 7;             // out_proj finished reading X
   uint64_t* g1_done = bars + 8;            // out_proj accumulator complete
-  uint64_t* xn_full = bars + 9;            // epilogue wrote xn into X and r1+b2 into R
-  uint64_t* hacc_full = bars + 10;         // [2] fc1 chunk accumulator complete
-  uint64_t* hacc_free = bars + 12;         // [2] epilogue drained the fc1 chunk accumulator
-  uint64_t* hbuf_full = bars + 14;         // [2] gelu(h) chunk written to HB
-  uint64_t* hbuf_free = bars + 16;         // [2] fc2 finished reading HB
-  uint64_t* out_full = bars + 18;          // fc2 accumulator complete
-  uint64_t* r_free = bars + 19;            // epilogue drained R
+  uint64_t* xn_full = bars + 9;            // epilogue wrote xn into TMEM and r1 into R
+  uint64_t* hacc_full = bars + 10;         // fc1 chunk accumulator complete
+  uint64_t* hacc_free = bars + 11;         // epilogue drained the fc1 chunk accumulator into registers
+  uint64_t* hbuf_full = bars + 12;         // [2] gelu(h) chunk written to HB
+  uint64_t* hbuf_free = bars + 14;         // [2] fc2 finished reading HB
+  uint64_t* out_full = bars + 16;          // fc2 accumulator complete
+  uint64_t* r_free = bars + 17;            // epilogue drained R
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 20);
   float (*s_part)[2][BM] = reinterpret_cast<float (*)[2][BM]>(smem + OFF_PART);  // [half][sum|sumsq][row]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // Each CTA walks the 8 fc1/fc2 hidden chunks starting at a different one, so the 148 CTAs do
-  // not all pull the same weight tile out of the same L2 slices at the same moment.
+  // not all pull the same weight tile out of L2 at the same moment.
   const int rot = blockIdx.x & (NCHUNK - 1);
-  // trace rows: 0 = producer, 1 = MMA issuer, 2 = epilogue warp 2; first two tiles of CTA 0
+  // trace rows: 0 = producer, 1 = MMA issuer, 2 = epilogue warp 2; CTA 0 only
   long long* trace = (p.trace && blockIdx.x == 0) ? p.trace : nullptr;
   int trace_n = 0;
   auto stamp = [&](int role) {
@@ -121,10 +122,8 @@ block_mlp_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
     for (int i = 0; i < NSLOT; ++i) { ptx::mbar_init(&w_full[i], 1); ptx::mbar_init(&w_empty[i], 1); }
     ptx::mbar_init(x_full, 1); ptx::mbar_init(x_free, 1); ptx::mbar_init(g1_done, 1);
     ptx::mbar_init(xn_full, 8);
-    for (int i = 0; i < 2; ++i) {
-      ptx::mbar_init(&hacc_full[i], 1); ptx::mbar_init(&hacc_free[i], 8);
-      ptx::mbar_init(&hbuf_full[i], 8); ptx::mbar_init(&hbuf_free[i], 1);
-    }
+    ptx::mbar_init(hacc_full, 1); ptx::mbar_init(hacc_free, 8);
+    for (int i = 0; i < 2; ++i) { ptx::mbar_init(&hbuf_full[i], 8); ptx::mbar_init(&hbuf_free[i], 1); }
     ptx::mbar_init(out_full, 1); ptx::mbar_init(r_free, 8);
     ptx::fence_mbar_init();
   } else if (warp == 1) {
@@ -145,20 +144,23 @@ block_mlp_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
         ptx::mbar_expect_tx(&w_full[s], SLOT_BYTES);
         return smem + OFF_W + s * SLOT_BYTES;
       };
-      uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
-        const int m0 = tile * BM;
-        ptx::mbar_wait(x_free, (it & 1) ^ 1);
+      // y tile of tile index `xt`, the `xit`-th tile of this CTA, into X
+      auto load_x = [&](int xt, uint32_t xit) {
+        ptx::mbar_wait(x_free, (xit & 1) ^ 1);
         ptx::mbar_expect_tx(x_full, X_BYTES);
         if (p.y_cm) {
-          const int b = tile / p.tiles_per_seq, t0 = (tile % p.tiles_per_seq) * BM;
+          const int b = xt / p.tiles_per_seq, t0 = (xt % p.tiles_per_seq) * BM;
           for (int kb = 0; kb < 4; ++kb)    // k-block = 64 channels; two 64-token halves of 8 KB each
             for (int hh = 0; hh < 2; ++hh)
               ptx::tma_load_3d(smem + OFF_X + kb * KB_BYTES + hh * (KB_BYTES / 2), &tmY, x_full, t0 + hh * 64, kb * BK, b);
         } else {
-          for (int kb = 0; kb < 4; ++kb) ptx::tma_load_2d(smem + OFF_X + kb * KB_BYTES, &tmY, x_full, kb * BK, m0);
+          for (int kb = 0; kb < 4; ++kb) ptx::tma_load_2d(smem + OFF_X + kb * KB_BYTES, &tmY, x_full, kb * BK, xt * BM);
         }
         stamp(0);
+      };
+      uint32_t it = 0;
+      if ((int)blockIdx.x < p.num_tiles) load_x(blockIdx.x, 0);
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
         // Weights are pre-tiled at finalize as [N/rt][K/64][rt][64] (rt = 256 for Wout/W2, 128 for W1), so
         // every 32 KB slot is ONE TMA instruction (a single thread issues ~1 TMA per 240 cycles).
         for (int kb = 0; kb < 4; ++kb) {               // out_proj: k-block kb = rows [256 kb, +256)
@@ -183,6 +185,8 @@ block_mlp_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
               ++wi;
             }
           }
+          // X is only read by out_proj, which is long finished by now: fetch the next tile's y early
+          if (j == 2 && tile + (int)gridDim.x < p.num_tiles) load_x(tile + gridDim.x, it + 1);
         }
       }
     }
@@ -209,14 +213,9 @@ block_mlp_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
       uint32_t it = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
         const uint32_t tph = it & 1;
-        // R and H swap TMEM halves every tile: this tile's out_proj accumulates into the columns the
-        // previous tile used for H (drained long ago), so it does not wait for the previous tile's
-        // output epilogue, which is still reading the other half.
-        const uint32_t TM_R = tph ? 256u : 0u, TM_H = tph ? 0u : 256u;
         // ---- G1: R = y * Wout^T
         stamp(1);
-        ptx::mbar_wait(&hacc_free[0], ((it * 4) & 1) ^ 1);   // previous tile's fc1 buffers drained (already true)
-        ptx::mbar_wait(&hacc_free[1], ((it * 4) & 1) ^ 1);
+        ptx::mbar_wait(r_free, tph ^ 1);     // previous tile's output drained from R
         ptx::mbar_wait(x_full, tph);
         ptx::tc_fence_after_sync();
         stamp(1);
@@ -237,16 +236,14 @@ block_mlp_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
           slot_release();
         }
         ptx::umma_commit(g1_done);
+        ptx::umma_commit(x_free);
         stamp(1);
         // ---- fc1 / fc2 software pipeline
         for (int j = 0; j <= NCHUNK; ++j) {
           if (j < NCHUNK) {
-            const uint32_t b = j & 1, u = it * 4 + (j >> 1);
-            if (j == 0) {
-              ptx::mbar_wait(xn_full, tph);
-              ptx::mbar_wait(r_free, tph ^ 1);   // previous tile's output drained from what is now H
-            }
-            ptx::mbar_wait(&hacc_free[b], (u & 1) ^ 1);
+            const uint32_t u = it * NCHUNK + j;
+            if (j == 0) ptx::mbar_wait(xn_full, tph);
+            ptx::mbar_wait(hacc_free, (u & 1) ^ 1);
             ptx::tc_fence_after_sync();
             stamp(1);
             for (int h2 = 0; h2 < 2; ++h2) {
@@ -254,16 +251,14 @@ block_mlp_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
 #pragma unroll
               for (int q = 0; q < 2; ++q) {
                 const int kb = 2 * h2 + q;
-                const uint64_t da = ptx::smem_desc_k_sw128(sX + kb * KB_BYTES);
                 const uint64_t db = ptx::smem_desc_k_sw128(sw + q * KB_BYTES);
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                  ptx::umma_f16(tmem_base + TM_H + b * 128, da + 2 * k, db + 2 * k, idesc128, (kb | k) != 0);
+                for (int k = 0; k < 4; ++k)   // A = xn from TMEM: 8 columns (16 bf16) per K step
+                  ptx::umma_f16_ts(tmem_base + TM_H, tmem_base + TM_XN + (kb * 4 + k) * 8, db + 2 * k, idesc128, (kb | k) != 0);
               }
               slot_release();
             }
-            ptx::umma_commit(&hacc_full[b]);
-            if (j == NCHUNK - 1) ptx::umma_commit(x_free);  // X (xn) not needed by later MMAs of this tile
+            ptx::umma_commit(hacc_full);
           }
           if (j >= 1) {
             const int jj = j - 1;
@@ -293,14 +288,13 @@ block_mlp_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
     const int hf = e >> 2;           // column half
     const int r = q * 32 + lane;     // row inside the tile
     const uint32_t lane_addr = tmem_base + (uint32_t(q * 32) << 16);
-    const uint32_t sX = ptx::smem_u32(smem + OFF_X);
     const uint32_t sHB = ptx::smem_u32(smem + OFF_HB);
     const uint32_t swz = uint32_t(r & 7);
+    const LayerConsts& lc = c_mlp[p.layer];
+    const bool tr = trace && warp == 2 && lane == 0;
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
       const uint32_t tph = it & 1;
-      const uint32_t TM_R = tph ? 256u : 0u, TM_H = tph ? 0u : 256u;
-      const LayerConsts& lc = c_mlp[p.layer];
       long long row;
       bool row_ok;
       if (p.y_cm) {
@@ -311,7 +305,7 @@ block_mlp_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
         row = (long long)tile * BM + r;
         row_ok = row < p.M;
       }
-      // ------------------------------------------------ E1: r1, LayerNorm2 -> xn
+      // ------------------------------------------------ E1: r1, LayerNorm2 -> xn (TMEM)
       // The residual half-row (128 fp32) is fetched into registers BEFORE waiting for the
       // out_proj accumulator, so its DRAM latency hides behind the y-tile load and G1.
       float4 rs[32];
@@ -319,7 +313,6 @@ block_mlp_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
       for (int j = 0; j < 32; ++j)
         rs[j] = row_ok ? *reinterpret_cast<const float4*>(p.res + ptx::r32_off(row, hf * 128 + 4 * j))
                        : make_float4(0.f, 0.f, 0.f, 0.f);
-      const bool tr = trace && warp == 2 && lane == 0;
       ptx::mbar_wait(g1_done, tph);
       ptx::tc_fence_after_sync();
       if (tr) stamp(2);
@@ -332,22 +325,21 @@ block_mlp_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
         ptx::tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const float4 rr = rs[ci * 8 + j];
+          float4& rr = rs[ci * 8 + j];
           const int cc = col + 4 * j;
-          const float v0 = __uint_as_float(a[4 * j + 0]) + lc.b_out[cc + 0] + rr.x;
-          const float v1 = __uint_as_float(a[4 * j + 1]) + lc.b_out[cc + 1] + rr.y;
-          const float v2 = __uint_as_float(a[4 * j + 2]) + lc.b_out[cc + 2] + rr.z;
-          const float v3 = __uint_as_float(a[4 * j + 3]) + lc.b_out[cc + 3] + rr.w;
-          s1 += (v0 + v1) + (v2 + v3);
-          s2 += (v0 * v0 + v1 * v1) + (v2 * v2 + v3 * v3);
-          a[4 * j + 0] = __float_as_uint(v0);   // r1 stays in TMEM as the fc2 accumulator's initial value
-          a[4 * j + 1] = __float_as_uint(v1);
-          a[4 * j + 2] = __float_as_uint(v2);
-          a[4 * j + 3] = __float_as_uint(v3);
+          rr.x += __uint_as_float(a[4 * j + 0]) + lc.b_out[cc + 0];   // rs now holds r1
+          rr.y += __uint_as_float(a[4 * j + 1]) + lc.b_out[cc + 1];
+          rr.z += __uint_as_float(a[4 * j + 2]) + lc.b_out[cc + 2];
+          rr.w += __uint_as_float(a[4 * j + 3]) + lc.b_out[cc + 3];
+          s1 += (rr.x + rr.y) + (rr.z + rr.w);
+          s2 += (rr.x * rr.x + rr.y * rr.y) + (rr.z * rr.z + rr.w * rr.w);
+          a[4 * j + 0] = __float_as_uint(rr.x);   // r1 stays in TMEM as the fc2 accumulator's initial value
+          a[4 * j + 1] = __float_as_uint(rr.y);
+          a[4 * j + 2] = __float_as_uint(rr.z);
+          a[4 * j + 3] = __float_as_uint(rr.w);
         }
         ptx::tmem_st_32x32b_x32(lane_addr + TM_R + col, a);
       }
-      ptx::tmem_st_wait();
       s_part[hf][0][r] = s1;
       s_part[hf][1][r] = s2;
       ptx::bar_sync(1, EPI_THREADS);
@@ -356,25 +348,20 @@ block_mlp_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
       const float mean = ts1 * (1.0f / D);
       const float var = fmaxf(ts2 * (1.0f / D) - mean * mean, 0.f);
       const float rstd = rsqrtf(var + p.eps);
-#pragma unroll 1
-      for (int c0 = 0; c0 < 128; c0 += 32) {
-        const int col = hf * 128 + c0;
-        uint32_t a[32];
-        ptx::tmem_ld_32x32b_x32(lane_addr + TM_R + col, a);
-        ptx::tmem_ld_wait();
-        const int kb = col >> 6;
-        const uint32_t rowaddr = sX + kb * KB_BYTES + r * 128;
+      // xn = (r1 - mean) * rstd (gamma/beta folded into W1/b1), packed bf16 pairs: this thread's 128 columns
+      // are 64 TMEM columns of the A operand
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {  // 4 chunks of 8 columns = 16 bytes each (gamma/beta are folded into W1/b1)
-          float x[8];
+      for (int hh = 0; hh < 2; ++hh) {
+        uint32_t w[32];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) x[j] = (__uint_as_float(a[g * 8 + j]) - mean) * rstd;
-          const uint32_t chunk = uint32_t(((col & 63) >> 3) + g) ^ swz;
-          ptx::st_shared_v4(rowaddr + chunk * 16, pack_bf16(x[0], x[1]), pack_bf16(x[2], x[3]), pack_bf16(x[4], x[5]),
-                            pack_bf16(x[6], x[7]));
+        for (int j = 0; j < 16; ++j) {
+          const float4 v = rs[hh * 16 + j];
+          w[2 * j] = pack_bf16((v.x - mean) * rstd, (v.y - mean) * rstd);
+          w[2 * j + 1] = pack_bf16((v.z - mean) * rstd, (v.w - mean) * rstd);
         }
+        ptx::tmem_st_32x32b_x32(lane_addr + TM_XN + hf * 64 + hh * 32, w);
       }
-      ptx::fence_proxy_async_smem();
+      ptx::tmem_st_wait();
       ptx::tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(xn_full);
@@ -382,17 +369,17 @@ block_mlp_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
       // ------------------------------------------------ E2: gelu(fc1 chunk) -> HB
 #pragma unroll 1
       for (int j = 0; j < NCHUNK; ++j) {
-        const uint32_t b = j & 1, u = it * 4 + (j >> 1);
-        ptx::mbar_wait(&hacc_full[b], u & 1);
+        const uint32_t b = j & 1, u = it * 4 + (j >> 1), uh = it * NCHUNK + j;
+        ptx::mbar_wait(hacc_full, uh & 1);
         ptx::tc_fence_after_sync();
         if (tr) stamp(2);
         uint32_t a0[32], a1[32];
-        ptx::tmem_ld_32x32b_x32(lane_addr + TM_H + b * 128 + hf * 64, a0);
-        ptx::tmem_ld_32x32b_x32(lane_addr + TM_H + b * 128 + hf * 64 + 32, a1);
+        ptx::tmem_ld_32x32b_x32(lane_addr + TM_H + hf * 64, a0);
+        ptx::tmem_ld_32x32b_x32(lane_addr + TM_H + hf * 64 + 32, a1);
         ptx::tmem_ld_wait();
         ptx::tc_fence_before_sync();
         __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&hacc_free[b]);
+        if (lane == 0) ptx::mbar_arrive(hacc_free);   // the accumulator is in registers: fc1 of the next chunk may start
         ptx::mbar_wait(&hbuf_free[b], (u & 1) ^ 1);
         const float* b1p = lc.b1 + ((j + rot) & (NCHUNK - 1)) * 128 + hf * 64;
         const uint32_t rowaddr = sHB + b * HB_BYTES + hf * KB_BYTES + r * 128;
@@ -411,7 +398,7 @@ block_mlp_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
         if (lane == 0) ptx::mbar_arrive(&hbuf_full[b]);
         if (tr) stamp(2);
       }
-      // ------------------------------------------------ E3: out = R -> res
+      // ------------------------------------------------ E3: out = R + b2 -> res
       ptx::mbar_wait(out_full, tph);
       ptx::tc_fence_after_sync();
       if (tr) stamp(2);
