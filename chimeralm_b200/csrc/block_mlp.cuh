@@ -11,14 +11,16 @@
 //
 // One CTA per SM loops over tiles of 128 tokens.  All three GEMMs run on tcgen05 with the
 // accumulators in TMEM:
+//   (the two 256-column halves swap roles every tile)
 //   cols [0,256)    R  : out_proj accumulator, rewritten in place by the epilogue as r1 and then used as
 //                        the fc2 accumulator (so the fc2 result already carries the residual)
 //   cols [256,384)  XN : LayerNorm2 output as packed bf16 - the A operand of fc1 read from TMEM
 //                        (tcgen05.mma TS form), so fc1 streams only its weights from shared memory
 //   cols [384,512)  H  : fc1 chunk accumulator (drained into registers before the GELU math)
-// Shared memory (224 KB): X (64 KB: y tile, later xn in the same UMMA layout), HB (2 x 32 KB:
-// gelu(h) chunks as the A operand of fc2), W ring (3 x 32 KB weight tiles streamed by TMA from
-// L2 in exactly the order the MMA thread consumes them).
+// Shared memory (224 KB): HB (2 x 32 KB: gelu(h) chunks as the A operand of fc2) and a 5 x 32 KB ring
+// through which TMA streams, in exactly the order the MMA thread consumes them, the y tile (two
+// k-blocks per slot) and every weight tile (one 32 KB box per slot).  A slot is held until the MMAs
+// reading it complete, so ring depth x slot size is what hides the L2 latency.
 //
 // Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc), warps 2..9 = epilogue
 // (TMEM lane quarter = warp % 4, column half = (warp - 2) / 4).
@@ -59,9 +61,8 @@ constexpr int KB_BYTES = BM * BK * 2;            // 16 KB: one [128 x 64] bf16 t
 constexpr int X_BYTES = 4 * KB_BYTES;            // 64 KB
 constexpr int HB_BYTES = 2 * KB_BYTES;           // 32 KB per buffer
 constexpr int SLOT_BYTES = 2 * KB_BYTES;         // 32 KB
-constexpr int NSLOT = 3;
-constexpr int OFF_X = 0;
-constexpr int OFF_HB = OFF_X + X_BYTES;
+constexpr int NSLOT = 5;                         // 160 KB ring: weights AND the y tile stream through it
+constexpr int OFF_HB = 0;
 constexpr int OFF_W = OFF_HB + 2 * HB_BYTES;
 constexpr int OFF_BAR = OFF_W + NSLOT * SLOT_BYTES;   // 229376
 constexpr int OFF_PART = OFF_BAR + 256;               // LayerNorm partial sums [2][2][128] fp32
@@ -69,7 +70,6 @@ constexpr int SMEM_TOTAL = OFF_PART + 2 * 2 * BM * 4; // 231680 <= 232448 (227 K
 constexpr int THREADS = 320;
 constexpr int EPI_THREADS = 256;
 constexpr int NCHUNK = DI / 128;                 // 8 fc1 column chunks
-constexpr uint32_t TM_R = 0, TM_XN = 256, TM_H = 384;
 
 __device__ __forceinline__ float gelu_tanh_fast(float x) {
   // 0.5 x (1 + tanh(u)), u = sqrt(2/pi) (x + 0.044715 x^3); tanh.approx is ONE MUFU op (the
@@ -91,18 +91,16 @@ block_mlp_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((ptx::smem_u32(smem) & 1023u) != 0) __trap();  // swizzled UMMA/TMA tiles need 1 KB alignment
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
-  uint64_t* w_full = bars;                 // [3]
-  uint64_t* w_empty = bars + 3;            // [3]
-  uint64_t* x_full = bars + 6;             // y tile landed in X
-  uint64_t* x_free = bars + 7;             // out_proj finished reading X
-  uint64_t* g1_done = bars + 8;            // out_proj accumulator complete
-  uint64_t* xn_full = bars + 9;            // epilogue wrote xn into TMEM and r1 into R
-  uint64_t* hacc_full = bars + 10;         // fc1 chunk accumulator complete
-  uint64_t* hacc_free = bars + 11;         // epilogue drained the fc1 chunk accumulator into registers
-  uint64_t* hbuf_full = bars + 12;         // [2] gelu(h) chunk written to HB
-  uint64_t* hbuf_free = bars + 14;         // [2] fc2 finished reading HB
-  uint64_t* out_full = bars + 16;          // fc2 accumulator complete
-  uint64_t* r_free = bars + 17;            // epilogue drained R
+  uint64_t* w_full = bars;                 // [NSLOT]
+  uint64_t* w_empty = bars + 5;            // [NSLOT]
+  uint64_t* g1_done = bars + 10;           // out_proj accumulator complete
+  uint64_t* xn_full = bars + 11;           // epilogue wrote xn into TMEM and r1 into R
+  uint64_t* hacc_full = bars + 12;         // fc1 chunk accumulator complete
+  uint64_t* hacc_free = bars + 13;         // epilogue drained the fc1 chunk accumulator into registers
+  uint64_t* hbuf_full = bars + 14;         // [2] gelu(h) chunk written to HB
+  uint64_t* hbuf_free = bars + 16;         // [2] fc2 finished reading HB
+  uint64_t* out_full = bars + 18;          // fc2 accumulator complete
+  uint64_t* r_free = bars + 19;            // epilogue drained R
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 20);
   float (*s_part)[2][BM] = reinterpret_cast<float (*)[2][BM]>(smem + OFF_PART);  // [half][sum|sumsq][row]
 
@@ -120,7 +118,7 @@ block_mlp_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmY); ptx::prefetch_tmap(&tmWout); ptx::prefetch_tmap(&tmW1); ptx::prefetch_tmap(&tmW2);
     for (int i = 0; i < NSLOT; ++i) { ptx::mbar_init(&w_full[i], 1); ptx::mbar_init(&w_empty[i], 1); }
-    ptx::mbar_init(x_full, 1); ptx::mbar_init(x_free, 1); ptx::mbar_init(g1_done, 1);
+    ptx::mbar_init(g1_done, 1);
     ptx::mbar_init(xn_full, 8);
     ptx::mbar_init(hacc_full, 1); ptx::mbar_init(hacc_free, 8);
     for (int i = 0; i < 2; ++i) { ptx::mbar_init(&hbuf_full[i], 8); ptx::mbar_init(&hbuf_free[i], 1); }
@@ -144,23 +142,25 @@ block_mlp_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
         ptx::mbar_expect_tx(&w_full[s], SLOT_BYTES);
         return smem + OFF_W + s * SLOT_BYTES;
       };
-      // y tile of tile index `xt`, the `xit`-th tile of this CTA, into X
-      auto load_x = [&](int xt, uint32_t xit) {
-        ptx::mbar_wait(x_free, (xit & 1) ^ 1);
-        ptx::mbar_expect_tx(x_full, X_BYTES);
-        if (p.y_cm) {
-          const int b = xt / p.tiles_per_seq, t0 = (xt % p.tiles_per_seq) * BM;
-          for (int kb = 0; kb < 4; ++kb)    // k-block = 64 channels; two 64-token halves of 8 KB each
-            for (int hh = 0; hh < 2; ++hh)
-              ptx::tma_load_3d(smem + OFF_X + kb * KB_BYTES + hh * (KB_BYTES / 2), &tmY, x_full, t0 + hh * 64, kb * BK, b);
-        } else {
-          for (int kb = 0; kb < 4; ++kb) ptx::tma_load_2d(smem + OFF_X + kb * KB_BYTES, &tmY, x_full, kb * BK, xt * BM);
-        }
-        stamp(0);
-      };
       uint32_t it = 0;
-      if ((int)blockIdx.x < p.num_tiles) load_x(blockIdx.x, 0);
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+        // y tile: 4 k-blocks of 16 KB, two per ring slot
+        for (int kp = 0; kp < 2; ++kp) {
+          uint8_t* s = slot_acquire();
+          uint64_t* fb = &w_full[wi % NSLOT];
+          for (int q = 0; q < 2; ++q) {
+            const int kb = 2 * kp + q;
+            if (p.y_cm) {
+              const int b = tile / p.tiles_per_seq, t0 = (tile % p.tiles_per_seq) * BM;
+              for (int hh = 0; hh < 2; ++hh)   // k-block = 64 channels; two 64-token halves of 8 KB each
+                ptx::tma_load_3d(s + q * KB_BYTES + hh * (KB_BYTES / 2), &tmY, fb, t0 + hh * 64, kb * BK, b);
+            } else {
+              ptx::tma_load_2d(s + q * KB_BYTES, &tmY, fb, kb * BK, tile * BM);
+            }
+          }
+          ++wi;
+          if (kp == 0) stamp(0);
+        }
         // Weights are pre-tiled at finalize as [N/rt][K/64][rt][64] (rt = 256 for Wout/W2, 128 for W1), so
         // every 32 KB slot is ONE TMA instruction (a single thread issues ~1 TMA per 240 cycles).
         for (int kb = 0; kb < 4; ++kb) {               // out_proj: k-block kb = rows [256 kb, +256)
@@ -185,8 +185,6 @@ block_mlp_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
               ++wi;
             }
           }
-          // X is only read by out_proj, which is long finished by now: fetch the next tile's y early
-          if (j == 2 && tile + (int)gridDim.x < p.num_tiles) load_x(tile + gridDim.x, it + 1);
         }
       }
     }
@@ -196,14 +194,27 @@ block_mlp_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
       constexpr uint32_t idesc256 = ptx::idesc_bf16_f32(BM, 256);
       constexpr uint32_t idesc256_amn = ptx::idesc_bf16_f32_amn(BM, 256);
       constexpr uint32_t idesc128 = ptx::idesc_bf16_f32(BM, 128);
-      const uint32_t sX = ptx::smem_u32(smem + OFF_X);
       const uint32_t sHB = ptx::smem_u32(smem + OFF_HB);
       const uint32_t sW = ptx::smem_u32(smem + OFF_W);
       uint32_t wi = 0;
+      long long wt_slot = 0, wt_hbuf = 0, wt_hacc = 0, wt_tile = 0, t_all = clock64();
+      // The barrier of the NEXT ring slot is probed right after the current slot is handed out, so the
+      // ~100-cycle try_wait round trip overlaps the MMA issue instead of preceding every slot.
+      bool next_ready = false;
+      uint32_t probed_wi = 0xffffffffu;
+      auto probe_next = [&](uint32_t w) {
+        next_ready = ptx::mbar_try_wait(&w_full[w % NSLOT], (w / NSLOT) & 1);
+        probed_wi = w;
+      };
       auto slot_wait = [&]() -> uint32_t {
         const uint32_t s = wi % NSLOT, ph = (wi / NSLOT) & 1;
-        ptx::mbar_wait(&w_full[s], ph);
+        if (!(probed_wi == wi && next_ready)) {
+          const long long t_ = trace ? clock64() : 0;
+          ptx::mbar_wait(&w_full[s], ph);
+          if (trace) wt_slot += clock64() - t_;
+        }
         ptx::tc_fence_after_sync();
+        probe_next(wi + 1);
         return sW + s * SLOT_BYTES;
       };
       auto slot_release = [&]() {
@@ -213,37 +224,53 @@ block_mlp_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
       uint32_t it = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
         const uint32_t tph = it & 1;
+        // TMEM halves alternate per tile: R takes the half that held XN+H in the previous tile, so out_proj
+        // of this tile runs while the epilogue is still draining the previous tile's R.
+        const uint32_t TM_R = tph ? 256u : 0u, TM_XN = tph ? 0u : 256u, TM_H = tph ? 128u : 384u;
         // ---- G1: R = y * Wout^T
         stamp(1);
-        ptx::mbar_wait(r_free, tph ^ 1);     // previous tile's output drained from R
-        ptx::mbar_wait(x_full, tph);
+        { const long long t_ = trace ? clock64() : 0;
+          ptx::mbar_wait(hacc_free, ((it * NCHUNK) & 1) ^ 1);   // previous tile's last fc1 chunk drained (long ago)
+          if (trace) wt_tile += clock64() - t_; }
         ptx::tc_fence_after_sync();
         stamp(1);
+        // ring order: y(kb 0,1), y(kb 2,3), Wout kb 0..3 - the y slots are released only after the last k-block
+        const uint32_t sy0 = slot_wait(); const uint32_t wi_y0 = wi; ++wi;
+        const uint32_t sy1 = slot_wait(); const uint32_t wi_y1 = wi; ++wi;
         for (int kb = 0; kb < 4; ++kb) {
           const uint32_t sw = slot_wait();
           const uint64_t db = ptx::smem_desc_k_sw128(sw);
+          const uint32_t sx = ((kb < 2) ? sy0 : sy1) + (kb & 1) * KB_BYTES;
           if (p.y_cm) {
             // A = y^T tile: MN(token)-major, 2 atoms of 64 tokens 8 KB apart, K rows of 128 B; 16 K-rows per step
-            const uint64_t da = ptx::smem_desc_mn_sw128(sX + kb * KB_BYTES, KB_BYTES / 2, 1024);
+            const uint64_t da = ptx::smem_desc_mn_sw128(sx, KB_BYTES / 2, 1024);
 #pragma unroll
             for (int k = 0; k < 4; ++k)
               ptx::umma_f16(tmem_base + TM_R, da + (2048 >> 4) * k, db + 2 * k, idesc256_amn, (kb | k) != 0);
           } else {
-            const uint64_t da = ptx::smem_desc_k_sw128(sX + kb * KB_BYTES);
+            const uint64_t da = ptx::smem_desc_k_sw128(sx);
 #pragma unroll
             for (int k = 0; k < 4; ++k) ptx::umma_f16(tmem_base + TM_R, da + 2 * k, db + 2 * k, idesc256, (kb | k) != 0);
           }
           slot_release();
+          if (kb == 1) ptx::umma_commit(&w_empty[wi_y0 % NSLOT]);
+          if (kb == 3) ptx::umma_commit(&w_empty[wi_y1 % NSLOT]);
         }
         ptx::umma_commit(g1_done);
-        ptx::umma_commit(x_free);
         stamp(1);
         // ---- fc1 / fc2 software pipeline
         for (int j = 0; j <= NCHUNK; ++j) {
           if (j < NCHUNK) {
             const uint32_t u = it * NCHUNK + j;
-            if (j == 0) ptx::mbar_wait(xn_full, tph);
-            ptx::mbar_wait(hacc_free, (u & 1) ^ 1);
+            { const long long t_ = trace ? clock64() : 0;
+              if (j == 0) {
+                ptx::mbar_wait(xn_full, tph);
+                ptx::mbar_wait(r_free, tph ^ 1);   // previous tile's R (this tile's XN/H half) fully drained
+              }
+              if (trace && j == 0) wt_tile += clock64() - t_; }
+            { const long long t_ = trace ? clock64() : 0;
+              ptx::mbar_wait(hacc_free, (u & 1) ^ 1);
+              if (trace) wt_hacc += clock64() - t_; }
             ptx::tc_fence_after_sync();
             stamp(1);
             for (int h2 = 0; h2 < 2; ++h2) {
@@ -263,7 +290,9 @@ block_mlp_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
           if (j >= 1) {
             const int jj = j - 1;
             const uint32_t b = jj & 1, u = it * 4 + (jj >> 1);
-            ptx::mbar_wait(&hbuf_full[b], u & 1);
+            { const long long t_ = trace ? clock64() : 0;
+              ptx::mbar_wait(&hbuf_full[b], u & 1);
+              if (trace) wt_hbuf += clock64() - t_; }
             ptx::tc_fence_after_sync();
             stamp(1);
             for (int kb = 0; kb < 2; ++kb) {
@@ -280,6 +309,9 @@ block_mlp_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
         ptx::umma_commit(out_full);
         stamp(1);
       }
+      if (trace) {   // where the issuing thread waited (row 0, slots 32..36): weights, gelu(h), H drain, tile-level, total
+        trace[32] = wt_slot; trace[33] = wt_hbuf; trace[34] = wt_hacc; trace[35] = wt_tile; trace[36] = clock64() - t_all;
+      }
     }
   } else {
     // =========================== epilogue warps ===========================
@@ -295,6 +327,7 @@ block_mlp_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
       const uint32_t tph = it & 1;
+      const uint32_t TM_R = tph ? 256u : 0u, TM_XN = tph ? 0u : 256u, TM_H = tph ? 128u : 384u;
       long long row;
       bool row_ok;
       if (p.y_cm) {

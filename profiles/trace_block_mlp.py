@@ -22,6 +22,9 @@ for _ in range(2):
 t = tr.cpu()
 t0 = int(t[t > 0].min())
 names = {0: "producer(x issued per tile)", 1: "mma", 2: "epilogue(warp2)"}
+w = [int(x) for x in t[0][32:37]]
+print(f"MMA-thread waits (cycles, whole kernel): weights {w[0]}, gelu(h) ready {w[1]}, H drained {w[2]}, tile-level (r_free/xn_full) {w[3]}, total {w[4]}")
+t[0][32:37] = 0
 for role in range(3):
     v = [int(x) - t0 for x in t[role] if x > 0]
     print(names[role], len(v))
