@@ -61,7 +61,7 @@ class ClockSampler:
         self.p = None
         try:
             self.p = subprocess.Popen(["nvidia-smi", f"--id={gpu_index}", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
-                                       "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+                                       "-lms", "20"], stdout=self.f, stderr=subprocess.DEVNULL)
         except OSError:
             pass
 
@@ -86,6 +86,13 @@ class ClockSampler:
         out["reasons"] = [n for i, n in enumerate(names) if any(r[5 + i].strip().lower().startswith("active") for r in rows)]
         out["samples"] = len(rows)
         return out
+
+
+def workload_config(L, T, B, world):
+    tokens_per_step = B * T
+    return {"workload": f"K2: synthetic {L} b reads, T={T} tokens (ids+[SEP]), batch {B} per GPU, random-init ChimeraLM",
+            "read_len": L, "batch_per_gpu": B, "parallelism": f"dp{world} (reads sharded, final all_gather of labels)",
+            "l2": f"per-step activation working set ~{tokens_per_step * 256 * 12 / 1e6:.0f} MB >> 126 MB L2; {N_DISTINCT} distinct input batches rotate"}
 
 
 def cpu_reference_path(sd, cfg, seqs_ascii: np.ndarray, batch: int = 12):
@@ -126,11 +133,12 @@ def run_reference(args, sd, cfg):
         "impl": "reference", "metric": "predict_reads_per_s", "value": val, "unit": "reads/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"K2: synthetic {READ_LEN} b reads (T={READ_LEN + 1}), CPU predict path, batch 12",
-                   "read_len": READ_LEN, "batch": 12},
+        "config": workload_config(args.read_len, args.read_len + 1, args.batch, max(1, args.gpus)),
         "bases_per_s": val * READ_LEN,
         "cpu_baseline": {"value": val, "unit": "reads/s", "cores": torch.get_num_threads(), "kind": "port",
-                         "sample": f"{n_per_step} reads x {READ_LEN} b per step, {args.steps} steps"},
+                         "sample": f"each step = {n_per_step} reads x {READ_LEN} b of the same synthetic workload through the CPU predict "
+                                   f"path (python tokeniser, collate, fp32 eager forward, argmax), batch 12 (the reference CLI default); "
+                                   f"{args.steps} steps; rank 0 only"},
         "e2e": {"value": val, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
@@ -277,9 +285,7 @@ def main():
         "metric": "predict_reads_per_s", "value": reads_per_s, "unit": "reads/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": f"K2: synthetic {L} b reads, T={T} tokens (ids+[SEP]), batch {B} per GPU, random-init ChimeraLM",
-                   "read_len": L, "batch_per_gpu": B, "parallelism": f"dp{world} (reads sharded, final all_gather of labels)",
-                   "l2": f"per-step activation working set ~{tokens_per_step * 256 * 12 / 1e6:.0f} MB >> 126 MB L2; {N_DISTINCT} distinct input batches rotate"},
+        "config": workload_config(L, T, B, world),
         "bases_per_s": reads_per_s * L,
         "tokens_per_s": reads_per_s * T,
         "dense_tensor_frac_of_peak": dense_frac,
