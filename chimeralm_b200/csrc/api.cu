@@ -68,6 +68,12 @@ struct clm_ctx {
   const float *lnf_g, *lnf_b, *emb;
   __nv_bfloat16* att0_w = nullptr;
   CUtensorMap tm_att0;
+  // ln_f affine folded into the scorer (consumes the normalised xn emitted by the last block_mlp)
+  __nv_bfloat16* att0_wf = nullptr;
+  float* att0_bf = nullptr;
+  CUtensorMap tm_att0f;
+  __nv_bfloat16* emb_norm = nullptr;   // [vocab_rows,256] normalised embedding rows (layer-0 LayerNorm input)
+  float *ones = nullptr, *zeros = nullptr;
   const float *att0_b, *att2_w;
   float att2_b = 0.f;
   HeadParams head{};
@@ -259,32 +265,45 @@ int make_tmap_ct_bf16_3d(clm_ctx* c, CUtensorMap* tm, const void* base, int B, i
   return 0;
 }
 
-int launch_block_in(clm_ctx* c, int layer, const float* res, int B, int T, int Tp, __nv_bfloat16* vx,
-                    __nv_bfloat16* x0, cudaStream_t st) {
+// xn as a 3-D tensor {col 256, t T, b B} over a token-major bf16 [B*T,256] buffer; box {64, box_rows, 1}
+int make_tmap_xn(clm_ctx* c, CUtensorMap* tm, const void* base, int B, int T, int box_rows) {
+  cuuint64_t dims[3] = {256, (cuuint64_t)T, (cuuint64_t)B};
+  cuuint64_t strides[2] = {512, (cuuint64_t)T * 512};
+  cuuint32_t box[3] = {64, (cuuint32_t)box_rows, 1}, estr[3] = {1, 1, 1};
+  CUresult r = c->encode_tiled(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(c, CLM_ERR_CUDA, "cuTensorMapEncodeTiled(xn) failed with CUresult %d", (int)r);
+  return 0;
+}
+
+int launch_block_in(clm_ctx* c, int layer, const __nv_bfloat16* xn, int B, int T, int Tp, __nv_bfloat16* vx,
+                    __nv_bfloat16* x0, cudaStream_t st, long long* trace = nullptr) {
   static bool attr_set = false;
   if (!attr_set) {
     CLM_CUDA(c, cudaFuncSetAttribute(block_in_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bi::SMEM_TOTAL));
     attr_set = true;
   }
   LayerW& L = c->layers[layer];
-  CUtensorMap tmVX, tmX0;
+  CUtensorMap tmVX, tmX0, tmXN;
   int rc;
   if ((rc = make_tmap_ct_bf16_3d(c, &tmVX, vx, B, c->cfg.d_model, Tp))) return rc;
   if ((rc = make_tmap_ct_bf16_3d(c, &tmX0, x0, B, c->cfg.d_model, Tp))) return rc;
+  if ((rc = make_tmap_xn(c, &tmXN, xn, B, T, bi::NCOL))) return rc;
   BlockInParams p{};
-  p.res = res; p.b_in = L.in_bf; p.cw = L.sc_w; p.cb = L.sc_b; p.eps = c->cfg.layer_norm_eps;
-  p.B = B; p.T = T;
+  p.b_in = L.in_bf; p.cw = L.sc_w; p.cb = L.sc_b;
+  p.B = B; p.T = T; p.trace = trace;
   p.tiles_per_seq = (T + bi::BT - 1) / bi::BT;
   p.num_tiles = B * p.tiles_per_seq;
   const int grid = std::min(p.num_tiles, c->num_sms);
-  block_in_kernel<<<grid, bi::THREADS, bi::SMEM_TOTAL, st>>>(L.tm_inf, tmVX, tmX0, p);
+  block_in_kernel<<<grid, bi::THREADS, bi::SMEM_TOTAL, st>>>(L.tm_inf, tmVX, tmX0, tmXN, p);
   CLM_LAUNCH_CHECK(c, "block_in");
   return 0;
 }
 
 // y token-major [M,256] when B == 0; channel-major [B][256][Tp] (M == B*T) otherwise
 int launch_block_mlp(clm_ctx* c, int layer, const __nv_bfloat16* y, float* res, int M, cudaStream_t st,
-                     long long* trace = nullptr, int B = 0, int T = 0, int Tp = 0) {
+                     long long* trace = nullptr, int B = 0, int T = 0, int Tp = 0, __nv_bfloat16* xn_out = nullptr) {
   static bool attr_set = false;
   if (!attr_set) {
     CLM_CUDA(c, cudaFuncSetAttribute(block_mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bm::SMEM_TOTAL));
@@ -312,8 +331,13 @@ int launch_block_mlp(clm_ctx* c, int layer, const __nv_bfloat16* y, float* res, 
   if (B > 0) {
     p.y_cm = 1; p.T = T; p.tiles_per_seq = (T + bm::BM - 1) / bm::BM; p.num_tiles = B * p.tiles_per_seq;
   }
+  CUtensorMap tmXN = tmY;
+  if (xn_out) {
+    p.write_xn = 1;
+    if ((rc = make_tmap_xn(c, &tmXN, xn_out, B > 0 ? B : 1, B > 0 ? T : M, 128))) return rc;
+  }
   const int grid = std::min(p.num_tiles, c->num_sms);
-  block_mlp_kernel<<<grid, bm::THREADS, bm::SMEM_TOTAL, st>>>(tmY, L.tm_out_t, L.tm_fc1_t, L.tm_fc2_t, p);
+  block_mlp_kernel<<<grid, bm::THREADS, bm::SMEM_TOTAL, st>>>(tmY, L.tm_out_t, L.tm_fc1_t, L.tm_fc2_t, tmXN, p);
   CLM_LAUNCH_CHECK(c, "block_mlp");
   return 0;
 }
@@ -691,6 +715,23 @@ int clm_finalize(clm_ctx* c) {
   CLM_CUDA(c, cudaMemcpy(&c->att2_b, a2b, sizeof(float), cudaMemcpyDeviceToHost));
   if ((rc = to_bf16(c, a0w, (int64_t)D * D, &c->att0_w))) return rc;
   if ((rc = make_tmap_bf16_2d(c, &c->tm_att0, c->att0_w, D, D, 256))) return rc;
+  {
+    float* wf = nullptr;
+    if ((rc = dev_alloc(c, &wf, (size_t)D * D))) return rc;
+    if ((rc = dev_alloc(c, &c->att0_bf, (size_t)D))) return rc;
+    fold_ln_kernel<<<D, 256>>>(a0w, c->att0_b, c->lnf_g, c->lnf_b, wf, c->att0_bf, D);
+    CLM_LAUNCH_CHECK(c, "fold_ln_f");
+    if ((rc = to_bf16(c, wf, (int64_t)D * D, &c->att0_wf))) return rc;
+    if ((rc = make_tmap_bf16_2d(c, &c->tm_att0f, c->att0_wf, D, D, 256))) return rc;
+    if ((rc = dev_alloc(c, &c->emb_norm, (size_t)g.vocab_rows * D))) return rc;
+    embed_norm_table_kernel<<<g.vocab_rows, 32>>>(c->emb, c->emb_norm, g.vocab_rows, g.layer_norm_eps);
+    CLM_LAUNCH_CHECK(c, "embed_norm_table");
+    std::vector<float> h1(D, 1.0f);
+    if ((rc = dev_alloc(c, &c->ones, (size_t)D))) return rc;
+    if ((rc = dev_alloc(c, &c->zeros, (size_t)D))) return rc;
+    CLM_CUDA(c, cudaMemcpy(c->ones, h1.data(), D * sizeof(float), cudaMemcpyHostToDevice));
+    CLM_CUDA(c, cudaMemset(c->zeros, 0, D * sizeof(float)));
+  }
   const int H = g.head_hidden;
   NEED(HD + "classifier.0.weight", (int64_t)H * D, &c->head.w0);
   NEED(HD + "classifier.0.bias", H, &c->head.b0);
@@ -790,19 +831,25 @@ int clm_forward(clm_ctx* c, const void* d_ids, int ids_dtype, int B, int T, floa
 
   { ProfScope ps_(c, PC_EMBED, st);
   switch (ids_dtype) {
-    case CLM_U8: embed_kernel<uint8_t><<<rows8, 256, 0, st>>>((const uint8_t*)d_ids, c->emb, c->R, M, D, g.vocab_rows, c->d_err); break;
-    case CLM_I32: embed_kernel<int32_t><<<rows8, 256, 0, st>>>((const int32_t*)d_ids, c->emb, c->R, M, D, g.vocab_rows, c->d_err); break;
-    case CLM_I64: embed_kernel<int64_t><<<rows8, 256, 0, st>>>((const int64_t*)d_ids, c->emb, c->R, M, D, g.vocab_rows, c->d_err); break;
+    case CLM_U8: embed_kernel<uint8_t><<<rows8, 256, 0, st>>>((const uint8_t*)d_ids, c->emb, c->emb_norm, c->R, c->XN, M, D, g.vocab_rows, c->d_err); break;
+    case CLM_I32: embed_kernel<int32_t><<<rows8, 256, 0, st>>>((const int32_t*)d_ids, c->emb, c->emb_norm, c->R, c->XN, M, D, g.vocab_rows, c->d_err); break;
+    case CLM_I64: embed_kernel<int64_t><<<rows8, 256, 0, st>>>((const int64_t*)d_ids, c->emb, c->emb_norm, c->R, c->XN, M, D, g.vocab_rows, c->d_err); break;
     default: return fail(c, CLM_ERR_INVALID, "clm_forward: ids dtype %d not supported", ids_dtype);
   }
   CLM_LAUNCH_CHECK(c, "embed"); }
   STOP_AFTER(0, 0);
+  bool xn_valid = true;   // XN holds the normalised (no affine) residual for the next LayerNorm consumer
 
   for (int l = 0; l < g.n_layer; ++l) {
     LayerW& L = c->layers[l];
     if (c->fused_in && c->dbg_layer != l) {
+      if (!xn_valid) {
+        ProfScope ps_(c, PC_LN, st);
+        layernorm_bf16_kernel<<<rows32, 256, 0, st>>>(c->R, c->ones, c->zeros, c->XN, M, g.layer_norm_eps);
+        CLM_LAUNCH_CHECK(c, "normalize");
+      }
       ProfScope ps_(c, PC_BLOCK_IN, st);
-      if ((rc = launch_block_in(c, l, c->R, B, T, Tp, c->VX, c->X0, st))) return rc;
+      if ((rc = launch_block_in(c, l, c->XN, B, T, Tp, c->VX, c->X0, st))) return rc;
     } else {
     { ProfScope ps_(c, PC_LN, st);
       layernorm_bf16_kernel<<<rows32, 256, 0, st>>>(c->R, L.ln1_g, L.ln1_b, c->XN, M, g.layer_norm_eps);
@@ -830,9 +877,10 @@ int clm_forward(clm_ctx* c, const void* d_ids, int ids_dtype, int B, int T, floa
     STOP_AFTER(l, 5);
     if (mlp_fused) {
       ProfScope ps_(c, PC_BLOCK_MLP, st);
-      if (c->y_channel_major) rc = launch_block_mlp(c, l, c->Y, c->R, (int)M, st, nullptr, B, T, Tp);
-      else rc = launch_block_mlp(c, l, c->YT, c->R, (int)M, st);
+      if (c->y_channel_major) rc = launch_block_mlp(c, l, c->Y, c->R, (int)M, st, nullptr, B, T, Tp, c->XN);
+      else rc = launch_block_mlp(c, l, c->YT, c->R, (int)M, st, nullptr, 0, 0, 0, c->XN);
       if (rc) return rc;
+      xn_valid = true;
     } else {
       GemmParams p{};
       p.M = (int)M; p.N = D; p.K = D; p.bias = L.out_b; p.out = c->R; p.res = c->R; p.ldo = D; p.r32 = 1;
@@ -853,18 +901,28 @@ int clm_forward(clm_ctx* c, const void* d_ids, int ids_dtype, int B, int T, floa
       { ProfScope ps_(c, PC_GEMM_FC2, st);
       if ((rc = launch_gemm(c, c->U, L.tm_fc2, p, EPI_BIAS_RES_F32, st))) return rc; }
     }
+    if (!mlp_fused) xn_valid = false;
     STOP_AFTER(l, 9);
   }
   const int NL = g.n_layer;
-  { ProfScope ps_(c, PC_LN, st);
-  layernorm_bf16_kernel<<<rows32, 256, 0, st>>>(c->R, c->lnf_g, c->lnf_b, c->XN, M, g.layer_norm_eps);
-  CLM_LAUNCH_CHECK(c, "ln_f"); }
+  const bool tail_folded = xn_valid && c->dbg_layer != NL;
+  if (!tail_folded) {
+    ProfScope ps_(c, PC_LN, st);
+    layernorm_bf16_kernel<<<rows32, 256, 0, st>>>(c->R, c->lnf_g, c->lnf_b, c->XN, M, g.layer_norm_eps);
+    CLM_LAUNCH_CHECK(c, "ln_f");
+  }
   STOP_AFTER(NL, 10);
   {
     GemmParams p{};
-    p.M = (int)M; p.N = D; p.K = D; p.bias = c->att0_b; p.w2 = c->att2_w; p.b2 = c->att2_b; p.score = c->score; p.ldo = D;
+    p.M = (int)M; p.N = D; p.K = D; p.w2 = c->att2_w; p.b2 = c->att2_b; p.score = c->score; p.ldo = D;
     ProfScope ps_(c, PC_SCORE, st);
-    if ((rc = launch_gemm(c, c->XN, c->tm_att0, p, EPI_SCORE, st))) return rc;
+    if (tail_folded) {   // XN = normalised residual from the last block: ln_f's affine lives in the folded scorer weights
+      p.bias = c->att0_bf;
+      if ((rc = launch_gemm(c, c->XN, c->tm_att0f, p, EPI_SCORE, st))) return rc;
+    } else {
+      p.bias = c->att0_b;
+      if ((rc = launch_gemm(c, c->XN, c->tm_att0, p, EPI_SCORE, st))) return rc;
+    }
   }
   STOP_AFTER(NL, 11);
   { ProfScope ps_(c, PC_POOL, st);
@@ -928,11 +986,32 @@ int clm_set_option(clm_ctx* c, const char* name, int value) {
   return 0;
 }
 
+// d_res (R32) is first normalised into the context's XN workspace (needs clm_reserve >= B x T)
+int normalize_for_block_in(clm_ctx* c, const float* d_res, int B, int T, cudaStream_t st) {
+  if ((size_t)B * T > (size_t)c->max_B * c->max_T) return fail(c, CLM_ERR_STATE, "clm_block_in: call clm_reserve(B, T) first");
+  const long long M = (long long)B * T;
+  layernorm_bf16_kernel<<<(unsigned)((M + 31) / 32), 256, 0, st>>>(d_res, c->ones, c->zeros, c->XN, M, c->cfg.layer_norm_eps);
+  CLM_LAUNCH_CHECK(c, "normalize");
+  return 0;
+}
+
 int clm_block_in(clm_ctx* c, int layer, const float* d_res, int B, int T, int Tp, void* d_vx, void* d_x0, void* stream) {
   if (!c || !c->finalized) return fail(c, CLM_ERR_STATE, "clm_block_in before clm_finalize");
   if (layer < 0 || layer >= c->cfg.n_layer || !d_res || !d_vx || !d_x0 || B <= 0 || T <= 0 || Tp < T || Tp % 64 != 0)
     return fail(c, CLM_ERR_INVALID, "clm_block_in: bad argument");
-  return launch_block_in(c, layer, d_res, B, T, Tp, (__nv_bfloat16*)d_vx, (__nv_bfloat16*)d_x0, (cudaStream_t)stream);
+  int rc = normalize_for_block_in(c, d_res, B, T, (cudaStream_t)stream);
+  if (rc) return rc;
+  return launch_block_in(c, layer, c->XN, B, T, Tp, (__nv_bfloat16*)d_vx, (__nv_bfloat16*)d_x0, (cudaStream_t)stream);
+}
+
+int clm_block_in_trace(clm_ctx* c, int layer, const float* d_res, int B, int T, int Tp, void* d_vx, void* d_x0,
+                       long long* d_trace, void* stream) {
+  if (!c || !c->finalized) return fail(c, CLM_ERR_STATE, "clm_block_in_trace before clm_finalize");
+  if (layer < 0 || layer >= c->cfg.n_layer || !d_res || !d_vx || !d_x0 || !d_trace || B <= 0 || T <= 0 || Tp < T || Tp % 64 != 0)
+    return fail(c, CLM_ERR_INVALID, "clm_block_in_trace: bad argument");
+  int rc = normalize_for_block_in(c, d_res, B, T, (cudaStream_t)stream);
+  if (rc) return rc;
+  return launch_block_in(c, layer, c->XN, B, T, Tp, (__nv_bfloat16*)d_vx, (__nv_bfloat16*)d_x0, (cudaStream_t)stream, d_trace);
 }
 
 int clm_block_mlp(clm_ctx* c, int layer, const void* d_y, float* d_res, int M, void* stream) {

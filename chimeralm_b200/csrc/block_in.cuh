@@ -1,13 +1,14 @@
 // Fused first half of a HyenaDNA block, one persistent kernel (SURVEY.md A.6 head + A.3):
 //
-//   xn      = LayerNorm1(res)                                  (affine folded into W'/b', see below)
+//   xn      = LayerNorm1(res)              (normalised by the PRODUCER of res - block_mlp's output epilogue or
+//                                           the embedding kernel; affine folded into W'/b', see below)
 //   u       = xn * W_in^T + b_in                               (HyenaOperator.in_proj, 256 -> 768)
 //   uc[c,t] = w[c,0] u[c,t-2] + w[c,1] u[c,t-1] + w[c,2] u[c,t] + cb[c]      (short_filter, causal k=3)
 //   x0, x1, v = uc[0:256], uc[256:512], uc[512:768];   vx = v * x1            (first gate)
 //   outputs : vx, x0 as channel-major bf16 [B][256][Tp]  (what the long convolution consumes)
 //
 // Replaces nn.LayerNorm + nn.Linear + nn.Conv1d(groups=768) + split + mul of the reference and
-// the transpose between them: per token the kernel reads 1 KB (res) and writes 1 KB (vx, x0);
+// the transpose between them: per token the kernel reads 512 B (xn) and writes 1 KB (vx, x0);
 // the 768-wide in_proj output never leaves the SM.
 //
 // The GEMM is computed TRANSPOSED: D[channel, token] = W'[channel,:] . xn[token,:], so that in
@@ -22,7 +23,9 @@
 // b' = b_in + W_in beta, so the kernel only normalises.
 //
 // Warp roles: warp 0 = TMA producer (weight ring, 2 x 32 KB), warp 1 = MMA issuer,
-// warps 2..9 = LayerNorm producers of the B operand, then epilogue (conv + gate + TMA store).
+// warps 2..9 = epilogue (conv + gate + TMA store).  The B operand tile arrives by TMA: an earlier version
+// normalised it in-kernel from the fp32 residual and spent 44% of each tile waiting on that burst of loads
+// (profiles/r1_trace_block_in.txt).
 // Weight slots are 32 KB single-TMA boxes (a single thread issues only ~1 TMA per 240 cycles,
 // profiles/probes/tma_stream_probe.cu).
 #pragma once
@@ -34,13 +37,12 @@
 namespace clm {
 
 struct BlockInParams {
-  const float* res;     // residual stream, R32 layout
   const float* b_in;    // [768] folded bias
   const float* cw;      // [768][3] short filter taps
   const float* cb;      // [768]   short filter bias
-  float eps;
   int B, T;
   int tiles_per_seq, num_tiles;
+  long long* trace;     // optional [2][64] clock64 stamps of CTA 0 (row 0 = MMA issuer, row 1 = epilogue warp 2)
 };
 
 namespace bi {
@@ -66,7 +68,7 @@ __device__ __forceinline__ void tmem_ld_32x32b_x2(uint32_t taddr, uint32_t& a, u
 
 __global__ void __launch_bounds__(bi::THREADS, 1)
 block_in_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmVX,
-                const __grid_constant__ CUtensorMap tmX0, BlockInParams p) {
+                const __grid_constant__ CUtensorMap tmX0, const __grid_constant__ CUtensorMap tmXN, BlockInParams p) {
   using namespace bi;
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((ptx::smem_u32(smem) & 1023u) != 0) __trap();
@@ -81,11 +83,16 @@ block_in_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
   float (*s_part)[2][128] = reinterpret_cast<float (*)[2][128]>(smem + OFF_PART);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  long long* trace = (p.trace && blockIdx.x == 0) ? p.trace : nullptr;
+  int trace_n = 0;
+  auto stamp = [&](int role) {
+    if (trace && trace_n < 64) trace[role * 64 + trace_n++] = clock64();
+  };
 
   if (warp == 0 && lane == 0) {
-    ptx::prefetch_tmap(&tmW); ptx::prefetch_tmap(&tmVX); ptx::prefetch_tmap(&tmX0);
+    ptx::prefetch_tmap(&tmW); ptx::prefetch_tmap(&tmVX); ptx::prefetch_tmap(&tmX0); ptx::prefetch_tmap(&tmXN);
     for (int i = 0; i < NSLOT; ++i) { ptx::mbar_init(&w_full[i], 1); ptx::mbar_init(&w_empty[i], 1); }
-    ptx::mbar_init(xn_full, 8); ptx::mbar_init(xn_free, 1);
+    ptx::mbar_init(xn_full, 1); ptx::mbar_init(xn_free, 1);
     ptx::mbar_init(acc_full, 1); ptx::mbar_init(acc_free, 8);
     ptx::fence_mbar_init();
   } else if (warp == 1) {
@@ -101,8 +108,15 @@ block_in_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
     // W' is pre-tiled at finalize as [n/128][kb][128][64]: k-blocks (2kp, 2kp+1) of one 128-channel block
     // are 256 consecutive rows of a [.. x 64] matrix, i.e. one 32 KB TMA box per slot.
     if (lane == 0) {
-      uint32_t wi = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      uint32_t wi = 0, it = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+        {  // B operand: normalised tokens [t0 - 16, t0 + 128) of read b, 4 k-blocks of [144 rows x 64]; rows
+           // outside [0, T) are zero-filled by TMA (their products are discarded by the epilogue)
+          const int b = tile / p.tiles_per_seq, t0 = (tile % p.tiles_per_seq) * BT;
+          ptx::mbar_wait(xn_free, (it & 1) ^ 1);
+          ptx::mbar_expect_tx(xn_full, XN_BYTES);
+          for (int kb = 0; kb < 4; ++kb) ptx::tma_load_3d(smem + OFF_XN + kb * KB_ROWS_BYTES, &tmXN, xn_full, kb * 64, t0 - HALO, b);
+        }
         for (int h = 0; h < 2; ++h)
           for (int g = 0; g < 3; ++g)
             for (int kp = 0; kp < 2; ++kp) {
@@ -121,10 +135,13 @@ block_in_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
       const uint32_t sXN = ptx::smem_u32(smem + OFF_XN), sW = ptx::smem_u32(smem + OFF_W);
       uint32_t wi = 0, it = 0, pass = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+        stamp(0);
         ptx::mbar_wait(xn_full, it & 1);
+        stamp(0);
         for (int h = 0; h < 2; ++h, ++pass) {
           ptx::mbar_wait(acc_free, (pass & 1) ^ 1);
           ptx::tc_fence_after_sync();
+          stamp(0);
           for (int g = 0; g < 3; ++g)
             for (int kp = 0; kp < 2; ++kp) {
               const uint32_t s = wi % NSLOT, ph = (wi / NSLOT) & 1;
@@ -144,6 +161,7 @@ block_in_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
             }
           ptx::umma_commit(acc_full);
           if (h == 1) ptx::umma_commit(xn_free);
+          stamp(0);
         }
       }
     }
@@ -154,85 +172,47 @@ block_in_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
     const int hf = e >> 2;             // LN: column half of the row; epilogue: token half of the tile
     const int r = q * 32 + lane;       // LN: row 0..127 of the tile; epilogue: channel inside the pass
     const uint32_t lane_addr = tmem_base + (uint32_t(q * 32) << 16);
-    const uint32_t sXN = ptx::smem_u32(smem + OFF_XN);
     const uint32_t sST = ptx::smem_u32(smem + OFF_STAGE);
     const bool issuer = (threadIdx.x == 64);
+    // per-thread channel constants for both passes (thread = channel h*128 + r of each group): loaded once
+    float c_bia[2][3], c_w0[2][3], c_w1[2][3], c_w2[2][3], c_cb[2][3];
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+      for (int g = 0; g < 3; ++g) {
+        const int ch = g * 256 + h * 128 + r;
+        c_bia[h][g] = __ldg(p.b_in + ch);
+        c_w0[h][g] = __ldg(p.cw + ch * 3);
+        c_w1[h][g] = __ldg(p.cw + ch * 3 + 1);
+        c_w2[h][g] = __ldg(p.cw + ch * 3 + 2);
+        c_cb[h][g] = __ldg(p.cb + ch);
+      }
     uint32_t it = 0, pass = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
       const int b = tile / p.tiles_per_seq;
       const int t0 = (tile % p.tiles_per_seq) * BT;
       const long long seq_row0 = (long long)b * p.T;
-      // ------------------------------------------------ LayerNorm -> B operand (xn, bf16, SW128 K-major)
-      ptx::mbar_wait(xn_free, (it & 1) ^ 1);
-      // round 0: tile rows 0..127 (thread = row r, column half hf); round 1: rows 128..143 (warp 2 only:
-      // lanes 0-15 take the low half, lanes 16-31 the high half of row 128 + lane % 16)
-#pragma unroll 1
-      for (int round = 0; round < 2; ++round) {
-        if (round == 1 && e != 0) break;
-        const int trow = (round == 0) ? r : (128 + (lane & 15));
-        const int half = (round == 0) ? hf : (lane >> 4);
-        const int t = t0 - HALO + trow;
-        const bool ok = (t >= 0);      // t < 0: left of the read (conv zero padding; value unused)
-        const long long grow = seq_row0 + t;
-        float4 x[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          x[j] = ok ? *reinterpret_cast<const float4*>(p.res + ptx::r32_off(grow, half * 128 + 4 * j))
-                    : make_float4(0.f, 0.f, 0.f, 0.f);
-        float s1 = 0.f, s2 = 0.f;
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          s1 += (x[j].x + x[j].y) + (x[j].z + x[j].w);
-          s2 += (x[j].x * x[j].x + x[j].y * x[j].y) + (x[j].z * x[j].z + x[j].w * x[j].w);
-        }
-        float ts1, ts2;
-        if (round == 0) {
-          s_part[hf][0][r] = s1;
-          s_part[hf][1][r] = s2;
-          ptx::bar_sync(1, EPI_THREADS);
-          ts1 = s_part[0][0][r] + s_part[1][0][r];
-          ts2 = s_part[0][1][r] + s_part[1][1][r];
-        } else {
-          ts1 = s1 + __shfl_xor_sync(0xffffffffu, s1, 16);
-          ts2 = s2 + __shfl_xor_sync(0xffffffffu, s2, 16);
-        }
-        const float mean = ts1 * (1.0f / D);
-        const float rstd = rsqrtf(fmaxf(ts2 * (1.0f / D) - mean * mean, 0.f) + p.eps);
-        const uint32_t swz = uint32_t(trow & 7);
-#pragma unroll
-        for (int c8 = 0; c8 < 16; ++c8) {   // 16 chunks of 8 columns in this half
-          const int col = half * 128 + c8 * 8;
-          const float4 a = x[2 * c8], c4 = x[2 * c8 + 1];
-          const uint32_t w0 = pack_bf16((a.x - mean) * rstd, (a.y - mean) * rstd);
-          const uint32_t w1 = pack_bf16((a.z - mean) * rstd, (a.w - mean) * rstd);
-          const uint32_t w2 = pack_bf16((c4.x - mean) * rstd, (c4.y - mean) * rstd);
-          const uint32_t w3 = pack_bf16((c4.z - mean) * rstd, (c4.w - mean) * rstd);
-          const uint32_t addr = sXN + (col >> 6) * KB_ROWS_BYTES + trow * 128 + ((uint32_t((col & 63) >> 3) ^ swz) << 4);
-          ptx::st_shared_v4(addr, w0, w1, w2, w3);
-        }
-      }
-      ptx::fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(xn_full);
+      const bool tr = trace && warp == 2 && lane == 0;
+      if (tr) stamp(1);
       // ------------------------------------------------ two passes of conv + gate epilogue
 #pragma unroll 1
       for (int h = 0; h < 2; ++h, ++pass) {
-        // per-thread channel constants (thread = channel h*128 + r of each group)
         float bia[3], w0[3], w1[3], w2[3], cbv[3];
 #pragma unroll
         for (int g = 0; g < 3; ++g) {
-          const int ch = g * 256 + h * 128 + r;
-          bia[g] = __ldg(p.b_in + ch);
-          w0[g] = __ldg(p.cw + ch * 3);
-          w1[g] = __ldg(p.cw + ch * 3 + 1);
-          w2[g] = __ldg(p.cw + ch * 3 + 2);
-          cbv[g] = __ldg(p.cb + ch);
+          bia[g] = h ? c_bia[1][g] : c_bia[0][g];
+          w0[g] = h ? c_w0[1][g] : c_w0[0][g];
+          w1[g] = h ? c_w1[1][g] : c_w1[0][g];
+          w2[g] = h ? c_w2[1][g] : c_w2[0][g];
+          cbv[g] = h ? c_cb[1][g] : c_cb[0][g];
         }
         // staging buffers may still be read by the previous pass's TMA stores
         if (issuer) ptx::tma_store_wait_read<0>();
         ptx::bar_sync(1, EPI_THREADS);
+        if (tr) stamp(1);
         ptx::mbar_wait(acc_full, pass & 1);
         ptx::tc_fence_after_sync();
+        if (tr) stamp(1);
         const int cbase = HALO + hf * 64;   // first output column of this thread
         float hm2[3], hm1[3];               // u[j-2], u[j-1] carried along the columns
 #pragma unroll
@@ -293,6 +273,7 @@ block_in_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
           }
           ptx::tma_store_commit();
         }
+        if (tr) stamp(1);
       }
     }
     if (issuer) ptx::tma_store_wait<0>();

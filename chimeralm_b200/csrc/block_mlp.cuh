@@ -42,6 +42,9 @@ struct BlockMlpParams {
   // y_cm == 1: y is channel-major [B][256][Tp] (tmY 3-D {t, c, b}); tiles are 128 tokens of ONE read,
   //            fed to out_proj as an MN-major A operand, so no transpose pass is needed.
   int y_cm, T, tiles_per_seq;
+  // write_xn: the output epilogue also emits xn = (out - mean) * rstd as bf16 [B][T][256] (tmXN, 3-D {col, t, b}):
+  // the next consumer's LayerNorm (affine folded into its weights) without another pass over the residual.
+  int write_xn;
   long long* trace;      // optional [3][64] clock64 stamps written by CTA 0 (null in production)
 };
 
@@ -86,7 +89,8 @@ __device__ __forceinline__ float gelu_tanh_fast(float x) {
 
 __global__ void __launch_bounds__(bm::THREADS, 1)
 block_mlp_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmWout,
-                 const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2, BlockMlpParams p) {
+                 const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2,
+                 const __grid_constant__ CUtensorMap tmXN, BlockMlpParams p) {
   using namespace bm;
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((ptx::smem_u32(smem) & 1023u) != 0) __trap();  // swizzled UMMA/TMA tiles need 1 KB alignment
@@ -117,6 +121,7 @@ block_mlp_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmY); ptx::prefetch_tmap(&tmWout); ptx::prefetch_tmap(&tmW1); ptx::prefetch_tmap(&tmW2);
+    ptx::prefetch_tmap(&tmXN);
     for (int i = 0; i < NSLOT; ++i) { ptx::mbar_init(&w_full[i], 1); ptx::mbar_init(&w_empty[i], 1); }
     ptx::mbar_init(g1_done, 1);
     ptx::mbar_init(xn_full, 8);
@@ -375,6 +380,7 @@ block_mlp_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
       }
       s_part[hf][0][r] = s1;
       s_part[hf][1][r] = s2;
+      if (threadIdx.x == 64) ptx::tma_store_wait_read<0>();   // previous tile's xn store has finished reading HB
       ptx::bar_sync(1, EPI_THREADS);
       const float ts1 = s_part[0][0][r] + s_part[1][0][r];
       const float ts2 = s_part[0][1][r] + s_part[1][1][r];
@@ -431,29 +437,71 @@ block_mlp_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
         if (lane == 0) ptx::mbar_arrive(&hbuf_full[b]);
         if (tr) stamp(2);
       }
-      // ------------------------------------------------ E3: out = R + b2 -> res
+      // ------------------------------------------------ E3: out = R + b2 -> res (+ normalised xn for the next consumer)
       ptx::mbar_wait(out_full, tph);
       ptx::tc_fence_after_sync();
       if (tr) stamp(2);
+      float o1 = 0.f, o2 = 0.f;
 #pragma unroll 1
-      for (int c0 = 0; c0 < 128; c0 += 32) {
-        const int col = hf * 128 + c0;
+      for (int ci = 0; ci < 4; ++ci) {
+        const int col = hf * 128 + ci * 32;
         uint32_t a[32];
         ptx::tmem_ld_32x32b_x32(lane_addr + TM_R + col, a);
         ptx::tmem_ld_wait();
-        if (row_ok) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
-            *reinterpret_cast<float4*>(p.res + ptx::r32_off(row, col + 4 * j)) =
-                make_float4(__uint_as_float(a[4 * j]) + lc.b2[col + 4 * j], __uint_as_float(a[4 * j + 1]) + lc.b2[col + 4 * j + 1],
-                            __uint_as_float(a[4 * j + 2]) + lc.b2[col + 4 * j + 2], __uint_as_float(a[4 * j + 3]) + lc.b2[col + 4 * j + 3]);
+        for (int j = 0; j < 8; ++j) {
+          const float4 v = make_float4(__uint_as_float(a[4 * j]) + lc.b2[col + 4 * j], __uint_as_float(a[4 * j + 1]) + lc.b2[col + 4 * j + 1],
+                                       __uint_as_float(a[4 * j + 2]) + lc.b2[col + 4 * j + 2], __uint_as_float(a[4 * j + 3]) + lc.b2[col + 4 * j + 3]);
+          if (row_ok) *reinterpret_cast<float4*>(p.res + ptx::r32_off(row, col + 4 * j)) = v;
+          o1 += (v.x + v.y) + (v.z + v.w);
+          o2 += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
         }
+      }
+      if (p.write_xn) {
+        s_part[hf][0][r] = o1;
+        s_part[hf][1][r] = o2;
+        ptx::bar_sync(2, EPI_THREADS);
+        const float m_ = (s_part[0][0][r] + s_part[1][0][r]) * (1.0f / D);
+        const float v_ = fmaxf((s_part[0][1][r] + s_part[1][1][r]) * (1.0f / D) - m_ * m_, 0.f);
+        const float rs_ = rsqrtf(v_ + p.eps);
+        // second sweep over R (TMEM reads are cheap): normalise and stage into HB (idle until the next tile's first
+        // GELU chunk) as 4 k-blocks of [128 rows x 128 B], 128B-swizzled, for the TMA store
+#pragma unroll 1
+        for (int ci = 0; ci < 4; ++ci) {
+          const int col = hf * 128 + ci * 32;
+          uint32_t a[32];
+          ptx::tmem_ld_32x32b_x32(lane_addr + TM_R + col, a);
+          ptx::tmem_ld_wait();
+          const uint32_t rowaddr = sHB + (col >> 6) * KB_BYTES + r * 128;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            float x[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) x[j] = (__uint_as_float(a[g * 8 + j]) + lc.b2[col + g * 8 + j] - m_) * rs_;
+            const uint32_t chunk = uint32_t(((col & 63) >> 3) + g) ^ swz;
+            ptx::st_shared_v4(rowaddr + chunk * 16, pack_bf16(x[0], x[1]), pack_bf16(x[2], x[3]), pack_bf16(x[4], x[5]),
+                              pack_bf16(x[6], x[7]));
+          }
+        }
+        ptx::fence_proxy_async_smem();
       }
       ptx::tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(r_free);
+      if (p.write_xn) {
+        ptx::bar_sync(1, EPI_THREADS);
+        if (threadIdx.x == 64) {
+          int xb, xt0;
+          if (p.y_cm) { xb = tile / p.tiles_per_seq; xt0 = (tile % p.tiles_per_seq) * BM; }
+          else { xb = 0; xt0 = tile * BM; }
+#pragma unroll
+          for (int kb = 0; kb < 4; ++kb) ptx::tma_store_3d(&tmXN, smem + OFF_HB + kb * KB_BYTES, kb * BK, xt0, xb);
+          ptx::tma_store_commit();
+        }
+      }
       if (tr) stamp(2);
     }
+    if (threadIdx.x == 64) ptx::tma_store_wait<0>();
   }
   ptx::tc_fence_before_sync();
   __syncthreads();

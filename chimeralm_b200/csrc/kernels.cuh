@@ -47,9 +47,12 @@ __global__ void __launch_bounds__(256) encode_kernel(EncodeParams p) {
 // ---------------------------------------------------------------------------------------------
 // Embedding gather (HyenaEmbeddings.word_embeddings, A.2): one warp per token, fp32 residual out
 // in the R32 blocked layout (ptx::r32_off).
+// It also writes the layer-0 LayerNorm input xn = (E[id] - mean) / std as bf16 token-major, looked up from a
+// per-vocabulary-row table built at finalize (the block kernels fold the LayerNorm affine into their weights).
 template <typename IdT>
 __global__ void __launch_bounds__(256) embed_kernel(const IdT* __restrict__ ids, const float* __restrict__ E,
-                                                    float* __restrict__ R, long long M, int D, int vocab_rows,
+                                                    const __nv_bfloat16* __restrict__ En, float* __restrict__ R,
+                                                    __nv_bfloat16* __restrict__ XN, long long M, int D, int vocab_rows,
                                                     int* __restrict__ err) {
   const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -61,6 +64,28 @@ __global__ void __launch_bounds__(256) embed_kernel(const IdT* __restrict__ ids,
   }
   const float4* src = reinterpret_cast<const float4*>(E + id * D);
   for (int i = lane; i < D / 4; i += 32) *reinterpret_cast<float4*>(R + ptx::r32_off(row, 4 * i)) = __ldg(src + i);
+  const uint4* srcn = reinterpret_cast<const uint4*>(En + id * D);   // 256 bf16 = 32 x 16 B
+  reinterpret_cast<uint4*>(XN + row * D)[lane] = __ldg(srcn + lane);
+}
+
+// En[v,:] = bf16((E[v,:] - mean) * rsqrt(var + eps)), one warp per vocabulary row
+__global__ void embed_norm_table_kernel(const float* __restrict__ E, __nv_bfloat16* __restrict__ En, int rows, float eps) {
+  constexpr int D = 256;
+  const int v = blockIdx.x, lane = threadIdx.x;
+  if (v >= rows) return;
+  float x[8];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { x[i] = E[v * D + lane + 32 * i]; s += x[i]; }
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s / D;
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { x[i] -= mean; ss += x[i] * x[i]; }
+  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  const float rstd = rsqrtf(ss / D + eps);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) En[v * D + lane + 32 * i] = __float2bfloat16(x[i] * rstd);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -180,6 +180,7 @@ class Engine:
     def block_in(self, layer: int, res_rows: torch.Tensor, B: int, T: int):
         """Fused LN1+in_proj+short conv+gate: res_rows fp32 [B*T,256] (row-major here) -> (vx, x0) bf16 [B,256,Tp]."""
         Tp = (T + 63) // 64 * 64
+        self.reserve(B, T)
         blocked = rows_to_r32(torch.cat([res_rows, torch.zeros(160, 256, dtype=res_rows.dtype, device=res_rows.device)]))
         vx = torch.zeros(B, 256, Tp, dtype=torch.bfloat16, device=self.device)
         x0 = torch.zeros_like(vx)

@@ -114,6 +114,9 @@ int clm_gemm(clm_ctx* ctx, const void* d_A, const void* d_W, const float* d_bias
  * the blocked R32 layout (with >= 160 rows of slack after the last token); outputs vx = v*x1 and
  * x0 as channel-major bf16 [B][256][Tp], Tp % 64 == 0. */
 int clm_block_in(clm_ctx* ctx, int layer, const float* d_res, int B, int T, int Tp, void* d_vx, void* d_x0, void* stream);
+/* Same, and CTA 0 records clock64() stamps (int64 [2][64], zero-filled by the caller): tuning aid. */
+int clm_block_in_trace(clm_ctx* ctx, int layer, const float* d_res, int B, int T, int Tp, void* d_vx, void* d_x0,
+                       long long* d_trace, void* stream);
 /* Fused second half of block `layer` (out_proj + residual + LayerNorm2 + fc1 + GELU + fc2 +
  * residual; HF HyenaBlock.forward): d_y bf16 [M,256] token-major, d_res fp32
  * [M,256] read and overwritten with the block output. */
