@@ -926,7 +926,12 @@ int clm_forward(clm_ctx* c, const void* d_ids, int ids_dtype, int B, int T, floa
   }
   STOP_AFTER(NL, 11);
   { ProfScope ps_(c, PC_POOL, st);
-  pool_partial_kernel<<<dim3(c->n_split, B), 256, 0, st>>>(c->R, c->score, c->lnf_g, c->lnf_b, c->part, T, c->n_split, g.layer_norm_eps);
+  if (!tail_folded) {   // XN currently holds ln_f WITH affine (scorer input): re-emit the plain normalised rows for pooling
+    ProfScope ps2_(c, PC_LN, st);
+    layernorm_bf16_kernel<<<rows32, 256, 0, st>>>(c->R, c->ones, c->zeros, c->XN, M, g.layer_norm_eps);
+    CLM_LAUNCH_CHECK(c, "normalize_for_pool");
+  }
+  pool_partial_kernel<<<dim3(c->n_split, B), 256, 0, st>>>(c->XN, c->score, c->lnf_g, c->lnf_b, c->part, T, c->n_split);
   CLM_LAUNCH_CHECK(c, "pool_partial"); }
   STOP_AFTER(NL, 12);
   HeadParams hp = c->head;

@@ -211,12 +211,15 @@ __global__ void __launch_bounds__(256) transpose_ct_kernel(const __nv_bfloat16* 
 // Attention pooling (chimeralm/models/components/hyena.py:117-132, mask == None):
 //   w = softmax_t(score[b,:]) over ALL T positions;  pooled[b,:] = sum_t w_t * ln_f(R[b,t,:])
 // Split over the sequence: each block reduces a slice with a running max (online softmax) and
-// writes (max, sum, acc[D]); the head kernel merges slices.  ln_f is recomputed from the fp32
-// residual so the pooled features never pass through bf16.
-__global__ void __launch_bounds__(256) pool_partial_kernel(const float* __restrict__ R, const float* __restrict__ score,
+// writes (max, sum, acc[D]); the head kernel merges slices.  The rows are the bf16 normalised tokens; the
+// weighted average over thousands of tokens washes out their 2^-9 rounding.
+__global__ void __launch_bounds__(256) pool_partial_kernel(const __nv_bfloat16* __restrict__ XN, const float* __restrict__ score,
                                                            const float* __restrict__ g, const float* __restrict__ bta,
                                                            float* __restrict__ part,  // [B][S][2+D]
-                                                           int T, int n_split, float eps) {
+                                                           int T, int n_split) {
+  // XN = (r - mean) * rstd of the final residual (bf16, token-major, emitted by the last block or the LayerNorm
+  // kernel with unit affine); ln_f's gamma/beta are applied ONCE to the pooled sum: sum_t w_t (xn_t g + b) =
+  // g * sum_t w_t xn_t + b * sum_t w_t.  One warp per token row (512 contiguous bytes), 8 bf16 per lane.
   constexpr int D = 256;
   __shared__ float sm_m[8], sm_l[8];
   __shared__ float sm_acc[8][D];
@@ -224,37 +227,28 @@ __global__ void __launch_bounds__(256) pool_partial_kernel(const float* __restri
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int per = (T + n_split - 1) / n_split;
   const int tb = sp * per, te = min(T, tb + per);
-  const float4 g0 = __ldg(reinterpret_cast<const float4*>(g) + lane), g1 = __ldg(reinterpret_cast<const float4*>(g) + lane + 32);
-  const float4 b0 = __ldg(reinterpret_cast<const float4*>(bta) + lane), b1 = __ldg(reinterpret_cast<const float4*>(bta) + lane + 32);
   float m = -INFINITY, l = 0.f;
   float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll 2
   for (int t = tb + warp; t < te; t += 8) {
     const long long row = (long long)b * T + t;
-    const float4 a = *reinterpret_cast<const float4*>(R + ptx::r32_off(row, 4 * lane));
-    const float4 c = *reinterpret_cast<const float4*>(R + ptx::r32_off(row, 128 + 4 * lane));
-    float s = a.x + a.y + a.z + a.w + c.x + c.y + c.z + c.w;
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    const float mean = s * (1.0f / D);
-    float v[8] = {a.x - mean, a.y - mean, a.z - mean, a.w - mean, c.x - mean, c.y - mean, c.z - mean, c.w - mean};
-    float ss = 0.f;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) ss += v[i] * v[i];
-    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-    const float rstd = rsqrtf(ss * (1.0f / D) + eps);
-    const float sc = score[row];
+    const uint4 raw = __ldg(reinterpret_cast<const uint4*>(XN + row * D) + lane);
+    const float sc = __ldg(score + row);
+    const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
     const float mn = fmaxf(m, sc);
     const float corr = __expf(m - mn);  // exp(-inf) = 0 on the first step
     const float pw = __expf(sc - mn);
     l = l * corr + pw;
-    const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] = acc[i] * corr + pw * (v[i] * rstd * gg[i] + bb[i]);
+    for (int i = 0; i < 4; ++i) {
+      acc[2 * i] = acc[2 * i] * corr + pw * __uint_as_float(w[i] << 16);
+      acc[2 * i + 1] = acc[2 * i + 1] * corr + pw * __uint_as_float(w[i] & 0xffff0000u);
+    }
     m = mn;
   }
   if (lane == 0) { sm_m[warp] = m; sm_l[warp] = l; }
 #pragma unroll
-  for (int i = 0; i < 4; ++i) { sm_acc[warp][lane * 4 + i] = acc[i]; sm_acc[warp][128 + lane * 4 + i] = acc[4 + i]; }
+  for (int i = 0; i < 8; ++i) sm_acc[warp][lane * 8 + i] = acc[i];
   __syncthreads();
   float M = -INFINITY;
   for (int w = 0; w < 8; ++w) M = fmaxf(M, sm_m[w]);
@@ -266,7 +260,7 @@ __global__ void __launch_bounds__(256) pool_partial_kernel(const float* __restri
     a += sm_acc[w][d] * f;
     L += sm_l[w] * f;
   }
-  out[2 + d] = a;
+  out[2 + d] = a * __ldg(g + d) + L * __ldg(bta + d);   // ln_f affine applied to the (unnormalised) weighted sum
   if (d == 0) { out[0] = M; out[1] = L; }
 }
 
@@ -288,21 +282,35 @@ template <int IN, int OUT, bool GELU>
 __device__ __forceinline__ void head_linear(const float* __restrict__ W, const float* __restrict__ bias,
                                             const float* x, float* y) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-  for (int o = warp; o < OUT; o += nw) {
-    const float* wr = W + (long long)o * IN;
-    float a = 0.f;
-    for (int i = lane; i < IN; i += 32) a += __ldg(wr + i) * x[i];
-    for (int s = 16; s > 0; s >>= 1) a += __shfl_xor_sync(0xffffffffu, a, s);
-    if (lane == 0) {
-      a += bias[o];
-      y[o] = GELU ? gelu_erf_h(a) : a;
+  constexpr int R = (OUT >= 64) ? 4 : 1;   // rows per warp step: keeps 4 x IN/128 independent 16-byte loads in flight
+  for (int o0 = warp * R; o0 < OUT; o0 += nw * R) {
+    float a[R];
+#pragma unroll
+    for (int rr = 0; rr < R; ++rr) a[rr] = 0.f;
+#pragma unroll 2
+    for (int i = lane * 4; i < IN; i += 128) {
+      const float4 xv = *reinterpret_cast<const float4*>(x + i);
+#pragma unroll
+      for (int rr = 0; rr < R; ++rr) {
+        const float4 wv = __ldg(reinterpret_cast<const float4*>(W + (long long)(o0 + rr) * IN + i));
+        a[rr] += wv.x * xv.x + wv.y * xv.y + wv.z * xv.z + wv.w * xv.w;
+      }
+    }
+#pragma unroll
+    for (int rr = 0; rr < R; ++rr) {
+      float v = a[rr];
+      for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+      if (lane == 0) {
+        v += bias[o0 + rr];
+        y[o0 + rr] = GELU ? gelu_erf_h(v) : v;
+      }
     }
   }
 }
 
 __global__ void __launch_bounds__(512) head_kernel(HeadParams p) {
   constexpr int D = 256, H = 512;
-  __shared__ float pooled[D], h1[H], h2[H], h3[H];
+  __shared__ __align__(16) float pooled[D], h1[H], h2[H], h3[H];
   __shared__ float s_lg[2];
   const int b = blockIdx.x, tid = threadIdx.x;
   const float* part = p.part + (long long)b * p.n_split * (2 + D);
