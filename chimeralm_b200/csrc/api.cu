@@ -82,6 +82,7 @@ struct clm_ctx {
   float* R = nullptr;
   __nv_bfloat16 *XN = nullptr, *U = nullptr, *VX = nullptr, *X0 = nullptr, *Y = nullptr, *YT = nullptr;
   float *score = nullptr, *part = nullptr, *pooled = nullptr;
+  float* hbuf[4] = {nullptr, nullptr, nullptr, nullptr};   // head activations [max_B, 512]
   float2* scratch = nullptr;
   size_t scratch_bytes = 0;
   int* d_err = nullptr;
@@ -773,6 +774,10 @@ int clm_reserve(clm_ctx* c, int max_B, int max_T) {
   c->n_split = std::max(1, std::min(64, (2 * c->num_sms + max_B - 1) / max_B));
   if ((rc = dev_alloc(c, &c->part, (size_t)max_B * c->n_split * (2 + D)))) return rc;
   if ((rc = dev_alloc(c, &c->pooled, (size_t)max_B * D))) return rc;
+  for (int i = 0; i < 4; ++i) {
+    dev_free(c, c->hbuf[i]);
+    if ((rc = dev_alloc(c, &c->hbuf[i], (size_t)max_B * c->cfg.head_hidden))) return rc;
+  }
   c->scratch_bytes = conv_scratch_bytes(c, max_T);
   c->scratch = nullptr;
   if (c->scratch_bytes) {
@@ -934,11 +939,23 @@ int clm_forward(clm_ctx* c, const void* d_ids, int ids_dtype, int B, int T, floa
   pool_partial_kernel<<<dim3(c->n_split, B), 256, 0, st>>>(c->XN, c->score, c->lnf_g, c->lnf_b, c->part, T, c->n_split);
   CLM_LAUNCH_CHECK(c, "pool_partial"); }
   STOP_AFTER(NL, 12);
-  HeadParams hp = c->head;
-  hp.part = c->part; hp.n_split = c->n_split; hp.logits = d_logits; hp.labels = d_labels; hp.pooled_out = c->pooled;
-  { ProfScope ps_(c, PC_HEAD, st);
-  head_kernel<<<B, 512, 0, st>>>(hp);
-  CLM_LAUNCH_CHECK(c, "head"); }
+  {
+    ProfScope ps_(c, PC_HEAD, st);
+    const HeadParams& hp = c->head;
+    const int H = g.head_hidden;
+    pool_merge_kernel<<<B, 256, 0, st>>>(c->part, c->n_split, c->pooled);
+    CLM_LAUNCH_CHECK(c, "pool_merge");
+    head_layer_kernel<256, true, false, false><<<H / 8, 256, 0, st>>>(hp.w0, hp.b0, c->pooled, nullptr, c->hbuf[0], nullptr, B, H);
+    CLM_LAUNCH_CHECK(c, "head_l0");
+    head_layer_kernel<512, true, false, false><<<H / 8, 256, 0, st>>>(hp.w1, hp.b1, c->hbuf[0], nullptr, c->hbuf[1], nullptr, B, H);
+    CLM_LAUNCH_CHECK(c, "head_l1");
+    head_layer_kernel<512, true, false, false><<<H / 8, 256, 0, st>>>(hp.wr0, hp.br0, c->hbuf[1], nullptr, c->hbuf[2], nullptr, B, H);
+    CLM_LAUNCH_CHECK(c, "head_r0");
+    head_layer_kernel<512, false, true, false><<<H / 8, 256, 0, st>>>(hp.wr1, hp.br1, c->hbuf[2], c->hbuf[1], c->hbuf[3], nullptr, B, H);
+    CLM_LAUNCH_CHECK(c, "head_r1");
+    head_layer_kernel<512, false, false, true><<<1, 256, 0, st>>>(hp.wo, hp.bo, c->hbuf[3], nullptr, d_logits, d_labels, B, 2);
+    CLM_LAUNCH_CHECK(c, "head_out");
+  }
 #undef STOP_AFTER
   return 0;
 }

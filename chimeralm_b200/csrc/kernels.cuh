@@ -347,4 +347,59 @@ __global__ void __launch_bounds__(512) head_kernel(HeadParams p) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Head as a chain of small kernels in which every weight row is read ONCE for the whole batch (the one-CTA-per-read
+// head_kernel above streams all 4 MB of head weights per read; at batch 32 that is 128 MB through L2).
+__global__ void __launch_bounds__(256) pool_merge_kernel(const float* __restrict__ part, int n_split, float* __restrict__ pooled) {
+  constexpr int D = 256;
+  const int b = blockIdx.x, d = threadIdx.x;
+  const float* pp = part + (long long)b * n_split * (2 + D);
+  float M = -INFINITY;
+  for (int s = 0; s < n_split; ++s) M = fmaxf(M, pp[s * (2 + D)]);
+  float a = 0.f, L = 0.f;
+  for (int s = 0; s < n_split; ++s) {
+    const float ms = pp[s * (2 + D)];
+    const float f = (ms == -INFINITY) ? 0.f : __expf(ms - M);
+    a += pp[s * (2 + D) + 2 + d] * f;
+    L += pp[s * (2 + D) + 1] * f;
+  }
+  pooled[(long long)b * D + d] = a / L;
+}
+
+// y[b,o] = act(bias[o] + sum_i W[o,i] x[b,i]) (+ skip[b,o]); one warp per output neuron o, looping over the batch.
+// FINAL: OUT == 2 -> also writes labels (argmax, ties -> 0; chimeralm/models/callbacks.py:107).
+template <int IN, bool GELU, bool SKIP, bool FINAL>
+__global__ void __launch_bounds__(256) head_layer_kernel(const float* __restrict__ W, const float* __restrict__ bias,
+                                                         const float* __restrict__ x, const float* __restrict__ skip,
+                                                         float* __restrict__ y, uint8_t* __restrict__ labels, int B, int OUT) {
+  const int o = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (o >= OUT) return;
+  constexpr int V = IN / 128;   // float4 per lane
+  float4 w[V];
+#pragma unroll
+  for (int v = 0; v < V; ++v) w[v] = __ldg(reinterpret_cast<const float4*>(W + (long long)o * IN) + lane + 32 * v);
+  const float bo = __ldg(bias + o);
+#pragma unroll 4
+  for (int b = 0; b < B; ++b) {
+    float a = 0.f;
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+      const float4 xv = __ldg(reinterpret_cast<const float4*>(x + (long long)b * IN) + lane + 32 * v);
+      a += w[v].x * xv.x + w[v].y * xv.y + w[v].z * xv.z + w[v].w * xv.w;
+    }
+    for (int s = 16; s > 0; s >>= 1) a += __shfl_xor_sync(0xffffffffu, a, s);
+    if (lane == 0) {
+      a += bo;
+      if (GELU) a = gelu_erf_h(a);
+      if (SKIP) a += skip[(long long)b * OUT + o];
+      y[(long long)b * OUT + o] = a;
+    }
+  }
+  if (FINAL) {   // OUT == 2: both logits of a read are written by warps 0 and 1 of block 0
+    __syncthreads();
+    if (labels && o == 0)
+      for (int b = lane; b < B; b += 32) labels[b] = (y[b * 2 + 1] > y[b * 2]) ? 1 : 0;
+  }
+}
+
 }  // namespace clm
