@@ -14,6 +14,7 @@
 #include "../../include/chimeralm_b200.h"
 #include "block_in.cuh"
 #include "block_mlp.cuh"
+#include "block_mlp2.cuh"
 #include "gemm_tcgen05.cuh"
 #include "kernels.cuh"
 #include "longconv.cuh"
@@ -42,6 +43,7 @@ struct LayerW {
   // block_mlp operands, pre-tiled [N/rt][K/64][rt][64] so that every 32 KB ring slot is one TMA box
   __nv_bfloat16 *out_wt = nullptr, *fc1_wt = nullptr, *fc2_wt = nullptr;
   CUtensorMap tm_out_t, tm_fc1_t, tm_fc2_t;
+  CUtensorMap tm_out_h, tm_fc1_h, tm_fc2_h;   // same buffers, half-tile boxes for the CTA-pair kernel
   float* k = nullptr;                               // [D][Lk]
   float2* gspec[LONGCONV_MAX_LOGN + 1] = {nullptr};  // per LOGN: [n_seg][D][N]
   float2* gspecT[LONGCONV_MAX_LOGN + 1] = {nullptr}; // per LOGN: [D][16][N/16], bias folded (longconv_fast)
@@ -105,6 +107,7 @@ struct clm_ctx {
   bool fused_mlp = true;  // out_proj+res+LN2+fc1+gelu+fc2+res in one kernel
   bool fused_in = true;   // LN1+in_proj+short conv+gate in one kernel
   bool fast_conv = true;  // tuned single-chunk long convolution
+  bool mlp_2cta = false;  // CTA-pair (cta_group::2) version of the fused block tail
   bool y_channel_major = true;  // block_mlp reads the conv output channel-major (MN-major UMMA operand): no transpose
   // debug
   int dbg_layer = -1, dbg_stage = -1;
@@ -209,6 +212,18 @@ int retile(clm_ctx* c, const float* src, int N, int K, int rt, __nv_bfloat16** o
                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(c, CLM_ERR_CUDA, "cuTensorMapEncodeTiled(retiled weight) failed with CUresult %d", (int)r);
+  return 0;
+}
+
+// tensor map over an already re-tiled [rows x 64] bf16 weight buffer with a box of `box_rows` rows
+int make_tmap_retiled(clm_ctx* c, CUtensorMap* tm, const void* buf, long long rows, int box_rows) {
+  cuuint64_t dims[2] = {64, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {128};
+  cuuint32_t box[2] = {64, (cuuint32_t)box_rows}, estr[2] = {1, 1};
+  CUresult r = c->encode_tiled(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(buf), dims, strides, box, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(c, CLM_ERR_CUDA, "cuTensorMapEncodeTiled(retiled, box %d) failed with CUresult %d", box_rows, (int)r);
   return 0;
 }
 
@@ -336,6 +351,18 @@ int launch_block_mlp(clm_ctx* c, int layer, const __nv_bfloat16* y, float* res, 
   if (xn_out) {
     p.write_xn = 1;
     if ((rc = make_tmap_xn(c, &tmXN, xn_out, B > 0 ? B : 1, B > 0 ? T : M, 128))) return rc;
+  }
+  if (c->mlp_2cta && !trace) {
+    static bool attr2_set = false;
+    if (!attr2_set) {
+      CLM_CUDA(c, cudaFuncSetAttribute(block_mlp2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bm2::SMEM_TOTAL2));
+      attr2_set = true;
+    }
+    const int n_pair_tiles = (p.num_tiles + 1) / 2;
+    const int grid2 = 2 * std::min(n_pair_tiles, c->num_sms / 2);
+    block_mlp2_kernel<<<grid2, bm::THREADS, bm2::SMEM_TOTAL2, st>>>(tmY, L.tm_out_h, L.tm_fc1_h, L.tm_fc2_h, tmXN, p);
+    CLM_LAUNCH_CHECK(c, "block_mlp2");
+    return 0;
   }
   const int grid = std::min(p.num_tiles, c->num_sms);
   block_mlp_kernel<<<grid, bm::THREADS, bm::SMEM_TOTAL, st>>>(tmY, L.tm_out_t, L.tm_fc1_t, L.tm_fc2_t, tmXN, p);
@@ -666,6 +693,9 @@ int clm_finalize(clm_ctx* c) {
       if ((rc = retile(c, out_w, D, D, 256, &L.out_wt, &L.tm_out_t))) return rc;
       if ((rc = retile(c, w1f, g.d_inner, D, 128, &L.fc1_wt, &L.tm_fc1_t))) return rc;
       if ((rc = retile(c, fc2_w, D, g.d_inner, 256, &L.fc2_wt, &L.tm_fc2_t))) return rc;
+      if ((rc = make_tmap_retiled(c, &L.tm_out_h, L.out_wt, (long long)D * D / 64, 128))) return rc;
+      if ((rc = make_tmap_retiled(c, &L.tm_fc1_h, L.fc1_wt, (long long)g.d_inner * D / 64, 64))) return rc;
+      if ((rc = make_tmap_retiled(c, &L.tm_fc2_h, L.fc2_wt, (long long)g.d_inner * D / 64, 128))) return rc;
       static bm::LayerConsts hc;
       CLM_CUDA(c, cudaMemcpy(hc.b_out, L.out_b, sizeof hc.b_out, cudaMemcpyDeviceToHost));
       CLM_CUDA(c, cudaMemcpy(hc.b2, L.fc2_b, sizeof hc.b2, cudaMemcpyDeviceToHost));
@@ -1004,6 +1034,7 @@ int clm_set_option(clm_ctx* c, const char* name, int value) {
   else if (n == "fused_in") c->fused_in = value != 0;
   else if (n == "fast_conv") c->fast_conv = value != 0;
   else if (n == "y_channel_major") c->y_channel_major = value != 0;
+  else if (n == "mlp_2cta") c->mlp_2cta = value != 0;
   else return fail(c, CLM_ERR_INVALID, "clm_set_option: unknown option '%s'", name);
   return 0;
 }
