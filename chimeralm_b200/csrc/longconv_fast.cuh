@@ -144,7 +144,9 @@ struct FastCfg {
   static constexpr int THREADS = ConvCfg<LOGN>::THREADS;
   static constexpr int OFF_TA = fft::padded_size(N) * 8;
   static constexpr int OFF_TB = OFF_TA + f2::TA * 8;
-  static constexpr int OFF_STG = (OFF_TB + f2::TB * 8 + 15) / 16 * 16;   // bf16 staging of the NEXT item's vx rows: [2][C]
+  // leading-pass twiddles W_N^j, j < N/R0 <= 4096, as W_N^(64 a) * W_N^b (two 64-entry tables, one complex multiply)
+  static constexpr int OFF_TC = OFF_TB + f2::TB * 8;
+  static constexpr int OFF_STG = (OFF_TC + 2 * 64 * 8 + 15) / 16 * 16;   // bf16 staging of the NEXT item's vx rows: [2][C]
   static constexpr int SMEM = OFF_STG + 2 * C * 2;
 };
 
@@ -210,6 +212,16 @@ __global__ void __launch_bounds__(FastCfg<LOGN>::THREADS, 1) longconv_fast_kerne
     sincospif((float)((e & 15) * ((e >> 4) + 1)) / 128.0f, &sn, &cs);     // 2*pi*(j q)/256
     tB[e] = make_float2(cs, -sn);
   }
+  float2* tC = reinterpret_cast<float2*>(smem_f + F::OFF_TC);   // [0,64): W_N^(64 a);  [64,128): W_N^b
+  for (int e = tid; e < 128; e += TH) {
+    float sn, cs;
+    const int k = (e < 64) ? 64 * e : (e - 64);
+    sincospif(2.0f * (float)k / (float)N, &sn, &cs);
+    tC[e] = make_float2(cs, -sn);
+  }
+  auto lead_twiddle = [&](int j) -> float2 {   // W_N^j for j < 4096
+    return fft::cmul(tC[j >> 6], tC[64 + (j & 63)]);
+  };
   __nv_bfloat16* stg = reinterpret_cast<__nv_bfloat16*>(smem_f + F::OFF_STG);
   // asynchronous copy of one item's vx rows (both reads, first min(C, Tp) tokens) into the staging buffer
   auto stage_item = [&](int it_) {
@@ -278,9 +290,7 @@ __global__ void __launch_bounds__(FastCfg<LOGN>::THREADS, 1) longconv_fast_kerne
           cx x[R0];
 #pragma unroll
           for (int r = 0; r < R0; ++r) x[r] = (r < HALF) ? f2::mk(xa[r < HALF ? r : 0][u], xb[r < HALF ? r : 0][u]) : f2::mk(0.f, 0.f);
-          float sn, cs;
-          sincospif(2.0f * (float)(j + u) / (float)N, &sn, &cs);
-          const float2 w1 = make_float2(cs, -sn);
+          const float2 w1 = lead_twiddle(j + u);
           if constexpr (R0 == 2) {
             const cx a = x[0];   // x[1] == 0
             x[1] = f2::cmul(a, w1);
@@ -341,6 +351,22 @@ __global__ void __launch_bounds__(FastCfg<LOGN>::THREADS, 1) longconv_fast_kerne
       }
     }
     __syncthreads();
+    // x0 for the output pass is fetched now (L2-prefetched rows) so its latency hides behind the inverse passes
+    constexpr int ZITER = (S0 / 2 + TH - 1) / TH;
+    uint32_t gxa[ZITER][HALF], gxb[ZITER][HALF];
+#pragma unroll
+    for (int zi = 0; zi < ZITER; ++zi) {
+      const int j = 2 * (tid + zi * TH);
+#pragma unroll
+      for (int r = 0; r < HALF; ++r) {
+        const int t = j + r * S0;
+        gxa[zi][r] = gxb[zi][r] = 0;
+        if (j < S0 && t < t_fft) {
+          gxa[zi][r] = __ldg(reinterpret_cast<const unsigned int*>(p.x0 + off0 + t));
+          if (has_b1) gxb[zi][r] = __ldg(reinterpret_cast<const unsigned int*>(p.x0 + off1 + t));
+        }
+      }
+    }
     // ---- inverse radix-16 passes back up
     f2::pass16<N, 256, true, TH>(z, tA, tB, tid);
     __syncthreads();
@@ -351,25 +377,15 @@ __global__ void __launch_bounds__(FastCfg<LOGN>::THREADS, 1) longconv_fast_kerne
     // ---- phase Z: last inverse radix-R0 pass fused with the output (only r >= R0/2 survive overlap-save)
     {
       constexpr int PAIRS = S0 / 2;
-#pragma unroll 2
-      for (int i = tid; i < PAIRS; i += TH) {
-        const int j = 2 * i;
-        uint32_t gxa[HALF], gxb[HALF];
 #pragma unroll
-        for (int r = 0; r < HALF; ++r) {
-          const int t = j + r * S0;
-          gxa[r] = gxb[r] = 0;
-          if (t < t_fft) {
-            gxa[r] = *reinterpret_cast<const uint32_t*>(p.x0 + off0 + t);
-            if (has_b1) gxb[r] = *reinterpret_cast<const uint32_t*>(p.x0 + off1 + t);
-          }
-        }
+      for (int zi = 0; zi < ZITER; ++zi) {
+        const int i = tid + zi * TH;
+        if (i >= PAIRS) break;
+        const int j = 2 * i;
         float oa[HALF][2], ob[HALF][2];
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
-          float sn, cs;
-          sincospif(2.0f * (float)(j + u) / (float)N, &sn, &cs);
-          const float2 w1 = make_float2(cs, -sn);
+          const float2 w1 = lead_twiddle(j + u);
           cx y[R0];
 #pragma unroll
           for (int q = 0; q < R0; ++q) y[q] = z[fft::pad_idx(j + u + q * S0)];
@@ -403,8 +419,8 @@ __global__ void __launch_bounds__(FastCfg<LOGN>::THREADS, 1) longconv_fast_kerne
           for (int r = 0; r < HALF; ++r) {
             float ya, yb;
             f2::un(xo[r], ya, yb);
-            const float xa_ = u ? __uint_as_float(gxa[r] & 0xffff0000u) : __uint_as_float(gxa[r] << 16);
-            const float xb_ = u ? __uint_as_float(gxb[r] & 0xffff0000u) : __uint_as_float(gxb[r] << 16);
+            const float xa_ = u ? __uint_as_float(gxa[zi][r] & 0xffff0000u) : __uint_as_float(gxa[zi][r] << 16);
+            const float xb_ = u ? __uint_as_float(gxb[zi][r] & 0xffff0000u) : __uint_as_float(gxb[zi][r] << 16);
             oa[r][u] = ya * xa_;
             ob[r][u] = yb * xb_;
           }
