@@ -258,18 +258,34 @@ def main():
     dom_name, (dom_ms, dom_n) = dom
     total_prof_ms = sum(v[0] for v in prof.values())
     per_launch_s = dom_ms / dom_n / 1e3
+    # algorithmic work per token per launch
     flop_per_tok = {"gemm_in_proj": 2 * 256 * 768, "gemm_out_proj": 2 * 256 * 256, "gemm_fc1": 2 * 256 * 1024,
-                    "gemm_fc2": 2 * 1024 * 256, "gemm_score": 2 * 256 * 256 + 2 * 256}
-    if dom_name in flop_per_tok:
-        ach = flop_per_tok[dom_name] * tokens_per_step / per_launch_s / 1e12
-        roof = {"bound": "tensor", "achieved": ach, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": ach / pk["tflops"]}
-    else:
-        bytes_per_tok = {"longconv": CONV_BYTES_TOK_LAYER, "layernorm": 1024 + 512, "shortconv_gate": 1536 + 1024,
-                         "transpose": 1024, "pool": 1028, "embed": 1025, "encode": 2, "head": 0}.get(dom_name, 0)
-        ach = bytes_per_tok * tokens_per_step / per_launch_s / 1e9
-        roof = {"bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"]}
-    roof.update({"kernel": dom_name, "traffic": None, "peak_source": pk["src"], "avg_launch_ms": dom_ms / dom_n,
-                 "share_of_step": dom_ms / total_prof_ms})
+                    "gemm_fc2": 2 * 1024 * 256, "gemm_score": 2 * 256 * 256 + 2 * 256,
+                    "block_in": 2 * 256 * 768, "block_mlp": 2 * 256 * 256 + 2 * 256 * 1024 + 2 * 1024 * 256}
+    bytes_per_tok = {"longconv": CONV_BYTES_TOK_LAYER, "layernorm": 1024 + 512, "shortconv_gate": 1536 + 1024,
+                     "transpose": 1024, "pool": 516, "embed": 1 + 1024 + 512, "encode": 2, "head": 0}
+    traffic = {}
+    tp = ROOT / "profiles" / "r1_traffic.json"
+    if tp.exists() and B == BATCH and L == READ_LEN:
+        traffic = {k: v for k, v in json.loads(tp.read_text()).items() if not k.startswith("_")}
+
+    def roofline_of(name, ms, n):
+        sec = ms / n / 1e3
+        if name in flop_per_tok:
+            ach = flop_per_tok[name] * tokens_per_step / sec / 1e12
+            r = {"bound": "tensor", "achieved": ach, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": ach / pk["tflops"]}
+        else:
+            ach = bytes_per_tok.get(name, 0) * tokens_per_step / sec / 1e9
+            r = {"bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"]}
+        r.update({"kernel": name, "traffic": traffic.get(name), "avg_launch_ms": ms / n, "share_of_step": ms / total_prof_ms})
+        return r
+
+    roof = roofline_of(dom_name, dom_ms, dom_n)
+    roof["peak_source"] = pk["src"]
+    if dom_name == "longconv":
+        roof["note"] = ("HBM roofline per SURVEY 8(d)'s compulsory-traffic model (1536 B/token/layer); the kernel itself is bound by "
+                        "fp32 FFT instruction issue (ncu: issue-active ~50%, DRAM ~9%), see profiles/r1_v6_longconv_fast.txt")
+    rooflines = {k: roofline_of(k, v[0], v[1]) for k, v in prof.items() if k in ("longconv", "block_mlp", "block_in", "gemm_score")}
     dense_frac = F_TOK * (reads_per_s / world) * T / 1e12 / pk["tflops"]
 
     cpu = None
@@ -293,6 +309,7 @@ def main():
                 "d2h_bytes_per_step": B * 2 * 4 + B, "api": "clm_predict_host (C-ABI, pinned host buffers)"},
         "gpu_launches": int(launches),
         "roofline": roof,
+        "rooflines_top_kernels": rooflines,
         "kernel_ms_per_step": {k: v[0] / args.steps for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])},
         "cpu_baseline": cpu,
         "clocks": clocks,
