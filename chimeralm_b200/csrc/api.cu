@@ -472,6 +472,8 @@ int launch_longconv(clm_ctx* c, int layer, const __nv_bfloat16* vx, const __nv_b
     if (pl.logn >= 13) grid = std::min(grid, c->num_sms);
     else grid = std::min(grid, c->num_sms * 4);
     switch (pl.logn) {
+      case 8: return conv_fast_t<8>(c, f, grid, st);
+      case 12: return conv_fast_t<12>(c, f, grid, st);
       case 9: return conv_fast_t<9>(c, f, grid, st);
       case 10: return conv_fast_t<10>(c, f, grid, st);
       case 11: return conv_fast_t<11>(c, f, grid, st);
@@ -731,6 +733,8 @@ int clm_finalize(clm_ctx* c) {
     if ((rc = spectrum_t<12>(c, L))) return rc;
     if ((rc = spectrum_t<13>(c, L))) return rc;
     if ((rc = spectrum_t<14>(c, L))) return rc;
+    if ((rc = spectrum_fast_t<8>(c, L))) return rc;
+    if ((rc = spectrum_fast_t<12>(c, L))) return rc;
     if ((rc = spectrum_fast_t<9>(c, L))) return rc;
     if ((rc = spectrum_fast_t<10>(c, L))) return rc;
     if ((rc = spectrum_fast_t<11>(c, L))) return rc;

@@ -139,8 +139,8 @@ __device__ __forceinline__ void pass16(cx* z, const float2* tA, const float2* tB
 template <int LOGN>
 struct FastCfg {
   static constexpr int N = 1 << LOGN, C = N / 2;
-  static constexpr int R0 = 1 << (LOGN % 4);
-  static constexpr bool kSupported = (R0 > 1) && (LOGN >= 9);
+  static constexpr int R0 = (LOGN % 4) ? (1 << (LOGN % 4)) : 16;   // leading radix 2/4/8, or 16 when logN is a multiple of 4
+  static constexpr bool kSupported = (LOGN >= 8) && (LOGN <= 14);
   static constexpr int THREADS = ConvCfg<LOGN>::THREADS;
   static constexpr int OFF_TA = fft::padded_size(N) * 8;
   static constexpr int OFF_TB = OFF_TA + f2::TA * 8;
@@ -195,7 +195,7 @@ __global__ void __launch_bounds__(FastCfg<LOGN>::THREADS, 1) longconv_fast_kerne
   using F = FastCfg<LOGN>;
   using f2::cx;
   constexpr int N = F::N, C = F::C, TH = F::THREADS, R0 = F::R0, S0 = N / R0, HALF = R0 / 2;
-  static_assert(F::kSupported, "longconv_fast_kernel needs a leading radix-2/4/8 pass");
+  static_assert(F::kSupported, "longconv_fast_kernel supports 256 <= N <= 16384");
   extern __shared__ __align__(16) uint8_t smem_f[];
   cx* z = reinterpret_cast<cx*>(smem_f);
   float2* tA = reinterpret_cast<float2*>(smem_f + F::OFF_TA);
@@ -302,6 +302,10 @@ __global__ void __launch_bounds__(FastCfg<LOGN>::THREADS, 1) longconv_fast_kerne
             x[1] = f2::cmul(f2::cadd(a, ib), w1);
             x[2] = f2::cmul(f2::csub(a, b), w2);
             x[3] = f2::cmul(f2::csub(a, ib), w3);
+          } else if constexpr (R0 == 16) {  // DFT16 on (x0..x7, 0 x 8); twiddles W_N^(j q) straight from the tables
+            f2::dft16<false>(x);
+#pragma unroll
+            for (int q = 1; q < 16; ++q) x[q] = f2::cmul(x[q], f2::tw_lookup<N>(tA, tB, j + u, q));
           } else {  // R0 == 8: generic DFT8 on (x0..x3, 0, 0, 0, 0)
             float2 xf[8];
 #pragma unroll
@@ -328,8 +332,10 @@ __global__ void __launch_bounds__(FastCfg<LOGN>::THREADS, 1) longconv_fast_kerne
       f2::pass16<N, 4096, false, TH>(z, tA, tB, tid);
       __syncthreads();
     }
-    f2::pass16<N, 256, false, TH>(z, tA, tB, tid);
-    __syncthreads();
+    if constexpr (S0 >= 256) {
+      f2::pass16<N, 256, false, TH>(z, tA, tB, tid);
+      __syncthreads();
+    }
     // ---- phase M: last forward radix-16 (blocks of 16) * spectrum * first inverse radix-16
     {
       const float2* g = p.gT + (long long)c * N;
@@ -368,8 +374,10 @@ __global__ void __launch_bounds__(FastCfg<LOGN>::THREADS, 1) longconv_fast_kerne
       }
     }
     // ---- inverse radix-16 passes back up
-    f2::pass16<N, 256, true, TH>(z, tA, tB, tid);
-    __syncthreads();
+    if constexpr (S0 >= 256) {
+      f2::pass16<N, 256, true, TH>(z, tA, tB, tid);
+      __syncthreads();
+    }
     if constexpr (S0 >= 4096) {
       f2::pass16<N, 4096, true, TH>(z, tA, tB, tid);
       __syncthreads();
@@ -400,6 +408,12 @@ __global__ void __launch_bounds__(FastCfg<LOGN>::THREADS, 1) longconv_fast_kerne
             const cx s13 = f2::cadd(y1, y3), d13 = f2::mul_mi<true>(f2::csub(y1, y3));   // i (Y1 - Y3)
             xo[0] = f2::csub(s02, s13);
             xo[1] = f2::csub(d02, d13);
+          } else if constexpr (R0 == 16) {
+#pragma unroll
+            for (int q = 1; q < 16; ++q) y[q] = f2::cmulc(y[q], f2::tw_lookup<N>(tA, tB, j + u, q));
+            f2::dft16<true>(y);
+#pragma unroll
+            for (int r = 0; r < HALF; ++r) xo[r] = y[HALF + r];
           } else {
             float2 yf[8];
             float2 w = w1;
