@@ -410,11 +410,12 @@ int spectrum_fast_t(clm_ctx* c, LayerW& L) {
   if constexpr (FastCfg<LOGN>::kSupported) {
     using Cfg = ConvCfg<LOGN>;
     const int D = c->cfg.d_model;
-    int rc = dev_alloc(c, &L.gspecT[LOGN], (size_t)D * Cfg::N);
+    const int nseg = n_segments(c, LOGN);
+    int rc = dev_alloc(c, &L.gspecT[LOGN], (size_t)nseg * D * Cfg::N);
     if (rc) return rc;
     auto kern = filter_spectrum_fast_kernel<LOGN>;
     CLM_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
-    kern<<<D, Cfg::THREADS, Cfg::SMEM>>>(L.k, c->Lk, c->cfg.max_seq_len, L.fbias, L.gspecT[LOGN], D);
+    kern<<<dim3(D, nseg), Cfg::THREADS, Cfg::SMEM>>>(L.k, c->Lk, c->cfg.max_seq_len, L.fbias, L.gspecT[LOGN], D);
     CLM_LAUNCH_CHECK(c, "filter_spectrum_fast");
   }
   return 0;
@@ -463,14 +464,19 @@ int launch_longconv(clm_ctx* c, int layer, const __nv_bfloat16* vx, const __nv_b
   if (T > c->cfg.max_seq_len) return fail(c, CLM_ERR_INVALID, "longconv: T=%d exceeds max_seq_len=%d", T, c->cfg.max_seq_len);
   const ConvPlan pl = plan_conv(T);
   LayerW& L = c->layers[layer];
-  if (c->fast_conv && pl.n_chunks == 1 && L.gspecT[pl.logn] != nullptr) {
+  if (c->fast_conv && L.gspecT[pl.logn] != nullptr) {
     LongConvFastParams f{};
     f.vx = vx; f.x0 = x0; f.out = out; f.gT = L.gspecT[pl.logn]; f.k = L.k; f.dbias = L.fbias; f.Lk = c->Lk;
     f.B = B; f.D = c->cfg.d_model; f.T = T; f.Tp = Tp;
+    f.n_chunks = pl.n_chunks; f.scratch = scratch;
     f.n_items = c->cfg.d_model * ((B + 1) / 2);
     int grid = f.n_items;
     if (pl.logn >= 13) grid = std::min(grid, c->num_sms);
     else grid = std::min(grid, c->num_sms * 4);
+    if (pl.n_chunks > 1) {
+      const size_t needb = (size_t)grid * pl.n_chunks * ((size_t)1 << pl.logn) * sizeof(float2);
+      if (needb > scratch_bytes) return fail(c, CLM_ERR_STATE, "longconv: scratch too small (%zu < %zu); call clm_reserve with max_T >= %d", scratch_bytes, needb, T);
+    }
     switch (pl.logn) {
       case 8: return conv_fast_t<8>(c, f, grid, st);
       case 12: return conv_fast_t<12>(c, f, grid, st);
@@ -979,15 +985,15 @@ int clm_forward(clm_ctx* c, const void* d_ids, int ids_dtype, int B, int T, floa
     const int H = g.head_hidden;
     pool_merge_kernel<<<B, 256, 0, st>>>(c->part, c->n_split, c->pooled);
     CLM_LAUNCH_CHECK(c, "pool_merge");
-    head_layer_kernel<256, true, false, false><<<H / 8, 256, 0, st>>>(hp.w0, hp.b0, c->pooled, nullptr, c->hbuf[0], nullptr, B, H);
+    head_layer_kernel<256, true, false, false><<<dim3(H / 8, (B + 31) / 32), 256, 0, st>>>(hp.w0, hp.b0, c->pooled, nullptr, c->hbuf[0], nullptr, B, H);
     CLM_LAUNCH_CHECK(c, "head_l0");
-    head_layer_kernel<512, true, false, false><<<H / 8, 256, 0, st>>>(hp.w1, hp.b1, c->hbuf[0], nullptr, c->hbuf[1], nullptr, B, H);
+    head_layer_kernel<512, true, false, false><<<dim3(H / 8, (B + 31) / 32), 256, 0, st>>>(hp.w1, hp.b1, c->hbuf[0], nullptr, c->hbuf[1], nullptr, B, H);
     CLM_LAUNCH_CHECK(c, "head_l1");
-    head_layer_kernel<512, true, false, false><<<H / 8, 256, 0, st>>>(hp.wr0, hp.br0, c->hbuf[1], nullptr, c->hbuf[2], nullptr, B, H);
+    head_layer_kernel<512, true, false, false><<<dim3(H / 8, (B + 31) / 32), 256, 0, st>>>(hp.wr0, hp.br0, c->hbuf[1], nullptr, c->hbuf[2], nullptr, B, H);
     CLM_LAUNCH_CHECK(c, "head_r0");
-    head_layer_kernel<512, false, true, false><<<H / 8, 256, 0, st>>>(hp.wr1, hp.br1, c->hbuf[2], c->hbuf[1], c->hbuf[3], nullptr, B, H);
+    head_layer_kernel<512, false, true, false><<<dim3(H / 8, (B + 31) / 32), 256, 0, st>>>(hp.wr1, hp.br1, c->hbuf[2], c->hbuf[1], c->hbuf[3], nullptr, B, H);
     CLM_LAUNCH_CHECK(c, "head_r1");
-    head_layer_kernel<512, false, false, true><<<1, 256, 0, st>>>(hp.wo, hp.bo, c->hbuf[3], nullptr, d_logits, d_labels, B, 2);
+    head_layer_kernel<512, false, false, true><<<dim3(1, (B + 31) / 32), 256, 0, st>>>(hp.wo, hp.bo, c->hbuf[3], nullptr, d_logits, d_labels, B, 2);
     CLM_LAUNCH_CHECK(c, "head_out");
   }
 #undef STOP_AFTER

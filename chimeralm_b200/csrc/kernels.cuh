@@ -379,8 +379,9 @@ __global__ void __launch_bounds__(256) head_layer_kernel(const float* __restrict
 #pragma unroll
   for (int v = 0; v < V; ++v) w[v] = __ldg(reinterpret_cast<const float4*>(W + (long long)o * IN) + lane + 32 * v);
   const float bo = __ldg(bias + o);
+  const int b_lo = blockIdx.y * 32, b_hi = min(B, b_lo + 32);   // grid.y tiles the batch
 #pragma unroll 4
-  for (int b = 0; b < B; ++b) {
+  for (int b = b_lo; b < b_hi; ++b) {
     float a = 0.f;
 #pragma unroll
     for (int v = 0; v < V; ++v) {
@@ -398,7 +399,7 @@ __global__ void __launch_bounds__(256) head_layer_kernel(const float* __restrict
   if (FINAL) {   // OUT == 2: both logits of a read are written by warps 0 and 1 of block 0
     __syncthreads();
     if (labels && o == 0)
-      for (int b = lane; b < B; b += 32) labels[b] = (y[b * 2 + 1] > y[b * 2]) ? 1 : 0;
+      for (int b = b_lo + lane; b < b_hi; b += 32) labels[b] = (y[b * 2 + 1] > y[b * 2]) ? 1 : 0;
   }
 }
 

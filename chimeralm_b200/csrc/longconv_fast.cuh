@@ -150,7 +150,8 @@ struct FastCfg {
   static constexpr int SMEM = OFF_STG + 2 * C * 2;
 };
 
-// Spectrum in the layout the fused middle pass wants: gT[c][q][b] = G_c[16 b + q], b < N/16.
+// Spectra in the layout the fused middle pass wants: gT[m][c][q][b] = G_{m,c}[16 b + q], b < N/16, for filter
+// segment m (g_m[p] = k[mC + p - C], longconv.cuh); the bias skip is folded into segment 0.
 template <int LOGN>
 __global__ void __launch_bounds__(ConvCfg<LOGN>::THREADS) filter_spectrum_fast_kernel(const float* __restrict__ k,
                                                                                        long long Lk, int L,
@@ -159,17 +160,17 @@ __global__ void __launch_bounds__(ConvCfg<LOGN>::THREADS) filter_spectrum_fast_k
   using Cfg = ConvCfg<LOGN>;
   constexpr int N = Cfg::N, C = Cfg::C, TH = Cfg::THREADS;
   extern __shared__ float2 zs[];
-  const int c = blockIdx.x, tid = threadIdx.x;
+  const int c = blockIdx.x, m = blockIdx.y, tid = threadIdx.x;   // m = filter segment (overlap-save chunk lag)
   const float* kc = k + (long long)c * Lk;
   for (int pidx = tid; pidx < N; pidx += TH) {
-    const int s = pidx - C;
-    float v = (s >= 0 && s < L) ? kc[s] : 0.f;
+    const long long s = (long long)m * C + pidx - C;
+    float v = (pidx >= 1 && s >= 0 && s < L) ? kc[s] : 0.f;
     if (s == 0) v += dbias[c];  // bias skip y += bias*vx  ==  k'[0] = k[0] + bias
     zs[fft::pad_idx(pidx)] = make_float2(v, 0.f);
   }
   __syncthreads();
   fft::fft_forward<LOGN, TH>(zs, tid);
-  float2* out = gT + (long long)c * N;
+  float2* out = gT + ((long long)m * D + c) * N;
   const float sc = 1.0f / (float)N;
   for (int i = tid; i < N; i += TH) {
     const float2 v = zs[fft::pad_idx(i)];
@@ -181,7 +182,9 @@ struct LongConvFastParams {
   const __nv_bfloat16* vx;
   const __nv_bfloat16* x0;
   __nv_bfloat16* out;
-  const float2* gT;     // [D][16][N/16]
+  const float2* gT;     // [n_seg][D][16][N/16]
+  float2* scratch;      // [gridDim.x][n_chunks][N] chunk spectra (n_chunks > 1 only)
+  int n_chunks;         // overlap-save chunks of C = N/2 tokens; outputs [0, n_chunks*C) come from the FFT path
   const float* k;       // [D][Lk]   (ragged end)
   const float* dbias;   // [D]       (ragged end)
   long long Lk;
@@ -224,10 +227,10 @@ __global__ void __launch_bounds__(FastCfg<LOGN>::THREADS, 1) longconv_fast_kerne
   };
   __nv_bfloat16* stg = reinterpret_cast<__nv_bfloat16*>(smem_f + F::OFF_STG);
   // asynchronous copy of one item's vx rows (both reads, first min(C, Tp) tokens) into the staging buffer
-  auto stage_item = [&](int it_) {
+  auto stage_item = [&](int it_, int ch_) {
     const int c_ = it_ / ((p.B + 1) / 2), b_ = (it_ % ((p.B + 1) / 2)) * 2;
-    const long long o0 = ((long long)b_ * p.D + c_) * p.Tp;
-    const int ncopy = min(C, p.Tp) / 8;   // 16-byte pieces per read
+    const long long o0 = ((long long)b_ * p.D + c_) * p.Tp + (long long)ch_ * C;
+    const int ncopy = max(0, min(C, p.Tp - ch_ * C)) / 8;   // 16-byte pieces per read
     const int nseq = (b_ + 1 < p.B) ? 2 : 1;
     for (int i = tid; i < nseq * ncopy; i += TH) {
       const int sq = i / ncopy, pc = i % ncopy;
@@ -237,10 +240,10 @@ __global__ void __launch_bounds__(FastCfg<LOGN>::THREADS, 1) longconv_fast_kerne
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
-  if ((int)blockIdx.x < p.n_items) stage_item(blockIdx.x);
+  if ((int)blockIdx.x < p.n_items) stage_item(blockIdx.x, 0);
   asm volatile("cp.async.wait_group 0;" ::: "memory");
   const int n_pairs = (p.B + 1) / 2;
-  const int t_fft = min(C, p.T);
+  const int t_fft = min(p.n_chunks * C, p.T);
   __syncthreads();
 
   for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
@@ -251,14 +254,20 @@ __global__ void __launch_bounds__(FastCfg<LOGN>::THREADS, 1) longconv_fast_kerne
     const long long off1 = has_b1 ? off0 + (long long)p.D * p.Tp : off0;
     const __nv_bfloat16* va = p.vx + off0;
     const __nv_bfloat16* vb = p.vx + off1;
-    // ---- L2 prefetch of the next item's x0 rows
+    for (int ch = 0; ch < p.n_chunks; ++ch) {
+    const int tbase = ch * C;
+    // the unit (item, chunk) processed after this one
+    const bool last_chunk = (ch + 1 == p.n_chunks);
+    const int n_item = last_chunk ? item + (int)gridDim.x : item;
+    const int n_ch = last_chunk ? 0 : ch + 1;
+    // ---- L2 prefetch of the next unit's x0 rows
     {
-      const int nitem = item + gridDim.x;
+      const int nitem = n_item;
       if (nitem < p.n_items) {
         const int nc = nitem / n_pairs, nb0 = (nitem % n_pairs) * 2;
-        const long long no0 = ((long long)nb0 * p.D + nc) * p.Tp;
+        const long long no0 = ((long long)nb0 * p.D + nc) * p.Tp + (long long)n_ch * C;
         const long long no1 = (nb0 + 1 < p.B) ? no0 + (long long)p.D * p.Tp : no0;
-        const int lines = (min(p.T, C) * 2 + 127) / 128;
+        const int lines = (max(0, min(p.T - n_ch * C, C)) * 2 + 127) / 128;
         for (int l = tid; l < 2 * lines; l += TH) {     // x0 rows only: vx is staged through shared memory
           const int which = l / lines, ln = l % lines;
           prefetch_l2(p.x0 + (which ? no1 : no0) + ln * 64);
@@ -276,14 +285,14 @@ __global__ void __launch_bounds__(FastCfg<LOGN>::THREADS, 1) longconv_fast_kerne
         for (int r = 0; r < HALF; ++r) {
           const int t = j + r * S0;
           uint32_t wa = 0, wb = 0;
-          if (t < p.T) {  // t even: the pair (t, t+1) was staged (t + 1 < min(C, Tp))
+          if (tbase + t < p.T) {  // t even: the pair (t, t+1) was staged (tbase + t + 1 < Tp)
             wa = *reinterpret_cast<const uint32_t*>(stg + t);
             if (has_b1) wb = *reinterpret_cast<const uint32_t*>(stg + C + t);
           }
           xa[r][0] = __uint_as_float(wa << 16);
-          xa[r][1] = (t + 1 < p.T) ? __uint_as_float(wa & 0xffff0000u) : 0.f;
+          xa[r][1] = (tbase + t + 1 < p.T) ? __uint_as_float(wa & 0xffff0000u) : 0.f;
           xb[r][0] = __uint_as_float(wb << 16);
-          xb[r][1] = (t + 1 < p.T) ? __uint_as_float(wb & 0xffff0000u) : 0.f;
+          xb[r][1] = (tbase + t + 1 < p.T) ? __uint_as_float(wb & 0xffff0000u) : 0.f;
         }
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
@@ -326,7 +335,7 @@ __global__ void __launch_bounds__(FastCfg<LOGN>::THREADS, 1) longconv_fast_kerne
       }
     }
     __syncthreads();
-    if (item + (int)gridDim.x < p.n_items) stage_item(item + gridDim.x);   // overlaps the whole transform
+    if (n_item < p.n_items) stage_item(n_item, n_ch);   // overlaps the whole transform
     // ---- forward radix-16 passes down to blocks of 256
     if constexpr (S0 >= 4096) {
       f2::pass16<N, 4096, false, TH>(z, tA, tB, tid);
@@ -337,7 +346,7 @@ __global__ void __launch_bounds__(FastCfg<LOGN>::THREADS, 1) longconv_fast_kerne
       __syncthreads();
     }
     // ---- phase M: last forward radix-16 (blocks of 16) * spectrum * first inverse radix-16
-    {
+    if (p.n_chunks == 1) {
       const float2* g = p.gT + (long long)c * N;
 #pragma unroll 1
       for (int bfly = tid; bfly < N / 16; bfly += TH) {
@@ -355,6 +364,47 @@ __global__ void __launch_bounds__(FastCfg<LOGN>::THREADS, 1) longconv_fast_kerne
 #pragma unroll
         for (int r = 0; r < 16; ++r) z[base + r] = x[r];
       }
+    } else {
+      // overlap-save: Y_ch = sum_{j <= ch} U_j . G_{ch-j}; earlier chunks' spectra U_j are parked in this CTA's scratch
+      // (L2-resident) in the same [q][butterfly] layout, so every load is coalesced
+      const float2* g = p.gT + (long long)c * N;
+      const long long gseg = (long long)p.D * N;
+      cx* sc = reinterpret_cast<cx*>(p.scratch) + (long long)blockIdx.x * p.n_chunks * N;
+#pragma unroll 1
+      for (int bfly = tid; bfly < N / 16; bfly += TH) {
+        cx x[16];
+        const int base = fft::pad_idx(bfly * 16);
+#pragma unroll
+        for (int r = 0; r < 16; ++r) x[r] = z[base + r];
+        f2::dft16<false>(x);
+        if (!last_chunk) {
+#pragma unroll
+          for (int q = 0; q < 16; ++q) sc[((long long)ch * 16 + q) * (N / 16) + bfly] = x[q];
+        }
+        float2 acc[16];
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+          float xr, xi;
+          f2::un(x[q], xr, xi);
+          acc[q] = fft::cmul(make_float2(xr, xi), __ldg(g + q * (N / 16) + bfly));
+        }
+        for (int j = 0; j < ch; ++j) {
+          const float2* gj = g + (long long)(ch - j) * gseg;
+#pragma unroll
+          for (int q = 0; q < 16; ++q) {
+            float ur, ui;
+            f2::un(sc[((long long)j * 16 + q) * (N / 16) + bfly], ur, ui);
+            const float2 gv = __ldg(gj + q * (N / 16) + bfly);
+            acc[q].x += ur * gv.x - ui * gv.y;
+            acc[q].y += ur * gv.y + ui * gv.x;
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < 16; ++q) x[q] = f2::mk(acc[q].x, acc[q].y);
+        f2::dft16<true>(x);
+#pragma unroll
+        for (int r = 0; r < 16; ++r) z[base + r] = x[r];
+      }
     }
     __syncthreads();
     // x0 for the output pass is fetched now (L2-prefetched rows) so its latency hides behind the inverse passes
@@ -367,9 +417,9 @@ __global__ void __launch_bounds__(FastCfg<LOGN>::THREADS, 1) longconv_fast_kerne
       for (int r = 0; r < HALF; ++r) {
         const int t = j + r * S0;
         gxa[zi][r] = gxb[zi][r] = 0;
-        if (j < S0 && t < t_fft) {
-          gxa[zi][r] = __ldg(reinterpret_cast<const unsigned int*>(p.x0 + off0 + t));
-          if (has_b1) gxb[zi][r] = __ldg(reinterpret_cast<const unsigned int*>(p.x0 + off1 + t));
+        if (j < S0 && tbase + t < t_fft) {
+          gxa[zi][r] = __ldg(reinterpret_cast<const unsigned int*>(p.x0 + off0 + tbase + t));
+          if (has_b1) gxb[zi][r] = __ldg(reinterpret_cast<const unsigned int*>(p.x0 + off1 + tbase + t));
         }
       }
     }
@@ -441,7 +491,7 @@ __global__ void __launch_bounds__(FastCfg<LOGN>::THREADS, 1) longconv_fast_kerne
         }
 #pragma unroll
         for (int r = 0; r < HALF; ++r) {
-          const int t = j + r * S0;
+          const int t = tbase + j + r * S0;
           if (t + 1 < t_fft) {
             __nv_bfloat162 va2 = __floats2bfloat162_rn(oa[r][0], oa[r][1]);
             *reinterpret_cast<__nv_bfloat162*>(p.out + off0 + t) = va2;
@@ -456,6 +506,9 @@ __global__ void __launch_bounds__(FastCfg<LOGN>::THREADS, 1) longconv_fast_kerne
         }
       }
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();   // this unit's reads of z are complete and the next unit's staged rows have landed
+    }  // chunk loop
     // ---- ragged end: direct causal dot products for t in [t_fft, T)
     for (int t = t_fft; t < p.T; ++t) {
       const float* kc = p.k + (long long)c * p.Lk;
@@ -486,8 +539,6 @@ __global__ void __launch_bounds__(FastCfg<LOGN>::THREADS, 1) longconv_fast_kerne
       }
       __syncthreads();
     }
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-    __syncthreads();   // phase Z reads of z complete and the next item's staged rows have landed
   }
 }
 
