@@ -62,6 +62,12 @@ _SIGNATURES = {
     "clm_get_filter": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
     "clm_set_debug_stop": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "clm_debug_copy": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "clm_bam_open": (C.c_int, [C.c_char_p, C.c_int, C.POINTER(C.c_void_p)]),
+    "clm_bam_close": (None, [C.c_void_p]),
+    "clm_bam_error": (C.c_char_p, [C.c_void_p]),
+    "clm_bam_records_seen": (C.c_longlong, [C.c_void_p]),
+    "clm_bam_next": (C.c_longlong, [C.c_void_p, C.c_longlong, C.c_longlong, C.c_int, C.c_void_p, C.c_longlong,
+                                    C.c_void_p, C.c_void_p, C.c_int]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

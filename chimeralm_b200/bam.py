@@ -152,6 +152,34 @@ def parse_bam_file_bytes(file_path: str | Path):
                 yield read.name, read.sequence_bytes()
 
 
+def make_record(name: str, seq: str | bytes, flag: int = 0, sa_tag: bool = True, ref_id: int = 0, pos: int = 0,
+                extra_aux: bytes = b"") -> BamRecord:
+    """A synthetic aligned record (one `<len>M` CIGAR op, quality 0xff) for tests and benches."""
+    sb = seq.encode() if isinstance(seq, str) else bytes(seq)
+    n = len(sb)
+    codes = np.zeros(256, np.uint8) + 15
+    codes[_NIB] = np.arange(16, dtype=np.uint8)
+    nib = codes[np.frombuffer(sb, np.uint8)]
+    if n & 1:
+        nib = np.append(nib, np.uint8(0))
+    packed = ((nib[0::2] << 4) | nib[1::2]).astype(np.uint8).tobytes()
+    nm = name.encode() + b"\0"
+    aux = extra_aux + (b"SAZchr1,100,+,50M,60,0;\0" if sa_tag else b"") + b"NMi" + struct.pack("<i", 0)
+    raw = (struct.pack("<iiBBHHHiiii", ref_id, pos, len(nm), 60, 4680, 1, flag, n, -1, -1, 0) + nm +
+           struct.pack("<I", (n << 4) | 0) + packed + b"\xff" * n + aux)
+    seq_off = 32 + len(nm) + 4
+    return BamRecord(ref_id, pos, flag, name, n, raw, seq_off, seq_off + (n + 1) // 2 + n)
+
+
+def minimal_header(references=(("chr1", 1_000_000),)) -> bytes:
+    text = b"@HD\tVN:1.6\tSO:unsorted\n" + b"".join(b"@SQ\tSN:%s\tLN:%d\n" % (n.encode(), l) for n, l in references)
+    out = [b"BAM\1", struct.pack("<i", len(text)), text, struct.pack("<i", len(references))]
+    for n, l in references:
+        nm = n.encode() + b"\0"
+        out += [struct.pack("<i", len(nm)), nm, struct.pack("<i", l)]
+    return b"".join(out)
+
+
 # ---------------------------------------------------------------------------------- writing
 _BGZF_EOF = bytes.fromhex("1f8b08040000000000ff0600424302001b0003000000000000000000")
 

@@ -9,7 +9,7 @@ from pathlib import Path
 PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIB = PKG / "libchimeralm_b200.so"
-SOURCES = [CSRC / "api.cu"]
+SOURCES = [CSRC / "api.cu", CSRC / "bam_ingest.cpp"]
 HEADERS = sorted(CSRC.glob("*.cuh")) + [PKG.parent / "include" / "chimeralm_b200.h"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-shared",
               "-Xcompiler", "-fPIC"]
@@ -26,7 +26,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     if not force and not needs_build():
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc, *NVCC_FLAGS, "-o", str(LIB), *map(str, SOURCES)]
+    cmd = [nvcc, *NVCC_FLAGS, "-o", str(LIB), *map(str, SOURCES), "-lz"]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     r = subprocess.run(cmd, capture_output=True, text=True)

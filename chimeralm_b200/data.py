@@ -19,15 +19,32 @@ from pathlib import Path
 import numpy as np
 import torch
 
-from .bam import parse_bam_file_bytes
+from .ingest import read_bam_flat
 from .tokenizer import DataCollator, encode_read_name
 
 
 class PredictDataset:
-    """Reads kept as (name, uint8 bases) in file order, already truncated to `max_bases`."""
+    """Kept reads in file order, already truncated to `max_bases`: names plus ONE flat uint8 array
+    of ASCII bases with int64 offsets (the layout the native ingest writes and the CUDA encoder
+    reads); `seqs[i]` is a view into it."""
 
-    def __init__(self, names: list[str], seqs: list[np.ndarray]):
-        self.names, self.seqs = names, seqs
+    def __init__(self, names: list[str], flat: np.ndarray, offsets: np.ndarray):
+        self.names, self.flat, self.offsets = names, flat, offsets
+        self.lengths = np.diff(offsets)
+        self._seqs = None
+
+    @classmethod
+    def from_lists(cls, names: list[str], seqs: list[np.ndarray]):
+        offsets = np.zeros(len(seqs) + 1, np.int64)
+        np.cumsum([len(s) for s in seqs], out=offsets[1:])
+        return cls(names, np.concatenate(seqs) if offsets[-1] else np.zeros(0, np.uint8), offsets)
+
+    @property
+    def seqs(self) -> list[np.ndarray]:
+        if self._seqs is None:
+            o = self.offsets
+            self._seqs = [self.flat[o[i] : o[i + 1]] for i in range(len(self.names))]
+        return self._seqs
 
     def __len__(self):
         return len(self.names)
@@ -59,6 +76,7 @@ class BamDataModule:
         self.max_predict_samples = max_predict_samples
         self.engine = engine
         self.bucket_by_length = bucket_by_length
+        self.num_workers = max(0, int(num_workers or 0))  # ingest threads; 0 = all host cores
         self.rank, self.world_size = rank, world_size
         self.batch_size_per_device = batch_size
         self.data_collator = DataCollator(tokenizer)
@@ -78,21 +96,27 @@ class BamDataModule:
             raise ValueError("Predict data path is required for prediction stage.")
         path = Path(self.predict_data_path)
         max_bases = self.tokenizer.max_len_single_sentence - self.tokenizer.num_special_tokens
-        it = read_fastq_bytes(path) if path.suffix in (".fq", ".fastq", ".gz") else parse_bam_file_bytes(path)
-        names, seqs = [], []
-        for name, seq in it:
-            names.append(name)
-            seqs.append(seq[:max_bases])
-            if self.max_predict_samples is not None and len(names) >= self.max_predict_samples:
-                break
-        self.data_predict = PredictDataset(names, seqs)
+        if path.suffix in (".fq", ".fastq", ".gz"):
+            names, seqs = [], []
+            for name, seq in read_fastq_bytes(path):
+                names.append(name)
+                seqs.append(seq[:max_bases])
+                if self.max_predict_samples is not None and len(names) >= self.max_predict_samples:
+                    break
+            self.data_predict = PredictDataset.from_lists(names, seqs)
+        else:
+            # Native ingest: BGZF inflate on `num_workers` threads (0 = all cores), is_chimeric filter
+            # and base decode in C++ (csrc/bam_ingest.cpp) - no per-read Python object.
+            names, flat, offsets = read_bam_flat(path, max_bases, self.max_predict_samples, chimeric_only=True,
+                                                 n_threads=self.num_workers)
+            self.data_predict = PredictDataset(names, flat, offsets)
 
     # -------------------------------------------------------------------------------------
     def _rank_indices(self) -> list[int]:
         n = len(self.data_predict)
         idx = list(range(n))
         if self.bucket_by_length:
-            idx.sort(key=lambda i: len(self.data_predict.seqs[i]))
+            idx.sort(key=lambda i: int(self.data_predict.lengths[i]))
         return idx[self.rank :: self.world_size]
 
     def predict_dataloader(self):

@@ -141,6 +141,30 @@ int clm_set_debug_stop(clm_ctx* ctx, int layer, int stage);
 /* Copies a named workspace ("resid","xn","u","vx","x0","y","yt","score","pooled") to d_dst. */
 int clm_debug_copy(clm_ctx* ctx, const char* what, void* d_dst, size_t max_bytes, void* stream);
 
+/* ---- Native BAM ingest (host only, no GPU needed) ----------------------------------------
+ * Replaces, for `chimeralm predict`, pysam.AlignmentFile iteration + is_chimeric +
+ * parse_bam_file (chimeralm/data/bam.py:21-38) and the per-read Python objects the HF dataset
+ * generator builds from them (chimeralm/data/bam.py:129-174).  BGZF blocks are inflated by
+ * n_threads workers (<= 0: all host cores) one chunk ahead of the parser; CRCs are checked. */
+typedef struct clm_bam clm_bam;
+int clm_bam_open(const char* path, int n_threads, clm_bam** out);
+void clm_bam_close(clm_bam* r);
+/* Message of the last failure on `r`; with r == NULL, of the last failed clm_bam_open on the
+ * calling thread. */
+const char* clm_bam_error(const clm_bam* r);
+/* Records consumed so far (kept or not). */
+long long clm_bam_records_seen(const clm_bam* r);
+/* Decodes the next reads, in file order, into caller-owned (ideally pinned) host buffers:
+ *   bases   : ASCII bases of the kept reads back to back, each cut to its first max_bases
+ *   offsets : int64[max_reads + 1] start offsets into bases (offsets[0] = 0)
+ *   names   : max_reads rows of name_stride bytes, NUL-terminated query names (may be NULL)
+ * chimeric_only != 0 keeps only records passing the reference's is_chimeric (mapped, SA tag,
+ * not secondary, not supplementary).  Stops at max_reads, when the next read would overflow
+ * bases_cap (it is kept for the next call), or at end of file.  Returns the number of reads
+ * written (0 = end of file) or a negative clm_status. */
+long long clm_bam_next(clm_bam* r, long long max_reads, long long max_bases, int chimeric_only, uint8_t* bases,
+                       long long bases_cap, int64_t* offsets, char* names, int name_stride);
+
 #ifdef __cplusplus
 }
 #endif

@@ -4,6 +4,7 @@ reader/writer, the C-ABI surface and the FFT plan."""
 import ctypes
 import json
 import re
+import struct
 import subprocess
 from pathlib import Path
 
@@ -175,3 +176,91 @@ def test_data_module_reference_batching():
     dm2.setup("predict")
     assert dm2.batch_size_per_device == 6
     assert sum(b["input_ids"].shape[0] for b in dm2.predict_dataloader()) == 50
+
+
+# ------------------------------------------------------------------ native BAM ingest (C++)
+def _synth_bam(path, n=300, seed=0, max_len=3000):
+    from chimeralm_b200.bam import make_record, minimal_header
+
+    rng = np.random.default_rng(seed)
+    alphabet = np.frombuffer(b"ACGTNRYKM=", np.uint8)
+    w = BamWriter(path, minimal_header())
+    flags = [0, 16, 4, 0x100, 0x800, 0x810, 1, 2048 | 16]
+    for i in range(n):
+        ln = int(rng.integers(0, max_len)) if i % 17 else (0 if i % 2 else 70000)  # empty and > 1 BGZF block
+        seq = alphabet[rng.integers(0, len(alphabet), ln)].tobytes()
+        extra = b"XAZsome,text;\0" + b"XBBc" + struct.pack("<i", 3) + b"\1\2\3" if i % 3 == 0 else b"ASi" + struct.pack("<i", 7)
+        w.write(make_record(f"r{i}/{'x' * (i % 40)}", seq, flag=flags[i % len(flags)], sa_tag=(i % 4 != 1), extra_aux=extra))
+    w.close()
+
+
+def test_native_ingest_matches_python_reader_on_reference_fixture():
+    from chimeralm_b200.bam import parse_bam_file_bytes
+    from chimeralm_b200.ingest import read_bam_flat
+
+    ref = list(parse_bam_file_bytes(GOLD / "test_chimric_reads.bam"))
+    for kw in ({}, {"block_reads": 7, "block_bytes": 40000}, {"n_threads": 3}):
+        names, flat, offs = read_bam_flat(GOLD / "test_chimric_reads.bam",
+                                          max_bases=32768, **kw)
+        assert names == [n for n, _ in ref]
+        for i, (_, s) in enumerate(ref):
+            assert np.array_equal(flat[offs[i] : offs[i + 1]], s[:32768])
+    names, flat, offs = read_bam_flat(GOLD / "test_chimric_reads.bam", max_bases=100, max_reads=13)
+    assert len(names) == 13 and np.all(np.diff(offs) <= 100)
+    assert np.array_equal(flat[offs[3] : offs[4]], ref[3][1][:100])
+
+
+def test_native_ingest_filter_flags_aux_and_block_spanning(tmp_path):
+    from chimeralm_b200.bam import parse_bam_file_bytes
+    from chimeralm_b200.ingest import read_bam_flat
+
+    p = tmp_path / "synth.bam"
+    _synth_bam(p)
+    ref = list(parse_bam_file_bytes(p))
+    assert 0 < len(ref) < 300
+    names, flat, offs = read_bam_flat(p, max_bases=1 << 20, block_reads=5, block_bytes=1 << 17)
+    assert names == [n for n, _ in ref]
+    assert all(np.array_equal(flat[offs[i] : offs[i + 1]], s) for i, (_, s) in enumerate(ref))
+    with BamReader(p) as bam:
+        every = [(r.name, r.sequence_bytes()) for r in bam]
+    names, flat, offs = read_bam_flat(p, max_bases=1 << 20, chimeric_only=False)
+    assert names == [n for n, _ in every] and len(names) == 300
+    assert all(np.array_equal(flat[offs[i] : offs[i + 1]], s) for i, (_, s) in enumerate(every))
+
+
+def test_native_ingest_rejects_damaged_files(tmp_path):
+    from chimeralm_b200._lib import ChimeraLMNativeError
+    from chimeralm_b200.ingest import read_bam_flat
+
+    p = tmp_path / "synth.bam"
+    _synth_bam(p, n=120)
+    raw = p.read_bytes()
+    with pytest.raises(ValueError, match="cannot open"):
+        read_bam_flat(tmp_path / "missing.bam", 100)
+    (tmp_path / "text.bam").write_bytes(b"this is not a bam file at all, not even gzip........")
+    with pytest.raises(ValueError, match="BGZF"):
+        read_bam_flat(tmp_path / "text.bam", 100)
+    (tmp_path / "cut.bam").write_bytes(raw[: len(raw) // 2])
+    with pytest.raises((ChimeraLMNativeError, ValueError), match="truncated"):
+        read_bam_flat(tmp_path / "cut.bam", 100)
+    bad = bytearray(raw)
+    bad[len(bad) // 2] ^= 0x5A
+    (tmp_path / "flip.bam").write_bytes(bytes(bad))
+    with pytest.raises((ChimeraLMNativeError, ValueError), match="CRC|inflate|BGZF|record|aux"):
+        read_bam_flat(tmp_path / "flip.bam", 100)
+
+
+def test_datamodule_uses_native_ingest_and_matches_generator(tmp_path):
+    from chimeralm_b200.bam import parse_bam_file
+    from chimeralm_b200.data import BamDataModule
+    from chimeralm_b200.tokenizer import load_tokenizer_from_hyena_model
+
+    tok = load_tokenizer_from_hyena_model("hyenadna-small-32k-seqlen")
+    dm = BamDataModule(tok, predict_data_path=GOLD / "test_chimric_reads.bam", batch_size=8, max_predict_samples=20)
+    dm.setup("predict")
+    ref = list(parse_bam_file(GOLD / "test_chimric_reads.bam"))[:20]
+    assert dm.data_predict.names == [r["id"] for r in ref]
+    mb = tok.max_len_single_sentence - tok.num_special_tokens
+    assert [s.tobytes().decode() for s in dm.data_predict.seqs] == [r["seq"][:mb] for r in ref]
+    batches = list(dm.predict_dataloader())
+    assert [len(b["names"]) for b in batches] == [8, 8, 4]
