@@ -44,7 +44,7 @@ def main(version: bool = typer.Option(None, "--version", "-V", help="Show the ap
 
 
 def _predict_rank(rank: int, world: int, data_path: Path, output_path: Path, batch_size: int, ckpt_path, seed_weights,
-                  max_sample, bucket: bool, port: int):
+                  max_sample, bucket: bool, port: int, num_workers: int = 0):
     import torch
 
     from .callbacks import PredictionWriter
@@ -65,7 +65,7 @@ def _predict_rank(rank: int, world: int, data_path: Path, output_path: Path, bat
         model = ChimeraLM.new(seed=seed_weights, device=rank)
     datamodule = BamDataModule(train_data_path=Path("dummy.bam"), tokenizer=tokenizer, predict_data_path=data_path,
                                batch_size=batch_size, max_predict_samples=max_sample, engine=model.engine,
-                               bucket_by_length=bucket)
+                               bucket_by_length=bucket, streaming=not bucket, num_workers=num_workers)
     callbacks = [PredictionWriter(output_dir=output_path, write_interval="batch")]
     trainer = Trainer(accelerator="gpu", devices=world, callbacks=callbacks, logger=False, rank=rank, world_size=world)
     trainer.predict(model=model, dataloaders=datamodule, return_predictions=False)
@@ -92,7 +92,7 @@ def predict(
     gpus: int = typer.Option(1, "--gpus", "-g", help="Number of GPUs to use"),
     output_path: Path = typer.Option(None, "--output", "-o", help="Output path for predictions"),
     batch_size: int = typer.Option(12, "--batch-size", "-b", help="Batch size"),
-    num_workers: int = typer.Option(0, "--workers", "-w", help="Number of workers"),
+    num_workers: int = typer.Option(0, "--workers", "-w", help="BAM ingest threads (0 = all host cores)"),
     ckpt_path: Path = typer.Option(None, "--ckpt", "-c", help="Path to the checkpoint file (.ckpt/.pt/.safetensors)"),
     random: bool = typer.Option(False, "--random", "-r", help="Make the prediction not deterministic"),
     verbose: bool = typer.Option(False, "--verbose", "-v", help="Enable verbose output"),
@@ -119,7 +119,7 @@ def predict(
         raise typer.Exit(1)
     if ckpt_path is None:
         log.info(f"No --ckpt: using seeded random-init ChimeraLM weights (seed {seed_weights}); the Hub is unreachable offline")
-    args = (world, data_path, output_path, batch_size, ckpt_path, seed_weights, max_sample, bucket, 29500 + os.getpid() % 2000)
+    args = (world, data_path, output_path, batch_size, ckpt_path, seed_weights, max_sample, bucket, 29500 + os.getpid() % 2000, num_workers)
     if world == 1:
         _predict_rank(0, *args)
     else:

@@ -54,6 +54,8 @@ struct clm_bam {
   size_t pos = 0;
   bool eof = false;
   long long n_records = 0;
+  long long n_kept = 0;       // records that passed the filter (the global read index)
+  int shard_rank = 0, shard_world = 1;
   std::string header_text;
   int n_ref = 0;
 
@@ -294,6 +296,13 @@ const char* clm_bam_error(const clm_bam* r) { return r ? r->err.c_str() : g_open
 
 long long clm_bam_records_seen(const clm_bam* r) { return r ? r->n_records : 0; }
 
+int clm_bam_set_shard(clm_bam* r, int rank, int world) {
+  if (!r || world < 1 || rank < 0 || rank >= world) return CLM_ERR_INVALID;
+  r->shard_rank = rank;
+  r->shard_world = world;
+  return CLM_OK;
+}
+
 long long clm_bam_next(clm_bam* r, long long max_reads, long long max_bases, int chimeric_only, uint8_t* bases,
                        long long bases_cap, int64_t* offsets, char* names, int name_stride) {
   if (!r || !bases || !offsets || max_reads < 0 || max_bases < 0 || bases_cap < 0 || (names && name_stride < 2))
@@ -342,6 +351,10 @@ long long clm_bam_next(clm_bam* r, long long max_reads, long long max_bases, int
         }
       }
     }
+    if (keep && r->shard_world > 1 && r->n_kept % r->shard_world != r->shard_rank) {
+      ++r->n_kept;  // another rank's read: counted, not decoded
+      keep = false;
+    }
     if (keep) {
       const long long nb = std::min<long long>((long long)l_seq, max_bases);
       if (used + nb > bases_cap) {
@@ -367,6 +380,7 @@ long long clm_bam_next(clm_bam* r, long long max_reads, long long max_bases, int
         nm[ln] = 0;
       }
       used += nb;
+      ++r->n_kept;
       ++n_out;
       offsets[n_out] = used;
     }

@@ -69,7 +69,8 @@ class BamDataModule:
     def __init__(self, tokenizer, train_data_path=None, batch_size: int = 12, val_data_path=None, test_data_path=None,
                  predict_data_path=None, num_workers: int = 1, max_train_samples=None, max_val_samples=None,
                  max_test_samples=None, max_predict_samples=None, *, pin_memory: bool = False, engine=None,
-                 bucket_by_length: bool = False, rank: int = 0, world_size: int = 1):
+                 bucket_by_length: bool = False, rank: int = 0, world_size: int = 1, streaming: bool = False,
+                 prefetch_batches: int = 3):
         self.tokenizer = tokenizer
         self.batch_size = batch_size
         self.predict_data_path = predict_data_path
@@ -78,6 +79,10 @@ class BamDataModule:
         self.bucket_by_length = bucket_by_length
         self.num_workers = max(0, int(num_workers or 0))  # ingest threads; 0 = all host cores
         self.rank, self.world_size = rank, world_size
+        # streaming: batches are decoded by a producer thread straight from the BAM into a ring of
+        # pinned buffers while the GPU works on earlier ones (file order, so no length bucketing)
+        self.streaming = streaming and not bucket_by_length
+        self.prefetch_batches = max(1, prefetch_batches)
         self.batch_size_per_device = batch_size
         self.data_collator = DataCollator(tokenizer)
         self.data_predict: PredictDataset | None = None
@@ -96,6 +101,10 @@ class BamDataModule:
             raise ValueError("Predict data path is required for prediction stage.")
         path = Path(self.predict_data_path)
         max_bases = self.tokenizer.max_len_single_sentence - self.tokenizer.num_special_tokens
+        if self.streaming and path.suffix not in (".fq", ".fastq", ".gz"):
+            self.data_predict = None  # read on the fly by _stream_batches
+            return
+        self.streaming = False
         if path.suffix in (".fq", ".fastq", ".gz"):
             names, seqs = [], []
             for name, seq in read_fastq_bytes(path):
@@ -119,7 +128,98 @@ class BamDataModule:
             idx.sort(key=lambda i: int(self.data_predict.lengths[i]))
         return idx[self.rank :: self.world_size]
 
+    def _stream_batches(self):
+        """Producer/consumer loader: a thread pulls this rank's reads from the native BAM reader
+        (`clm_bam_next` with `clm_bam_set_shard`) into pinned buffers `prefetch_batches` ahead."""
+        import queue
+        import threading
+
+        from .ingest import NAME_STRIDE, NativeBamReader
+
+        tok, bs, W, rank = self.tokenizer, self.batch_size_per_device, self.world_size, self.rank
+        ns = tok.num_special_tokens
+        max_bases = tok.max_len_single_sentence - ns
+        pin = self.engine is not None
+        depth = self.prefetch_batches + 3  # queue + one being filled + one in flight + one being written
+        ring = [(torch.empty(bs * max_bases, dtype=torch.uint8, pin_memory=pin),
+                 torch.empty(bs + 1, dtype=torch.int64, pin_memory=pin),
+                 np.empty((bs, NAME_STRIDE), np.uint8)) for _ in range(depth)]
+        q: queue.Queue = queue.Queue(maxsize=self.prefetch_batches)
+        limit = self.max_predict_samples
+        stop = threading.Event()
+
+        def put(item) -> bool:
+            while not stop.is_set():
+                try:
+                    q.put(item, timeout=0.1)
+                    return True
+                except queue.Full:
+                    continue
+            return False
+
+        def produce():
+            try:
+                with NativeBamReader(self.predict_data_path, self.num_workers) as rd:
+                    rd.set_shard(rank, W)
+                    done, k = 0, 0
+                    while True:
+                        want = bs
+                        if limit is not None:  # global cap: this rank owns indices rank, rank+W, ... < limit
+                            mine = max(0, (limit - rank + W - 1) // W)
+                            want = min(bs, mine - done)
+                        if want <= 0:
+                            break
+                        bases, offs, nm = ring[k % depth]
+                        n = rd.next_block(want, max_bases, bases.numpy(), offs.numpy(), nm, True)
+                        if n == 0:
+                            break
+                        if not put((k, n, done)):
+                            return
+                        done += n
+                        k += 1
+                put(None)
+            except BaseException as e:  # noqa: BLE001 - surfaced on the consumer side
+                put(e)
+
+        th = threading.Thread(target=produce, name="clm-bam-ingest", daemon=True)
+        th.start()
+        try:
+            while True:
+                item = q.get()
+                if item is None:
+                    break
+                if isinstance(item, BaseException):
+                    raise item
+                k, n, done = item
+                bases, offs, nm = ring[k % depth]
+                o = offs.numpy()
+                names = [r[: r.index(0)].decode("ascii", "replace") for r in (nm[i].tobytes() for i in range(n))]
+                T = int(np.diff(o[: n + 1]).max()) + ns
+                id_rows = np.array([encode_read_name(x) for x in names], dtype=np.int64).astype(np.int8)
+                batch = {"id": torch.from_numpy(id_rows), "labels": torch.full((n,), -1, dtype=torch.int64),
+                         "names": names, "indices": [rank + W * (done + i) for i in range(n)]}
+                nb = int(o[n])
+                if self.engine is not None:
+                    dev = self.engine.device
+                    ids, _ = self.engine.encode(bases[: max(nb, 1)].to(dev, non_blocking=True),
+                                                offs[: n + 1].to(dev, non_blocking=True), T, add_cls=tok.add_cls,
+                                                add_sep=tok.add_sep, pad_left=tok.padding_side == "left",
+                                                max_bases=max_bases)
+                    batch["input_ids"] = ids
+                else:
+                    b = bases.numpy()
+                    feats = [{"input_ids": tok.encode_array(b[o[i] : o[i + 1]].tobytes(), max_length=tok.max_len_single_sentence)}
+                             for i in range(n)]
+                    batch["input_ids"] = tok.pad(feats, return_tensors="pt")["input_ids"]
+                yield batch
+        finally:
+            stop.set()
+            th.join(timeout=5)
+
     def predict_dataloader(self):
+        if self.streaming:
+            yield from self._stream_batches()
+            return
         ds = self.data_predict
         idx = self._rank_indices()
         bs = self.batch_size_per_device
@@ -174,11 +274,32 @@ class Trainer:
             loader = dm
         model.eval()
         results = []
-        for batch_idx, batch in enumerate(loader):
-            pred = model.predict_step(batch, batch_idx)
+
+        def finish(item):
+            # Batch k's outputs are consumed (callbacks, files) only after batch k+1 was launched, so
+            # the device never waits for the host side of the loop.
+            batch_idx, batch, pred, ev = item
+            if ev is not None:
+                ev.synchronize()
             for cb in self.callbacks:
                 cb.write_on_batch_end(self, model, pred, None, batch, batch_idx, 0)
             if return_predictions or self.world_size > 1:
                 results.append((batch.get("indices"), pred[2].cpu() if len(pred) > 2 else pred[0].argmax(1).cpu()))
+
+        pending = None
+        for batch_idx, batch in enumerate(loader):
+            pred = model.predict_step(batch, batch_idx)
+            ev = None
+            if isinstance(pred, (tuple, list)) and pred[0].is_cuda:
+                host = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True).copy_(t, non_blocking=True)
+                        if isinstance(t, torch.Tensor) and t.is_cuda else t for t in pred]
+                ev = torch.cuda.Event()
+                ev.record(torch.cuda.current_stream(pred[0].device))
+                pred = tuple(host)
+            if pending is not None:
+                finish(pending)
+            pending = (batch_idx, batch, pred, ev)
+        if pending is not None:
+            finish(pending)
         self.last_results = results
         return results if return_predictions else None

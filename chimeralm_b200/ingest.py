@@ -48,6 +48,11 @@ class NativeBamReader:
             raise ChimeraLMNativeError(f"clm_bam_next failed (status {n}): {msg.decode() if msg else '?'}")
         return int(n)
 
+    def set_shard(self, rank: int, world: int) -> None:
+        """Only kept reads with running index i % world == rank are returned from now on."""
+        if self.lib.clm_bam_set_shard(self.h, int(rank), int(world)) < 0:
+            raise ValueError(f"bad shard {rank}/{world}")
+
     @property
     def records_seen(self) -> int:
         return int(self.lib.clm_bam_records_seen(self.h))

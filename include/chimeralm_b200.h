@@ -154,6 +154,11 @@ void clm_bam_close(clm_bam* r);
 const char* clm_bam_error(const clm_bam* r);
 /* Records consumed so far (kept or not). */
 long long clm_bam_records_seen(const clm_bam* r);
+/* Data-parallel sharding (Lightning's predict sampler: rank r takes kept reads r, r+W, ...,
+ * chimeralm/data/bam.py:287-299 under DDP): after this call clm_bam_next only returns the
+ * kept reads whose running index i satisfies i % world == rank; the others are skipped
+ * without being decoded. */
+int clm_bam_set_shard(clm_bam* r, int rank, int world);
 /* Decodes the next reads, in file order, into caller-owned (ideally pinned) host buffers:
  *   bases   : ASCII bases of the kept reads back to back, each cut to its first max_bases
  *   offsets : int64[max_reads + 1] start offsets into bases (offsets[0] = 0)

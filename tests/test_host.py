@@ -264,3 +264,25 @@ def test_datamodule_uses_native_ingest_and_matches_generator(tmp_path):
     assert [s.tobytes().decode() for s in dm.data_predict.seqs] == [r["seq"][:mb] for r in ref]
     batches = list(dm.predict_dataloader())
     assert [len(b["names"]) for b in batches] == [8, 8, 4]
+
+
+def test_streaming_loader_matches_load_all_and_shards_like_the_sampler(tmp_path):
+    from chimeralm_b200.data import BamDataModule
+    from chimeralm_b200.tokenizer import load_tokenizer_from_hyena_model
+
+    tok = load_tokenizer_from_hyena_model("hyenadna-small-32k-seqlen")
+    p = tmp_path / "synth.bam"
+    _synth_bam(p, n=200, max_len=400)
+
+    def batches(streaming, rank=0, world=1, limit=None):
+        dm = BamDataModule(tok, predict_data_path=p, batch_size=8 * world, max_predict_samples=limit, streaming=streaming,
+                           rank=rank, world_size=world)
+        dm.setup("predict")
+        return list(dm.predict_dataloader())
+
+    for rank, world, limit in ((0, 1, None), (0, 2, None), (1, 2, None), (1, 2, 37), (0, 1, 5)):
+        a, b = batches(False, rank, world, limit), batches(True, rank, world, limit)
+        assert len(a) == len(b) > 0
+        for x, y in zip(a, b):
+            assert x["names"] == y["names"] and list(x["indices"]) == list(y["indices"])
+            assert torch.equal(x["input_ids"], y["input_ids"]) and torch.equal(x["id"], y["id"])
