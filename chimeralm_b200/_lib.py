@@ -59,6 +59,10 @@ _SIGNATURES = {
     "clm_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int]),
     "clm_longconv": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                C.c_void_p]),
+    "clm_longconv_tc": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                  C.c_void_p]),
+    "clm_longconv_tc_trace": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                        C.c_void_p, C.c_void_p]),
     "clm_get_filter": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
     "clm_set_debug_stop": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "clm_debug_copy": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_size_t, C.c_void_p]),

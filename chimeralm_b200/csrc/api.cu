@@ -19,6 +19,7 @@
 #include "kernels.cuh"
 #include "longconv.cuh"
 #include "longconv_fast.cuh"
+#include "longconv_tc.cuh"
 
 using namespace clm;
 
@@ -47,6 +48,7 @@ struct LayerW {
   float* k = nullptr;                               // [D][Lk]
   float2* gspec[LONGCONV_MAX_LOGN + 1] = {nullptr};  // per LOGN: [n_seg][D][N]
   float2* gspecT[LONGCONV_MAX_LOGN + 1] = {nullptr}; // per LOGN: [D][16][N/16], bias folded (longconv_fast)
+  __half2* gtc = nullptr;                            // [D][16384] fp16 spectrum, lane-interleaved (longconv_tc)
 };
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -107,6 +109,8 @@ struct clm_ctx {
   bool fused_mlp = true;  // out_proj+res+LN2+fc1+gelu+fc2+res in one kernel
   bool fused_in = true;   // LN1+in_proj+short conv+gate in one kernel
   bool fast_conv = true;  // tuned single-chunk long convolution
+  bool tc_conv = true;    // tensor-core FFT long convolution for reads of 8192..8200 tokens (needs fused_in)
+  __half* tc_S = nullptr; // shared-memory image of the DFT constant stack (longconv_tc)
   bool mlp_2cta = false;  // CTA-pair (cta_group::2) version of the fused block tail
   bool y_channel_major = true;  // block_mlp reads the conv output channel-major (MN-major UMMA operand): no transpose
   // debug
@@ -294,7 +298,7 @@ int make_tmap_xn(clm_ctx* c, CUtensorMap* tm, const void* base, int B, int T, in
 }
 
 int launch_block_in(clm_ctx* c, int layer, const __nv_bfloat16* xn, int B, int T, int Tp, __nv_bfloat16* vx,
-                    __nv_bfloat16* x0, cudaStream_t st, long long* trace = nullptr) {
+                    __nv_bfloat16* x0, cudaStream_t st, long long* trace = nullptr, bool vx_f16 = false) {
   static bool attr_set = false;
   if (!attr_set) {
     CLM_CUDA(c, cudaFuncSetAttribute(block_in_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bi::SMEM_TOTAL));
@@ -308,7 +312,7 @@ int launch_block_in(clm_ctx* c, int layer, const __nv_bfloat16* xn, int B, int T
   if ((rc = make_tmap_xn(c, &tmXN, xn, B, T, bi::NCOL))) return rc;
   BlockInParams p{};
   p.b_in = L.in_bf; p.cw = L.sc_w; p.cb = L.sc_b;
-  p.B = B; p.T = T; p.trace = trace;
+  p.B = B; p.T = T; p.trace = trace; p.vx_f16 = vx_f16 ? 1 : 0;
   p.tiles_per_seq = (T + bi::BT - 1) / bi::BT;
   p.num_tiles = B * p.tiles_per_seq;
   const int grid = std::min(p.num_tiles, c->num_sms);
@@ -511,6 +515,61 @@ int launch_longconv(clm_ctx* c, int layer, const __nv_bfloat16* vx, const __nv_b
     case 14: return conv_t<14>(c, p, grid, st);
   }
   return fail(c, CLM_ERR_INVALID, "longconv: no plan for T=%d", T);
+}
+
+bool tc_conv_applies(const clm_ctx* c, int T) {
+  return c->tc_conv && T >= tc::C && T <= tc::C + LONGCONV_TAIL_MAX && c->layers[0].gtc != nullptr;
+}
+
+// vx is fp16 here (block_in writes it that way when the tensor-core conv follows)
+int launch_longconv_tc(clm_ctx* c, int layer, const __half* vx, const __nv_bfloat16* x0, __nv_bfloat16* out, int B, int T,
+                       int Tp, cudaStream_t st, long long* trace = nullptr) {
+  if (!tc_conv_applies(c, T)) return fail(c, CLM_ERR_INVALID, "longconv_tc: T=%d is outside [%d, %d]", T, tc::C, tc::C + LONGCONV_TAIL_MAX);
+  static bool attr_set = false;
+  if (!attr_set) {
+    CLM_CUDA(c, cudaFuncSetAttribute(longconv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_TOTAL));
+    attr_set = true;
+  }
+  LayerW& L = c->layers[layer];
+  const int D = c->cfg.d_model;
+  CUtensorMap tm;
+  {
+    cuuint64_t dims[3] = {128, 64, (cuuint64_t)B * D};
+    cuuint64_t strides[2] = {256, (cuuint64_t)Tp * 2};
+    cuuint32_t box[3] = {64, 64, 1}, estr[3] = {1, 1, 1};
+    CUresult r = c->encode_tiled(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<__half*>(vx), dims, strides, box, estr,
+                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(c, CLM_ERR_CUDA, "cuTensorMapEncodeTiled(vx fp16) failed with CUresult %d", (int)r);
+  }
+  CUtensorMap tmo;
+  {
+    cuuint64_t dims[3] = {128, 64, (cuuint64_t)B * D};
+    cuuint64_t strides[2] = {256, (cuuint64_t)Tp * 2};
+    cuuint32_t box[3] = {128, 64, 1}, estr[3] = {1, 1, 1};
+    CUresult r = c->encode_tiled(&tmo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, out, dims, strides, box, estr,
+                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(c, CLM_ERR_CUDA, "cuTensorMapEncodeTiled(conv out) failed with CUresult %d", (int)r);
+  }
+  CUtensorMap tmg;
+  {
+    cuuint64_t dims[3] = {128, 64, (cuuint64_t)B * D};
+    cuuint64_t strides[2] = {256, (cuuint64_t)Tp * 2};
+    cuuint32_t box[3] = {128, 64, 1}, estr[3] = {1, 1, 1};
+    CUresult r = c->encode_tiled(&tmg, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<__nv_bfloat16*>(x0), dims, strides, box, estr,
+                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(c, CLM_ERR_CUDA, "cuTensorMapEncodeTiled(conv gate) failed with CUresult %d", (int)r);
+  }
+  LongConvTcParams p{};
+  p.T = T; p.vx = vx; p.k = L.k; p.dbias = L.fbias; p.Lk = c->Lk;
+  p.x0 = x0; p.out = out; p.S = reinterpret_cast<const uint4*>(c->tc_S); p.G = reinterpret_cast<const uint4*>(L.gtc);
+  p.B = B; p.D = D; p.Tp = Tp; p.n_pairs = (B + 1) / 2; p.n_items = D * p.n_pairs; p.trace = trace;
+  const int grid = std::min(p.n_items, c->num_sms);
+  longconv_tc_kernel<<<grid, tc::THREADS, tc::SMEM_TOTAL, st>>>(tm, tmo, tmg, p);
+  CLM_LAUNCH_CHECK(c, "longconv_tc");
+  return 0;
 }
 
 int round_up(int x, int m) { return (x + m - 1) / m * m; }
@@ -746,7 +805,16 @@ int clm_finalize(clm_ctx* c) {
     if ((rc = spectrum_fast_t<11>(c, L))) return rc;
     if ((rc = spectrum_fast_t<13>(c, L))) return rc;
     if ((rc = spectrum_fast_t<14>(c, L))) return rc;
+    if (c->cfg.max_seq_len >= tc::C) {
+      if ((rc = dev_alloc(c, &L.gtc, (size_t)D * tc::N))) return rc;
+      CLM_CUDA(c, cudaFuncSetAttribute(tc::spectrum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::N * (int)sizeof(float2)));
+      tc::spectrum_kernel<<<D, 256, tc::N * sizeof(float2)>>>(L.k, c->Lk, L.fbias, L.gtc);
+      CLM_LAUNCH_CHECK(c, "tc_spectrum");
+    }
   }
+  if ((rc = dev_alloc(c, &c->tc_S, (size_t)tc::S_BYTES / 2))) return rc;
+  tc::build_s_kernel<<<(tc::S_ROWS * 128 + 255) / 256, 256>>>(c->tc_S);
+  CLM_LAUNCH_CHECK(c, "tc_build_s");
   // head
   const float *a0w, *a2b;
   NEED(HD + "attention.0.weight", (int64_t)D * D, &a0w);
@@ -887,6 +955,7 @@ int clm_forward(clm_ctx* c, const void* d_ids, int ids_dtype, int B, int T, floa
 
   for (int l = 0; l < g.n_layer; ++l) {
     LayerW& L = c->layers[l];
+    bool use_tc = false;   // this layer's VX is fp16 and feeds the tensor-core long convolution
     if (c->fused_in && c->dbg_layer != l) {
       if (!xn_valid) {
         ProfScope ps_(c, PC_LN, st);
@@ -894,7 +963,8 @@ int clm_forward(clm_ctx* c, const void* d_ids, int ids_dtype, int B, int T, floa
         CLM_LAUNCH_CHECK(c, "normalize");
       }
       ProfScope ps_(c, PC_BLOCK_IN, st);
-      if ((rc = launch_block_in(c, l, c->XN, B, T, Tp, c->VX, c->X0, st))) return rc;
+      use_tc = tc_conv_applies(c, T);
+      if ((rc = launch_block_in(c, l, c->XN, B, T, Tp, c->VX, c->X0, st, nullptr, use_tc))) return rc;
     } else {
     { ProfScope ps_(c, PC_LN, st);
       layernorm_bf16_kernel<<<rows32, 256, 0, st>>>(c->R, L.ln1_g, L.ln1_b, c->XN, M, g.layer_norm_eps);
@@ -911,7 +981,9 @@ int clm_forward(clm_ctx* c, const void* d_ids, int ids_dtype, int B, int T, floa
     }
     STOP_AFTER(l, 3);
     { ProfScope ps_(c, PC_LONGCONV, st);
-    if ((rc = launch_longconv(c, l, c->VX, c->X0, c->Y, B, T, Tp, c->scratch, c->scratch_bytes, st))) return rc; }
+    if (use_tc) rc = launch_longconv_tc(c, l, reinterpret_cast<const __half*>(c->VX), c->X0, c->Y, B, T, Tp, st);
+    else rc = launch_longconv(c, l, c->VX, c->X0, c->Y, B, T, Tp, c->scratch, c->scratch_bytes, st);
+    if (rc) return rc; }
     STOP_AFTER(l, 4);
     const bool mlp_fused = c->fused_mlp && c->dbg_layer != l;
     if (!(mlp_fused && c->y_channel_major)) {
@@ -1043,6 +1115,7 @@ int clm_set_option(clm_ctx* c, const char* name, int value) {
   if (n == "fused_mlp") c->fused_mlp = value != 0;
   else if (n == "fused_in") c->fused_in = value != 0;
   else if (n == "fast_conv") c->fast_conv = value != 0;
+  else if (n == "tc_conv") c->tc_conv = value != 0;
   else if (n == "y_channel_major") c->y_channel_major = value != 0;
   else if (n == "mlp_2cta") c->mlp_2cta = value != 0;
   else return fail(c, CLM_ERR_INVALID, "clm_set_option: unknown option '%s'", name);
@@ -1110,6 +1183,24 @@ int clm_longconv(clm_ctx* c, int layer, const void* d_vx, const void* d_x0, void
   }
   return launch_longconv(c, layer, (const __nv_bfloat16*)d_vx, (const __nv_bfloat16*)d_x0, (__nv_bfloat16*)d_out, B, T, Tp,
                          c->scratch, c->scratch_bytes, (cudaStream_t)stream);
+}
+
+int clm_longconv_tc_trace(clm_ctx* c, int layer, const void* d_vx_f16, const void* d_x0, void* d_out, int B, int T, int Tp,
+                          long long* d_trace, void* stream) {
+  if (!c || !c->finalized) return fail(c, CLM_ERR_STATE, "clm_longconv_tc_trace before clm_finalize");
+  if (layer < 0 || layer >= c->cfg.n_layer || !d_vx_f16 || !d_x0 || !d_out || !d_trace || B <= 0 || Tp < T || Tp % 64 != 0)
+    return fail(c, CLM_ERR_INVALID, "clm_longconv_tc_trace: bad argument");
+  return launch_longconv_tc(c, layer, (const __half*)d_vx_f16, (const __nv_bfloat16*)d_x0, (__nv_bfloat16*)d_out, B, T, Tp,
+                            (cudaStream_t)stream, d_trace);
+}
+
+int clm_longconv_tc(clm_ctx* c, int layer, const void* d_vx_f16, const void* d_x0, void* d_out, int B, int T, int Tp,
+                    void* stream) {
+  if (!c || !c->finalized) return fail(c, CLM_ERR_STATE, "clm_longconv_tc before clm_finalize");
+  if (layer < 0 || layer >= c->cfg.n_layer || !d_vx_f16 || !d_x0 || !d_out || B <= 0 || Tp < T || Tp % 64 != 0)
+    return fail(c, CLM_ERR_INVALID, "clm_longconv_tc: bad argument");
+  return launch_longconv_tc(c, layer, (const __half*)d_vx_f16, (const __nv_bfloat16*)d_x0, (__nv_bfloat16*)d_out, B, T, Tp,
+                            (cudaStream_t)stream);
 }
 
 int clm_get_filter(clm_ctx* c, int layer, float* d_out, int L, void* stream) {

@@ -42,6 +42,7 @@ struct BlockInParams {
   const float* cb;      // [768]   short filter bias
   int B, T;
   int tiles_per_seq, num_tiles;
+  int vx_f16;           // write v * x1 as fp16 instead of bf16 (operand of the tensor-core long convolution)
   long long* trace;     // optional [2][64] clock64 stamps of CTA 0 (row 0 = MMA issuer, row 1 = epilogue warp 2)
 };
 
@@ -256,9 +257,14 @@ block_in_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
             const float* x1p = &uc[1][k * 8];
             const float* vp = &uc[2][k * 8];
             const uint32_t chunk = (uint32_t(s * 4 + k) ^ swz) << 4;
-            ptx::st_shared_v4(sST + (0 * 2 + hf) * STAGE_BOX + rowoff + chunk, pack_bf16(vp[0] * x1p[0], vp[1] * x1p[1]),
-                              pack_bf16(vp[2] * x1p[2], vp[3] * x1p[3]), pack_bf16(vp[4] * x1p[4], vp[5] * x1p[5]),
-                              pack_bf16(vp[6] * x1p[6], vp[7] * x1p[7]));
+            if (p.vx_f16)
+              ptx::st_shared_v4(sST + (0 * 2 + hf) * STAGE_BOX + rowoff + chunk, pack_f16(vp[0] * x1p[0], vp[1] * x1p[1]),
+                                pack_f16(vp[2] * x1p[2], vp[3] * x1p[3]), pack_f16(vp[4] * x1p[4], vp[5] * x1p[5]),
+                                pack_f16(vp[6] * x1p[6], vp[7] * x1p[7]));
+            else
+              ptx::st_shared_v4(sST + (0 * 2 + hf) * STAGE_BOX + rowoff + chunk, pack_bf16(vp[0] * x1p[0], vp[1] * x1p[1]),
+                                pack_bf16(vp[2] * x1p[2], vp[3] * x1p[3]), pack_bf16(vp[4] * x1p[4], vp[5] * x1p[5]),
+                                pack_bf16(vp[6] * x1p[6], vp[7] * x1p[7]));
             ptx::st_shared_v4(sST + (1 * 2 + hf) * STAGE_BOX + rowoff + chunk, pack_bf16(x0p[0], x0p[1]),
                               pack_bf16(x0p[2], x0p[3]), pack_bf16(x0p[4], x0p[5]), pack_bf16(x0p[6], x0p[7]));
           }

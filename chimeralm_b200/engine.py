@@ -219,6 +219,17 @@ class Engine:
         self._check(rc, "clm_longconv")
         return out
 
+    def longconv_tc(self, layer: int, vx_f16: torch.Tensor, x0: torch.Tensor, T: int):
+        """Tensor-core FFT long conv (8192 <= T <= 8200): vx fp16 [B,D,Tp], x0 bf16 -> bf16 [B,D,Tp]."""
+        if vx_f16.dtype != torch.float16 or x0.dtype != torch.bfloat16:
+            raise TypeError("longconv_tc takes fp16 vx and bf16 x0")
+        B, D, Tp = vx_f16.shape
+        out = torch.zeros_like(x0)
+        rc = self.lib.clm_longconv_tc(self.ctx, layer, C.c_void_p(vx_f16.data_ptr()), C.c_void_p(x0.data_ptr()),
+                                      C.c_void_p(out.data_ptr()), B, T, Tp, _stream_ptr(self.device))
+        self._check(rc, "clm_longconv_tc")
+        return out
+
     def get_filter(self, layer: int, L: int) -> torch.Tensor:
         out = torch.empty(self.cfg.d_model, L, dtype=torch.float32, device=self.device)
         self._check(self.lib.clm_get_filter(self.ctx, layer, C.c_void_p(out.data_ptr()), L, _stream_ptr(self.device)),

@@ -133,6 +133,13 @@ int clm_set_option(clm_ctx* ctx, const char* name, int value);
 int clm_longconv(clm_ctx* ctx, int layer, const void* d_vx, const void* d_x0, void* d_out, int B, int T, int Tp,
                  void* stream);
 /* Copies the generated time-domain filter k[layer][:, :L] (float32 [D, L]) to a device buffer. */
+/* Tensor-core FFT long convolution (reads of 8192..8200 tokens): same contract as clm_longconv except
+ * that d_vx holds fp16 values (what the fused in_proj kernel emits when this kernel follows). */
+int clm_longconv_tc(clm_ctx* ctx, int layer, const void* d_vx_f16, const void* d_x0, void* d_out, int B, int T, int Tp,
+                    void* stream);
+/* Same, and CTA 0 writes clock64() stamps into d_trace[2][64] (row 0 MMA issuer, row 1 epilogue warp). */
+int clm_longconv_tc_trace(clm_ctx* ctx, int layer, const void* d_vx_f16, const void* d_x0, void* d_out, int B, int T,
+                          int Tp, long long* d_trace, void* stream);
 int clm_get_filter(clm_ctx* ctx, int layer, float* d_out, int L, void* stream);
 /* Forward stops after (layer, stage); layer == n_layer addresses the final stages; -1 disables.
  * Stages: 0 embed | per layer 1 ln1 2 in_proj 3 shortconv+gate 4 longconv 5 transpose 6 out_proj
