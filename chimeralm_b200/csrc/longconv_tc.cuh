@@ -183,7 +183,7 @@ longconv_tc_kernel(const __grid_constant__ CUtensorMap tmVX, const __grid_consta
   if ((ptx::smem_u32(smem) & 1023u) != 0) __trap();
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
   uint64_t* z_full = bars;        // [2] TMA landed
-  uint64_t* z_empty = bars + 2;   // [2] step 1 finished reading AND the output tile staged in the same buffer was stored
+  uint64_t* z_empty = bars + 2;   // [2] step 1 finished reading z
   uint64_t* x_full = bars + 4;    // step 1 accumulators complete
   uint64_t* p1_full = bars + 5;   // E1 wrote P1
   uint64_t* y_full = bars + 6;    // step 3 complete
@@ -192,7 +192,8 @@ longconv_tc_kernel(const __grid_constant__ CUtensorMap tmVX, const __grid_consta
   uint64_t* bt_full = bars + 9;   // E3 wrote BT
   uint64_t* o_full = bars + 10;   // step 7 complete
   uint64_t* g_full = bars + 11;   // x0 gate tile landed in the z buffer (TMA, issued once step 1 has consumed z)
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 12);
+  uint64_t* out_ready = bars + 12; // [2] E4 wrote the output tile into the z buffer (8 warp arrivals)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 14);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // contiguous item ranges per CTA: consecutive items share the channel (and its spectrum lines in L2)
@@ -211,7 +212,7 @@ longconv_tc_kernel(const __grid_constant__ CUtensorMap tmVX, const __grid_consta
   }
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmVX); ptx::prefetch_tmap(&tmOut); ptx::prefetch_tmap(&tmX0);
-    for (int i = 0; i < 2; ++i) { ptx::mbar_init(&z_full[i], 1); ptx::mbar_init(&z_empty[i], 2); }
+    for (int i = 0; i < 2; ++i) { ptx::mbar_init(&z_full[i], 1); ptx::mbar_init(&z_empty[i], 1); ptx::mbar_init(&out_ready[i], 8); }
     ptx::mbar_init(x_full, 1); ptx::mbar_init(p1_full, 8);
     ptx::mbar_init(y_full, 1); ptx::mbar_init(p2_full, 8);
     ptx::mbar_init(x2_full, 1); ptx::mbar_init(bt_full, 8);
@@ -228,20 +229,36 @@ longconv_tc_kernel(const __grid_constant__ CUtensorMap tmVX, const __grid_consta
   const uint32_t TM_X = tmem_base, TM_Y = tmem_base + 256;
 
   if (warp == 0) {
-    // =========================== TMA producer ===========================
+    // =========================== TMA producer (+ output stores) ===========================
+    // Buffer b cycles: z tile of item i -> (step 1 done) x0 gate tile of item i -> (E4) output tile of item i -> stored
+    // -> z tile of item i + 2.  This thread issues the z loads and the output stores; the gate load is issued by an
+    // epilogue thread, which is the one that knows when step 1 has finished.
     if (lane == 0) {
-      uint32_t it = 0;
-      for (int item = item0; item < item1; ++item, ++it) {
-        const uint32_t buf = it & 1, ph = (it >> 1) & 1;
-        const int ch = item / p.n_pairs, pr = item % p.n_pairs;
-        ptx::mbar_wait(&z_empty[buf], ph ^ 1);
-        ptx::mbar_expect_tx(&z_full[buf], Z_BYTES);
+      const int n_it = item1 - item0;
+      for (int it = 0; it < n_it + 2; ++it) {
+        const uint32_t buf = it & 1;
         uint8_t* z = smem + OFF_Z + buf * Z_BYTES;
-        for (int part = 0; part < 2; ++part) {
-          const int row = (2 * pr + part) * p.D + ch;    // reads past B are out of bounds -> zero filled
-          for (int a = 0; a < 2; ++a) ptx::tma_load_3d(z + part * 16384 + a * 8192, &tmVX, &z_full[buf], 64 * a, 0, row);
+        if (it >= 2) {   // retire item it - 2: its output tile is complete in z
+          const int item = item0 + it - 2;
+          const int ch = item / p.n_pairs, pr = item % p.n_pairs;
+          ptx::mbar_wait(&out_ready[buf], ((it - 2) >> 1) & 1);
+          ptx::tma_store_3d(&tmOut, z, 0, 0, 2 * pr * p.D + ch);
+          if (2 * pr + 1 < p.B) ptx::tma_store_3d(&tmOut, z + 16384, 0, 0, (2 * pr + 1) * p.D + ch);
+          ptx::tma_store_commit();
+          ptx::tma_store_wait_read<0>();
+        }
+        if (it < n_it) {
+          const int item = item0 + it;
+          const int ch = item / p.n_pairs, pr = item % p.n_pairs;
+          if (it >= 2) ptx::mbar_wait(&z_empty[buf], ((it - 2) >> 1) & 1);   // long since true
+          ptx::mbar_expect_tx(&z_full[buf], Z_BYTES);
+          for (int part = 0; part < 2; ++part) {
+            const int row = (2 * pr + part) * p.D + ch;    // reads past B are out of bounds -> zero filled
+            for (int a = 0; a < 2; ++a) ptx::tma_load_3d(z + part * 16384 + a * 8192, &tmVX, &z_full[buf], 64 * a, 0, row);
+          }
         }
       }
+      ptx::tma_store_wait<0>();
     }
   } else if (warp == 1) {
     // =========================== MMA issuer ===========================
@@ -532,17 +549,10 @@ longconv_tc_kernel(const __grid_constant__ CUtensorMap tmVX, const __grid_consta
       }
       ptx::fence_proxy_async_smem();
       ptx::tc_fence_before_sync();
-      ptx::bar_sync(2, 256);
-      if (threadIdx.x == 64) {
-        ptx::tma_store_3d(&tmOut, zb, 0, 0, b0 * p.D + ch);
-        if (has1) ptx::tma_store_3d(&tmOut, zb + 16384, 0, 0, b1 * p.D + ch);
-        ptx::tma_store_commit();
-        ptx::tma_store_wait_read<0>();
-        ptx::mbar_arrive(&z_empty[buf]);
-      }
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&out_ready[buf]);
     }
   }
-  if (threadIdx.x == 64) ptx::tma_store_wait<0>();
   ptx::tc_fence_before_sync();
   __syncthreads();
   if (warp == 1) {
