@@ -109,6 +109,7 @@ struct clm_ctx {
   bool fused_mlp = true;  // out_proj+res+LN2+fc1+gelu+fc2+res in one kernel
   bool fused_in = true;   // LN1+in_proj+short conv+gate in one kernel
   bool fast_conv = true;  // tuned single-chunk long convolution
+  int mlp_stagger = 0;    // block_mlp: CTA phase stagger in cycles (0 = off)
   bool tc_conv = true;    // tensor-core FFT long convolution for reads of 8192..8200 tokens (needs fused_in)
   __half* tc_S = nullptr; // shared-memory image of the DFT constant stack (longconv_tc)
   bool mlp_2cta = false;  // CTA-pair (cta_group::2) version of the fused block tail
@@ -348,6 +349,7 @@ int launch_block_mlp(clm_ctx* c, int layer, const __nv_bfloat16* y, float* res, 
   p.eps = c->cfg.layer_norm_eps;
   p.num_tiles = (M + bm::BM - 1) / bm::BM;
   p.trace = trace;
+  p.stagger_cycles = c->mlp_stagger;
   if (B > 0) {
     p.y_cm = 1; p.T = T; p.tiles_per_seq = (T + bm::BM - 1) / bm::BM; p.num_tiles = B * p.tiles_per_seq;
   }
@@ -1116,6 +1118,7 @@ int clm_set_option(clm_ctx* c, const char* name, int value) {
   else if (n == "fused_in") c->fused_in = value != 0;
   else if (n == "fast_conv") c->fast_conv = value != 0;
   else if (n == "tc_conv") c->tc_conv = value != 0;
+  else if (n == "mlp_stagger") c->mlp_stagger = value;
   else if (n == "y_channel_major") c->y_channel_major = value != 0;
   else if (n == "mlp_2cta") c->mlp_2cta = value != 0;
   else return fail(c, CLM_ERR_INVALID, "clm_set_option: unknown option '%s'", name);
@@ -1161,6 +1164,16 @@ int clm_block_mlp_cm(clm_ctx* c, int layer, const void* d_y_cm, float* d_res, in
   if (layer < 0 || layer >= c->cfg.n_layer || !d_y_cm || !d_res || B <= 0 || T <= 0 || Tp < T || Tp % 64 != 0)
     return fail(c, CLM_ERR_INVALID, "clm_block_mlp_cm: bad argument");
   return launch_block_mlp(c, layer, (const __nv_bfloat16*)d_y_cm, d_res, B * T, (cudaStream_t)stream, nullptr, B, T, Tp);
+}
+
+int clm_block_mlp_cm_trace(clm_ctx* c, int layer, const void* d_y_cm, float* d_res, int B, int T, int Tp, int write_xn,
+                           long long* d_trace, void* stream) {
+  if (!c || !c->finalized) return fail(c, CLM_ERR_STATE, "clm_block_mlp_cm_trace before clm_finalize");
+  if (layer < 0 || layer >= c->cfg.n_layer || !d_y_cm || !d_res || B <= 0 || T <= 0 || Tp < T || Tp % 64 != 0)
+    return fail(c, CLM_ERR_INVALID, "clm_block_mlp_cm_trace: bad argument");
+  if (write_xn && (size_t)B * T > (size_t)c->max_B * c->max_T) return fail(c, CLM_ERR_STATE, "clm_block_mlp_cm_trace: call clm_reserve(B, T) first");
+  return launch_block_mlp(c, layer, (const __nv_bfloat16*)d_y_cm, d_res, B * T, (cudaStream_t)stream, d_trace, B, T, Tp,
+                          write_xn ? c->XN : nullptr);
 }
 
 int clm_block_mlp_trace(clm_ctx* c, int layer, const void* d_y, float* d_res, int M, long long* d_trace, void* stream) {

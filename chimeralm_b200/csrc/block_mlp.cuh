@@ -45,6 +45,7 @@ struct BlockMlpParams {
   // write_xn: the output epilogue also emits xn = (out - mean) * rstd as bf16 [B][T][256] (tmXN, 3-D {col, t, b}):
   // the next consumer's LayerNorm (affine folded into its weights) without another pass over the residual.
   int write_xn;
+  int stagger_cycles;    // CTA b starts (b % 4) * stagger_cycles late (0 = off)
   long long* trace;      // optional [3][64] clock64 stamps written by CTA 0 (null in production)
 };
 
@@ -84,6 +85,20 @@ __device__ __forceinline__ float gelu_tanh_fast(float x) {
   asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(u));
   const float hx = 0.5f * x;
   return fmaf(hx, t, hx);
+}
+// Two GELUs at once on packed fp32 pairs (FMUL2/FFMA2): 4.5 issue slots per element instead of 8.
+__device__ __forceinline__ uint32_t gelu_tanh_bf16x2(f2t x) {
+  const f2t C0 = f2_pack(0.7978845608028654f, 0.7978845608028654f), C1 = f2_pack(0.035677408136300125f, 0.035677408136300125f);
+  const f2t HALF = f2_pack(0.5f, 0.5f);
+  const f2t u = f2_mul(x, f2_fma(f2_mul(x, x), C1, C0));
+  float u0, u1, t0, t1;
+  f2_unpack(u, u0, u1);
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(u0));
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(u1));
+  const f2t hx = f2_mul(x, HALF);
+  float r0, r1;
+  f2_unpack(f2_fma(hx, f2_pack(t0, t1), hx), r0, r1);
+  return pack_bf16(r0, r1);
 }
 }  // namespace bm
 
@@ -136,6 +151,12 @@ block_mlp_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
   __syncthreads();
   ptx::tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_ptr;
+  // All CTAs run the same tile schedule in lockstep, so their residual reads (E1) and writes (E3) would hit HBM as
+  // chip-wide bursts while the tensor pipes idle.  Starting the CTAs in `stagger` phase groups spreads that traffic.
+  if (p.stagger_cycles > 0) {
+    const long long t_end = clock64() + (long long)(blockIdx.x & 3) * p.stagger_cycles;
+    while (clock64() < t_end) {}
+  }
 
   if (warp == 0) {
     // =========================== TMA producer ===========================
@@ -343,6 +364,22 @@ block_mlp_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
         row = (long long)tile * BM + r;
         row_ok = row < p.M;
       }
+      // row of this thread in the NEXT tile of this CTA (for the residual L2 prefetch)
+      long long pf_row = 0;
+      bool pf_ok = false;
+      {
+        const int nt_ = tile + gridDim.x;
+        if (nt_ < p.num_tiles) {
+          if (p.y_cm) {
+            const int t = (nt_ % p.tiles_per_seq) * BM + r;
+            pf_row = (long long)(nt_ / p.tiles_per_seq) * p.T + t;
+            pf_ok = t < p.T;
+          } else {
+            pf_row = (long long)nt_ * BM + r;
+            pf_ok = pf_row < p.M;
+          }
+        }
+      }
       // ------------------------------------------------ E1: r1, LayerNorm2 -> xn (TMEM)
       // The residual half-row (128 fp32) is fetched into registers BEFORE waiting for the
       // out_proj accumulator, so its DRAM latency hides behind the y-tile load and G1.
@@ -419,18 +456,30 @@ block_mlp_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
         ptx::tc_fence_before_sync();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(hacc_free);   // the accumulator is in registers: fc1 of the next chunk may start
-        ptx::mbar_wait(&hbuf_free[b], (u & 1) ^ 1);
+        if (j < 4 && pf_ok) {
+          // next tile's residual half-row (512 B per thread, 32 float4 at 512 B stride): pull 8 of them towards L2 per
+          // chunk so that E1 of the next tile does not start with a 19 MB chip-wide HBM burst
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.res + ptx::r32_off(pf_row, hf * 128 + 4 * (8 * j + i))));
+        }
         const float* b1p = lc.b1 + ((j + rot) & (NCHUNK - 1)) * 128 + hf * 64;
         const uint32_t rowaddr = sHB + b * HB_BYTES + hf * KB_BYTES + r * 128;
+        // all the GELU math first (results in registers), THEN wait for fc2 of chunk j - 2 to release the HB buffer:
+        // that MMA group sits behind fc1 of chunk j in the tensor pipe, ~1000 cycles after this epilogue may start
+        uint32_t o[32];
 #pragma unroll
         for (int g = 0; g < 8; ++g) {
           const uint32_t* src = (g < 4) ? &a0[g * 8] : &a1[(g - 4) * 8];
-          float x[8];
 #pragma unroll
-          for (int jj = 0; jj < 8; ++jj) x[jj] = gelu_tanh_fast(__uint_as_float(src[jj]) + b1p[g * 8 + jj]);
+          for (int jj = 0; jj < 4; ++jj)
+            o[4 * g + jj] = gelu_tanh_bf16x2(f2_add(f2_packu(src[2 * jj], src[2 * jj + 1]), f2_pack(b1p[g * 8 + 2 * jj], b1p[g * 8 + 2 * jj + 1])));
+        }
+        ptx::mbar_wait(&hbuf_free[b], (u & 1) ^ 1);
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
           const uint32_t chunk = uint32_t(g) ^ swz;
-          ptx::st_shared_v4(rowaddr + chunk * 16, pack_bf16(x[0], x[1]), pack_bf16(x[2], x[3]), pack_bf16(x[4], x[5]),
-                            pack_bf16(x[6], x[7]));
+          ptx::st_shared_v4(rowaddr + chunk * 16, o[4 * g], o[4 * g + 1], o[4 * g + 2], o[4 * g + 3]);
         }
         ptx::fence_proxy_async_smem();
         __syncwarp();

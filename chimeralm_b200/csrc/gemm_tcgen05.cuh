@@ -71,6 +71,22 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
+// packed fp32x2 arithmetic (FMUL2 / FFMA2 / FADD2 on sm_100): one instruction per two elements
+typedef unsigned long long f2t;
+__device__ __forceinline__ f2t f2_pack(float lo, float hi) { f2t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ f2t f2_packu(uint32_t lo, uint32_t hi) { f2t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi)); return r; }
+__device__ __forceinline__ f2t f2_mul(f2t a, f2t b) { f2t d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ f2t f2_sub(f2t a, f2t b) { f2t d; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ f2t f2_fma(f2t a, f2t b, f2t c) { f2t d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ uint32_t f2_to_h2(f2t a) {   // two floats -> packed fp16 pair
+  float lo, hi;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a));
+  return pack_f16(lo, hi);
+}
+
+__device__ __forceinline__ f2t f2_add(f2t a, f2t b) { f2t d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ void f2_unpack(f2t a, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a)); }
+
 template <int BN, int STAGES, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmParams p) {

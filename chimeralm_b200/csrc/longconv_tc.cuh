@@ -91,18 +91,6 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
                : "memory");
 }
 
-// packed fp32x2 arithmetic (FMUL2 / FFMA2 / FADD2 on sm_100): one instruction per two elements
-typedef unsigned long long f2t;
-__device__ __forceinline__ f2t f2_pack(float lo, float hi) { f2t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
-__device__ __forceinline__ f2t f2_packu(uint32_t lo, uint32_t hi) { f2t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi)); return r; }
-__device__ __forceinline__ f2t f2_mul(f2t a, f2t b) { f2t d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
-__device__ __forceinline__ f2t f2_sub(f2t a, f2t b) { f2t d; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
-__device__ __forceinline__ f2t f2_fma(f2t a, f2t b, f2t c) { f2t d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
-__device__ __forceinline__ uint32_t f2_to_h2(f2t a) {   // two floats -> packed fp16 pair
-  float lo, hi;
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a));
-  return pack_f16(lo, hi);
-}
 __device__ __forceinline__ f2t h2_to_f2(uint32_t h) {
   const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&h));
   return f2_pack(f.x, f.y);

@@ -127,6 +127,10 @@ int clm_block_mlp_cm(clm_ctx* ctx, int layer, const void* d_y_cm, float* d_res, 
 /* Same, and CTA 0 records clock64() stamps of its producer / MMA / epilogue roles into
  * d_trace (int64 [3][64], zero-filled by the caller) - a timeline for tuning, not a product path. */
 int clm_block_mlp_trace(clm_ctx* ctx, int layer, const void* d_y, float* d_res, int M, long long* d_trace, void* stream);
+/* Production form of the fused block tail (channel-major y, optional normalised-xn output into the context's
+ * workspace) with the optional clock trace (d_trace may be NULL). */
+int clm_block_mlp_cm_trace(clm_ctx* ctx, int layer, const void* d_y_cm, float* d_res, int B, int T, int Tp, int write_xn,
+                           long long* d_trace, void* stream);
 /* Runtime switches: "fused_mlp" / "fused_in" (default 1) select the fused block kernels in clm_forward. */
 int clm_set_option(clm_ctx* ctx, const char* name, int value);
 /* out = (causal_long_conv(vx, k_layer) + bias_layer * vx) * x0 on channel-major bf16 [B][D][Tp]. */
