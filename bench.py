@@ -269,6 +269,14 @@ def main():
     if tp.exists() and B == BATCH and L == READ_LEN:
         traffic = {k: v for k, v in json.loads(tp.read_text()).items() if not k.startswith("_")}
 
+    conv_variant = eng.longconv_variant(T)
+    if conv_variant == "fft_tensor_core":
+        # Monarch FFT on tcgen05 (csrc/longconv_tc.cuh): per item (one channel of two reads) 16 MMAs 128x128x16 + 2 x 16 MMAs
+        # 128x256x16 + 32 MMAs 128xN7x16 (N7 = 80 when T > 8192, else 64); 256 * ceil(B / 2) items per launch.
+        n7 = 80 if T > 8192 else 64
+        item_flop = 2 * 16 * (16 * 128 * 128 + 2 * 16 * 128 * 256 + 32 * 128 * n7)
+        flop_per_tok["longconv"] = item_flop * 256 * ((B + 1) // 2) / tokens_per_step
+
     def roofline_of(name, ms, n):
         sec = ms / n / 1e3
         if name in flop_per_tok:
@@ -282,7 +290,7 @@ def main():
 
     roof = roofline_of(dom_name, dom_ms, dom_n)
     roof["peak_source"] = pk["src"]
-    if dom_name == "longconv":
+    if dom_name == "longconv" and conv_variant != "fft_tensor_core":
         roof["note"] = ("HBM roofline per SURVEY 8(d)'s compulsory-traffic model (1536 B/token/layer); the kernel itself is bound by "
                         "fp32 FFT instruction issue (ncu: issue-active ~50%, DRAM ~9%), see profiles/r1_v6_longconv_fast.txt")
     rooflines = {k: roofline_of(k, v[0], v[1]) for k, v in prof.items() if k in ("longconv", "block_mlp", "block_in", "gemm_score")}
@@ -310,6 +318,7 @@ def main():
         "gpu_launches": int(launches),
         "roofline": roof,
         "rooflines_top_kernels": rooflines,
+        "longconv_kernel": conv_variant,
         "kernel_ms_per_step": {k: v[0] / args.steps for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])},
         "cpu_baseline": cpu,
         "clocks": clocks,

@@ -1216,6 +1216,13 @@ int clm_longconv_tc(clm_ctx* c, int layer, const void* d_vx_f16, const void* d_x
                             (cudaStream_t)stream);
 }
 
+int clm_longconv_variant(const clm_ctx* c, int T) {
+  if (!c || !c->finalized || T <= 0) return -1;
+  if (c->fused_in && tc_conv_applies(c, T)) return 2;
+  const ConvPlan pl = plan_conv(T);
+  return (c->fast_conv && c->layers[0].gspecT[pl.logn] != nullptr) ? 1 : 0;
+}
+
 int clm_get_filter(clm_ctx* c, int layer, float* d_out, int L, void* stream) {
   if (!c || !c->finalized) return fail(c, CLM_ERR_STATE, "clm_get_filter before clm_finalize");
   if (layer < 0 || layer >= c->cfg.n_layer || L <= 0 || L > c->cfg.max_seq_len) return fail(c, CLM_ERR_INVALID, "clm_get_filter: bad argument");

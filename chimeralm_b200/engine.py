@@ -230,6 +230,10 @@ class Engine:
         self._check(rc, "clm_longconv_tc")
         return out
 
+    def longconv_variant(self, T: int) -> str:
+        """Name of the long-convolution kernel `forward` uses for reads of T tokens."""
+        return {0: "fft_fp32", 1: "fft_fp32_tuned", 2: "fft_tensor_core"}.get(self.lib.clm_longconv_variant(self.ctx, int(T)), "?")
+
     def get_filter(self, layer: int, L: int) -> torch.Tensor:
         out = torch.empty(self.cfg.d_model, L, dtype=torch.float32, device=self.device)
         self._check(self.lib.clm_get_filter(self.ctx, layer, C.c_void_p(out.data_ptr()), L, _stream_ptr(self.device)),

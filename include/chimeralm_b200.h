@@ -141,6 +141,9 @@ int clm_longconv(clm_ctx* ctx, int layer, const void* d_vx, const void* d_x0, vo
  * that d_vx holds fp16 values (what the fused in_proj kernel emits when this kernel follows). */
 int clm_longconv_tc(clm_ctx* ctx, int layer, const void* d_vx_f16, const void* d_x0, void* d_out, int B, int T, int Tp,
                     void* stream);
+/* Which long-convolution kernel clm_forward uses for reads of T tokens: 0 = first fp32 FFT kernel, 1 = tuned fp32
+ * FFT kernel, 2 = tensor-core FFT kernel; -1 before clm_finalize. */
+int clm_longconv_variant(const clm_ctx* ctx, int T);
 /* Same, and CTA 0 writes clock64() stamps into d_trace[2][64] (row 0 MMA issuer, row 1 epilogue warp). */
 int clm_longconv_tc_trace(clm_ctx* ctx, int layer, const void* d_vx_f16, const void* d_x0, void* d_out, int B, int T,
                           int Tp, long long* d_trace, void* stream);
