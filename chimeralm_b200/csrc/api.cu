@@ -519,14 +519,18 @@ int launch_longconv(clm_ctx* c, int layer, const __nv_bfloat16* vx, const __nv_b
   return fail(c, CLM_ERR_INVALID, "longconv: no plan for T=%d", T);
 }
 
+// Reads of 4097..8200 tokens (the N = 16384 transform class).  Below 8192 tokens the input rows past T are zero
+// filled (TMA bounds + block_in writes zeros for t in [T, Tp)), so the same kernel serves them.
 bool tc_conv_applies(const clm_ctx* c, int T) {
-  return c->tc_conv && T >= tc::C && T <= tc::C + LONGCONV_TAIL_MAX && c->layers[0].gtc != nullptr;
+  return c->tc_conv && T > tc::C / 2 && T <= tc::C + LONGCONV_TAIL_MAX && c->layers[0].gtc != nullptr;
 }
 
 // vx is fp16 here (block_in writes it that way when the tensor-core conv follows)
 int launch_longconv_tc(clm_ctx* c, int layer, const __half* vx, const __nv_bfloat16* x0, __nv_bfloat16* out, int B, int T,
                        int Tp, cudaStream_t st, long long* trace = nullptr) {
-  if (!tc_conv_applies(c, T)) return fail(c, CLM_ERR_INVALID, "longconv_tc: T=%d is outside [%d, %d]", T, tc::C, tc::C + LONGCONV_TAIL_MAX);
+  if (!tc_conv_applies(c, T)) return fail(c, CLM_ERR_INVALID, "longconv_tc: T=%d is outside (%d, %d]", T, tc::C / 2, tc::C + LONGCONV_TAIL_MAX);
+  if (T < tc::C && Tp % 128 != 0) return fail(c, CLM_ERR_INVALID, "longconv_tc: Tp must be a multiple of 128 when T < %d", tc::C);
+  const cuuint64_t n_rows = (cuuint64_t)std::min(64, Tp / 128);   // 128-token rows that exist per channel
   static bool attr_set = false;
   if (!attr_set) {
     CLM_CUDA(c, cudaFuncSetAttribute(longconv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_TOTAL));
@@ -536,7 +540,7 @@ int launch_longconv_tc(clm_ctx* c, int layer, const __half* vx, const __nv_bfloa
   const int D = c->cfg.d_model;
   CUtensorMap tm;
   {
-    cuuint64_t dims[3] = {128, 64, (cuuint64_t)B * D};
+    cuuint64_t dims[3] = {128, n_rows, (cuuint64_t)B * D};
     cuuint64_t strides[2] = {256, (cuuint64_t)Tp * 2};
     cuuint32_t box[3] = {64, 64, 1}, estr[3] = {1, 1, 1};
     CUresult r = c->encode_tiled(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<__half*>(vx), dims, strides, box, estr,
@@ -546,7 +550,7 @@ int launch_longconv_tc(clm_ctx* c, int layer, const __half* vx, const __nv_bfloa
   }
   CUtensorMap tmo;
   {
-    cuuint64_t dims[3] = {128, 64, (cuuint64_t)B * D};
+    cuuint64_t dims[3] = {128, n_rows, (cuuint64_t)B * D};
     cuuint64_t strides[2] = {256, (cuuint64_t)Tp * 2};
     cuuint32_t box[3] = {128, 64, 1}, estr[3] = {1, 1, 1};
     CUresult r = c->encode_tiled(&tmo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, out, dims, strides, box, estr,
@@ -556,7 +560,7 @@ int launch_longconv_tc(clm_ctx* c, int layer, const __half* vx, const __nv_bfloa
   }
   CUtensorMap tmg;
   {
-    cuuint64_t dims[3] = {128, 64, (cuuint64_t)B * D};
+    cuuint64_t dims[3] = {128, n_rows, (cuuint64_t)B * D};
     cuuint64_t strides[2] = {256, (cuuint64_t)Tp * 2};
     cuuint32_t box[3] = {128, 64, 1}, estr[3] = {1, 1, 1};
     CUresult r = c->encode_tiled(&tmg, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<__nv_bfloat16*>(x0), dims, strides, box, estr,
@@ -870,7 +874,7 @@ int clm_reserve(clm_ctx* c, int max_B, int max_T) {
   for (void* p : olds) dev_free(c, p);
   const int D = c->cfg.d_model;
   const size_t M = (size_t)max_B * max_T;
-  const int Tp = round_up(max_T, 64);
+  const int Tp = round_up(max_T, 128);
   const size_t CT = (size_t)max_B * D * Tp;
   int rc;
   if ((rc = dev_alloc(c, &c->R, (M + 160) * D))) return rc;  // R32 layout: whole 32-row groups + tile overhang
@@ -937,7 +941,7 @@ int clm_forward(clm_ctx* c, const void* d_ids, int ids_dtype, int B, int T, floa
   const int D = g.d_model;
   const long long M = (long long)B * T;
   if (M > 0x7fffffffLL) return fail(c, CLM_ERR_INVALID, "clm_forward: B*T too large");
-  const int Tp = round_up(T, 64);
+  const int Tp = round_up(T, 128);   // whole 128-token rows per channel: the tensor-core conv views a channel as [n1][128]
   const unsigned rows8 = (unsigned)((M + 7) / 8);
   const unsigned rows32 = (unsigned)((M + 31) / 32);
   int rc;

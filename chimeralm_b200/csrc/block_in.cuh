@@ -257,10 +257,14 @@ block_in_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
             const float* x1p = &uc[1][k * 8];
             const float* vp = &uc[2][k * 8];
             const uint32_t chunk = (uint32_t(s * 4 + k) ^ swz) << 4;
-            if (p.vx_f16)
-              ptx::st_shared_v4(sST + (0 * 2 + hf) * STAGE_BOX + rowoff + chunk, pack_f16(vp[0] * x1p[0], vp[1] * x1p[1]),
-                                pack_f16(vp[2] * x1p[2], vp[3] * x1p[3]), pack_f16(vp[4] * x1p[4], vp[5] * x1p[5]),
-                                pack_f16(vp[6] * x1p[6], vp[7] * x1p[7]));
+            if (p.vx_f16) {
+              // the tensor-core conv reads whole 128-token rows: positions past the end of the read must be ZERO
+              float m[8];
+#pragma unroll
+              for (int e8 = 0; e8 < 8; ++e8) m[e8] = (t0 + hf * 64 + s * 32 + k * 8 + e8 < p.T) ? vp[e8] * x1p[e8] : 0.f;
+              ptx::st_shared_v4(sST + (0 * 2 + hf) * STAGE_BOX + rowoff + chunk, pack_f16(m[0], m[1]), pack_f16(m[2], m[3]),
+                                pack_f16(m[4], m[5]), pack_f16(m[6], m[7]));
+            }
             else
               ptx::st_shared_v4(sST + (0 * 2 + hf) * STAGE_BOX + rowoff + chunk, pack_bf16(vp[0] * x1p[0], vp[1] * x1p[1]),
                                 pack_bf16(vp[2] * x1p[2], vp[3] * x1p[3]), pack_bf16(vp[4] * x1p[4], vp[5] * x1p[5]),
