@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdarg>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 #include <map>
@@ -140,10 +141,20 @@ int fail(clm_ctx* c, int code, const char* fmt, ...) {
       return fail(ctx, CLM_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
   } while (0)
 
+// CLM_SYNC_CHECK=1 in the environment: synchronise after every launch so an execution fault names its kernel.
+static const bool g_sync_check = [] { const char* e = getenv("CLM_SYNC_CHECK"); return e && e[0] == '1'; }();
+
 #define CLM_LAUNCH_CHECK(ctx, what)                                                                  \
   do {                                                                                               \
     cudaError_t e_ = cudaGetLastError();                                                             \
     if (e_ != cudaSuccess) return fail(ctx, CLM_ERR_CUDA, "launch %s failed: %s", what, cudaGetErrorString(e_)); \
+    if (g_sync_check) {                                                                              \
+      e_ = cudaDeviceSynchronize();                                                                  \
+      if (e_ != cudaSuccess) {                                                                       \
+        fprintf(stderr, "[chimeralm_b200] kernel %s faulted: %s\n", what, cudaGetErrorString(e_));   \
+        return fail(ctx, CLM_ERR_CUDA, "kernel %s faulted: %s", what, cudaGetErrorString(e_));       \
+      }                                                                                              \
+    }                                                                                                \
     (ctx)->launches++;                                                                               \
   } while (0)
 

@@ -179,9 +179,13 @@ longconv_tc_kernel(const __grid_constant__ CUtensorMap tmVX, const __grid_consta
   uint64_t* x2_full = bars + 8;   // step 5 complete
   uint64_t* bt_full = bars + 9;   // E3 wrote BT
   uint64_t* o_full = bars + 10;   // step 7 complete
-  uint64_t* g_full = bars + 11;   // x0 gate tile landed in the z buffer (TMA, issued once step 1 has consumed z)
+  // [2] x0 gate tile landed in z buffer `buf` (TMA issued by ONE epilogue thread once step 1 has consumed z).  Per buffer on
+  // purpose: that thread may run a whole E4 ahead of a slower warp (the one doing the tail-token loads), and with a single
+  // barrier it could complete the NEXT item's phase before the slow warp has observed this one - the waiter would then be
+  // lapped and the kernel would dead-lock (seen as a rare launch failure from the bounded wait).
+  uint64_t* g_full = bars + 14;
   uint64_t* out_ready = bars + 12; // [2] E4 wrote the output tile into the z buffer (8 warp arrivals)
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 14);
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 16);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // contiguous item ranges per CTA: consecutive items share the channel (and its spectrum lines in L2)
@@ -204,7 +208,7 @@ longconv_tc_kernel(const __grid_constant__ CUtensorMap tmVX, const __grid_consta
     ptx::mbar_init(x_full, 1); ptx::mbar_init(p1_full, 8);
     ptx::mbar_init(y_full, 1); ptx::mbar_init(p2_full, 8);
     ptx::mbar_init(x2_full, 1); ptx::mbar_init(bt_full, 8);
-    ptx::mbar_init(o_full, 1); ptx::mbar_init(g_full, 1);
+    ptx::mbar_init(o_full, 1); ptx::mbar_init(&g_full[0], 1); ptx::mbar_init(&g_full[1], 1);
     ptx::fence_mbar_init();
   } else if (warp == 1) {
     ptx::tmem_alloc<512>(tmem_ptr);
@@ -369,9 +373,9 @@ longconv_tc_kernel(const __grid_constant__ CUtensorMap tmVX, const __grid_consta
       ptx::tc_fence_after_sync();
       if (tr) stamp(1);
       if (threadIdx.x == 64) {   // z has been consumed: its buffer now receives the x0 gate tile [n1][n2] of both reads
-        ptx::mbar_expect_tx(g_full, has1 ? Z_BYTES : Z_BYTES / 2);
-        ptx::tma_load_3d(zb, &tmX0, g_full, 0, 0, b0 * p.D + ch);
-        if (has1) ptx::tma_load_3d(zb + 16384, &tmX0, g_full, 0, 0, b1 * p.D + ch);
+        ptx::mbar_expect_tx(&g_full[buf], has1 ? Z_BYTES : Z_BYTES / 2);
+        ptx::tma_load_3d(zb, &tmX0, &g_full[buf], 0, 0, b0 * p.D + ch);
+        if (has1) ptx::tma_load_3d(zb + 16384, &tmX0, &g_full[buf], 0, 0, b1 * p.D + ch);
       }
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
@@ -504,7 +508,7 @@ longconv_tc_kernel(const __grid_constant__ CUtensorMap tmVX, const __grid_consta
       ptx::mbar_wait(o_full, ph);
       ptx::tc_fence_after_sync();
       if (tr) stamp(1);
-      ptx::mbar_wait(g_full, ph);
+      ptx::mbar_wait(&g_full[buf], (it >> 1) & 1);
       unsigned short* st0 = reinterpret_cast<unsigned short*>(zb) + r;   // [n1][n2] bf16, 256 B per n1 row: gate in, product out
 #pragma unroll
       for (int h2 = 0; h2 < 2; ++h2) {

@@ -153,3 +153,32 @@ def test_mixed_lengths_bucketed(engine, state_dict):
     logits = engine.forward(ids).cpu()
     ref = O.forward(state_dict, torch.tensor(ids_ref), CFG)
     assert (logits - ref).abs().max().item() <= LOGIT_TOL
+
+
+def test_repeated_forward_under_copy_traffic_is_stable_and_deterministic(state_dict):
+    """Stress for the persistent kernels' mbarrier protocols (a lapped single-phase barrier in the tensor-core conv once
+    showed up only as a rare launch failure in the BAM predict loop): many K2-shaped forwards back to back while another
+    stream keeps the copy engines and HBM busy; every result must be bit-identical to the first."""
+    from chimeralm_b200.engine import Engine
+
+    B, T = 32, 8193
+    eng = Engine(state_dict, device=0, max_batch=B, max_tokens=T)
+    try:
+        ids = _ids(B, T, seed=7).to(torch.uint8).cuda()
+        assert eng.longconv_variant(T) == "fft_tensor_core"
+        first = eng.forward(ids).clone()
+        side = torch.cuda.Stream()
+        host = torch.empty(64 << 20, dtype=torch.uint8).pin_memory()
+        dev = torch.empty(64 << 20, dtype=torch.uint8, device="cuda")
+        for i in range(150):
+            if i % 3 == 0:
+                with torch.cuda.stream(side):
+                    dev.copy_(host, non_blocking=True)
+                    host.copy_(dev, non_blocking=True)
+            out = eng.forward(ids)
+            if i % 25 == 24:
+                assert torch.equal(out, first), i
+        torch.cuda.synchronize()
+        assert torch.equal(out, first)
+    finally:
+        eng.close()
