@@ -113,6 +113,10 @@ struct clm_ctx {
   int mlp_stagger = 0;    // block_mlp: CTA phase stagger in cycles (0 = off)
   bool tc_conv = true;    // tensor-core FFT long convolution for reads of 8192..8200 tokens (needs fused_in)
   __half* tc_S = nullptr; // shared-memory image of the DFT constant stack (longconv_tc)
+  bool tc_chunked = true; // tensor-core conv also for reads longer than 8200 tokens (overlap-add over 8192-token chunks)
+  int tc_nseg = 0;        // filter segments of 8192 taps with a spectrum table
+  float* tc_scratch = nullptr;
+  size_t tc_scratch_floats = 0;
   bool mlp_2cta = false;  // CTA-pair (cta_group::2) version of the fused block tail
   bool y_channel_major = true;  // block_mlp reads the conv output channel-major (MN-major UMMA operand): no transpose
   // debug
@@ -532,21 +536,36 @@ int launch_longconv(clm_ctx* c, int layer, const __nv_bfloat16* vx, const __nv_b
 
 // Reads of 4097..8200 tokens (the N = 16384 transform class).  Below 8192 tokens the input rows past T are zero
 // filled (TMA bounds + block_in writes zeros for t in [T, Tp)), so the same kernel serves them.
+struct TcPlan { int nc, nt; };   // transforms (chunks of 8192 tokens) per read, tail tokens finished by direct products
+TcPlan tc_plan(int T) {
+  const int rem = T % tc::C;
+  if (T > tc::C && rem > 0 && rem <= LONGCONV_TAIL_MAX) return {T / tc::C, rem};
+  return {std::max(1, (T + tc::C - 1) / tc::C), 0};
+}
+size_t tc_scratch_per_cta(int nc) { return nc > 1 ? (size_t)(nc - 1) * 2 * tc::N + 2 * tc::C : 0; }   // floats
+
 bool tc_conv_applies(const clm_ctx* c, int T) {
-  return c->tc_conv && T > tc::C / 2 && T <= tc::C + LONGCONV_TAIL_MAX && c->layers[0].gtc != nullptr;
+  if (!c->tc_conv || T <= tc::C / 2 || c->layers[0].gtc == nullptr) return false;
+  const TcPlan pl = tc_plan(T);
+  return pl.nc == 1 || (c->tc_chunked && pl.nc <= c->tc_nseg);
 }
 
 // vx is fp16 here (block_in writes it that way when the tensor-core conv follows)
 int launch_longconv_tc(clm_ctx* c, int layer, const __half* vx, const __nv_bfloat16* x0, __nv_bfloat16* out, int B, int T,
                        int Tp, cudaStream_t st, long long* trace = nullptr) {
-  if (!tc_conv_applies(c, T)) return fail(c, CLM_ERR_INVALID, "longconv_tc: T=%d is outside (%d, %d]", T, tc::C / 2, tc::C + LONGCONV_TAIL_MAX);
-  if (T < tc::C && Tp % 128 != 0) return fail(c, CLM_ERR_INVALID, "longconv_tc: Tp must be a multiple of 128 when T < %d", tc::C);
-  const cuuint64_t n_rows = (cuuint64_t)std::min(64, Tp / 128);   // 128-token rows that exist per channel
+  if (!tc_conv_applies(c, T)) return fail(c, CLM_ERR_INVALID, "longconv_tc: no tensor-core plan for T=%d", T);
+  const TcPlan pl = tc_plan(T);
+  const bool whole_rows = T >= tc::C && pl.nc == 1;   // every 128-token row the kernel touches lies inside [0, Tp)
+  if (!whole_rows && Tp % 128 != 0) return fail(c, CLM_ERR_INVALID, "longconv_tc: Tp must be a multiple of 128 for T=%d", T);
+  const cuuint64_t n_rows = (cuuint64_t)(whole_rows ? std::min(64, Tp / 128) : Tp / 128);   // 128-token rows per channel
   static bool attr_set = false;
   if (!attr_set) {
-    CLM_CUDA(c, cudaFuncSetAttribute(longconv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_TOTAL));
+    CLM_CUDA(c, cudaFuncSetAttribute(longconv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_TOTAL));
+    CLM_CUDA(c, cudaFuncSetAttribute(longconv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_TOTAL));
     attr_set = true;
   }
+  if (tc_scratch_per_cta(pl.nc) * c->num_sms > c->tc_scratch_floats)
+    return fail(c, CLM_ERR_STATE, "longconv_tc: scratch too small for T=%d; call clm_reserve with max_T >= %d", T, T);
   LayerW& L = c->layers[layer];
   const int D = c->cfg.d_model;
   CUtensorMap tm;
@@ -583,9 +602,12 @@ int launch_longconv_tc(clm_ctx* c, int layer, const __half* vx, const __nv_bfloa
   p.T = T; p.vx = vx; p.k = L.k; p.dbias = L.fbias; p.Lk = c->Lk;
   p.x0 = x0; p.out = out; p.S = reinterpret_cast<const uint4*>(c->tc_S); p.G = reinterpret_cast<const uint4*>(L.gtc);
   p.B = B; p.D = D; p.Tp = Tp; p.n_pairs = (B + 1) / 2; p.n_items = D * p.n_pairs; p.trace = trace;
+  p.n_chunks = pl.nc; p.nt = pl.nt; p.scratch = c->tc_scratch; p.scratch_per_cta = (long long)tc_scratch_per_cta(pl.nc);
+  p.g_seg_stride = (long long)D * (tc::N / 4);
   const int grid = std::min(p.n_items, c->num_sms);
-  longconv_tc_kernel<<<grid, tc::THREADS, tc::SMEM_TOTAL, st>>>(tm, tmo, tmg, p);
-  CLM_LAUNCH_CHECK(c, "longconv_tc");
+  if (pl.nc > 1) longconv_tc_kernel<true><<<grid, tc::THREADS, tc::SMEM_TOTAL, st>>>(tm, tmo, tmg, p);
+  else longconv_tc_kernel<false><<<grid, tc::THREADS, tc::SMEM_TOTAL, st>>>(tm, tmo, tmg, p);
+  CLM_LAUNCH_CHECK(c, pl.nc > 1 ? "longconv_tc_chunked" : "longconv_tc");
   return 0;
 }
 
@@ -823,9 +845,10 @@ int clm_finalize(clm_ctx* c) {
     if ((rc = spectrum_fast_t<13>(c, L))) return rc;
     if ((rc = spectrum_fast_t<14>(c, L))) return rc;
     if (c->cfg.max_seq_len >= tc::C) {
-      if ((rc = dev_alloc(c, &L.gtc, (size_t)D * tc::N))) return rc;
+      c->tc_nseg = (c->cfg.max_seq_len + tc::C - 1) / tc::C;   // one spectrum table per 8192-tap filter segment
+      if ((rc = dev_alloc(c, &L.gtc, (size_t)c->tc_nseg * D * tc::N))) return rc;
       CLM_CUDA(c, cudaFuncSetAttribute(tc::spectrum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::N * (int)sizeof(float2)));
-      tc::spectrum_kernel<<<D, 256, tc::N * sizeof(float2)>>>(L.k, c->Lk, L.fbias, L.gtc);
+      tc::spectrum_kernel<<<dim3(D, c->tc_nseg), 256, tc::N * sizeof(float2)>>>(L.k, c->Lk, c->cfg.max_seq_len, L.fbias, L.gtc);
       CLM_LAUNCH_CHECK(c, "tc_spectrum");
     }
   }
@@ -911,6 +934,14 @@ int clm_reserve(clm_ctx* c, int max_B, int max_T) {
     const size_t worst = (size_t)c->num_sms * ((max_T + C - 1) / C) * ((size_t)1 << LONGCONV_MAX_LOGN) * sizeof(float2);
     c->scratch_bytes = std::max(c->scratch_bytes, worst);
     if ((rc = dev_alloc(c, reinterpret_cast<uint8_t**>(&c->scratch), c->scratch_bytes))) return rc;
+  }
+  {
+    const size_t need = tc_scratch_per_cta(tc_plan(max_T).nc) * c->num_sms;
+    if (need > c->tc_scratch_floats) {
+      dev_free(c, c->tc_scratch);
+      if ((rc = dev_alloc(c, &c->tc_scratch, need))) return rc;
+      c->tc_scratch_floats = need;
+    }
   }
   if ((rc = dev_alloc(c, &c->st_offsets, (size_t)max_B + 1))) return rc;
   if ((rc = dev_alloc(c, &c->st_ids, M))) return rc;
@@ -1133,6 +1164,7 @@ int clm_set_option(clm_ctx* c, const char* name, int value) {
   else if (n == "fused_in") c->fused_in = value != 0;
   else if (n == "fast_conv") c->fast_conv = value != 0;
   else if (n == "tc_conv") c->tc_conv = value != 0;
+  else if (n == "tc_chunked") c->tc_chunked = value != 0;
   else if (n == "mlp_stagger") c->mlp_stagger = value;
   else if (n == "y_channel_major") c->y_channel_major = value != 0;
   else if (n == "mlp_2cta") c->mlp_2cta = value != 0;
@@ -1213,11 +1245,23 @@ int clm_longconv(clm_ctx* c, int layer, const void* d_vx, const void* d_x0, void
                          c->scratch, c->scratch_bytes, (cudaStream_t)stream);
 }
 
+int ensure_tc_scratch(clm_ctx* c, int T) {
+  const size_t need = tc_scratch_per_cta(tc_plan(T).nc) * c->num_sms;
+  if (need <= c->tc_scratch_floats) return 0;
+  CLM_CUDA(c, cudaDeviceSynchronize());
+  dev_free(c, c->tc_scratch);
+  int rc = dev_alloc(c, &c->tc_scratch, need);
+  if (rc) return rc;
+  c->tc_scratch_floats = need;
+  return 0;
+}
+
 int clm_longconv_tc_trace(clm_ctx* c, int layer, const void* d_vx_f16, const void* d_x0, void* d_out, int B, int T, int Tp,
                           long long* d_trace, void* stream) {
   if (!c || !c->finalized) return fail(c, CLM_ERR_STATE, "clm_longconv_tc_trace before clm_finalize");
   if (layer < 0 || layer >= c->cfg.n_layer || !d_vx_f16 || !d_x0 || !d_out || !d_trace || B <= 0 || Tp < T || Tp % 64 != 0)
     return fail(c, CLM_ERR_INVALID, "clm_longconv_tc_trace: bad argument");
+  if (int rc = ensure_tc_scratch(c, T)) return rc;
   return launch_longconv_tc(c, layer, (const __half*)d_vx_f16, (const __nv_bfloat16*)d_x0, (__nv_bfloat16*)d_out, B, T, Tp,
                             (cudaStream_t)stream, d_trace);
 }
@@ -1227,6 +1271,7 @@ int clm_longconv_tc(clm_ctx* c, int layer, const void* d_vx_f16, const void* d_x
   if (!c || !c->finalized) return fail(c, CLM_ERR_STATE, "clm_longconv_tc before clm_finalize");
   if (layer < 0 || layer >= c->cfg.n_layer || !d_vx_f16 || !d_x0 || !d_out || B <= 0 || Tp < T || Tp % 64 != 0)
     return fail(c, CLM_ERR_INVALID, "clm_longconv_tc: bad argument");
+  if (int rc = ensure_tc_scratch(c, T)) return rc;
   return launch_longconv_tc(c, layer, (const __half*)d_vx_f16, (const __nv_bfloat16*)d_x0, (__nv_bfloat16*)d_out, B, T, Tp,
                             (cudaStream_t)stream);
 }

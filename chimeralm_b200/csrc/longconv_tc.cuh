@@ -51,6 +51,12 @@ struct LongConvTcParams {
   const float* k;            // [D][Lk] filter taps
   const float* dbias;        // [D] bias skip (folded into tap 0)
   long long Lk;
+  // chunked mode (reads longer than 8200 tokens, overlap-add over chunks of 8192 tokens): n_chunks > 1
+  int n_chunks;              // transforms per item
+  int nt;                    // tail tokens after the last chunk (0..LONGCONV_TAIL_MAX), finished by direct products
+  float* scratch;            // per CTA: (n_chunks - 1) parked spectra (16384 float2 each) + carry (2 x 8192 float)
+  long long scratch_per_cta; // floats
+  long long g_seg_stride;    // uint4 between the spectrum tables of consecutive filter segments
   long long* trace;          // optional [2][64] clock64 stamps of CTA 0: row 0 = MMA issuer, row 1 = epilogue warp 2
 };
 
@@ -116,25 +122,28 @@ __global__ void build_s_kernel(__half* __restrict__ img) {
 // {re(k2, k2+1), im(k2, k2+1), re(k2+2, k2+3), im(k2+2, k2+3)} at uint4 index
 //   (((ch * 4 + k1 / 32) * 2 + k2 / 64) * 16 + (k2 % 64) / 4) * 32 + k1 % 32
 // so that a warp of 32 consecutive k1 reads 512 contiguous bytes per 16-byte load.
-__global__ void __launch_bounds__(256) spectrum_kernel(const float* __restrict__ k, long long Lk,
-                                                       const float* __restrict__ dbias, __half2* __restrict__ G) {
+__global__ void __launch_bounds__(256) spectrum_kernel(const float* __restrict__ k, long long Lk, int n_taps,
+                                                       const float* __restrict__ dbias, __half2* __restrict__ G_all) {
   extern __shared__ float2 sm_a[];            // A[k1][n2], 128 KB
   __shared__ float2 w128[128];
-  const int ch = blockIdx.x;
-  const float* kc = k + (long long)ch * Lk;
+  // blockIdx.y = filter segment: taps [seg * C, (seg + 1) * C) (zero past n_taps); the bias skip lives in tap 0 only
+  const int ch = blockIdx.x, seg = blockIdx.y;
+  const float* kc = k + (long long)ch * Lk + (long long)seg * C;
+  const int n_here = max(0, min(C, n_taps - seg * C));
+  __half2* G = G_all + (size_t)seg * gridDim.x * N;
   if (threadIdx.x < 128) {
     float s, c;
     sincospif(-2.0f * float(threadIdx.x) / 128.0f, &s, &c);
     w128[threadIdx.x] = make_float2(c, s);
   }
   __syncthreads();
-  const float tap0 = kc[0] + dbias[ch];
+  const float tap0 = n_here > 0 ? kc[0] + (seg == 0 ? dbias[ch] : 0.f) : 0.f;
   for (int o = threadIdx.x; o < N; o += blockDim.x) {
     const int k1 = o / R, n2 = o % R;
     float ar = 0.f, ai = 0.f;
     for (int n1 = 0; n1 < 64; ++n1) {
       const int t = 128 * n1 + n2;
-      const float v = t == 0 ? tap0 : kc[t];
+      const float v = t == 0 ? tap0 : (t < n_here ? kc[t] : 0.f);
       const float2 w = w128[(k1 * n1) & 127];
       ar = fmaf(v, w.x, ar);
       ai = fmaf(v, w.y, ai);
@@ -163,6 +172,7 @@ __global__ void __launch_bounds__(256) spectrum_kernel(const float* __restrict__
 
 }  // namespace tc
 
+template <bool CH>   // CH: chunked mode (n_chunks > 1)
 __global__ void __launch_bounds__(tc::THREADS, 1)
 longconv_tc_kernel(const __grid_constant__ CUtensorMap tmVX, const __grid_constant__ CUtensorMap tmOut,
                    const __grid_constant__ CUtensorMap tmX0, LongConvTcParams p) {
@@ -191,6 +201,10 @@ longconv_tc_kernel(const __grid_constant__ CUtensorMap tmVX, const __grid_consta
   // contiguous item ranges per CTA: consecutive items share the channel (and its spectrum lines in L2)
   const int per = (p.n_items + gridDim.x - 1) / gridDim.x;
   const int item0 = blockIdx.x * per, item1 = min(p.n_items, item0 + per);
+  // work units = (item, chunk); all the pipeline state (buffers, barrier phases) is indexed by the unit counter `it`
+  const int NC = CH ? p.n_chunks : 1;
+  const int n_units = max(0, item1 - item0) * NC;
+  constexpr int ZIM = CH ? 128 : ZIM_COL;   // step 7: z'_im column offset inside Y
   long long* trace = (p.trace && blockIdx.x == 0) ? p.trace : nullptr;
   int trace_n = 0;
   auto stamp = [&](int role) {
@@ -226,27 +240,27 @@ longconv_tc_kernel(const __grid_constant__ CUtensorMap tmVX, const __grid_consta
     // -> z tile of item i + 2.  This thread issues the z loads and the output stores; the gate load is issued by an
     // epilogue thread, which is the one that knows when step 1 has finished.
     if (lane == 0) {
-      const int n_it = item1 - item0;
-      for (int it = 0; it < n_it + 2; ++it) {
+      for (int it = 0; it < n_units + 2; ++it) {
         const uint32_t buf = it & 1;
         uint8_t* z = smem + OFF_Z + buf * Z_BYTES;
-        if (it >= 2) {   // retire item it - 2: its output tile is complete in z
-          const int item = item0 + it - 2;
+        if (it >= 2) {   // retire unit it - 2: its output tile is complete in z
+          const int un = it - 2, item = item0 + un / NC, c = un % NC;
           const int ch = item / p.n_pairs, pr = item % p.n_pairs;
-          ptx::mbar_wait(&out_ready[buf], ((it - 2) >> 1) & 1);
-          ptx::tma_store_3d(&tmOut, z, 0, 0, 2 * pr * p.D + ch);
-          if (2 * pr + 1 < p.B) ptx::tma_store_3d(&tmOut, z + 16384, 0, 0, (2 * pr + 1) * p.D + ch);
+          ptx::mbar_wait(&out_ready[buf], (un >> 1) & 1);
+          ptx::tma_store_3d(&tmOut, z, 0, 64 * c, 2 * pr * p.D + ch);
+          if (2 * pr + 1 < p.B) ptx::tma_store_3d(&tmOut, z + 16384, 0, 64 * c, (2 * pr + 1) * p.D + ch);
           ptx::tma_store_commit();
           ptx::tma_store_wait_read<0>();
         }
-        if (it < n_it) {
-          const int item = item0 + it;
+        if (it < n_units) {
+          const int item = item0 + it / NC, c = it % NC;
           const int ch = item / p.n_pairs, pr = item % p.n_pairs;
           if (it >= 2) ptx::mbar_wait(&z_empty[buf], ((it - 2) >> 1) & 1);   // long since true
           ptx::mbar_expect_tx(&z_full[buf], Z_BYTES);
           for (int part = 0; part < 2; ++part) {
             const int row = (2 * pr + part) * p.D + ch;    // reads past B are out of bounds -> zero filled
-            for (int a = 0; a < 2; ++a) ptx::tma_load_3d(z + part * 16384 + a * 8192, &tmVX, &z_full[buf], 64 * a, 0, row);
+            for (int a = 0; a < 2; ++a)
+              ptx::tma_load_3d(z + part * 16384 + a * 8192, &tmVX, &z_full[buf], 64 * a, 64 * c, row);
           }
         }
       }
@@ -259,14 +273,13 @@ longconv_tc_kernel(const __grid_constant__ CUtensorMap tmVX, const __grid_consta
       constexpr uint32_t id35 = idesc(256, false, false);  // steps 3, 5: A from TMEM, B K-major, N = 256
       // step 7: A MN-major, B K-major; N = 64 output rows n1, or 80 when tail tokens are wanted (row n1 = 64 = outputs
       // 8192..8319 of the same transform)
-      const uint32_t id7 = p.T > C ? idesc(80, true, false) : idesc(64, true, false);
+      const uint32_t id7 = CH ? idesc(128, true, false) : (p.nt > 0 ? idesc(80, true, false) : idesc(64, true, false));
       const uint32_t sS = ptx::smem_u32(smem + OFF_S), sBT = ptx::smem_u32(smem + OFF_BT);
       uint64_t dS = ptx::smem_desc_k_sw128(sS);
       auto s_desc = [&](int row0, int kk) -> uint64_t {    // constant rows row0.., K index kk (multiple of 16)
         return dS + (uint64_t)(((kk >> 6) * S_PANEL + row0 * 128 + (kk & 63) * 2) >> 4);
       };
-      uint32_t it = 0;
-      for (int item = item0; item < item1; ++item, ++it) {
+      for (uint32_t it = 0; it < (uint32_t)n_units; ++it) {
         const uint32_t buf = it & 1, zph = (it >> 1) & 1, ph = it & 1;
         const uint32_t sZ = ptx::smem_u32(smem + OFF_Z + buf * Z_BYTES);
         asm volatile("" : "+l"(dS));   // keeps ptxas from tabulating every descriptor in local memory across items
@@ -326,7 +339,7 @@ longconv_tc_kernel(const __grid_constant__ CUtensorMap tmVX, const __grid_consta
             const int rows = o == 0 ? (part == 0 ? ROW_FRE : ROW_FIM) : (part == 0 ? ROW_NFIM : ROW_FRE);
 #pragma unroll
             for (int j = 0; j < 8; ++j)
-              ptx::umma_f16(TM_Y + o * ZIM_COL, dBT + (uint64_t)(((part * 128 + 16 * j) * 128) >> 4), s_desc(rows, 16 * j), id7,
+              ptx::umma_f16(TM_Y + o * ZIM, dBT + (uint64_t)(((part * 128 + 16 * j) * 128) >> 4), s_desc(rows, 16 * j), id7,
                             (part | j) != 0);
           }
         }
@@ -346,11 +359,16 @@ longconv_tc_kernel(const __grid_constant__ CUtensorMap tmVX, const __grid_consta
 #pragma unroll
     for (int u = 0; u < 4; ++u) sincospif(-2.0f * float((r * (64 * hf + 16 * u)) % N) / float(N), &seed[u].y, &seed[u].x);
     const bool tr = trace && warp == 2 && lane == 0;
-    const int nt = p.T - C;   // tail tokens, 0..LONGCONV_TAIL_MAX
+    const int nt = p.nt;      // tail tokens after the last chunk, 0..LONGCONV_TAIL_MAX
     const float2 w2 = make_float2(wstep.x * wstep.x - wstep.y * wstep.y, 2.0f * wstep.x * wstep.y);
-    uint32_t it = 0;
-    for (int item = item0; item < item1; ++item, ++it) {
+    // chunked mode: this CTA's scratch = parked spectra of chunks 0..NC-2 (float4 = two complex values; a warp's 32 lanes
+    // write 512 contiguous bytes) followed by the carry (second halves of the last inverse transform, [2][64][128] fp32)
+    float4* park = reinterpret_cast<float4*>(p.scratch + (long long)blockIdx.x * p.scratch_per_cta);
+    float* carry = p.scratch + (long long)blockIdx.x * p.scratch_per_cta + (long long)(NC - 1) * 2 * N;
+    const int e_warp = warp - 2;
+    for (uint32_t it = 0; it < (uint32_t)n_units; ++it) {
       const uint32_t ph = it & 1, buf = it & 1;
+      const int item = item0 + (int)it / NC, c = (int)it % NC;   // c: chunk (tokens [c C, c C + C))
       const int ch = item / p.n_pairs, pr = item % p.n_pairs;
       uint8_t* zb = smem + OFF_Z + buf * Z_BYTES;
       const int b0 = 2 * pr, b1 = 2 * pr + 1;
@@ -374,8 +392,8 @@ longconv_tc_kernel(const __grid_constant__ CUtensorMap tmVX, const __grid_consta
       if (tr) stamp(1);
       if (threadIdx.x == 64) {   // z has been consumed: its buffer now receives the x0 gate tile [n1][n2] of both reads
         ptx::mbar_expect_tx(&g_full[buf], has1 ? Z_BYTES : Z_BYTES / 2);
-        ptx::tma_load_3d(zb, &tmX0, &g_full[buf], 0, 0, b0 * p.D + ch);
-        if (has1) ptx::tma_load_3d(zb + 16384, &tmX0, &g_full[buf], 0, 0, b1 * p.D + ch);
+        ptx::tma_load_3d(zb, &tmX0, &g_full[buf], 0, 64 * c, b0 * p.D + ch);
+        if (has1) ptx::tma_load_3d(zb + 16384, &tmX0, &g_full[buf], 0, 64 * c, b1 * p.D + ch);
       }
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
@@ -406,7 +424,7 @@ longconv_tc_kernel(const __grid_constant__ CUtensorMap tmVX, const __grid_consta
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(p1_full);
       if (tr) stamp(1);
-      // ------------------------------------------------ E2: P2 = fp16(S .* G')
+      // ------------------------------------------------ E2: P2 = fp16(sum_j S_{c-j} .* G'_j)   (j = 0 only when not chunked)
       const uint4* gp = p.G + ((((size_t)ch * 4 + q) * 2 + hf) * 16) * 32 + lane;
       uint4 g[16];
 #pragma unroll
@@ -421,6 +439,7 @@ longconv_tc_kernel(const __grid_constant__ CUtensorMap tmVX, const __grid_consta
         tmem_ld16(TM_Y + lane_addr + col, xr);
         tmem_ld16(TM_Y + lane_addr + 128 + col, xi);
         ptx::tmem_ld_wait();
+        f2t ar[8], ai[8];   // products for elements (2 m, 2 m + 1)
 #pragma unroll
         for (int v = 0; v < 4; ++v) {
           const uint32_t gw[4] = {g[4 * u + v].x, g[4 * u + v].y, g[4 * u + v].z, g[4 * u + v].w};
@@ -429,9 +448,47 @@ longconv_tc_kernel(const __grid_constant__ CUtensorMap tmVX, const __grid_consta
             const int idx = 4 * v + 2 * hp;
             const f2t GR = h2_to_f2(gw[2 * hp]), GI = h2_to_f2(gw[2 * hp + 1]);
             const f2t XR = f2_packu(xr[idx], xr[idx + 1]), XI = f2_packu(xi[idx], xi[idx + 1]);
-            w[idx / 2] = f2_to_h2(f2_sub(f2_mul(XR, GR), f2_mul(XI, GI)));
-            w[8 + idx / 2] = f2_to_h2(f2_fma(XR, GI, f2_mul(XI, GR)));
+            ar[idx / 2] = f2_sub(f2_mul(XR, GR), f2_mul(XI, GI));
+            ai[idx / 2] = f2_fma(XR, GI, f2_mul(XI, GR));
           }
+        }
+        if constexpr (CH) {
+          // park this chunk's spectrum for the later chunks, then add the earlier chunks' spectra times the later filter
+          // segments: W_c = sum_j S_{c-j} G_j (overlap-add in the frequency domain, one inverse transform per chunk)
+          const size_t slot = (((size_t)u * 8) * 8 + e_warp) * 32 + lane;   // + v * 256 per float4, + chunk * 8192
+          if (c < NC - 1) {
+#pragma unroll
+            for (int v = 0; v < 8; ++v)
+              park[(size_t)c * 8192 + slot + (size_t)v * 256] =
+                  make_float4(__uint_as_float(xr[2 * v]), __uint_as_float(xi[2 * v]), __uint_as_float(xr[2 * v + 1]), __uint_as_float(xi[2 * v + 1]));
+          }
+#pragma unroll 1
+          for (int j = 1; j <= c; ++j) {
+            const uint4* gj = gp + (size_t)j * p.g_seg_stride + (4 * u) * 32;
+            uint4 gq[4];
+            float4 sv[8];
+#pragma unroll
+            for (int v = 0; v < 4; ++v) gq[v] = __ldg(gj + v * 32);
+#pragma unroll
+            for (int v = 0; v < 8; ++v) sv[v] = park[(size_t)(c - j) * 8192 + slot + (size_t)v * 256];
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+              const uint32_t gw[4] = {gq[v].x, gq[v].y, gq[v].z, gq[v].w};
+#pragma unroll
+              for (int hp = 0; hp < 2; ++hp) {
+                const int m = 2 * v + hp;   // elements 2 m, 2 m + 1
+                const f2t GR = h2_to_f2(gw[2 * hp]), GI = h2_to_f2(gw[2 * hp + 1]);
+                const f2t XR = f2_pack(sv[m].x, sv[m].z), XI = f2_pack(sv[m].y, sv[m].w);
+                ar[m] = f2_sub(f2_fma(XR, GR, ar[m]), f2_mul(XI, GI));
+                ai[m] = f2_fma(XI, GR, f2_fma(XR, GI, ai[m]));
+              }
+            }
+          }
+        }
+#pragma unroll
+        for (int m = 0; m < 8; ++m) {
+          w[m] = f2_to_h2(ar[m]);
+          w[8 + m] = f2_to_h2(ai[m]);
         }
         tmem_st8(TM_Y + lane_addr + col, w);
         tmem_st8(TM_Y + lane_addr + col + 8, w + 8);
@@ -485,25 +542,24 @@ longconv_tc_kernel(const __grid_constant__ CUtensorMap tmVX, const __grid_consta
       if (lane == 0) ptx::mbar_arrive(bt_full);
       if (tr) stamp(1);
       // ------------------------------------------------ E4: out = z' * x0, staged in the (free) z buffer, TMA store
-      // tail tokens t = C + j (j < nt): the same transform's outputs 8192 + j (row n1 = 64, lane j) hold the taps
-      // 0..8191 part; what is missing are the <= 2 (j + 1) products with taps >= 8192 and with x[t >= 8192]
-      const bool tail_thread = nt > 0 && hf == 0 && q == 0 && lane < nt;
+      // Tail tokens t = NC C + j (j < nt, last chunk only): the last transform's outputs C + j (row n1 = 64, lane j) hold
+      // every (input chunk a, filter segment s) pair with a + s = NC - 1; what is missing are the pairs with a + s = NC,
+      // i.e. per input chunk a (including the tail itself, a = NC) the <= j + 1 products x[a C + i] k'[(NC - a) C + j - i].
+      const bool last_chunk = c == NC - 1;
+      const bool tail_thread = nt > 0 && last_chunk && hf == 0 && q == 0 && lane < nt;
       float tc0 = 0.f, tc1 = 0.f, tx0 = 0.f, tx1 = 0.f;
       if (tail_thread) {
         const float* kq = p.k + (long long)ch * p.Lk;
         const int j = lane;
-        for (int n = 0; n <= j; ++n) {
-          const float k_hi = kq[C + j - n];                                 // tap index >= 8192, times x[n]
-          const float k_lo = n == j ? kq[0] + p.dbias[ch] : kq[j - n];      // tap index j - n, times x[C + n]
-          tc0 = fmaf(__half2float(p.vx[row0 + n]), k_hi, tc0);
-          tc0 = fmaf(__half2float(p.vx[row0 + C + n]), k_lo, tc0);
-          if (has1) {
-            tc1 = fmaf(__half2float(p.vx[row1 + n]), k_hi, tc1);
-            tc1 = fmaf(__half2float(p.vx[row1 + C + n]), k_lo, tc1);
+        for (int a = 0; a <= NC; ++a)
+          for (int i = 0; i <= j; ++i) {
+            const int tap = (NC - a) * C + j - i;
+            const float kv = tap == 0 ? kq[0] + p.dbias[ch] : kq[tap];
+            tc0 = fmaf(__half2float(p.vx[row0 + a * C + i]), kv, tc0);
+            if (has1) tc1 = fmaf(__half2float(p.vx[row1 + a * C + i]), kv, tc1);
           }
-        }
-        tx0 = __bfloat162float(p.x0[row0 + C + j]);
-        if (has1) tx1 = __bfloat162float(p.x0[row1 + C + j]);
+        tx0 = __bfloat162float(p.x0[row0 + NC * C + j]);
+        if (has1) tx1 = __bfloat162float(p.x0[row1 + NC * C + j]);
       }
       ptx::mbar_wait(o_full, ph);
       ptx::tc_fence_after_sync();
@@ -514,29 +570,55 @@ longconv_tc_kernel(const __grid_constant__ CUtensorMap tmVX, const __grid_consta
       for (int h2 = 0; h2 < 2; ++h2) {
         uint32_t zr[16], zi[16];
         tmem_ld16(TM_Y + lane_addr + 32 * hf + 16 * h2, zr);
-        tmem_ld16(TM_Y + lane_addr + ZIM_COL + 32 * hf + 16 * h2, zi);
+        tmem_ld16(TM_Y + lane_addr + ZIM + 32 * hf + 16 * h2, zi);
         ptx::tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           const int n1 = 32 * hf + 16 * h2 + j;
+          float va = __uint_as_float(zr[j]), vb = __uint_as_float(zi[j]);
+          if constexpr (CH) {   // + the previous chunk's overlap
+            if (c > 0) {
+              va += carry[n1 * 128 + r];
+              vb += carry[8192 + n1 * 128 + r];
+            }
+          }
           const float ga = __uint_as_float(uint32_t(st0[n1 * 128]) << 16);
-          const __nv_bfloat16 oa = __float2bfloat16(__uint_as_float(zr[j]) * ga);
+          const __nv_bfloat16 oa = __float2bfloat16(va * ga);
           st0[n1 * 128] = *reinterpret_cast<const unsigned short*>(&oa);
           if (has1) {
             const float gb = __uint_as_float(uint32_t(st0[8192 + n1 * 128]) << 16);
-            const __nv_bfloat16 ob = __float2bfloat16(__uint_as_float(zi[j]) * gb);
+            const __nv_bfloat16 ob = __float2bfloat16(vb * gb);
             st0[8192 + n1 * 128] = *reinterpret_cast<const unsigned short*>(&ob);
           }
         }
       }
-      if (nt > 0 && hf == 0 && q == 0) {   // warp-uniform
+      if constexpr (CH) {
+        // second half of this transform (rows n1 >= 64) = what it contributes to the next chunk's outputs.  The thread that
+        // reads carry[n1][r] for n1 in [32 hf, 32 hf + 32) above is the one that rewrites exactly those entries here.
+        if (!last_chunk) {
+#pragma unroll
+          for (int h2 = 0; h2 < 2; ++h2) {
+            uint32_t zr[16], zi[16];
+            tmem_ld16(TM_Y + lane_addr + 64 + 32 * hf + 16 * h2, zr);
+            tmem_ld16(TM_Y + lane_addr + ZIM + 64 + 32 * hf + 16 * h2, zi);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const int n1 = 32 * hf + 16 * h2 + j;
+              carry[n1 * 128 + r] = __uint_as_float(zr[j]);
+              carry[8192 + n1 * 128 + r] = __uint_as_float(zi[j]);
+            }
+          }
+        }
+      }
+      if (nt > 0 && last_chunk && hf == 0 && q == 0) {   // warp-uniform
         uint32_t zr[16], zi[16];
         tmem_ld16(TM_Y + lane_addr + 64, zr);
-        tmem_ld16(TM_Y + lane_addr + ZIM_COL + 64, zi);
+        tmem_ld16(TM_Y + lane_addr + ZIM + 64, zi);
         ptx::tmem_ld_wait();
         if (tail_thread) {
-          p.out[row0 + C + lane] = __float2bfloat16((__uint_as_float(zr[0]) + tc0) * tx0);
-          if (has1) p.out[row1 + C + lane] = __float2bfloat16((__uint_as_float(zi[0]) + tc1) * tx1);
+          p.out[row0 + NC * C + lane] = __float2bfloat16((__uint_as_float(zr[0]) + tc0) * tx0);
+          if (has1) p.out[row1 + NC * C + lane] = __float2bfloat16((__uint_as_float(zi[0]) + tc1) * tx1);
         }
       }
       ptx::fence_proxy_async_smem();
