@@ -84,6 +84,7 @@ struct clm_ctx {
   HeadParams head{};
   // workspaces
   int max_B = 0, max_T = 0, Tp_max = 0;
+  int last_B = 0, last_T = 0;   // shape of the last complete forward (clm_attention_weights)
   float* R = nullptr;
   __nv_bfloat16 *XN = nullptr, *U = nullptr, *VX = nullptr, *X0 = nullptr, *Y = nullptr, *YT = nullptr;
   float *score = nullptr, *part = nullptr, *pooled = nullptr;
@@ -1117,6 +1118,7 @@ int clm_forward(clm_ctx* c, const void* d_ids, int ids_dtype, int B, int T, floa
     CLM_LAUNCH_CHECK(c, "head_out");
   }
 #undef STOP_AFTER
+  c->last_B = B; c->last_T = T;
   return 0;
 }
 
@@ -1281,6 +1283,15 @@ int clm_longconv_variant(const clm_ctx* c, int T) {
   if (c->fused_in && tc_conv_applies(c, T)) return 2;
   const ConvPlan pl = plan_conv(T);
   return (c->fast_conv && c->layers[0].gspecT[pl.logn] != nullptr) ? 1 : 0;
+}
+
+int clm_attention_weights(clm_ctx* c, float* d_out, int B, int T, void* stream) {
+  if (!c || !c->finalized) return fail(c, CLM_ERR_STATE, "clm_attention_weights before clm_finalize");
+  if (!d_out || B <= 0 || T <= 0) return fail(c, CLM_ERR_INVALID, "clm_attention_weights: bad argument");
+  if (B != c->last_B || T != c->last_T) return fail(c, CLM_ERR_STATE, "clm_attention_weights: the last forward was %d x %d, not %d x %d", c->last_B, c->last_T, B, T);
+  attention_softmax_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(c->score, d_out, T);
+  CLM_LAUNCH_CHECK(c, "attention_softmax");
+  return 0;
 }
 
 int clm_get_filter(clm_ctx* c, int layer, float* d_out, int L, void* stream) {

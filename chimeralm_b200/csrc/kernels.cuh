@@ -264,6 +264,32 @@ __global__ void __launch_bounds__(256) pool_partial_kernel(const __nv_bfloat16* 
   if (d == 0) { out[0] = M; out[1] = L; }
 }
 
+// Attention weights export (components/hyena.py:129-130, `save_attention=True`): w[b,t] = softmax_t(score[b,:]).
+// One block per read; the scores are those of the last forward.
+__global__ void __launch_bounds__(256) attention_softmax_kernel(const float* __restrict__ score, float* __restrict__ out, int T) {
+  __shared__ float red[8];
+  const float* s = score + (long long)blockIdx.x * T;
+  float* o = out + (long long)blockIdx.x * T;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float m = -INFINITY;
+  for (int t = threadIdx.x; t < T; t += 256) m = fmaxf(m, s[t]);
+  for (int k = 16; k; k >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, k));
+  if (lane == 0) red[warp] = m;
+  __syncthreads();
+  m = red[0];
+  for (int w = 1; w < 8; ++w) m = fmaxf(m, red[w]);
+  __syncthreads();
+  float l = 0.f;
+  for (int t = threadIdx.x; t < T; t += 256) l += expf(s[t] - m);
+  for (int k = 16; k; k >>= 1) l += __shfl_xor_sync(0xffffffffu, l, k);
+  if (lane == 0) red[warp] = l;
+  __syncthreads();
+  l = 0.f;
+  for (int w = 0; w < 8; ++w) l += red[w];
+  const float inv = 1.0f / l;
+  for (int t = threadIdx.x; t < T; t += 256) o[t] = expf(s[t] - m) * inv;
+}
+
 // Classifier head (components/hyena.py:55-74,142-146,149-180): merge pooling slices, then
 //   Lin(256,512) GELU Lin(512,512) GELU [Lin(512,512) GELU Lin(512,512)] + skip, Lin(512,2);
 //   label = argmax(logits) with ties -> 0 (chimeralm/models/callbacks.py:107).  One block per read.

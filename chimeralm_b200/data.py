@@ -50,7 +50,29 @@ class PredictDataset:
         return len(self.names)
 
 
+_UPPER = np.arange(256, dtype=np.uint8)
+_UPPER[ord("a") : ord("z") + 1] -= 32
+
+
+def read_parquet_records(path, max_records=None):
+    """Predict input as the authors ran large evaluations (`chimeralm/data/fq.py:152-181`, HF `load_dataset("parquet")`):
+    columns `id` and `seq` (a `qual` column, if present, is ignored exactly like `input_quals` is)."""
+    import pyarrow.parquet as pq
+
+    n = 0
+    pf = pq.ParquetFile(str(path))
+    for rg in range(pf.num_row_groups):
+        tbl = pf.read_row_group(rg, columns=["id", "seq"])
+        for name, seq in zip(tbl.column("id").to_pylist(), tbl.column("seq").to_pylist()):
+            yield name, np.frombuffer(seq.encode("ascii", "replace"), dtype=np.uint8)
+            n += 1
+            if max_records is not None and n >= max_records:
+                return
+
+
 def read_fastq_bytes(path):
+    """FASTQ(.gz) records as (name, uint8 bases), upper-cased like `pyfastx.Fastx(uppercase=True)`
+    (`chimeralm/data/only_fq.py:22-41`); the name is the header up to the first whitespace."""
     import gzip
 
     op = gzip.open if str(path).endswith(".gz") else open
@@ -62,7 +84,7 @@ def read_fastq_bytes(path):
             s = f.readline().rstrip(b"\r\n")
             f.readline()
             f.readline()
-            yield h[1:].split()[0].decode("ascii", "replace"), np.frombuffer(s, dtype=np.uint8)
+            yield h[1:].split()[0].decode("ascii", "replace"), _UPPER[np.frombuffer(s, dtype=np.uint8)]
 
 
 class BamDataModule:
@@ -101,13 +123,13 @@ class BamDataModule:
             raise ValueError("Predict data path is required for prediction stage.")
         path = Path(self.predict_data_path)
         max_bases = self.tokenizer.max_len_single_sentence - self.tokenizer.num_special_tokens
-        if self.streaming and path.suffix not in (".fq", ".fastq", ".gz"):
+        if self.streaming and path.suffix not in (".fq", ".fastq", ".gz", ".parquet"):
             self.data_predict = None  # read on the fly by _stream_batches
             return
         self.streaming = False
-        if path.suffix in (".fq", ".fastq", ".gz"):
+        if path.suffix in (".fq", ".fastq", ".gz", ".parquet"):
             names, seqs = [], []
-            for name, seq in read_fastq_bytes(path):
+            for name, seq in (read_parquet_records(path) if path.suffix == ".parquet" else read_fastq_bytes(path)):
                 names.append(name)
                 seqs.append(seq[:max_bases])
                 if self.max_predict_samples is not None and len(names) >= self.max_predict_samples:

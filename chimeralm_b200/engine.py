@@ -230,6 +230,13 @@ class Engine:
         self._check(rc, "clm_longconv_tc")
         return out
 
+    def attention_weights(self, B: int, T: int) -> torch.Tensor:
+        """softmax_t of the attention-pooling scores of the last forward: float32 [B, T]."""
+        out = torch.empty(B, T, dtype=torch.float32, device=self.device)
+        self._check(self.lib.clm_attention_weights(self.ctx, C.c_void_p(out.data_ptr()), B, T, _stream_ptr(self.device)),
+                    "clm_attention_weights")
+        return out
+
     def longconv_variant(self, T: int) -> str:
         """Name of the long-convolution kernel `forward` uses for reads of T tokens."""
         return {0: "fft_fp32", 1: "fft_fp32_tuned", 2: "fft_tensor_core"}.get(self.lib.clm_longconv_variant(self.ctx, int(T)), "?")

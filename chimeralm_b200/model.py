@@ -21,8 +21,12 @@ class ClassificationLit:
     """Inference-only stand-in for the reference LightningModule."""
 
     def __init__(self, state_dict, *, device: int | str = 0, cfg: HyenaConfig = DEFAULT_CONFIG, max_batch: int = 12,
-                 max_tokens: int = 8193):
+                 max_tokens: int = 8193, save_attention: bool = False):
         self.cfg = cfg
+        # `save_attention=True` (chimeralm/models/lm.py:14,30): after every forward `attention_weights` holds the pooling
+        # weights [B, T, 1], like `BinarySequenceClassifier.attention_weights` (components/hyena.py:129-130)
+        self.save_attention = save_attention
+        self.attention_weights = None
         self._state_dict = state_dict
         self.engine = Engine(state_dict, device=device, cfg=cfg, max_batch=max_batch, max_tokens=max_tokens)
         self.device = self.engine.device
@@ -50,7 +54,10 @@ class ClassificationLit:
     def forward(self, input_ids: torch.Tensor, input_quals: torch.Tensor | None = None) -> torch.Tensor:
         """logits [B, 2] float32; `input_quals` is accepted and ignored exactly like
         `HyenaDna.forward` ignores it (chimeralm/models/components/hyena.py:244-256)."""
-        return self.engine.forward(input_ids)
+        logits = self.engine.forward(input_ids)
+        if self.save_attention:
+            self.attention_weights = self.engine.attention_weights(*input_ids.shape).unsqueeze(-1)
+        return logits
 
     __call__ = forward
 
@@ -58,6 +65,8 @@ class ClassificationLit:
         """Returns `(logits, batch["labels"])` like the reference; device-side argmax labels
         (same rule as PredictionWriter, callbacks.py:107) ride along as a third element."""
         logits, labels = self.engine.forward(batch["input_ids"], return_labels=True)
+        if self.save_attention:
+            self.attention_weights = self.engine.attention_weights(*batch["input_ids"].shape).unsqueeze(-1)
         return logits, batch["labels"], labels
 
 
@@ -69,7 +78,7 @@ class ChimeraLM:
         """Random-init model of the named architecture.  (The reference's `new()` still pulls the
         pretrained HyenaDNA backbone from the Hub, components/hyena.py:237; offline the backbone
         is random-init too, seeded for reproducibility.)"""
-        return ClassificationLit(make_state_dict(seed), device=device, **kw)
+        return ClassificationLit(make_state_dict(seed), device=device, save_attention=save_attention, **kw)
 
     @classmethod
     def from_pretrained(cls, model_name: str = "yangliz5/chimeralm", *, save_attention: bool = False,
@@ -87,4 +96,4 @@ class ChimeraLM:
             raise FileNotFoundError(
                 f"'{model_name}' is not a local checkpoint; downloading from the Hugging Face Hub is not possible "
                 "offline. Pass --ckpt / a local path.")
-        return ClassificationLit(load_checkpoint(p), device=device, **kw)
+        return ClassificationLit(load_checkpoint(p), device=device, save_attention=save_attention, **kw)

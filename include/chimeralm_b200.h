@@ -137,6 +137,10 @@ int clm_set_option(clm_ctx* ctx, const char* name, int value);
 int clm_longconv(clm_ctx* ctx, int layer, const void* d_vx, const void* d_x0, void* d_out, int B, int T, int Tp,
                  void* stream);
 /* Copies the generated time-domain filter k[layer][:, :L] (float32 [D, L]) to a device buffer. */
+/* Attention-pooling weights of the LAST clm_forward (same B, T): d_out[b*T + t] = softmax_t(score[b, :]).  Replaces
+ * `save_attention=True` / `BinarySequenceClassifier.attention_weights` (chimeralm/models/components/hyena.py:129-130,
+ * chimeralm/models/lm.py:14,30). */
+int clm_attention_weights(clm_ctx* ctx, float* d_out, int B, int T, void* stream);
 /* Tensor-core FFT long convolution (reads of 8192..8200 tokens): same contract as clm_longconv except
  * that d_vx holds fp16 values (what the fused in_proj kernel emits when this kernel follows). */
 int clm_longconv_tc(clm_ctx* ctx, int layer, const void* d_vx_f16, const void* d_x0, void* d_out, int B, int T, int Tp,

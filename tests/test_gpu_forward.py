@@ -182,3 +182,26 @@ def test_repeated_forward_under_copy_traffic_is_stable_and_deterministic(state_d
         assert torch.equal(out, first)
     finally:
         eng.close()
+
+
+def test_attention_weights_export(state_dict):
+    """`save_attention=True` exposes softmax_t(scores) of the last forward, shape [B, T, 1] like the
+    reference's `BinarySequenceClassifier.attention_weights` (oracle head pinned on the reference's own golden)."""
+    from chimeralm_b200.model import ClassificationLit
+
+    B, T = 3, 700
+    ids = _ids(B, T, seed=11, pad_left=100)
+    _, _, logits_ref, attn_ref = _oracle_states(state_dict, ids)
+    model = ClassificationLit(state_dict, device=0, max_batch=B, max_tokens=T, save_attention=True)
+    try:
+        logits = model.forward(ids.cuda()).cpu()
+        attn = model.attention_weights.cpu()
+        assert attn.shape == (B, T, 1)
+        assert (logits - logits_ref).abs().max().item() <= LOGIT_TOL
+        ref = attn_ref.reshape(B, T)
+        assert torch.allclose(attn[..., 0].sum(1), torch.ones(B), atol=1e-4)
+        assert (attn[..., 0] - ref).abs().max().item() <= 2e-2 * ref.max().item()
+        with pytest.raises(Exception):
+            model.engine.attention_weights(B, T + 1)
+    finally:
+        model.engine.close()

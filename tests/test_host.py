@@ -286,3 +286,32 @@ def test_streaming_loader_matches_load_all_and_shards_like_the_sampler(tmp_path)
         for x, y in zip(a, b):
             assert x["names"] == y["names"] and list(x["indices"]) == list(y["indices"])
             assert torch.equal(x["input_ids"], y["input_ids"]) and torch.equal(x["id"], y["id"])
+
+
+def test_fastq_and_parquet_predict_inputs(tmp_path):
+    """FASTQ (plain / gz, upper-cased like pyfastx(uppercase=True)) and Parquet (columns id, seq) feed the same
+    tokenise + collate path as the BAM module; ids are checked against the oracle tokenizer."""
+    import gzip
+
+    import pyarrow as pa
+    import pyarrow.parquet as pq
+
+    from chimeralm_b200.data import BamDataModule
+    from chimeralm_b200.tokenizer import load_tokenizer_from_hyena_model
+
+    tok = load_tokenizer_from_hyena_model("hyenadna-small-32k-seqlen")
+    recs = [("r1 extra words", "ACGTNacgtn"), ("r2", "GGGTTTAAACCC"), ("r3/1", "A"), ("r4", "TTTTGGGGCCCCAAAA" * 5)]
+    fq = "".join(f"@{n}\n{s}\n+\n{'I' * len(s)}\n" for n, s in recs)
+    (tmp_path / "a.fastq").write_text(fq)
+    with gzip.open(tmp_path / "b.fq.gz", "wt") as f:
+        f.write(fq)
+    pq.write_table(pa.table({"id": [n.split()[0] for n, _ in recs], "seq": [s.upper() for _, s in recs],
+                             "qual": ["I" * len(s) for _, s in recs]}), tmp_path / "c.parquet")
+    want_names = [n.split()[0] for n, _ in recs]
+    want_ids = TO.collate([TO.encode(s.upper(), max_length=32769, add_cls=False) for _, s in recs], padding_side="left")
+    for path in ("a.fastq", "b.fq.gz", "c.parquet"):
+        dm = BamDataModule(tok, predict_data_path=tmp_path / path, batch_size=8, streaming=True)
+        dm.setup("predict")
+        (batch,) = list(dm.predict_dataloader())
+        assert batch["names"] == want_names, path
+        assert batch["input_ids"].tolist() == want_ids, path
