@@ -21,6 +21,7 @@
 #include "longconv.cuh"
 #include "longconv_fast.cuh"
 #include "longconv_tc.cuh"
+#include "score_pool.cuh"
 
 using namespace clm;
 
@@ -114,6 +115,7 @@ struct clm_ctx {
   int mlp_stagger = 0;    // block_mlp: CTA phase stagger in cycles (0 = off)
   bool tc_conv = true;    // tensor-core FFT long convolution for reads of 8192..8200 tokens (needs fused_in)
   __half* tc_S = nullptr; // shared-memory image of the DFT constant stack (longconv_tc)
+  bool fused_score_pool = true;   // scorer GEMM + pooling partials in one persistent kernel (needs the folded tail)
   bool tc_chunked = true; // tensor-core conv also for reads longer than 8200 tokens (overlap-add over 8192-token chunks)
   int tc_nseg = 0;        // filter segments of 8192 taps with a spectrum table
   float* tc_scratch = nullptr;
@@ -921,7 +923,7 @@ int clm_reserve(clm_ctx* c, int max_B, int max_T) {
   if ((rc = dev_alloc(c, &c->YT, M * D))) return rc;
   if ((rc = dev_alloc(c, &c->score, M))) return rc;
   c->n_split = std::max(1, std::min(64, (2 * c->num_sms + max_B - 1) / max_B));
-  if ((rc = dev_alloc(c, &c->part, (size_t)max_B * c->n_split * (2 + D)))) return rc;
+  if ((rc = dev_alloc(c, &c->part, (size_t)max_B * std::max(c->n_split, (max_T + 127) / 128) * (2 + D)))) return rc;
   if ((rc = dev_alloc(c, &c->pooled, (size_t)max_B * D))) return rc;
   for (int i = 0; i < 4; ++i) {
     dev_free(c, c->hbuf[i]);
@@ -1078,6 +1080,26 @@ int clm_forward(clm_ctx* c, const void* d_ids, int ids_dtype, int B, int T, floa
     CLM_LAUNCH_CHECK(c, "ln_f");
   }
   STOP_AFTER(NL, 10);
+  // dbg stages 11 (scores) and 12 (pooling) are separate kernels only on the unfused path
+  const bool sp_fused = tail_folded && c->fused_score_pool && c->dbg_layer != NL;
+  int n_split = c->n_split;
+  if (sp_fused) {
+    static bool attr_set = false;
+    if (!attr_set) {
+      CLM_CUDA(c, cudaFuncSetAttribute(score_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sp::SMEM_TOTAL));
+      attr_set = true;
+    }
+    ProfScope ps_(c, PC_SCORE, st);
+    CUtensorMap tmA;
+    if ((rc = make_tmap_xn(c, &tmA, c->XN, B, T, sp::BM))) return rc;
+    ScorePoolParams sp_{};
+    sp_.b0 = c->att0_bf; sp_.w2 = c->att2_w; sp_.b2 = c->att2_b; sp_.g = c->lnf_g; sp_.beta = c->lnf_b;
+    sp_.score = c->score; sp_.part = c->part; sp_.B = B; sp_.T = T;
+    sp_.tiles_per_seq = (T + sp::BM - 1) / sp::BM; sp_.num_tiles = B * sp_.tiles_per_seq;
+    n_split = sp_.tiles_per_seq;
+    score_pool_kernel<<<std::min(sp_.num_tiles, c->num_sms), sp::THREADS, sp::SMEM_TOTAL, st>>>(tmA, c->tm_att0f, sp_);
+    CLM_LAUNCH_CHECK(c, "score_pool");
+  } else {
   {
     GemmParams p{};
     p.M = (int)M; p.N = D; p.K = D; p.w2 = c->att2_w; p.b2 = c->att2_b; p.score = c->score; p.ldo = D;
@@ -1100,11 +1122,12 @@ int clm_forward(clm_ctx* c, const void* d_ids, int ids_dtype, int B, int T, floa
   pool_partial_kernel<<<dim3(c->n_split, B), 256, 0, st>>>(c->XN, c->score, c->lnf_g, c->lnf_b, c->part, T, c->n_split);
   CLM_LAUNCH_CHECK(c, "pool_partial"); }
   STOP_AFTER(NL, 12);
+  }
   {
     ProfScope ps_(c, PC_HEAD, st);
     const HeadParams& hp = c->head;
     const int H = g.head_hidden;
-    pool_merge_kernel<<<B, 256, 0, st>>>(c->part, c->n_split, c->pooled);
+    pool_merge_kernel<<<B, 256, 0, st>>>(c->part, n_split, c->pooled);
     CLM_LAUNCH_CHECK(c, "pool_merge");
     head_layer_kernel<256, true, false, false><<<dim3(H / 8, (B + 31) / 32), 256, 0, st>>>(hp.w0, hp.b0, c->pooled, nullptr, c->hbuf[0], nullptr, B, H);
     CLM_LAUNCH_CHECK(c, "head_l0");
@@ -1167,6 +1190,7 @@ int clm_set_option(clm_ctx* c, const char* name, int value) {
   else if (n == "fast_conv") c->fast_conv = value != 0;
   else if (n == "tc_conv") c->tc_conv = value != 0;
   else if (n == "tc_chunked") c->tc_chunked = value != 0;
+  else if (n == "fused_score_pool") c->fused_score_pool = value != 0;
   else if (n == "mlp_stagger") c->mlp_stagger = value;
   else if (n == "y_channel_major") c->y_channel_major = value != 0;
   else if (n == "mlp_2cta") c->mlp_2cta = value != 0;
