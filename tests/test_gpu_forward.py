@@ -6,6 +6,8 @@ residual stream, fp32 FFT and fp32 pooling/head.  Residual stream |err| <= 5e-2 
 scaled by the block outputs), logits |err| <= 5e-3 (north_star: "stated bf16 tolerance";
 SURVEY.md 8(d) allows up to 2e-2), labels must agree wherever |oracle margin| > 2 * 5e-3."""
 
+from pathlib import Path
+
 import pytest
 import torch
 
@@ -14,6 +16,7 @@ from chimeralm_b200.config import DEFAULT_CONFIG as CFG
 pytestmark = pytest.mark.gpu
 
 LOGIT_TOL = 5e-3
+ROOT = Path(__file__).resolve().parents[1]
 
 
 def _ids(B, T, seed, pad_left=0):
@@ -205,3 +208,41 @@ def test_attention_weights_export(state_dict):
             model.engine.attention_weights(B, T + 1)
     finally:
         model.engine.close()
+
+
+def _synthetic_bam(path, n=96, seed=3):
+    import numpy as np
+
+    from chimeralm_b200.bam import BamWriter, make_record, minimal_header
+
+    rng = np.random.default_rng(seed)
+    acgt = np.frombuffer(b"ACGT", np.uint8)
+    w = BamWriter(path, minimal_header())
+    for i in range(n):
+        w.write(make_record(f"read_{i:04d}", acgt[rng.integers(0, 4, int(rng.integers(200, 3000)))].tobytes(), sa_tag=(i % 7 != 0)))
+    w.close()
+
+
+@pytest.mark.parametrize("gpus", [1, 2])
+def test_cli_predict_subprocess(tmp_path, gpus):
+    """`python -m chimeralm_b200 predict` end to end in a fresh process; with 2 GPUs the per-rank workers are spawned
+    (they must be importable from the children: the worker lives in predict_worker.py, not in __main__) and the union of the
+    per-rank files equals the single-GPU result."""
+    import subprocess
+    import sys
+
+    from chimeralm_b200.callbacks import load_predictions_from_folder
+
+    if torch.cuda.device_count() < gpus:
+        pytest.skip(f"needs {gpus} GPUs")
+    bam = tmp_path / "in.bam"
+    _synthetic_bam(bam)
+    outs = {}
+    for g in sorted({1, gpus}):
+        out = tmp_path / f"pred{g}"
+        r = subprocess.run([sys.executable, "-m", "chimeralm_b200", "predict", str(bam), "-o", str(out), "-b", "16", "--gpus", str(g)],
+                           capture_output=True, text=True, timeout=600, cwd=str(ROOT))
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        outs[g] = load_predictions_from_folder(out)
+    assert len(outs[1]) == 96 - 14   # every 7th record has no SA tag
+    assert outs[gpus] == outs[1]
