@@ -16,6 +16,7 @@
 #include "block_in.cuh"
 #include "block_mlp.cuh"
 #include "block_mlp2.cuh"
+#include "block_mlp16.cuh"
 #include "gemm_tcgen05.cuh"
 #include "kernels.cuh"
 #include "longconv.cuh"
@@ -121,6 +122,7 @@ struct clm_ctx {
   float* tc_scratch = nullptr;
   size_t tc_scratch_floats = 0;
   bool mlp_2cta = false;  // CTA-pair (cta_group::2) version of the fused block tail
+  bool mlp_epi16 = false; // fused block tail with 16 epilogue warps (block_mlp16.cuh)
   bool y_channel_major = true;  // block_mlp reads the conv output channel-major (MN-major UMMA operand): no transpose
   // debug
   int dbg_layer = -1, dbg_stage = -1;
@@ -389,6 +391,16 @@ int launch_block_mlp(clm_ctx* c, int layer, const __nv_bfloat16* y, float* res, 
     return 0;
   }
   const int grid = std::min(p.num_tiles, c->num_sms);
+  if (c->mlp_epi16) {
+    static bool attr16_set = false;
+    if (!attr16_set) {
+      CLM_CUDA(c, cudaFuncSetAttribute(block_mlp16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bm16::SMEM_TOTAL));
+      attr16_set = true;
+    }
+    block_mlp16_kernel<<<grid, bm16::THREADS, bm16::SMEM_TOTAL, st>>>(tmY, L.tm_out_t, L.tm_fc1_t, L.tm_fc2_t, tmXN, p);
+    CLM_LAUNCH_CHECK(c, "block_mlp16");
+    return 0;
+  }
   block_mlp_kernel<<<grid, bm::THREADS, bm::SMEM_TOTAL, st>>>(tmY, L.tm_out_t, L.tm_fc1_t, L.tm_fc2_t, tmXN, p);
   CLM_LAUNCH_CHECK(c, "block_mlp");
   return 0;
@@ -1194,6 +1206,7 @@ int clm_set_option(clm_ctx* c, const char* name, int value) {
   else if (n == "mlp_stagger") c->mlp_stagger = value;
   else if (n == "y_channel_major") c->y_channel_major = value != 0;
   else if (n == "mlp_2cta") c->mlp_2cta = value != 0;
+  else if (n == "mlp_epi16") c->mlp_epi16 = value != 0;
   else return fail(c, CLM_ERR_INVALID, "clm_set_option: unknown option '%s'", name);
   return 0;
 }

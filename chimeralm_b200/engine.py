@@ -7,6 +7,7 @@ pointers; every computation happens in the CUDA library.
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -50,6 +51,10 @@ class Engine:
         self._check(self.lib.clm_finalize(self.ctx), "clm_finalize")
         self.max_batch = self.max_tokens = 0
         self.reserve(max_batch, max_tokens)
+        # CLM_OPTIONS="name=value,name=value": kernel-selection switches (clm_set_option) for A/B runs of the test suite / bench
+        for item in filter(None, os.environ.get("CLM_OPTIONS", "").split(",")):
+            name, _, val = item.partition("=")
+            self.set_option(name.strip(), int(val))
 
     # ------------------------------------------------------------------ plumbing
     def _check(self, rc, what):
