@@ -183,9 +183,10 @@ longconv_tc_kernel(const __grid_constant__ CUtensorMap tmVX, const __grid_consta
   uint64_t* z_full = bars;        // [2] TMA landed
   uint64_t* z_empty = bars + 2;   // [2] step 1 finished reading z
   uint64_t* x_full = bars + 4;    // step 1 accumulators complete
-  uint64_t* p1_full = bars + 5;   // E1 wrote P1
+  uint64_t* p1_full = bars + 16;  // [2] E1 wrote the P1 columns of index half h (steps 3 / 5 sum over that index: the MMAs
+                                  //     over the first half are issued while the epilogue still packs the second)
   uint64_t* y_full = bars + 6;    // step 3 complete
-  uint64_t* p2_full = bars + 7;   // E2 wrote P2
+  uint64_t* p2_full = bars + 18;  // [2] E2 wrote the P2 columns of index half h
   uint64_t* x2_full = bars + 8;   // step 5 complete
   uint64_t* bt_full = bars + 9;   // E3 wrote BT
   uint64_t* o_full = bars + 10;   // step 7 complete
@@ -195,7 +196,7 @@ longconv_tc_kernel(const __grid_constant__ CUtensorMap tmVX, const __grid_consta
   // lapped and the kernel would dead-lock (seen as a rare launch failure from the bounded wait).
   uint64_t* g_full = bars + 14;
   uint64_t* out_ready = bars + 12; // [2] E4 wrote the output tile into the z buffer (8 warp arrivals)
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 16);
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 20);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // contiguous item ranges per CTA: consecutive items share the channel (and its spectrum lines in L2)
@@ -219,8 +220,8 @@ longconv_tc_kernel(const __grid_constant__ CUtensorMap tmVX, const __grid_consta
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmVX); ptx::prefetch_tmap(&tmOut); ptx::prefetch_tmap(&tmX0);
     for (int i = 0; i < 2; ++i) { ptx::mbar_init(&z_full[i], 1); ptx::mbar_init(&z_empty[i], 1); ptx::mbar_init(&out_ready[i], 8); }
-    ptx::mbar_init(x_full, 1); ptx::mbar_init(p1_full, 8);
-    ptx::mbar_init(y_full, 1); ptx::mbar_init(p2_full, 8);
+    ptx::mbar_init(x_full, 1); ptx::mbar_init(&p1_full[0], 8); ptx::mbar_init(&p1_full[1], 8);
+    ptx::mbar_init(y_full, 1); ptx::mbar_init(&p2_full[0], 8); ptx::mbar_init(&p2_full[1], 8);
     ptx::mbar_init(x2_full, 1); ptx::mbar_init(bt_full, 8);
     ptx::mbar_init(o_full, 1); ptx::mbar_init(&g_full[0], 1); ptx::mbar_init(&g_full[1], 1);
     ptx::fence_mbar_init();
@@ -304,11 +305,15 @@ longconv_tc_kernel(const __grid_constant__ CUtensorMap tmVX, const __grid_consta
         ptx::umma_commit(x_full);
         stamp(0);
         // ---- step 3: Y = [S_re | S_im] = P1 x F
-        ptx::mbar_wait(p1_full, ph);
+        ptx::mbar_wait(&p1_full[0], ph);
         ptx::tc_fence_after_sync();
         stamp(0);
 #pragma unroll
         for (int s = 0; s < 16; ++s) {
+          if (s == 8) {   // second index half
+            ptx::mbar_wait(&p1_full[1], ph);
+            ptx::tc_fence_after_sync();
+          }
           const int t = s & 1, n2 = 16 * (s >> 1);          // packed K order: per run of 16 indices, re then im
           const int rows = t == 0 ? ROW_FRE : ROW_NFIM;    // re part: [Fre; Fim], im part: [-Fim; Fre]
           ptx::umma_f16_ts(TM_Y, TM_X + 8 * s, s_desc(rows, n2), id35, s != 0);
@@ -316,11 +321,15 @@ longconv_tc_kernel(const __grid_constant__ CUtensorMap tmVX, const __grid_consta
         ptx::umma_commit(y_full);
         stamp(0);
         // ---- step 5: X = [B_im | B_re] = P2 x conj(F)
-        ptx::mbar_wait(p2_full, ph);
+        ptx::mbar_wait(&p2_full[0], ph);
         ptx::tc_fence_after_sync();
         stamp(0);
 #pragma unroll
         for (int s = 0; s < 16; ++s) {
+          if (s == 8) {
+            ptx::mbar_wait(&p2_full[1], ph);
+            ptx::tc_fence_after_sync();
+          }
           const int t = s & 1, k2 = 16 * (s >> 1);
           const int rows = t == 0 ? ROW_NFIM : ROW_FRE;    // re part: [-Fim; Fre], im part: [Fre; Fim]
           ptx::umma_f16_ts(TM_X, TM_Y + 8 * s, s_desc(rows, k2), id35, s != 0);
@@ -358,6 +367,12 @@ longconv_tc_kernel(const __grid_constant__ CUtensorMap tmVX, const __grid_consta
     sincospif(-2.0f * float(r) / float(N), &wstep.y, &wstep.x);
 #pragma unroll
     for (int u = 0; u < 4; ++u) sincospif(-2.0f * float((r * (64 * hf + 16 * u)) % N) / float(N), &seed[u].y, &seed[u].x);
+    // E1 / E2 walk the index (n2, k2) so that EVERY warp finishes the first half [0, 64) before the second: run u covers
+    // 16 indices from col12(u); E3 keeps the plain split (its output rows go to the shared-memory atom hf)
+    auto col12 = [&](int u) { return (u < 2 ? 0 : 64) + 32 * hf + 16 * (u & 1); };
+    float2 seed1[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) sincospif(-2.0f * float((r * col12(u)) % N) / float(N), &seed1[u].y, &seed1[u].x);
     const bool tr = trace && warp == 2 && lane == 0;
     const int nt = p.nt;      // tail tokens after the last chunk, 0..LONGCONV_TAIL_MAX
     const float2 w2 = make_float2(wstep.x * wstep.x - wstep.y * wstep.y, 2.0f * wstep.x * wstep.y);
@@ -398,11 +413,13 @@ longconv_tc_kernel(const __grid_constant__ CUtensorMap tmVX, const __grid_consta
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         uint32_t xr[16], xi[16], w[16];
-        const uint32_t col = 64 * hf + 16 * u;
+        const uint32_t col = col12(u);
         tmem_ld16(TM_X + lane_addr + col, xr);
         tmem_ld16(TM_X + lane_addr + 128 + col, xi);
         ptx::tmem_ld_wait();
-        const float2 t0 = make_float2(sd[u].x * S1, sd[u].y * S1);
+        float2 s1v = seed1[u];
+        asm volatile("" : "+f"(s1v.x), "+f"(s1v.y));
+        const float2 t0 = make_float2(s1v.x * S1, s1v.y * S1);
         const float2 t1 = make_float2(t0.x * ws.x - t0.y * ws.y, t0.x * ws.y + t0.y * ws.x);
         f2t TWX = f2_pack(t0.x, t1.x), TWY = f2_pack(t0.y, t1.y);   // twiddles of elements (2 j, 2 j + 1)
 #pragma unroll
@@ -416,26 +433,32 @@ longconv_tc_kernel(const __grid_constant__ CUtensorMap tmVX, const __grid_consta
             TWX = NX;
           }
         }
-        tmem_st8(TM_X + lane_addr + col, w);          // K slice 2 u' (re), u' = 4 hf + u
-        tmem_st8(TM_X + lane_addr + col + 8, w + 8);  // K slice 2 u' + 1 (im)
+        tmem_st8(TM_X + lane_addr + col, w);          // K slice 2 (col / 16) (re)
+        tmem_st8(TM_X + lane_addr + col + 8, w + 8);  // K slice 2 (col / 16) + 1 (im)
+        if (u & 1) {   // an index half is complete
+          ptx::tmem_st_wait();
+          ptx::tc_fence_before_sync();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&p1_full[u >> 1]);
+        }
       }
-      ptx::tmem_st_wait();
-      ptx::tc_fence_before_sync();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(p1_full);
       if (tr) stamp(1);
       // ------------------------------------------------ E2: P2 = fp16(sum_j S_{c-j} .* G'_j)   (j = 0 only when not chunked)
-      const uint4* gp = p.G + ((((size_t)ch * 4 + q) * 2 + hf) * 16) * 32 + lane;
+      // spectrum table: uint4 (4 consecutive k2) at (((ch * 4 + k1 / 32) * 2 + k2 / 64) * 16 + (k2 % 64) / 4) * 32 + k1 % 32
+      const uint4* gp = p.G + (((size_t)ch * 4 + q) * 2) * 16 * 32 + lane;
+      auto g_off = [&](int u) { const int k2 = col12(u); return (size_t)((k2 >> 6) * 16 + ((k2 & 63) >> 2)) * 32; };
       uint4 g[16];
 #pragma unroll
-      for (int v = 0; v < 16; ++v) g[v] = __ldg(gp + v * 32);
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int v = 0; v < 4; ++v) g[4 * u + v] = __ldg(gp + g_off(u) + v * 32);
       ptx::mbar_wait(y_full, ph);
       ptx::tc_fence_after_sync();
       if (tr) stamp(1);
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         uint32_t xr[16], xi[16], w[16];
-        const uint32_t col = 64 * hf + 16 * u;
+        const uint32_t col = col12(u);
         tmem_ld16(TM_Y + lane_addr + col, xr);
         tmem_ld16(TM_Y + lane_addr + 128 + col, xi);
         ptx::tmem_ld_wait();
@@ -464,7 +487,7 @@ longconv_tc_kernel(const __grid_constant__ CUtensorMap tmVX, const __grid_consta
           }
 #pragma unroll 1
           for (int j = 1; j <= c; ++j) {
-            const uint4* gj = gp + (size_t)j * p.g_seg_stride + (4 * u) * 32;
+            const uint4* gj = gp + (size_t)j * p.g_seg_stride + g_off(u);
             uint4 gq[4];
             float4 sv[8];
 #pragma unroll
@@ -492,11 +515,13 @@ longconv_tc_kernel(const __grid_constant__ CUtensorMap tmVX, const __grid_consta
         }
         tmem_st8(TM_Y + lane_addr + col, w);
         tmem_st8(TM_Y + lane_addr + col + 8, w + 8);
+        if (u & 1) {
+          ptx::tmem_st_wait();
+          ptx::tc_fence_before_sync();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&p2_full[u >> 1]);
+        }
       }
-      ptx::tmem_st_wait();
-      ptx::tc_fence_before_sync();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(p2_full);
       if (tr) stamp(1);
       // ------------------------------------------------ E3: BT = fp16(conj(tw) .* B), shared memory
       ptx::mbar_wait(x2_full, ph);
