@@ -116,6 +116,9 @@ struct clm_ctx {
   int mlp_stagger = 0;    // block_mlp: CTA phase stagger in cycles (0 = off)
   bool tc_conv = true;    // tensor-core FFT long convolution for reads of 8192..8200 tokens (needs fused_in)
   __half* tc_S = nullptr; // shared-memory image of the DFT constant stack (longconv_tc)
+  bool fused_head = true;         // pooling merge + classifier layers in one cooperative launch
+  unsigned int* head_counter = nullptr;
+  unsigned int head_base = 0;
   bool fused_score_pool = true;   // scorer GEMM + pooling partials in one persistent kernel (needs the folded tail)
   bool tc_chunked = true; // tensor-core conv also for reads longer than 8200 tokens (overlap-add over 8192-token chunks)
   int tc_nseg = 0;        // filter segments of 8192 taps with a spectrum table
@@ -870,6 +873,9 @@ int clm_finalize(clm_ctx* c) {
   if ((rc = dev_alloc(c, &c->tc_S, (size_t)tc::S_BYTES / 2))) return rc;
   tc::build_s_kernel<<<(tc::S_ROWS * 128 + 255) / 256, 256>>>(c->tc_S);
   CLM_LAUNCH_CHECK(c, "tc_build_s");
+  if ((rc = dev_alloc(c, &c->head_counter, 1))) return rc;
+  CLM_CUDA(c, cudaMemset(c->head_counter, 0, sizeof(unsigned int)));
+  c->head_base = 0;
   // head
   const float *a0w, *a2b;
   NEED(HD + "attention.0.weight", (int64_t)D * D, &a0w);
@@ -1139,6 +1145,25 @@ int clm_forward(clm_ctx* c, const void* d_ids, int ids_dtype, int B, int T, floa
     ProfScope ps_(c, PC_HEAD, st);
     const HeadParams& hp = c->head;
     const int H = g.head_hidden;
+    if (c->fused_head && c->head_counter && H == 512 && D == 256) {
+      HeadFusedParams hf{};
+      hf.part = c->part; hf.n_split = n_split;
+      hf.w0 = hp.w0; hf.b0 = hp.b0; hf.w1 = hp.w1; hf.b1 = hp.b1; hf.wr0 = hp.wr0; hf.br0 = hp.br0; hf.wr1 = hp.wr1; hf.br1 = hp.br1;
+      hf.wo = hp.wo; hf.bo = hp.bo;
+      hf.pooled = c->pooled; hf.h0 = c->hbuf[0]; hf.h1 = c->hbuf[1]; hf.h2 = c->hbuf[2]; hf.h3 = c->hbuf[3];
+      hf.logits = d_logits; hf.labels = d_labels; hf.counter = c->head_counter; hf.base = c->head_base; hf.B = B;
+      const int grid = H / 8;
+      c->head_base += 5u * (unsigned)grid;   // five grid barriers per launch; the counter is never reset
+      void* args[] = {&hf};
+      constexpr size_t head_smem = (size_t)HEAD_BT * 512 * sizeof(float);
+      static bool head_attr = false;
+      if (!head_attr) {
+        CLM_CUDA(c, cudaFuncSetAttribute(head_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)head_smem));
+        head_attr = true;
+      }
+      CLM_CUDA(c, cudaLaunchCooperativeKernel((const void*)head_fused_kernel, dim3(grid), dim3(256), args, head_smem, st));
+      CLM_LAUNCH_CHECK(c, "head_fused");
+    } else {
     pool_merge_kernel<<<B, 256, 0, st>>>(c->part, n_split, c->pooled);
     CLM_LAUNCH_CHECK(c, "pool_merge");
     head_layer_kernel<256, true, false, false><<<dim3(H / 8, (B + 31) / 32), 256, 0, st>>>(hp.w0, hp.b0, c->pooled, nullptr, c->hbuf[0], nullptr, B, H);
@@ -1151,6 +1176,7 @@ int clm_forward(clm_ctx* c, const void* d_ids, int ids_dtype, int B, int T, floa
     CLM_LAUNCH_CHECK(c, "head_r1");
     head_layer_kernel<512, false, false, true><<<dim3(1, (B + 31) / 32), 256, 0, st>>>(hp.wo, hp.bo, c->hbuf[3], nullptr, d_logits, d_labels, B, 2);
     CLM_LAUNCH_CHECK(c, "head_out");
+    }
   }
 #undef STOP_AFTER
   c->last_B = B; c->last_T = T;
@@ -1203,6 +1229,7 @@ int clm_set_option(clm_ctx* c, const char* name, int value) {
   else if (n == "tc_conv") c->tc_conv = value != 0;
   else if (n == "tc_chunked") c->tc_chunked = value != 0;
   else if (n == "fused_score_pool") c->fused_score_pool = value != 0;
+  else if (n == "fused_head") c->fused_head = value != 0;
   else if (n == "mlp_stagger") c->mlp_stagger = value;
   else if (n == "y_channel_major") c->y_channel_major = value != 0;
   else if (n == "mlp_2cta") c->mlp_2cta = value != 0;

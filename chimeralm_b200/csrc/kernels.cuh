@@ -429,4 +429,113 @@ __global__ void __launch_bounds__(256) head_layer_kernel(const float* __restrict
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// The whole head in ONE cooperative launch (pooling merge + 5 layers were 6 launch-latency-bound kernels, 0.11 ms/step):
+// 64 CTAs, each weight row still read once for the whole batch, a grid-wide barrier between layers.  The barrier is a
+// monotonically increasing counter (never reset; the host passes the value it has before this launch), the launch is
+// cooperative so that all CTAs are guaranteed to be resident.  Activations written by other CTAs are read with plain
+// (coherent) loads after the barrier's fences, never through the read-only path.
+struct HeadFusedParams {
+  const float* part; int n_split;
+  const float *w0, *b0, *w1, *b1, *wr0, *br0, *wr1, *br1, *wo, *bo;
+  float *pooled, *h0, *h1, *h2, *h3;   // [B,256], [B,512] x4
+  float* logits;      // [B,2]
+  uint8_t* labels;    // [B] (may be null)
+  unsigned int* counter;
+  unsigned int base;  // counter value before this launch
+  int B;
+};
+
+__device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(counter, 1u);
+    while ((int)(*reinterpret_cast<volatile unsigned int*>(counter) - target) < 0) {}
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+constexpr int HEAD_BT = 32;   // reads per shared-memory tile of the layer input (32 x 512 fp32 = 64 KB)
+
+// One layer for output neuron o (one warp), all reads: the layer input is staged in shared memory tile by tile (every warp of
+// the CTA needs all of it; from global memory each warp would pull B x IN floats through L2 again).
+template <int IN, bool GELU, bool SKIP>
+__device__ __forceinline__ void head_fused_layer(const float* __restrict__ W, const float* __restrict__ bias, const float* x,
+                                                 const float* skip, float* y, int o, int OUT, int B, float* xs) {
+  const int lane = threadIdx.x & 31;
+  constexpr int V = IN / 128;
+  float4 w[V];
+  float bo = 0.f;
+  if (o < OUT) {
+#pragma unroll
+    for (int v = 0; v < V; ++v) w[v] = __ldg(reinterpret_cast<const float4*>(W + (long long)o * IN) + lane + 32 * v);
+    bo = __ldg(bias + o);
+  }
+  for (int b0 = 0; b0 < B; b0 += HEAD_BT) {
+    const int nb = min(HEAD_BT, B - b0);
+    __syncthreads();   // previous tile fully consumed
+    for (int i = threadIdx.x; i < nb * (IN / 4); i += blockDim.x)
+      reinterpret_cast<float4*>(xs)[i] = reinterpret_cast<const float4*>(x + (long long)b0 * IN)[i];   // coherent load
+    __syncthreads();
+    if (o < OUT) {
+#pragma unroll 4
+      for (int b = 0; b < nb; ++b) {
+        float a = 0.f;
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+          const float4 xv = reinterpret_cast<const float4*>(xs + b * IN)[lane + 32 * v];
+          a += w[v].x * xv.x + w[v].y * xv.y + w[v].z * xv.z + w[v].w * xv.w;
+        }
+        for (int s2 = 16; s2 > 0; s2 >>= 1) a += __shfl_xor_sync(0xffffffffu, a, s2);
+        if (lane == 0) {
+          a += bo;
+          if (GELU) a = gelu_erf_h(a);
+          if (SKIP) a += skip[(long long)(b0 + b) * OUT + o];
+          y[(long long)(b0 + b) * OUT + o] = a;
+        }
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) head_fused_kernel(HeadFusedParams p) {
+  constexpr int D = 256, H = 512;
+  extern __shared__ __align__(16) float head_xs[];   // HEAD_BT x 512 fp32
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const unsigned int G = gridDim.x;
+  // phase 0: merge the pooling partials of each read (pool_merge_kernel)
+  for (int b = blockIdx.x; b < p.B; b += G) {
+    const int d = threadIdx.x;
+    const float* pp = p.part + (long long)b * p.n_split * (2 + D);
+    float M = -INFINITY;
+    for (int s = 0; s < p.n_split; ++s) M = fmaxf(M, pp[s * (2 + D)]);
+    float a = 0.f, L = 0.f;
+    for (int s = 0; s < p.n_split; ++s) {
+      const float ms = pp[s * (2 + D)];
+      const float f = (ms == -INFINITY) ? 0.f : __expf(ms - M);
+      a += pp[s * (2 + D) + 2 + d] * f;
+      L += pp[s * (2 + D) + 1] * f;
+    }
+    p.pooled[(long long)b * D + d] = a / L;
+  }
+  grid_barrier(p.counter, p.base + 1 * G);
+  const int o = blockIdx.x * 8 + warp;   // G * 8 == H
+  head_fused_layer<D, true, false>(p.w0, p.b0, p.pooled, nullptr, p.h0, o, H, p.B, head_xs);
+  grid_barrier(p.counter, p.base + 2 * G);
+  head_fused_layer<H, true, false>(p.w1, p.b1, p.h0, nullptr, p.h1, o, H, p.B, head_xs);
+  grid_barrier(p.counter, p.base + 3 * G);
+  head_fused_layer<H, true, false>(p.wr0, p.br0, p.h1, nullptr, p.h2, o, H, p.B, head_xs);
+  grid_barrier(p.counter, p.base + 4 * G);
+  head_fused_layer<H, false, true>(p.wr1, p.br1, p.h2, p.h1, p.h3, o, H, p.B, head_xs);
+  grid_barrier(p.counter, p.base + 5 * G);
+  if (blockIdx.x == 0) {
+    head_fused_layer<H, false, false>(p.wo, p.bo, p.h3, nullptr, p.logits, warp, 2, p.B, head_xs);
+    __syncthreads();
+    if (p.labels && warp == 0)
+      for (int b = lane; b < p.B; b += 32) p.labels[b] = (p.logits[b * 2 + 1] > p.logits[b * 2]) ? 1 : 0;   // ties -> 0
+  }
+}
+
 }  // namespace clm
