@@ -694,7 +694,8 @@ int clm_create(const clm_config* cfg, int device, clm_ctx** out) {
   *out = nullptr;
   // The kernels are specialised for the named architecture; refuse anything else loudly.
   if (cfg->d_model != 256 || cfg->d_inner != 1024 || cfg->head_hidden != 512 || cfg->num_classes != 2 ||
-      cfg->short_filter_order != 3 || cfg->filter_order > 64 || cfg->num_inner_mlps != 2 || cfg->n_layer < 1)
+      cfg->short_filter_order != 3 || cfg->filter_order > 64 || cfg->num_inner_mlps != 2 || cfg->n_layer < 1 ||
+      cfg->vocab_rows < 1 || cfg->vocab_rows > 16)
     return CLM_ERR_INVALID;
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return CLM_ERR_CUDA;
@@ -1005,7 +1006,7 @@ int clm_forward(clm_ctx* c, const void* d_ids, int ids_dtype, int B, int T, floa
   const long long M = (long long)B * T;
   if (M > 0x7fffffffLL) return fail(c, CLM_ERR_INVALID, "clm_forward: B*T too large");
   const int Tp = round_up(T, 128);   // whole 128-token rows per channel: the tensor-core conv views a channel as [n1][128]
-  const unsigned rows8 = (unsigned)((M + 7) / 8);
+  const unsigned rows32e = (unsigned)((M + 31) / 32);   // embed_kernel: one CTA per 32-row block of the R32 layout
   const unsigned rows32 = (unsigned)((M + 31) / 32);
   int rc;
 #define STOP_AFTER(layer, stage) \
@@ -1013,9 +1014,9 @@ int clm_forward(clm_ctx* c, const void* d_ids, int ids_dtype, int B, int T, floa
 
   { ProfScope ps_(c, PC_EMBED, st);
   switch (ids_dtype) {
-    case CLM_U8: embed_kernel<uint8_t><<<rows8, 256, 0, st>>>((const uint8_t*)d_ids, c->emb, c->emb_norm, c->R, c->XN, M, D, g.vocab_rows, c->d_err); break;
-    case CLM_I32: embed_kernel<int32_t><<<rows8, 256, 0, st>>>((const int32_t*)d_ids, c->emb, c->emb_norm, c->R, c->XN, M, D, g.vocab_rows, c->d_err); break;
-    case CLM_I64: embed_kernel<int64_t><<<rows8, 256, 0, st>>>((const int64_t*)d_ids, c->emb, c->emb_norm, c->R, c->XN, M, D, g.vocab_rows, c->d_err); break;
+    case CLM_U8: embed_kernel<uint8_t><<<rows32e, 256, 0, st>>>((const uint8_t*)d_ids, c->emb, c->emb_norm, c->R, c->XN, M, D, g.vocab_rows, c->d_err); break;
+    case CLM_I32: embed_kernel<int32_t><<<rows32e, 256, 0, st>>>((const int32_t*)d_ids, c->emb, c->emb_norm, c->R, c->XN, M, D, g.vocab_rows, c->d_err); break;
+    case CLM_I64: embed_kernel<int64_t><<<rows32e, 256, 0, st>>>((const int64_t*)d_ids, c->emb, c->emb_norm, c->R, c->XN, M, D, g.vocab_rows, c->d_err); break;
     default: return fail(c, CLM_ERR_INVALID, "clm_forward: ids dtype %d not supported", ids_dtype);
   }
   CLM_LAUNCH_CHECK(c, "embed"); }

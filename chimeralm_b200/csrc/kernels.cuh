@@ -54,18 +54,47 @@ __global__ void __launch_bounds__(256) embed_kernel(const IdT* __restrict__ ids,
                                                     const __nv_bfloat16* __restrict__ En, float* __restrict__ R,
                                                     __nv_bfloat16* __restrict__ XN, long long M, int D, int vocab_rows,
                                                     int* __restrict__ err) {
-  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (row >= M) return;
-  long long id = (long long)ids[row];
-  if (id < 0 || id >= vocab_rows) {
-    if (lane == 0) atomicExch(err, 1);
-    id = 0;
+  // One CTA per 32 consecutive rows = one contiguous 32 KB block of the R32 layout.  For the fp32 residual a warp's lanes
+  // are the 32 ROWS and it walks column groups, so every store instruction writes 512 contiguous bytes (lane-per-column
+  // wrote 16 bytes every 512).  The embedding table (<= 16 rows) sits in shared memory, rows padded by 16 B against bank
+  // conflicts between lanes holding different ids.  The bf16 xn rows are token-major: one warp per row, 512 B per store.
+  constexpr int DD = 256, PADF = DD + 4;
+  __shared__ __align__(16) float Es[16 * PADF];
+  __shared__ int s_id[32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long row0 = (long long)blockIdx.x * 32;
+  const int nv = min(vocab_rows, 16);
+  for (int i = threadIdx.x; i < nv * (DD / 4); i += 256) {
+    const int v = i / (DD / 4), c4 = i % (DD / 4);
+    *reinterpret_cast<float4*>(Es + v * PADF + 4 * c4) = __ldg(reinterpret_cast<const float4*>(E + (long long)v * D) + c4);
   }
-  const float4* src = reinterpret_cast<const float4*>(E + id * D);
-  for (int i = lane; i < D / 4; i += 32) *reinterpret_cast<float4*>(R + ptx::r32_off(row, 4 * i)) = __ldg(src + i);
-  const uint4* srcn = reinterpret_cast<const uint4*>(En + id * D);   // 256 bf16 = 32 x 16 B
-  reinterpret_cast<uint4*>(XN + row * D)[lane] = __ldg(srcn + lane);
+  if (threadIdx.x < 32) {
+    const long long row = row0 + threadIdx.x;
+    long long id = row < M ? (long long)ids[row] : 0;
+    if (id < 0 || id >= nv) {
+      if (row < M) atomicExch(err, 1);
+      id = 0;
+    }
+    s_id[threadIdx.x] = (int)id;
+  }
+  __syncthreads();
+  {
+    const long long row = row0 + lane;
+    const float* src = Es + s_id[lane] * PADF;
+    if (row < M) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int c4 = warp + 8 * k;   // column group (4 floats)
+        *reinterpret_cast<float4*>(R + ptx::r32_off(row, 4 * c4)) = *reinterpret_cast<const float4*>(src + 4 * c4);
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int rr = warp * 4 + k;
+    const long long row = row0 + rr;
+    if (row < M) reinterpret_cast<uint4*>(XN + row * D)[lane] = __ldg(reinterpret_cast<const uint4*>(En + (long long)s_id[rr] * D) + lane);
+  }
 }
 
 // En[v,:] = bf16((E[v,:] - mean) * rsqrt(var + eps)), one warp per vocabulary row
