@@ -51,12 +51,13 @@ constexpr int D = 256, BT = 128, HALO = 16, NCOL = BT + HALO;   // 144 token col
 constexpr int KB_ROWS_BYTES = NCOL * 128;                       // one k-block of xn: 144 rows x 128 B
 constexpr int XN_BYTES = 4 * KB_ROWS_BYTES;                     // 73728
 constexpr int SLOT_BYTES = 2 * 128 * 64 * 2;                    // 32 KB: two k-blocks of [128 channels x 64 k], ONE TMA box
-constexpr int NSLOT = 2;
+constexpr int NSLOT = 3;                                        // ring depth x 32 KB is what hides the TMA latency: with 2 slots
+                                                                // (one of look-ahead) a pass took 4.4-5.9 K cycles to issue 3.5 K of MMAs
 constexpr int STAGE_BOX = 128 * 128;                            // 16 KB: [128 channels x 64 tokens] bf16
 constexpr int OFF_XN = 0;
 constexpr int OFF_W = OFF_XN + XN_BYTES;                        // 73728 (multiple of 1024)
 constexpr int OFF_STAGE = OFF_W + NSLOT * SLOT_BYTES;           // 139264
-constexpr int OFF_BAR = OFF_STAGE + 4 * STAGE_BOX;              // 204800
+constexpr int OFF_BAR = OFF_STAGE + 2 * STAGE_BOX;              // staging: ONE tensor at a time (x0, then v * x1), two token halves
 constexpr int OFF_PART = OFF_BAR + 256;                         // LN partials [2][2][128] fp32
 constexpr int SMEM_TOTAL = OFF_PART + 2 * 2 * 128 * 4;          // 207104
 constexpr int THREADS = 320, EPI_THREADS = 256;
@@ -75,12 +76,14 @@ block_in_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
   if ((ptx::smem_u32(smem) & 1023u) != 0) __trap();
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
   uint64_t* w_full = bars;          // [NSLOT]
-  uint64_t* w_empty = bars + 4;     // [NSLOT]
+  uint64_t* w_empty = bars + 4;     // [NSLOT] (NSLOT <= 4)
   uint64_t* xn_full = bars + 8;     // LN warps wrote the B operand
   uint64_t* xn_free = bars + 9;     // both passes' MMAs finished reading it
-  uint64_t* acc_full = bars + 10;   // one pass accumulated
-  uint64_t* acc_free = bars + 11;   // epilogue drained TMEM
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 12);
+  // Two accumulator sets per pass so that the tensor pipe never waits for the epilogue to drain TMEM: A = the x0 group
+  // (columns [0,144)), B = the x1 and v groups ([144,432)).  While the epilogue drains one set the MMAs fill the other.
+  uint64_t* acc_full = bars + 10;   // [2] set A / B accumulated
+  uint64_t* acc_free = bars + 12;   // [2] epilogue drained set A / B
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 14);
   float (*s_part)[2][128] = reinterpret_cast<float (*)[2][128]>(smem + OFF_PART);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -94,7 +97,7 @@ block_in_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
     ptx::prefetch_tmap(&tmW); ptx::prefetch_tmap(&tmVX); ptx::prefetch_tmap(&tmX0); ptx::prefetch_tmap(&tmXN);
     for (int i = 0; i < NSLOT; ++i) { ptx::mbar_init(&w_full[i], 1); ptx::mbar_init(&w_empty[i], 1); }
     ptx::mbar_init(xn_full, 1); ptx::mbar_init(xn_free, 1);
-    ptx::mbar_init(acc_full, 1); ptx::mbar_init(acc_free, 8);
+    for (int i = 0; i < 2; ++i) { ptx::mbar_init(&acc_full[i], 1); ptx::mbar_init(&acc_free[i], 8); }
     ptx::fence_mbar_init();
   } else if (warp == 1) {
     ptx::tmem_alloc<512>(tmem_ptr);
@@ -140,10 +143,12 @@ block_in_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
         ptx::mbar_wait(xn_full, it & 1);
         stamp(0);
         for (int h = 0; h < 2; ++h, ++pass) {
-          ptx::mbar_wait(acc_free, (pass & 1) ^ 1);
-          ptx::tc_fence_after_sync();
-          stamp(0);
-          for (int g = 0; g < 3; ++g)
+          for (int g = 0; g < 3; ++g) {
+            if (g < 2) {   // g == 0 starts set A, g == 1 starts set B
+              ptx::mbar_wait(&acc_free[g], (pass & 1) ^ 1);
+              ptx::tc_fence_after_sync();
+              if (g == 0) stamp(0);
+            }
             for (int kp = 0; kp < 2; ++kp) {
               const uint32_t s = wi % NSLOT, ph = (wi / NSLOT) & 1;
               ptx::mbar_wait(&w_full[s], ph);
@@ -160,7 +165,9 @@ block_in_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
               ptx::umma_commit(&w_empty[s]);
               ++wi;
             }
-          ptx::umma_commit(acc_full);
+            if (g == 0) ptx::umma_commit(&acc_full[0]);
+            if (g == 2) ptx::umma_commit(&acc_full[1]);
+          }
           if (h == 1) ptx::umma_commit(xn_free);
           stamp(0);
         }
@@ -211,65 +218,53 @@ block_in_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
         if (issuer) ptx::tma_store_wait_read<0>();
         ptx::bar_sync(1, EPI_THREADS);
         if (tr) stamp(1);
-        ptx::mbar_wait(acc_full, pass & 1);
-        ptx::tc_fence_after_sync();
-        if (tr) stamp(1);
         const int cbase = HALO + hf * 64;   // first output column of this thread
+        const uint32_t swz = uint32_t(r & 7);
+        const uint32_t rowoff = uint32_t(r) * 128;
         float hm2[3], hm1[3];               // u[j-2], u[j-1] carried along the columns
-#pragma unroll
-        for (int g = 0; g < 3; ++g) {
+        auto halo = [&](int g) {
           uint32_t a, c2;
           tmem_ld_32x32b_x2(lane_addr + g * GCOLS + cbase - 2, a, c2);
           ptx::tmem_ld_wait();
           const int tm2 = t0 - HALO + cbase - 2;
           hm2[g] = (tm2 >= 0) ? __uint_as_float(a) + bia[g] : 0.f;
           hm1[g] = (tm2 + 1 >= 0) ? __uint_as_float(c2) + bia[g] : 0.f;
-        }
-#pragma unroll 1
-        for (int s = 0; s < 2; ++s) {       // two sub-blocks of 32 token columns
-          float uc[3][32];
+        };
+        // group g, sub-block s (32 token columns): 3-tap causal filter along this thread's registers
+        auto conv_sub = [&](int g, int s, float (&out)[32]) {
+          uint32_t a[32];
+          ptx::tmem_ld_32x32b_x32(lane_addr + g * GCOLS + cbase + s * 32, a);
+          ptx::tmem_ld_wait();
+          float um2 = hm2[g], um1 = hm1[g];
 #pragma unroll
-          for (int g = 0; g < 3; ++g) {
-            uint32_t a[32];
-            ptx::tmem_ld_32x32b_x32(lane_addr + g * GCOLS + cbase + s * 32, a);
-            ptx::tmem_ld_wait();
-            float um2 = hm2[g], um1 = hm1[g];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const float u = __uint_as_float(a[j]) + bia[g];   // cbase + s*32 + j >= HALO -> t >= 0
-              uc[g][j] = fmaf(w0[g], um2, fmaf(w1[g], um1, fmaf(w2[g], u, cbv[g])));
-              um2 = um1;
-              um1 = u;
-            }
-            hm2[g] = um2;
-            hm1[g] = um1;
+          for (int j = 0; j < 32; ++j) {
+            const float u = __uint_as_float(a[j]) + bia[g];   // cbase + s*32 + j >= HALO -> t >= 0
+            out[j] = fmaf(w0[g], um2, fmaf(w1[g], um1, fmaf(w2[g], u, cbv[g])));
+            um2 = um1;
+            um1 = u;
           }
-          if (s == 1) {                      // all TMEM reads of this pass are done
+          hm2[g] = um2;
+          hm1[g] = um1;
+        };
+        // ---- set A: x0
+        ptx::mbar_wait(&acc_full[0], pass & 1);
+        ptx::tc_fence_after_sync();
+        if (tr) stamp(1);
+        halo(0);
+#pragma unroll 1
+        for (int s = 0; s < 2; ++s) {
+          float x0v[32];
+          conv_sub(0, s, x0v);
+          if (s == 1) {                      // set A is in registers: the next pass may overwrite it
             ptx::tc_fence_before_sync();
             __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(acc_free);
+            if (lane == 0) ptx::mbar_arrive(&acc_free[0]);
           }
-          const uint32_t swz = uint32_t(r & 7);
-          const uint32_t rowoff = uint32_t(r) * 128;
 #pragma unroll
           for (int k = 0; k < 4; ++k) {     // 4 chunks of 8 tokens
-            const float* x0p = &uc[0][k * 8];
-            const float* x1p = &uc[1][k * 8];
-            const float* vp = &uc[2][k * 8];
+            const float* x0p = &x0v[k * 8];
             const uint32_t chunk = (uint32_t(s * 4 + k) ^ swz) << 4;
-            if (p.vx_f16) {
-              // the tensor-core conv reads whole 128-token rows: positions past the end of the read must be ZERO
-              float m[8];
-#pragma unroll
-              for (int e8 = 0; e8 < 8; ++e8) m[e8] = (t0 + hf * 64 + s * 32 + k * 8 + e8 < p.T) ? vp[e8] * x1p[e8] : 0.f;
-              ptx::st_shared_v4(sST + (0 * 2 + hf) * STAGE_BOX + rowoff + chunk, pack_f16(m[0], m[1]), pack_f16(m[2], m[3]),
-                                pack_f16(m[4], m[5]), pack_f16(m[6], m[7]));
-            }
-            else
-              ptx::st_shared_v4(sST + (0 * 2 + hf) * STAGE_BOX + rowoff + chunk, pack_bf16(vp[0] * x1p[0], vp[1] * x1p[1]),
-                                pack_bf16(vp[2] * x1p[2], vp[3] * x1p[3]), pack_bf16(vp[4] * x1p[4], vp[5] * x1p[5]),
-                                pack_bf16(vp[6] * x1p[6], vp[7] * x1p[7]));
-            ptx::st_shared_v4(sST + (1 * 2 + hf) * STAGE_BOX + rowoff + chunk, pack_bf16(x0p[0], x0p[1]),
+            ptx::st_shared_v4(sST + hf * STAGE_BOX + rowoff + chunk, pack_bf16(x0p[0], x0p[1]),
                               pack_bf16(x0p[2], x0p[3]), pack_bf16(x0p[4], x0p[5]), pack_bf16(x0p[6], x0p[7]));
           }
         }
@@ -277,10 +272,52 @@ block_in_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
         ptx::bar_sync(2, EPI_THREADS);
         if (issuer) {
 #pragma unroll
-          for (int hh = 0; hh < 2; ++hh) {
-            ptx::tma_store_3d(&tmVX, smem + OFF_STAGE + (0 * 2 + hh) * STAGE_BOX, t0 + hh * 64, h * 128, b);
-            ptx::tma_store_3d(&tmX0, smem + OFF_STAGE + (1 * 2 + hh) * STAGE_BOX, t0 + hh * 64, h * 128, b);
+          for (int hh = 0; hh < 2; ++hh) ptx::tma_store_3d(&tmX0, smem + OFF_STAGE + hh * STAGE_BOX, t0 + hh * 64, h * 128, b);
+          ptx::tma_store_commit();
+        }
+        // ---- set B: v * x1
+        ptx::mbar_wait(&acc_full[1], pass & 1);
+        ptx::tc_fence_after_sync();
+        halo(1);
+        halo(2);
+#pragma unroll 1
+        for (int s = 0; s < 2; ++s) {
+          float x1v[32], vv[32];
+          conv_sub(1, s, x1v);
+          conv_sub(2, s, vv);
+          if (s == 1) {
+            ptx::tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&acc_free[1]);
           }
+          if (s == 0) {   // the staging buffers are being read by the x0 store of this pass (long since issued)
+            if (issuer) ptx::tma_store_wait_read<0>();
+            ptx::bar_sync(1, EPI_THREADS);
+          }
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float* x1p = &x1v[k * 8];
+            const float* vp = &vv[k * 8];
+            const uint32_t chunk = (uint32_t(s * 4 + k) ^ swz) << 4;
+            if (p.vx_f16) {
+              // the tensor-core conv reads whole 128-token rows: positions past the end of the read must be ZERO
+              float m[8];
+#pragma unroll
+              for (int e8 = 0; e8 < 8; ++e8) m[e8] = (t0 + hf * 64 + s * 32 + k * 8 + e8 < p.T) ? vp[e8] * x1p[e8] : 0.f;
+              ptx::st_shared_v4(sST + hf * STAGE_BOX + rowoff + chunk, pack_f16(m[0], m[1]), pack_f16(m[2], m[3]),
+                                pack_f16(m[4], m[5]), pack_f16(m[6], m[7]));
+            } else {
+              ptx::st_shared_v4(sST + hf * STAGE_BOX + rowoff + chunk, pack_bf16(vp[0] * x1p[0], vp[1] * x1p[1]),
+                                pack_bf16(vp[2] * x1p[2], vp[3] * x1p[3]), pack_bf16(vp[4] * x1p[4], vp[5] * x1p[5]),
+                                pack_bf16(vp[6] * x1p[6], vp[7] * x1p[7]));
+            }
+          }
+        }
+        ptx::fence_proxy_async_smem();
+        ptx::bar_sync(2, EPI_THREADS);
+        if (issuer) {
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) ptx::tma_store_3d(&tmVX, smem + OFF_STAGE + hh * STAGE_BOX, t0 + hh * 64, h * 128, b);
           ptx::tma_store_commit();
         }
         if (tr) stamp(1);
