@@ -560,12 +560,12 @@ TcPlan tc_plan(int T) {
   if (T > tc::C && rem > 0 && rem <= LONGCONV_TAIL_MAX) return {T / tc::C, rem};
   return {std::max(1, (T + tc::C - 1) / tc::C), 0};
 }
-size_t tc_scratch_per_cta(int nc) { return nc > 1 ? (size_t)(nc - 1) * 2 * tc::N + 2 * tc::C : 0; }   // floats
+size_t tc_scratch_per_cta(int nc) { return nc > 1 ? (size_t)(nc - 1) * tc::N + 2 * tc::C : 0; }   // floats (parked spectra are fp16 pairs)
 
 bool tc_conv_applies(const clm_ctx* c, int T) {
   if (!c->tc_conv || T <= tc::C / 2 || c->layers[0].gtc == nullptr) return false;
   const TcPlan pl = tc_plan(T);
-  return pl.nc == 1 || (c->tc_chunked && pl.nc <= c->tc_nseg);
+  return pl.nc == 1 || (c->tc_chunked && pl.nc <= std::min(c->tc_nseg, 4));   // the kernel's segment loop is unrolled for <= 4 chunks
 }
 
 // vx is fp16 here (block_in writes it that way when the tensor-core conv follows)

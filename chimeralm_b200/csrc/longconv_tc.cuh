@@ -54,7 +54,7 @@ struct LongConvTcParams {
   // chunked mode (reads longer than 8200 tokens, overlap-add over chunks of 8192 tokens): n_chunks > 1
   int n_chunks;              // transforms per item
   int nt;                    // tail tokens after the last chunk (0..LONGCONV_TAIL_MAX), finished by direct products
-  float* scratch;            // per CTA: (n_chunks - 1) parked spectra (16384 float2 each) + carry (2 x 8192 float)
+  float* scratch;            // per CTA: (n_chunks - 1) parked spectra (16384 x fp16 (re, im) each) + carry (2 x 8192 float)
   long long scratch_per_cta; // floats
   long long g_seg_stride;    // uint4 between the spectrum tables of consecutive filter segments
   long long* trace;          // optional [2][64] clock64 stamps of CTA 0: row 0 = MMA issuer, row 1 = epilogue warp 2
@@ -378,8 +378,8 @@ longconv_tc_kernel(const __grid_constant__ CUtensorMap tmVX, const __grid_consta
     const float2 w2 = make_float2(wstep.x * wstep.x - wstep.y * wstep.y, 2.0f * wstep.x * wstep.y);
     // chunked mode: this CTA's scratch = parked spectra of chunks 0..NC-2 (float4 = two complex values; a warp's 32 lanes
     // write 512 contiguous bytes) followed by the carry (second halves of the last inverse transform, [2][64][128] fp32)
-    float4* park = reinterpret_cast<float4*>(p.scratch + (long long)blockIdx.x * p.scratch_per_cta);
-    float* carry = p.scratch + (long long)blockIdx.x * p.scratch_per_cta + (long long)(NC - 1) * 2 * N;
+    uint4* park = reinterpret_cast<uint4*>(p.scratch + (long long)blockIdx.x * p.scratch_per_cta);
+    float* carry = p.scratch + (long long)blockIdx.x * p.scratch_per_cta + (long long)(NC - 1) * N;
     const int e_warp = warp - 2;
     for (uint32_t it = 0; it < (uint32_t)n_units; ++it) {
       const uint32_t ph = it & 1, buf = it & 1;
@@ -478,30 +478,36 @@ longconv_tc_kernel(const __grid_constant__ CUtensorMap tmVX, const __grid_consta
         if constexpr (CH) {
           // park this chunk's spectrum for the later chunks, then add the earlier chunks' spectra times the later filter
           // segments: W_c = sum_j S_{c-j} G_j (overlap-add in the frequency domain, one inverse transform per chunk)
-          const size_t slot = (((size_t)u * 8) * 8 + e_warp) * 32 + lane;   // + v * 256 per float4, + chunk * 8192
+          // (parked as fp16 in the layout of the spectrum table - the sum is rounded to fp16 right below anyway - so a run
+          // is 4 x 16 B per thread; chunk region = 4096 uint4)
+          const size_t slot = ((size_t)u * 4 * 8 + e_warp) * 32 + lane;   // + v * 256 per uint4, + chunk * 4096
           if (c < NC - 1) {
 #pragma unroll
-            for (int v = 0; v < 8; ++v)
-              park[(size_t)c * 8192 + slot + (size_t)v * 256] =
-                  make_float4(__uint_as_float(xr[2 * v]), __uint_as_float(xi[2 * v]), __uint_as_float(xr[2 * v + 1]), __uint_as_float(xi[2 * v + 1]));
+            for (int v = 0; v < 4; ++v)
+              park[(size_t)c * 4096 + slot + (size_t)v * 256] =
+                  make_uint4(pack_f16(__uint_as_float(xr[4 * v]), __uint_as_float(xr[4 * v + 1])),
+                             pack_f16(__uint_as_float(xi[4 * v]), __uint_as_float(xi[4 * v + 1])),
+                             pack_f16(__uint_as_float(xr[4 * v + 2]), __uint_as_float(xr[4 * v + 3])),
+                             pack_f16(__uint_as_float(xi[4 * v + 2]), __uint_as_float(xi[4 * v + 3])));
           }
 #pragma unroll 1
           for (int j = 1; j <= c; ++j) {
             const uint4* gj = gp + (size_t)j * p.g_seg_stride + g_off(u);
-            uint4 gq[4];
-            float4 sv[8];
+            uint4 gq[4], sq[4];
 #pragma unroll
-            for (int v = 0; v < 4; ++v) gq[v] = __ldg(gj + v * 32);
-#pragma unroll
-            for (int v = 0; v < 8; ++v) sv[v] = park[(size_t)(c - j) * 8192 + slot + (size_t)v * 256];
+            for (int v = 0; v < 4; ++v) {
+              gq[v] = __ldg(gj + v * 32);
+              sq[v] = park[(size_t)(c - j) * 4096 + slot + (size_t)v * 256];
+            }
 #pragma unroll
             for (int v = 0; v < 4; ++v) {
               const uint32_t gw[4] = {gq[v].x, gq[v].y, gq[v].z, gq[v].w};
+              const uint32_t sw[4] = {sq[v].x, sq[v].y, sq[v].z, sq[v].w};
 #pragma unroll
               for (int hp = 0; hp < 2; ++hp) {
                 const int m = 2 * v + hp;   // elements 2 m, 2 m + 1
                 const f2t GR = h2_to_f2(gw[2 * hp]), GI = h2_to_f2(gw[2 * hp + 1]);
-                const f2t XR = f2_pack(sv[m].x, sv[m].z), XI = f2_pack(sv[m].y, sv[m].w);
+                const f2t XR = h2_to_f2(sw[2 * hp]), XI = h2_to_f2(sw[2 * hp + 1]);
                 ar[m] = f2_sub(f2_fma(XR, GR, ar[m]), f2_mul(XI, GI));
                 ai[m] = f2_fma(XI, GR, f2_fma(XR, GI, ai[m]));
               }

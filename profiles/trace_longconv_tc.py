@@ -9,10 +9,10 @@ sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 from chimeralm_b200.engine import Engine, _stream_ptr  # noqa: E402
 from chimeralm_b200.weights import make_state_dict  # noqa: E402
 
-B = 32
-eng = Engine(make_state_dict(0), device=0, max_batch=B, max_tokens=8200)
-for T in (8192, 8193):
-    Tp = (T + 63) // 64 * 64
+B = 16
+eng = Engine(make_state_dict(0), device=0, max_batch=B, max_tokens=32769)
+for T in (tuple(int(a) for a in sys.argv[1:]) or (8192, 8193)):
+    Tp = (T + 127) // 128 * 128
     vx = (torch.randn(B, 256, Tp, device="cuda") * 0.3).half()
     x0 = torch.randn(B, 256, Tp, device="cuda").bfloat16()
     out = torch.zeros_like(x0)
