@@ -246,3 +246,27 @@ def test_cli_predict_subprocess(tmp_path, gpus):
         outs[g] = load_predictions_from_folder(out)
     assert len(outs[1]) == 96 - 14   # every 7th record has no SA tag
     assert outs[gpus] == outs[1]
+
+
+def test_full_size_batch_permutation_invariance(state_dict):
+    """Size-independent property at the K2 size (32 reads x 8193 tokens, too big for the CPU oracle in a test): reads are
+    independent, so permuting the batch permutes the logits.  Not bit-exact by construction - the tensor-core conv carries two
+    reads in one complex transform, and a read's fp16 operand roundings depend on its partner - but far inside the logit
+    tolerance; the same reads against the oracle are covered at B = 2 by test_logits_and_labels."""
+    from chimeralm_b200.engine import Engine
+
+    B, T = 32, 8193
+    eng = Engine(state_dict, device=0, max_batch=B, max_tokens=T)
+    try:
+        ids = _ids(B, T, seed=123, pad_left=2000).to(torch.uint8).cuda()
+        base = eng.forward(ids).clone()
+        g = torch.Generator().manual_seed(5)
+        for _ in range(2):
+            perm = torch.randperm(B, generator=g).cuda()
+            out = eng.forward(ids[perm].contiguous())
+            assert (out - base[perm]).abs().max().item() <= 1e-3
+        # an odd batch (the last read has no partner in the conv) and a batch of one
+        assert (eng.forward(ids[:31].contiguous()) - base[:31]).abs().max().item() <= 1e-3
+        assert (eng.forward(ids[7:8].contiguous()) - base[7:8]).abs().max().item() <= 1e-3
+    finally:
+        eng.close()
