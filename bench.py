@@ -310,6 +310,7 @@ def main():
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": workload_config(L, T, B, world),
+        "dtype_note": "bf16 GEMM operands, fp16 operands in the tensor-core FFT conv, fp32 accumulation / residual / pooling / head",
         "bases_per_s": reads_per_s * L,
         "tokens_per_s": reads_per_s * T,
         "dense_tensor_frac_of_peak": dense_frac,
