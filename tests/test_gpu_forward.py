@@ -270,3 +270,26 @@ def test_full_size_batch_permutation_invariance(state_dict):
         assert (eng.forward(ids[7:8].contiguous()) - base[7:8]).abs().max().item() <= 1e-3
     finally:
         eng.close()
+
+
+@pytest.mark.parametrize("option,T", [("fused_score_pool", 1500), ("fused_head", 1500), ("tc_conv", 8193), ("tc_chunked", 9000),
+                                      ("fused_mlp", 700), ("fused_in", 700), ("fast_conv", 700), ("mlp_epi16", 1500)])
+def test_kernel_variants_agree(state_dict, option, T):
+    """Every `clm_set_option` switch selects a different kernel for the same math (fused vs unfused, tensor-core vs fp32 FFT,
+    8 vs 16 epilogue warps): flipping it must not move the logits by more than the parity tolerance."""
+    from chimeralm_b200.engine import Engine
+
+    B = 3
+    eng = Engine(state_dict, device=0, max_batch=B, max_tokens=T)
+    try:
+        ids = _ids(B, T, seed=T, pad_left=T // 4).to(torch.uint8).cuda()
+        base = eng.forward(ids).clone()
+        default_on = option != "mlp_epi16"
+        eng.set_option(option, 0 if default_on else 1)
+        other = eng.forward(ids).clone()
+        eng.set_option(option, 1 if default_on else 0)
+        again = eng.forward(ids)
+        assert (other - base).abs().max().item() <= LOGIT_TOL, option
+        assert torch.equal(again, base), option
+    finally:
+        eng.close()
