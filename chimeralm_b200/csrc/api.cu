@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstring>
 #include <map>
+#include <set>
 #include <string>
 #include <vector>
 
@@ -132,6 +133,8 @@ struct clm_ctx {
   long long launches = 0;
   EncodeTiledFn encode_tiled = nullptr;
   std::vector<void*> owned;  // device allocations freed at destroy
+  std::vector<bm::LayerConsts> h_mlp;     // this model's block-tail constants (the __constant__ bank is per DEVICE, see bind_constants)
+  std::set<const void*> smem_attr_done;   // kernels whose dynamic-smem limit was raised on THIS device (per context, not per process)
 };
 
 namespace {
@@ -169,6 +172,24 @@ static const bool g_sync_check = [] { const char* e = getenv("CLM_SYNC_CHECK"); 
     }                                                                                                \
     (ctx)->launches++;                                                                               \
   } while (0)
+
+// bm::c_mlp is ONE __constant__ bank per device, shared by every context (model) on it: before a block-tail launch make sure
+// it holds THIS model's biases (a second model finalized on the same device would otherwise silently replace them).
+const clm_ctx* g_const_owner[64] = {nullptr};
+int bind_constants(clm_ctx* c, cudaStream_t st) {
+  const int dev = c->device & 63;
+  if (g_const_owner[dev] == c || c->h_mlp.empty()) return 0;
+  CLM_CUDA(c, cudaMemcpyToSymbolAsync(bm::c_mlp, c->h_mlp.data(), c->h_mlp.size() * sizeof(bm::LayerConsts), 0, cudaMemcpyHostToDevice, st));
+  g_const_owner[dev] = c;
+  return 0;
+}
+
+int ensure_smem_attr(clm_ctx* c, const void* func, int bytes) {
+  if (c->smem_attr_done.count(func)) return 0;
+  CLM_CUDA(c, cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  c->smem_attr_done.insert(func);
+  return 0;
+}
 
 template <typename T>
 int dev_alloc(clm_ctx* c, T** p, size_t count) {
@@ -266,12 +287,8 @@ int to_bf16(clm_ctx* c, const float* src, int64_t n, __nv_bfloat16** out) {
 template <int BN, int STAGES, int EPI>
 int launch_gemm_t(clm_ctx* c, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t st) {
   using S = GemmSmem<BN, STAGES>;
-  static bool attr_set = false;
   auto kern = gemm_bf16_tn_kernel<BN, STAGES, EPI>;
-  if (!attr_set) {
-    CLM_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
-    attr_set = true;
-  }
+  if (int rc_attr = ensure_smem_attr(c, (const void*)(kern), (int)(S::kTotal))) return rc_attr;
   dim3 grid((unsigned)(((p.M + GEMM_BM - 1) / GEMM_BM) * (p.N / BN)));
   kern<<<grid, GEMM_THREADS, S::kTotal, st>>>(tmA, tmB, p);
   CLM_LAUNCH_CHECK(c, "gemm_bf16_tn");
@@ -323,11 +340,7 @@ int make_tmap_xn(clm_ctx* c, CUtensorMap* tm, const void* base, int B, int T, in
 
 int launch_block_in(clm_ctx* c, int layer, const __nv_bfloat16* xn, int B, int T, int Tp, __nv_bfloat16* vx,
                     __nv_bfloat16* x0, cudaStream_t st, long long* trace = nullptr, bool vx_f16 = false) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    CLM_CUDA(c, cudaFuncSetAttribute(block_in_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bi::SMEM_TOTAL));
-    attr_set = true;
-  }
+  if (int rc_attr = ensure_smem_attr(c, (const void*)(block_in_kernel), (int)(bi::SMEM_TOTAL))) return rc_attr;
   LayerW& L = c->layers[layer];
   CUtensorMap tmVX, tmX0, tmXN;
   int rc;
@@ -348,11 +361,8 @@ int launch_block_in(clm_ctx* c, int layer, const __nv_bfloat16* xn, int B, int T
 // y token-major [M,256] when B == 0; channel-major [B][256][Tp] (M == B*T) otherwise
 int launch_block_mlp(clm_ctx* c, int layer, const __nv_bfloat16* y, float* res, int M, cudaStream_t st,
                      long long* trace = nullptr, int B = 0, int T = 0, int Tp = 0, __nv_bfloat16* xn_out = nullptr) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    CLM_CUDA(c, cudaFuncSetAttribute(block_mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bm::SMEM_TOTAL));
-    attr_set = true;
-  }
+  if (int rc_attr = ensure_smem_attr(c, (const void*)(block_mlp_kernel), (int)(bm::SMEM_TOTAL))) return rc_attr;
+  if (int rc_c = bind_constants(c, st)) return rc_c;
   LayerW& L = c->layers[layer];
   CUtensorMap tmY;
   int rc;
@@ -382,11 +392,7 @@ int launch_block_mlp(clm_ctx* c, int layer, const __nv_bfloat16* y, float* res, 
     if ((rc = make_tmap_xn(c, &tmXN, xn_out, B > 0 ? B : 1, B > 0 ? T : M, 128))) return rc;
   }
   if (c->mlp_2cta && !trace) {
-    static bool attr2_set = false;
-    if (!attr2_set) {
-      CLM_CUDA(c, cudaFuncSetAttribute(block_mlp2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bm2::SMEM_TOTAL2));
-      attr2_set = true;
-    }
+    if (int rc_attr = ensure_smem_attr(c, (const void*)(block_mlp2_kernel), (int)(bm2::SMEM_TOTAL2))) return rc_attr;
     const int n_pair_tiles = (p.num_tiles + 1) / 2;
     const int grid2 = 2 * std::min(n_pair_tiles, c->num_sms / 2);
     block_mlp2_kernel<<<grid2, bm::THREADS, bm2::SMEM_TOTAL2, st>>>(tmY, L.tm_out_h, L.tm_fc1_h, L.tm_fc2_h, tmXN, p);
@@ -395,11 +401,7 @@ int launch_block_mlp(clm_ctx* c, int layer, const __nv_bfloat16* y, float* res, 
   }
   const int grid = std::min(p.num_tiles, c->num_sms);
   if (c->mlp_epi16) {
-    static bool attr16_set = false;
-    if (!attr16_set) {
-      CLM_CUDA(c, cudaFuncSetAttribute(block_mlp16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bm16::SMEM_TOTAL));
-      attr16_set = true;
-    }
+    if (int rc_attr = ensure_smem_attr(c, (const void*)(block_mlp16_kernel), (int)(bm16::SMEM_TOTAL))) return rc_attr;
     block_mlp16_kernel<<<grid, bm16::THREADS, bm16::SMEM_TOTAL, st>>>(tmY, L.tm_out_t, L.tm_fc1_t, L.tm_fc2_t, tmXN, p);
     CLM_LAUNCH_CHECK(c, "block_mlp16");
     return 0;
@@ -464,12 +466,8 @@ template <int LOGN>
 int conv_fast_t(clm_ctx* c, const LongConvFastParams& p, int grid, cudaStream_t st) {
   if constexpr (FastCfg<LOGN>::kSupported) {
     using F = FastCfg<LOGN>;
-    static bool attr_set = false;
     auto kern = longconv_fast_kernel<LOGN>;
-    if (!attr_set) {
-      CLM_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, F::SMEM));
-      attr_set = true;
-    }
+    if (int rc_attr = ensure_smem_attr(c, (const void*)(kern), (int)(F::SMEM))) return rc_attr;
     kern<<<grid, F::THREADS, F::SMEM, st>>>(p);
     CLM_LAUNCH_CHECK(c, "longconv_fast");
     return 0;
@@ -481,12 +479,8 @@ int conv_fast_t(clm_ctx* c, const LongConvFastParams& p, int grid, cudaStream_t 
 template <int LOGN>
 int conv_t(clm_ctx* c, const LongConvParams& p, int grid, cudaStream_t st) {
   using Cfg = ConvCfg<LOGN>;
-  static bool attr_set = false;
   auto kern = longconv_kernel<LOGN>;
-  if (!attr_set) {
-    CLM_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
-    attr_set = true;
-  }
+  if (int rc_attr = ensure_smem_attr(c, (const void*)(kern), (int)(Cfg::SMEM))) return rc_attr;
   kern<<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(p);
   CLM_LAUNCH_CHECK(c, "longconv");
   return 0;
@@ -576,12 +570,8 @@ int launch_longconv_tc(clm_ctx* c, int layer, const __half* vx, const __nv_bfloa
   const bool whole_rows = T >= tc::C && pl.nc == 1;   // every 128-token row the kernel touches lies inside [0, Tp)
   if (!whole_rows && Tp % 128 != 0) return fail(c, CLM_ERR_INVALID, "longconv_tc: Tp must be a multiple of 128 for T=%d", T);
   const cuuint64_t n_rows = (cuuint64_t)(whole_rows ? std::min(64, Tp / 128) : Tp / 128);   // 128-token rows per channel
-  static bool attr_set = false;
-  if (!attr_set) {
-    CLM_CUDA(c, cudaFuncSetAttribute(longconv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_TOTAL));
-    CLM_CUDA(c, cudaFuncSetAttribute(longconv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_TOTAL));
-    attr_set = true;
-  }
+  if (int rc_attr = ensure_smem_attr(c, (const void*)(longconv_tc_kernel<false>), (int)(tc::SMEM_TOTAL))) return rc_attr;
+  if (int rc_attr = ensure_smem_attr(c, (const void*)(longconv_tc_kernel<true>), (int)(tc::SMEM_TOTAL))) return rc_attr;
   if (tc_scratch_per_cta(pl.nc) * c->num_sms > c->tc_scratch_floats)
     return fail(c, CLM_ERR_STATE, "longconv_tc: scratch too small for T=%d; call clm_reserve with max_T >= %d", T, T);
   LayerW& L = c->layers[layer];
@@ -728,6 +718,7 @@ int clm_create(const clm_config* cfg, int device, clm_ctx** out) {
 
 void clm_destroy(clm_ctx* c) {
   if (!c) return;
+  if (g_const_owner[c->device & 63] == c) g_const_owner[c->device & 63] = nullptr;
   cudaSetDevice(c->device);
   cudaDeviceSynchronize();
   for (void* p : c->owned)
@@ -821,11 +812,11 @@ int clm_finalize(clm_ctx* c) {
       if ((rc = make_tmap_retiled(c, &L.tm_out_h, L.out_wt, (long long)D * D / 64, 128))) return rc;
       if ((rc = make_tmap_retiled(c, &L.tm_fc1_h, L.fc1_wt, (long long)g.d_inner * D / 64, 64))) return rc;
       if ((rc = make_tmap_retiled(c, &L.tm_fc2_h, L.fc2_wt, (long long)g.d_inner * D / 64, 128))) return rc;
-      static bm::LayerConsts hc;
+      if ((int)c->h_mlp.size() <= l) c->h_mlp.resize(l + 1);
+      bm::LayerConsts& hc = c->h_mlp[l];
       CLM_CUDA(c, cudaMemcpy(hc.b_out, L.out_b, sizeof hc.b_out, cudaMemcpyDeviceToHost));
       CLM_CUDA(c, cudaMemcpy(hc.b2, L.fc2_b, sizeof hc.b2, cudaMemcpyDeviceToHost));
       CLM_CUDA(c, cudaMemcpy(hc.b1, b1f, sizeof hc.b1, cudaMemcpyDeviceToHost));
-      CLM_CUDA(c, cudaMemcpyToSymbol(bm::c_mlp, &hc, sizeof hc, (size_t)l * sizeof(bm::LayerConsts)));
     }
     // implicit filter k[l] = HyenaFilter.filter(Lmax)
     FilterGenParams fp{};
@@ -1103,11 +1094,7 @@ int clm_forward(clm_ctx* c, const void* d_ids, int ids_dtype, int B, int T, floa
   const bool sp_fused = tail_folded && c->fused_score_pool && c->dbg_layer != NL;
   int n_split = c->n_split;
   if (sp_fused) {
-    static bool attr_set = false;
-    if (!attr_set) {
-      CLM_CUDA(c, cudaFuncSetAttribute(score_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sp::SMEM_TOTAL));
-      attr_set = true;
-    }
+    if (int rc_attr = ensure_smem_attr(c, (const void*)(score_pool_kernel), (int)(sp::SMEM_TOTAL))) return rc_attr;
     ProfScope ps_(c, PC_SCORE, st);
     CUtensorMap tmA;
     if ((rc = make_tmap_xn(c, &tmA, c->XN, B, T, sp::BM))) return rc;
@@ -1157,11 +1144,7 @@ int clm_forward(clm_ctx* c, const void* d_ids, int ids_dtype, int B, int T, floa
       c->head_base += 5u * (unsigned)grid;   // five grid barriers per launch; the counter is never reset
       void* args[] = {&hf};
       constexpr size_t head_smem = (size_t)HEAD_BT * 512 * sizeof(float);
-      static bool head_attr = false;
-      if (!head_attr) {
-        CLM_CUDA(c, cudaFuncSetAttribute(head_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)head_smem));
-        head_attr = true;
-      }
+      if (int rc_attr = ensure_smem_attr(c, (const void*)(head_fused_kernel), (int)((int)head_smem))) return rc_attr;
       CLM_CUDA(c, cudaLaunchCooperativeKernel((const void*)head_fused_kernel, dim3(grid), dim3(256), args, head_smem, st));
       CLM_LAUNCH_CHECK(c, "head_fused");
     } else {

@@ -293,3 +293,31 @@ def test_kernel_variants_agree(state_dict, option, T):
         assert torch.equal(again, base), option
     finally:
         eng.close()
+
+
+def test_two_models_on_one_device_do_not_share_constants(state_dict):
+    """The block-tail biases live in a __constant__ bank, which is per device, not per context: two models with different
+    weights on the same GPU must each see their own (the bank is re-bound when the launching model changes)."""
+    from chimeralm_b200.engine import Engine
+    from chimeralm_b200.weights import make_state_dict
+
+    sd_b = {k: torch.as_tensor(v) for k, v in make_state_dict(1).items()}
+    B, T = 2, 600
+    ids = _ids(B, T, seed=9).to(torch.uint8).cuda()
+    a = Engine(state_dict, device=0, max_batch=B, max_tokens=T)
+    ref_a = a.forward(ids).clone()
+    b = Engine(sd_b, device=0, max_batch=B, max_tokens=T)   # finalizing b used to overwrite a's biases
+    try:
+        ref_b = b.forward(ids).clone()
+        assert not torch.allclose(ref_a, ref_b)
+        for _ in range(2):
+            assert torch.equal(a.forward(ids), ref_a)
+            assert torch.equal(b.forward(ids), ref_b)
+    finally:
+        a.close()
+        b.close()
+    c = Engine(sd_b, device=0, max_batch=B, max_tokens=T)
+    try:
+        assert torch.equal(c.forward(ids), ref_b)
+    finally:
+        c.close()
