@@ -21,7 +21,7 @@
 // constants.  All constant operands are slices of ONE 96 KB stack S = [-Im F; Re F; Im F]
 // (384 rows x 128 K, fp16, 128-byte swizzled K-major), resident in shared memory.
 // Error of the fp16 operand rounding: ~4e-4 relative L2 on real layer inputs, a third of the bf16
-// rounding the output gets anyway (profiles/probes/fp16_monarch_fft_emulation.py).
+// rounding the output gets anyway (tests/probes/fp16_monarch_fft_emulation.py).
 //
 // TMEM: X = cols [0,256), Y = cols [256,512).  step 1 -> X (A_re | A_im); E1 packs P1 in place over
 // X[0,128); step 3 -> Y (S_re | S_im); E2 packs P2 over Y[0,128); step 5 -> X (B_im | B_re);

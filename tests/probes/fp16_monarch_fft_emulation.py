@@ -1,7 +1,8 @@
 """Numerical emulation (CPU, torch) of a tensor-core Monarch FFT long conv with fp16 operands and
 fp32 accumulation: N = 16384 = 128 x 128, two reads per complex transform, operands rounded to
 fp16 before every matrix product - compared with a float64 direct FFT conv on REAL layer inputs
-(vx = v * x1 and the implicit filter of each layer, from the oracle)."""
+(vx = v * x1 and the implicit filter of each layer, from the oracle).  Test infrastructure (it imports `oracle/`), not
+part of the product; run by hand: `python tests/probes/fp16_monarch_fft_emulation.py [g16]`."""
 import math
 import sys
 from pathlib import Path
