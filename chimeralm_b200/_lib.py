@@ -74,6 +74,7 @@ _SIGNATURES = {
     "clm_bam_close": (None, [C.c_void_p]),
     "clm_bam_error": (C.c_char_p, [C.c_void_p]),
     "clm_bam_records_seen": (C.c_longlong, [C.c_void_p]),
+    "clm_bam_set_chunk_bytes": (C.c_int, [C.c_void_p, C.c_longlong]),
     "clm_bam_set_shard": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "clm_bam_next": (C.c_longlong, [C.c_void_p, C.c_longlong, C.c_longlong, C.c_int, C.c_void_p, C.c_longlong,
                                     C.c_void_p, C.c_void_p, C.c_int]),

@@ -120,9 +120,11 @@ Chunk clm_bam::load_chunk() {
       out.eof = true;
       return out;
     }
-    if (file_eof) out.err = "truncated BGZF block at end of file";
-    else out.err = "BGZF block does not fit the read chunk";
-    return out;
+    if (file_eof) {
+      out.err = "truncated BGZF block at end of file";
+      return out;
+    }
+    return load_chunk();   // the read so far ends inside the first block (tiny chunk size): read more, cbuf keeps the carry
   }
   out.data.resize(out_off);
   std::atomic<size_t> cursor{0};
@@ -295,6 +297,13 @@ void clm_bam_close(clm_bam* r) {
 const char* clm_bam_error(const clm_bam* r) { return r ? r->err.c_str() : g_open_err.c_str(); }
 
 long long clm_bam_records_seen(const clm_bam* r) { return r ? r->n_records : 0; }
+
+int clm_bam_set_chunk_bytes(clm_bam* r, long long bytes) {
+  if (!r || bytes < 64) return CLM_ERR_INVALID;
+  if (r->next.valid()) r->next.wait();   // the background load reads chunk_bytes: change it only between loads
+  r->chunk_bytes = (size_t)bytes;
+  return CLM_OK;
+}
 
 int clm_bam_set_shard(clm_bam* r, int rank, int world) {
   if (!r || world < 1 || rank < 0 || rank >= world) return CLM_ERR_INVALID;

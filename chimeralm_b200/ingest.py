@@ -23,7 +23,7 @@ NAME_STRIDE = 256  # BAM l_read_name is one byte: names are at most 254 chars + 
 class NativeBamReader:
     """Streaming reader: `next_block()` fills caller-sized buffers with the next kept reads."""
 
-    def __init__(self, path: str | Path, n_threads: int = 0):
+    def __init__(self, path: str | Path, n_threads: int = 0, chunk_bytes: int | None = None):
         self.lib = _lib.load()
         h = C.c_void_p()
         rc = self.lib.clm_bam_open(str(path).encode(), int(n_threads), C.byref(h))
@@ -31,6 +31,8 @@ class NativeBamReader:
             msg = self.lib.clm_bam_error(None)
             raise ValueError(f"clm_bam_open failed (status {rc}): {msg.decode() if msg else '?'}")
         self.h = h
+        if chunk_bytes is not None and self.lib.clm_bam_set_chunk_bytes(self.h, int(chunk_bytes)) < 0:
+            raise ValueError(f"bad chunk size {chunk_bytes}")
 
     def next_block(self, max_reads: int, max_bases: int, bases: np.ndarray, offsets: np.ndarray,
                    names: np.ndarray | None, chimeric_only: bool = True) -> int:
@@ -84,7 +86,7 @@ def _names_from_rows(rows: np.ndarray) -> list[str]:
 
 
 def read_bam_flat(path: str | Path, max_bases: int, max_reads: int | None = None, chimeric_only: bool = True,
-                  n_threads: int = 0, block_reads: int = 8192, block_bytes: int = 64 << 20):
+                  n_threads: int = 0, block_reads: int = 8192, block_bytes: int = 64 << 20, chunk_bytes: int | None = None):
     """All kept reads of a BAM as (names, flat uint8 bases, int64 offsets[n+1]), file order."""
     block_bytes = max(block_bytes, max_bases)
     names: list[str] = []
@@ -93,7 +95,7 @@ def read_bam_flat(path: str | Path, max_bases: int, max_reads: int | None = None
     bases = np.empty(block_bytes, np.uint8)
     offs = np.empty(block_reads + 1, np.int64)
     nm = np.empty((block_reads, NAME_STRIDE), np.uint8)
-    with NativeBamReader(path, n_threads) as rd:
+    with NativeBamReader(path, n_threads, chunk_bytes) as rd:
         while max_reads is None or len(names) < max_reads:
             want = block_reads if max_reads is None else min(block_reads, max_reads - len(names))
             n = rd.next_block(want, max_bases, bases, offs, nm, chimeric_only)

@@ -172,6 +172,9 @@ void clm_bam_close(clm_bam* r);
 const char* clm_bam_error(const clm_bam* r);
 /* Records consumed so far (kept or not). */
 long long clm_bam_records_seen(const clm_bam* r);
+/* Compressed bytes read from the file per background load (default 16 MiB); mainly for tests of the block / record carry
+ * across loads. */
+int clm_bam_set_chunk_bytes(clm_bam* r, long long bytes);
 /* Data-parallel sharding (Lightning's predict sampler: rank r takes kept reads r, r+W, ...,
  * chimeralm/data/bam.py:287-299 under DDP): after this call clm_bam_next only returns the
  * kept reads whose running index i satisfies i % world == rank; the others are skipped

@@ -315,3 +315,19 @@ def test_fastq_and_parquet_predict_inputs(tmp_path):
         (batch,) = list(dm.predict_dataloader())
         assert batch["names"] == want_names, path
         assert batch["input_ids"].tolist() == want_ids, path
+
+
+def test_native_ingest_block_and_record_carry_across_file_chunks(tmp_path):
+    """BGZF blocks and BAM records that straddle the reader's file chunks (default 16 MiB, here a few bytes to a few
+    blocks) must come out identical; a synthetic file adds records longer than one BGZF block."""
+    from chimeralm_b200.bam import parse_bam_file_bytes
+    from chimeralm_b200.ingest import read_bam_flat
+
+    p = tmp_path / "synth.bam"
+    _synth_bam(p, n=150, seed=4)
+    for path in (GOLD / "test_chimric_reads.bam", p):
+        ref = list(parse_bam_file_bytes(path))
+        for chunk in (64, 999, 70_000, 200_001):
+            names, flat, offs = read_bam_flat(path, 1 << 20, chunk_bytes=chunk, n_threads=3, block_reads=11)
+            assert names == [n for n, _ in ref], (path, chunk)
+            assert all(np.array_equal(flat[offs[i] : offs[i + 1]], s) for i, (_, s) in enumerate(ref)), (path, chunk)
