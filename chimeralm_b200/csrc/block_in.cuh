@@ -58,8 +58,7 @@ constexpr int OFF_XN = 0;
 constexpr int OFF_W = OFF_XN + XN_BYTES;                        // 73728 (multiple of 1024)
 constexpr int OFF_STAGE = OFF_W + NSLOT * SLOT_BYTES;           // 139264
 constexpr int OFF_BAR = OFF_STAGE + 2 * STAGE_BOX;              // staging: ONE tensor at a time (x0, then v * x1), two token halves
-constexpr int OFF_PART = OFF_BAR + 256;                         // LN partials [2][2][128] fp32
-constexpr int SMEM_TOTAL = OFF_PART + 2 * 2 * 128 * 4;          // 207104
+constexpr int SMEM_TOTAL = OFF_BAR + 256;
 constexpr int THREADS = 320, EPI_THREADS = 256;
 constexpr int GCOLS = NCOL;                                     // TMEM columns per channel group
 }  // namespace bi
@@ -84,7 +83,6 @@ block_in_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
   uint64_t* acc_full = bars + 10;   // [2] set A / B accumulated
   uint64_t* acc_free = bars + 12;   // [2] epilogue drained set A / B
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 14);
-  float (*s_part)[2][128] = reinterpret_cast<float (*)[2][128]>(smem + OFF_PART);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   long long* trace = (p.trace && blockIdx.x == 0) ? p.trace : nullptr;
@@ -199,7 +197,6 @@ block_in_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
       const int b = tile / p.tiles_per_seq;
       const int t0 = (tile % p.tiles_per_seq) * BT;
-      const long long seq_row0 = (long long)b * p.T;
       const bool tr = trace && warp == 2 && lane == 0;
       if (tr) stamp(1);
       // ------------------------------------------------ two passes of conv + gate epilogue

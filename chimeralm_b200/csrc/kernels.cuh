@@ -321,7 +321,7 @@ __global__ void __launch_bounds__(256) attention_softmax_kernel(const float* __r
 
 // Classifier head (components/hyena.py:55-74,142-146,149-180): merge pooling slices, then
 //   Lin(256,512) GELU Lin(512,512) GELU [Lin(512,512) GELU Lin(512,512)] + skip, Lin(512,2);
-//   label = argmax(logits) with ties -> 0 (chimeralm/models/callbacks.py:107).  One block per read.
+//   label = argmax(logits) with ties -> 0 (chimeralm/models/callbacks.py:107).
 struct HeadParams {
   const float* part; int n_split;
   const float *w0, *b0, *w1, *b1, *wr0, *br0, *wr1, *br1, *wo, *bo;
@@ -332,79 +332,10 @@ struct HeadParams {
 
 __device__ __forceinline__ float gelu_erf_h(float x) { return 0.5f * x * (1.0f + erff(x * 0.7071067811865476f)); }
 
-// y[o] = act(b[o] + sum_i W[o,i] x[i]) for o in [0,OUT): one warp per output row, coalesced W reads.
-template <int IN, int OUT, bool GELU>
-__device__ __forceinline__ void head_linear(const float* __restrict__ W, const float* __restrict__ bias,
-                                            const float* x, float* y) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-  constexpr int R = (OUT >= 64) ? 4 : 1;   // rows per warp step: keeps 4 x IN/128 independent 16-byte loads in flight
-  for (int o0 = warp * R; o0 < OUT; o0 += nw * R) {
-    float a[R];
-#pragma unroll
-    for (int rr = 0; rr < R; ++rr) a[rr] = 0.f;
-#pragma unroll 2
-    for (int i = lane * 4; i < IN; i += 128) {
-      const float4 xv = *reinterpret_cast<const float4*>(x + i);
-#pragma unroll
-      for (int rr = 0; rr < R; ++rr) {
-        const float4 wv = __ldg(reinterpret_cast<const float4*>(W + (long long)(o0 + rr) * IN + i));
-        a[rr] += wv.x * xv.x + wv.y * xv.y + wv.z * xv.z + wv.w * xv.w;
-      }
-    }
-#pragma unroll
-    for (int rr = 0; rr < R; ++rr) {
-      float v = a[rr];
-      for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
-      if (lane == 0) {
-        v += bias[o0 + rr];
-        y[o0 + rr] = GELU ? gelu_erf_h(v) : v;
-      }
-    }
-  }
-}
-
-__global__ void __launch_bounds__(512) head_kernel(HeadParams p) {
-  constexpr int D = 256, H = 512;
-  __shared__ __align__(16) float pooled[D], h1[H], h2[H], h3[H];
-  __shared__ float s_lg[2];
-  const int b = blockIdx.x, tid = threadIdx.x;
-  const float* part = p.part + (long long)b * p.n_split * (2 + D);
-  float M = -INFINITY;
-  for (int s = 0; s < p.n_split; ++s) M = fmaxf(M, part[s * (2 + D)]);
-  if (tid < D) {
-    float a = 0.f, L = 0.f;
-    for (int s = 0; s < p.n_split; ++s) {
-      const float ms = part[s * (2 + D)];
-      const float f = (ms == -INFINITY) ? 0.f : __expf(ms - M);
-      a += part[s * (2 + D) + 2 + tid] * f;
-      L += part[s * (2 + D) + 1] * f;
-    }
-    pooled[tid] = a / L;
-    if (p.pooled_out) p.pooled_out[(long long)b * D + tid] = a / L;
-  }
-  __syncthreads();
-  head_linear<D, H, true>(p.w0, p.b0, pooled, h1);
-  __syncthreads();
-  head_linear<H, H, true>(p.w1, p.b1, h1, h2);
-  __syncthreads();
-  head_linear<H, H, true>(p.wr0, p.br0, h2, h3);
-  __syncthreads();
-  head_linear<H, H, false>(p.wr1, p.br1, h3, h1);
-  __syncthreads();
-  for (int i = tid; i < H; i += blockDim.x) h1[i] += h2[i];
-  __syncthreads();
-  head_linear<H, 2, false>(p.wo, p.bo, h1, s_lg);
-  __syncthreads();
-  if (tid == 0) {
-    p.logits[b * 2 + 0] = s_lg[0];
-    p.logits[b * 2 + 1] = s_lg[1];
-    if (p.labels) p.labels[b] = (s_lg[1] > s_lg[0]) ? 1 : 0;
-  }
-}
-
 // ---------------------------------------------------------------------------------------------
-// Head as a chain of small kernels in which every weight row is read ONCE for the whole batch (the one-CTA-per-read
-// head_kernel above streams all 4 MB of head weights per read; at batch 32 that is 128 MB through L2).
+// Head as a chain of small kernels in which every weight row is read ONCE for the whole batch (a one-CTA-per-read
+// head streamed all 4 MB of head weights per read; at batch 32 that is 128 MB through L2).  Unfused path; the fused
+// head_fused_kernel below is what clm_forward launches.
 __global__ void __launch_bounds__(256) pool_merge_kernel(const float* __restrict__ part, int n_split, float* __restrict__ pooled) {
   constexpr int D = 256;
   const int b = blockIdx.x, d = threadIdx.x;
