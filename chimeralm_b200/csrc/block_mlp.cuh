@@ -490,31 +490,31 @@ block_mlp_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
       ptx::mbar_wait(out_full, tph);
       ptx::tc_fence_after_sync();
       if (tr) stamp(2);
-      float o1 = 0.f, o2 = 0.f;
-#pragma unroll 1
-      for (int ci = 0; ci < 4; ++ci) {
-        const int col = hf * 128 + ci * 32;
-        uint32_t a[32];
-        ptx::tmem_ld_32x32b_x32(lane_addr + TM_R + col, a);
-        ptx::tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float4 v = make_float4(__uint_as_float(a[4 * j]) + lc.b2[col + 4 * j], __uint_as_float(a[4 * j + 1]) + lc.b2[col + 4 * j + 1],
-                                       __uint_as_float(a[4 * j + 2]) + lc.b2[col + 4 * j + 2], __uint_as_float(a[4 * j + 3]) + lc.b2[col + 4 * j + 3]);
-          if (row_ok) *reinterpret_cast<float4*>(p.res + ptx::r32_off(row, col + 4 * j)) = v;
-          o1 += (v.x + v.y) + (v.z + v.w);
-          o2 += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
-        }
-      }
       if (p.write_xn) {
+        // Sweep A (TMEM reads only, no stores): row statistics of out = R + b2.  The row-statistics barrier then comes after
+        // a cheap sweep instead of after the store-heavy one, whose slowest warp used to hold everybody.
+        float o1 = 0.f, o2 = 0.f;
+#pragma unroll 1
+        for (int ci = 0; ci < 4; ++ci) {
+          const int col = hf * 128 + ci * 32;
+          uint32_t a[32];
+          ptx::tmem_ld_32x32b_x32(lane_addr + TM_R + col, a);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float v = __uint_as_float(a[j]) + lc.b2[col + j];
+            o1 += v;
+            o2 = fmaf(v, v, o2);
+          }
+        }
         s_part[hf][0][r] = o1;
         s_part[hf][1][r] = o2;
         ptx::bar_sync(2, EPI_THREADS);
         const float m_ = (s_part[0][0][r] + s_part[1][0][r]) * (1.0f / D);
         const float v_ = fmaxf((s_part[0][1][r] + s_part[1][1][r]) * (1.0f / D) - m_ * m_, 0.f);
         const float rs_ = rsqrtf(v_ + p.eps);
-        // second sweep over R (TMEM reads are cheap): normalise and stage into HB (idle until the next tile's first
-        // GELU chunk) as 4 k-blocks of [128 rows x 128 B], 128B-swizzled, for the TMA store
+        // Sweep B: residual stores (fp32, R32 layout) and the normalised bf16 row staged into HB (idle until the next tile's
+        // first GELU chunk) as 4 k-blocks of [128 rows x 128 B], 128B-swizzled, for the TMA store - one pass.
 #pragma unroll 1
         for (int ci = 0; ci < 4; ++ci) {
           const int col = hf * 128 + ci * 32;
@@ -526,13 +526,33 @@ block_mlp_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
           for (int g = 0; g < 4; ++g) {
             float x[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) x[j] = (__uint_as_float(a[g * 8 + j]) + lc.b2[col + g * 8 + j] - m_) * rs_;
+            for (int j = 0; j < 8; ++j) x[j] = __uint_as_float(a[g * 8 + j]) + lc.b2[col + g * 8 + j];
+            if (row_ok) {
+              *reinterpret_cast<float4*>(p.res + ptx::r32_off(row, col + g * 8)) = make_float4(x[0], x[1], x[2], x[3]);
+              *reinterpret_cast<float4*>(p.res + ptx::r32_off(row, col + g * 8 + 4)) = make_float4(x[4], x[5], x[6], x[7]);
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) x[j] = (x[j] - m_) * rs_;
             const uint32_t chunk = uint32_t(((col & 63) >> 3) + g) ^ swz;
             ptx::st_shared_v4(rowaddr + chunk * 16, pack_bf16(x[0], x[1]), pack_bf16(x[2], x[3]), pack_bf16(x[4], x[5]),
                               pack_bf16(x[6], x[7]));
           }
         }
         ptx::fence_proxy_async_smem();
+      } else {
+#pragma unroll 1
+        for (int ci = 0; ci < 4; ++ci) {
+          const int col = hf * 128 + ci * 32;
+          uint32_t a[32];
+          ptx::tmem_ld_32x32b_x32(lane_addr + TM_R + col, a);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 v = make_float4(__uint_as_float(a[4 * j]) + lc.b2[col + 4 * j], __uint_as_float(a[4 * j + 1]) + lc.b2[col + 4 * j + 1],
+                                         __uint_as_float(a[4 * j + 2]) + lc.b2[col + 4 * j + 2], __uint_as_float(a[4 * j + 3]) + lc.b2[col + 4 * j + 3]);
+            if (row_ok) *reinterpret_cast<float4*>(p.res + ptx::r32_off(row, col + 4 * j)) = v;
+          }
+        }
       }
       ptx::tc_fence_before_sync();
       __syncwarp();
