@@ -92,7 +92,7 @@ def predict(
 
 def filter_bam_by_predcition(bam_path: Path, prediction_path: Path, *, index: bool = True, output_prediction: bool = False) -> None:
     """`chimeralm/__main__.py:99-153`: drop reads predicted 1, keep reads without a prediction."""
-    from .bam import BamReader, BamWriter
+    from .bam import BamReader, BamWriter, coordinate_sorted_header
     from .callbacks import load_predictions_from_folder
 
     predictions = load_predictions_from_folder(prediction_path)
@@ -120,15 +120,20 @@ def filter_bam_by_predcition(bam_path: Path, prediction_path: Path, *, index: bo
                 kept.append(read)
             out.close()
             if index:
-                # coordinate sort (samtools order: refID as unsigned so unplaced reads go last, then pos)
+                # `samtools sort` order: refID as unsigned (unplaced reads last), position, forward strand first;
+                # Python's sort is stable, so ties keep file order
                 sorted_path = output_path.with_suffix(".sorted.bam")
                 log.info(f"Sorting {output_path}")
-                kept.sort(key=lambda r: ((r.ref_id & 0xFFFFFFFF), r.pos))
-                so = BamWriter(sorted_path, bam.header_bytes())
+                kept.sort(key=lambda r: ((r.ref_id & 0xFFFFFFFF), r.pos + 1, (r.flag >> 4) & 1))
+                so = BamWriter(sorted_path, coordinate_sorted_header(bam))
                 for r in kept:
                     so.write(r)
                 so.close()
-                log.info(f"Sorted BAM written to {sorted_path} (BAI index generation is not implemented yet)")
+        if index:
+            from .bai import index_bam
+
+            log.info(f"Indexing {sorted_path}")
+            index_bam(sorted_path)
     except Exception as e:
         log.error(f"Error filtering BAM file: {e}")
         if output_path.exists():

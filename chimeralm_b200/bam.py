@@ -136,6 +136,24 @@ class BamReader:
         self.close()
 
 
+def coordinate_sorted_header(bam: "BamReader") -> bytes:
+    """Header of `bam` with `@HD ... SO:coordinate` (what `samtools sort` writes; an index needs a sorted file)."""
+    lines = bam.header_text.rstrip(b"\0").split(b"\n")
+    if lines and lines[0].startswith(b"@HD"):
+        fields = [f for f in lines[0].split(b"\t") if not f.startswith((b"SO:", b"GO:"))]
+        lines[0] = b"\t".join(fields + [b"SO:coordinate"])
+    else:
+        lines.insert(0, b"@HD\tVN:1.6\tSO:coordinate")
+    text = b"\n".join(lines)
+    if not text.endswith(b"\n"):
+        text += b"\n"
+    out = [b"BAM\1", struct.pack("<i", len(text)), text, struct.pack("<i", len(bam.references))]
+    for name, l_ref in bam.references:
+        nm = name.encode() + b"\0"
+        out += [struct.pack("<i", len(nm)), nm, struct.pack("<i", l_ref)]
+    return b"".join(out)
+
+
 def parse_bam_file(file_path: str | Path) -> Iterator[dict]:
     """Reference `parse_bam_file` (chimeralm/data/bam.py:26-38)."""
     with BamReader(file_path) as bam:

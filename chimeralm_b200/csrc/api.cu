@@ -18,6 +18,7 @@
 #include "block_mlp.cuh"
 #include "block_mlp2.cuh"
 #include "block_mlp16.cuh"
+#include "block_mlp_pp.cuh"
 #include "gemm_tcgen05.cuh"
 #include "kernels.cuh"
 #include "longconv.cuh"
@@ -49,6 +50,8 @@ struct LayerW {
   __nv_bfloat16 *out_wt = nullptr, *fc1_wt = nullptr, *fc2_wt = nullptr;
   CUtensorMap tm_out_t, tm_fc1_t, tm_fc2_t;
   CUtensorMap tm_out_h, tm_fc1_h, tm_fc2_h;   // same buffers, half-tile boxes for the CTA-pair kernel
+  __nv_bfloat16* fc1_w64 = nullptr;           // fc1 weights re-tiled with rt = 64: a 64-unit chunk is one 32 KB box
+  CUtensorMap tm_fc1_64;                      // (block_mlp_pp.cuh)
   float* k = nullptr;                               // [D][Lk]
   float2* gspec[LONGCONV_MAX_LOGN + 1] = {nullptr};  // per LOGN: [n_seg][D][N]
   float2* gspecT[LONGCONV_MAX_LOGN + 1] = {nullptr}; // per LOGN: [D][16][N/16], bias folded (longconv_fast)
@@ -127,6 +130,7 @@ struct clm_ctx {
   size_t tc_scratch_floats = 0;
   bool mlp_2cta = false;  // CTA-pair (cta_group::2) version of the fused block tail
   bool mlp_epi16 = false; // fused block tail with 16 epilogue warps (block_mlp16.cuh)
+  bool mlp_pp = false;    // fused block tail with two interleaved fc1/GELU/fc2 chains of 64-unit chunks (block_mlp_pp.cuh)
   bool y_channel_major = true;  // block_mlp reads the conv output channel-major (MN-major UMMA operand): no transpose
   // debug
   int dbg_layer = -1, dbg_stage = -1;
@@ -400,6 +404,12 @@ int launch_block_mlp(clm_ctx* c, int layer, const __nv_bfloat16* y, float* res, 
     return 0;
   }
   const int grid = std::min(p.num_tiles, c->num_sms);
+  if (c->mlp_pp) {
+    if (int rc_attr = ensure_smem_attr(c, (const void*)(block_mlp_pp_kernel), (int)(bm::SMEM_TOTAL))) return rc_attr;
+    block_mlp_pp_kernel<<<grid, bm::THREADS, bm::SMEM_TOTAL, st>>>(tmY, L.tm_out_t, L.tm_fc1_64, L.tm_fc2_t, tmXN, p);
+    CLM_LAUNCH_CHECK(c, "block_mlp_pp");
+    return 0;
+  }
   if (c->mlp_epi16) {
     if (int rc_attr = ensure_smem_attr(c, (const void*)(block_mlp16_kernel), (int)(bm16::SMEM_TOTAL))) return rc_attr;
     block_mlp16_kernel<<<grid, bm16::THREADS, bm16::SMEM_TOTAL, st>>>(tmY, L.tm_out_t, L.tm_fc1_t, L.tm_fc2_t, tmXN, p);
@@ -809,6 +819,7 @@ int clm_finalize(clm_ctx* c) {
       if ((rc = retile(c, out_w, D, D, 256, &L.out_wt, &L.tm_out_t))) return rc;
       if ((rc = retile(c, w1f, g.d_inner, D, 128, &L.fc1_wt, &L.tm_fc1_t))) return rc;
       if ((rc = retile(c, fc2_w, D, g.d_inner, 256, &L.fc2_wt, &L.tm_fc2_t))) return rc;
+      if ((rc = retile(c, w1f, g.d_inner, D, 64, &L.fc1_w64, &L.tm_fc1_64))) return rc;
       if ((rc = make_tmap_retiled(c, &L.tm_out_h, L.out_wt, (long long)D * D / 64, 128))) return rc;
       if ((rc = make_tmap_retiled(c, &L.tm_fc1_h, L.fc1_wt, (long long)g.d_inner * D / 64, 64))) return rc;
       if ((rc = make_tmap_retiled(c, &L.tm_fc2_h, L.fc2_wt, (long long)g.d_inner * D / 64, 128))) return rc;
@@ -1218,6 +1229,7 @@ int clm_set_option(clm_ctx* c, const char* name, int value) {
   else if (n == "y_channel_major") c->y_channel_major = value != 0;
   else if (n == "mlp_2cta") c->mlp_2cta = value != 0;
   else if (n == "mlp_epi16") c->mlp_epi16 = value != 0;
+  else if (n == "mlp_pp") c->mlp_pp = value != 0;
   else return fail(c, CLM_ERR_INVALID, "clm_set_option: unknown option '%s'", name);
   return 0;
 }

@@ -1,0 +1,505 @@
+// block_mlp_kernel (block_mlp.cuh) with the fc1 / GELU / fc2 chunk phase run as TWO interleaved chains.
+//
+// Same math, tiles, TMEM half alternation, ring and E1 / E3 epilogues as block_mlp_kernel; what differs is the chunk
+// phase.  There the single chain fc1(j) -> drain -> GELU -> st.shared -> fc2(j) made the 8 epilogue warps the critical
+// path: ~3.1 K cycles per 128-unit chunk against 2.05 K of tensor work, with the two warps of every scheduler in the
+// same phase (their MUFU.TANH and fma-pipe time added up, profiles/r1_trace_block_mlp.txt).  Here:
+//   * the hidden dimension is walked in 16 chunks of 64 units; fc1 accumulates chunk c in H[c & 1] (2 x 64 TMEM
+//     columns, the same 128 columns as before), fc2 consumes it as ONE k-block out of HB[c & 3] (4 x 16 KB);
+//   * epilogue group g (4 warps, one per scheduler) owns the chunks with c & 1 == g: each warp handles its 32 rows x
+//     all 64 columns, exactly the per-thread work of the old half-chunk, so registers and code shape are unchanged;
+//   * every weight slot is still one 32 KB TMA box: W1 re-tiled with rt = 64 (a chunk = 4 k-blocks of [64][64]),
+//     W2 unchanged (k-block c = [256][64]).
+// Tensor order per tile: fc1(0) fc1(1) fc2(0) fc1(2) fc2(1) ... - a group has two chunk periods (2 x 1024 tensor cycles)
+// for its ld -> GELU -> st chain and the two groups run half a period apart.
+#pragma once
+#include "block_mlp.cuh"
+
+namespace clm {
+namespace bmpp {
+constexpr int CW = 64;                 // hidden units per chunk
+constexpr int NCH = bm::DI / CW;       // 16 chunks
+}  // namespace bmpp
+
+__global__ void __launch_bounds__(bm::THREADS, 1)
+block_mlp_pp_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmWout,
+                 const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2,
+                 const __grid_constant__ CUtensorMap tmXN, BlockMlpParams p) {
+  using namespace bm;
+  using namespace bmpp;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((ptx::smem_u32(smem) & 1023u) != 0) __trap();  // swizzled UMMA/TMA tiles need 1 KB alignment
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
+  uint64_t* w_full = bars;                 // [NSLOT]
+  uint64_t* w_empty = bars + 5;            // [NSLOT]
+  uint64_t* g1_done = bars + 10;           // out_proj accumulator complete
+  uint64_t* xn_full = bars + 11;           // epilogue wrote xn into TMEM and r1 into R
+  uint64_t* hacc_full = bars + 12;         // [2] fc1 chunk accumulator H[c & 1] complete
+  uint64_t* hacc_free = bars + 14;         // [2] the chunk's epilogue group drained H[c & 1] into registers
+  uint64_t* hbuf_full = bars + 16;         // [4] gelu(h) chunk written to HB[c & 3]
+  uint64_t* hbuf_free = bars + 20;         // [4] fc2 finished reading HB[c & 3]
+  uint64_t* out_full = bars + 24;          // fc2 accumulator complete
+  uint64_t* r_free = bars + 25;            // epilogue drained R
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 26);
+  float (*s_part)[2][BM] = reinterpret_cast<float (*)[2][BM]>(smem + OFF_PART);  // [half][sum|sumsq][row]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // Each CTA walks the 8 fc1/fc2 hidden chunks starting at a different one, so the 148 CTAs do
+  // not all pull the same weight tile out of L2 at the same moment.
+  const int rot = blockIdx.x & (NCH - 1);
+  // trace rows: 0 = producer, 1 = MMA issuer, 2 = epilogue warp 2; CTA 0 only
+  long long* trace = (p.trace && blockIdx.x == 0) ? p.trace : nullptr;
+  int trace_n = 0;
+  auto stamp = [&](int role) {
+    if (trace && trace_n < 64) trace[role * 64 + trace_n++] = clock64();
+  };
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmY); ptx::prefetch_tmap(&tmWout); ptx::prefetch_tmap(&tmW1); ptx::prefetch_tmap(&tmW2);
+    ptx::prefetch_tmap(&tmXN);
+    for (int i = 0; i < NSLOT; ++i) { ptx::mbar_init(&w_full[i], 1); ptx::mbar_init(&w_empty[i], 1); }
+    ptx::mbar_init(g1_done, 1);
+    ptx::mbar_init(xn_full, 8);
+    for (int i = 0; i < 2; ++i) { ptx::mbar_init(&hacc_full[i], 1); ptx::mbar_init(&hacc_free[i], 4); }
+    for (int i = 0; i < 4; ++i) { ptx::mbar_init(&hbuf_full[i], 4); ptx::mbar_init(&hbuf_free[i], 1); }
+    ptx::mbar_init(out_full, 1); ptx::mbar_init(r_free, 8);
+    ptx::fence_mbar_init();
+  } else if (warp == 1) {
+    ptx::tmem_alloc<512>(tmem_ptr);
+  }
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  ptx::tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_ptr;
+  // All CTAs run the same tile schedule in lockstep, so their residual reads (E1) and writes (E3) would hit HBM as
+  // chip-wide bursts while the tensor pipes idle.  Starting the CTAs in `stagger` phase groups spreads that traffic.
+  if (p.stagger_cycles > 0) {
+    const long long t_end = clock64() + (long long)(blockIdx.x & 3) * p.stagger_cycles;
+    while (clock64() < t_end) {}
+  }
+
+  if (warp == 0) {
+    // =========================== TMA producer ===========================
+    if (lane == 0) {
+      uint32_t wi = 0;  // running weight-slot counter
+      auto slot_acquire = [&]() -> uint8_t* {
+        const uint32_t s = wi % NSLOT, ph = (wi / NSLOT) & 1;
+        ptx::mbar_wait(&w_empty[s], ph ^ 1);
+        ptx::mbar_expect_tx(&w_full[s], SLOT_BYTES);
+        return smem + OFF_W + s * SLOT_BYTES;
+      };
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+        // y tile: 4 k-blocks of 16 KB, two per ring slot
+        for (int kp = 0; kp < 2; ++kp) {
+          uint8_t* s = slot_acquire();
+          uint64_t* fb = &w_full[wi % NSLOT];
+          for (int q = 0; q < 2; ++q) {
+            const int kb = 2 * kp + q;
+            if (p.y_cm) {
+              const int b = tile / p.tiles_per_seq, t0 = (tile % p.tiles_per_seq) * BM;
+              for (int hh = 0; hh < 2; ++hh)   // k-block = 64 channels; two 64-token halves of 8 KB each
+                ptx::tma_load_3d(s + q * KB_BYTES + hh * (KB_BYTES / 2), &tmY, fb, t0 + hh * 64, kb * BK, b);
+            } else {
+              ptx::tma_load_2d(s + q * KB_BYTES, &tmY, fb, kb * BK, tile * BM);
+            }
+          }
+          ++wi;
+          if (kp == 0) stamp(0);
+        }
+        // Weights are pre-tiled at finalize as [N/rt][K/64][rt][64] (rt = 256 for Wout/W2, 128 for W1), so
+        // every 32 KB slot is ONE TMA instruction (a single thread issues ~1 TMA per 240 cycles).
+        for (int kb = 0; kb < 4; ++kb) {               // out_proj: k-block kb = rows [256 kb, +256)
+          uint8_t* s = slot_acquire();
+          ptx::tma_load_2d(s, &tmWout, &w_full[wi % NSLOT], 0, kb * 256);
+          ++wi;
+        }
+        for (int j = 0; j < NCH + 2; ++j) {
+          if (j < NCH) {  // fc1 chunk jc (64 hidden units; W1 re-tiled with rt = 64): 4 k-blocks of [64][64] = rows [256 jc, +256)
+            const int jc = (j + rot) & (NCH - 1);
+            uint8_t* s = slot_acquire();
+            ptx::tma_load_2d(s, &tmW1, &w_full[wi % NSLOT], 0, jc * 256);
+            ++wi;
+          }
+          if (j >= 2) {  // fc2 k-block jj (the same 64 hidden units): [256][64] = rows [256 jj, +256)
+            const int jj = (j - 2 + rot) & (NCH - 1);
+            uint8_t* s = slot_acquire();
+            ptx::tma_load_2d(s, &tmW2, &w_full[wi % NSLOT], 0, jj * 256);
+            ++wi;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =========================== MMA issuer ===========================
+    if (lane == 0) {
+      constexpr uint32_t idesc256 = ptx::idesc_bf16_f32(BM, 256);
+      constexpr uint32_t idesc256_amn = ptx::idesc_bf16_f32_amn(BM, 256);
+      constexpr uint32_t idesc64 = ptx::idesc_bf16_f32(BM, CW);
+      const uint32_t sHB = ptx::smem_u32(smem + OFF_HB);
+      const uint32_t sW = ptx::smem_u32(smem + OFF_W);
+      uint32_t wi = 0;
+      long long wt_slot = 0, wt_hbuf = 0, wt_hacc = 0, wt_tile = 0, t_all = clock64();
+      // The barrier of the NEXT ring slot is probed right after the current slot is handed out, so the
+      // ~100-cycle try_wait round trip overlaps the MMA issue instead of preceding every slot.
+      bool next_ready = false;
+      uint32_t probed_wi = 0xffffffffu;
+      auto probe_next = [&](uint32_t w) {
+        next_ready = ptx::mbar_try_wait(&w_full[w % NSLOT], (w / NSLOT) & 1);
+        probed_wi = w;
+      };
+      auto slot_wait = [&]() -> uint32_t {
+        const uint32_t s = wi % NSLOT, ph = (wi / NSLOT) & 1;
+        if (!(probed_wi == wi && next_ready)) {
+          const long long t_ = trace ? clock64() : 0;
+          ptx::mbar_wait(&w_full[s], ph);
+          if (trace) wt_slot += clock64() - t_;
+        }
+        ptx::tc_fence_after_sync();
+        probe_next(wi + 1);
+        return sW + s * SLOT_BYTES;
+      };
+      auto slot_release = [&]() {
+        ptx::umma_commit(&w_empty[wi % NSLOT]);
+        ++wi;
+      };
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+        const uint32_t tph = it & 1;
+        // TMEM halves alternate per tile: R takes the half that held XN+H in the previous tile, so out_proj
+        // of this tile runs while the epilogue is still draining the previous tile's R.
+        const uint32_t TM_R = tph ? 256u : 0u, TM_XN = tph ? 0u : 256u, TM_H = tph ? 128u : 384u;   // H[i] = TM_H + 64 i
+        // ---- G1: R = y * Wout^T
+        stamp(1);
+        { const long long t_ = trace ? clock64() : 0;
+          if (it > 0) {   // the previous tile's last two fc1 chunks (use 8 it - 1 of H[0] and of H[1]) drained (long ago)
+            ptx::mbar_wait(&hacc_free[0], 1);
+            ptx::mbar_wait(&hacc_free[1], 1);
+          }
+          if (trace) wt_tile += clock64() - t_; }
+        ptx::tc_fence_after_sync();
+        stamp(1);
+        // ring order: y(kb 0,1), y(kb 2,3), Wout kb 0..3 - the y slots are released only after the last k-block
+        const uint32_t sy0 = slot_wait(); const uint32_t wi_y0 = wi; ++wi;
+        const uint32_t sy1 = slot_wait(); const uint32_t wi_y1 = wi; ++wi;
+        for (int kb = 0; kb < 4; ++kb) {
+          const uint32_t sw = slot_wait();
+          const uint64_t db = ptx::smem_desc_k_sw128(sw);
+          const uint32_t sx = ((kb < 2) ? sy0 : sy1) + (kb & 1) * KB_BYTES;
+          if (p.y_cm) {
+            // A = y^T tile: MN(token)-major, 2 atoms of 64 tokens 8 KB apart, K rows of 128 B; 16 K-rows per step
+            const uint64_t da = ptx::smem_desc_mn_sw128(sx, KB_BYTES / 2, 1024);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              ptx::umma_f16(tmem_base + TM_R, da + (2048 >> 4) * k, db + 2 * k, idesc256_amn, (kb | k) != 0);
+          } else {
+            const uint64_t da = ptx::smem_desc_k_sw128(sx);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) ptx::umma_f16(tmem_base + TM_R, da + 2 * k, db + 2 * k, idesc256, (kb | k) != 0);
+          }
+          slot_release();
+          if (kb == 1) ptx::umma_commit(&w_empty[wi_y0 % NSLOT]);
+          if (kb == 3) ptx::umma_commit(&w_empty[wi_y1 % NSLOT]);
+        }
+        ptx::umma_commit(g1_done);
+        stamp(1);
+        // ---- fc1 / fc2 software pipeline
+        for (int j = 0; j < NCH + 2; ++j) {
+          if (j < NCH) {
+            const uint32_t hb = j & 1, u = it * (NCH / 2) + (j >> 1);   // u-th use of H[hb]
+            { const long long t_ = trace ? clock64() : 0;
+              if (j == 0) {
+                ptx::mbar_wait(xn_full, tph);
+                ptx::mbar_wait(r_free, tph ^ 1);   // previous tile's R (this tile's XN/H half) fully drained
+              }
+              if (trace && j == 0) wt_tile += clock64() - t_; }
+            { const long long t_ = trace ? clock64() : 0;
+              ptx::mbar_wait(&hacc_free[hb], (u & 1) ^ 1);
+              if (trace) wt_hacc += clock64() - t_; }
+            ptx::tc_fence_after_sync();
+            stamp(1);
+            {
+              const uint32_t sw = slot_wait();
+#pragma unroll
+              for (int kb = 0; kb < 4; ++kb) {
+                const uint64_t db = ptx::smem_desc_k_sw128(sw + kb * (KB_BYTES / 2));   // [64 units][64 k] = 8 KB per k-block
+#pragma unroll
+                for (int k = 0; k < 4; ++k)   // A = xn from TMEM: 8 columns (16 bf16) per K step
+                  ptx::umma_f16_ts(tmem_base + TM_H + hb * CW, tmem_base + TM_XN + (kb * 4 + k) * 8, db + 2 * k, idesc64, (kb | k) != 0);
+              }
+              slot_release();
+            }
+            ptx::umma_commit(&hacc_full[hb]);
+          }
+          if (j >= 2) {
+            const int jj = j - 2;
+            const uint32_t b = jj & 3, u = it * (NCH / 4) + (jj >> 2);
+            { const long long t_ = trace ? clock64() : 0;
+              ptx::mbar_wait(&hbuf_full[b], u & 1);
+              if (trace) wt_hbuf += clock64() - t_; }
+            ptx::tc_fence_after_sync();
+            stamp(1);
+            {
+              const uint32_t sw = slot_wait();
+              const uint64_t da = ptx::smem_desc_k_sw128(sHB + b * KB_BYTES);
+              const uint64_t db = ptx::smem_desc_k_sw128(sw);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) ptx::umma_f16(tmem_base + TM_R, da + 2 * k, db + 2 * k, idesc256, 1u);
+              slot_release();
+            }
+            ptx::umma_commit(&hbuf_free[b]);
+          }
+        }
+        ptx::umma_commit(out_full);
+        stamp(1);
+      }
+      if (trace) {   // where the issuing thread waited (row 0, slots 32..36): weights, gelu(h), H drain, tile-level, total
+        trace[32] = wt_slot; trace[33] = wt_hbuf; trace[34] = wt_hacc; trace[35] = wt_tile; trace[36] = clock64() - t_all;
+      }
+    }
+  } else {
+    // =========================== epilogue warps ===========================
+    const int e = warp - 2;
+    const int q = warp & 3;          // TMEM lane quarter this warp may access
+    const int hf = e >> 2;           // column half
+    const int r = q * 32 + lane;     // row inside the tile
+    const uint32_t lane_addr = tmem_base + (uint32_t(q * 32) << 16);
+    const uint32_t sHB = ptx::smem_u32(smem + OFF_HB);
+    const uint32_t swz = uint32_t(r & 7);
+    const LayerConsts& lc = c_mlp[p.layer];
+    const bool tr = trace && warp == 2 && lane == 0;
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      const uint32_t tph = it & 1;
+      const uint32_t TM_R = tph ? 256u : 0u, TM_XN = tph ? 0u : 256u, TM_H = tph ? 128u : 384u;
+      long long row;
+      bool row_ok;
+      if (p.y_cm) {
+        const int b = tile / p.tiles_per_seq, t = (tile % p.tiles_per_seq) * BM + r;
+        row = (long long)b * p.T + t;
+        row_ok = t < p.T;
+      } else {
+        row = (long long)tile * BM + r;
+        row_ok = row < p.M;
+      }
+      // row of this thread in the NEXT tile of this CTA (for the residual L2 prefetch)
+      long long pf_row = 0;
+      bool pf_ok = false;
+      {
+        const int nt_ = tile + gridDim.x;
+        if (nt_ < p.num_tiles) {
+          if (p.y_cm) {
+            const int t = (nt_ % p.tiles_per_seq) * BM + r;
+            pf_row = (long long)(nt_ / p.tiles_per_seq) * p.T + t;
+            pf_ok = t < p.T;
+          } else {
+            pf_row = (long long)nt_ * BM + r;
+            pf_ok = pf_row < p.M;
+          }
+        }
+      }
+      // ------------------------------------------------ E1: r1, LayerNorm2 -> xn (TMEM)
+      // The residual half-row (128 fp32) is fetched into registers BEFORE waiting for the
+      // out_proj accumulator, so its DRAM latency hides behind the y-tile load and G1.
+      float4 rs[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        rs[j] = row_ok ? *reinterpret_cast<const float4*>(p.res + ptx::r32_off(row, hf * 128 + 4 * j))
+                       : make_float4(0.f, 0.f, 0.f, 0.f);
+      ptx::mbar_wait(g1_done, tph);
+      ptx::tc_fence_after_sync();
+      if (tr) stamp(2);
+      float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+      for (int ci = 0; ci < 4; ++ci) {
+        const int col = hf * 128 + ci * 32;
+        uint32_t a[32];
+        ptx::tmem_ld_32x32b_x32(lane_addr + TM_R + col, a);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float4& rr = rs[ci * 8 + j];
+          const int cc = col + 4 * j;
+          rr.x += __uint_as_float(a[4 * j + 0]) + lc.b_out[cc + 0];   // rs now holds r1
+          rr.y += __uint_as_float(a[4 * j + 1]) + lc.b_out[cc + 1];
+          rr.z += __uint_as_float(a[4 * j + 2]) + lc.b_out[cc + 2];
+          rr.w += __uint_as_float(a[4 * j + 3]) + lc.b_out[cc + 3];
+          s1 += (rr.x + rr.y) + (rr.z + rr.w);
+          s2 += (rr.x * rr.x + rr.y * rr.y) + (rr.z * rr.z + rr.w * rr.w);
+          a[4 * j + 0] = __float_as_uint(rr.x);   // r1 stays in TMEM as the fc2 accumulator's initial value
+          a[4 * j + 1] = __float_as_uint(rr.y);
+          a[4 * j + 2] = __float_as_uint(rr.z);
+          a[4 * j + 3] = __float_as_uint(rr.w);
+        }
+        ptx::tmem_st_32x32b_x32(lane_addr + TM_R + col, a);
+      }
+      s_part[hf][0][r] = s1;
+      s_part[hf][1][r] = s2;
+      if (threadIdx.x == 64) ptx::tma_store_wait_read<0>();   // previous tile's xn store has finished reading HB
+      ptx::bar_sync(1, EPI_THREADS);
+      const float ts1 = s_part[0][0][r] + s_part[1][0][r];
+      const float ts2 = s_part[0][1][r] + s_part[1][1][r];
+      const float mean = ts1 * (1.0f / D);
+      const float var = fmaxf(ts2 * (1.0f / D) - mean * mean, 0.f);
+      const float rstd = rsqrtf(var + p.eps);
+      // xn = (r1 - mean) * rstd (gamma/beta folded into W1/b1), packed bf16 pairs: this thread's 128 columns
+      // are 64 TMEM columns of the A operand
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        uint32_t w[32];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float4 v = rs[hh * 16 + j];
+          w[2 * j] = pack_bf16((v.x - mean) * rstd, (v.y - mean) * rstd);
+          w[2 * j + 1] = pack_bf16((v.z - mean) * rstd, (v.w - mean) * rstd);
+        }
+        ptx::tmem_st_32x32b_x32(lane_addr + TM_XN + hf * 64 + hh * 32, w);
+      }
+      ptx::tmem_st_wait();
+      ptx::tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(xn_full);
+      if (tr) stamp(2);
+      // ------------------------------------------------ E2: gelu(fc1 chunk) -> HB
+      // The two epilogue groups (hf = 0: warps 2..5, hf = 1: warps 6..9; one warp per scheduler each) take alternate
+      // 64-unit chunks, each warp its 32 rows x all 64 columns, out of its own accumulator H[hf].  The groups run half a
+      // period apart, so one group's MUFU phase overlaps the other's fma / st.shared / barrier phases, and each group
+      // has two chunk periods of tensor time for its ld -> GELU -> st chain.
+#pragma unroll 1
+      for (int j = 0; j < NCH / 2; ++j) {
+        const int c = 2 * j + hf;                                    // chunk in issue order
+        const uint32_t b = c & 3, u = it * (NCH / 4) + (c >> 2), uh = it * (NCH / 2) + j;
+        ptx::mbar_wait(&hacc_full[hf], uh & 1);
+        ptx::tc_fence_after_sync();
+        if (tr) stamp(2);
+        uint32_t a0[32], a1[32];
+        ptx::tmem_ld_32x32b_x32(lane_addr + TM_H + hf * CW, a0);
+        ptx::tmem_ld_32x32b_x32(lane_addr + TM_H + hf * CW + 32, a1);
+        ptx::tmem_ld_wait();
+        ptx::tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&hacc_free[hf]);   // the accumulator is in registers: fc1 of chunk c + 2 may start
+        if (j < 4 && pf_ok) {
+          // next tile's residual half-row (512 B per thread, 32 float4 at 512 B stride): pull 8 of them towards L2 per
+          // chunk so that E1 of the next tile does not start with a 19 MB chip-wide HBM burst
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.res + ptx::r32_off(pf_row, hf * 128 + 4 * (8 * j + i))));
+        }
+        const float* b1p = lc.b1 + ((c + rot) & (NCH - 1)) * CW;
+        const uint32_t rowaddr = sHB + b * KB_BYTES + r * 128;
+        // all the GELU math first (results in registers), THEN wait for fc2 of chunk c - 4 to release the HB buffer
+        uint32_t o[32];
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          const uint32_t* src = (g < 4) ? &a0[g * 8] : &a1[(g - 4) * 8];
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj)
+            o[4 * g + jj] = gelu_tanh_bf16x2(f2_add(f2_packu(src[2 * jj], src[2 * jj + 1]), f2_pack(b1p[g * 8 + 2 * jj], b1p[g * 8 + 2 * jj + 1])));
+        }
+        ptx::mbar_wait(&hbuf_free[b], (u & 1) ^ 1);
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          const uint32_t chunk = uint32_t(g) ^ swz;
+          ptx::st_shared_v4(rowaddr + chunk * 16, o[4 * g], o[4 * g + 1], o[4 * g + 2], o[4 * g + 3]);
+        }
+        ptx::fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&hbuf_full[b]);
+        if (tr) stamp(2);
+      }
+      // ------------------------------------------------ E3: out = R + b2 -> res (+ normalised xn for the next consumer)
+      ptx::mbar_wait(out_full, tph);
+      ptx::tc_fence_after_sync();
+      if (tr) stamp(2);
+      if (p.write_xn) {
+        // Sweep A (TMEM reads only, no stores): row statistics of out = R + b2.  The row-statistics barrier then comes after
+        // a cheap sweep instead of after the store-heavy one, whose slowest warp used to hold everybody.
+        float o1 = 0.f, o2 = 0.f;
+#pragma unroll 1
+        for (int ci = 0; ci < 4; ++ci) {
+          const int col = hf * 128 + ci * 32;
+          uint32_t a[32];
+          ptx::tmem_ld_32x32b_x32(lane_addr + TM_R + col, a);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float v = __uint_as_float(a[j]) + lc.b2[col + j];
+            o1 += v;
+            o2 = fmaf(v, v, o2);
+          }
+        }
+        s_part[hf][0][r] = o1;
+        s_part[hf][1][r] = o2;
+        ptx::bar_sync(2, EPI_THREADS);
+        const float m_ = (s_part[0][0][r] + s_part[1][0][r]) * (1.0f / D);
+        const float v_ = fmaxf((s_part[0][1][r] + s_part[1][1][r]) * (1.0f / D) - m_ * m_, 0.f);
+        const float rs_ = rsqrtf(v_ + p.eps);
+        // Sweep B: residual stores (fp32, R32 layout) and the normalised bf16 row staged into HB (idle until the next tile's
+        // first GELU chunk) as 4 k-blocks of [128 rows x 128 B], 128B-swizzled, for the TMA store - one pass.
+#pragma unroll 1
+        for (int ci = 0; ci < 4; ++ci) {
+          const int col = hf * 128 + ci * 32;
+          uint32_t a[32];
+          ptx::tmem_ld_32x32b_x32(lane_addr + TM_R + col, a);
+          ptx::tmem_ld_wait();
+          const uint32_t rowaddr = sHB + (col >> 6) * KB_BYTES + r * 128;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            float x[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) x[j] = __uint_as_float(a[g * 8 + j]) + lc.b2[col + g * 8 + j];
+            if (row_ok) {
+              *reinterpret_cast<float4*>(p.res + ptx::r32_off(row, col + g * 8)) = make_float4(x[0], x[1], x[2], x[3]);
+              *reinterpret_cast<float4*>(p.res + ptx::r32_off(row, col + g * 8 + 4)) = make_float4(x[4], x[5], x[6], x[7]);
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) x[j] = (x[j] - m_) * rs_;
+            const uint32_t chunk = uint32_t(((col & 63) >> 3) + g) ^ swz;
+            ptx::st_shared_v4(rowaddr + chunk * 16, pack_bf16(x[0], x[1]), pack_bf16(x[2], x[3]), pack_bf16(x[4], x[5]),
+                              pack_bf16(x[6], x[7]));
+          }
+        }
+        ptx::fence_proxy_async_smem();
+      } else {
+#pragma unroll 1
+        for (int ci = 0; ci < 4; ++ci) {
+          const int col = hf * 128 + ci * 32;
+          uint32_t a[32];
+          ptx::tmem_ld_32x32b_x32(lane_addr + TM_R + col, a);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 v = make_float4(__uint_as_float(a[4 * j]) + lc.b2[col + 4 * j], __uint_as_float(a[4 * j + 1]) + lc.b2[col + 4 * j + 1],
+                                         __uint_as_float(a[4 * j + 2]) + lc.b2[col + 4 * j + 2], __uint_as_float(a[4 * j + 3]) + lc.b2[col + 4 * j + 3]);
+            if (row_ok) *reinterpret_cast<float4*>(p.res + ptx::r32_off(row, col + 4 * j)) = v;
+          }
+        }
+      }
+      ptx::tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(r_free);
+      if (p.write_xn) {
+        ptx::bar_sync(1, EPI_THREADS);
+        if (threadIdx.x == 64) {
+          int xb, xt0;
+          if (p.y_cm) { xb = tile / p.tiles_per_seq; xt0 = (tile % p.tiles_per_seq) * BM; }
+          else { xb = 0; xt0 = tile * BM; }
+#pragma unroll
+          for (int kb = 0; kb < 4; ++kb) ptx::tma_store_3d(&tmXN, smem + OFF_HB + kb * KB_BYTES, kb * BK, xt0, xb);
+          ptx::tma_store_commit();
+        }
+      }
+      if (tr) stamp(2);
+    }
+    if (threadIdx.x == 64) ptx::tma_store_wait<0>();
+  }
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after_sync();
+    ptx::tmem_dealloc<512>(tmem_base);
+  }
+}
+
+}  // namespace clm

@@ -75,6 +75,10 @@ int main() {
     run<128, 1>("TS (A tmem)  M128 N128", grid, d);
     run<256, 1>("TS (A tmem)  M128 N256", grid, d);
     run<256, 2>("SS A MN-major M128 N256", grid, d);
+    run<64, 0>("SS K-major   M128 N64", grid, d);
+    run<64, 1>("TS (A tmem)  M128 N64", grid, d);
+    run<96, 1>("TS (A tmem)  M128 N96", grid, d);
+    run<32, 1>("TS (A tmem)  M128 N32", grid, d);
   }
   return 0;
 }

@@ -54,3 +54,16 @@ def test_filter_drops_label1_and_keeps_unknown(tmp_path):
     with BamReader(tmp_path / "in.filtered.sorted.bam") as f:
         keys = [((rec.ref_id & 0xFFFFFFFF), rec.pos) for rec in f]
     assert keys == sorted(keys) and len(keys) == len(kept)
+    # ... and the sorted file is indexed (reference: pysam.index, `__main__.py:150-151`): the index is the one a fresh build
+    # gives, and a region query through it returns what a full scan returns
+    from chimeralm_b200 import bai
+
+    sorted_bam = tmp_path / "in.filtered.sorted.bam"
+    idx = bai.parse_index((tmp_path / "in.filtered.sorted.bam.bai").read_bytes())
+    assert idx == bai.build_index(sorted_bam)
+    with BamReader(sorted_bam) as f:
+        assert b"SO:coordinate" in f.header_text.split(b"\n")[0]
+        recs = [(rec.ref_id, rec.pos, rec.name) for rec in f]
+    tid, pos, name = recs[len(recs) // 2]
+    hits = bai.fetch(sorted_bam, idx, tid, pos, pos + 1)
+    assert name in [h[0] for h in hits] and all(h[1] <= pos < h[2] for h in hits)

@@ -331,3 +331,85 @@ def test_native_ingest_block_and_record_carry_across_file_chunks(tmp_path):
             names, flat, offs = read_bam_flat(path, 1 << 20, chunk_bytes=chunk, n_threads=3, block_reads=11)
             assert names == [n for n, _ in ref], (path, chunk)
             assert all(np.array_equal(flat[offs[i] : offs[i + 1]], s) for i, (_, s) in enumerate(ref)), (path, chunk)
+
+
+# ---------------------------------------------------------------------------------- BAI index (`filter`)
+def test_bai_matches_the_reference_fixture_index():
+    """`tests/golden/test_chimric_reads.bam.bai` is the reference's own samtools-written index of its test BAM
+    (`/root/reference/tests/data/`): every bin, chunk, linear-index entry, pseudo-bin and the unplaced-read count agree.
+    (Byte equality is not expected: htslib stores a reference's bins in its hash-table order.)"""
+    from chimeralm_b200 import bai
+
+    golden = Path(__file__).parent / "golden"
+    want = bai.parse_index((golden / "test_chimric_reads.bam.bai").read_bytes())
+    got = bai.build_index(golden / "test_chimric_reads.bam")
+    assert len(got["refs"]) == len(want["refs"]) == 639
+    assert sum(len(r["bins"]) for r in want["refs"]) == 71 and len(want["refs"][0]["linear"]) > 1000
+    assert got == want
+    assert bai.parse_index(bai.serialize_index(got)) == got
+
+
+def test_bai_region_queries_equal_a_full_scan():
+    """Size-independent property: for any window, reading only the chunks the index names finds exactly the records a
+    scan of the whole file finds."""
+    import struct as st
+
+    from chimeralm_b200 import bai
+    from chimeralm_b200.bam import BamReader
+
+    bam = Path(__file__).parent / "golden" / "test_chimric_reads.bam"
+    idx = bai.build_index(bam)
+    recs = []
+    with BamReader(bam) as f:
+        for rec in f:
+            l_read_name, n_cigar = rec.raw[8], st.unpack_from("<H", rec.raw, 12)[0]
+            recs.append((rec.ref_id, rec.pos, bai._reference_end(rec.raw, rec.pos, rec.flag, l_read_name, n_cigar), rec.name))
+    rng = np.random.default_rng(3)
+    tids = sorted({r[0] for r in recs if r[0] >= 0})
+    for _ in range(60):
+        tid = tids[int(rng.integers(len(tids)))]
+        on = [r for r in recs if r[0] == tid]
+        anchor = on[int(rng.integers(len(on)))]
+        beg = max(0, anchor[1] + int(rng.integers(-50_000, 50_000)))
+        end = beg + int(rng.integers(1, 200_000))
+        want = sorted((r[3], r[1], r[2]) for r in on if r[1] < end and r[2] > beg)
+        assert sorted(bai.fetch(bam, idx, tid, beg, end)) == want
+
+
+def test_bai_small_cases(tmp_path):
+    """Edge cases: an empty BAM, unplaced reads at the end (counted, not binned), an unsorted file (refused), reg2bin KATs
+    from the SAM specification's bin numbering."""
+    from chimeralm_b200 import bai
+    from chimeralm_b200.bam import BamWriter, make_record, minimal_header
+
+    assert [bai.reg2bin(0, 1), bai.reg2bin(16383, 16384), bai.reg2bin(16383, 16385), bai.reg2bin(0, 1 << 29)] == [4681, 4681, 585, 0]
+    assert bai.reg2bin((1 << 26) - 1, (1 << 26) + 1) == 0 and bai.reg2bin(1 << 26, (1 << 26) + 1) == 4681 + 4096
+    hdr = minimal_header((("chr1", 1_000_000), ("chr2", 500_000)))
+    empty = tmp_path / "e.bam"
+    BamWriter(empty, hdr).close()
+    idx = bai.build_index(empty)
+    assert idx == {"refs": [{"bins": {}, "linear": []}, {"bins": {}, "linear": []}], "n_no_coor": 0}
+    assert bai.parse_index(bai.serialize_index(idx)) == idx
+
+    w = BamWriter(tmp_path / "s.bam", hdr)
+    w.write(make_record("a", "ACGT" * 10, ref_id=0, pos=100))
+    w.write(make_record("b", "ACGT" * 10, ref_id=0, pos=40_000))
+    w.write(make_record("c", "ACGT" * 10, ref_id=1, pos=7))
+    w.write(make_record("u1", "ACGT", flag=4, ref_id=-1, pos=-1))
+    w.write(make_record("u2", "ACGT", flag=4, ref_id=-1, pos=-1))
+    w.close()
+    idx = bai.build_index(tmp_path / "s.bam")
+    assert idx["n_no_coor"] == 2
+    assert idx["refs"][0]["bins"][bai.META_BIN][1] == [2, 0] and idx["refs"][1]["bins"][bai.META_BIN][1] == [1, 0]
+    assert len(idx["refs"][0]["linear"]) == 3 and idx["refs"][0]["linear"][1] == idx["refs"][0]["linear"][2]
+    assert [h[0] for h in bai.fetch(tmp_path / "s.bam", idx, 0, 39_000, 41_000)] == ["b"]
+    assert bai.fetch(tmp_path / "s.bam", idx, 0, 200, 300) == []
+    p = bai.index_bam(tmp_path / "s.bam")
+    assert p.name == "s.bam.bai" and bai.parse_index(p.read_bytes()) == idx
+
+    w = BamWriter(tmp_path / "u.bam", hdr)
+    w.write(make_record("b", "ACGT", ref_id=0, pos=500))
+    w.write(make_record("a", "ACGT", ref_id=0, pos=100))
+    w.close()
+    with pytest.raises(ValueError, match="not coordinate-sorted"):
+        bai.build_index(tmp_path / "u.bam")
