@@ -130,6 +130,8 @@ struct clm_ctx {
   size_t tc_scratch_floats = 0;
   bool mlp_2cta = false;  // CTA-pair (cta_group::2) version of the fused block tail
   bool mlp_epi16 = false; // fused block tail with 16 epilogue warps (block_mlp16.cuh)
+  int mlp_early_res = 0;  // (0/8/16/24/32 of the 32 float4) block_mlp: next tile's residual loaded into registers before this tile's output epilogue
+  int mlp_grid = 0;       // block_mlp: cap on the number of CTAs (0 = one per SM); diagnostic
   bool mlp_pp = false;    // fused block tail with two interleaved fc1/GELU/fc2 chains of 64-unit chunks (block_mlp_pp.cuh)
   bool y_channel_major = true;  // block_mlp reads the conv output channel-major (MN-major UMMA operand): no transpose
   // debug
@@ -365,7 +367,6 @@ int launch_block_in(clm_ctx* c, int layer, const __nv_bfloat16* xn, int B, int T
 // y token-major [M,256] when B == 0; channel-major [B][256][Tp] (M == B*T) otherwise
 int launch_block_mlp(clm_ctx* c, int layer, const __nv_bfloat16* y, float* res, int M, cudaStream_t st,
                      long long* trace = nullptr, int B = 0, int T = 0, int Tp = 0, __nv_bfloat16* xn_out = nullptr) {
-  if (int rc_attr = ensure_smem_attr(c, (const void*)(block_mlp_kernel), (int)(bm::SMEM_TOTAL))) return rc_attr;
   if (int rc_c = bind_constants(c, st)) return rc_c;
   LayerW& L = c->layers[layer];
   CUtensorMap tmY;
@@ -403,7 +404,7 @@ int launch_block_mlp(clm_ctx* c, int layer, const __nv_bfloat16* y, float* res, 
     CLM_LAUNCH_CHECK(c, "block_mlp2");
     return 0;
   }
-  const int grid = std::min(p.num_tiles, c->num_sms);
+  const int grid = std::min(p.num_tiles, c->mlp_grid > 0 ? std::min(c->mlp_grid, c->num_sms) : c->num_sms);
   if (c->mlp_pp) {
     if (int rc_attr = ensure_smem_attr(c, (const void*)(block_mlp_pp_kernel), (int)(bm::SMEM_TOTAL))) return rc_attr;
     block_mlp_pp_kernel<<<grid, bm::THREADS, bm::SMEM_TOTAL, st>>>(tmY, L.tm_out_t, L.tm_fc1_64, L.tm_fc2_t, tmXN, p);
@@ -416,7 +417,17 @@ int launch_block_mlp(clm_ctx* c, int layer, const __nv_bfloat16* y, float* res, 
     CLM_LAUNCH_CHECK(c, "block_mlp16");
     return 0;
   }
-  block_mlp_kernel<<<grid, bm::THREADS, bm::SMEM_TOTAL, st>>>(tmY, L.tm_out_t, L.tm_fc1_t, L.tm_fc2_t, tmXN, p);
+#define CLM_MLP_LAUNCH(E)                                                                                                  \
+  {                                                                                                                        \
+    if (int rc_attr = ensure_smem_attr(c, (const void*)(block_mlp_kernel<E>), (int)(bm::SMEM_TOTAL))) return rc_attr;       \
+    block_mlp_kernel<E><<<grid, bm::THREADS, bm::SMEM_TOTAL, st>>>(tmY, L.tm_out_t, L.tm_fc1_t, L.tm_fc2_t, tmXN, p);      \
+  }
+  if (c->mlp_early_res >= 32) CLM_MLP_LAUNCH(32)
+  else if (c->mlp_early_res >= 24) CLM_MLP_LAUNCH(24)
+  else if (c->mlp_early_res >= 16) CLM_MLP_LAUNCH(16)
+  else if (c->mlp_early_res >= 8) CLM_MLP_LAUNCH(8)
+  else CLM_MLP_LAUNCH(0)
+#undef CLM_MLP_LAUNCH
   CLM_LAUNCH_CHECK(c, "block_mlp");
   return 0;
 }
@@ -1230,6 +1241,8 @@ int clm_set_option(clm_ctx* c, const char* name, int value) {
   else if (n == "mlp_2cta") c->mlp_2cta = value != 0;
   else if (n == "mlp_epi16") c->mlp_epi16 = value != 0;
   else if (n == "mlp_pp") c->mlp_pp = value != 0;
+  else if (n == "mlp_grid") c->mlp_grid = value;
+  else if (n == "mlp_early_res") c->mlp_early_res = value;
   else return fail(c, CLM_ERR_INVALID, "clm_set_option: unknown option '%s'", name);
   return 0;
 }

@@ -27,6 +27,8 @@
 #pragma once
 #include <cuda_bf16.h>
 
+#include <type_traits>
+
 #include "gemm_tcgen05.cuh"
 #include "ptx.cuh"
 
@@ -102,6 +104,10 @@ __device__ __forceinline__ uint32_t gelu_tanh_bf16x2(f2t x) {
 }
 }  // namespace bm
 
+// EARLY_RES: the next tile's residual half-row is loaded into registers BEFORE the output epilogue (E3) of this tile
+// instead of after it, so the loads (per-SM outstanding-miss bound: ~6.5 K cycles for 128 KB even from L2) complete
+// under E3's stores instead of in front of E1.
+template <int EARLY_RES>   // number of the 32 float4 loaded early (0 = all after E3, the first version)
 __global__ void __launch_bounds__(bm::THREADS, 1)
 block_mlp_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmWout,
                  const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2,
@@ -351,6 +357,24 @@ block_mlp_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
     const LayerConsts& lc = c_mlp[p.layer];
     const bool tr = trace && warp == 2 && lane == 0;
     uint32_t it = 0;
+    float4 rs[32];
+    auto load_res = [&](long long lrow, bool ok, auto j0_, auto j1_) {
+#pragma unroll
+      for (int j = decltype(j0_)::value; j < decltype(j1_)::value; ++j)
+        rs[j] = ok ? *reinterpret_cast<const float4*>(p.res + ptx::r32_off(lrow, hf * 128 + 4 * j))
+                   : make_float4(0.f, 0.f, 0.f, 0.f);
+    };
+    using I0 = std::integral_constant<int, 0>;
+    using IE = std::integral_constant<int, EARLY_RES>;
+    using I32 = std::integral_constant<int, 32>;
+    if (EARLY_RES && (int)blockIdx.x < p.num_tiles) {
+      if (p.y_cm) {
+        const int t = ((int)blockIdx.x % p.tiles_per_seq) * BM + r;
+        load_res((long long)((int)blockIdx.x / p.tiles_per_seq) * p.T + t, t < p.T, I0{}, IE{});
+      } else {
+        load_res((long long)blockIdx.x * BM + r, (long long)blockIdx.x * BM + r < p.M, I0{}, IE{});
+      }
+    }
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
       const uint32_t tph = it & 1;
       const uint32_t TM_R = tph ? 256u : 0u, TM_XN = tph ? 0u : 256u, TM_H = tph ? 128u : 384u;
@@ -383,11 +407,7 @@ block_mlp_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
       // ------------------------------------------------ E1: r1, LayerNorm2 -> xn (TMEM)
       // The residual half-row (128 fp32) is fetched into registers BEFORE waiting for the
       // out_proj accumulator, so its DRAM latency hides behind the y-tile load and G1.
-      float4 rs[32];
-#pragma unroll
-      for (int j = 0; j < 32; ++j)
-        rs[j] = row_ok ? *reinterpret_cast<const float4*>(p.res + ptx::r32_off(row, hf * 128 + 4 * j))
-                       : make_float4(0.f, 0.f, 0.f, 0.f);
+      load_res(row, row_ok, IE{}, I32{});
       ptx::mbar_wait(g1_done, tph);
       ptx::tc_fence_after_sync();
       if (tr) stamp(2);
@@ -487,6 +507,7 @@ block_mlp_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
         if (tr) stamp(2);
       }
       // ------------------------------------------------ E3: out = R + b2 -> res (+ normalised xn for the next consumer)
+      if (EARLY_RES) load_res(pf_row, pf_ok, I0{}, IE{});   // rs is dead since E1; another CTA's rows, so E3's stores do not alias them
       ptx::mbar_wait(out_full, tph);
       ptx::tc_fence_after_sync();
       if (tr) stamp(2);
