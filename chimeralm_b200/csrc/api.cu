@@ -130,7 +130,7 @@ struct clm_ctx {
   size_t tc_scratch_floats = 0;
   bool mlp_2cta = false;  // CTA-pair (cta_group::2) version of the fused block tail
   bool mlp_epi16 = false; // fused block tail with 16 epilogue warps (block_mlp16.cuh)
-  int mlp_early_res = 0;  // (0/8/16/24/32 of the 32 float4) block_mlp: next tile's residual loaded into registers before this tile's output epilogue
+  int mlp_early_res = 33; // block_mlp: float4 of the next tile's residual half-row loaded before E3 (0, 16, 32; 33 = spread over E3)
   int mlp_grid = 0;       // block_mlp: cap on the number of CTAs (0 = one per SM); diagnostic
   bool mlp_pp = false;    // fused block tail with two interleaved fc1/GELU/fc2 chains of 64-unit chunks (block_mlp_pp.cuh)
   bool y_channel_major = true;  // block_mlp reads the conv output channel-major (MN-major UMMA operand): no transpose
@@ -420,12 +420,11 @@ int launch_block_mlp(clm_ctx* c, int layer, const __nv_bfloat16* y, float* res, 
 #define CLM_MLP_LAUNCH(E)                                                                                                  \
   {                                                                                                                        \
     if (int rc_attr = ensure_smem_attr(c, (const void*)(block_mlp_kernel<E>), (int)(bm::SMEM_TOTAL))) return rc_attr;       \
-    block_mlp_kernel<E><<<grid, bm::THREADS, bm::SMEM_TOTAL, st>>>(tmY, L.tm_out_t, L.tm_fc1_t, L.tm_fc2_t, tmXN, p);      \
+    block_mlp_kernel<E><<<grid, bm::THREADS_WG, bm::SMEM_TOTAL, st>>>(tmY, L.tm_out_t, L.tm_fc1_t, L.tm_fc2_t, tmXN, p);      \
   }
-  if (c->mlp_early_res >= 32) CLM_MLP_LAUNCH(32)
-  else if (c->mlp_early_res >= 24) CLM_MLP_LAUNCH(24)
+  if (c->mlp_early_res >= 33) CLM_MLP_LAUNCH(33)
+  else if (c->mlp_early_res >= 32) CLM_MLP_LAUNCH(32)
   else if (c->mlp_early_res >= 16) CLM_MLP_LAUNCH(16)
-  else if (c->mlp_early_res >= 8) CLM_MLP_LAUNCH(8)
   else CLM_MLP_LAUNCH(0)
 #undef CLM_MLP_LAUNCH
   CLM_LAUNCH_CHECK(c, "block_mlp");

@@ -22,8 +22,11 @@
 // k-blocks per slot) and every weight tile (one 32 KB box per slot).  A slot is held until the MMAs
 // reading it complete, so ring depth x slot size is what hides the L2 latency.
 //
-// Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc), warps 2..9 = epilogue
-// (TMEM lane quarter = warp % 4, column half = (warp - 2) / 4).
+// Warp roles (three warpgroups, 384 threads): warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc), warps 2..3 idle,
+// warps 4..11 = epilogue (TMEM lane quarter = warp % 4, column half = (warp - 4) / 4).  The roles sit on warpgroup
+// boundaries so that `setmaxnreg` can move registers from the first warpgroup (104 each) to the epilogue warps (200
+// each): with 10 warps three of them share a scheduler's 16 K registers and ptxas caps the kernel at 168, too few to
+// hold the next tile's residual half-row (128 registers) across the output epilogue without spilling loaded values.
 #pragma once
 #include <cuda_bf16.h>
 
@@ -73,7 +76,10 @@ constexpr int OFF_W = OFF_HB + 2 * HB_BYTES;
 constexpr int OFF_BAR = OFF_W + NSLOT * SLOT_BYTES;   // 229376
 constexpr int OFF_PART = OFF_BAR + 256;               // LayerNorm partial sums [2][2][128] fp32
 constexpr int SMEM_TOTAL = OFF_PART + 2 * 2 * BM * 4; // 231680 <= 232448 (227 KB)
-constexpr int THREADS = 320;
+constexpr int THREADS = 320;            // the experimental variants (block_mlp2/16/pp): warps 0, 1, 2..9
+constexpr int THREADS_WG = 384;         // block_mlp_kernel: three warpgroups
+constexpr int EPI_WARP0 = 4;
+constexpr int EPI_TID0 = EPI_WARP0 * 32;
 constexpr int EPI_THREADS = 256;
 constexpr int NCHUNK = DI / 128;                 // 8 fc1 column chunks
 
@@ -108,7 +114,7 @@ __device__ __forceinline__ uint32_t gelu_tanh_bf16x2(f2t x) {
 // instead of after it, so the loads (per-SM outstanding-miss bound: ~6.5 K cycles for 128 KB even from L2) complete
 // under E3's stores instead of in front of E1.
 template <int EARLY_RES>   // number of the 32 float4 loaded early (0 = all after E3, the first version)
-__global__ void __launch_bounds__(bm::THREADS, 1)
+__global__ void __launch_bounds__(bm::THREADS_WG, 1)
 block_mlp_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmWout,
                  const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2,
                  const __grid_constant__ CUtensorMap tmXN, BlockMlpParams p) {
@@ -164,8 +170,11 @@ block_mlp_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
     while (clock64() < t_end) {}
   }
 
+  // setmaxnreg sits INSIDE each role's branch: ptxas applies the smallest count to everything after a point where the
+  // branches have merged again
   if (warp == 0) {
     // =========================== TMA producer ===========================
+    ptx::setmaxnreg_dec<104>();
     if (lane == 0) {
       uint32_t wi = 0;  // running weight-slot counter
       auto slot_acquire = [&]() -> uint8_t* {
@@ -222,6 +231,7 @@ block_mlp_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
     }
   } else if (warp == 1) {
     // =========================== MMA issuer ===========================
+    ptx::setmaxnreg_dec<104>();
     if (lane == 0) {
       constexpr uint32_t idesc256 = ptx::idesc_bf16_f32(BM, 256);
       constexpr uint32_t idesc256_amn = ptx::idesc_bf16_f32_amn(BM, 256);
@@ -345,9 +355,12 @@ block_mlp_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
         trace[32] = wt_slot; trace[33] = wt_hbuf; trace[34] = wt_hacc; trace[35] = wt_tile; trace[36] = clock64() - t_all;
       }
     }
+  } else if (warp < EPI_WARP0) {
+    ptx::setmaxnreg_dec<104>();   // idle warps of the first warpgroup
   } else {
     // =========================== epilogue warps ===========================
-    const int e = warp - 2;
+    ptx::setmaxnreg_inc<200>();
+    const int e = warp - EPI_WARP0;
     const int q = warp & 3;          // TMEM lane quarter this warp may access
     const int hf = e >> 2;           // column half
     const int r = q * 32 + lane;     // row inside the tile
@@ -355,7 +368,7 @@ block_mlp_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
     const uint32_t sHB = ptx::smem_u32(smem + OFF_HB);
     const uint32_t swz = uint32_t(r & 7);
     const LayerConsts& lc = c_mlp[p.layer];
-    const bool tr = trace && warp == 2 && lane == 0;
+    const bool tr = trace && warp == EPI_WARP0 && lane == 0;
     uint32_t it = 0;
     float4 rs[32];
     auto load_res = [&](long long lrow, bool ok, auto j0_, auto j1_) {
@@ -364,8 +377,16 @@ block_mlp_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
         rs[j] = ok ? *reinterpret_cast<const float4*>(p.res + ptx::r32_off(lrow, hf * 128 + 4 * j))
                    : make_float4(0.f, 0.f, 0.f, 0.f);
     };
+    // (lo, n) become constants once the calling loop is fully unrolled, so rs[] stays in registers
+    auto load_res_dyn = [&](long long lrow, bool ok, int lo, int n) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j >= lo && j < lo + n)
+          rs[j] = ok ? *reinterpret_cast<const float4*>(p.res + ptx::r32_off(lrow, hf * 128 + 4 * j))
+                     : make_float4(0.f, 0.f, 0.f, 0.f);
+    };
     using I0 = std::integral_constant<int, 0>;
-    using IE = std::integral_constant<int, EARLY_RES>;
+    using IE = std::integral_constant<int, (EARLY_RES > 32 ? 32 : EARLY_RES)>;
     using I32 = std::integral_constant<int, 32>;
     if (EARLY_RES && (int)blockIdx.x < p.num_tiles) {
       if (p.y_cm) {
@@ -437,7 +458,7 @@ block_mlp_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
       }
       s_part[hf][0][r] = s1;
       s_part[hf][1][r] = s2;
-      if (threadIdx.x == 64) ptx::tma_store_wait_read<0>();   // previous tile's xn store has finished reading HB
+      if (threadIdx.x == EPI_TID0) ptx::tma_store_wait_read<0>();   // previous tile's xn store has finished reading HB
       ptx::bar_sync(1, EPI_THREADS);
       const float ts1 = s_part[0][0][r] + s_part[1][0][r];
       const float ts2 = s_part[0][1][r] + s_part[1][1][r];
@@ -507,7 +528,10 @@ block_mlp_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
         if (tr) stamp(2);
       }
       // ------------------------------------------------ E3: out = R + b2 -> res (+ normalised xn for the next consumer)
-      if (EARLY_RES) load_res(pf_row, pf_ok, I0{}, IE{});   // rs is dead since E1; another CTA's rows, so E3's stores do not alias them
+      // EARLY_RES == 33: 8 float4 here, 16 between the steps of the statistics sweep, 8 between the steps of the store sweep -
+      // the loads are throttled at issue by the SM's in-flight limit (~17 KB), so one burst of 32 stalls ~4 K cycles here
+      if constexpr (EARLY_RES == 33) load_res_dyn(pf_row, pf_ok, 0, 8);
+      else if (EARLY_RES) load_res(pf_row, pf_ok, I0{}, IE{});   // rs is dead since E1; another CTA's rows, so E3's stores do not alias them
       ptx::mbar_wait(out_full, tph);
       ptx::tc_fence_after_sync();
       if (tr) stamp(2);
@@ -515,7 +539,7 @@ block_mlp_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
         // Sweep A (TMEM reads only, no stores): row statistics of out = R + b2.  The row-statistics barrier then comes after
         // a cheap sweep instead of after the store-heavy one, whose slowest warp used to hold everybody.
         float o1 = 0.f, o2 = 0.f;
-#pragma unroll 1
+#pragma unroll(EARLY_RES == 33 ? 4 : 1)
         for (int ci = 0; ci < 4; ++ci) {
           const int col = hf * 128 + ci * 32;
           uint32_t a[32];
@@ -527,6 +551,7 @@ block_mlp_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
             o1 += v;
             o2 = fmaf(v, v, o2);
           }
+          if constexpr (EARLY_RES == 33) load_res_dyn(pf_row, pf_ok, 8 + 4 * ci, 4);
         }
         s_part[hf][0][r] = o1;
         s_part[hf][1][r] = o2;
@@ -536,7 +561,7 @@ block_mlp_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
         const float rs_ = rsqrtf(v_ + p.eps);
         // Sweep B: residual stores (fp32, R32 layout) and the normalised bf16 row staged into HB (idle until the next tile's
         // first GELU chunk) as 4 k-blocks of [128 rows x 128 B], 128B-swizzled, for the TMA store - one pass.
-#pragma unroll 1
+#pragma unroll(EARLY_RES == 33 ? 4 : 1)
         for (int ci = 0; ci < 4; ++ci) {
           const int col = hf * 128 + ci * 32;
           uint32_t a[32];
@@ -558,6 +583,7 @@ block_mlp_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
             ptx::st_shared_v4(rowaddr + chunk * 16, pack_bf16(x[0], x[1]), pack_bf16(x[2], x[3]), pack_bf16(x[4], x[5]),
                               pack_bf16(x[6], x[7]));
           }
+          if constexpr (EARLY_RES == 33) load_res_dyn(pf_row, pf_ok, 24 + 2 * ci, 2);
         }
         ptx::fence_proxy_async_smem();
       } else {
@@ -580,7 +606,7 @@ block_mlp_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
       if (lane == 0) ptx::mbar_arrive(r_free);
       if (p.write_xn) {
         ptx::bar_sync(1, EPI_THREADS);
-        if (threadIdx.x == 64) {
+        if (threadIdx.x == EPI_TID0) {
           int xb, xt0;
           if (p.y_cm) { xb = tile / p.tiles_per_seq; xt0 = (tile % p.tiles_per_seq) * BM; }
           else { xb = 0; xt0 = tile * BM; }
@@ -591,7 +617,7 @@ block_mlp_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
       }
       if (tr) stamp(2);
     }
-    if (threadIdx.x == 64) ptx::tma_store_wait<0>();
+    if (threadIdx.x == EPI_TID0) ptx::tma_store_wait<0>();
   }
   ptx::tc_fence_before_sync();
   __syncthreads();

@@ -22,7 +22,9 @@ What is restated, and from where
   (SURVEY.md Appendix A.2-A.6).  PARITY UNPINNED for the backbone numerics: the
   reference holds no golden logits, forward test or fixture for it.  Independent
   cross-checks kept in `tests/test_oracle.py`: the FFT long convolution against a
-  float64 direct causal sum, and parameter counts against the advertised model size.
+  float64 direct causal sum, parameter counts against the advertised model size, and
+  `fftconv` / the `pos_emb.z` table against the independent implementation of the same
+  lineage in the installed `fla` package (`fla/modules/conv/long_conv.py`).
 """
 
 from __future__ import annotations

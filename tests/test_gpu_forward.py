@@ -284,10 +284,10 @@ def test_kernel_variants_agree(state_dict, option, T):
     try:
         ids = _ids(B, T, seed=T, pad_left=T // 4).to(torch.uint8).cuda()
         base = eng.forward(ids).clone()
-        default_on = option not in ("mlp_epi16", "mlp_pp", "mlp_early_res")
+        default_on = option not in ("mlp_epi16", "mlp_pp")
         eng.set_option(option, 0 if default_on else 1)
         other = eng.forward(ids).clone()
-        eng.set_option(option, 1 if default_on else 0)
+        eng.set_option(option, {"mlp_early_res": 33}.get(option, 1 if default_on else 0))
         again = eng.forward(ids)
         assert (other - base).abs().max().item() <= LOGIT_TOL, option
         assert torch.equal(again, base), option
