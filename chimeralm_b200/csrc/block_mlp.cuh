@@ -587,6 +587,7 @@ block_mlp_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
         }
         ptx::fence_proxy_async_smem();
       } else {
+        if constexpr (EARLY_RES == 33) load_res_dyn(pf_row, pf_ok, 8, 24);   // (no xn output: unit-test / debug form)
 #pragma unroll 1
         for (int ci = 0; ci < 4; ++ci) {
           const int col = hf * 128 + ci * 32;

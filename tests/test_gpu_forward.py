@@ -273,7 +273,7 @@ def test_full_size_batch_permutation_invariance(state_dict):
 
 
 @pytest.mark.parametrize("option,T", [("fused_score_pool", 1500), ("fused_head", 1500), ("tc_conv", 8193), ("tc_chunked", 9000),
-                                      ("fused_mlp", 700), ("fused_in", 700), ("fast_conv", 700), ("mlp_epi16", 1500), ("mlp_pp", 1500), ("mlp_early_res", 1500)])
+                                      ("fused_mlp", 700), ("fused_in", 700), ("fast_conv", 700), ("mlp_epi16", 1500), ("mlp_pp", 8193), ("mlp_early_res", 8193)])
 def test_kernel_variants_agree(state_dict, option, T):
     """Every `clm_set_option` switch selects a different kernel for the same math (fused vs unfused, tensor-core vs fp32 FFT,
     8 vs 16 epilogue warps): flipping it must not move the logits by more than the parity tolerance."""
