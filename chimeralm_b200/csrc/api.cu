@@ -225,6 +225,11 @@ __global__ void retile_bf16_kernel(const float* __restrict__ src, __nv_bfloat16*
   dst[o] = __float2bfloat16(src[i]);
 }
 
+__global__ void scale_f32_kernel(float* __restrict__ x, long long n, float f) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) x[i] *= f;
+}
+
 __global__ void f32_to_bf16_kernel(const float* __restrict__ s, __nv_bfloat16* __restrict__ d, long long n) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) d[i] = __float2bfloat16(s[i]);
@@ -826,6 +831,10 @@ int clm_finalize(clm_ctx* c) {
       if ((rc = dev_alloc(c, &b1f, (size_t)g.d_inner))) return rc;
       fold_ln_kernel<<<g.d_inner, 256>>>(fc1_w, L.fc1_b, L.ln2_g, L.ln2_b, w1f, b1f, D);
       CLM_LAUNCH_CHECK(c, "fold_ln2");
+      // the fused block tail works on h = fc1(x) / 2 (bm::gelu_tanh_bf16x2): halve W1' and b1' (exact)
+      scale_f32_kernel<<<(unsigned)(((size_t)g.d_inner * D + 255) / 256), 256>>>(w1f, (long long)g.d_inner * D, 0.5f);
+      scale_f32_kernel<<<(unsigned)((g.d_inner + 255) / 256), 256>>>(b1f, g.d_inner, 0.5f);
+      CLM_LAUNCH_CHECK(c, "scale_fc1");
       if ((rc = retile(c, out_w, D, D, 256, &L.out_wt, &L.tm_out_t))) return rc;
       if ((rc = retile(c, w1f, g.d_inner, D, 128, &L.fc1_wt, &L.tm_fc1_t))) return rc;
       if ((rc = retile(c, fc2_w, D, g.d_inner, 256, &L.fc2_wt, &L.tm_fc2_t))) return rc;

@@ -61,7 +61,7 @@ constexpr int MAX_LAYERS = 8;
 struct LayerConsts {
   float b_out[256];
   float b2[256];
-  float b1[1024];   // fc1 bias with LayerNorm2's beta folded in
+  float b1[1024];   // (fc1 bias with LayerNorm2's beta folded in) / 2, see gelu_tanh_bf16x2
 };
 __constant__ LayerConsts c_mlp[MAX_LAYERS];
 
@@ -83,29 +83,27 @@ constexpr int EPI_TID0 = EPI_WARP0 * 32;
 constexpr int EPI_THREADS = 256;
 constexpr int NCHUNK = DI / 128;                 // 8 fc1 column chunks
 
-__device__ __forceinline__ float gelu_tanh_fast(float x) {
-  // 0.5 x (1 + tanh(u)), u = sqrt(2/pi) (x + 0.044715 x^3); tanh.approx is ONE MUFU op (the
-  // exp + rcp formulation needs two and made the GELU epilogue MUFU-bound at the MMA's pace).
-  // |tanh.approx error| <= 2^-10.987, well below the bf16 rounding applied to the result.
-  const float x2 = x * x;
-  const float u = x * fmaf(0.035677408136300125f, x2, 0.7978845608028654f);
+// The fused kernels' fc1 weights and bias are stored pre-multiplied by 1/2 (exact in bf16 / fp32), so the accumulator
+// holds h = x / 2 and gelu_tanh(x) = h + h tanh(u), u = sqrt(2/pi) (x + 0.044715 x^3) = h (2 c0 + 8 c1 h^2): one multiply per
+// element less than starting from x.
+__device__ __forceinline__ float gelu_tanh_fast(float h) {
+  // tanh.approx is ONE MUFU op (the exp + rcp formulation needs two and made the GELU epilogue MUFU-bound at the
+  // MMA's pace).  |tanh.approx error| <= 2^-10.987, well below the bf16 rounding applied to the result.
+  const float u = h * fmaf(0.285419265090401f, h * h, 1.5957691216057308f);
   float t;
   asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(u));
-  const float hx = 0.5f * x;
-  return fmaf(hx, t, hx);
+  return fmaf(h, t, h);
 }
-// Two GELUs at once on packed fp32 pairs (FMUL2/FFMA2): 4.5 issue slots per element instead of 8.
-__device__ __forceinline__ uint32_t gelu_tanh_bf16x2(f2t x) {
-  const f2t C0 = f2_pack(0.7978845608028654f, 0.7978845608028654f), C1 = f2_pack(0.035677408136300125f, 0.035677408136300125f);
-  const f2t HALF = f2_pack(0.5f, 0.5f);
-  const f2t u = f2_mul(x, f2_fma(f2_mul(x, x), C1, C0));
+// Two GELUs at once on packed fp32 pairs (FMUL2/FFMA2): 4 issue slots per element instead of 8.
+__device__ __forceinline__ uint32_t gelu_tanh_bf16x2(f2t h) {
+  const f2t C0 = f2_pack(1.5957691216057308f, 1.5957691216057308f), C1 = f2_pack(0.285419265090401f, 0.285419265090401f);
+  const f2t u = f2_mul(h, f2_fma(f2_mul(h, h), C1, C0));
   float u0, u1, t0, t1;
   f2_unpack(u, u0, u1);
   asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(u0));
   asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(u1));
-  const f2t hx = f2_mul(x, HALF);
   float r0, r1;
-  f2_unpack(f2_fma(hx, f2_pack(t0, t1), hx), r0, r1);
+  f2_unpack(f2_fma(h, f2_pack(t0, t1), h), r0, r1);
   return pack_bf16(r0, r1);
 }
 }  // namespace bm
