@@ -131,6 +131,7 @@ struct clm_ctx {
   bool mlp_2cta = false;  // CTA-pair (cta_group::2) version of the fused block tail
   bool mlp_epi16 = false; // fused block tail with 16 epilogue warps (block_mlp16.cuh)
   int mlp_early_res = 33; // block_mlp: float4 of the next tile's residual half-row loaded before E3 (0, 16, 32; 33 = spread over E3)
+  int mlp_fc2_lag = 1;    // block_mlp: fc2 of chunk j - lag is issued after fc1 of chunk j (2: recorded experiment, no faster)
   int mlp_grid = 0;       // block_mlp: cap on the number of CTAs (0 = one per SM); diagnostic
   bool mlp_pp = false;    // fused block tail with two interleaved fc1/GELU/fc2 chains of 64-unit chunks (block_mlp_pp.cuh)
   bool y_channel_major = true;  // block_mlp reads the conv output channel-major (MN-major UMMA operand): no transpose
@@ -422,15 +423,16 @@ int launch_block_mlp(clm_ctx* c, int layer, const __nv_bfloat16* y, float* res, 
     CLM_LAUNCH_CHECK(c, "block_mlp16");
     return 0;
   }
-#define CLM_MLP_LAUNCH(E)                                                                                                  \
+#define CLM_MLP_LAUNCH(E, LAG)                                                                                             \
   {                                                                                                                        \
-    if (int rc_attr = ensure_smem_attr(c, (const void*)(block_mlp_kernel<E>), (int)(bm::SMEM_TOTAL))) return rc_attr;       \
-    block_mlp_kernel<E><<<grid, bm::THREADS_WG, bm::SMEM_TOTAL, st>>>(tmY, L.tm_out_t, L.tm_fc1_t, L.tm_fc2_t, tmXN, p);      \
+    if (int rc_attr = ensure_smem_attr(c, (const void*)(block_mlp_kernel<E, LAG>), (int)(bm::SMEM_TOTAL))) return rc_attr;  \
+    block_mlp_kernel<E, LAG><<<grid, bm::THREADS_WG, bm::SMEM_TOTAL, st>>>(tmY, L.tm_out_t, L.tm_fc1_t, L.tm_fc2_t, tmXN, p); \
   }
-  if (c->mlp_early_res >= 33) CLM_MLP_LAUNCH(33)
-  else if (c->mlp_early_res >= 32) CLM_MLP_LAUNCH(32)
-  else if (c->mlp_early_res >= 16) CLM_MLP_LAUNCH(16)
-  else CLM_MLP_LAUNCH(0)
+  if (c->mlp_fc2_lag >= 2) CLM_MLP_LAUNCH(33, 2)
+  else if (c->mlp_early_res >= 33) CLM_MLP_LAUNCH(33, 1)
+  else if (c->mlp_early_res >= 32) CLM_MLP_LAUNCH(32, 1)
+  else if (c->mlp_early_res >= 16) CLM_MLP_LAUNCH(16, 1)
+  else CLM_MLP_LAUNCH(0, 1)
 #undef CLM_MLP_LAUNCH
   CLM_LAUNCH_CHECK(c, "block_mlp");
   return 0;
@@ -1250,6 +1252,7 @@ int clm_set_option(clm_ctx* c, const char* name, int value) {
   else if (n == "mlp_epi16") c->mlp_epi16 = value != 0;
   else if (n == "mlp_pp") c->mlp_pp = value != 0;
   else if (n == "mlp_grid") c->mlp_grid = value;
+  else if (n == "mlp_fc2_lag") c->mlp_fc2_lag = value;
   else if (n == "mlp_early_res") c->mlp_early_res = value;
   else return fail(c, CLM_ERR_INVALID, "clm_set_option: unknown option '%s'", name);
   return 0;

@@ -111,7 +111,13 @@ __device__ __forceinline__ uint32_t gelu_tanh_bf16x2(f2t h) {
 // EARLY_RES: the next tile's residual half-row is loaded into registers BEFORE the output epilogue (E3) of this tile
 // instead of after it, so the loads (per-SM outstanding-miss bound: ~6.5 K cycles for 128 KB even from L2) complete
 // under E3's stores instead of in front of E1.
-template <int EARLY_RES>   // number of the 32 float4 loaded early (0 = all after E3, the first version)
+// LAG: fc2 of chunk j - LAG is issued right after fc1 of chunk j (1 in production).  tcgen05.mma issue blocks while the MMA
+// queue is full, so the issuing thread runs in step with the tensor pipe: per chunk it spends ~1 440 cycles issuing fc1
+// (16 TS-form MMAs, 90 cycles each instead of the probe's 64), ~1 070 issuing fc2 and ~880 in barrier waits that nothing
+// overlaps - that sum is the 3.1 K chunk period.  LAG = 2 (wait for the drain first, the fc2 issued afterwards has had its
+// operand ready for a whole chunk) moves time from the gelu(h) wait to the drain wait and is no faster; a second issuing
+// thread for fc2 was slower (its MMAs queue in front of fc1 on the epilogue's critical path).  profiles/r1_trace_block_mlp.txt.
+template <int EARLY_RES, int LAG = 1>   // EARLY_RES: number of the 32 float4 loaded early (0 = all after E3)
 __global__ void __launch_bounds__(bm::THREADS_WG, 1)
 block_mlp_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmWout,
                  const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2,
@@ -207,7 +213,7 @@ block_mlp_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
           ptx::tma_load_2d(s, &tmWout, &w_full[wi % NSLOT], 0, kb * 256);
           ++wi;
         }
-        for (int j = 0; j <= NCHUNK; ++j) {
+        for (int j = 0; j < NCHUNK + LAG; ++j) {
           if (j < NCHUNK) {  // fc1 chunk jc: k-blocks (2 h2, 2 h2 + 1) = rows [(4 jc + 2 h2) 128, +256)
             const int jc = (j + rot) & (NCHUNK - 1);
             for (int h2 = 0; h2 < 2; ++h2) {
@@ -216,8 +222,8 @@ block_mlp_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
               ++wi;
             }
           }
-          if (j >= 1) {  // fc2 K-chunk jj: k-blocks 2 jj + kb = rows [(2 jj + kb) 256, +256)
-            const int jj = (j - 1 + rot) & (NCHUNK - 1);
+          if (j >= LAG) {  // fc2 K-chunk jj: k-blocks 2 jj + kb = rows [(2 jj + kb) 256, +256)
+            const int jj = (j - LAG + rot) & (NCHUNK - 1);
             for (int kb = 0; kb < 2; ++kb) {
               uint8_t* s = slot_acquire();
               ptx::tma_load_2d(s, &tmW2, &w_full[wi % NSLOT], 0, (jj * 2 + kb) * 256);
@@ -237,7 +243,7 @@ block_mlp_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
       const uint32_t sHB = ptx::smem_u32(smem + OFF_HB);
       const uint32_t sW = ptx::smem_u32(smem + OFF_W);
       uint32_t wi = 0;
-      long long wt_slot = 0, wt_hbuf = 0, wt_hacc = 0, wt_tile = 0, t_all = clock64();
+      long long wt_slot = 0, wt_hbuf = 0, wt_hacc = 0, wt_tile = 0, wt_i1 = 0, wt_i2 = 0, t_all = clock64();
       // The barrier of the NEXT ring slot is probed right after the current slot is handed out, so the
       // ~100-cycle try_wait round trip overlaps the MMA issue instead of preceding every slot.
       bool next_ready = false;
@@ -299,7 +305,7 @@ block_mlp_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
         ptx::umma_commit(g1_done);
         stamp(1);
         // ---- fc1 / fc2 software pipeline
-        for (int j = 0; j <= NCHUNK; ++j) {
+        for (int j = 0; j < NCHUNK + LAG; ++j) {
           if (j < NCHUNK) {
             const uint32_t u = it * NCHUNK + j;
             { const long long t_ = trace ? clock64() : 0;
@@ -313,6 +319,7 @@ block_mlp_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
               if (trace) wt_hacc += clock64() - t_; }
             ptx::tc_fence_after_sync();
             stamp(1);
+            const long long ti1_ = trace ? clock64() : 0, ts1_ = wt_slot;   // issue time of the group, slot waits excluded
             for (int h2 = 0; h2 < 2; ++h2) {
               const uint32_t sw = slot_wait();
 #pragma unroll
@@ -326,15 +333,17 @@ block_mlp_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
               slot_release();
             }
             ptx::umma_commit(hacc_full);
+            if (trace) wt_i1 += (clock64() - ti1_) - (wt_slot - ts1_);
           }
-          if (j >= 1) {
-            const int jj = j - 1;
+          if (j >= LAG) {
+            const int jj = j - LAG;
             const uint32_t b = jj & 1, u = it * 4 + (jj >> 1);
             { const long long t_ = trace ? clock64() : 0;
               ptx::mbar_wait(&hbuf_full[b], u & 1);
               if (trace) wt_hbuf += clock64() - t_; }
             ptx::tc_fence_after_sync();
             stamp(1);
+            const long long ti2_ = trace ? clock64() : 0, ts2_ = wt_slot;
             for (int kb = 0; kb < 2; ++kb) {
               const uint32_t sw = slot_wait();
               const uint64_t da = ptx::smem_desc_k_sw128(sHB + b * HB_BYTES + kb * KB_BYTES);
@@ -344,6 +353,7 @@ block_mlp_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
               slot_release();
             }
             ptx::umma_commit(&hbuf_free[b]);
+            if (trace) wt_i2 += (clock64() - ti2_) - (wt_slot - ts2_);
           }
         }
         ptx::umma_commit(out_full);
@@ -351,6 +361,7 @@ block_mlp_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
       }
       if (trace) {   // where the issuing thread waited (row 0, slots 32..36): weights, gelu(h), H drain, tile-level, total
         trace[32] = wt_slot; trace[33] = wt_hbuf; trace[34] = wt_hacc; trace[35] = wt_tile; trace[36] = clock64() - t_all;
+        trace[37] = wt_i1; trace[38] = wt_i2;   // cycles spent issuing the fc1 / fc2 groups (slot waits excluded)
       }
     }
   } else if (warp < EPI_WARP0) {

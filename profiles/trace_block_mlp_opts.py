@@ -35,9 +35,10 @@ for setting in sys.argv[1:] or [""]:
     eng._check(eng.lib.clm_block_mlp_cm_trace(*args, C.c_void_p(tr.data_ptr()), st), "trace")
     torch.cuda.synchronize()
     t = tr.cpu().clone()
-    w = [int(x) for x in t[0][32:37]]
-    print(f"  MMA-thread waits: weights {w[0]}, gelu(h) ready {w[1]}, H drained {w[2]}, tile-level {w[3]}, total {w[4]}")
-    t[0][32:37] = 0
+    w = [int(x) for x in t[0][32:39]]
+    print(f"  MMA-thread waits: weights {w[0]}, gelu(h) ready {w[1]}, H drained {w[2]}, tile-level {w[3]}, total {w[4]}; "
+          f"issuing fc1 groups {w[5]}, fc2 groups {w[6]} (whole launch, CTA 0)")
+    t[0][32:39] = 0
     t0 = int(t[t > 0].min())
     for role, name in ((1, "mma"), (2, "epilogue")):
         v = [int(x) - t0 for x in t[role] if x > 0]
