@@ -16,6 +16,7 @@ forward + argmax) on a bounded sample.
 from __future__ import annotations
 
 import argparse
+import datetime
 import json
 import os
 import subprocess
@@ -52,18 +53,27 @@ def peaks():
 
 
 class ClockSampler:
-    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    """`nvidia-smi -lms 20` on one GPU.  Started early (nvidia-smi needs up to a second to come up on an 8-GPU box, longer
+    than a short timed region), rows are time-stamped and only those taken inside [mark_start, mark_end] are reported."""
+    QUERY = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         self.p = None
+        self.t0 = self.t1 = None
         try:
             self.p = subprocess.Popen(["nvidia-smi", f"--id={gpu_index}", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
                                        "-lms", "20"], stdout=self.f, stderr=subprocess.DEVNULL)
         except OSError:
             pass
+
+    def mark_start(self):
+        self.t0 = datetime.datetime.now()
+
+    def mark_end(self):
+        self.t1 = datetime.datetime.now()
 
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
@@ -75,15 +85,30 @@ class ClockSampler:
         except subprocess.TimeoutExpired:
             self.p.kill()
         self.f.flush()
-        rows = [r.split(", ") for r in Path(self.f.name).read_text().strip().splitlines() if r.count(",") >= 8]
+        rows = [r.split(", ") for r in Path(self.f.name).read_text().strip().splitlines() if r.count(",") >= 9]
         os.unlink(self.f.name)
         if not rows:
             return out
-        sm = sorted(float(r[1]) for r in rows)
+
+        def when(r):
+            try:
+                return datetime.datetime.strptime(r[0].strip(), "%Y/%m/%d %H:%M:%S.%f")
+            except ValueError:
+                return None
+
+        inside = [r for r in rows if self.t0 and self.t1 and when(r) and self.t0 <= when(r) <= self.t1]
+        if inside:
+            out["window"] = "timed region"
+        else:  # region shorter than the sampling period: the samples taken under load closest to it (warm-up + region)
+            before_end = [r for r in rows if self.t1 and when(r) and when(r) <= self.t1]
+            inside = before_end[-3:] or rows[-3:]
+            out["window"] = "last samples up to the end of the timed region (region shorter than the 20 ms sampling period)"
+        rows = inside
+        sm = sorted(float(r[2]) for r in rows)
         out["sm_mhz"] = sm[len(sm) // 2]
-        out["sm_max_mhz"] = float(rows[0][2])
+        out["sm_max_mhz"] = float(rows[0][3])
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        out["reasons"] = [n for i, n in enumerate(names) if any(r[5 + i].strip().lower().startswith("active") for r in rows)]
+        out["reasons"] = [n for i, n in enumerate(names) if any(r[6 + i].strip().lower().startswith("active") for r in rows)]
         out["samples"] = len(rows)
         return out
 
@@ -176,6 +201,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    sampler = ClockSampler(local_rank) if rank == 0 else None   # started now, rows outside the timed region are dropped
     B, L = args.batch, args.read_len
     T = L + 1
     eng = Engine(sd, device=local_rank, max_batch=B, max_tokens=T)
@@ -203,7 +229,8 @@ def main():
     for i in range(args.warmup):
         step_resident(i)
     barrier()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.mark_start()
     eng.profile_reset()
     eng.profile(True)
     launches0 = eng.launch_count
@@ -219,6 +246,8 @@ def main():
         dist.all_gather(gathered, my_labels)
     ev1.record()
     barrier()
+    if sampler:
+        sampler.mark_end()
     ms = ev0.elapsed_time(ev1)
     launches = eng.launch_count - launches0
     prof = eng.profile_read()
