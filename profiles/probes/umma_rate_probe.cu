@@ -31,7 +31,10 @@ __global__ void __launch_bounds__(128, 1) probe(int n_mma, int same_acc, long lo
     for (int i = 0; i < n_mma; ++i) {
       const int k = i & 3;
       const uint32_t d = tb + (same_acc ? 0 : ((i >> 2) & 1) * 256);
-      if (MODE == 1) ptx::umma_f16_ts(d, tb + 384 + k * 8, db + 2 * k, idesc, i >= 8);
+      if (MODE == 3) {   // the fused block tail's fc1: 16 K-steps walk 128 TMEM columns of A and four 16 KB k-blocks of B
+        const int kk = i & 15;
+        ptx::umma_f16_ts(d, tb + 384 + kk * 8, ptx::smem_desc_k_sw128(sB + (kk >> 2) * 8192) + 2 * (kk & 3), idesc, i >= 16);
+      } else if (MODE == 1) ptx::umma_f16_ts(d, tb + 384 + k * 8, db + 2 * k, idesc, i >= 8);
       else if (MODE == 2) ptx::umma_f16(d, da + 128 * k, db + 2 * k, idesc, i >= 8);
       else ptx::umma_f16(d, da + 2 * k, db + 2 * k, idesc, i >= 8);
     }
@@ -75,6 +78,7 @@ int main() {
     run<128, 1>("TS (A tmem)  M128 N128", grid, d);
     run<256, 1>("TS (A tmem)  M128 N256", grid, d);
     run<256, 2>("SS A MN-major M128 N256", grid, d);
+    run<128, 3>("TS 16 K-steps M128 N128", grid, d);
     run<64, 0>("SS K-major   M128 N64", grid, d);
     run<64, 1>("TS (A tmem)  M128 N64", grid, d);
     run<96, 1>("TS (A tmem)  M128 N96", grid, d);
