@@ -147,7 +147,7 @@ block_mlp_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
   long long* trace = (p.trace && blockIdx.x == 0) ? p.trace : nullptr;
   int trace_n = 0;
   auto stamp = [&](int role) {
-    if (trace && trace_n < 64) trace[role * 64 + trace_n++] = clock64();
+    if (trace && lane == 0 && trace_n < 64) trace[role * 64 + trace_n++] = clock64();
   };
 
   if (warp == 0 && lane == 0) {
@@ -236,7 +236,7 @@ block_mlp_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
   } else if (warp == 1) {
     // =========================== MMA issuer ===========================
     ptx::setmaxnreg_dec<104>();
-    if (lane == 0) {
+    {   // the WHOLE warp runs this loop (uniform control flow and descriptors); one elected lane issues, see ptx::umma_f16_e
       constexpr uint32_t idesc256 = ptx::idesc_bf16_f32(BM, 256);
       constexpr uint32_t idesc256_amn = ptx::idesc_bf16_f32_amn(BM, 256);
       constexpr uint32_t idesc128 = ptx::idesc_bf16_f32(BM, 128);
@@ -264,7 +264,7 @@ block_mlp_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
         return sW + s * SLOT_BYTES;
       };
       auto slot_release = [&]() {
-        ptx::umma_commit(&w_empty[wi % NSLOT]);
+        ptx::umma_commit_e(&w_empty[wi % NSLOT]);
         ++wi;
       };
       uint32_t it = 0;
@@ -292,17 +292,17 @@ block_mlp_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
             const uint64_t da = ptx::smem_desc_mn_sw128(sx, KB_BYTES / 2, 1024);
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-              ptx::umma_f16(tmem_base + TM_R, da + (2048 >> 4) * k, db + 2 * k, idesc256_amn, (kb | k) != 0);
+              ptx::umma_f16_e(tmem_base + TM_R, da + (2048 >> 4) * k, db + 2 * k, idesc256_amn, (kb | k) != 0);
           } else {
             const uint64_t da = ptx::smem_desc_k_sw128(sx);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) ptx::umma_f16(tmem_base + TM_R, da + 2 * k, db + 2 * k, idesc256, (kb | k) != 0);
+            for (int k = 0; k < 4; ++k) ptx::umma_f16_e(tmem_base + TM_R, da + 2 * k, db + 2 * k, idesc256, (kb | k) != 0);
           }
           slot_release();
-          if (kb == 1) ptx::umma_commit(&w_empty[wi_y0 % NSLOT]);
-          if (kb == 3) ptx::umma_commit(&w_empty[wi_y1 % NSLOT]);
+          if (kb == 1) ptx::umma_commit_e(&w_empty[wi_y0 % NSLOT]);
+          if (kb == 3) ptx::umma_commit_e(&w_empty[wi_y1 % NSLOT]);
         }
-        ptx::umma_commit(g1_done);
+        ptx::umma_commit_e(g1_done);
         stamp(1);
         // ---- fc1 / fc2 software pipeline
         for (int j = 0; j < NCHUNK + LAG; ++j) {
@@ -328,11 +328,11 @@ block_mlp_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
                 const uint64_t db = ptx::smem_desc_k_sw128(sw + q * KB_BYTES);
 #pragma unroll
                 for (int k = 0; k < 4; ++k)   // A = xn from TMEM: 8 columns (16 bf16) per K step
-                  ptx::umma_f16_ts(tmem_base + TM_H, tmem_base + TM_XN + (kb * 4 + k) * 8, db + 2 * k, idesc128, (kb | k) != 0);
+                  ptx::umma_f16_ts_e(tmem_base + TM_H, tmem_base + TM_XN + (kb * 4 + k) * 8, db + 2 * k, idesc128, (kb | k) != 0);
               }
               slot_release();
             }
-            ptx::umma_commit(hacc_full);
+            ptx::umma_commit_e(hacc_full);
             if (trace) wt_i1 += (clock64() - ti1_) - (wt_slot - ts1_);
           }
           if (j >= LAG) {
@@ -349,17 +349,17 @@ block_mlp_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
               const uint64_t da = ptx::smem_desc_k_sw128(sHB + b * HB_BYTES + kb * KB_BYTES);
               const uint64_t db = ptx::smem_desc_k_sw128(sw);
 #pragma unroll
-              for (int k = 0; k < 4; ++k) ptx::umma_f16(tmem_base + TM_R, da + 2 * k, db + 2 * k, idesc256, 1u);
+              for (int k = 0; k < 4; ++k) ptx::umma_f16_e(tmem_base + TM_R, da + 2 * k, db + 2 * k, idesc256, 1u);
               slot_release();
             }
-            ptx::umma_commit(&hbuf_free[b]);
+            ptx::umma_commit_e(&hbuf_free[b]);
             if (trace) wt_i2 += (clock64() - ti2_) - (wt_slot - ts2_);
           }
         }
-        ptx::umma_commit(out_full);
+        ptx::umma_commit_e(out_full);
         stamp(1);
       }
-      if (trace) {   // where the issuing thread waited (row 0, slots 32..36): weights, gelu(h), H drain, tile-level, total
+      if (trace && lane == 0) {   // where the issuing thread waited (row 0, slots 32..36): weights, gelu(h), H drain, tile-level, total
         trace[32] = wt_slot; trace[33] = wt_hbuf; trace[34] = wt_hacc; trace[35] = wt_tile; trace[36] = clock64() - t_all;
         trace[37] = wt_i1; trace[38] = wt_i2;   // cycles spent issuing the fc1 / fc2 groups (slot waits excluded)
       }

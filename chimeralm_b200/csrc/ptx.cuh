@@ -152,6 +152,43 @@ __device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, ui
       "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Whole-warp forms: every lane of a converged warp executes the call, one elected lane issues.  When the issuing loop
+// is warp-uniform the descriptors live in uniform registers and each MMA costs a handful of instructions; inside an
+// `if (lane == 0)` region the compiler treats them as per-thread values and emits ELECT + 5 x R2UR.BROADCAST + a
+// BRA.U.ANY loop per MMA (~16 dependent instructions), more than the 64 cycles an N = 128 MMA takes.
+__device__ __forceinline__ void umma_f16_e(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                           uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_f16_ts_e(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_e(uint64_t* bar) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t"
+      "}\n" ::"r"(smem_u32(bar))
+      : "memory");
+}
 // Arrive on an mbarrier when all previously issued MMAs of this thread have completed
 // (implies tcgen05.fence::before_thread_sync).
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
