@@ -88,7 +88,7 @@ block_in_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
   long long* trace = (p.trace && blockIdx.x == 0) ? p.trace : nullptr;
   int trace_n = 0;
   auto stamp = [&](int role) {
-    if (trace && trace_n < 64) trace[role * 64 + trace_n++] = clock64();
+    if (trace && (threadIdx.x & 31) == 0 && trace_n < 64) trace[role * 64 + trace_n++] = clock64();
   };
 
   if (warp == 0 && lane == 0) {
@@ -132,7 +132,7 @@ block_in_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
     }
   } else if (warp == 1) {
     // =========================== MMA issuer ===========================
-    if (lane == 0) {
+    {   // whole warp, uniform control flow; one elected lane issues (ptx::umma_f16_e)
       constexpr uint32_t idesc = ptx::idesc_bf16_f32(128, NCOL);
       const uint32_t sXN = ptx::smem_u32(smem + OFF_XN), sW = ptx::smem_u32(smem + OFF_W);
       uint32_t wi = 0, it = 0, pass = 0;
@@ -158,15 +158,15 @@ block_in_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
                 const uint64_t db = ptx::smem_desc_k_sw128(sXN + kb * KB_ROWS_BYTES);
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
-                  ptx::umma_f16(tmem_base + g * GCOLS, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                  ptx::umma_f16_e(tmem_base + g * GCOLS, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
               }
-              ptx::umma_commit(&w_empty[s]);
+              ptx::umma_commit_e(&w_empty[s]);
               ++wi;
             }
-            if (g == 0) ptx::umma_commit(&acc_full[0]);
-            if (g == 2) ptx::umma_commit(&acc_full[1]);
+            if (g == 0) ptx::umma_commit_e(&acc_full[0]);
+            if (g == 2) ptx::umma_commit_e(&acc_full[1]);
           }
-          if (h == 1) ptx::umma_commit(xn_free);
+          if (h == 1) ptx::umma_commit_e(xn_free);
           stamp(0);
         }
       }

@@ -209,7 +209,7 @@ longconv_tc_kernel(const __grid_constant__ CUtensorMap tmVX, const __grid_consta
   long long* trace = (p.trace && blockIdx.x == 0) ? p.trace : nullptr;
   int trace_n = 0;
   auto stamp = [&](int role) {
-    if (trace && trace_n < 64) trace[role * 64 + trace_n++] = clock64();
+    if (trace && (threadIdx.x & 31) == 0 && trace_n < 64) trace[role * 64 + trace_n++] = clock64();
   };
 
   // constant stack -> shared memory
@@ -269,7 +269,7 @@ longconv_tc_kernel(const __grid_constant__ CUtensorMap tmVX, const __grid_consta
     }
   } else if (warp == 1) {
     // =========================== MMA issuer ===========================
-    if (lane == 0) {
+    {   // whole warp, uniform control flow; one elected lane issues (ptx::umma_f16_e)
       constexpr uint32_t id1 = idesc(128, false, true);    // step 1: A K-major, B MN-major, N = 128
       constexpr uint32_t id35 = idesc(256, false, false);  // steps 3, 5: A from TMEM, B K-major, N = 256
       // step 7: A MN-major, B K-major; N = 64 output rows n1, or 80 when tail tokens are wanted (row n1 = 64 = outputs
@@ -297,12 +297,12 @@ longconv_tc_kernel(const __grid_constant__ CUtensorMap tmVX, const __grid_consta
             const int rows = o == 0 ? (part == 0 ? ROW_FRE : ROW_NFIM) : (part == 0 ? ROW_FIM : ROW_FRE);
 #pragma unroll
             for (int j = 0; j < 4; ++j)                    // 16 n1 rows per MMA
-              ptx::umma_f16(TM_X + o * 128, s_desc(rows, 16 * j), dZ + (uint64_t)((part * 16384 + 2048 * j) >> 4), id1,
+              ptx::umma_f16_e(TM_X + o * 128, s_desc(rows, 16 * j), dZ + (uint64_t)((part * 16384 + 2048 * j) >> 4), id1,
                             (part | j) != 0);
           }
         }
-        ptx::umma_commit(&z_empty[buf]);
-        ptx::umma_commit(x_full);
+        ptx::umma_commit_e(&z_empty[buf]);
+        ptx::umma_commit_e(x_full);
         stamp(0);
         // ---- step 3: Y = [S_re | S_im] = P1 x F
         ptx::mbar_wait(&p1_full[0], ph);
@@ -316,9 +316,9 @@ longconv_tc_kernel(const __grid_constant__ CUtensorMap tmVX, const __grid_consta
           }
           const int t = s & 1, n2 = 16 * (s >> 1);          // packed K order: per run of 16 indices, re then im
           const int rows = t == 0 ? ROW_FRE : ROW_NFIM;    // re part: [Fre; Fim], im part: [-Fim; Fre]
-          ptx::umma_f16_ts(TM_Y, TM_X + 8 * s, s_desc(rows, n2), id35, s != 0);
+          ptx::umma_f16_ts_e(TM_Y, TM_X + 8 * s, s_desc(rows, n2), id35, s != 0);
         }
-        ptx::umma_commit(y_full);
+        ptx::umma_commit_e(y_full);
         stamp(0);
         // ---- step 5: X = [B_im | B_re] = P2 x conj(F)
         ptx::mbar_wait(&p2_full[0], ph);
@@ -332,9 +332,9 @@ longconv_tc_kernel(const __grid_constant__ CUtensorMap tmVX, const __grid_consta
           }
           const int t = s & 1, k2 = 16 * (s >> 1);
           const int rows = t == 0 ? ROW_NFIM : ROW_FRE;    // re part: [-Fim; Fre], im part: [Fre; Fim]
-          ptx::umma_f16_ts(TM_X, TM_Y + 8 * s, s_desc(rows, k2), id35, s != 0);
+          ptx::umma_f16_ts_e(TM_X, TM_Y + 8 * s, s_desc(rows, k2), id35, s != 0);
         }
-        ptx::umma_commit(x2_full);
+        ptx::umma_commit_e(x2_full);
         stamp(0);
         // ---- step 7: Y[0,64) = z_re = Bre Fre + Bim Fim, Y[64,128) = z_im = Bim Fre - Bre Fim   (n1 < 64)
         ptx::mbar_wait(bt_full, ph);
@@ -348,11 +348,11 @@ longconv_tc_kernel(const __grid_constant__ CUtensorMap tmVX, const __grid_consta
             const int rows = o == 0 ? (part == 0 ? ROW_FRE : ROW_FIM) : (part == 0 ? ROW_NFIM : ROW_FRE);
 #pragma unroll
             for (int j = 0; j < 8; ++j)
-              ptx::umma_f16(TM_Y + o * ZIM, dBT + (uint64_t)(((part * 128 + 16 * j) * 128) >> 4), s_desc(rows, 16 * j), id7,
+              ptx::umma_f16_e(TM_Y + o * ZIM, dBT + (uint64_t)(((part * 128 + 16 * j) * 128) >> 4), s_desc(rows, 16 * j), id7,
                             (part | j) != 0);
           }
         }
-        ptx::umma_commit(o_full);
+        ptx::umma_commit_e(o_full);
         stamp(0);
       }
     }
