@@ -100,11 +100,19 @@ __device__ __forceinline__ uint32_t gelu_tanh_bf16x2(f2t h) {
   const f2t u = f2_mul(h, f2_fma(f2_mul(h, h), C1, C0));
   float u0, u1, t0, t1;
   f2_unpack(u, u0, u1);
+#if defined(CLM_E2_DIAG) && CLM_E2_DIAG == 1   // timing diagnostic only (wrong results): no MUFU
+  t0 = u0; t1 = u1;
+#else
   asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(u0));
   asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(u1));
+#endif
+#if defined(CLM_E2_DIAG) && CLM_E2_DIAG == 2   // timing diagnostic only (wrong results): MUFU only, no tail arithmetic
+  return pack_bf16(t0, t1);
+#else
   float r0, r1;
   f2_unpack(f2_fma(h, f2_pack(t0, t1), h), r0, r1);
   return pack_bf16(r0, r1);
+#endif
 }
 }  // namespace bm
 
@@ -513,17 +521,23 @@ block_mlp_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
           for (int i = 0; i < 8; ++i)
             asm volatile("prefetch.global.L2 [%0];" ::"l"(p.res + ptx::r32_off(pf_row, hf * 128 + 4 * (8 * j + i))));
         }
-        const float* b1p = lc.b1 + ((j + rot) & (NCHUNK - 1)) * 128 + hf * 64;
         const uint32_t rowaddr = sHB + b * HB_BYTES + hf * KB_BYTES + r * 128;
         // all the GELU math first (results in registers), THEN wait for fc2 of chunk j - 2 to release the HB buffer:
         // that MMA group sits behind fc1 of chunk j in the tensor pipe, ~1000 cycles after this epilogue may start
         uint32_t o[32];
+        // (CLM_E2_DIAG = 1 / 2 / 3 compile timing-only variants without MUFU / without the tail arithmetic / without the bias
+        // loads: they shorten this ~2.3 K-cycle epilogue by 250 / 0 / 350 cycles - no single piece dominates it.)
+        const float* b1p = lc.b1 + ((j + rot) & (NCHUNK - 1)) * 128 + hf * 64;
 #pragma unroll
         for (int g = 0; g < 8; ++g) {
           const uint32_t* src = (g < 4) ? &a0[g * 8] : &a1[(g - 4) * 8];
 #pragma unroll
           for (int jj = 0; jj < 4; ++jj)
+#if defined(CLM_E2_DIAG) && CLM_E2_DIAG == 3   // timing diagnostic only (wrong results): no bias loads
+            o[4 * g + jj] = gelu_tanh_bf16x2(f2_add(f2_packu(src[2 * jj], src[2 * jj + 1]), f2_pack(0.25f, 0.125f)));
+#else
             o[4 * g + jj] = gelu_tanh_bf16x2(f2_add(f2_packu(src[2 * jj], src[2 * jj + 1]), f2_pack(b1p[g * 8 + 2 * jj], b1p[g * 8 + 2 * jj + 1])));
+#endif
         }
         ptx::mbar_wait(&hbuf_free[b], (u & 1) ^ 1);
 #pragma unroll
