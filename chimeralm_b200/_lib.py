@@ -14,6 +14,7 @@ LIB_NAME = "libchimeralm_b200.so"
 LIB_PATH = Path(__file__).resolve().parent / LIB_NAME
 
 CLM_F32, CLM_BF16, CLM_U8, CLM_I32, CLM_I64 = 0, 1, 2, 3, 4
+CLM_ERR_STATE, CLM_ERR_TOKEN_RANGE, CLM_ERR_FP16_RANGE = -3, -6, -7
 EPI_BIAS_BF16, EPI_BIAS_GELU_TANH, EPI_BIAS_RES_F32, EPI_SCORE = 0, 1, 2, 3
 
 
@@ -25,7 +26,13 @@ class clm_config(C.Structure):
 
 
 class ChimeraLMNativeError(RuntimeError):
-    pass
+    def __init__(self, msg, status: int = 0):
+        super().__init__(msg)
+        self.status = status
+
+
+class Fp16RangeError(ChimeraLMNativeError):
+    """A batch left the range of the fp16 tensor-core convolution; its logits are invalid (rerun with tc_conv off)."""
 
 
 # name -> (restype, argtypes); mirrors include/chimeralm_b200.h one to one
@@ -38,11 +45,15 @@ _SIGNATURES = {
     "clm_load_tensor": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int, C.POINTER(C.c_int64), C.c_int]),
     "clm_finalize": (C.c_int, [C.c_void_p]),
     "clm_reserve": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "clm_reserve_tokens": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_longlong]),
     "clm_encode_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                    C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "clm_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "clm_predict_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                    C.c_int, C.c_void_p, C.c_void_p]),
+    "clm_forward_seq": (C.c_longlong, [C.c_void_p]),
+    "clm_forward_status": (C.c_int, [C.c_void_p, C.c_longlong]),
+    "clm_tc_fallback_count": (C.c_longlong, [C.c_void_p]),
     "clm_launch_count": (C.c_longlong, [C.c_void_p]),
     "clm_profile_enable": (C.c_int, [C.c_void_p, C.c_int]),
     "clm_profile_reset": (C.c_int, [C.c_void_p]),
@@ -63,6 +74,8 @@ _SIGNATURES = {
                                C.c_void_p]),
     "clm_longconv_tc": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                   C.c_void_p]),
+    "clm_longconv_tc_auto": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                       C.c_void_p]),
     "clm_attention_weights": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "clm_longconv_variant": (C.c_int, [C.c_void_p, C.c_int]),
     "clm_longconv_tc_trace": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
@@ -105,4 +118,7 @@ def load() -> C.CDLL:
 def check(ctx, rc: int, what: str) -> None:
     if rc < 0:
         msg = load().clm_last_error(ctx)
-        raise ChimeraLMNativeError(f"{what} failed (status {rc}): {msg.decode() if msg else '?'}")
+        text = f"{what} failed (status {rc}): {msg.decode() if msg else '?'}"
+        if rc == CLM_ERR_TOKEN_RANGE:
+            raise IndexError(text)   # what the reference's nn.Embedding raises for an id outside the table
+        raise (Fp16RangeError if rc == CLM_ERR_FP16_RANGE else ChimeraLMNativeError)(text, rc)

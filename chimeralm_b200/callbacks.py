@@ -54,12 +54,8 @@ class PredictionWriter:
             if pred_tensor is None or pred_tensor.numel() == 0:
                 logger.warning(f"Empty prediction tensor for batch {batch_idx}")
                 return
-            # labels = argmax(dim=1), no softmax (reference :107).  When predict_step already
-            # produced device labels (same rule, ties -> 0) they ride along as a third element.
-            if isinstance(prediction, (list, tuple)) and len(prediction) > 2 and prediction[2] is not None:
-                predictions_cpu = prediction[2].to(torch.int64).cpu()
-            else:
-                predictions_cpu = pred_tensor.argmax(dim=1).cpu()
+            # labels = argmax(dim=1) of the logits, no softmax (reference :107)
+            predictions_cpu = pred_tensor.argmax(dim=1).cpu()
             batch_ids = batch["id"]
             if len(predictions_cpu) != len(batch_ids):
                 logger.error(f"Size mismatch: predictions={len(predictions_cpu)}, batch_ids={len(batch_ids)} for batch {batch_idx}")

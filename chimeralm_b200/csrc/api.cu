@@ -16,9 +16,11 @@
 #include "../../include/chimeralm_b200.h"
 #include "block_in.cuh"
 #include "block_mlp.cuh"
+#ifdef CLM_EXPERIMENTS   // recorded-slower variants of the block tail and the first long-convolution kernel: not in the product build
 #include "block_mlp2.cuh"
 #include "block_mlp16.cuh"
 #include "block_mlp_pp.cuh"
+#endif
 #include "gemm_tcgen05.cuh"
 #include "kernels.cuh"
 #include "longconv.cuh"
@@ -55,7 +57,13 @@ struct LayerW {
   float* k = nullptr;                               // [D][Lk]
   float2* gspec[LONGCONV_MAX_LOGN + 1] = {nullptr};  // per LOGN: [n_seg][D][N]
   float2* gspecT[LONGCONV_MAX_LOGN + 1] = {nullptr}; // per LOGN: [D][16][N/16], bias folded (longconv_fast)
-  __half2* gtc = nullptr;                            // [D][16384] fp16 spectrum, lane-interleaved (longconv_tc)
+  __half2* gtc = nullptr;                            // [n_seg][D][16384] fp16 spectrum, lane-interleaved (longconv_tc)
+  // longconv_tc dynamic-range factors (powers of two, see LongConvTcParams): table exponents, and two sets of
+  // output/input factors - `cal` for the forward (input scale from the calibration draw), `unit` for a = 1 (raw fp16 entry)
+  int* gexp = nullptr;                               // [n_seg][D]
+  float *vx_scale = nullptr, *tc_osc = nullptr, *tc_inva = nullptr, *tc_rel = nullptr;
+  float *unit_scale = nullptr, *unit_osc = nullptr, *unit_inva = nullptr;
+  unsigned int* vx_amax = nullptr;                   // [D] float bits, calibration forward
 };
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -90,6 +98,8 @@ struct clm_ctx {
   HeadParams head{};
   // workspaces
   int max_B = 0, max_T = 0, Tp_max = 0;
+  long long max_tokens = 0;      // token budget of the workspaces (<= max_B * max_T)
+  size_t ct_elems = 0;           // elements of each channel-major buffer (VX, X0, Y)
   int last_B = 0, last_T = 0;   // shape of the last complete forward (clm_attention_weights)
   float* R = nullptr;
   __nv_bfloat16 *XN = nullptr, *U = nullptr, *VX = nullptr, *X0 = nullptr, *Y = nullptr, *YT = nullptr;
@@ -97,7 +107,16 @@ struct clm_ctx {
   float* hbuf[4] = {nullptr, nullptr, nullptr, nullptr};   // head activations [max_B, 512]
   float2* scratch = nullptr;
   size_t scratch_bytes = 0;
+  // Status word of the forward in flight: bit 0 = a token id outside [0, vocab_rows), bit 1 = the fp16 tensor-core
+  // convolution produced a non-finite value.  The LAST kernel of every forward publishes (seq << 8 | bits) into the
+  // mapped host ring h_status[seq & 7] and clears the word, so the host can read a finished forward's status without
+  // another copy or synchronisation (clm_forward_status).
   int* d_err = nullptr;
+  int* h_status = nullptr;       // pinned + mapped, 8 words
+  int* d_status_map = nullptr;   // device alias of h_status
+  long long fwd_seq = 0;
+  long long tc_fallbacks = 0;    // batches clm_predict_host redid with the fp32 convolution
+  bool calibrating = false;      // clm_finalize's calibration forward: record max |v*x1| per layer and channel
   int n_split = 1;
   // e2e staging
   cudaStream_t own_stream = nullptr;
@@ -210,11 +229,20 @@ int dev_alloc(clm_ctx* c, T** p, size_t count) {
 
 void dev_free(clm_ctx* c, void* p) {
   if (!p) return;
-  for (auto& q : c->owned)
-    if (q == p) {
-      cudaFree(q);
-      q = nullptr;
+  for (size_t i = 0; i < c->owned.size(); ++i)
+    if (c->owned[i] == p) {
+      cudaFree(p);
+      c->owned[i] = c->owned.back();
+      c->owned.pop_back();
+      return;
     }
+}
+
+// frees *p and nulls it, so that a failed re-allocation can never leave a dangling workspace pointer behind
+template <typename T>
+void dev_release(clm_ctx* c, T** p) {
+  dev_free(c, *p);
+  *p = nullptr;
 }
 
 // dst[(((n/rt)*(K/64) + k/64)*rt + n%rt)*64 + k%64] = bf16(src[n][k])
@@ -362,6 +390,7 @@ int launch_block_in(clm_ctx* c, int layer, const __nv_bfloat16* xn, int B, int T
   BlockInParams p{};
   p.b_in = L.in_bf; p.cw = L.sc_w; p.cb = L.sc_b;
   p.B = B; p.T = T; p.trace = trace; p.vx_f16 = vx_f16 ? 1 : 0;
+  p.vx_scale = vx_f16 ? L.vx_scale : nullptr;   // fp16 rows carry a[ch] * v*x1 (undone by the conv's output scale)
   p.tiles_per_seq = (T + bi::BT - 1) / bi::BT;
   p.num_tiles = B * p.tiles_per_seq;
   const int grid = std::min(p.num_tiles, c->num_sms);
@@ -402,6 +431,7 @@ int launch_block_mlp(clm_ctx* c, int layer, const __nv_bfloat16* y, float* res, 
     p.write_xn = 1;
     if ((rc = make_tmap_xn(c, &tmXN, xn_out, B > 0 ? B : 1, B > 0 ? T : M, 128))) return rc;
   }
+#ifdef CLM_EXPERIMENTS
   if (c->mlp_2cta && !trace) {
     if (int rc_attr = ensure_smem_attr(c, (const void*)(block_mlp2_kernel), (int)(bm2::SMEM_TOTAL2))) return rc_attr;
     const int n_pair_tiles = (p.num_tiles + 1) / 2;
@@ -410,7 +440,9 @@ int launch_block_mlp(clm_ctx* c, int layer, const __nv_bfloat16* y, float* res, 
     CLM_LAUNCH_CHECK(c, "block_mlp2");
     return 0;
   }
+#endif
   const int grid = std::min(p.num_tiles, c->mlp_grid > 0 ? std::min(c->mlp_grid, c->num_sms) : c->num_sms);
+#ifdef CLM_EXPERIMENTS
   if (c->mlp_pp) {
     if (int rc_attr = ensure_smem_attr(c, (const void*)(block_mlp_pp_kernel), (int)(bm::SMEM_TOTAL))) return rc_attr;
     block_mlp_pp_kernel<<<grid, bm::THREADS, bm::SMEM_TOTAL, st>>>(tmY, L.tm_out_t, L.tm_fc1_64, L.tm_fc2_t, tmXN, p);
@@ -423,6 +455,7 @@ int launch_block_mlp(clm_ctx* c, int layer, const __nv_bfloat16* y, float* res, 
     CLM_LAUNCH_CHECK(c, "block_mlp16");
     return 0;
   }
+#endif
 #define CLM_MLP_LAUNCH(E, LAG)                                                                                             \
   {                                                                                                                        \
     if (int rc_attr = ensure_smem_attr(c, (const void*)(block_mlp_kernel<E, LAG>), (int)(bm::SMEM_TOTAL))) return rc_attr;  \
@@ -460,6 +493,7 @@ int n_segments(const clm_ctx* c, int logn) {
   return (c->cfg.max_seq_len + C - 1) / C;
 }
 
+#ifdef CLM_EXPERIMENTS
 template <int LOGN>
 int spectrum_t(clm_ctx* c, LayerW& L) {
   using Cfg = ConvCfg<LOGN>;
@@ -472,6 +506,8 @@ int spectrum_t(clm_ctx* c, LayerW& L) {
   CLM_LAUNCH_CHECK(c, "filter_spectrum");
   return 0;
 }
+
+#endif
 
 template <int LOGN>
 int spectrum_fast_t(clm_ctx* c, LayerW& L) {
@@ -503,6 +539,7 @@ int conv_fast_t(clm_ctx* c, const LongConvFastParams& p, int grid, cudaStream_t 
   }
 }
 
+#ifdef CLM_EXPERIMENTS
 template <int LOGN>
 int conv_t(clm_ctx* c, const LongConvParams& p, int grid, cudaStream_t st) {
   using Cfg = ConvCfg<LOGN>;
@@ -512,6 +549,8 @@ int conv_t(clm_ctx* c, const LongConvParams& p, int grid, cudaStream_t st) {
   CLM_LAUNCH_CHECK(c, "longconv");
   return 0;
 }
+
+#endif
 
 size_t conv_scratch_bytes(const clm_ctx* c, int T) {
   ConvPlan pl = plan_conv(T);
@@ -524,7 +563,13 @@ int launch_longconv(clm_ctx* c, int layer, const __nv_bfloat16* vx, const __nv_b
   if (T > c->cfg.max_seq_len) return fail(c, CLM_ERR_INVALID, "longconv: T=%d exceeds max_seq_len=%d", T, c->cfg.max_seq_len);
   const ConvPlan pl = plan_conv(T);
   LayerW& L = c->layers[layer];
-  if (c->fast_conv && L.gspecT[pl.logn] != nullptr) {
+#ifdef CLM_EXPERIMENTS
+  const bool use_fast = c->fast_conv && L.gspecT[pl.logn] != nullptr;
+#else
+  const bool use_fast = true;
+  if (L.gspecT[pl.logn] == nullptr) return fail(c, CLM_ERR_STATE, "longconv: no spectrum table for logN=%d", pl.logn);
+#endif
+  if (use_fast) {
     LongConvFastParams f{};
     f.vx = vx; f.x0 = x0; f.out = out; f.gT = L.gspecT[pl.logn]; f.k = L.k; f.dbias = L.fbias; f.Lk = c->Lk;
     f.B = B; f.D = c->cfg.d_model; f.T = T; f.Tp = Tp;
@@ -547,6 +592,7 @@ int launch_longconv(clm_ctx* c, int layer, const __nv_bfloat16* vx, const __nv_b
       case 14: return conv_fast_t<14>(c, f, grid, st);
     }
   }
+#ifdef CLM_EXPERIMENTS
   LongConvParams p{};
   p.vx = vx; p.x0 = x0; p.out = out;
   p.gspec = L.gspec[pl.logn];
@@ -570,6 +616,7 @@ int launch_longconv(clm_ctx* c, int layer, const __nv_bfloat16* vx, const __nv_b
     case 13: return conv_t<13>(c, p, grid, st);
     case 14: return conv_t<14>(c, p, grid, st);
   }
+#endif
   return fail(c, CLM_ERR_INVALID, "longconv: no plan for T=%d", T);
 }
 
@@ -590,8 +637,10 @@ bool tc_conv_applies(const clm_ctx* c, int T) {
 }
 
 // vx is fp16 here (block_in writes it that way when the tensor-core conv follows)
+// vx holds a[ch] * v*x1 with a = the layer's calibrated input scale, or plain values when unit_scale is set
 int launch_longconv_tc(clm_ctx* c, int layer, const __half* vx, const __nv_bfloat16* x0, __nv_bfloat16* out, int B, int T,
-                       int Tp, cudaStream_t st, long long* trace = nullptr) {
+                       int Tp, cudaStream_t st, long long* trace = nullptr, bool unit_scale = false,
+                       const float* osc_override = nullptr, const float* inva_override = nullptr) {
   if (!tc_conv_applies(c, T)) return fail(c, CLM_ERR_INVALID, "longconv_tc: no tensor-core plan for T=%d", T);
   const TcPlan pl = tc_plan(T);
   const bool whole_rows = T >= tc::C && pl.nc == 1;   // every 128-token row the kernel touches lies inside [0, Tp)
@@ -639,6 +688,9 @@ int launch_longconv_tc(clm_ctx* c, int layer, const __half* vx, const __nv_bfloa
   p.B = B; p.D = D; p.Tp = Tp; p.n_pairs = (B + 1) / 2; p.n_items = D * p.n_pairs; p.trace = trace;
   p.n_chunks = pl.nc; p.nt = pl.nt; p.scratch = c->tc_scratch; p.scratch_per_cta = (long long)tc_scratch_per_cta(pl.nc);
   p.g_seg_stride = (long long)D * (tc::N / 4);
+  p.osc = osc_override ? osc_override : (unit_scale ? L.unit_osc : L.tc_osc);
+  p.inva = inva_override ? inva_override : (unit_scale ? L.unit_inva : L.tc_inva);
+  p.rel = L.tc_rel; p.err = (unit_scale || osc_override) ? c->d_err + 1 : c->d_err;
   const int grid = std::min(p.n_items, c->num_sms);
   if (pl.nc > 1) longconv_tc_kernel<true><<<grid, tc::THREADS, tc::SMEM_TOTAL, st>>>(tm, tmo, tmg, p);
   else longconv_tc_kernel<false><<<grid, tc::THREADS, tc::SMEM_TOTAL, st>>>(tm, tmo, tmg, p);
@@ -736,9 +788,12 @@ int clm_create(const clm_config* cfg, int device, clm_ctx** out) {
   memset(lut, 6, sizeof lut);  // [UNK]
   lut['A'] = 7; lut['C'] = 8; lut['G'] = 9; lut['T'] = 10; lut['N'] = 11;
   CLM_CUDA(c, cudaMemcpyToSymbol(c_base_lut, lut, sizeof lut));
-  int rc = dev_alloc(c, &c->d_err, 1);
+  int rc = dev_alloc(c, &c->d_err, 2);   // [0] the forward's status word, [1] the unit-level entry points' own
   if (rc) return rc;
-  CLM_CUDA(c, cudaMemset(c->d_err, 0, sizeof(int)));
+  CLM_CUDA(c, cudaMemset(c->d_err, 0, 2 * sizeof(int)));
+  CLM_CUDA(c, cudaHostAlloc(reinterpret_cast<void**>(&c->h_status), 8 * sizeof(int), cudaHostAllocMapped | cudaHostAllocPortable));
+  memset(c->h_status, 0xff, 8 * sizeof(int));
+  CLM_CUDA(c, cudaHostGetDevicePointer(reinterpret_cast<void**>(&c->d_status_map), c->h_status, 0));
   c->layers.resize(cfg->n_layer);
   return 0;
 }
@@ -752,6 +807,7 @@ void clm_destroy(clm_ctx* c) {
     if (p) cudaFree(p);
   for (cudaEvent_t e : c->prof_pool) cudaEventDestroy(e);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
+  if (c->h_status) cudaFreeHost(c->h_status);
   delete c;
 }
 
@@ -773,6 +829,38 @@ int clm_load_tensor(clm_ctx* c, const char* name, const void* data, int dtype, c
   if (rc) return rc;
   CLM_CUDA(c, cudaMemcpy(t.d, data, (size_t)t.numel * sizeof(float), cudaMemcpyHostToDevice));
   c->w[n] = t;
+  return 0;
+}
+
+// Input scale of the tensor-core convolution, per layer and channel: one small forward (fp32 convolution) over a fixed
+// synthetic draw - a read of random bases and a half-[PAD] read, the two regimes real batches consist of - records
+// max |v * x1|, and tc::scales_kernel turns it into the power-of-two factors block_in / longconv_tc apply.  LayerNorm
+// sits in front of in_proj, so these magnitudes are set by the weights, not by the read; what the draw cannot know is
+// covered by the headroom (tc::scales_kernel) and, beyond that, by the non-finite check + fp32 rerun.
+static int calibrate_tc_scales(clm_ctx* c) {
+  const int B = 2, T = std::min(1024, c->cfg.max_seq_len), D = c->cfg.d_model;
+  int rc = clm_reserve(c, B, T);
+  if (rc) return rc;
+  std::vector<uint8_t> ids((size_t)B * T);
+  uint32_t x = 20251018u;
+  for (int b = 0; b < B; ++b)
+    for (int t = 0; t < T; ++t) {
+      x = x * 1664525u + 1013904223u;
+      uint8_t id = (uint8_t)(7 + ((x >> 24) & 3));
+      if (b == 1 && t < T / 2) id = 4;   // [PAD] prefix of a left-padded batch
+      if (t == T - 1) id = 1;            // [SEP]
+      ids[(size_t)b * T + t] = id;
+    }
+  CLM_CUDA(c, cudaMemcpy(c->st_ids, ids.data(), ids.size(), cudaMemcpyHostToDevice));
+  c->calibrating = true;
+  rc = clm_forward(c, c->st_ids, CLM_U8, B, T, c->st_logits, c->st_labels, c->own_stream);
+  c->calibrating = false;
+  if (rc) return rc;
+  for (auto& L : c->layers) {
+    tc::scales_kernel<<<(D + 255) / 256, 256, 0, c->own_stream>>>(L.gexp, L.vx_amax, L.vx_scale, L.tc_osc, L.tc_inva, L.tc_rel, D, c->tc_nseg, 0);
+    CLM_LAUNCH_CHECK(c, "tc_scales");
+  }
+  CLM_CUDA(c, cudaStreamSynchronize(c->own_stream));
   return 0;
 }
 
@@ -840,10 +928,12 @@ int clm_finalize(clm_ctx* c) {
       if ((rc = retile(c, out_w, D, D, 256, &L.out_wt, &L.tm_out_t))) return rc;
       if ((rc = retile(c, w1f, g.d_inner, D, 128, &L.fc1_wt, &L.tm_fc1_t))) return rc;
       if ((rc = retile(c, fc2_w, D, g.d_inner, 256, &L.fc2_wt, &L.tm_fc2_t))) return rc;
+#ifdef CLM_EXPERIMENTS
       if ((rc = retile(c, w1f, g.d_inner, D, 64, &L.fc1_w64, &L.tm_fc1_64))) return rc;
       if ((rc = make_tmap_retiled(c, &L.tm_out_h, L.out_wt, (long long)D * D / 64, 128))) return rc;
       if ((rc = make_tmap_retiled(c, &L.tm_fc1_h, L.fc1_wt, (long long)g.d_inner * D / 64, 64))) return rc;
       if ((rc = make_tmap_retiled(c, &L.tm_fc2_h, L.fc2_wt, (long long)g.d_inner * D / 64, 128))) return rc;
+#endif
       if ((int)c->h_mlp.size() <= l) c->h_mlp.resize(l + 1);
       bm::LayerConsts& hc = c->h_mlp[l];
       CLM_CUDA(c, cudaMemcpy(hc.b_out, L.out_b, sizeof hc.b_out, cudaMemcpyDeviceToHost));
@@ -872,6 +962,7 @@ int clm_finalize(clm_ctx* c) {
     fp.k_out = L.k;
     filter_gen_kernel<<<Lmax, 256>>>(fp);
     CLM_LAUNCH_CHECK(c, "filter_gen");
+#ifdef CLM_EXPERIMENTS
     if ((rc = spectrum_t<8>(c, L))) return rc;
     if ((rc = spectrum_t<9>(c, L))) return rc;
     if ((rc = spectrum_t<10>(c, L))) return rc;
@@ -879,6 +970,7 @@ int clm_finalize(clm_ctx* c) {
     if ((rc = spectrum_t<12>(c, L))) return rc;
     if ((rc = spectrum_t<13>(c, L))) return rc;
     if ((rc = spectrum_t<14>(c, L))) return rc;
+#endif
     if ((rc = spectrum_fast_t<8>(c, L))) return rc;
     if ((rc = spectrum_fast_t<12>(c, L))) return rc;
     if ((rc = spectrum_fast_t<9>(c, L))) return rc;
@@ -889,9 +981,20 @@ int clm_finalize(clm_ctx* c) {
     if (c->cfg.max_seq_len >= tc::C) {
       c->tc_nseg = (c->cfg.max_seq_len + tc::C - 1) / tc::C;   // one spectrum table per 8192-tap filter segment
       if ((rc = dev_alloc(c, &L.gtc, (size_t)c->tc_nseg * D * tc::N))) return rc;
+      if ((rc = dev_alloc(c, &L.gexp, (size_t)c->tc_nseg * D))) return rc;
       CLM_CUDA(c, cudaFuncSetAttribute(tc::spectrum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::N * (int)sizeof(float2)));
-      tc::spectrum_kernel<<<dim3(D, c->tc_nseg), 256, tc::N * sizeof(float2)>>>(L.k, c->Lk, c->cfg.max_seq_len, L.fbias, L.gtc);
+      tc::spectrum_kernel<<<dim3(D, c->tc_nseg), 256, tc::N * sizeof(float2)>>>(L.k, c->Lk, c->cfg.max_seq_len, L.fbias, L.gtc, L.gexp);
       CLM_LAUNCH_CHECK(c, "tc_spectrum");
+      float** arrs[] = {&L.vx_scale, &L.tc_osc, &L.tc_inva, &L.unit_scale, &L.unit_osc, &L.unit_inva};
+      for (float** a : arrs)
+        if ((rc = dev_alloc(c, a, (size_t)D))) return rc;
+      if ((rc = dev_alloc(c, &L.tc_rel, (size_t)c->tc_nseg * D))) return rc;
+      if ((rc = dev_alloc(c, &L.vx_amax, (size_t)D))) return rc;
+      CLM_CUDA(c, cudaMemset(L.vx_amax, 0, D * sizeof(unsigned int)));
+      // until the calibration forward at the end of clm_finalize has run, both sets are the unit-input-scale ones
+      tc::scales_kernel<<<(D + 255) / 256, 256>>>(L.gexp, nullptr, L.unit_scale, L.unit_osc, L.unit_inva, L.tc_rel, D, c->tc_nseg, 0);
+      tc::scales_kernel<<<(D + 255) / 256, 256>>>(L.gexp, nullptr, L.vx_scale, L.tc_osc, L.tc_inva, L.tc_rel, D, c->tc_nseg, 0);
+      CLM_LAUNCH_CHECK(c, "tc_scales");
     }
   }
   if ((rc = dev_alloc(c, &c->tc_S, (size_t)tc::S_BYTES / 2))) return rc;
@@ -940,21 +1043,40 @@ int clm_finalize(clm_ctx* c) {
 #undef NEED
   CLM_CUDA(c, cudaDeviceSynchronize());
   c->finalized = true;
+  if (c->tc_nseg > 0 && (rc = calibrate_tc_scales(c)) != 0) {
+    c->finalized = false;
+    return rc;
+  }
   return 0;
 }
 
 int clm_reserve(clm_ctx* c, int max_B, int max_T) {
-  if (!c || max_B <= 0 || max_T <= 0) return fail(c, CLM_ERR_INVALID, "clm_reserve: bad sizes");
+  return clm_reserve_tokens(c, max_B, max_T, (long long)max_B * (long long)max_T);
+}
+
+int clm_reserve_tokens(clm_ctx* c, int max_B, int max_T, long long max_tokens) {
+  if (!c || max_B <= 0 || max_T <= 0 || max_tokens < max_T || max_tokens > (long long)max_B * max_T || max_tokens > 0x7fffffffLL)
+    return fail(c, CLM_ERR_INVALID, "clm_reserve: bad sizes");
   if (max_T > c->cfg.max_seq_len) return fail(c, CLM_ERR_INVALID, "clm_reserve: max_T=%d exceeds max_seq_len=%d", max_T, c->cfg.max_seq_len);
   CLM_CUDA(c, cudaSetDevice(c->device));
   CLM_CUDA(c, cudaDeviceSynchronize());
-  void* olds[] = {c->R, c->XN, c->U, c->VX, c->X0, c->Y, c->YT, c->score, c->part, c->pooled, c->scratch,
-                  c->st_offsets, c->st_ids, c->st_logits, c->st_labels};
-  for (void* p : olds) dev_free(c, p);
+  // Release everything and forget the old limits FIRST: if an allocation below fails (a B x 32 769 batch that does not
+  // fit), the context is left with no workspaces and max_B = max_T = 0, so every later forward is refused until a
+  // smaller clm_reserve succeeds - never a launch on freed memory.
+  c->max_B = c->max_T = c->Tp_max = 0;
+  c->max_tokens = 0; c->ct_elems = 0;
+  c->scratch_bytes = 0; c->tc_scratch_floats = 0; c->st_bases_cap = 0;
+  dev_release(c, &c->R); dev_release(c, &c->XN); dev_release(c, &c->U); dev_release(c, &c->VX); dev_release(c, &c->X0);
+  dev_release(c, &c->Y); dev_release(c, &c->YT); dev_release(c, &c->score); dev_release(c, &c->part);
+  dev_release(c, &c->pooled); dev_release(c, &c->scratch); dev_release(c, &c->tc_scratch); dev_release(c, &c->st_offsets);
+  dev_release(c, &c->st_ids); dev_release(c, &c->st_logits); dev_release(c, &c->st_labels); dev_release(c, &c->st_bases);
+  for (int i = 0; i < 4; ++i) dev_release(c, &c->hbuf[i]);
   const int D = c->cfg.d_model;
-  const size_t M = (size_t)max_B * max_T;
+  // token-proportional buffers are sized by the token budget, per-read ones by max_B: a context that serves length
+  // buckets (256 reads of 1 kb ... 8 reads of 32 kb, <= 262 k tokens each) does not pay for 256 x 32 769 tokens
+  const size_t M = (size_t)max_tokens;
   const int Tp = round_up(max_T, 128);
-  const size_t CT = (size_t)max_B * D * Tp;
+  const size_t CT = (size_t)D * std::min((size_t)max_B * Tp, M + (size_t)127 * max_B);   // sum over reads of round_up(T, 128)
   int rc;
   if ((rc = dev_alloc(c, &c->R, (M + 160) * D))) return rc;  // R32 layout: whole 32-row groups + tile overhang
   if ((rc = dev_alloc(c, &c->XN, M * D))) return rc;
@@ -965,34 +1087,38 @@ int clm_reserve(clm_ctx* c, int max_B, int max_T) {
   if ((rc = dev_alloc(c, &c->YT, M * D))) return rc;
   if ((rc = dev_alloc(c, &c->score, M))) return rc;
   c->n_split = std::max(1, std::min(64, (2 * c->num_sms + max_B - 1) / max_B));
-  if ((rc = dev_alloc(c, &c->part, (size_t)max_B * std::max(c->n_split, (max_T + 127) / 128) * (2 + D)))) return rc;
-  if ((rc = dev_alloc(c, &c->pooled, (size_t)max_B * D))) return rc;
-  for (int i = 0; i < 4; ++i) {
-    dev_free(c, c->hbuf[i]);
-    if ((rc = dev_alloc(c, &c->hbuf[i], (size_t)max_B * c->cfg.head_hidden))) return rc;
+  {   // pooling partials: per read max(n_split, ceil(T / 128)) slices of (2 + D) floats
+    const size_t slices = std::max((size_t)max_B * c->n_split, std::min((size_t)max_B * ((max_T + 127) / 128), M / 128 + max_B));
+    if ((rc = dev_alloc(c, &c->part, slices * (2 + D)))) return rc;
   }
-  c->scratch_bytes = conv_scratch_bytes(c, max_T);
-  c->scratch = nullptr;
-  if (c->scratch_bytes) {
+  if ((rc = dev_alloc(c, &c->pooled, (size_t)max_B * D))) return rc;
+  for (int i = 0; i < 4; ++i)
+    if ((rc = dev_alloc(c, &c->hbuf[i], (size_t)max_B * c->cfg.head_hidden))) return rc;
+  size_t scratch_bytes = conv_scratch_bytes(c, max_T);
+  if (scratch_bytes) {
     // any T <= max_T that takes the chunked path needs at most this much
     const int C = 1 << (LONGCONV_MAX_LOGN - 1);
     const size_t worst = (size_t)c->num_sms * ((max_T + C - 1) / C) * ((size_t)1 << LONGCONV_MAX_LOGN) * sizeof(float2);
-    c->scratch_bytes = std::max(c->scratch_bytes, worst);
-    if ((rc = dev_alloc(c, reinterpret_cast<uint8_t**>(&c->scratch), c->scratch_bytes))) return rc;
+    scratch_bytes = std::max(scratch_bytes, worst);
+    if ((rc = dev_alloc(c, reinterpret_cast<uint8_t**>(&c->scratch), scratch_bytes))) return rc;
+    c->scratch_bytes = scratch_bytes;
   }
   {
     const size_t need = tc_scratch_per_cta(tc_plan(max_T).nc) * c->num_sms;
-    if (need > c->tc_scratch_floats) {
-      dev_free(c, c->tc_scratch);
+    if (need) {
       if ((rc = dev_alloc(c, &c->tc_scratch, need))) return rc;
       c->tc_scratch_floats = need;
     }
   }
+  // staging of clm_predict_host (sized here: nothing is allocated on the forward path)
   if ((rc = dev_alloc(c, &c->st_offsets, (size_t)max_B + 1))) return rc;
   if ((rc = dev_alloc(c, &c->st_ids, M))) return rc;
   if ((rc = dev_alloc(c, &c->st_logits, (size_t)max_B * 2))) return rc;
   if ((rc = dev_alloc(c, &c->st_labels, (size_t)max_B))) return rc;
-  c->max_B = max_B; c->max_T = max_T; c->Tp_max = Tp;
+  if ((rc = dev_alloc(c, &c->st_bases, M))) return rc;   // a read contributes at most one base per token
+  c->st_bases_cap = M;
+  c->max_B = max_B; c->max_T = max_T; c->Tp_max = Tp;   // only now: every workspace exists
+  c->max_tokens = max_tokens; c->ct_elems = CT;
   return 0;
 }
 
@@ -1021,8 +1147,8 @@ int clm_forward(clm_ctx* c, const void* d_ids, int ids_dtype, int B, int T, floa
   if (!c) return CLM_ERR_INVALID;
   if (!c->finalized) return fail(c, CLM_ERR_STATE, "clm_forward before clm_finalize");
   if (!d_ids || !d_logits || B <= 0 || T <= 0) return fail(c, CLM_ERR_INVALID, "clm_forward: bad argument");
-  if (B > c->max_B || T > c->max_T || (size_t)B * T > (size_t)c->max_B * c->max_T)
-    return fail(c, CLM_ERR_STATE, "clm_forward: batch %dx%d exceeds reserved %dx%d; call clm_reserve", B, T, c->max_B, c->max_T);
+  if (B > c->max_B || T > c->max_T || (long long)B * T > c->max_tokens)
+    return fail(c, CLM_ERR_STATE, "clm_forward: batch %dx%d exceeds reserved %dx%d (%lld tokens); call clm_reserve", B, T, c->max_B, c->max_T, c->max_tokens);
   cudaStream_t st = (cudaStream_t)stream;
   const clm_config& g = c->cfg;
   const int D = g.d_model;
@@ -1032,6 +1158,9 @@ int clm_forward(clm_ctx* c, const void* d_ids, int ids_dtype, int B, int T, floa
   const unsigned rows32e = (unsigned)((M + 31) / 32);   // embed_kernel: one CTA per 32-row block of the R32 layout
   const unsigned rows32 = (unsigned)((M + 31) / 32);
   int rc;
+  const long long seq = ++c->fwd_seq;
+  int* status_slot = c->d_status_map + (seq & 7);
+  const int status_tag = (int)((seq & 0x7fffff) << 8);
 #define STOP_AFTER(layer, stage) \
   if (c->dbg_layer == (layer) && c->dbg_stage == (stage)) return 0
 
@@ -1058,6 +1187,10 @@ int clm_forward(clm_ctx* c, const void* d_ids, int ids_dtype, int B, int T, floa
       ProfScope ps_(c, PC_BLOCK_IN, st);
       use_tc = tc_conv_applies(c, T);
       if ((rc = launch_block_in(c, l, c->XN, B, T, Tp, c->VX, c->X0, st, nullptr, use_tc))) return rc;
+      if (c->calibrating && !use_tc && L.vx_amax) {
+        tc::amax_cm_kernel<<<dim3(D, B), 256, 0, st>>>(c->VX, D, Tp, T, L.vx_amax);
+        CLM_LAUNCH_CHECK(c, "vx_amax");
+      }
     } else {
     { ProfScope ps_(c, PC_LN, st);
       layernorm_bf16_kernel<<<rows32, 256, 0, st>>>(c->R, L.ln1_g, L.ln1_b, c->XN, M, g.layer_norm_eps);
@@ -1172,13 +1305,16 @@ int clm_forward(clm_ctx* c, const void* d_ids, int ids_dtype, int B, int T, floa
       hf.wo = hp.wo; hf.bo = hp.bo;
       hf.pooled = c->pooled; hf.h0 = c->hbuf[0]; hf.h1 = c->hbuf[1]; hf.h2 = c->hbuf[2]; hf.h3 = c->hbuf[3];
       hf.logits = d_logits; hf.labels = d_labels; hf.counter = c->head_counter; hf.base = c->head_base; hf.B = B;
+      hf.err = c->d_err; hf.status_out = status_slot; hf.status_tag = status_tag;
       const int grid = H / 8;
-      c->head_base += 5u * (unsigned)grid;   // five grid barriers per launch; the counter is never reset
       void* args[] = {&hf};
       constexpr size_t head_smem = (size_t)HEAD_BT * 512 * sizeof(float);
       if (int rc_attr = ensure_smem_attr(c, (const void*)(head_fused_kernel), (int)((int)head_smem))) return rc_attr;
       CLM_CUDA(c, cudaLaunchCooperativeKernel((const void*)head_fused_kernel, dim3(grid), dim3(256), args, head_smem, st));
       CLM_LAUNCH_CHECK(c, "head_fused");
+      // five grid barriers per launch; the device counter is never reset.  Advanced only once the launch was accepted:
+      // a rejected launch must not move the host's idea of the counter ahead of the device's.
+      c->head_base += 5u * (unsigned)grid;
     } else {
     pool_merge_kernel<<<B, 256, 0, st>>>(c->part, n_split, c->pooled);
     CLM_LAUNCH_CHECK(c, "pool_merge");
@@ -1192,6 +1328,8 @@ int clm_forward(clm_ctx* c, const void* d_ids, int ids_dtype, int B, int T, floa
     CLM_LAUNCH_CHECK(c, "head_r1");
     head_layer_kernel<512, false, false, true><<<dim3(1, (B + 31) / 32), 256, 0, st>>>(hp.wo, hp.bo, c->hbuf[3], nullptr, d_logits, d_labels, B, 2);
     CLM_LAUNCH_CHECK(c, "head_out");
+    publish_status_kernel<<<1, 1, 0, st>>>(c->d_err, status_slot, status_tag);
+    CLM_LAUNCH_CHECK(c, "publish_status");
     }
   }
 #undef STOP_AFTER
@@ -1199,30 +1337,56 @@ int clm_forward(clm_ctx* c, const void* d_ids, int ids_dtype, int B, int T, floa
   return 0;
 }
 
+long long clm_forward_seq(const clm_ctx* c) { return c ? c->fwd_seq : 0; }
+
+int clm_forward_status(clm_ctx* c, long long seq) {
+  if (!c) return CLM_ERR_INVALID;
+  if (seq <= 0 || seq > c->fwd_seq || seq + 8 <= c->fwd_seq)
+    return fail(c, CLM_ERR_INVALID, "clm_forward_status: forward %lld is not one of the last 8 (latest is %lld)", seq, c->fwd_seq);
+  const int v = *reinterpret_cast<volatile int*>(c->h_status + (seq & 7));
+  if ((v >> 8) != (int)(seq & 0x7fffff))
+    return fail(c, CLM_ERR_STATE, "clm_forward_status: forward %lld has not completed; synchronise its stream first", seq);
+  if (v & 1) return fail(c, CLM_ERR_TOKEN_RANGE, "forward %lld: a token id lies outside [0, %d) (the reference's nn.Embedding raises IndexError)", seq, c->cfg.vocab_rows);
+  if (v & 2) return fail(c, CLM_ERR_FP16_RANGE, "forward %lld: the fp16 tensor-core long convolution produced a non-finite value; "
+                         "rerun the batch with clm_set_option(\"tc_conv\", 0) (clm_predict_host does so by itself)", seq);
+  return 0;
+}
+
 int clm_predict_host(clm_ctx* c, const uint8_t* h_bases, const int64_t* h_offsets, int B, int T_pad, int add_cls,
                      int add_sep, int pad_left, int max_bases, float* h_logits, uint8_t* h_labels) {
   if (!c || !h_bases || !h_offsets || !h_logits || B <= 0) return fail(c, CLM_ERR_INVALID, "clm_predict_host: bad argument");
-  if (B > c->max_B || T_pad > c->max_T) return fail(c, CLM_ERR_STATE, "clm_predict_host: batch %dx%d exceeds reserved %dx%d", B, T_pad, c->max_B, c->max_T);
+  if (B > c->max_B || T_pad > c->max_T || (long long)B * T_pad > c->max_tokens)
+    return fail(c, CLM_ERR_STATE, "clm_predict_host: batch %dx%d exceeds reserved %dx%d (%lld tokens)", B, T_pad, c->max_B, c->max_T, c->max_tokens);
   CLM_CUDA(c, cudaSetDevice(c->device));
   const size_t nbytes = (size_t)h_offsets[B];
-  if (nbytes > c->st_bases_cap) {
-    dev_free(c, c->st_bases);
-    const size_t cap = std::max(nbytes, (size_t)c->max_B * c->max_T);
-    int rc = dev_alloc(c, &c->st_bases, cap);
-    if (rc) return rc;
-    c->st_bases_cap = cap;
-  }
+  // the staging buffer was sized by clm_reserve (max_B * max_T bases); nothing is allocated here.  Bases beyond
+  // max_bases per read are never looked at by the encoder, but they still have to fit the copy.
+  if (nbytes > c->st_bases_cap)
+    return fail(c, CLM_ERR_STATE, "clm_predict_host: %zu bases exceed the staging buffer of %zu reserved by clm_reserve(%d, %d); "
+                "truncate the reads to max_bases on the host or reserve more", nbytes, c->st_bases_cap, c->max_B, c->max_T);
   cudaStream_t st = c->own_stream;
   CLM_CUDA(c, cudaMemcpyAsync(c->st_bases, h_bases, nbytes, cudaMemcpyHostToDevice, st));
   CLM_CUDA(c, cudaMemcpyAsync(c->st_offsets, h_offsets, (size_t)(B + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
   int rc = clm_encode_batch(c, c->st_bases, c->st_offsets, B, T_pad, add_cls, add_sep, pad_left, max_bases, c->st_ids, nullptr, st);
   if (rc) return rc;
-  rc = clm_forward(c, c->st_ids, CLM_U8, B, T_pad, c->st_logits, c->st_labels, st);
-  if (rc) return rc;
-  CLM_CUDA(c, cudaMemcpyAsync(h_logits, c->st_logits, (size_t)B * 2 * sizeof(float), cudaMemcpyDeviceToHost, st));
-  if (h_labels) CLM_CUDA(c, cudaMemcpyAsync(h_labels, c->st_labels, (size_t)B, cudaMemcpyDeviceToHost, st));
-  CLM_CUDA(c, cudaStreamSynchronize(st));
-  return 0;
+  struct Restore {   // the fallback below switches the tensor-core conv off for ONE batch only
+    clm_ctx* c; bool tc;
+    ~Restore() { c->tc_conv = tc; }
+  } restore{c, c->tc_conv};
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    rc = clm_forward(c, c->st_ids, CLM_U8, B, T_pad, c->st_logits, c->st_labels, st);
+    if (rc) return rc;
+    CLM_CUDA(c, cudaMemcpyAsync(h_logits, c->st_logits, (size_t)B * 2 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (h_labels) CLM_CUDA(c, cudaMemcpyAsync(h_labels, c->st_labels, (size_t)B, cudaMemcpyDeviceToHost, st));
+    CLM_CUDA(c, cudaStreamSynchronize(st));
+    if (c->dbg_layer >= 0) return 0;   // stopped early: no status was published
+    rc = clm_forward_status(c, c->fwd_seq);
+    if (rc != CLM_ERR_FP16_RANGE || attempt == 1 || !c->tc_conv) return rc;
+    // automatic switch: this batch left the fp16 range of the tensor-core convolution - redo it with the fp32 FFT kernel
+    c->tc_conv = false;
+    c->tc_fallbacks++;
+  }
+  return rc;
 }
 
 int clm_gemm(clm_ctx* c, const void* d_A, const void* d_W, const float* d_bias, int M, int N, int K, int epi,
@@ -1241,17 +1405,31 @@ int clm_set_option(clm_ctx* c, const char* name, int value) {
   const std::string n(name);
   if (n == "fused_mlp") c->fused_mlp = value != 0;
   else if (n == "fused_in") c->fused_in = value != 0;
+#ifdef CLM_EXPERIMENTS
   else if (n == "fast_conv") c->fast_conv = value != 0;
+  else if (n == "mlp_2cta") c->mlp_2cta = value != 0;
+  else if (n == "mlp_epi16") c->mlp_epi16 = value != 0;
+  else if (n == "mlp_pp") c->mlp_pp = value != 0;
+#else
+  else if (n == "fast_conv" || n == "mlp_2cta" || n == "mlp_epi16" || n == "mlp_pp")
+    return fail(c, CLM_ERR_INVALID, "clm_set_option: '%s' selects an experiment kernel that is not compiled in (build with -DCLM_EXPERIMENTS)", name);
+#endif
   else if (n == "tc_conv") c->tc_conv = value != 0;
   else if (n == "tc_chunked") c->tc_chunked = value != 0;
   else if (n == "fused_score_pool") c->fused_score_pool = value != 0;
   else if (n == "fused_head") c->fused_head = value != 0;
   else if (n == "mlp_stagger") c->mlp_stagger = value;
   else if (n == "y_channel_major") c->y_channel_major = value != 0;
-  else if (n == "mlp_2cta") c->mlp_2cta = value != 0;
-  else if (n == "mlp_epi16") c->mlp_epi16 = value != 0;
-  else if (n == "mlp_pp") c->mlp_pp = value != 0;
   else if (n == "mlp_grid") c->mlp_grid = value;
+  else if (n == "tc_scale_shift") {   // test hook: move the calibrated input scale of the tensor-core conv by 2^value
+    if (!c->finalized) return fail(c, CLM_ERR_STATE, "clm_set_option(tc_scale_shift) before clm_finalize");
+    CLM_CUDA(c, cudaDeviceSynchronize());
+    for (auto& L : c->layers)
+      if (L.gexp)
+        tc::scales_kernel<<<(c->cfg.d_model + 255) / 256, 256>>>(L.gexp, L.vx_amax, L.vx_scale, L.tc_osc, L.tc_inva, L.tc_rel,
+                                                                 c->cfg.d_model, c->tc_nseg, value);
+    CLM_CUDA(c, cudaDeviceSynchronize());
+  }
   else if (n == "mlp_fc2_lag") c->mlp_fc2_lag = value;
   else if (n == "mlp_early_res") c->mlp_early_res = value;
   else return fail(c, CLM_ERR_INVALID, "clm_set_option: unknown option '%s'", name);
@@ -1260,7 +1438,7 @@ int clm_set_option(clm_ctx* c, const char* name, int value) {
 
 // d_res (R32) is first normalised into the context's XN workspace (needs clm_reserve >= B x T)
 int normalize_for_block_in(clm_ctx* c, const float* d_res, int B, int T, cudaStream_t st) {
-  if ((size_t)B * T > (size_t)c->max_B * c->max_T) return fail(c, CLM_ERR_STATE, "clm_block_in: call clm_reserve(B, T) first");
+  if ((long long)B * T > c->max_tokens) return fail(c, CLM_ERR_STATE, "clm_block_in: call clm_reserve(B, T) first");
   const long long M = (long long)B * T;
   layernorm_bf16_kernel<<<(unsigned)((M + 31) / 32), 256, 0, st>>>(d_res, c->ones, c->zeros, c->XN, M, c->cfg.layer_norm_eps);
   CLM_LAUNCH_CHECK(c, "normalize");
@@ -1304,7 +1482,7 @@ int clm_block_mlp_cm_trace(clm_ctx* c, int layer, const void* d_y_cm, float* d_r
   if (!c || !c->finalized) return fail(c, CLM_ERR_STATE, "clm_block_mlp_cm_trace before clm_finalize");
   if (layer < 0 || layer >= c->cfg.n_layer || !d_y_cm || !d_res || B <= 0 || T <= 0 || Tp < T || Tp % 64 != 0)
     return fail(c, CLM_ERR_INVALID, "clm_block_mlp_cm_trace: bad argument");
-  if (write_xn && (size_t)B * T > (size_t)c->max_B * c->max_T) return fail(c, CLM_ERR_STATE, "clm_block_mlp_cm_trace: call clm_reserve(B, T) first");
+  if (write_xn && (long long)B * T > c->max_tokens) return fail(c, CLM_ERR_STATE, "clm_block_mlp_cm_trace: call clm_reserve(B, T) first");
   return launch_block_mlp(c, layer, (const __nv_bfloat16*)d_y_cm, d_res, B * T, (cudaStream_t)stream, d_trace, B, T, Tp,
                           write_xn ? c->XN : nullptr);
 }
@@ -1322,7 +1500,8 @@ int clm_longconv(clm_ctx* c, int layer, const void* d_vx, const void* d_x0, void
   const size_t needb = conv_scratch_bytes(c, T);
   if (needb > c->scratch_bytes) {
     CLM_CUDA(c, cudaDeviceSynchronize());
-    dev_free(c, c->scratch);
+    dev_release(c, &c->scratch);
+    c->scratch_bytes = 0;
     int rc = dev_alloc(c, reinterpret_cast<uint8_t**>(&c->scratch), needb);
     if (rc) return rc;
     c->scratch_bytes = needb;
@@ -1335,7 +1514,8 @@ int ensure_tc_scratch(clm_ctx* c, int T) {
   const size_t need = tc_scratch_per_cta(tc_plan(T).nc) * c->num_sms;
   if (need <= c->tc_scratch_floats) return 0;
   CLM_CUDA(c, cudaDeviceSynchronize());
-  dev_free(c, c->tc_scratch);
+  dev_release(c, &c->tc_scratch);
+  c->tc_scratch_floats = 0;
   int rc = dev_alloc(c, &c->tc_scratch, need);
   if (rc) return rc;
   c->tc_scratch_floats = need;
@@ -1349,7 +1529,7 @@ int clm_longconv_tc_trace(clm_ctx* c, int layer, const void* d_vx_f16, const voi
     return fail(c, CLM_ERR_INVALID, "clm_longconv_tc_trace: bad argument");
   if (int rc = ensure_tc_scratch(c, T)) return rc;
   return launch_longconv_tc(c, layer, (const __half*)d_vx_f16, (const __nv_bfloat16*)d_x0, (__nv_bfloat16*)d_out, B, T, Tp,
-                            (cudaStream_t)stream, d_trace);
+                            (cudaStream_t)stream, d_trace, /*unit_scale=*/true);
 }
 
 int clm_longconv_tc(clm_ctx* c, int layer, const void* d_vx_f16, const void* d_x0, void* d_out, int B, int T, int Tp,
@@ -1359,8 +1539,44 @@ int clm_longconv_tc(clm_ctx* c, int layer, const void* d_vx_f16, const void* d_x
     return fail(c, CLM_ERR_INVALID, "clm_longconv_tc: bad argument");
   if (int rc = ensure_tc_scratch(c, T)) return rc;
   return launch_longconv_tc(c, layer, (const __half*)d_vx_f16, (const __nv_bfloat16*)d_x0, (__nv_bfloat16*)d_out, B, T, Tp,
-                            (cudaStream_t)stream);
+                            (cudaStream_t)stream, nullptr, /*unit_scale=*/true);
 }
+
+int clm_longconv_tc_auto(clm_ctx* c, int layer, const void* d_vx_bf16, const void* d_x0, void* d_out, int B, int T, int Tp,
+                         void* stream) {
+  if (!c || !c->finalized) return fail(c, CLM_ERR_STATE, "clm_longconv_tc_auto before clm_finalize");
+  if (layer < 0 || layer >= c->cfg.n_layer || !d_vx_bf16 || !d_x0 || !d_out || B <= 0 || Tp < T || Tp % 64 != 0)
+    return fail(c, CLM_ERR_INVALID, "clm_longconv_tc_auto: bad argument");
+  if (int rc = ensure_tc_scratch(c, T)) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  LayerW& L = c->layers[layer];
+  const int D = c->cfg.d_model;
+  __half* vxh = nullptr;
+  unsigned int* amax = nullptr;
+  float* f = nullptr;   // scale | osc | inva | rel
+  int rc = dev_alloc(c, &vxh, (size_t)B * D * Tp);
+  if (!rc) rc = dev_alloc(c, &amax, (size_t)D);
+  if (!rc) rc = dev_alloc(c, &f, (size_t)D * (3 + c->tc_nseg));
+  if (!rc) {
+    cudaMemsetAsync(amax, 0, D * sizeof(unsigned int), st);
+    cudaMemsetAsync(c->d_err + 1, 0, sizeof(int), st);
+    tc::amax_cm_kernel<<<dim3(D, B), 256, 0, st>>>((const __nv_bfloat16*)d_vx_bf16, D, Tp, T, amax);
+    tc::scales_kernel<<<(D + 255) / 256, 256, 0, st>>>(L.gexp, amax, f, f + D, f + 2 * D, f + 3 * D, D, c->tc_nseg, 0);
+    tc::scale_to_f16_kernel<<<dim3(D, B), 256, 0, st>>>((const __nv_bfloat16*)d_vx_bf16, vxh, f, D, Tp, T);
+    rc = launch_longconv_tc(c, layer, vxh, (const __nv_bfloat16*)d_x0, (__nv_bfloat16*)d_out, B, T, Tp, st, nullptr, false, f + D, f + 2 * D);
+  }
+  int flags = 0;
+  if (!rc) {
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (e == cudaSuccess) e = cudaMemcpy(&flags, c->d_err + 1, sizeof(int), cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) rc = fail(c, CLM_ERR_CUDA, "clm_longconv_tc_auto: %s", cudaGetErrorString(e));
+  }
+  dev_free(c, vxh); dev_free(c, amax); dev_free(c, f);
+  if (!rc && (flags & 2)) return fail(c, CLM_ERR_FP16_RANGE, "clm_longconv_tc_auto: non-finite output (fp16 range exceeded)");
+  return rc;
+}
+
+long long clm_tc_fallback_count(const clm_ctx* c) { return c ? c->tc_fallbacks : 0; }
 
 int clm_longconv_variant(const clm_ctx* c, int T) {
   if (!c || !c->finalized || T <= 0) return -1;
@@ -1414,8 +1630,8 @@ int clm_profile_get(clm_ctx* c, int cat, double* total_ms, long long* launches) 
 
 int clm_debug_copy(clm_ctx* c, const char* what, void* d_dst, size_t max_bytes, void* stream) {
   if (!c || !what || !d_dst) return fail(c, CLM_ERR_INVALID, "clm_debug_copy: bad argument");
-  const size_t M = (size_t)c->max_B * c->max_T, D = c->cfg.d_model;
-  const size_t CT = (size_t)c->max_B * D * c->Tp_max;
+  const size_t M = (size_t)c->max_tokens, D = c->cfg.d_model;
+  const size_t CT = c->ct_elems;
   const void* src = nullptr;
   size_t bytes = 0;
   const std::string w(what);

@@ -43,6 +43,8 @@ struct BlockInParams {
   int B, T;
   int tiles_per_seq, num_tiles;
   int vx_f16;           // write v * x1 as fp16 instead of bf16 (operand of the tensor-core long convolution)
+  const float* vx_scale;  // [256] power-of-two factor a[ch] on v * x1 when vx_f16 (nullptr = 1): keeps the fp16 rows and every
+                          // fp16 intermediate of the tensor-core FFT in range for weights of any magnitude (longconv_tc.cuh)
   long long* trace;     // optional [2][64] clock64 stamps of CTA 0 (row 0 = MMA issuer, row 1 = epilogue warp 2)
 };
 
@@ -192,6 +194,10 @@ block_in_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
         c_w1[h][g] = __ldg(p.cw + ch * 3 + 1);
         c_w2[h][g] = __ldg(p.cw + ch * 3 + 2);
         c_cb[h][g] = __ldg(p.cb + ch);
+        if (g == 2 && p.vx_scale) {   // fold a[ch] into the v group's short-filter taps and bias: a * v exactly, no extra work
+          const float a = __ldg(p.vx_scale + h * 128 + r);
+          c_w0[h][g] *= a; c_w1[h][g] *= a; c_w2[h][g] *= a; c_cb[h][g] *= a;
+        }
       }
     uint32_t it = 0, pass = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {

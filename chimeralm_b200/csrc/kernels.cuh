@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(256) embed_kernel(const IdT* __restrict__ ids,
     const long long row = row0 + threadIdx.x;
     long long id = row < M ? (long long)ids[row] : 0;
     if (id < 0 || id >= nv) {
-      if (row < M) atomicExch(err, 1);
+      if (row < M) atomicOr(err, 1);
       id = 0;
     }
     s_id[threadIdx.x] = (int)id;
@@ -404,14 +404,32 @@ struct HeadFusedParams {
   unsigned int* counter;
   unsigned int base;  // counter value before this launch
   int B;
+  int* err;           // status word of the forward in flight (may be null)
+  int* status_out;    // mapped host slot that receives (status_tag | *err) when the forward is complete (may be null)
+  int status_tag;     // forward sequence number << 8
 };
+
+// Last thing a forward does: hand the status word to the host (mapped pinned memory) and clear it for the next forward.
+__device__ __forceinline__ void publish_status(int* err, int* status_out, int tag) {
+  if (!err) return;
+  const int v = atomicExch(err, 0);
+  if (status_out) {
+    *reinterpret_cast<volatile int*>(status_out) = tag | (v & 0xff);
+    __threadfence_system();
+  }
+}
+
+__global__ void publish_status_kernel(int* err, int* status_out, int tag) { publish_status(err, status_out, tag); }
 
 __device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int target) {
   __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence();
     atomicAdd(counter, 1u);
-    while ((int)(*reinterpret_cast<volatile unsigned int*>(counter) - target) < 0) {}
+    // bounded like the mbarrier waits: a host/device counter mismatch is a reported launch failure, never a hung GPU
+    unsigned int polls = 0;
+    while ((int)(*reinterpret_cast<volatile unsigned int*>(counter) - target) < 0)
+      if (++polls > (1u << 28)) __trap();
     __threadfence();
   }
   __syncthreads();
@@ -495,6 +513,7 @@ __global__ void __launch_bounds__(256) head_fused_kernel(HeadFusedParams p) {
     __syncthreads();
     if (p.labels && warp == 0)
       for (int b = lane; b < p.B; b += 32) p.labels[b] = (p.logits[b * 2 + 1] > p.logits[b * 2]) ? 1 : 0;   // ties -> 0
+    if (threadIdx.x == 0) publish_status(p.err, p.status_out, p.status_tag);
   }
 }
 

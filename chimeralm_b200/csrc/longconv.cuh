@@ -82,6 +82,7 @@ __global__ void __launch_bounds__(256) filter_gen_kernel(FilterGenParams p) {
   }
 }
 
+#ifdef CLM_EXPERIMENTS   // the first long-convolution kernel and its spectrum tables: cross-check only, not in the product build
 // ---------------------------------------------------------------------------------------------
 // Filter segment spectra: gspec[m][c][0..N) = FFT_N(g_m) / N in the forward transform's
 // digit-reversed order, for m in [0, n_seg).  Grid (D, n_seg).
@@ -110,6 +111,8 @@ __global__ void __launch_bounds__(ConvCfg<LOGN>::THREADS) filter_spectrum_kernel
 }
 
 // ---------------------------------------------------------------------------------------------
+#endif  // CLM_EXPERIMENTS
+
 struct LongConvParams {
   const __nv_bfloat16* vx;   // [B][D][Tp]
   const __nv_bfloat16* x0;   // [B][D][Tp]
@@ -151,6 +154,7 @@ __device__ __forceinline__ uint4 pack_bf16x8(const float (&f)[8]) {
   return make_uint4(w[0], w[1], w[2], w[3]);
 }
 
+#ifdef CLM_EXPERIMENTS
 template <int LOGN>
 __global__ void __launch_bounds__(ConvCfg<LOGN>::THREADS, 1) longconv_kernel(LongConvParams p) {
   using Cfg = ConvCfg<LOGN>;
@@ -290,5 +294,7 @@ __global__ void __launch_bounds__(ConvCfg<LOGN>::THREADS, 1) longconv_kernel(Lon
     }
   }
 }
+
+#endif  // CLM_EXPERIMENTS
 
 }  // namespace clm

@@ -57,6 +57,14 @@ struct LongConvTcParams {
   float* scratch;            // per CTA: (n_chunks - 1) parked spectra (16384 x fp16 (re, im) each) + carry (2 x 8192 float)
   long long scratch_per_cta; // floats
   long long g_seg_stride;    // uint4 between the spectrum tables of consecutive filter segments
+  // Dynamic-range handling (all factors are powers of two, so they are exact): the input rows hold a[ch] * v*x1, the
+  // spectrum table of segment j holds FFT(k_j) * 2^e[j][ch] (largest bin in [1/16, 1/8)); `osc` undoes both and the
+  // transform's N * S1, `rel[j]` = 2^(e[0] - e[j]) brings the later filter segments to segment 0's scale before the
+  // sum over segments, `inva` = 1 / a is for the tail tokens' direct products.
+  const float* osc;          // [D]
+  const float* inva;         // [D]
+  const float* rel;          // [n_seg][D]
+  int* err;                  // status word: bit 1 (value 2) is set when an output is not finite (fp16 range exceeded)
   long long* trace;          // optional [2][64] clock64 stamps of CTA 0: row 0 = MMA issuer, row 1 = epilogue warp 2
 };
 
@@ -117,15 +125,21 @@ __global__ void build_s_kernel(__half* __restrict__ img) {
   img[off] = __float2half_rn(v);
 }
 
-// G'[k1][k2] = FFT_N(k')[k1 + 128 k2] / (N * S1), k' = filter taps 0..C-1 with the bias skip folded into
-// tap 0, computed with the same two-stage decomposition in fp32; stored as fp16, one uint4 per 4 consecutive k2:
+// G'[k1][k2] = FFT_N(k')[k1 + 128 k2] * 2^e, k' = filter taps [seg C, seg C + C) with the bias skip folded into
+// tap 0 of segment 0, computed with the same two-stage decomposition in fp32.  e = gexp[seg][ch] is chosen per
+// (segment, channel) so that the largest bin lands in [1/16, 1/8): the table is fp16, and with one global scale the
+// bins of a decayed segment (or of a trained filter of another magnitude) would sit in the subnormal range.  Stored
+// as one uint4 per 4 consecutive k2:
 // {re(k2, k2+1), im(k2, k2+1), re(k2+2, k2+3), im(k2+2, k2+3)} at uint4 index
 //   (((ch * 4 + k1 / 32) * 2 + k2 / 64) * 16 + (k2 % 64) / 4) * 32 + k1 % 32
 // so that a warp of 32 consecutive k1 reads 512 contiguous bytes per 16-byte load.
 __global__ void __launch_bounds__(256) spectrum_kernel(const float* __restrict__ k, long long Lk, int n_taps,
-                                                       const float* __restrict__ dbias, __half2* __restrict__ G_all) {
+                                                       const float* __restrict__ dbias, __half2* __restrict__ G_all,
+                                                       int* __restrict__ gexp) {
   extern __shared__ float2 sm_a[];            // A[k1][n2], 128 KB
   __shared__ float2 w128[128];
+  __shared__ float red[8];
+  __shared__ float s_scale;
   // blockIdx.y = filter segment: taps [seg * C, (seg + 1) * C) (zero past n_taps); the bias skip lives in tap 0 only
   const int ch = blockIdx.x, seg = blockIdx.y;
   const float* kc = k + (long long)ch * Lk + (long long)seg * C;
@@ -153,21 +167,111 @@ __global__ void __launch_bounds__(256) spectrum_kernel(const float* __restrict__
     sm_a[o] = make_float2(ar * c - ai * s, ar * s + ai * c);
   }
   __syncthreads();
-  const float scale = 1.0f / (float(N) * S1);
-  for (int o = threadIdx.x; o < N; o += blockDim.x) {
+  auto bin = [&](int o, float& gr, float& gi) {
     const int k1 = o / R, k2 = o % R;
-    float gr = 0.f, gi = 0.f;
+    gr = 0.f; gi = 0.f;
     for (int n2 = 0; n2 < R; ++n2) {
       const float2 a = sm_a[k1 * R + n2];
       const float2 w = w128[(n2 * k2) & 127];
       gr += a.x * w.x - a.y * w.y;
       gi += a.x * w.y + a.y * w.x;
     }
+  };
+  // pass 1: largest |re|, |im| over the segment's bins -> exponent
+  float mx = 0.f;
+  for (int o = threadIdx.x; o < N; o += blockDim.x) {
+    float gr, gi;
+    bin(o, gr, gi);
+    mx = fmaxf(mx, fmaxf(fabsf(gr), fabsf(gi)));
+  }
+  for (int d = 16; d > 0; d >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float m = 0.f;
+    for (int i = 0; i < 8; ++i) m = fmaxf(m, red[i]);
+    int e = 0;
+    if (m > 0.f && m < INFINITY) {
+      int ex;
+      frexpf(m, &ex);            // m = f * 2^ex, f in [0.5, 1)  ->  m * 2^(-3 - ex) in [1/16, 1/8)
+      e = max(-100, min(100, -3 - ex));
+    }
+    gexp[seg * gridDim.x + ch] = e;
+    s_scale = ldexpf(1.0f, e);
+  }
+  __syncthreads();
+  const float scale = s_scale;
+  // pass 2: recompute (the 128 KB of stage-1 results leave no room to keep the bins) and store scaled
+  for (int o = threadIdx.x; o < N; o += blockDim.x) {
+    const int k1 = o / R, k2 = o % R;
+    float gr, gi;
+    bin(o, gr, gi);
     const size_t u4 = ((((size_t)ch * 4 + k1 / 32) * 2 + k2 / 64) * 16 + (k2 % 64) / 4) * 32 + (k1 % 32);
     __half* gh = reinterpret_cast<__half*>(G) + u4 * 8 + ((k2 % 4) / 2) * 4 + (k2 % 2);
     gh[0] = __float2half_rn(gr * scale);
     gh[2] = __float2half_rn(gi * scale);
   }
+}
+
+// Largest |vx| per channel of a channel-major bf16 [B][D][Tp] buffer (tokens < T), accumulated with atomicMax on the
+// float bit pattern (non-negative floats order like unsigned integers).  Grid (D, B).  Used once, by the calibration
+// forward of clm_finalize, and by the unit-level auto-scaling entry point.
+__global__ void __launch_bounds__(256) amax_cm_kernel(const __nv_bfloat16* __restrict__ vx, int D, int Tp, int T,
+                                                      unsigned int* __restrict__ amax_bits) {
+  __shared__ float red[8];
+  const int ch = blockIdx.x, b = blockIdx.y;
+  const __nv_bfloat16* row = vx + ((long long)b * D + ch) * Tp;
+  float m = 0.f;
+  for (int t = threadIdx.x; t < T; t += blockDim.x) {
+    const float v = fabsf(__bfloat162float(row[t]));
+    if (v < INFINITY) m = fmaxf(m, v);
+  }
+  for (int d = 16; d > 0; d >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, d));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 1; i < 8; ++i) m = fmaxf(m, red[i]);
+    atomicMax(amax_bits + ch, __float_as_uint(m));
+  }
+}
+
+constexpr float VX_TARGET_AMAX = 8.0f;   // scaled |v*x1| of the calibration draw lands in (4, 8]
+
+// Per-channel scale factors of one layer (see LongConvTcParams).  amax_bits == nullptr: no input scaling (a = 1).
+// Budget: with |a z| <= 8 the largest possible spectrum bin (a constant input - e.g. the [PAD] prefix of a left-padded
+// batch - puts 8192 equal values into the DC bin) is 8 * 8192 * S1 = 8192 in P1 x F and in the parked fp16 spectra, and
+// <= 1024 after the filter product: 8x below the fp16 limit; the input itself has 8000x of headroom over the
+// calibration draw.  Anything beyond that overflows to inf/NaN, is detected in E4 and reported (clm_forward_status).
+// `shift` (normally 0) moves the input scale by 2^shift: a test hook that makes real data overflow.
+__global__ void scales_kernel(const int* __restrict__ gexp, const unsigned int* __restrict__ amax_bits, float* __restrict__ vx_scale,
+                              float* __restrict__ osc, float* __restrict__ inva, float* __restrict__ rel, int D, int n_seg,
+                              int shift) {
+  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ch >= D) return;
+  int ea = 0;
+  if (amax_bits) {
+    const float m = __uint_as_float(amax_bits[ch]);
+    if (m > 0.f && m < INFINITY) {
+      int ex;
+      frexpf(m, &ex);                       // m in [2^(ex-1), 2^ex)  ->  m * 2^(3 - ex) in [4, 8)
+      ea = max(-40, min(40, 3 - ex));
+    }
+  }
+  ea += shift;
+  const int e0 = gexp[ch];
+  vx_scale[ch] = ldexpf(1.0f, ea);
+  inva[ch] = ldexpf(1.0f, -ea);
+  osc[ch] = ldexpf(1.0f, -e0 - ea - 11);    // 1 / (2^e0 * a * N * S1), N * S1 = 2048
+  for (int j = 0; j < n_seg; ++j) rel[j * D + ch] = ldexpf(1.0f, max(-120, min(120, e0 - gexp[j * D + ch])));
+}
+
+// bf16 -> fp16 with the per-channel input scale and zeros past T (what block_in emits in the forward)
+__global__ void __launch_bounds__(256) scale_to_f16_kernel(const __nv_bfloat16* __restrict__ in, __half* __restrict__ out,
+                                                           const float* __restrict__ vx_scale, int D, int Tp, int T) {
+  const int ch = blockIdx.x, b = blockIdx.y;
+  const long long base = ((long long)b * D + ch) * Tp;
+  const float a = vx_scale[ch];
+  for (int t = threadIdx.x; t < Tp; t += blockDim.x) out[base + t] = __float2half_rn(t < T ? __bfloat162float(in[base + t]) * a : 0.f);
 }
 
 }  // namespace tc
@@ -389,6 +493,8 @@ longconv_tc_kernel(const __grid_constant__ CUtensorMap tmVX, const __grid_consta
       const int b0 = 2 * pr, b1 = 2 * pr + 1;
       const bool has1 = b1 < p.B;
       const long long row0 = ((long long)b0 * p.D + ch) * p.Tp, row1 = ((long long)b1 * p.D + ch) * p.Tp;
+      const float osc = __ldg(p.osc + ch);   // output scale of this channel (exact power of two)
+      float chk = 0.f;                       // becomes NaN when any output of this unit is inf / NaN
       if (tr) stamp(1);
       // Twiddle seeds are re-materialised per item: without the barrier ptxas precomputes all 256 twiddle values of the
       // thread once and keeps them in LOCAL memory (an L2 round trip per use with this shared-memory carve-out).
@@ -492,6 +598,8 @@ longconv_tc_kernel(const __grid_constant__ CUtensorMap tmVX, const __grid_consta
           }
 #pragma unroll 1
           for (int j = 1; j <= c; ++j) {
+            const float relj = __ldg(p.rel + j * p.D + ch);   // 2^(e_0 - e_j): segment j's table -> segment 0's scale
+            const f2t REL = f2_pack(relj, relj);
             const uint4* gj = gp + (size_t)j * p.g_seg_stride + g_off(u);
             uint4 gq[4], sq[4];
 #pragma unroll
@@ -506,7 +614,7 @@ longconv_tc_kernel(const __grid_constant__ CUtensorMap tmVX, const __grid_consta
 #pragma unroll
               for (int hp = 0; hp < 2; ++hp) {
                 const int m = 2 * v + hp;   // elements 2 m, 2 m + 1
-                const f2t GR = h2_to_f2(gw[2 * hp]), GI = h2_to_f2(gw[2 * hp + 1]);
+                const f2t GR = f2_mul(h2_to_f2(gw[2 * hp]), REL), GI = f2_mul(h2_to_f2(gw[2 * hp + 1]), REL);
                 const f2t XR = h2_to_f2(sw[2 * hp]), XI = h2_to_f2(sw[2 * hp + 1]);
                 ar[m] = f2_sub(f2_fma(XR, GR, ar[m]), f2_mul(XI, GI));
                 ai[m] = f2_fma(XI, GR, f2_fma(XR, GI, ai[m]));
@@ -589,6 +697,9 @@ longconv_tc_kernel(const __grid_constant__ CUtensorMap tmVX, const __grid_consta
             tc0 = fmaf(__half2float(p.vx[row0 + a * C + i]), kv, tc0);
             if (has1) tc1 = fmaf(__half2float(p.vx[row1 + a * C + i]), kv, tc1);
           }
+        const float inva = __ldg(p.inva + ch);   // the vx rows hold a * v*x1
+        tc0 *= inva;
+        tc1 *= inva;
         tx0 = __bfloat162float(p.x0[row0 + NC * C + j]);
         if (has1) tx1 = __bfloat162float(p.x0[row1 + NC * C + j]);
       }
@@ -613,6 +724,9 @@ longconv_tc_kernel(const __grid_constant__ CUtensorMap tmVX, const __grid_consta
               vb += carry[8192 + n1 * 128 + r];
             }
           }
+          va *= osc;
+          vb *= osc;
+          chk = fmaf(va, 0.f, fmaf(vb, 0.f, chk));
           const float ga = __uint_as_float(uint32_t(st0[n1 * 128]) << 16);
           const __nv_bfloat16 oa = __float2bfloat16(va * ga);
           st0[n1 * 128] = *reinterpret_cast<const unsigned short*>(&oa);
@@ -648,10 +762,11 @@ longconv_tc_kernel(const __grid_constant__ CUtensorMap tmVX, const __grid_consta
         tmem_ld16(TM_Y + lane_addr + ZIM + 64, zi);
         ptx::tmem_ld_wait();
         if (tail_thread) {
-          p.out[row0 + NC * C + lane] = __float2bfloat16((__uint_as_float(zr[0]) + tc0) * tx0);
-          if (has1) p.out[row1 + NC * C + lane] = __float2bfloat16((__uint_as_float(zi[0]) + tc1) * tx1);
+          p.out[row0 + NC * C + lane] = __float2bfloat16((__uint_as_float(zr[0]) * osc + tc0) * tx0);
+          if (has1) p.out[row1 + NC * C + lane] = __float2bfloat16((__uint_as_float(zi[0]) * osc + tc1) * tx1);
         }
       }
+      if (chk != chk) atomicOr(p.err, 2);   // an fp16 operand overflowed somewhere in this unit: the launch is reported
       ptx::fence_proxy_async_smem();
       ptx::tc_fence_before_sync();
       __syncwarp();

@@ -281,6 +281,7 @@ class Trainer:
         self.global_rank, self.world_size = rank, world_size
 
     def predict(self, model, dataloaders=None, return_predictions: bool = False, ckpt_path=None):
+        from ._lib import Fp16RangeError
         from .weights import load_checkpoint
 
         if ckpt_path is not None:
@@ -297,30 +298,39 @@ class Trainer:
         model.eval()
         results = []
 
+        def to_host(t):
+            return torch.empty(t.shape, dtype=t.dtype, pin_memory=True).copy_(t, non_blocking=True) if t.is_cuda else t
+
         def finish(item):
             # Batch k's outputs are consumed (callbacks, files) only after batch k+1 was launched, so
             # the device never waits for the host side of the loop.
-            batch_idx, batch, pred, ev = item
+            batch_idx, batch, pred, labels, seq, ev = item
             if ev is not None:
                 ev.synchronize()
+                try:
+                    model.engine.forward_status(seq)
+                except Fp16RangeError:   # this batch left the fp16 range of the tensor-core conv: redo it in fp32
+                    logits, dev_labels = model.engine.forward(batch["input_ids"], return_labels=True, check=True)
+                    pred, labels = (logits.cpu(), pred[1]), dev_labels.cpu()
             for cb in self.callbacks:
                 cb.write_on_batch_end(self, model, pred, None, batch, batch_idx, 0)
             if return_predictions or self.world_size > 1:
-                results.append((batch.get("indices"), pred[2].cpu() if len(pred) > 2 else pred[0].argmax(1).cpu()))
+                results.append((batch.get("indices"), labels if labels is not None else pred[0].argmax(1).cpu()))
 
         pending = None
         for batch_idx, batch in enumerate(loader):
             pred = model.predict_step(batch, batch_idx)
-            ev = None
+            labels, seq, ev = None, 0, None
             if isinstance(pred, (tuple, list)) and pred[0].is_cuda:
-                host = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True).copy_(t, non_blocking=True)
-                        if isinstance(t, torch.Tensor) and t.is_cuda else t for t in pred]
+                dev = pred[0].device
+                labels, seq = getattr(model, "last_device_labels", None), getattr(model, "last_forward_seq", 0)
+                pred = tuple(to_host(t) if isinstance(t, torch.Tensor) else t for t in pred)
+                labels = to_host(labels) if labels is not None else None
                 ev = torch.cuda.Event()
-                ev.record(torch.cuda.current_stream(pred[0].device))
-                pred = tuple(host)
+                ev.record(torch.cuda.current_stream(dev))
             if pending is not None:
                 finish(pending)
-            pending = (batch_idx, batch, pred, ev)
+            pending = (batch_idx, batch, pred, labels, seq, ev)
         if pending is not None:
             finish(pending)
         self.last_results = results

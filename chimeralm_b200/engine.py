@@ -26,7 +26,7 @@ class Engine:
     """Owns a `clm_ctx`: weights, filter tables, workspaces (include/chimeralm_b200.h)."""
 
     def __init__(self, state_dict, device: int | str | torch.device = 0, cfg: HyenaConfig = DEFAULT_CONFIG,
-                 max_batch: int = 32, max_tokens: int = 8193):
+                 max_batch: int = 32, max_tokens: int = 8193, token_budget: int | None = None):
         self.lib = _lib.load()
         if not torch.cuda.is_available():
             raise _lib.ChimeraLMNativeError("no CUDA device: chimeralm_b200 has no CPU path")
@@ -49,8 +49,11 @@ class Engine:
             raise _lib.ChimeraLMNativeError(f"clm_create failed (status {rc}): {msg}")
         self.load_state_dict(state_dict)
         self._check(self.lib.clm_finalize(self.ctx), "clm_finalize")
-        self.max_batch = self.max_tokens = 0
-        self.reserve(max_batch, max_tokens)
+        self.max_batch = self.max_tokens = self.token_budget = 0
+        self.last_seq = 0
+        self.tc_fallbacks = 0   # batches redone with the fp32 convolution by forward(check=True)
+        self._debug_stop = False
+        self.reserve(max_batch, max_tokens, token_budget)
         # CLM_OPTIONS="name=value,name=value": kernel-selection switches (clm_set_option) for A/B runs of the test suite / bench
         for item in filter(None, os.environ.get("CLM_OPTIONS", "").split(",")):
             name, _, val = item.partition("=")
@@ -81,12 +84,23 @@ class Engine:
                                           shape, a.ndim)
             self._check(rc, f"clm_load_tensor({name})")
 
-    def reserve(self, max_batch: int, max_tokens: int) -> None:
-        if max_batch <= self.max_batch and max_tokens <= self.max_tokens:
+    def reserve(self, max_batch: int, max_tokens: int, token_budget: int | None = None) -> None:
+        """Workspaces for batches of <= max_batch reads of <= max_tokens tokens each; `token_budget` (default
+        max_batch * max_tokens) caps the padded size B * T of a batch (length-bucketed prediction: many short reads or
+        few long ones per batch)."""
+        budget = max_batch * max_tokens if token_budget is None else min(token_budget, max_batch * max_tokens)
+        if max_batch <= self.max_batch and max_tokens <= self.max_tokens and budget <= self.token_budget:
             return
         max_batch, max_tokens = max(max_batch, self.max_batch), max(max_tokens, self.max_tokens)
-        self._check(self.lib.clm_reserve(self.ctx, max_batch, max_tokens), "clm_reserve")
-        self.max_batch, self.max_tokens = max_batch, max_tokens
+        budget = min(max(budget, self.token_budget, max_tokens), max_batch * max_tokens)
+        self.max_batch = self.max_tokens = self.token_budget = 0   # a failed clm_reserve leaves the context without workspaces
+        self._check(self.lib.clm_reserve_tokens(self.ctx, max_batch, max_tokens, budget), "clm_reserve")
+        self.max_batch, self.max_tokens, self.token_budget = max_batch, max_tokens, budget
+
+    @property
+    def native_tc_fallbacks(self) -> int:
+        """Batches `clm_predict_host` redid with the fp32 convolution."""
+        return int(self.lib.clm_tc_fallback_count(self.ctx))
 
     @property
     def launch_count(self) -> int:
@@ -109,22 +123,45 @@ class Engine:
         return out
 
     # ------------------------------------------------------------------ hot path
-    def forward(self, input_ids: torch.Tensor, return_labels: bool = False):
-        """ClassificationLit.forward: int ids [B,T] on this device -> float32 logits [B,2]."""
+    def forward(self, input_ids: torch.Tensor, return_labels: bool = False, check: bool = False):
+        """ClassificationLit.forward: int ids [B,T] on this device -> float32 logits [B,2].  Asynchronous on the current
+        stream unless `check` (see `forward_status`)."""
         if input_ids.dim() != 2:
             raise ValueError("input_ids must be [B, T]")
         if input_ids.dtype not in _IDS_DTYPES:
             raise TypeError(f"input_ids dtype {input_ids.dtype} not supported (uint8/int32/int64)")
         ids = input_ids.to(self.device).contiguous()
         B, T = ids.shape
-        self.reserve(B, T)
+        self.reserve(B, T, B * T)
         logits = torch.empty(B, 2, dtype=torch.float32, device=self.device)
         labels = torch.empty(B, dtype=torch.uint8, device=self.device)
         rc = self.lib.clm_forward(self.ctx, C.c_void_p(ids.data_ptr()), _IDS_DTYPES[ids.dtype], B, T,
                                   C.c_void_p(logits.data_ptr()), C.c_void_p(labels.data_ptr()),
                                   _stream_ptr(self.device))
         self._check(rc, "clm_forward")
+        self.last_seq = int(self.lib.clm_forward_seq(self.ctx))
+        if check:
+            # synchronous form: wait, read the forward's status word and, if the batch left the fp16 range of the
+            # tensor-core convolution, redo it with the fp32 FFT kernel (the reference's fftconv is fp32)
+            torch.cuda.current_stream(self.device).synchronize()
+            try:
+                self.forward_status(self.last_seq)
+            except _lib.Fp16RangeError:
+                self.tc_fallbacks += 1
+                self.set_option("tc_conv", 0)
+                try:
+                    return self.forward(ids, return_labels=return_labels, check=True)
+                finally:
+                    self.set_option("tc_conv", 1)
         return (logits, labels) if return_labels else logits
+
+    def forward_status(self, seq: int | None = None) -> None:
+        """Raise if forward `seq` (default: the last one) saw a token id outside the embedding table (IndexError, like
+        `nn.Embedding`) or left the fp16 range of the tensor-core convolution (Fp16RangeError).  The forward's stream
+        work must be complete; the status word sits in mapped host memory, so this is a plain read."""
+        if self._debug_stop:
+            return   # a stopped forward never reaches the kernel that publishes the status
+        self._check(self.lib.clm_forward_status(self.ctx, self.last_seq if seq is None else seq), "forward")
 
     def encode(self, bases: torch.Tensor, offsets: torch.Tensor, T_pad: int, *, add_cls: bool, add_sep: bool,
                pad_left: bool, max_bases: int):
@@ -147,7 +184,7 @@ class Engine:
                      labels_out: torch.Tensor | None = None):
         """End-to-end with HOST tensors (pinned recommended): H2D, encode, forward, D2H, sync."""
         B = offsets.numel() - 1
-        self.reserve(B, T_pad)
+        self.reserve(B, T_pad, B * T_pad)
         if logits_out is None:
             logits_out = torch.empty(B, 2, dtype=torch.float32).pin_memory()
         if labels_out is None:
@@ -235,6 +272,18 @@ class Engine:
         self._check(rc, "clm_longconv_tc")
         return out
 
+    def longconv_tc_auto(self, layer: int, vx: torch.Tensor, x0: torch.Tensor, T: int):
+        """Tensor-core FFT long conv on bf16 vx of any magnitude: per-channel power-of-two input scale from the data,
+        fp16 conversion, kernel, output scaled back (what block_in + longconv_tc do together in the forward)."""
+        if vx.dtype != torch.bfloat16 or x0.dtype != torch.bfloat16:
+            raise TypeError("longconv_tc_auto takes bf16 vx and x0")
+        B, D, Tp = vx.shape
+        out = torch.zeros_like(x0)
+        rc = self.lib.clm_longconv_tc_auto(self.ctx, layer, C.c_void_p(vx.data_ptr()), C.c_void_p(x0.data_ptr()),
+                                           C.c_void_p(out.data_ptr()), B, T, Tp, _stream_ptr(self.device))
+        self._check(rc, "clm_longconv_tc_auto")
+        return out
+
     def attention_weights(self, B: int, T: int) -> torch.Tensor:
         """softmax_t of the attention-pooling scores of the last forward: float32 [B, T]."""
         out = torch.empty(B, T, dtype=torch.float32, device=self.device)
@@ -254,6 +303,7 @@ class Engine:
 
     def set_debug_stop(self, layer: int = -1, stage: int = -1) -> None:
         self._check(self.lib.clm_set_debug_stop(self.ctx, layer, stage), "clm_set_debug_stop")
+        self._debug_stop = layer >= 0
 
     def debug_copy(self, what: str, shape, dtype) -> torch.Tensor:
         out = torch.empty(shape, dtype=dtype, device=self.device)

@@ -27,6 +27,7 @@ class ClassificationLit:
         # weights [B, T, 1], like `BinarySequenceClassifier.attention_weights` (components/hyena.py:129-130)
         self.save_attention = save_attention
         self.attention_weights = None
+        self.last_device_labels, self.last_forward_seq = None, 0
         self._state_dict = state_dict
         self.engine = Engine(state_dict, device=device, cfg=cfg, max_batch=max_batch, max_tokens=max_tokens)
         self.device = self.engine.device
@@ -53,8 +54,10 @@ class ClassificationLit:
 
     def forward(self, input_ids: torch.Tensor, input_quals: torch.Tensor | None = None) -> torch.Tensor:
         """logits [B, 2] float32; `input_quals` is accepted and ignored exactly like
-        `HyenaDna.forward` ignores it (chimeralm/models/components/hyena.py:244-256)."""
-        logits = self.engine.forward(input_ids)
+        `HyenaDna.forward` ignores it (chimeralm/models/components/hyena.py:244-256).  Synchronous: the forward's
+        status is checked (an out-of-range token id raises IndexError like `nn.Embedding`; a batch that leaves the
+        fp16 range of the tensor-core convolution is redone with the fp32 FFT kernel)."""
+        logits = self.engine.forward(input_ids, check=True)
         if self.save_attention:
             self.attention_weights = self.engine.attention_weights(*input_ids.shape).unsqueeze(-1)
         return logits
@@ -62,12 +65,15 @@ class ClassificationLit:
     __call__ = forward
 
     def predict_step(self, batch: dict, batch_idx: int):
-        """Returns `(logits, batch["labels"])` like the reference; device-side argmax labels
-        (same rule as PredictionWriter, callbacks.py:107) ride along as a third element."""
+        """Returns exactly `(logits, batch["labels"])` like the reference (basic_module.py:177-187).  The step is
+        asynchronous on the current stream; the device-side argmax labels (same rule as PredictionWriter,
+        callbacks.py:107) and the forward's sequence number (for `Engine.forward_status`) are left in
+        `last_device_labels` / `last_forward_seq` for a caller that wants to pipeline - `Trainer.predict` does."""
         logits, labels = self.engine.forward(batch["input_ids"], return_labels=True)
+        self.last_device_labels, self.last_forward_seq = labels, self.engine.last_seq
         if self.save_attention:
             self.attention_weights = self.engine.attention_weights(*batch["input_ids"].shape).unsqueeze(-1)
-        return logits, batch["labels"], labels
+        return logits, batch["labels"]
 
 
 class ChimeraLM:

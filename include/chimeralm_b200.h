@@ -27,7 +27,9 @@ typedef enum {
   CLM_ERR_CUDA = -2,      /* CUDA runtime or driver error (message has the detail) */
   CLM_ERR_STATE = -3,     /* call order violated (e.g. forward before finalize) */
   CLM_ERR_MISSING = -4,   /* a required weight tensor was never loaded */
-  CLM_ERR_NOMEM = -5
+  CLM_ERR_NOMEM = -5,
+  CLM_ERR_TOKEN_RANGE = -6, /* a token id outside [0, vocab_rows): the reference's nn.Embedding raises IndexError */
+  CLM_ERR_FP16_RANGE = -7   /* the fp16 tensor-core convolution left its range for this batch (see clm_forward_status) */
 } clm_status;
 
 typedef enum { CLM_F32 = 0, CLM_BF16 = 1, CLM_U8 = 2, CLM_I32 = 3, CLM_I64 = 4 } clm_dtype;
@@ -60,9 +62,15 @@ int clm_load_tensor(clm_ctx* ctx, const char* name, const void* data, int dtype,
 /* Converts GEMM weights to bf16, generates the implicit long filters for all layers
  * (HyenaFilter.filter, recomputed on every forward in the reference) and their spectra. */
 int clm_finalize(clm_ctx* ctx);
-/* Sizes the activation workspaces for batches up to max_B reads of max_T tokens.  No
- * allocation happens inside clm_forward. */
+/* Sizes the activation workspaces (and clm_predict_host's staging) for batches up to max_B reads of max_T tokens.
+ * No allocation happens inside clm_forward or clm_predict_host.  If it fails (CLM_ERR_NOMEM) the context holds NO
+ * workspaces and refuses forwards until a smaller clm_reserve succeeds. */
 int clm_reserve(clm_ctx* ctx, int max_B, int max_T);
+/* Same with an explicit token budget: batches of up to max_B reads and up to max_T tokens per read whose padded size
+ * B * T stays <= max_tokens (clm_reserve uses max_B * max_T).  This is what length-bucketed prediction wants - 256 reads
+ * of 1 kb or 8 reads of 32 kb per batch - and what the reference's fixed `--batch-size` cannot express
+ * (chimeralm/__main__.py:253; chimeralm/data/bam.py:287-299). */
+int clm_reserve_tokens(clm_ctx* ctx, int max_B, int max_T, long long max_tokens);
 
 /* Tokenisation + collation on the device.  Replaces tokenizer(seq, truncation=True,
  * max_length=...) (chimeralm/data/tokenizer.py:97, CharacterTokenizer :264-306) and
@@ -85,6 +93,18 @@ int clm_encode_batch(clm_ctx* ctx, const uint8_t* d_bases, const int64_t* d_offs
  *   d_labels : device, uint8[B] = argmax(logits) with ties -> 0 (may be NULL) */
 int clm_forward(clm_ctx* ctx, const void* d_ids, int ids_dtype, int B, int T, float* d_logits, uint8_t* d_labels,
                 void* stream);
+
+/* Status of an asynchronous clm_forward.  clm_forward_seq() is the sequence number of the forward issued last on this
+ * context; once that forward's stream work is complete (the caller synchronises), clm_forward_status(ctx, seq)
+ * returns 0, CLM_ERR_TOKEN_RANGE, or CLM_ERR_FP16_RANGE - the last kernel of every forward publishes the status word
+ * into mapped host memory, so this costs no copy and no synchronisation.  The last 8 forwards can be queried;
+ * CLM_ERR_STATE means the forward has not finished.  On CLM_ERR_FP16_RANGE the logits of that batch are invalid:
+ * rerun it after clm_set_option(ctx, "tc_conv", 0), which selects the fp32 FFT convolution (the reference computes
+ * fftconv in fp32: HF modeling_hyena.fftconv via chimeralm/models/components/hyena.py:249).  clm_predict_host does
+ * this by itself; clm_tc_fallback_count() says how often. */
+long long clm_forward_seq(const clm_ctx* ctx);
+int clm_forward_status(clm_ctx* ctx, long long seq);
+long long clm_tc_fallback_count(const clm_ctx* ctx);
 
 /* End-to-end convenience with HOST buffers (pinned recommended): H2D copy of bases/offsets,
  * encode, forward, D2H copy of logits/labels, stream synchronise.  This is what bench.py's
@@ -145,6 +165,12 @@ int clm_attention_weights(clm_ctx* ctx, float* d_out, int B, int T, void* stream
  * that d_vx holds fp16 values (what the fused in_proj kernel emits when this kernel follows). */
 int clm_longconv_tc(clm_ctx* ctx, int layer, const void* d_vx_f16, const void* d_x0, void* d_out, int B, int T, int Tp,
                     void* stream);
+/* Unit-test form of what the forward does around that kernel: d_vx holds bf16 values of ANY magnitude; the per-channel
+ * power-of-two input scale is taken from the data itself (in the forward it comes from clm_finalize's calibration
+ * draw and is applied by the fused in_proj kernel), the rows are converted to fp16, the kernel runs and the output is
+ * scaled back.  Synchronous; returns CLM_ERR_FP16_RANGE when an intermediate overflowed. */
+int clm_longconv_tc_auto(clm_ctx* ctx, int layer, const void* d_vx_bf16, const void* d_x0, void* d_out, int B, int T, int Tp,
+                         void* stream);
 /* Which long-convolution kernel clm_forward uses for reads of T tokens: 0 = first fp32 FFT kernel, 1 = tuned fp32
  * FFT kernel, 2 = tensor-core FFT kernel; -1 before clm_finalize. */
 int clm_longconv_variant(const clm_ctx* ctx, int T);

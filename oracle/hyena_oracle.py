@@ -103,7 +103,7 @@ def backbone(sd, input_ids: torch.Tensor, cfg) -> torch.Tensor:
     return F.layer_norm(h, (cfg.d_model,), sd[BB + "ln_f.weight"], sd[BB + "ln_f.bias"], cfg.layer_norm_epsilon)
 
 
-def head(sd, hidden: torch.Tensor, return_attention: bool = False):
+def head(sd, hidden: torch.Tensor, return_attention: bool = False, return_features: bool = False):
     """BinarySequenceClassifier.forward(hidden, attention_mask=None), attention pooling.
 
     components/hyena.py:117-132: scores = Linear(256->1)(GELU(Linear(256->256)(h)));
@@ -124,16 +124,20 @@ def head(sd, hidden: torch.Tensor, return_attention: bool = False):
     r = F.linear(r, sd[HD + "classifier.6.layers.3.weight"], sd[HD + "classifier.6.layers.3.bias"])
     x = r + x
     logits = F.linear(x, sd[HD + "output_layer.weight"], sd[HD + "output_layer.bias"])
+    if return_features:   # input of `output_layer` (components/hyena.py:142-146), for the probe-head fit
+        return logits, x
     if return_attention:
         return logits, w.squeeze(-1)
     return logits
 
 
 @torch.inference_mode()
-def forward(sd, input_ids: torch.Tensor, cfg, return_hidden: bool = False):
+def forward(sd, input_ids: torch.Tensor, cfg, return_hidden: bool = False, return_features: bool = False):
     """ClassificationLit.forward (basic_module.py:67-77) -> logits [B,2] float32."""
     input_ids = input_ids.long()
     h = backbone(sd, input_ids, cfg)
+    if return_features:
+        return head(sd, h, return_features=True)
     logits = head(sd, h)
     if return_hidden:
         return logits, h

@@ -2,9 +2,10 @@
 final logits, on identical padded input_ids and identical seeded weights.
 
 Tolerances: bf16 GEMM operands / bf16 inter-kernel activations with fp32 accumulation, fp32
-residual stream, fp32 FFT and fp32 pooling/head.  Residual stream |err| <= 5e-2 (values ~ N(0,1)
-scaled by the block outputs), logits |err| <= 5e-3 (north_star: "stated bf16 tolerance";
-SURVEY.md 8(d) allows up to 2e-2), labels must agree wherever |oracle margin| > 2 * 5e-3."""
+residual stream, fp16-operand tensor-core FFT (fp32 accumulate) and fp32 pooling/head.  Residual
+stream |err| <= 5e-2 (values ~ N(0,1) scaled by the block outputs), logits |err| <= 1e-3 (measured
+2-3e-4; north_star: "stated bf16 tolerance", SURVEY.md 8(d) allows up to 2e-2), labels must agree
+wherever |oracle margin| > 2 * 1e-3.  Label agreement proper is measured in test_gpu_labels.py."""
 
 from pathlib import Path
 
@@ -15,7 +16,7 @@ from chimeralm_b200.config import DEFAULT_CONFIG as CFG
 
 pytestmark = pytest.mark.gpu
 
-LOGIT_TOL = 5e-3
+LOGIT_TOL = 1e-3
 ROOT = Path(__file__).resolve().parents[1]
 
 
@@ -121,20 +122,26 @@ def test_k1_bam_anchor_end_to_end(tmp_path, state_dict):
     recs = list(parse_bam_file(bam))
     assert len(preds) == 100 and set(preds) == {r["id"] for r in recs}
     assert sorted(p.name for p in out.glob("*.txt")) == sorted(f"0_{i}.txt" for i in range(9))
-    # first batch vs oracle (token ids from the oracle tokenizer: bit-exact check of the GPU encoder too)
-    ids_ref = TO.collate([TO.encode(r["seq"], max_length=32769, add_cls=False) for r in recs[:12]], padding_side="left")
+    # every batch vs the oracle on identical padded ids (token ids from the oracle tokenizer: bit-exact check of the GPU
+    # encoder too); 6 of the 9 batches pad to 32 769 tokens (chunked FFT path, up to 60x left padding)
     dm.setup("predict")
-    first = next(iter(dm.predict_dataloader()))
-    assert first["input_ids"].cpu().tolist() == ids_ref
-    logits = model.forward(first["input_ids"]).cpu()
-    ref = O.forward(state_dict, torch.tensor(ids_ref), CFG)
-    err = (logits - ref).abs().max().item()
-    print(f"K1 first batch ({len(ids_ref)} x {len(ids_ref[0])} tokens): logits max|err| {err:.3e}")
-    assert err <= LOGIT_TOL, err
-    margin = ref[:, 1] - ref[:, 0]
-    decided = margin.abs() > 2 * LOGIT_TOL
-    got = torch.tensor([preds[r["id"]] for r in recs[:12]])
-    assert torch.equal(got[decided], ref.argmax(1)[decided])
+    worst = 0.0
+    for bi, batch in enumerate(dm.predict_dataloader()):
+        chunk = recs[12 * bi: 12 * bi + 12]
+        ids_ref = TO.collate([TO.encode(r["seq"], max_length=32769, add_cls=False) for r in chunk], padding_side="left")
+        assert batch["input_ids"].cpu().tolist() == ids_ref, bi
+        logits = model.forward(batch["input_ids"]).cpu()
+        ref = O.forward(state_dict, torch.tensor(ids_ref), CFG)
+        err = (logits - ref).abs().max().item()
+        worst = max(worst, err)
+        print(f"K1 batch {bi} ({len(ids_ref)} x {len(ids_ref[0])} tokens): logits max|err| {err:.3e}")
+        assert err <= LOGIT_TOL, (bi, err)
+        margin = ref[:, 1] - ref[:, 0]
+        decided = margin.abs() > 2 * LOGIT_TOL
+        got = torch.tensor([preds[r["id"]] for r in chunk])
+        assert torch.equal(got[decided], ref.argmax(1)[decided]), bi
+    assert bi == 8
+    assert model.engine.tc_fallbacks == 0
     model.engine.close()
 
 
@@ -279,13 +286,20 @@ def test_kernel_variants_agree(state_dict, option, T):
     8 vs 16 epilogue warps): flipping it must not move the logits by more than the parity tolerance."""
     from chimeralm_b200.engine import Engine
 
+    from chimeralm_b200._lib import ChimeraLMNativeError
+
     B = 3
     eng = Engine(state_dict, device=0, max_batch=B, max_tokens=T)
     try:
         ids = _ids(B, T, seed=T, pad_left=T // 4).to(torch.uint8).cuda()
         base = eng.forward(ids).clone()
         default_on = option not in ("mlp_epi16", "mlp_pp")
-        eng.set_option(option, {"mlp_fc2_lag": 2}.get(option, 0 if default_on else 1))
+        try:
+            eng.set_option(option, {"mlp_fc2_lag": 2}.get(option, 0 if default_on else 1))
+        except ChimeraLMNativeError as e:
+            if "not compiled in" in str(e):
+                pytest.skip(f"{option}: experiment kernel, product build (-DCLM_EXPERIMENTS adds it)")
+            raise
         other = eng.forward(ids).clone()
         eng.set_option(option, {"mlp_early_res": 33, "mlp_fc2_lag": 1}.get(option, 1 if default_on else 0))
         again = eng.forward(ids)
@@ -321,3 +335,185 @@ def test_two_models_on_one_device_do_not_share_constants(state_dict):
         assert torch.equal(c.forward(ids), ref_b)
     finally:
         c.close()
+
+
+def test_k2_full_batch_vs_oracle(state_dict):
+    """K2 at its full size - 32 reads x 8 193 tokens, the benchmark's step - against the CPU oracle on the same ids
+    (no padding: K2 reads all have 8 192 bases), plus the same batch through the host entry point clm_predict_host."""
+    from chimeralm_b200 import synth
+    from chimeralm_b200.engine import Engine
+    from oracle import hyena_oracle as O
+
+    B, L = 32, 8192
+    reads = synth.uniform_reads(B, L, synth.K2_SEED)
+    ids = torch.from_numpy(synth.pad_left_ids(list(reads)))
+    assert ids.shape == (B, L + 1)
+    ref = O.forward(state_dict, ids, CFG)
+    eng = Engine(state_dict, device=0, max_batch=B, max_tokens=L + 1)
+    try:
+        assert eng.longconv_variant(L + 1) == "fft_tensor_core"
+        logits = eng.forward(ids.cuda(), check=True).cpu()
+        err = (logits - ref).abs().max().item()
+        print(f"K2 full batch 32 x 8193: logits max|err| {err:.3e}")
+        assert err <= LOGIT_TOL, err
+        bases = torch.from_numpy(reads.reshape(-1).copy()).pin_memory()
+        offs = torch.arange(0, (B + 1) * L, L, dtype=torch.int64).pin_memory()
+        lo, la = eng.predict_host(bases, offs, L + 1, add_cls=False, add_sep=True, pad_left=True, max_bases=32768)
+        assert torch.equal(lo, logits)
+        assert torch.equal(la.long(), (logits[:, 1] > logits[:, 0]).long())
+        assert eng.tc_fallbacks == 0 and eng.native_tc_fallbacks == 0
+    finally:
+        eng.close()
+
+
+def test_predict_step_contract(state_dict):
+    """`predict_step` returns exactly `(logits, batch["labels"])` like the reference (basic_module.py:177-187); the
+    device labels are an attribute, not a third element."""
+    from chimeralm_b200.model import ClassificationLit
+
+    B, T = 3, 400
+    ids = _ids(B, T, seed=5, pad_left=50)
+    model = ClassificationLit(state_dict, device=0, max_batch=B, max_tokens=T)
+    try:
+        batch = {"input_ids": ids.cuda(), "labels": torch.full((B,), -1, dtype=torch.int64), "id": torch.zeros(B, 256, dtype=torch.int8)}
+        out = model.predict_step(batch, 0)
+        assert isinstance(out, tuple) and len(out) == 2
+        logits, labels = out
+        assert logits.shape == (B, 2) and logits.dtype == torch.float32
+        assert labels is batch["labels"]
+        torch.cuda.synchronize()
+        assert torch.equal(model.last_device_labels.cpu().long(), logits.argmax(1).cpu())
+        assert torch.equal(model.forward(ids.cuda()), logits)
+    finally:
+        model.engine.close()
+
+
+def test_token_id_out_of_range_is_reported(state_dict):
+    """The reference's nn.Embedding raises IndexError for an id outside the table; here the forward's status word says
+    so (embed_kernel flags it, the last kernel of the forward publishes it)."""
+    from chimeralm_b200.engine import Engine
+
+    B, T = 2, 300
+    eng = Engine(state_dict, device=0, max_batch=B, max_tokens=T)
+    try:
+        ids = _ids(B, T, seed=1).to(torch.int32)
+        good = eng.forward(ids.cuda(), check=True).clone()
+        bad = ids.clone()
+        bad[1, 17] = 16
+        with pytest.raises(IndexError):
+            eng.forward(bad.cuda(), check=True)
+        neg = ids.clone()
+        neg[0, 3] = -1
+        eng.forward(neg.cuda())          # asynchronous form: the status is read after a synchronise
+        seq = eng.last_seq
+        torch.cuda.synchronize()
+        with pytest.raises(IndexError):
+            eng.forward_status(seq)
+        # the word is cleared: the next clean forward is clean, and identical to the first
+        assert torch.equal(eng.forward(ids.cuda(), check=True), good)
+    finally:
+        eng.close()
+
+
+def test_failed_reserve_leaves_a_safe_context(state_dict):
+    """a clm_reserve that runs out of memory must not leave dangling workspaces behind the old limits."""
+    from chimeralm_b200._lib import ChimeraLMNativeError
+    from chimeralm_b200.engine import Engine
+
+    B, T = 2, 500
+    eng = Engine(state_dict, device=0, max_batch=B, max_tokens=T)
+    try:
+        ids = _ids(B, T, seed=2).to(torch.uint8).cuda()
+        good = eng.forward(ids, check=True).clone()
+        with pytest.raises(ChimeraLMNativeError):
+            eng.reserve(8192, 32769)     # ~1.7 TB of workspaces
+        rc = eng.lib.clm_forward(eng.ctx, ids.data_ptr(), 2, B, T, good.data_ptr(), None, None)
+        assert rc < 0, "a forward after a failed reserve must be refused, not run on freed memory"
+        eng.reserve(B, T)
+        assert torch.equal(eng.forward(ids, check=True), good)
+    finally:
+        eng.close()
+
+
+def _trained_magnitude_weights(sd):
+    """Weights of the magnitudes a trained checkpoint may have (random init keeps every activation tiny): in_proj x 6
+    (v * x1 grows 36x, into the hundreds), per-layer filters scaled up / down by 50x, a large bias skip."""
+    out = {k: v.clone() for k, v in sd.items()}
+    fscale = [50.0, 0.02, 8.0, 0.3]
+    for i in range(CFG.n_layer):
+        p = f"net.backbone.backbone.layers.{i}.mixer."
+        out[p + "in_proj.weight"] *= 6.0
+        out[p + "in_proj.bias"] *= 6.0
+        out[p + "filter_fn.implicit_filter.6.weight"] *= fscale[i]
+        out[p + "filter_fn.bias"] *= 1.0 if i % 2 else 30.0
+    return out
+
+
+@pytest.mark.parametrize("B,T", [(2, 8193), (1, 20000), (1, 32769)])
+def test_forward_with_trained_weight_magnitudes(state_dict, B, T):
+    """ADVICE r1 / VERDICT weak #3: the fp16 tensor-core convolution with activations and filters far from the
+    random-init magnitudes, full forward vs the oracle at 8 193, 20 000 and 32 769 tokens.  The per-channel input scale
+    (calibration draw) and the per-segment spectrum scale keep every fp16 operand in range, so the tensor-core path must
+    be as close to the oracle as the fp32-convolution path is."""
+    from chimeralm_b200.engine import Engine
+    from oracle import hyena_oracle as O
+
+    sd = _trained_magnitude_weights(state_dict)
+    ids = _ids(B, T, seed=T + 1, pad_left=T // 2)
+    ref = O.forward(sd, ids, CFG)
+    eng = Engine(sd, device=0, max_batch=B, max_tokens=T)
+    try:
+        assert eng.longconv_variant(T) == "fft_tensor_core"
+        tc = eng.forward(ids.to(torch.uint8).cuda(), check=True).cpu()
+        assert eng.tc_fallbacks == 0, "the batch left the fp16 range although the scales were calibrated"
+        eng.set_option("tc_conv", 0)
+        fp = eng.forward(ids.to(torch.uint8).cuda(), check=True).cpu()
+        e_tc, e_fp = (tc - ref).abs().max().item(), (fp - ref).abs().max().item()
+        vx = eng.debug_copy("vx", (B * 256 * ((T + 127) // 128 * 128),), torch.bfloat16).float().abs().max().item()
+        print(f"trained-magnitude weights, {B} x {T}: |logits| {ref.abs().max():.3f}  max|v*x1| (last layer) {vx:.1f}  "
+              f"err tensor-core conv {e_tc:.3e}, fp32 conv {e_fp:.3e}")
+        assert torch.isfinite(tc).all()
+        assert e_tc <= max(LOGIT_TOL, 2.0 * e_fp), (e_tc, e_fp)
+    finally:
+        eng.close()
+
+
+def test_fp16_range_overflow_switches_to_fp32_conv(state_dict):
+    """Automatic switch: with the input scale pushed 2^13 too high (test hook) the tensor-core convolution overflows,
+    the forward's status says so, and both synchronous entry points redo the batch with the fp32 FFT kernel."""
+    from chimeralm_b200._lib import Fp16RangeError
+    from chimeralm_b200.engine import Engine
+
+    B, T, L = 2, 8193, 8192
+    eng = Engine(state_dict, device=0, max_batch=B, max_tokens=T)
+    try:
+        ids = _ids(B, T, seed=77).to(torch.uint8).cuda()
+        eng.set_option("tc_conv", 0)
+        want = eng.forward(ids, check=True).clone()
+        eng.set_option("tc_conv", 1)
+        eng.set_option("tc_scale_shift", 13)
+        eng.forward(ids)
+        seq = eng.last_seq
+        torch.cuda.synchronize()
+        with pytest.raises(Fp16RangeError):
+            eng.forward_status(seq)
+        got = eng.forward(ids, check=True)
+        assert eng.tc_fallbacks == 1 and torch.equal(got, want)
+        # clm_predict_host does the same on its own
+        from chimeralm_b200 import synth
+
+        reads = synth.uniform_reads(B, L, 9)
+        bases = torch.from_numpy(reads.reshape(-1).copy()).pin_memory()
+        offs = torch.arange(0, (B + 1) * L, L, dtype=torch.int64).pin_memory()
+        kw = dict(add_cls=False, add_sep=True, pad_left=True, max_bases=32768)
+        lo, _ = eng.predict_host(bases, offs, T, **kw)
+        assert eng.native_tc_fallbacks == 1 and torch.isfinite(lo).all()
+        eng.set_option("tc_scale_shift", 0)
+        eng.set_option("tc_conv", 0)
+        lo_fp, _ = eng.predict_host(bases, offs, T, **kw)
+        assert torch.equal(lo, lo_fp)
+        eng.set_option("tc_conv", 1)
+        lo_tc, _ = eng.predict_host(bases, offs, T, **kw)
+        assert eng.native_tc_fallbacks == 1 and (lo_tc - lo_fp).abs().max().item() <= LOGIT_TOL
+    finally:
+        eng.close()
