@@ -1,16 +1,26 @@
 #!/usr/bin/env python
-"""Headline benchmark: `chimeralm predict` throughput (reads/s) on synthetic 8 kb reads.
+"""Headline benchmark: `chimeralm predict` throughput (reads/s) on synthetic long reads.
 
-Contract (see the task brief): `python bench.py --gpus N --steps K --warmup W` prints ONE JSON
-line.  A step = one batch of BATCH reads through the predict hot path (tokenise -> forward ->
-labels).  `value` is measured with the read bytes already resident in HBM; `e2e` goes through
-the C-ABI host entry point (`clm_predict_host`) with pinned HOST buffers, H2D and D2H inside
-the timed region.  `roofline` is for the dominant kernel class, timed live with CUDA events
-on the launching stream (`clm_profile_*`).  `cpu_baseline` is the reference-equivalent CPU
-predict path (the oracle port: per-base Python tokeniser + collate + fp32 eager PyTorch
-forward + argmax) on a bounded sample.
+Contract (see the task brief): `python bench.py --gpus N --steps K --warmup W` prints ONE JSON line.
 
-`--impl reference` times that CPU path alone, on the same workload definition.
+  value / e2e     K2 (BASELINE.json configs[1]): 8 192-base reads, batch 32 per GPU, T = 8 193.  A step = one batch
+                  through the predict hot path (tokenise -> forward -> labels).  `value` has the read bytes resident
+                  in HBM; `e2e` goes through the C-ABI host entry point (`clm_predict_host`) with pinned HOST buffers,
+                  H2D and D2H inside the timed region.  Timed with CUDA events, max over ranks, the final NCCL
+                  all_gather of labels inside the region (warmed once before it, and also timed on its own).
+  roofline        dominant kernel class, from a SECOND, profiled pass over the same steps (`clm_profile_*`: CUDA
+                  events on the launching stream around every launch) so the profiling never sits inside `value`.
+  k3              configs[2..3]: log-normal 1-32 kb reads (seed 20251019), length-bucketed into batches of <= 256
+                  reads / <= 262 176 padded tokens; at N > 1 (= K4) the batches are dealt to the ranks by greedy LPT on
+                  the batch cost model and the (index, label) pairs are gathered at the end.  Strong scaling: the
+                  sample is fixed, `value` = sample reads / slowest rank's time.  Unpadded bases/s and padding waste
+                  are reported, because throughput counts real bases.
+  k5              configs[4]: reads of exactly 32 768 bases (T = 32 769), batch 64 per GPU, weak scaling.
+  label_agreement argmax labels vs the CPU oracle's golden logits on the 2 028-read label set (tests/golden/
+                  label_agreement.npz; probe head, see oracle/make_label_golden.py), rank 0.
+  cpu_baseline    the reference-equivalent CPU predict path (oracle port) on a bounded sample, rank 0.
+
+`--impl reference` times that CPU path alone on the same workload definition.
 """
 
 from __future__ import annotations
@@ -31,30 +41,30 @@ import torch
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
+from chimeralm_b200 import synth  # noqa: E402
+
 READ_LEN = 8192          # K2: fixed 8 kb reads
 BATCH = 32               # K2: batch 32
-SEED = 20251018
 N_DISTINCT = 8           # distinct synthetic batches rotated through the timed region
 F_TOK = 6_423_040        # dense FLOP/token
-CONV_BYTES_TOK_LAYER = 1536  # long-conv algorithmic bytes/token/layer (bf16 vx in, x0 in, y*x0 out)
-
-
-def synth_reads(n, length, seed):
-    rng = np.random.default_rng(seed)
-    return np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, size=(n, length))]
+CONV_BYTES_TOK_LAYER = 1536  # long-conv algorithmic bytes/token/layer (vx in, x0 in, y*x0 out; 2 B each x 256 channels)
+K3_TOKEN_CAP = BATCH * (READ_LEN + 1)   # padded tokens per bucketed batch: the K2 step's size
+K3_MAX_READS = 256
+ENC = dict(add_cls=False, add_sep=True, pad_left=True, max_bases=32768)
 
 
 def peaks():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
         d = json.loads(p.read_text())
-        return {"hbm_gbs": d["hbm_gbs"], "tflops": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "src": "measured"}
-    return {"hbm_gbs": 6650.0, "tflops": 1590.0, "src": "fallback"}
+        return {"hbm_gbs": d["hbm_gbs"], "tflops_burst": d["bf16_tflops"],
+                "tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "src": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "tflops_burst": 1590.0, "tflops_sustained": 1590.0, "src": "fallback (B200_PROFILING.md)"}
 
 
 class ClockSampler:
-    """`nvidia-smi -lms 20` on one GPU.  Started early (nvidia-smi needs up to a second to come up on an 8-GPU box, longer
-    than a short timed region), rows are time-stamped and only those taken inside [mark_start, mark_end] are reported."""
+    """`nvidia-smi -lms 20` on one GPU, started early (nvidia-smi needs up to a second to come up on an 8-GPU box);
+    rows are time-stamped and reported per named window [mark_start, mark_end]."""
     QUERY = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
@@ -62,23 +72,23 @@ class ClockSampler:
     def __init__(self, gpu_index):
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         self.p = None
-        self.t0 = self.t1 = None
+        self.windows = {}
         try:
             self.p = subprocess.Popen(["nvidia-smi", f"--id={gpu_index}", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
                                        "-lms", "20"], stdout=self.f, stderr=subprocess.DEVNULL)
         except OSError:
             pass
 
-    def mark_start(self):
-        self.t0 = datetime.datetime.now()
+    def mark_start(self, name="k2"):
+        self.windows[name] = [datetime.datetime.now(), None]
 
-    def mark_end(self):
-        self.t1 = datetime.datetime.now()
+    def mark_end(self, name="k2"):
+        self.windows[name][1] = datetime.datetime.now()
 
     def stop(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        empty = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
         if self.p is None:
-            return out
+            return {k: dict(empty) for k in self.windows}
         self.p.terminate()
         try:
             self.p.wait(timeout=5)
@@ -87,8 +97,6 @@ class ClockSampler:
         self.f.flush()
         rows = [r.split(", ") for r in Path(self.f.name).read_text().strip().splitlines() if r.count(",") >= 9]
         os.unlink(self.f.name)
-        if not rows:
-            return out
 
         def when(r):
             try:
@@ -96,20 +104,26 @@ class ClockSampler:
             except ValueError:
                 return None
 
-        inside = [r for r in rows if self.t0 and self.t1 and when(r) and self.t0 <= when(r) <= self.t1]
-        if inside:
-            out["window"] = "timed region"
-        else:  # region shorter than the sampling period: the samples taken under load closest to it (warm-up + region)
-            before_end = [r for r in rows if self.t1 and when(r) and when(r) <= self.t1]
-            inside = before_end[-3:] or rows[-3:]
-            out["window"] = "last samples up to the end of the timed region (region shorter than the 20 ms sampling period)"
-        rows = inside
-        sm = sorted(float(r[2]) for r in rows)
-        out["sm_mhz"] = sm[len(sm) // 2]
-        out["sm_max_mhz"] = float(rows[0][3])
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        out["reasons"] = [n for i, n in enumerate(names) if any(r[6 + i].strip().lower().startswith("active") for r in rows)]
-        out["samples"] = len(rows)
+        out = {}
+        for name, (t0, t1) in self.windows.items():
+            o = dict(empty)
+            inside = [r for r in rows if t0 and t1 and when(r) and t0 <= when(r) <= t1]
+            if inside:
+                o["window"] = "timed region"
+            else:  # region shorter than the sampling period: the samples taken under load closest to it
+                before_end = [r for r in rows if t1 and when(r) and when(r) <= t1]
+                inside = before_end[-3:] or rows[-3:]
+                o["window"] = "last samples up to the end of the timed region (region shorter than the 20 ms sampling period)"
+            if inside:
+                sm = sorted(float(r[2]) for r in inside)
+                o["sm_mhz"] = sm[len(sm) // 2]
+                o["sm_mhz_min"] = sm[0]
+                o["sm_max_mhz"] = float(inside[0][3])
+                o["power_w_max"] = max(float(r[4]) for r in inside)
+                names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+                o["reasons"] = [n for i, n in enumerate(names) if any(r[6 + i].strip().lower().startswith("active") for r in inside)]
+                o["samples"] = len(inside)
+            out[name] = o
         return out
 
 
@@ -144,14 +158,16 @@ def run_reference(args, sd, cfg):
         return
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    n_per_step = 12
-    reads = synth_reads(n_per_step * max(1, min(args.steps + args.warmup, 4)), READ_LEN, SEED)
+    # one step = one batch of the SAME workload (batch 32 x 8 192 b) through the CPU path, ~4 s on 16 cores; with many
+    # steps requested the per-step sample shrinks to the reference CLI's default batch of 12 so the run stays bounded
+    n_per_step = args.batch if args.steps + args.warmup <= 30 else 12
+    reads = synth.uniform_reads(n_per_step * max(1, min(args.steps + args.warmup, 4)), args.read_len, synth.K2_SEED)
     for w in range(args.warmup):
-        cpu_reference_path(sd, cfg, reads[:n_per_step])
+        cpu_reference_path(sd, cfg, reads[:n_per_step], batch=n_per_step)
     t0 = time.perf_counter()
     for s in range(args.steps):
         off = (s % (reads.shape[0] // n_per_step)) * n_per_step
-        cpu_reference_path(sd, cfg, reads[off:off + n_per_step])
+        cpu_reference_path(sd, cfg, reads[off:off + n_per_step], batch=n_per_step)
     dt = time.perf_counter() - t0
     val = n_per_step * args.steps / dt
     line = {
@@ -159,14 +175,333 @@ def run_reference(args, sd, cfg):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args.read_len, args.read_len + 1, args.batch, max(1, args.gpus)),
-        "bases_per_s": val * READ_LEN,
+        "bases_per_s": val * args.read_len,
         "cpu_baseline": {"value": val, "unit": "reads/s", "cores": torch.get_num_threads(), "kind": "port",
-                         "sample": f"each step = {n_per_step} reads x {READ_LEN} b of the same synthetic workload through the CPU predict "
-                                   f"path (python tokeniser, collate, fp32 eager forward, argmax), batch 12 (the reference CLI default); "
-                                   f"{args.steps} steps; rank 0 only"},
+                         "sample": f"each step = one batch of {n_per_step} reads x {args.read_len} b of the same synthetic workload through the "
+                                   f"CPU predict path (python tokeniser, collate, fp32 eager forward, argmax); {args.steps} steps; rank 0 only"},
         "e2e": {"value": val, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+class Dist:
+    """torch.distributed plumbing (NCCL) with the N = 1 case folded in."""
+
+    def __init__(self, local_rank):
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.dev = torch.device("cuda", local_rank)
+        self.pg = None
+        if self.world > 1:
+            import torch.distributed as dist
+
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            dist.init_process_group("nccl", device_id=self.dev)
+            self.pg = dist
+
+    def barrier(self):
+        torch.cuda.synchronize()
+        if self.pg is not None:
+            self.pg.barrier()
+        torch.cuda.synchronize()
+
+    def all_gather(self, t):
+        if self.pg is None:
+            return [t]
+        out = [torch.empty_like(t) for _ in range(self.world)]
+        self.pg.all_gather(out, t)
+        return out
+
+    def gather_floats(self, vals):
+        """list of per-rank float lists (every rank contributes len(vals) numbers)"""
+        t = torch.tensor(vals, dtype=torch.float64, device=self.dev)
+        return [x.tolist() for x in self.all_gather(t)]
+
+    def close(self):
+        if self.pg is not None:
+            self.pg.destroy_process_group()
+            self.pg = None
+
+
+def e2e_pipelined(eng, items, max_reads):
+    """Batches from pinned HOST memory through the C-ABI's submit / wait pair with up to 3 in flight: H2D, encode, forward
+    and D2H of every batch are inside the caller's timed region; returns when the last batch's labels are on the host."""
+    from collections import deque
+
+    lo = [torch.empty(max_reads, 2, dtype=torch.float32).pin_memory() for _ in range(3)]
+    la = [torch.empty(max_reads, dtype=torch.uint8).pin_memory() for _ in range(3)]
+    pending = deque()
+    for i, (hb, ho, T, B) in enumerate(items):
+        pending.append(eng.predict_host_submit(hb, ho, T, logits_out=lo[i % 3][:B], labels_out=la[i % 3][:B], **ENC))
+        if len(pending) == 3:
+            eng.predict_host_wait(pending.popleft())
+    while pending:
+        eng.predict_host_wait(pending.popleft())
+    return lo, la
+
+
+def run_k2(args, eng, D, sampler):
+    B, L = args.batch, args.read_len
+    T = L + 1
+    reads = synth.uniform_reads(N_DISTINCT * B, L, synth.K2_SEED + D.rank)   # each rank its own shard (weak scaling)
+    offsets_h = torch.arange(0, (B + 1) * L, L, dtype=torch.int64)
+    dev_batches = [torch.from_numpy(reads[i * B:(i + 1) * B].reshape(-1).copy()).to(D.dev) for i in range(N_DISTINCT)]
+    host_batches = [torch.from_numpy(reads[i * B:(i + 1) * B].reshape(-1).copy()).pin_memory() for i in range(N_DISTINCT)]
+    offsets_d, offsets_p = offsets_h.to(D.dev), offsets_h.pin_memory()
+
+    def step_resident(i):
+        ids, _ = eng.encode(dev_batches[i % N_DISTINCT], offsets_d, T, **ENC)
+        return eng.forward(ids, return_labels=True)
+
+    def timed_pass():
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        labels = []
+        ev[0].record()
+        for i in range(args.steps):
+            labels.append(step_resident(i)[1])
+        mine = torch.cat(labels)
+        ev[1].record()
+        D.all_gather(mine)   # the path's only exchange: final gather of predictions
+        ev[2].record()
+        return ev
+
+    # ---- `value`: device-resident, un-profiled
+    for i in range(args.warmup):
+        step_resident(i)
+    D.all_gather(torch.zeros(args.steps * B, dtype=torch.uint8, device=D.dev))   # NCCL's first collective of this shape is not a step
+    D.barrier()
+    if sampler:
+        sampler.mark_start("k2")
+    launches0 = eng.launch_count
+    ev = timed_pass()
+    D.barrier()
+    if sampler:
+        sampler.mark_end("k2")
+    ms, gather_ms = ev[0].elapsed_time(ev[2]), ev[1].elapsed_time(ev[2])
+    launches = eng.launch_count - launches0
+    assert eng.forward_status() is None
+
+    # ---- second pass with per-launch CUDA events: kernel times for the roofline (not part of `value`)
+    D.barrier()
+    eng.profile_reset()
+    eng.profile(True)
+    evp = timed_pass()
+    D.barrier()
+    prof = eng.profile_read()
+    eng.profile(False)
+    ms_prof = evp[0].elapsed_time(evp[2])
+    kernel_sum = sum(v[0] for v in prof.values())
+
+    # ---- `e2e`: through the C-ABI host entry point, H2D + D2H inside
+    e2e_pipelined(eng, [(host_batches[i % N_DISTINCT], offsets_p, T, B) for i in range(args.warmup)], B)
+    D.barrier()
+    t0 = time.perf_counter()
+    e2e_pipelined(eng, [(host_batches[i % N_DISTINCT], offsets_p, T, B) for i in range(args.steps)], B)
+    e2e_s = time.perf_counter() - t0
+    # and the plain synchronous call, one batch at a time (what a caller without a pipeline gets)
+    lo = torch.empty(B, 2, dtype=torch.float32).pin_memory()
+    D.barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        eng.predict_host(host_batches[i % N_DISTINCT], offsets_p, T, logits_out=lo, **ENC)
+    e2e_sync_s = time.perf_counter() - t0
+    per_rank = D.gather_floats([ms, gather_ms, ms_prof, kernel_sum, e2e_s * 1e3, e2e_sync_s * 1e3])
+    return {"B": B, "L": L, "T": T, "prof": prof, "launches": launches, "per_rank": per_rank}
+
+
+def run_k5(args, eng, D, sampler):
+    """K5: 32 768-base reads (T = 32 769), batch 64 per GPU, >= 16 batches per GPU; weak scaling."""
+    B, L = args.k5_batch, 32768
+    T = L + 1
+    eng.reserve(B, T)
+    reads = synth.uniform_reads(2 * B, L, synth.K5_SEED + D.rank)
+    offsets_d = torch.arange(0, (B + 1) * L, L, dtype=torch.int64, device=D.dev)
+    dev_batches = [torch.from_numpy(reads[i * B:(i + 1) * B].reshape(-1).copy()).to(D.dev) for i in range(2)]
+    host_batches = [torch.from_numpy(reads[i * B:(i + 1) * B].reshape(-1).copy()).pin_memory() for i in range(2)]
+    offsets_p = torch.arange(0, (B + 1) * L, L, dtype=torch.int64).pin_memory()
+
+    def step(i):
+        ids, _ = eng.encode(dev_batches[i % 2], offsets_d, T, **ENC)
+        return eng.forward(ids, return_labels=True)[1]
+
+    for i in range(2):
+        step(i)
+    D.all_gather(torch.zeros(args.k5_steps * B, dtype=torch.uint8, device=D.dev))
+    D.barrier()
+    if sampler:
+        sampler.mark_start("k5")
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    labels = [step(i) for i in range(args.k5_steps)]
+    D.all_gather(torch.cat(labels))
+    ev1.record()
+    D.barrier()
+    if sampler:
+        sampler.mark_end("k5")
+    ms = ev0.elapsed_time(ev1)
+    assert eng.forward_status() is None
+    eng.profile_reset()
+    eng.profile(True)
+    for i in range(2):
+        step(i)
+    torch.cuda.synchronize()
+    prof = eng.profile_read()
+    eng.profile(False)
+    e2e_pipelined(eng, [(host_batches[0], offsets_p, T, B)], B)
+    D.barrier()
+    t0 = time.perf_counter()
+    n_e2e = max(3, args.k5_steps // 2)
+    e2e_pipelined(eng, [(host_batches[i % 2], offsets_p, T, B) for i in range(n_e2e)], B)
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / n_e2e
+    per_rank = D.gather_floats([ms, e2e_ms])
+    ms_max = max(r[0] for r in per_rank)
+    reads_s = D.world * B * args.k5_steps / (ms_max / 1e3)
+    return {"workload": f"K5: {L} b reads, T={T}, batch {B} per GPU, {args.k5_steps} batches per GPU, weak scaling",
+            "reads_per_s": reads_s, "bases_per_s": reads_s * L, "tokens_per_s": reads_s * T, "ms_per_step": ms_max / args.k5_steps,
+            "ms_per_rank": [r[0] for r in per_rank],
+            "e2e_reads_per_s": D.world * B / (max(r[1] for r in per_rank) / 1e3),
+            "dense_tensor_frac_of_burst_peak": F_TOK * reads_s / D.world * T / 1e12 / peaks()["tflops_burst"],
+            "longconv_kernel": eng.longconv_variant(T),
+            "kernel_ms_per_step": {k: v[0] / 2 for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])}}
+
+
+def run_k3(args, eng, D, sampler):
+    """K3 (N = 1) / K4 (N > 1): log-normal 1-32 kb reads, length-bucketed, token-balanced LPT dealing, final gather."""
+    n = args.k3_reads
+    flat, offsets = synth.k3_reads(n)
+    lens = np.diff(offsets)
+    batches = synth.bucket_batches(lens, K3_MAX_READS, n_special=1, max_tokens_per_batch=K3_TOKEN_CAP)
+    shapes = [(len(b), int(lens[b].max()) + 1) for b in batches]
+    costs = [synth.batch_cost(B, T) for B, T in shapes]
+    ranks, loads = synth.deal_lpt(costs, D.world)
+    mine = ranks[D.rank]
+    eng.reserve(K3_MAX_READS, 32769, K3_TOKEN_CAP)
+    staged = []
+    for bi in mine:   # assemble this rank's batches: contiguous bases + offsets, pinned on the host and resident on the device
+        idx = batches[bi]
+        offs = np.zeros(len(idx) + 1, np.int64)
+        np.cumsum(lens[idx], out=offs[1:])
+        bases = np.concatenate([flat[offsets[i]:offsets[i + 1]] for i in idx])
+        hb, ho = torch.from_numpy(bases).pin_memory(), torch.from_numpy(offs).pin_memory()
+        staged.append((bi, hb, ho, hb.to(D.dev), ho.to(D.dev), shapes[bi]))
+    my_reads = sum(s[5][0] for s in staged)
+    my_tokens = sum(int(lens[batches[s[0]]].sum()) + s[5][0] for s in staged)
+    my_padded = sum(s[5][0] * s[5][1] for s in staged)
+    n_max = max(sum(shapes[b][0] for b in r) for r in ranks)
+
+    def resident(s):
+        ids, _ = eng.encode(s[3], s[4], s[5][1], **ENC)
+        return eng.forward(ids, return_labels=True)[1]
+
+    for s in (staged[:: max(1, len(staged) // 6)] + staged[-1:]):   # warm every kernel variant the sample uses
+        resident(s)
+    D.all_gather(torch.zeros(n_max, 2, dtype=torch.int32, device=D.dev))
+    D.barrier()
+    if sampler:
+        sampler.mark_start("k3")
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    ev[0].record()
+    labels = [resident(s) for s in staged]
+    pairs = torch.zeros(n_max, 2, dtype=torch.int32, device=D.dev)   # (read index, label), padded to the largest rank
+    if staged:
+        idx_dev = torch.from_numpy(np.concatenate([batches[s[0]] for s in staged]).astype(np.int32)).to(D.dev, non_blocking=True)
+        pairs[:my_reads, 0] = idx_dev
+        pairs[:my_reads, 1] = torch.cat(labels).to(torch.int32)
+    pairs[my_reads:, 0] = -1
+    ev[1].record()
+    gathered = D.all_gather(pairs)
+    ev[2].record()
+    D.barrier()
+    if sampler:
+        sampler.mark_end("k3")
+    ms, gather_ms = ev[0].elapsed_time(ev[2]), ev[1].elapsed_time(ev[2])
+    assert eng.forward_status() is None
+    got = torch.cat(gathered)[:, 0]
+    assert sorted(got[got >= 0].tolist()) == list(range(n)), "every read must come back exactly once"
+
+    # e2e: the same batches from pinned host memory through clm_predict_host
+    D.barrier()
+    t0 = time.perf_counter()
+    e2e_pipelined(eng, [(s[1], s[2], s[5][1], s[5][0]) for s in staged], K3_MAX_READS)
+    e2e_ms = (time.perf_counter() - t0) * 1e3
+    per_rank = D.gather_floats([ms, gather_ms, e2e_ms, my_reads, my_tokens, my_padded, float(loads[D.rank])])
+    ms_max = max(r[0] for r in per_rank)
+    tokens = [r[4] for r in per_rank]
+    real_bases = int(lens.sum())
+    return {"workload": f"{'K3' if D.world == 1 else 'K4'}: first {n} reads of the K3 stream (log-normal 1-32 kb, seed {synth.K3_SEED}), "
+                        f"length-bucketed into {len(batches)} batches (<= {K3_MAX_READS} reads, <= {K3_TOKEN_CAP} padded tokens), "
+                        f"LPT-dealt to {D.world} rank(s), final gather of (index, label)",
+            "scaling": "strong", "n_reads": n, "mean_read_len": float(lens.mean()),
+            "reads_per_s": n / (ms_max / 1e3), "bases_per_s": real_bases / (ms_max / 1e3),
+            "e2e_reads_per_s": n / (max(r[2] for r in per_rank) / 1e3), "e2e_bases_per_s": real_bases / (max(r[2] for r in per_rank) / 1e3),
+            "padding_waste": sum(r[5] for r in per_rank) / sum(tokens) - 1.0,
+            "ms_per_rank": [r[0] for r in per_rank], "gather_ms_per_rank": [r[1] for r in per_rank],
+            "tokens_per_rank": tokens, "reads_per_rank": [r[3] for r in per_rank],
+            "token_imbalance_max_over_mean": max(tokens) / (sum(tokens) / len(tokens)),
+            "cost_imbalance_max_over_mean": max(r[6] for r in per_rank) / (sum(r[6] for r in per_rank) / len(per_rank)),
+            "dense_tensor_frac_of_burst_peak": F_TOK * sum(tokens) / D.world / (ms_max / 1e3) / 1e12 / peaks()["tflops_burst"]}
+
+
+def run_label_agreement(device):
+    """Probe-head label agreement against the oracle's golden logits (tests/golden/label_agreement.npz)."""
+    from chimeralm_b200.engine import Engine, pack_reads
+
+    from chimeralm_b200.weights import make_state_dict, perturb_norms
+
+    g = np.load(ROOT / "tests" / "golden" / "label_agreement.npz")
+    sd = dict(perturb_norms(make_state_dict(0), 1))   # the weights the golden logits were generated with (== tests' state_dict)
+    sd["net.head.output_layer.weight"] = torch.from_numpy(g["probe_w"].copy())
+    sd["net.head.output_layer.bias"] = torch.from_numpy(g["probe_b"].copy())
+    eng = Engine(sd, device=device, max_batch=32, max_tokens=32769, token_budget=12 * 32769)
+    logits, labels = [], []
+    t0 = time.perf_counter()
+    for seqs, _ in synth.label_eval_batches():
+        T = max(len(s) for s in seqs) + 1
+        bases, offs = pack_reads([s.tobytes() for s in seqs], pinned=True)
+        ids, _ = eng.encode(bases, offs, T, **ENC)
+        lg, lb = eng.forward(ids, return_labels=True, check=True)
+        logits.append(lg.cpu())
+        labels.append(lb.cpu())
+    dt = time.perf_counter() - t0
+    fallbacks = eng.tc_fallbacks
+    eng.close()
+    got, lab, ref = torch.cat(logits).numpy(), torch.cat(labels).numpy().astype(np.int64), g["logits_probe"]
+    margin = ref[:, 1] - ref[:, 0]
+    ref_lab = (margin > 0).astype(np.int64)
+    return {"label_agreement": float((lab == ref_lab).mean()), "n_reads": int(len(lab)), "n_differ": int((lab != ref_lab).sum()),
+            "logit_max_err": float(np.abs(got - ref).max()), "min_abs_oracle_margin": float(np.abs(margin).min()),
+            "label1_fraction": float(ref_lab.mean()), "fp32_conv_fallbacks": int(fallbacks),
+            "head": "probe (output layer fitted on a calibration draw; every other weight seeded random init) - oracle/make_label_golden.py",
+            "reference": "CPU oracle fp32 logits, tests/golden/label_agreement.npz", "seconds": dt}
+
+
+def run_cli_multi_gpu(world):
+    """The mirrored CLI (`python -m chimeralm_b200 predict --gpus N`, one spawned worker per GPU) against a 1-GPU run on
+    the same BAM.  Reads of equal length: no padding, so a read's logits do not depend on who shares its batch."""
+    from chimeralm_b200.bam import BamWriter, make_record, minimal_header
+    from chimeralm_b200.callbacks import load_predictions_from_folder
+
+    tmp = Path(tempfile.mkdtemp(prefix="clm_cli_"))
+    bam = tmp / "in.bam"
+    seqs, _ = synth.label_reads(96, 31, fixed_len=2000)
+    w = BamWriter(bam, minimal_header())
+    for i, s in enumerate(seqs):
+        w.write(make_record(f"read_{i:04d}", s.tobytes(), sa_tag=True))
+    w.close()
+    outs = {}
+    t0 = time.perf_counter()
+    for g in (1, world):
+        out = tmp / f"pred{g}"
+        r = subprocess.run([sys.executable, "-m", "chimeralm_b200", "predict", str(bam), "-o", str(out), "-b", "16", "--gpus", str(g)],
+                           capture_output=True, text=True, timeout=900, cwd=str(ROOT))
+        if r.returncode != 0:
+            return {"ok": False, "gpus": g, "error": (r.stdout + r.stderr)[-400:]}
+        outs[g] = load_predictions_from_folder(out)
+    files = sorted(p.name for p in (tmp / f"pred{world}").glob("*.txt"))
+    return {"ok": outs[1] == outs[world] and len(outs[1]) == 96, "gpus": world, "reads": len(outs[world]),
+            "identical_to_single_gpu": outs[1] == outs[world], "rank_files": len(files),
+            "ranks_seen": sorted({f.split("_")[0] for f in files}), "seconds": time.perf_counter() - t0}
 
 
 def main():
@@ -177,7 +512,12 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--read-len", type=int, default=READ_LEN)
-    ap.add_argument("--cpu-sample", type=int, default=12, help="reads in the CPU baseline sample (0 = skip)")
+    ap.add_argument("--cpu-sample", type=int, default=96, help="reads in the CPU baseline sample (0 = skip)")
+    ap.add_argument("--k3-reads", type=int, default=24576, help="reads of the K3 stream in the k3 sub-record (0 = skip)")
+    ap.add_argument("--k5-steps", type=int, default=16, help="timed K5 batches per GPU (0 = skip)")
+    ap.add_argument("--k5-batch", type=int, default=64)
+    ap.add_argument("--no-labels", action="store_true", help="skip the label-agreement pass")
+    ap.add_argument("--no-cli", action="store_true", help="skip the 2-GPU CLI check (only runs at --gpus 2)")
     args = ap.parse_args()
 
     from chimeralm_b200.config import DEFAULT_CONFIG as cfg
@@ -190,172 +530,128 @@ def main():
 
     from chimeralm_b200.engine import Engine
 
-    rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    sampler = ClockSampler(local_rank) if rank == 0 else None   # started now, rows outside the timed region are dropped
-    B, L = args.batch, args.read_len
-    T = L + 1
-    eng = Engine(sd, device=local_rank, max_batch=B, max_tokens=T)
+    D = Dist(local_rank)
+    rank, world = D.rank, D.world
+    sampler = ClockSampler(local_rank) if rank == 0 else None   # started now, rows outside the timed regions are dropped
+    eng = Engine(sd, device=local_rank, max_batch=args.batch, max_tokens=args.read_len + 1)
 
-    # synthetic reads: each rank owns its own shard (weak scaling; reads are independent)
-    reads = synth_reads(N_DISTINCT * B, L, SEED + rank)
-    offsets_h = torch.arange(0, (B + 1) * L, L, dtype=torch.int64)
-    dev_batches = [torch.from_numpy(reads[i * B:(i + 1) * B].reshape(-1).copy()).to(dev) for i in range(N_DISTINCT)]
-    host_batches = [torch.from_numpy(reads[i * B:(i + 1) * B].reshape(-1).copy()).pin_memory() for i in range(N_DISTINCT)]
-    offsets_d = offsets_h.to(dev)
-    offsets_p = offsets_h.pin_memory()
-    enc = dict(add_cls=False, add_sep=True, pad_left=True, max_bases=32768)
-
-    def step_resident(i):
-        ids, _ = eng.encode(dev_batches[i % N_DISTINCT], offsets_d, T, **enc)
-        return eng.forward(ids, return_labels=True)
-
-    def barrier():
-        torch.cuda.synchronize()
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    # ---------------- device-resident throughput (`value`)
-    for i in range(args.warmup):
-        step_resident(i)
-    barrier()
-    if sampler:
-        sampler.mark_start()
-    eng.profile_reset()
-    eng.profile(True)
-    launches0 = eng.launch_count
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    all_labels = []
-    ev0.record()
-    for i in range(args.steps):
-        _, labels = step_resident(i)
-        all_labels.append(labels)
-    my_labels = torch.cat(all_labels)
-    if dist is not None:  # the path's only exchange: final gather of predictions
-        gathered = [torch.empty_like(my_labels) for _ in range(world)]
-        dist.all_gather(gathered, my_labels)
-    ev1.record()
-    barrier()
-    if sampler:
-        sampler.mark_end()
-    ms = ev0.elapsed_time(ev1)
-    launches = eng.launch_count - launches0
-    prof = eng.profile_read()
-    eng.profile(False)
-    clocks = sampler.stop() if sampler else None
-    t = torch.tensor([ms], device=dev)
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
-
-    # ---------------- end to end through the C-ABI host entry point (`e2e`)
-    lo = torch.empty(B, 2, dtype=torch.float32).pin_memory()
-    la = torch.empty(B, dtype=torch.uint8).pin_memory()
-    for i in range(args.warmup):
-        eng.predict_host(host_batches[i % N_DISTINCT], offsets_p, T, logits_out=lo, labels_out=la, **enc)
-    barrier()
-    t0 = time.perf_counter()
-    for i in range(args.steps):
-        eng.predict_host(host_batches[i % N_DISTINCT], offsets_p, T, logits_out=lo, labels_out=la, **enc)
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    t = torch.tensor([e2e_s], device=dev)
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_s = float(t.item())
-
+    k2 = run_k2(args, eng, D, sampler)
+    conv_variant = eng.longconv_variant(k2["T"])
+    k5 = run_k5(args, eng, D, sampler) if args.k5_steps > 0 else None
+    k3 = run_k3(args, eng, D, sampler) if args.k3_reads > 0 else None
+    eng.close()
+    D.barrier()
+    D.close()
     if rank != 0:
-        if dist is not None:
-            dist.destroy_process_group()
         return
+    clocks = sampler.stop() if sampler else {}
 
+    B, L, T, prof = k2["B"], k2["L"], k2["T"], k2["prof"]
+    per_rank = k2["per_rank"]   # [ms, gather_ms, ms_profiled, kernel_sum_ms, e2e_ms] per rank
+    ms_max = max(r[0] for r in per_rank)
+    slow = max(range(world), key=lambda r: per_rank[r][0])
     reads_per_s = world * B * args.steps / (ms_max / 1e3)
+    e2e_s = max(r[4] for r in per_rank) / 1e3
     tokens_per_step = B * T
     pk = peaks()
-    # dominant kernel class by device time
-    dom = max(prof.items(), key=lambda kv: kv[1][0])
-    dom_name, (dom_ms, dom_n) = dom
     total_prof_ms = sum(v[0] for v in prof.values())
-    per_launch_s = dom_ms / dom_n / 1e3
     # algorithmic work per token per launch
     flop_per_tok = {"gemm_in_proj": 2 * 256 * 768, "gemm_out_proj": 2 * 256 * 256, "gemm_fc1": 2 * 256 * 1024,
-                    "gemm_fc2": 2 * 1024 * 256, "gemm_score": 2 * 256 * 256 + 2 * 256,
-                    "block_in": 2 * 256 * 768, "block_mlp": 2 * 256 * 256 + 2 * 256 * 1024 + 2 * 1024 * 256}
+                    "gemm_fc2": 2 * 1024 * 256, "block_in": 2 * 256 * 768,
+                    "block_mlp": 2 * 256 * 256 + 2 * 256 * 1024 + 2 * 1024 * 256}
     bytes_per_tok = {"longconv": CONV_BYTES_TOK_LAYER, "layernorm": 1024 + 512, "shortconv_gate": 1536 + 1024,
-                     "transpose": 1024, "pool": 516, "embed": 1 + 1024 + 512, "encode": 2, "head": 0}
-    traffic = {}
-    tp = ROOT / "profiles" / "r1_traffic.json"
-    if tp.exists() and B == BATCH and L == READ_LEN:
-        traffic = {k: v for k, v in json.loads(tp.read_text()).items() if not k.startswith("_")}
-
-    conv_variant = eng.longconv_variant(T)
-    if conv_variant == "fft_tensor_core":
-        # Monarch FFT on tcgen05 (csrc/longconv_tc.cuh): per item (one channel of two reads) 16 MMAs 128x128x16 + 2 x 16 MMAs
-        # 128x256x16 + 32 MMAs 128xN7x16 (N7 = 80 when T > 8192, else 64); 256 * ceil(B / 2) items per launch.
-        n7 = 80 if T > 8192 else 64
-        item_flop = 2 * 16 * (16 * 128 * 128 + 2 * 16 * 128 * 256 + 32 * 128 * n7)
-        flop_per_tok["longconv"] = item_flop * 256 * ((B + 1) // 2) / tokens_per_step
+                     "transpose": 1024, "pool": 516, "embed": 1 + 1024 + 512, "encode": 2, "head": 0,
+                     "gemm_score": 512}   # fused scorer + pooling: the normalised tokens are read once (bf16)
+    traffic, traffic_src = {}, None
+    for name in ("r2_traffic.json", "r1_traffic.json"):
+        tp = ROOT / "profiles" / name
+        if tp.exists() and B == BATCH and L == READ_LEN:
+            traffic = {k: v for k, v in json.loads(tp.read_text()).items() if not k.startswith("_")}
+            traffic_src = f"profiles/{name}: dram__bytes_read.sum + dram__bytes_write.sum per launch from a committed `ncu --set full` capture of this workload (not measured in this run)"
+            break
 
     def roofline_of(name, ms, n):
         sec = ms / n / 1e3
         if name in flop_per_tok:
             ach = flop_per_tok[name] * tokens_per_step / sec / 1e12
-            r = {"bound": "tensor", "achieved": ach, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": ach / pk["tflops"]}
+            r = {"bound": "tensor", "achieved": ach, "peak": pk["tflops_burst"], "unit": "TFLOP/s", "frac": ach / pk["tflops_burst"],
+                 "frac_of_sustained_peak": ach / pk["tflops_sustained"]}
         else:
             ach = bytes_per_tok.get(name, 0) * tokens_per_step / sec / 1e9
             r = {"bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"]}
         r.update({"kernel": name, "traffic": traffic.get(name), "avg_launch_ms": ms / n, "share_of_step": ms / total_prof_ms})
         return r
 
+    dom_name, (dom_ms, dom_n) = max(prof.items(), key=lambda kv: kv[1][0])
     roof = roofline_of(dom_name, dom_ms, dom_n)
-    roof["peak_source"] = pk["src"]
-    if dom_name == "longconv" and conv_variant != "fft_tensor_core":
-        roof["note"] = ("HBM roofline per SURVEY 8(d)'s compulsory-traffic model (1536 B/token/layer); the kernel itself is bound by "
-                        "fp32 FFT instruction issue (ncu: issue-active ~50%, DRAM ~9%), see profiles/r1_v6_longconv_fast.txt")
+    roof["peak_source"] = pk["src"] + ("; burst bf16 figure: the timed region is a fraction of a second, not a power-capped long step"
+                                       if roof["bound"] == "tensor" else "")
+    roof["traffic_source"] = traffic_src
     rooflines = {k: roofline_of(k, v[0], v[1]) for k, v in prof.items() if k in ("longconv", "block_mlp", "block_in", "gemm_score")}
-    dense_frac = F_TOK * (reads_per_s / world) * T / 1e12 / pk["tflops"]
+    if "longconv" in rooflines and conv_variant == "fft_tensor_core":
+        # Monarch FFT on tcgen05 (csrc/longconv_tc.cuh): per item (one channel of two reads) 16 MMAs 128x128x16 + 2 x 16 MMAs
+        # 128x256x16 + 32 MMAs 128xN7x16 (N7 = 80 when T > 8192, else 64); 256 * ceil(B / 2) items per launch.  These are
+        # EXECUTED fp16 tensor FLOPs (22x the algorithmic FFT count): a pipe-utilisation figure, not a roofline fraction.
+        n7 = 80 if T > 8192 else 64
+        item_flop = 2 * 16 * (16 * 128 * 128 + 2 * 16 * 128 * 256 + 32 * 128 * n7)
+        sec = rooflines["longconv"]["avg_launch_ms"] / 1e3
+        rooflines["longconv"]["tensor_pipe_executed_tflops"] = item_flop * 256 * ((B + 1) // 2) / sec / 1e12
+    dense_tflops = F_TOK * (reads_per_s / world) * T / 1e12
 
     cpu = None
     if args.cpu_sample > 0:
         torch.set_num_threads(os.cpu_count() or 1)
-        sample = synth_reads(args.cpu_sample, L, SEED)
-        v, t_tok, t_fwd, cpu_labels = cpu_reference_path(sd, cfg, sample)
+        sample = synth.uniform_reads(args.cpu_sample, L, synth.K2_SEED)
+        v, t_tok, t_fwd, _ = cpu_reference_path(sd, cfg, sample)
         cpu = {"value": v, "unit": "reads/s", "cores": torch.get_num_threads(), "kind": "port",
-               "sample": f"{args.cpu_sample} reads x {L} b, batch 12; tokenise {t_tok:.2f}s + forward {t_fwd:.2f}s",
+               "sample": f"{args.cpu_sample} reads x {L} b of the K2 stream, batch 12 (the reference CLI default); tokenise {t_tok:.2f}s + forward {t_fwd:.2f}s",
                "torch": torch.__version__}
+    labels = None if args.no_labels else run_label_agreement(local_rank)
+    cli = run_cli_multi_gpu(world) if (world == 2 and not args.no_cli) else None
 
     line = {
         "metric": "predict_reads_per_s", "value": reads_per_s, "unit": "reads/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": workload_config(L, T, B, world),
-        "dtype_note": "bf16 GEMM operands, fp16 operands in the tensor-core FFT conv, fp32 accumulation / residual / pooling / head",
+        "dtype_note": "bf16 GEMM operands, fp16 operands in the tensor-core FFT conv (power-of-two range scaling, fp32 fallback on overflow), "
+                      "fp32 accumulation / residual / pooling / head",
         "bases_per_s": reads_per_s * L,
         "tokens_per_s": reads_per_s * T,
-        "dense_tensor_frac_of_peak": dense_frac,
+        "dense_tensor_tflops_per_gpu": dense_tflops,
+        "dense_tensor_frac_of_burst_peak": dense_tflops / pk["tflops_burst"],
+        "dense_tensor_frac_of_sustained_peak": dense_tflops / pk["tflops_sustained"],
         "e2e": {"value": world * B * args.steps / e2e_s, "unit": "reads/s", "h2d_bytes_per_step": B * L + (B + 1) * 8,
-                "d2h_bytes_per_step": B * 2 * 4 + B, "api": "clm_predict_host (C-ABI, pinned host buffers)"},
-        "gpu_launches": int(launches),
+                "d2h_bytes_per_step": B * 2 * 4 + B,
+                "api": "clm_predict_host_submit / clm_predict_host_wait (C-ABI, pinned host buffers, up to 3 batches in flight)",
+                "one_batch_at_a_time": {"value": world * B * args.steps / (max(r[5] for r in per_rank) / 1e3), "unit": "reads/s",
+                                        "api": "clm_predict_host (submit + wait per batch)"}},
+        "gpu_launches": int(k2["launches"]),
         "roofline": roof,
         "rooflines_top_kernels": rooflines,
         "longconv_kernel": conv_variant,
         "kernel_ms_per_step": {k: v[0] / args.steps for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])},
+        "kernel_ms_per_step_note": "rank 0, from the second (profiled) pass; `value` comes from the first, un-profiled pass",
+        "ms_per_rank": [r[0] / args.steps for r in per_rank],
+        "gather_ms_per_rank": [r[1] for r in per_rank],
+        "slowest_rank": {"rank": slow, "ms_per_step": per_rank[slow][0] / args.steps,
+                         "kernel_sum_ms_per_step": per_rank[slow][3] / args.steps,
+                         "profiled_pass_ms_per_step": per_rank[slow][2] / args.steps},
+        "label_agreement": labels["label_agreement"] if labels else None,
+        "n_reads": labels["n_reads"] if labels else None,
+        "logit_max_err": labels["logit_max_err"] if labels else None,
+        "labels": labels,
+        "k3": k3,
+        "k5": k5,
+        "cli_multi_gpu": cli,
         "cpu_baseline": cpu,
-        "clocks": clocks,
+        "clocks": clocks.get("k2"),
+        "clocks_k3": clocks.get("k3"),
+        "clocks_k5": clocks.get("k5"),
     }
     print(json.dumps(line))
-    if dist is not None:
-        dist.destroy_process_group()
 
 
 if __name__ == "__main__":

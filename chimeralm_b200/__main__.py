@@ -92,7 +92,7 @@ def predict(
 
 def filter_bam_by_predcition(bam_path: Path, prediction_path: Path, *, index: bool = True, output_prediction: bool = False) -> None:
     """`chimeralm/__main__.py:99-153`: drop reads predicted 1, keep reads without a prediction."""
-    from .bam import BamReader, BamWriter, coordinate_sorted_header
+    from .bam import BamReader, BamWriter, coordinate_sorted_header, sorted_records_external
     from .callbacks import load_predictions_from_folder
 
     predictions = load_predictions_from_folder(prediction_path)
@@ -109,26 +109,35 @@ def filter_bam_by_predcition(bam_path: Path, prediction_path: Path, *, index: bo
     log.info(f"Biological: {counter.get(0, 0)} ({counter.get(0, 0) / len(predictions) * 100:.1f}%), "
              f"Chimera artifact: {counter.get(1, 0)} ({counter.get(1, 0) / len(predictions) * 100:.1f}%)")
     output_path = bam_path.with_suffix(".filtered.bam")
+    run_bytes = int(os.environ.get("CLM_SORT_RUN_BYTES", 256 << 20))
     try:
         with BamReader(bam_path) as bam:
             out = BamWriter(output_path, bam.header_bytes())
-            kept = []
-            for read in bam:
-                if predictions.get(read.name) == 1:
-                    continue
-                out.write(read)
-                kept.append(read)
-            out.close()
+
+            def kept():
+                for read in bam:
+                    # The reference iterates `bam_file.fetch()` (chimeralm/__main__.py:131), which is index-driven and
+                    # yields placed reads only: records without a reference (refID -1, the unplaced tail of the file) are
+                    # not copied.  A placed read with the unmapped flag (a mate stored at its partner's position) is.
+                    if read.ref_id < 0:
+                        continue
+                    if predictions.get(read.name) == 1:
+                        continue
+                    out.write(read)
+                    yield read
+
             if index:
-                # `samtools sort` order: refID as unsigned (unplaced reads last), position, forward strand first;
-                # Python's sort is stable, so ties keep file order
+                # sorted with bounded memory (runs of CLM_SORT_RUN_BYTES spilled to disk and merged), like `samtools sort`
                 sorted_path = output_path.with_suffix(".sorted.bam")
                 log.info(f"Sorting {output_path}")
-                kept.sort(key=lambda r: ((r.ref_id & 0xFFFFFFFF), r.pos + 1, (r.flag >> 4) & 1))
                 so = BamWriter(sorted_path, coordinate_sorted_header(bam))
-                for r in kept:
+                for r in sorted_records_external(kept(), run_bytes=run_bytes, tmpdir=str(output_path.parent)):
                     so.write(r)
                 so.close()
+            else:
+                for _ in kept():
+                    pass
+            out.close()
         if index:
             from .bai import index_bam
 

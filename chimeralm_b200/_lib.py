@@ -51,6 +51,9 @@ _SIGNATURES = {
     "clm_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "clm_predict_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                    C.c_int, C.c_void_p, C.c_void_p]),
+    "clm_predict_host_submit": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                          C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]),
+    "clm_predict_host_wait": (C.c_int, [C.c_void_p, C.c_int]),
     "clm_forward_seq": (C.c_longlong, [C.c_void_p]),
     "clm_forward_status": (C.c_int, [C.c_void_p, C.c_longlong]),
     "clm_tc_fallback_count": (C.c_longlong, [C.c_void_p]),

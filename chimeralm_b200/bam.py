@@ -120,11 +120,7 @@ class BamReader:
             raw = f.read(block_size)
             if len(raw) < block_size:
                 raise ValueError("truncated BAM record")
-            ref_id, pos, l_read_name, _mapq, _bin, n_cigar, flag, l_seq = struct.unpack_from("<iiBBHHHi", raw, 0)
-            name = raw[32 : 32 + l_read_name - 1].decode("ascii", "replace")
-            seq_off = 32 + l_read_name + 4 * n_cigar
-            aux_off = seq_off + (l_seq + 1) // 2 + l_seq
-            yield BamRecord(ref_id, pos, flag, name, l_seq, raw, seq_off, aux_off)
+            yield record_from_raw(raw)
 
     def close(self):
         self.f.close()
@@ -134,6 +130,69 @@ class BamReader:
 
     def __exit__(self, *a):
         self.close()
+
+
+def record_from_raw(raw: bytes) -> BamRecord:
+    """Parse the fixed part of one BAM record (everything after its block_size field)."""
+    ref_id, pos, l_read_name, _mapq, _bin, n_cigar, flag, l_seq = struct.unpack_from("<iiBBHHHi", raw, 0)
+    name = raw[32 : 32 + l_read_name - 1].decode("ascii", "replace")
+    seq_off = 32 + l_read_name + 4 * n_cigar
+    aux_off = seq_off + (l_seq + 1) // 2 + l_seq
+    return BamRecord(ref_id, pos, flag, name, l_seq, raw, seq_off, aux_off)
+
+
+def samtools_sort_key(r: BamRecord):
+    """`samtools sort` coordinate order: refID as unsigned (unplaced reads last), position, forward strand first."""
+    return ((r.ref_id & 0xFFFFFFFF), r.pos + 1, (r.flag >> 4) & 1)
+
+
+def sorted_records_external(records, run_bytes: int = 256 << 20, tmpdir=None) -> Iterator[BamRecord]:
+    """Coordinate-sort a stream of records with bounded memory, the way `samtools sort` (which the reference calls
+    through `pysam.sort`, chimeralm/__main__.py:148) does: sorted runs of at most `run_bytes` of record data are spilled
+    to temporary files and merged k-way; ties keep input order (every record carries its arrival number).  A stream
+    that fits one run never touches the disk."""
+    import heapq
+    import tempfile
+
+    runs, cur, cur_bytes, seq = [], [], 0, 0
+
+    def spill():
+        nonlocal cur, cur_bytes
+        cur.sort(key=lambda t: t[0])
+        f = tempfile.TemporaryFile(dir=tmpdir, prefix="clm_sort_run_")
+        for (_k, n, raw) in cur:
+            f.write(struct.pack("<qi", n, len(raw)))
+            f.write(raw)
+        f.seek(0)
+        runs.append(f)
+        cur, cur_bytes = [], 0
+
+    for r in records:
+        cur.append((samtools_sort_key(r) + (seq,), seq, r.raw))
+        cur_bytes += len(r.raw) + 64
+        seq += 1
+        if cur_bytes >= run_bytes:
+            spill()
+    if not runs:
+        cur.sort(key=lambda t: t[0])
+        for (_k, _n, raw) in cur:
+            yield record_from_raw(raw)
+        return
+    if cur:
+        spill()
+
+    def read_run(f):
+        while True:
+            head = f.read(12)
+            if len(head) < 12:
+                f.close()
+                return
+            n, size = struct.unpack("<qi", head)
+            rec = record_from_raw(f.read(size))
+            yield samtools_sort_key(rec) + (n,), rec
+
+    for _k, rec in heapq.merge(*(read_run(f) for f in runs), key=lambda t: t[0]):
+        yield rec
 
 
 def coordinate_sorted_header(bam: "BamReader") -> bytes:

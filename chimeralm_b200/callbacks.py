@@ -12,6 +12,7 @@ import logging
 from pathlib import Path
 from typing import Any
 
+import numpy as np
 import torch
 
 logger = logging.getLogger(__name__)
@@ -32,6 +33,32 @@ def resume_read_name(bytes_data) -> str:
         return "".join(chr(b) for b in bytes_data[1 : 1 + n] if 32 <= b <= 126)
     except (IndexError, TypeError, ValueError) as e:
         raise ValueError("Invalid read name data") from e
+
+
+def resume_read_names(batch_ids) -> list:
+    """`resume_read_name` for a whole `[B, 256]` int8 batch in one numpy pass; an entry is the name, or the ValueError the
+    scalar function would have raised for that row (bad length byte)."""
+    a = batch_ids.numpy() if isinstance(batch_ids, torch.Tensor) else np.asarray(batch_ids)
+    if a.ndim != 2 or a.shape[1] < 2:
+        return [_try_resume(r) for r in batch_ids]
+    a = a.astype(np.int64)
+    n = a[:, 0]
+    keep = (np.arange(1, a.shape[1])[None, :] <= n[:, None]) & (a[:, 1:] >= 32) & (a[:, 1:] <= 126)
+    chars = np.where(keep, a[:, 1:], 0).astype(np.uint8)
+    out = []
+    for i in range(a.shape[0]):
+        if n[i] <= 0 or n[i] >= a.shape[1]:
+            out.append(ValueError("Invalid read name data"))
+        else:
+            out.append(chars[i][keep[i]].tobytes().decode("ascii"))
+    return out
+
+
+def _try_resume(row):
+    try:
+        return resume_read_name(row)
+    except ValueError as e:
+        return e
 
 
 class PredictionWriter:
@@ -61,21 +88,20 @@ class PredictionWriter:
                 logger.error(f"Size mismatch: predictions={len(predictions_cpu)}, batch_ids={len(batch_ids)} for batch {batch_idx}")
                 return
             read_names = []
-            for i, batch_id in enumerate(batch_ids):
-                try:
-                    name = resume_read_name(batch_id)
-                    if not name:
-                        name = f"unknown_read_{i}"
-                        logger.warning(f"Empty read name for index {i} in batch {batch_idx}")
-                    read_names.append(name)
-                except Exception as e:  # noqa: BLE001 - reference behaviour: log and continue
-                    logger.error(f"Error processing read name at index {i}: {e}")
+            for i, name in enumerate(resume_read_names(batch_ids)):   # same rule as resume_read_name per row, vectorised
+                if isinstance(name, Exception):   # reference behaviour: log and continue
+                    logger.error(f"Error processing read name at index {i}: {name}")
                     read_names.append(f"error_read_{i}")
+                    continue
+                if not name:
+                    name = f"unknown_read_{i}"
+                    logger.warning(f"Empty read name for index {i} in batch {batch_idx}")
+                read_names.append(name)
             if not self.output_dir.exists():
                 self.output_dir.mkdir(parents=False, exist_ok=True)
             output_file = self.output_dir / f"{trainer.global_rank}_{batch_idx}.txt"
             try:
-                lines = [f"{n}\t{p.item()}\n" for n, p in zip(read_names, predictions_cpu, strict=True)]
+                lines = [f"{n}\t{p}\n" for n, p in zip(read_names, predictions_cpu.tolist(), strict=True)]
                 with output_file.open("w") as f:
                     f.writelines(lines)
             except OSError as e:

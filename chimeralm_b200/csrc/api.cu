@@ -120,12 +120,27 @@ struct clm_ctx {
   int n_split = 1;
   // e2e staging
   cudaStream_t own_stream = nullptr;
-  uint8_t* st_bases = nullptr;
+  // Staging of the host entry points: HOST_SLOTS independent sets, so that clm_predict_host_submit can copy and enqueue
+  // batch k + 1 (and k + 2) while batch k is still running; slot 0's buffers double as the calibration forward's.
+  static constexpr int HOST_SLOTS = 3;
+  struct HostSlot {
+    uint8_t* bases = nullptr;
+    int64_t* offsets = nullptr;
+    uint8_t* ids = nullptr;
+    float* logits = nullptr;
+    uint8_t* labels = nullptr;
+    cudaEvent_t done = nullptr;
+    bool busy = false;
+    long long seq = 0;
+    int B = 0, T = 0;
+    float* h_logits = nullptr;
+    uint8_t* h_labels = nullptr;
+  } slot[HOST_SLOTS];
+  int next_slot = 0;
   size_t st_bases_cap = 0;
-  int64_t* st_offsets = nullptr;
-  uint8_t* st_ids = nullptr;
-  float* st_logits = nullptr;
-  uint8_t* st_labels = nullptr;
+  uint8_t*& st_ids = slot[0].ids;
+  float*& st_logits = slot[0].logits;
+  uint8_t*& st_labels = slot[0].labels;
   // per-kernel-class device timing (CUDA events on the launching stream)
   bool prof_on = false;
   std::vector<cudaEvent_t> prof_pool;
@@ -153,6 +168,7 @@ struct clm_ctx {
   int mlp_fc2_lag = 1;    // block_mlp: fc2 of chunk j - lag is issued after fc1 of chunk j (2: recorded experiment, no faster)
   int mlp_grid = 0;       // block_mlp: cap on the number of CTAs (0 = one per SM); diagnostic
   bool mlp_pp = false;    // fused block tail with two interleaved fc1/GELU/fc2 chains of 64-unit chunks (block_mlp_pp.cuh)
+  bool skip_dead_res = true;    // the last block does not store its fp32 residual (nothing reads it)
   bool y_channel_major = true;  // block_mlp reads the conv output channel-major (MN-major UMMA operand): no transpose
   // debug
   int dbg_layer = -1, dbg_stage = -1;
@@ -221,7 +237,10 @@ template <typename T>
 int dev_alloc(clm_ctx* c, T** p, size_t count) {
   void* q = nullptr;
   cudaError_t e = cudaMalloc(&q, count * sizeof(T) + 256);
-  if (e != cudaSuccess) return fail(c, CLM_ERR_NOMEM, "cudaMalloc(%zu bytes) failed: %s", count * sizeof(T), cudaGetErrorString(e));
+  if (e != cudaSuccess) {
+    cudaGetLastError();   // clear the (non-sticky) error: the next launch check must not report this allocation failure
+    return fail(c, CLM_ERR_NOMEM, "cudaMalloc(%zu bytes) failed: %s", count * sizeof(T), cudaGetErrorString(e));
+  }
   c->owned.push_back(q);
   *p = reinterpret_cast<T*>(q);
   return 0;
@@ -401,7 +420,8 @@ int launch_block_in(clm_ctx* c, int layer, const __nv_bfloat16* xn, int B, int T
 
 // y token-major [M,256] when B == 0; channel-major [B][256][Tp] (M == B*T) otherwise
 int launch_block_mlp(clm_ctx* c, int layer, const __nv_bfloat16* y, float* res, int M, cudaStream_t st,
-                     long long* trace = nullptr, int B = 0, int T = 0, int Tp = 0, __nv_bfloat16* xn_out = nullptr) {
+                     long long* trace = nullptr, int B = 0, int T = 0, int Tp = 0, __nv_bfloat16* xn_out = nullptr,
+                     bool skip_res_store = false) {
   if (int rc_c = bind_constants(c, st)) return rc_c;
   LayerW& L = c->layers[layer];
   CUtensorMap tmY;
@@ -423,6 +443,7 @@ int launch_block_mlp(clm_ctx* c, int layer, const __nv_bfloat16* y, float* res, 
   p.num_tiles = (M + bm::BM - 1) / bm::BM;
   p.trace = trace;
   p.stagger_cycles = c->mlp_stagger;
+  p.skip_res_store = (skip_res_store && xn_out) ? 1 : 0;
   if (B > 0) {
     p.y_cm = 1; p.T = T; p.tiles_per_seq = (T + bm::BM - 1) / bm::BM; p.num_tiles = B * p.tiles_per_seq;
   }
@@ -808,6 +829,8 @@ void clm_destroy(clm_ctx* c) {
   for (cudaEvent_t e : c->prof_pool) cudaEventDestroy(e);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
   if (c->h_status) cudaFreeHost(c->h_status);
+  for (auto& sl : c->slot)
+    if (sl.done) cudaEventDestroy(sl.done);
   delete c;
 }
 
@@ -1068,8 +1091,12 @@ int clm_reserve_tokens(clm_ctx* c, int max_B, int max_T, long long max_tokens) {
   c->scratch_bytes = 0; c->tc_scratch_floats = 0; c->st_bases_cap = 0;
   dev_release(c, &c->R); dev_release(c, &c->XN); dev_release(c, &c->U); dev_release(c, &c->VX); dev_release(c, &c->X0);
   dev_release(c, &c->Y); dev_release(c, &c->YT); dev_release(c, &c->score); dev_release(c, &c->part);
-  dev_release(c, &c->pooled); dev_release(c, &c->scratch); dev_release(c, &c->tc_scratch); dev_release(c, &c->st_offsets);
-  dev_release(c, &c->st_ids); dev_release(c, &c->st_logits); dev_release(c, &c->st_labels); dev_release(c, &c->st_bases);
+  dev_release(c, &c->pooled); dev_release(c, &c->scratch); dev_release(c, &c->tc_scratch);
+  for (auto& sl : c->slot) {
+    dev_release(c, &sl.bases); dev_release(c, &sl.offsets); dev_release(c, &sl.ids); dev_release(c, &sl.logits);
+    dev_release(c, &sl.labels);
+    sl.busy = false;
+  }
   for (int i = 0; i < 4; ++i) dev_release(c, &c->hbuf[i]);
   const int D = c->cfg.d_model;
   // token-proportional buffers are sized by the token budget, per-read ones by max_B: a context that serves length
@@ -1111,11 +1138,14 @@ int clm_reserve_tokens(clm_ctx* c, int max_B, int max_T, long long max_tokens) {
     }
   }
   // staging of clm_predict_host (sized here: nothing is allocated on the forward path)
-  if ((rc = dev_alloc(c, &c->st_offsets, (size_t)max_B + 1))) return rc;
-  if ((rc = dev_alloc(c, &c->st_ids, M))) return rc;
-  if ((rc = dev_alloc(c, &c->st_logits, (size_t)max_B * 2))) return rc;
-  if ((rc = dev_alloc(c, &c->st_labels, (size_t)max_B))) return rc;
-  if ((rc = dev_alloc(c, &c->st_bases, M))) return rc;   // a read contributes at most one base per token
+  for (auto& sl : c->slot) {
+    if ((rc = dev_alloc(c, &sl.offsets, (size_t)max_B + 1))) return rc;
+    if ((rc = dev_alloc(c, &sl.ids, M))) return rc;
+    if ((rc = dev_alloc(c, &sl.logits, (size_t)max_B * 2))) return rc;
+    if ((rc = dev_alloc(c, &sl.labels, (size_t)max_B))) return rc;
+    if ((rc = dev_alloc(c, &sl.bases, M))) return rc;   // a read contributes at most one base per token
+    if (!sl.done) CLM_CUDA(c, cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
+  }
   c->st_bases_cap = M;
   c->max_B = max_B; c->max_T = max_T; c->Tp_max = Tp;   // only now: every workspace exists
   c->max_tokens = max_tokens; c->ct_elems = CT;
@@ -1220,8 +1250,10 @@ int clm_forward(clm_ctx* c, const void* d_ids, int ids_dtype, int B, int T, floa
     STOP_AFTER(l, 5);
     if (mlp_fused) {
       ProfScope ps_(c, PC_BLOCK_MLP, st);
-      if (c->y_channel_major) rc = launch_block_mlp(c, l, c->Y, c->R, (int)M, st, nullptr, B, T, Tp, c->XN);
-      else rc = launch_block_mlp(c, l, c->YT, c->R, (int)M, st, nullptr, 0, 0, 0, c->XN);
+      // the last block's residual has no reader on the folded tail (scorer + pooling read xn); any debug stop keeps it
+      const bool dead_res = l == g.n_layer - 1 && c->dbg_layer < 0 && c->skip_dead_res;
+      if (c->y_channel_major) rc = launch_block_mlp(c, l, c->Y, c->R, (int)M, st, nullptr, B, T, Tp, c->XN, dead_res);
+      else rc = launch_block_mlp(c, l, c->YT, c->R, (int)M, st, nullptr, 0, 0, 0, c->XN, dead_res);
       if (rc) return rc;
       xn_valid = true;
     } else {
@@ -1352,41 +1384,69 @@ int clm_forward_status(clm_ctx* c, long long seq) {
   return 0;
 }
 
-int clm_predict_host(clm_ctx* c, const uint8_t* h_bases, const int64_t* h_offsets, int B, int T_pad, int add_cls,
-                     int add_sep, int pad_left, int max_bases, float* h_logits, uint8_t* h_labels) {
-  if (!c || !h_bases || !h_offsets || !h_logits || B <= 0) return fail(c, CLM_ERR_INVALID, "clm_predict_host: bad argument");
+int clm_predict_host_submit(clm_ctx* c, const uint8_t* h_bases, const int64_t* h_offsets, int B, int T_pad, int add_cls,
+                            int add_sep, int pad_left, int max_bases, float* h_logits, uint8_t* h_labels, int* ticket) {
+  if (!c || !h_bases || !h_offsets || !h_logits || !ticket || B <= 0) return fail(c, CLM_ERR_INVALID, "clm_predict_host: bad argument");
   if (B > c->max_B || T_pad > c->max_T || (long long)B * T_pad > c->max_tokens)
     return fail(c, CLM_ERR_STATE, "clm_predict_host: batch %dx%d exceeds reserved %dx%d (%lld tokens)", B, T_pad, c->max_B, c->max_T, c->max_tokens);
   CLM_CUDA(c, cudaSetDevice(c->device));
   const size_t nbytes = (size_t)h_offsets[B];
-  // the staging buffer was sized by clm_reserve (max_B * max_T bases); nothing is allocated here.  Bases beyond
-  // max_bases per read are never looked at by the encoder, but they still have to fit the copy.
+  // the staging buffers were sized by clm_reserve (one base per token of the budget); nothing is allocated here.  Bases
+  // beyond max_bases per read are never looked at by the encoder, but they still have to fit the copy.
   if (nbytes > c->st_bases_cap)
     return fail(c, CLM_ERR_STATE, "clm_predict_host: %zu bases exceed the staging buffer of %zu reserved by clm_reserve(%d, %d); "
                 "truncate the reads to max_bases on the host or reserve more", nbytes, c->st_bases_cap, c->max_B, c->max_T);
+  clm_ctx::HostSlot& sl = c->slot[c->next_slot];
+  if (sl.busy) return fail(c, CLM_ERR_STATE, "clm_predict_host_submit: %d batches are already in flight; call clm_predict_host_wait", clm_ctx::HOST_SLOTS);
   cudaStream_t st = c->own_stream;
-  CLM_CUDA(c, cudaMemcpyAsync(c->st_bases, h_bases, nbytes, cudaMemcpyHostToDevice, st));
-  CLM_CUDA(c, cudaMemcpyAsync(c->st_offsets, h_offsets, (size_t)(B + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
-  int rc = clm_encode_batch(c, c->st_bases, c->st_offsets, B, T_pad, add_cls, add_sep, pad_left, max_bases, c->st_ids, nullptr, st);
+  CLM_CUDA(c, cudaMemcpyAsync(sl.bases, h_bases, nbytes, cudaMemcpyHostToDevice, st));
+  CLM_CUDA(c, cudaMemcpyAsync(sl.offsets, h_offsets, (size_t)(B + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+  int rc = clm_encode_batch(c, sl.bases, sl.offsets, B, T_pad, add_cls, add_sep, pad_left, max_bases, sl.ids, nullptr, st);
   if (rc) return rc;
-  struct Restore {   // the fallback below switches the tensor-core conv off for ONE batch only
+  rc = clm_forward(c, sl.ids, CLM_U8, B, T_pad, sl.logits, sl.labels, st);
+  if (rc) return rc;
+  CLM_CUDA(c, cudaMemcpyAsync(h_logits, sl.logits, (size_t)B * 2 * sizeof(float), cudaMemcpyDeviceToHost, st));
+  if (h_labels) CLM_CUDA(c, cudaMemcpyAsync(h_labels, sl.labels, (size_t)B, cudaMemcpyDeviceToHost, st));
+  CLM_CUDA(c, cudaEventRecord(sl.done, st));
+  sl.busy = true; sl.seq = c->fwd_seq; sl.B = B; sl.T = T_pad; sl.h_logits = h_logits; sl.h_labels = h_labels;
+  *ticket = c->next_slot;
+  c->next_slot = (c->next_slot + 1) % clm_ctx::HOST_SLOTS;
+  return 0;
+}
+
+int clm_predict_host_wait(clm_ctx* c, int ticket) {
+  if (!c || ticket < 0 || ticket >= clm_ctx::HOST_SLOTS) return fail(c, CLM_ERR_INVALID, "clm_predict_host_wait: bad ticket");
+  clm_ctx::HostSlot& sl = c->slot[ticket];
+  if (!sl.busy) return fail(c, CLM_ERR_STATE, "clm_predict_host_wait: ticket %d is not in flight", ticket);
+  sl.busy = false;
+  CLM_CUDA(c, cudaSetDevice(c->device));
+  CLM_CUDA(c, cudaEventSynchronize(sl.done));
+  if (c->dbg_layer >= 0) return 0;   // stopped early: no status was published
+  int rc = clm_forward_status(c, sl.seq);
+  if (rc != CLM_ERR_FP16_RANGE || !c->tc_conv) return rc;
+  // automatic switch: this batch left the fp16 range of the tensor-core convolution - redo it with the fp32 FFT kernel
+  // (its token ids are still in the slot; later batches already queued on the stream are not disturbed)
+  struct Restore {
     clm_ctx* c; bool tc;
     ~Restore() { c->tc_conv = tc; }
   } restore{c, c->tc_conv};
-  for (int attempt = 0; attempt < 2; ++attempt) {
-    rc = clm_forward(c, c->st_ids, CLM_U8, B, T_pad, c->st_logits, c->st_labels, st);
-    if (rc) return rc;
-    CLM_CUDA(c, cudaMemcpyAsync(h_logits, c->st_logits, (size_t)B * 2 * sizeof(float), cudaMemcpyDeviceToHost, st));
-    if (h_labels) CLM_CUDA(c, cudaMemcpyAsync(h_labels, c->st_labels, (size_t)B, cudaMemcpyDeviceToHost, st));
-    CLM_CUDA(c, cudaStreamSynchronize(st));
-    if (c->dbg_layer >= 0) return 0;   // stopped early: no status was published
-    rc = clm_forward_status(c, c->fwd_seq);
-    if (rc != CLM_ERR_FP16_RANGE || attempt == 1 || !c->tc_conv) return rc;
-    // automatic switch: this batch left the fp16 range of the tensor-core convolution - redo it with the fp32 FFT kernel
-    c->tc_conv = false;
-    c->tc_fallbacks++;
-  }
-  return rc;
+  c->tc_conv = false;
+  c->tc_fallbacks++;
+  cudaStream_t st = c->own_stream;
+  rc = clm_forward(c, sl.ids, CLM_U8, sl.B, sl.T, sl.logits, sl.labels, st);
+  if (rc) return rc;
+  CLM_CUDA(c, cudaMemcpyAsync(sl.h_logits, sl.logits, (size_t)sl.B * 2 * sizeof(float), cudaMemcpyDeviceToHost, st));
+  if (sl.h_labels) CLM_CUDA(c, cudaMemcpyAsync(sl.h_labels, sl.labels, (size_t)sl.B, cudaMemcpyDeviceToHost, st));
+  CLM_CUDA(c, cudaStreamSynchronize(st));
+  return clm_forward_status(c, c->fwd_seq);
+}
+
+int clm_predict_host(clm_ctx* c, const uint8_t* h_bases, const int64_t* h_offsets, int B, int T_pad, int add_cls,
+                     int add_sep, int pad_left, int max_bases, float* h_logits, uint8_t* h_labels) {
+  int ticket = -1;
+  int rc = clm_predict_host_submit(c, h_bases, h_offsets, B, T_pad, add_cls, add_sep, pad_left, max_bases, h_logits, h_labels, &ticket);
+  if (rc) return rc;
+  return clm_predict_host_wait(c, ticket);
 }
 
 int clm_gemm(clm_ctx* c, const void* d_A, const void* d_W, const float* d_bias, int M, int N, int K, int epi,
@@ -1421,6 +1481,7 @@ int clm_set_option(clm_ctx* c, const char* name, int value) {
   else if (n == "mlp_stagger") c->mlp_stagger = value;
   else if (n == "y_channel_major") c->y_channel_major = value != 0;
   else if (n == "mlp_grid") c->mlp_grid = value;
+  else if (n == "skip_dead_res") c->skip_dead_res = value != 0;
   else if (n == "tc_scale_shift") {   // test hook: move the calibrated input scale of the tensor-core conv by 2^value
     if (!c->finalized) return fail(c, CLM_ERR_STATE, "clm_set_option(tc_scale_shift) before clm_finalize");
     CLM_CUDA(c, cudaDeviceSynchronize());

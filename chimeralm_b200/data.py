@@ -5,7 +5,11 @@ Batching policy is the reference's: file order, `batch_size // world_size` reads
 `shuffle=False`, last batch short, every batch padded to its longest member on the
 tokenizer's `padding_side`.  Under data parallelism rank r takes samples r, r+W, r+2W, ...
 (Lightning's unrepeated distributed sampler in predict mode).  `bucket_by_length=True` is the
-B200-side option that sorts reads by length first so batches carry little padding.
+B200-side option: reads are sorted by length and cut into batches under a padded-token budget
+(`batch_size x longest read`, so short reads travel many to a batch), and the batches are dealt to
+the ranks by greedy longest-processing-time on a cost model of the step, so every GPU gets the
+same amount of work instead of the same number of reads (`chimeralm_b200.synth.bucket_batches /
+deal_lpt`; replaces the reference's policy at chimeralm/data/bam.py:142-146,287-299).
 
 When an `Engine` is attached the batch's `input_ids` are produced on the GPU by
 `clm_encode_batch` from raw bases staged in pinned memory (uint8 ids, device tensor);
@@ -19,8 +23,9 @@ from pathlib import Path
 import numpy as np
 import torch
 
+from . import synth
 from .ingest import read_bam_flat
-from .tokenizer import DataCollator, encode_read_name
+from .tokenizer import DataCollator, encode_read_name, encode_read_name_rows, names_to_rows
 
 
 class PredictDataset:
@@ -38,6 +43,16 @@ class PredictDataset:
         offsets = np.zeros(len(seqs) + 1, np.int64)
         np.cumsum([len(s) for s in seqs], out=offsets[1:])
         return cls(names, np.concatenate(seqs) if offsets[-1] else np.zeros(0, np.uint8), offsets)
+
+    @property
+    def id_rows(self) -> np.ndarray:
+        """int8 [n, 256] read-name rows of the whole dataset (`encode_read_name` per read, vectorised)."""
+        if getattr(self, "_id_rows", None) is None:
+            if any(len(x) > 254 for x in self.names):   # longer than a BAM name can be: the scalar rule keeps len(name)
+                self._id_rows = np.array([encode_read_name(x) for x in self.names], dtype=np.int64).astype(np.int8).reshape(-1, 256)
+            else:
+                self._id_rows = encode_read_name_rows(names_to_rows(self.names))
+        return self._id_rows
 
     @property
     def seqs(self) -> list[np.ndarray]:
@@ -143,12 +158,28 @@ class BamDataModule:
             self.data_predict = PredictDataset(names, flat, offsets)
 
     # -------------------------------------------------------------------------------------
-    def _rank_indices(self) -> list[int]:
+    def _rank_batches(self) -> list[np.ndarray]:
+        """Index arrays of this rank's batches, in the order they are run."""
         n = len(self.data_predict)
-        idx = list(range(n))
-        if self.bucket_by_length:
-            idx.sort(key=lambda i: int(self.data_predict.lengths[i]))
-        return idx[self.rank :: self.world_size]
+        bs = self.batch_size_per_device
+        if not self.bucket_by_length:
+            # the reference's policy: file order, Lightning's unrepeated sampler (rank r takes reads r, r + W, ...), fixed size
+            idx = np.arange(self.rank, n, self.world_size)
+            return [idx[i : i + bs] for i in range(0, len(idx), bs)]
+        lens = np.asarray(self.data_predict.lengths, dtype=np.int64)
+        ns = self.tokenizer.num_special_tokens
+        budget = bs * (int(lens.max()) + ns) if n else 0
+        batches = synth.bucket_batches(lens, max(bs, min(8 * bs, 256)), n_special=ns, max_tokens_per_batch=budget)
+        costs = [synth.batch_cost(len(b), int(lens[b].max()) + ns) for b in batches]
+        ranks, _ = synth.deal_lpt(costs, self.world_size)
+        return [batches[i] for i in ranks[self.rank]]
+
+    def max_batch_shape(self) -> tuple[int, int, int]:
+        """(max reads, max tokens, max padded tokens) over this rank's batches: what the engine has to reserve."""
+        ns = self.tokenizer.num_special_tokens
+        lens = self.data_predict.lengths
+        shapes = [(len(b), int(lens[b].max()) + ns) for b in self._rank_batches()] or [(1, 1)]
+        return max(s[0] for s in shapes), max(s[1] for s in shapes), max(s[0] * s[1] for s in shapes)
 
     def _stream_batches(self):
         """Producer/consumer loader: a thread pulls this rank's reads from the native BAM reader
@@ -215,11 +246,10 @@ class BamDataModule:
                 k, n, done = item
                 bases, offs, nm = ring[k % depth]
                 o = offs.numpy()
-                names = [r[: r.index(0)].decode("ascii", "replace") for r in (nm[i].tobytes() for i in range(n))]
                 T = int(np.diff(o[: n + 1]).max()) + ns
-                id_rows = np.array([encode_read_name(x) for x in names], dtype=np.int64).astype(np.int8)
+                id_rows = encode_read_name_rows(nm[:n])   # one numpy pass, no per-read Python
                 batch = {"id": torch.from_numpy(id_rows), "labels": torch.full((n,), -1, dtype=torch.int64),
-                         "names": names, "indices": [rank + W * (done + i) for i in range(n)]}
+                         "indices": np.arange(rank + W * done, rank + W * (done + n), W)}
                 nb = int(o[n])
                 if self.engine is not None:
                     dev = self.engine.device
@@ -243,31 +273,44 @@ class BamDataModule:
             yield from self._stream_batches()
             return
         ds = self.data_predict
-        idx = self._rank_indices()
-        bs = self.batch_size_per_device
         tok = self.tokenizer
-        for b0 in range(0, len(idx), bs):
-            sel = idx[b0 : b0 + bs]
-            names = [ds.names[i] for i in sel]
-            seqs = [ds.seqs[i] for i in sel]
-            ns = tok.num_special_tokens
-            T = max(len(s) for s in seqs) + ns
-            id_rows = np.array([encode_read_name(n) for n in names], dtype=np.int64).astype(np.int8)
-            batch = {"id": torch.from_numpy(id_rows), "labels": torch.full((len(sel),), -1, dtype=torch.int64),
-                     "names": names, "indices": sel}
+        ns = tok.num_special_tokens
+        batches = self._rank_batches()
+        ring = None
+        if self.engine is not None and batches:
+            # persistent pinned staging, three deep: batch k + 1 is assembled while batch k's copy may still be in flight and
+            # batch k - 1 has been consumed (Trainer.predict synchronises on batch k - 1 before asking for batch k + 1)
+            nb_max = max(int(ds.lengths[b].sum()) for b in batches)
+            ring = [(torch.empty(max(nb_max, 1), dtype=torch.uint8).pin_memory(),
+                     torch.empty(max(len(b) for b in batches) + 1, dtype=torch.int64).pin_memory()) for _ in range(3)]
+            B, T, budget = self.max_batch_shape()
+            self.engine.reserve(B, T, budget)
+        id_rows_all = ds.id_rows
+        for k, sel in enumerate(batches):
+            lens = ds.lengths[sel]
+            T = int(lens.max()) + ns
+            batch = {"id": torch.from_numpy(id_rows_all[sel]), "labels": torch.full((len(sel),), -1, dtype=torch.int64),
+                     "indices": sel}
             if self.engine is not None:
-                offsets = np.zeros(len(seqs) + 1, dtype=np.int64)
-                np.cumsum([len(s) for s in seqs], out=offsets[1:])
-                flat = np.concatenate(seqs) if offsets[-1] else np.zeros(1, np.uint8)
-                bases = torch.from_numpy(flat).pin_memory()
-                offs = torch.from_numpy(offsets).pin_memory()
-                ids, _ = self.engine.encode(bases.to(self.engine.device, non_blocking=True),
-                                            offs.to(self.engine.device, non_blocking=True), T, add_cls=tok.add_cls,
+                bases, offs = ring[k % 3]
+                o = offs.numpy()
+                o[0] = 0
+                np.cumsum(lens, out=o[1 : len(sel) + 1])
+                fb = bases.numpy()
+                if len(sel) and sel[-1] - sel[0] == len(sel) - 1 and np.all(np.diff(sel) == 1):
+                    fb[: o[len(sel)]] = ds.flat[ds.offsets[sel[0]] : ds.offsets[sel[-1] + 1]]   # consecutive reads: one copy
+                else:
+                    for j, i in enumerate(sel):
+                        fb[o[j] : o[j + 1]] = ds.flat[ds.offsets[i] : ds.offsets[i + 1]]
+                nb = int(o[len(sel)])
+                dev = self.engine.device
+                ids, _ = self.engine.encode(bases[: max(nb, 1)].to(dev, non_blocking=True),
+                                            offs[: len(sel) + 1].to(dev, non_blocking=True), T, add_cls=tok.add_cls,
                                             add_sep=tok.add_sep, pad_left=tok.padding_side == "left",
                                             max_bases=tok.max_len_single_sentence - ns)
                 batch["input_ids"] = ids
             else:
-                feats = [{"input_ids": tok.encode_array(s.tobytes(), max_length=tok.max_len_single_sentence)} for s in seqs]
+                feats = [{"input_ids": tok.encode_array(ds.seqs[i].tobytes(), max_length=tok.max_len_single_sentence)} for i in sel]
                 batch["input_ids"] = tok.pad(feats, return_tensors="pt")["input_ids"]
             yield batch
 

@@ -195,6 +195,23 @@ class Engine:
         self._check(rc, "clm_predict_host")
         return logits_out, labels_out
 
+    def predict_host_submit(self, bases: torch.Tensor, offsets: torch.Tensor, T_pad: int, *, add_cls: bool, add_sep: bool,
+                            pad_left: bool, max_bases: int, logits_out: torch.Tensor, labels_out: torch.Tensor | None = None) -> int:
+        """Enqueue one batch (HOST tensors, pinned) and return a ticket at once; `predict_host_wait(ticket)` blocks until
+        `logits_out` / `labels_out` are valid.  Up to 3 batches in flight; the tensors must stay alive until the wait."""
+        B = offsets.numel() - 1
+        self.reserve(B, T_pad, B * T_pad)
+        ticket = C.c_int(-1)
+        rc = self.lib.clm_predict_host_submit(self.ctx, C.c_void_p(bases.data_ptr()), C.c_void_p(offsets.data_ptr()), B, T_pad,
+                                              int(add_cls), int(add_sep), int(pad_left), int(max_bases),
+                                              C.c_void_p(logits_out.data_ptr()),
+                                              C.c_void_p(labels_out.data_ptr() if labels_out is not None else 0), C.byref(ticket))
+        self._check(rc, "clm_predict_host_submit")
+        return ticket.value
+
+    def predict_host_wait(self, ticket: int) -> None:
+        self._check(self.lib.clm_predict_host_wait(self.ctx, int(ticket)), "clm_predict_host_wait")
+
     # ------------------------------------------------------------------ unit-level access (tests)
     def gemm(self, A, W, bias, epi, res=None, w2=None, b2=0.0):
         M, K = A.shape

@@ -160,6 +160,30 @@ def encode_read_name(rid: str, max_id_length: int = MAX_ID_LENGTH) -> list[int]:
     return new_id[:max_id_length] if len(new_id) > max_id_length else new_id + [0] * (max_id_length - len(new_id))
 
 
+def encode_read_name_rows(name_rows: np.ndarray, max_id_length: int = MAX_ID_LENGTH) -> np.ndarray:
+    """The same rows for a whole batch, without a Python loop per read: `name_rows` is uint8 [n, stride] of
+    NUL-terminated names (what the native BAM reader fills).  Returns int8 [n, max_id_length] exactly equal to
+    `np.array([encode_read_name(name) ...]).astype(np.int8)` (the collator's cast, reference :167-168)."""
+    n, stride = name_rows.shape
+    is_nul = name_rows == 0
+    lens = np.where(is_nul.any(axis=1), is_nul.argmax(axis=1), stride)
+    out = np.zeros((n, max_id_length), np.uint8)
+    w = min(stride, max_id_length - 1)
+    out[:, 1 : 1 + w] = np.where(np.arange(w)[None, :] < lens[:, None], name_rows[:, :w], 0)
+    out[:, 0] = lens.astype(np.uint8)          # len <= 254 for BAM names; int64 -> int8 wraps the same way
+    return out.view(np.int8)
+
+
+def names_to_rows(names, stride: int = MAX_ID_LENGTH) -> np.ndarray:
+    """list[str] -> uint8 [n, stride] NUL-padded (names longer than stride - 1 are cut like the reference's slice)."""
+    if not len(names):
+        return np.zeros((0, stride), np.uint8)
+    fixed = np.array([x.encode("ascii", "replace") for x in names], dtype=f"S{stride - 1}")
+    rows = np.zeros((len(names), stride), np.uint8)
+    rows[:, : stride - 1] = fixed.view(np.uint8).reshape(len(names), stride - 1)
+    return rows
+
+
 def tokenize_and_align_labels_and_quals_ids(data, tokenizer, max_length, *, include_qual=False, seq_feature=SEQ_FEATURE,
                                             id_feature=ID_FEATURE, max_id_length=MAX_ID_LENGTH, **_):
     """Per-example tokenise fn of the predict dataset (reference :85-114)."""

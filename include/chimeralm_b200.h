@@ -111,6 +111,15 @@ long long clm_tc_fallback_count(const clm_ctx* ctx);
  * `e2e` figure and the Python predict loop time. */
 int clm_predict_host(clm_ctx* ctx, const uint8_t* h_bases, const int64_t* h_offsets, int B, int T_pad, int add_cls,
                      int add_sep, int pad_left, int max_bases, float* h_logits, uint8_t* h_labels);
+/* The same in two halves, so that the host can prepare and enqueue batch k + 1 while batch k runs (the reference's
+ * DataLoader workers + Lightning loop overlap the same way, chimeralm/__main__.py:308-317): submit copies and enqueues
+ * one batch on the context's own stream and returns a ticket at once; wait blocks until THAT batch's h_logits /
+ * h_labels are valid and returns its status (a batch that left the fp16 range of the tensor-core convolution is redone
+ * with the fp32 kernel before wait returns).  Up to 3 batches may be in flight; the host buffers of a batch must stay
+ * valid until its wait returns.  clm_predict_host == submit + wait. */
+int clm_predict_host_submit(clm_ctx* ctx, const uint8_t* h_bases, const int64_t* h_offsets, int B, int T_pad, int add_cls,
+                            int add_sep, int pad_left, int max_bases, float* h_logits, uint8_t* h_labels, int* ticket);
+int clm_predict_host_wait(clm_ctx* ctx, int ticket);
 
 /* Number of kernel launches issued by this context since creation (bench.py's gpu_launches). */
 long long clm_launch_count(const clm_ctx* ctx);

@@ -67,3 +67,43 @@ def test_filter_drops_label1_and_keeps_unknown(tmp_path):
     tid, pos, name = recs[len(recs) // 2]
     hits = bai.fetch(sorted_bam, idx, tid, pos, pos + 1)
     assert name in [h[0] for h in hits] and all(h[1] <= pos < h[2] for h in hits)
+
+
+def test_filter_sorts_with_bounded_memory_and_skips_unplaced_reads(tmp_path, monkeypatch):
+    """`filter` must not hold the BAM in memory (the reference goes through `samtools sort`, an external merge
+    sort) and, like the reference's index-driven `fetch()`, copies placed reads only.  With a run size of 20 kB the
+    400 records spill into many sorted runs; the merged result must equal a plain stable sort."""
+    import numpy as np
+
+    from chimeralm_b200.__main__ import app
+    from chimeralm_b200.bam import BamReader, BamWriter, make_record, minimal_header, samtools_sort_key, sorted_records_external
+
+    rng = np.random.default_rng(4)
+    bam = tmp_path / "in.bam"
+    w = BamWriter(bam, minimal_header((("chr1", 1_000_000), ("chr2", 500_000))))
+    recs = []
+    for i in range(400):
+        ref = int(rng.integers(-1, 2))            # -1 = unplaced
+        pos = int(rng.integers(0, 400)) if ref >= 0 else -1     # few positions: many ties
+        flag = int(rng.choice([0, 16])) | (4 if ref < 0 else 0)
+        r = make_record(f"r{i:04d}", "ACGT" * int(rng.integers(10, 60)), flag=flag, ref_id=ref, pos=pos)
+        recs.append(r)
+        w.write(r)
+    w.close()
+    placed = [r for r in recs if r.ref_id >= 0]
+    want = [r.name for r in sorted(placed, key=samtools_sort_key)]          # Python's sort is stable
+    got_runs = [r.name for r in sorted_records_external(iter(placed), run_bytes=20_000, tmpdir=str(tmp_path))]
+    assert got_runs == want
+    assert [r.name for r in sorted_records_external(iter(placed))] == want  # single run, no spill
+    pred = tmp_path / "pred"
+    pred.mkdir()
+    (pred / "0_0.txt").write_text("r0000\t0\n")
+    monkeypatch.setenv("CLM_SORT_RUN_BYTES", "20000")
+    r = CliRunner().invoke(app, ["filter", str(bam), str(pred)])
+    assert r.exit_code == 0, r.output
+    with BamReader(tmp_path / "in.filtered.bam") as f:
+        assert [x.name for x in f] == [x.name for x in placed]
+    with BamReader(tmp_path / "in.filtered.sorted.bam") as f:
+        assert [x.name for x in f] == want
+    assert not list(tmp_path.glob("clm_sort_run_*"))
+    assert (tmp_path / "in.filtered.sorted.bam.bai").exists()

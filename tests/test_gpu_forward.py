@@ -280,7 +280,8 @@ def test_full_size_batch_permutation_invariance(state_dict):
 
 
 @pytest.mark.parametrize("option,T", [("fused_score_pool", 1500), ("fused_head", 1500), ("tc_conv", 8193), ("tc_chunked", 9000),
-                                      ("fused_mlp", 700), ("fused_in", 700), ("fast_conv", 700), ("mlp_epi16", 1500), ("mlp_pp", 8193), ("mlp_early_res", 8193), ("mlp_fc2_lag", 8193)])
+                                      ("fused_mlp", 700), ("fused_in", 700), ("fast_conv", 700), ("mlp_epi16", 1500), ("mlp_pp", 8193), ("mlp_early_res", 8193), ("mlp_fc2_lag", 8193),
+                                      ("skip_dead_res", 700)])
 def test_kernel_variants_agree(state_dict, option, T):
     """Every `clm_set_option` switch selects a different kernel for the same math (fused vs unfused, tensor-core vs fp32 FFT,
     8 vs 16 epilogue warps): flipping it must not move the logits by more than the parity tolerance."""
@@ -517,3 +518,86 @@ def test_fp16_range_overflow_switches_to_fp32_conv(state_dict):
         assert eng.native_tc_fallbacks == 1 and (lo_tc - lo_fp).abs().max().item() <= LOGIT_TOL
     finally:
         eng.close()
+
+
+def test_predict_host_submit_wait_pipeline(state_dict):
+    """The two-halves form of clm_predict_host: three batches in flight, results identical to the one-at-a-time call,
+    a fourth submit without a wait is refused, and a batch that overflows the fp16 convolution is
+    redone in fp32 inside its own wait without disturbing the batches queued behind it."""
+    from chimeralm_b200 import synth
+    from chimeralm_b200._lib import ChimeraLMNativeError
+    from chimeralm_b200.engine import Engine
+
+    B, L = 4, 8192
+    T = L + 1
+    eng = Engine(state_dict, device=0, max_batch=B, max_tokens=T)
+    kw = dict(add_cls=False, add_sep=True, pad_left=True, max_bases=32768)
+    try:
+        reads = [synth.uniform_reads(B, L, 100 + i) for i in range(5)]
+        bases = [torch.from_numpy(r.reshape(-1).copy()).pin_memory() for r in reads]
+        offs = torch.arange(0, (B + 1) * L, L, dtype=torch.int64).pin_memory()
+        want = [eng.predict_host(b, offs, T, **kw)[0].clone() for b in bases]
+        lo = [torch.empty(B, 2).pin_memory() for _ in range(5)]
+        la = [torch.empty(B, dtype=torch.uint8).pin_memory() for _ in range(5)]
+        tickets = [eng.predict_host_submit(bases[i], offs, T, logits_out=lo[i], labels_out=la[i], **kw) for i in range(3)]
+        with pytest.raises(ChimeraLMNativeError):
+            eng.predict_host_submit(bases[3], offs, T, logits_out=lo[3], labels_out=la[3], **kw)
+        eng.predict_host_wait(tickets[0])
+        tickets.append(eng.predict_host_submit(bases[3], offs, T, logits_out=lo[3], labels_out=la[3], **kw))
+        for t in tickets[1:]:
+            eng.predict_host_wait(t)
+        with pytest.raises(ChimeraLMNativeError):
+            eng.predict_host_wait(tickets[0])        # already waited for
+        for i in range(4):
+            assert torch.equal(lo[i], want[i]), i
+            assert torch.equal(la[i].long(), (want[i][:, 1] > want[i][:, 0]).long())
+        # overflow in the middle of the queue: batch 1 is submitted with the input scale pushed up (test hook)
+        eng.set_option("tc_conv", 0)
+        fp = [eng.predict_host(b, offs, T, **kw)[0].clone() for b in bases[:3]]
+        eng.set_option("tc_conv", 1)
+        t0 = eng.predict_host_submit(bases[0], offs, T, logits_out=lo[0], labels_out=la[0], **kw)
+        torch.cuda.synchronize()
+        eng.set_option("tc_scale_shift", 13)
+        t1 = eng.predict_host_submit(bases[1], offs, T, logits_out=lo[1], labels_out=la[1], **kw)
+        torch.cuda.synchronize()
+        eng.set_option("tc_scale_shift", 0)
+        t2 = eng.predict_host_submit(bases[2], offs, T, logits_out=lo[2], labels_out=la[2], **kw)
+        for t in (t0, t1, t2):
+            eng.predict_host_wait(t)
+        assert eng.native_tc_fallbacks == 1
+        assert torch.equal(lo[0], want[0]) and torch.equal(lo[2], want[2]) and torch.equal(lo[1], fp[1])
+    finally:
+        eng.close()
+
+
+def test_bucketed_predict_flow_matches_per_read_forward(tmp_path, state_dict):
+    """`--bucket` through the mirrored stack (BamDataModule -> Trainer -> PredictionWriter): length-sorted batches under a
+    token budget, vectorised name rows, pinned staging ring.  Every read gets exactly one line, and a read's label equals
+    the label of a forward on the identical padded batch."""
+    from chimeralm_b200.callbacks import PredictionWriter, load_predictions_from_folder, resume_read_names
+    from chimeralm_b200.data import BamDataModule, Trainer
+    from chimeralm_b200.model import ClassificationLit
+    from chimeralm_b200.tokenizer import load_tokenizer_from_hyena_model
+
+    bam = tmp_path / "in.bam"
+    _synthetic_bam(bam, n=120, seed=5)
+    tok = load_tokenizer_from_hyena_model("hyenadna-small-32k-seqlen")
+    model = ClassificationLit(state_dict, device=0, max_batch=8, max_tokens=3001)
+    try:
+        dm = BamDataModule(tok, batch_size=8, predict_data_path=bam, engine=model.engine, bucket_by_length=True)
+        out = tmp_path / "pred"
+        res = Trainer(callbacks=[PredictionWriter(out, "batch")]).predict(model, dataloaders=dm, return_predictions=True)
+        preds = load_predictions_from_folder(out)
+        n_kept = len(dm.data_predict)
+        assert len(preds) == n_kept == sum(len(i) for i, _ in res)
+        assert sorted(int(j) for i, _ in res for j in i) == list(range(n_kept))
+        lens = dm.data_predict.lengths
+        budget = 8 * (int(lens.max()) + 1)
+        for batch in dm.predict_dataloader():
+            B_, T_ = batch["input_ids"].shape
+            assert B_ * T_ <= budget and B_ <= 64
+            logits = model.forward(batch["input_ids"]).cpu()
+            names = resume_read_names(batch["id"])
+            assert [preds[n] for n in names] == logits.argmax(1).tolist()
+    finally:
+        model.engine.close()

@@ -263,7 +263,7 @@ def test_datamodule_uses_native_ingest_and_matches_generator(tmp_path):
     mb = tok.max_len_single_sentence - tok.num_special_tokens
     assert [s.tobytes().decode() for s in dm.data_predict.seqs] == [r["seq"][:mb] for r in ref]
     batches = list(dm.predict_dataloader())
-    assert [len(b["names"]) for b in batches] == [8, 8, 4]
+    assert [len(b["id"]) for b in batches] == [8, 8, 4]
 
 
 def test_streaming_loader_matches_load_all_and_shards_like_the_sampler(tmp_path):
@@ -284,7 +284,7 @@ def test_streaming_loader_matches_load_all_and_shards_like_the_sampler(tmp_path)
         a, b = batches(False, rank, world, limit), batches(True, rank, world, limit)
         assert len(a) == len(b) > 0
         for x, y in zip(a, b):
-            assert x["names"] == y["names"] and list(x["indices"]) == list(y["indices"])
+            assert torch.equal(x["id"], y["id"]) and list(x["indices"]) == list(y["indices"])
             assert torch.equal(x["input_ids"], y["input_ids"]) and torch.equal(x["id"], y["id"])
 
 
@@ -313,7 +313,9 @@ def test_fastq_and_parquet_predict_inputs(tmp_path):
         dm = BamDataModule(tok, predict_data_path=tmp_path / path, batch_size=8, streaming=True)
         dm.setup("predict")
         (batch,) = list(dm.predict_dataloader())
-        assert batch["names"] == want_names, path
+        from chimeralm_b200.callbacks import resume_read_names
+
+        assert resume_read_names(batch["id"]) == want_names, path
         assert batch["input_ids"].tolist() == want_ids, path
 
 
@@ -413,3 +415,77 @@ def test_bai_small_cases(tmp_path):
     w.close()
     with pytest.raises(ValueError, match="not coordinate-sorted"):
         bai.build_index(tmp_path / "u.bam")
+
+
+def test_vectorised_read_name_rows_equal_the_scalar_rule(tok_gold):
+    """`encode_read_name_rows` / `resume_read_names` (one numpy pass per batch) against the per-read functions that mirror
+    the reference (`tokenizer.py:108-111`, `callbacks.py:38-63`) and against the reference-generated golden rows."""
+    from chimeralm_b200.callbacks import resume_read_name, resume_read_names
+
+    names = list(tok_gold["names"]) + ["", "r", "x" * 254, "read/1 with space", "tab\tname", "café"]
+    names = [n for n in names if len(n) <= 254]
+    want = np.array([T.encode_read_name(n) for n in names], dtype=np.int64).astype(np.int8)
+    rows = T.names_to_rows(names)
+    got = T.encode_read_name_rows(rows)
+    enc = [n.encode("ascii", "replace").decode() for n in names]
+    want_enc = np.array([T.encode_read_name(n) for n in enc], dtype=np.int64).astype(np.int8)
+    assert got.dtype == np.int8 and np.array_equal(got, want_enc)
+    ascii_only = [i for i, n in enumerate(names) if n.isascii()]
+    assert np.array_equal(got[ascii_only], want[ascii_only])
+    # garbage after the NUL (the native reader does not clear its rows) must not leak
+    dirty = rows.copy()
+    dirty[:, 200:] = np.where(dirty[:, 200:] == 0, 65, dirty[:, 200:])
+    lens = np.array([len(n) for n in enc])
+    ok = lens < 199
+    assert np.array_equal(T.encode_read_name_rows(dirty)[ok], got[ok])
+    back = resume_read_names(torch.from_numpy(got))
+    for i, n in enumerate(enc):
+        if 0 < len(n) <= 127:
+            assert back[i] == resume_read_name(torch.from_numpy(got[i])) == "".join(c for c in n if 32 <= ord(c) <= 126), n
+        else:
+            # len byte 0, or > 127 and therefore negative after the collator's int8 cast: the scalar function raises (the
+            # reference's writer then logs and writes "error_read_i")
+            assert isinstance(back[i], ValueError)
+            with pytest.raises(ValueError):
+                resume_read_name(torch.from_numpy(got[i]))
+
+
+def test_bucketed_datamodule_deals_token_balanced_batches(tmp_path):
+    """`bucket_by_length`: every read exactly once across the ranks, batches under the padded-token budget, ranks balanced by
+    cost (LPT) - and the reference's policy (file order, rank::world, fixed size) untouched when the option is off."""
+    from chimeralm_b200.data import BamDataModule
+    from chimeralm_b200.tokenizer import load_tokenizer_from_hyena_model
+
+    tok = load_tokenizer_from_hyena_model("hyenadna-small-32k-seqlen")
+    from chimeralm_b200.bam import make_record, minimal_header
+
+    p = tmp_path / "synth.bam"
+    rng = np.random.default_rng(8)
+    w = BamWriter(p, minimal_header())
+    for i in range(400):
+        w.write(make_record(f"read{i}", "ACGT"[i % 4] * int(np.exp(rng.uniform(np.log(100), np.log(3000)))), sa_tag=True))
+    w.close()
+    for world in (1, 2, 4):
+        seen, loads = [], []
+        for rank in range(world):
+            dm = BamDataModule(tok, predict_data_path=p, batch_size=8 * world, bucket_by_length=True, rank=rank, world_size=world)
+            dm.setup("predict")
+            lens = dm.data_predict.lengths
+            budget = 8 * (int(lens.max()) + 1)
+            tokens = 0
+            for b in dm.predict_dataloader():
+                idx = np.asarray(b["indices"])
+                Tb = b["input_ids"].shape[1]
+                assert b["input_ids"].shape[0] == len(idx) <= 64 and len(idx) * Tb <= budget
+                assert Tb == int(lens[idx].max()) + 1
+                seen += idx.tolist()
+                tokens += len(idx) * Tb
+            loads.append(tokens)
+            B, Tm, bud = dm.max_batch_shape()
+            assert bud <= budget and Tm == int(lens.max()) + 1 or world > 1
+        assert sorted(seen) == list(range(400))            # every read exactly once across the ranks
+        assert max(loads) / (sum(loads) / world) < 1.15
+    dm = BamDataModule(tok, predict_data_path=p, batch_size=8, rank=1, world_size=2)
+    dm.setup("predict")
+    first = next(iter(dm.predict_dataloader()))
+    assert list(first["indices"]) == [1, 3, 5, 7]
