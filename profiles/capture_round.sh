@@ -1,15 +1,18 @@
 #!/bin/bash
 # One GPU-box pass that produces a round's evidence under gpurun_out/ (copied to profiles/ afterwards):
 #   bench lines (own arm, reference arm), the ncu launch list of the bench command and one `--set full` capture per hot kernel.
-# usage (on the box): bash profiles/capture_round.sh r1_v12
+# Every ncu pass runs only after the same command has exited 0 without ncu; numbers printed under ncu are never bench values.
+# usage (on the box): bash profiles/capture_round.sh r2_v1
 TAG=${1:-round}
+K2ONLY="--k3-reads 0 --k5-steps 0 --no-labels --cpu-sample 0"
 mkdir -p gpurun_out
 python bench.py --steps 40 --warmup 5 > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err || exit 1
 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/${TAG}_bench_reference.json 2>> gpurun_out/${TAG}_bench.err
-ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${TAG}_launches.csv \
-    python bench.py --steps 2 --warmup 1 > gpurun_out/${TAG}_ncu_launches.log 2>&1
+python bench.py --steps 2 --warmup 1 $K2ONLY > gpurun_out/${TAG}_bench_short.json 2>> gpurun_out/${TAG}_bench.err || exit 1
+ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/${TAG}_launches.csv \
+    python bench.py --steps 2 --warmup 1 $K2ONLY > gpurun_out/${TAG}_ncu_launches.log 2>&1
 for k in block_mlp_kernel longconv_tc_kernel block_in_kernel score_pool_kernel; do
   ncu --set full --clock-control none --import-source on -k regex:$k --launch-skip 6 -c 1 -f -o gpurun_out/${TAG}_$k \
-      python bench.py --steps 2 --warmup 1 > gpurun_out/${TAG}_ncu_$k.log 2>&1
+      python bench.py --steps 2 --warmup 1 $K2ONLY > gpurun_out/${TAG}_ncu_$k.log 2>&1
 done
 tail -c 400 gpurun_out/${TAG}_bench.json
