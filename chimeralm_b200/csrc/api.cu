@@ -713,7 +713,7 @@ int launch_longconv_tc(clm_ctx* c, int layer, const __half* vx, const __nv_bfloa
   p.inva = inva_override ? inva_override : (unit_scale ? L.unit_inva : L.tc_inva);
   p.rel = L.tc_rel; p.err = (unit_scale || osc_override) ? c->d_err + 1 : c->d_err;
   const int grid = std::min(p.n_items, c->num_sms);
-  if (pl.nc > 1) longconv_tc_kernel<true><<<grid, tc::THREADS, tc::SMEM_TOTAL, st>>>(tm, tmo, tmg, p);
+  if (pl.nc > 1) longconv_tc_kernel<true><<<grid, tc::THREADS_CH, tc::SMEM_TOTAL, st>>>(tm, tmo, tmg, p);
   else longconv_tc_kernel<false><<<grid, tc::THREADS, tc::SMEM_TOTAL, st>>>(tm, tmo, tmg, p);
   CLM_LAUNCH_CHECK(c, pl.nc > 1 ? "longconv_tc_chunked" : "longconv_tc");
   return 0;

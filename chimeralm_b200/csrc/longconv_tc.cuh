@@ -82,7 +82,11 @@ constexpr int OFF_Z = OFF_S + S_BYTES;            // 2 buffers
 constexpr int OFF_BT = OFF_Z + 2 * Z_BYTES;
 constexpr int OFF_BAR = OFF_BT + BT_BYTES;        // 229376
 constexpr int SMEM_TOTAL = OFF_BAR + 256;
-constexpr int THREADS = 320;
+constexpr int THREADS = 320;        // single-chunk kernel: warp 0 producer, warp 1 MMA issuer, warps 2..9 epilogue
+// Chunked kernel: three warpgroups (producer, MMA issuer and two idle warps | eight epilogue warps) so that `setmaxnreg` can
+// move registers to the epilogue warps (200 each instead of the 168 ptxas allows 320 threads): the segment sum and the
+// carry of the overlap-add keep ~60 more values live than the single-chunk epilogue.
+constexpr int THREADS_CH = 384;
 constexpr int ROW_NFIM = 0, ROW_FRE = 128, ROW_FIM = 256;   // row blocks of S
 constexpr int ZIM_COL = 80;                                 // step 7: z'_re at Y[0, 80), z'_im at Y[80, 160)
 
@@ -277,7 +281,7 @@ __global__ void __launch_bounds__(256) scale_to_f16_kernel(const __nv_bfloat16* 
 }  // namespace tc
 
 template <bool CH>   // CH: chunked mode (n_chunks > 1)
-__global__ void __launch_bounds__(tc::THREADS, 1)
+__global__ void __launch_bounds__(CH ? tc::THREADS_CH : tc::THREADS, 1)
 longconv_tc_kernel(const __grid_constant__ CUtensorMap tmVX, const __grid_constant__ CUtensorMap tmOut,
                    const __grid_constant__ CUtensorMap tmX0, LongConvTcParams p) {
   using namespace tc;
@@ -319,7 +323,7 @@ longconv_tc_kernel(const __grid_constant__ CUtensorMap tmVX, const __grid_consta
   // constant stack -> shared memory
   {
     uint4* dst = reinterpret_cast<uint4*>(smem + OFF_S);
-    for (int i = threadIdx.x; i < S_BYTES / 16; i += THREADS) dst[i] = __ldg(p.S + i);
+    for (int i = threadIdx.x; i < S_BYTES / 16; i += (CH ? THREADS_CH : THREADS)) dst[i] = __ldg(p.S + i);
   }
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmVX); ptx::prefetch_tmap(&tmOut); ptx::prefetch_tmap(&tmX0);
@@ -339,8 +343,10 @@ longconv_tc_kernel(const __grid_constant__ CUtensorMap tmVX, const __grid_consta
   const uint32_t tmem_base = *tmem_ptr;
   const uint32_t TM_X = tmem_base, TM_Y = tmem_base + 256;
 
+  constexpr int EPI_W0 = CH ? 4 : 2;   // first epilogue warp
   if (warp == 0) {
     // =========================== TMA producer (+ output stores) ===========================
+    if constexpr (CH) ptx::setmaxnreg_dec<104>();
     // Buffer b cycles: z tile of item i -> (step 1 done) x0 gate tile of item i -> (E4) output tile of item i -> stored
     // -> z tile of item i + 2.  This thread issues the z loads and the output stores; the gate load is issued by an
     // epilogue thread, which is the one that knows when step 1 has finished.
@@ -373,6 +379,7 @@ longconv_tc_kernel(const __grid_constant__ CUtensorMap tmVX, const __grid_consta
     }
   } else if (warp == 1) {
     // =========================== MMA issuer ===========================
+    if constexpr (CH) ptx::setmaxnreg_dec<104>();
     {   // whole warp, uniform control flow; one elected lane issues (ptx::umma_f16_e)
       constexpr uint32_t id1 = idesc(128, false, true);    // step 1: A K-major, B MN-major, N = 128
       constexpr uint32_t id35 = idesc(256, false, false);  // steps 3, 5: A from TMEM, B K-major, N = 256
@@ -460,9 +467,12 @@ longconv_tc_kernel(const __grid_constant__ CUtensorMap tmVX, const __grid_consta
         stamp(0);
       }
     }
+  } else if (warp < EPI_W0) {
+    if constexpr (CH) ptx::setmaxnreg_dec<104>();   // idle warps of the first warpgroup (chunked kernel only)
   } else {
     // =========================== epilogue warps ===========================
-    const int q = warp & 3, hf = (warp - 2) >> 2;
+    if constexpr (CH) ptx::setmaxnreg_inc<200>();
+    const int q = warp & 3, hf = (warp - EPI_W0) >> 2;
     const int r = q * 32 + lane;                         // TMEM lane: k1 (E1-E3) or n2 (E4)
     const uint32_t lane_addr = uint32_t(q * 32) << 16;
     const uint32_t sBT = ptx::smem_u32(smem + OFF_BT);
@@ -477,14 +487,14 @@ longconv_tc_kernel(const __grid_constant__ CUtensorMap tmVX, const __grid_consta
     float2 seed1[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) sincospif(-2.0f * float((r * col12(u)) % N) / float(N), &seed1[u].y, &seed1[u].x);
-    const bool tr = trace && warp == 2 && lane == 0;
+    const bool tr = trace && warp == EPI_W0 && lane == 0;
     const int nt = p.nt;      // tail tokens after the last chunk, 0..LONGCONV_TAIL_MAX
     const float2 w2 = make_float2(wstep.x * wstep.x - wstep.y * wstep.y, 2.0f * wstep.x * wstep.y);
     // chunked mode: this CTA's scratch = parked spectra of chunks 0..NC-2 (float4 = two complex values; a warp's 32 lanes
     // write 512 contiguous bytes) followed by the carry (second halves of the last inverse transform, [2][64][128] fp32)
     uint4* park = reinterpret_cast<uint4*>(p.scratch + (long long)blockIdx.x * p.scratch_per_cta);
     float* carry = p.scratch + (long long)blockIdx.x * p.scratch_per_cta + (long long)(NC - 1) * N;
-    const int e_warp = warp - 2;
+    const int e_warp = warp - EPI_W0;
     for (uint32_t it = 0; it < (uint32_t)n_units; ++it) {
       const uint32_t ph = it & 1, buf = it & 1;
       const int item = item0 + (int)it / NC, c = (int)it % NC;   // c: chunk (tokens [c C, c C + C))
@@ -511,7 +521,7 @@ longconv_tc_kernel(const __grid_constant__ CUtensorMap tmVX, const __grid_consta
       ptx::mbar_wait(x_full, ph);
       ptx::tc_fence_after_sync();
       if (tr) stamp(1);
-      if (threadIdx.x == 64) {   // z has been consumed: its buffer now receives the x0 gate tile [n1][n2] of both reads
+      if (threadIdx.x == EPI_W0 * 32) {   // z has been consumed: its buffer now receives the x0 gate tile [n1][n2] of both reads
         ptx::mbar_expect_tx(&g_full[buf], has1 ? Z_BYTES : Z_BYTES / 2);
         ptx::tma_load_3d(zb, &tmX0, &g_full[buf], 0, 64 * c, b0 * p.D + ch);
         if (has1) ptx::tma_load_3d(zb + 16384, &tmX0, &g_full[buf], 0, 64 * c, b1 * p.D + ch);
@@ -703,6 +713,19 @@ longconv_tc_kernel(const __grid_constant__ CUtensorMap tmVX, const __grid_consta
         tx0 = __bfloat162float(p.x0[row0 + NC * C + j]);
         if (has1) tx1 = __bfloat162float(p.x0[row1 + NC * C + j]);
       }
+      // chunked mode: the previous chunk's overlap (this thread's 64 carry values, an L2 round trip each) is fetched into
+      // registers BEFORE waiting for step 7, so the loads fly under that wait instead of inside the output loop
+      // (first half here, second half while the first is being multiplied: all 64 at once do not fit the register file)
+      float cra[CH ? 32 : 1], crb[CH ? 32 : 1];
+      if constexpr (CH) {
+        if (c > 0) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            cra[i] = carry[(32 * hf + i) * 128 + r];
+            crb[i] = carry[8192 + (32 * hf + i) * 128 + r];
+          }
+        }
+      }
       ptx::mbar_wait(o_full, ph);
       ptx::tc_fence_after_sync();
       if (tr) stamp(1);
@@ -713,6 +736,15 @@ longconv_tc_kernel(const __grid_constant__ CUtensorMap tmVX, const __grid_consta
         uint32_t zr[16], zi[16];
         tmem_ld16(TM_Y + lane_addr + 32 * hf + 16 * h2, zr);
         tmem_ld16(TM_Y + lane_addr + ZIM + 32 * hf + 16 * h2, zi);
+        if constexpr (CH) {
+          if (c > 0 && h2 == 0) {
+#pragma unroll
+            for (int i = 16; i < 32; ++i) {
+              cra[i] = carry[(32 * hf + i) * 128 + r];
+              crb[i] = carry[8192 + (32 * hf + i) * 128 + r];
+            }
+          }
+        }
         ptx::tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
@@ -720,8 +752,8 @@ longconv_tc_kernel(const __grid_constant__ CUtensorMap tmVX, const __grid_consta
           float va = __uint_as_float(zr[j]), vb = __uint_as_float(zi[j]);
           if constexpr (CH) {   // + the previous chunk's overlap
             if (c > 0) {
-              va += carry[n1 * 128 + r];
-              vb += carry[8192 + n1 * 128 + r];
+              va += cra[16 * h2 + j];
+              vb += crb[16 * h2 + j];
             }
           }
           va *= osc;
