@@ -499,10 +499,18 @@ def run_cli_multi_gpu(world):
     w.close()
     outs = {}
     t0 = time.perf_counter()
+    # a clean environment: under torchrun this process carries RANK / WORLD_SIZE / MASTER_* / TORCHELASTIC_* (with
+    # TORCHELASTIC_USE_AGENT_STORE the children's own rendezvous would wait on torchrun's store for ever)
+    env = {k: v for k, v in os.environ.items()
+           if not (k.startswith(("TORCHELASTIC_", "MASTER_", "GROUP_", "ROLE_", "LOCAL_", "NCCL_ASYNC", "TORCH_NCCL_ASYNC"))
+                   or k in ("RANK", "WORLD_SIZE", "OMP_NUM_THREADS"))}
     for g in (1, world):
         out = tmp / f"pred{g}"
-        r = subprocess.run([sys.executable, "-m", "chimeralm_b200", "predict", str(bam), "-o", str(out), "-b", "16", "--gpus", str(g)],
-                           capture_output=True, text=True, timeout=900, cwd=str(ROOT))
+        try:
+            r = subprocess.run([sys.executable, "-m", "chimeralm_b200", "predict", str(bam), "-o", str(out), "-b", "16", "--gpus", str(g)],
+                               capture_output=True, text=True, timeout=240, cwd=str(ROOT), env=env)
+        except subprocess.TimeoutExpired:
+            return {"ok": False, "gpus": g, "error": "timed out after 240 s"}
         if r.returncode != 0:
             return {"ok": False, "gpus": g, "error": (r.stdout + r.stderr)[-400:]}
         outs[g] = load_predictions_from_folder(out)
@@ -547,8 +555,18 @@ def main():
 
     k2 = run_k2(args, eng, D, sampler)
     conv_variant = eng.longconv_variant(k2["T"])
-    k5 = run_k5(args, eng, D, sampler) if args.k5_steps > 0 else None
-    k3 = run_k3(args, eng, D, sampler) if args.k3_reads > 0 else None
+
+    def guarded(fn, *a):
+        # a sub-record must never cost the headline line: its failure is reported in its place.  (Collective calls inside
+        # run on every rank or on none - an exception on one rank alone would still hang the others, so only failures
+        # that are the same on all ranks, like running out of memory for a shape, are survivable here.)
+        try:
+            return fn(*a)
+        except Exception as e:  # noqa: BLE001
+            return {"error": f"{type(e).__name__}: {e}"[:400]}
+
+    k5 = guarded(run_k5, args, eng, D, sampler) if args.k5_steps > 0 else None
+    k3 = guarded(run_k3, args, eng, D, sampler) if args.k3_reads > 0 else None
     eng.close()
     D.barrier()
     D.close()
@@ -616,8 +634,8 @@ def main():
         cpu = {"value": v, "unit": "reads/s", "cores": torch.get_num_threads(), "kind": "port",
                "sample": f"{args.cpu_sample} reads x {L} b of the K2 stream, batch 12 (the reference CLI default); tokenise {t_tok:.2f}s + forward {t_fwd:.2f}s",
                "torch": torch.__version__}
-    labels = None if args.no_labels else run_label_agreement(local_rank)
-    cli = run_cli_multi_gpu(world) if (world == 2 and not args.no_cli) else None
+    labels = None if args.no_labels else guarded(run_label_agreement, local_rank)
+    cli = guarded(run_cli_multi_gpu, world) if (world == 2 and not args.no_cli) else None
 
     line = {
         "metric": "predict_reads_per_s", "value": reads_per_s, "unit": "reads/s", "n_gpus": world,
@@ -647,9 +665,9 @@ def main():
         "slowest_rank": {"rank": slow, "ms_per_step": per_rank[slow][0] / args.steps,
                          "kernel_sum_ms_per_step": per_rank[slow][3] / args.steps,
                          "profiled_pass_ms_per_step": per_rank[slow][2] / args.steps},
-        "label_agreement": labels["label_agreement"] if labels else None,
-        "n_reads": labels["n_reads"] if labels else None,
-        "logit_max_err": labels["logit_max_err"] if labels else None,
+        "label_agreement": labels.get("label_agreement") if labels else None,
+        "n_reads": labels.get("n_reads") if labels else None,
+        "logit_max_err": labels.get("logit_max_err") if labels else None,
         "labels": labels,
         "k3": k3,
         "k5": k5,

@@ -26,8 +26,10 @@ def predict_rank(rank: int, world: int, data_path: Path, output_path: Path, batc
     if world > 1:
         import torch.distributed as dist
 
-        os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
-        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+        # explicit TCP rendezvous on the loopback: independent of any RANK / MASTER_* / TORCHELASTIC_* variables the parent
+        # process may carry (run from inside a torchrun worker, the env:// rendezvous would wait on torchrun's own store)
+        dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world,
+                                device_id=torch.device("cuda", rank))
     tokenizer = load_tokenizer_from_hyena_model("hyenadna-small-32k-seqlen")
     if ckpt_path is not None:
         model = ChimeraLM.from_pretrained(str(ckpt_path), device=rank)
