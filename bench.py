@@ -550,7 +550,7 @@ def main():
     torch.cuda.set_device(local_rank)
     D = Dist(local_rank)
     rank, world = D.rank, D.world
-    sampler = ClockSampler(local_rank) if rank == 0 else None   # started now, rows outside the timed regions are dropped
+    sampler = ClockSampler(local_rank)   # every rank samples ITS GPU; started now, rows outside the timed regions are dropped
     eng = Engine(sd, device=local_rank, max_batch=args.batch, max_tokens=args.read_len + 1)
 
     k2 = run_k2(args, eng, D, sampler)
@@ -569,10 +569,13 @@ def main():
     k3 = guarded(run_k3, args, eng, D, sampler) if args.k3_reads > 0 else None
     eng.close()
     D.barrier()
+    clocks = sampler.stop()
+    ck = clocks.get("k2", {})
+    clocks_per_rank = D.gather_floats([ck.get("sm_mhz") or 0.0, ck.get("sm_mhz_min") or 0.0, ck.get("power_w_max") or 0.0,
+                                       float("sw_power_cap" in ck.get("reasons", []))])
     D.close()
     if rank != 0:
         return
-    clocks = sampler.stop() if sampler else {}
 
     B, L, T, prof = k2["B"], k2["L"], k2["T"], k2["prof"]
     per_rank = k2["per_rank"]   # [ms, gather_ms, ms_profiled, kernel_sum_ms, e2e_ms] per rank
@@ -661,6 +664,8 @@ def main():
         "kernel_ms_per_step": {k: v[0] / args.steps for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])},
         "kernel_ms_per_step_note": "rank 0, from the second (profiled) pass; `value` comes from the first, un-profiled pass",
         "ms_per_rank": [r[0] / args.steps for r in per_rank],
+        "compute_ms_per_rank": [(r[0] - r[1]) / args.steps for r in per_rank],   # the same region without the final gather
+        "clocks_per_rank": [{"sm_mhz": c[0], "sm_mhz_min": c[1], "power_w_max": c[2], "sw_power_cap": bool(c[3])} for c in clocks_per_rank],
         "gather_ms_per_rank": [r[1] for r in per_rank],
         "slowest_rank": {"rank": slow, "ms_per_step": per_rank[slow][0] / args.steps,
                          "kernel_sum_ms_per_step": per_rank[slow][3] / args.steps,

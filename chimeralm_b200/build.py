@@ -27,6 +27,10 @@ def build(force: bool = False, verbose: bool = False) -> Path:
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     cmd = [nvcc, *NVCC_FLAGS, "-o", str(LIB), *map(str, SOURCES), "-lz"]
+    if os.environ.get("CLM_EXPERIMENTS") == "1":
+        # recorded-slower variants (block_mlp2 / block_mlp16 / block_mlp_pp, the first long-convolution kernel): not part of
+        # the product library; `clm_set_option` refuses their switches unless they were compiled in
+        cmd.insert(1, "-DCLM_EXPERIMENTS")
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     r = subprocess.run(cmd, capture_output=True, text=True)
