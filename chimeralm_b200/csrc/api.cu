@@ -17,6 +17,7 @@
 #include "block_in.cuh"
 #include "block_mlp.cuh"
 #ifdef CLM_EXPERIMENTS   // recorded-slower variants of the block tail and the first long-convolution kernel: not in the product build
+#include "block_in2.cuh"
 #include "block_mlp2.cuh"
 #include "block_mlp16.cuh"
 #include "block_mlp_pp.cuh"
@@ -168,6 +169,7 @@ struct clm_ctx {
   int mlp_fc2_lag = 1;    // block_mlp: fc2 of chunk j - lag is issued after fc1 of chunk j (2: recorded experiment, no faster)
   int mlp_grid = 0;       // block_mlp: cap on the number of CTAs (0 = one per SM); diagnostic
   bool mlp_pp = false;    // fused block tail with two interleaved fc1/GELU/fc2 chains of 64-unit chunks (block_mlp_pp.cuh)
+  bool in_2cta = false;         // block_in on CTA pairs (block_in2.cuh)
   bool skip_dead_res = true;    // the last block does not store its fp32 residual (nothing reads it)
   bool y_channel_major = true;  // block_mlp reads the conv output channel-major (MN-major UMMA operand): no transpose
   // debug
@@ -405,13 +407,27 @@ int launch_block_in(clm_ctx* c, int layer, const __nv_bfloat16* xn, int B, int T
   int rc;
   if ((rc = make_tmap_ct_bf16_3d(c, &tmVX, vx, B, c->cfg.d_model, Tp))) return rc;
   if ((rc = make_tmap_ct_bf16_3d(c, &tmX0, x0, B, c->cfg.d_model, Tp))) return rc;
+#ifdef CLM_EXPERIMENTS
+  const bool pair = c->in_2cta && c->num_sms >= 2;
+  if ((rc = make_tmap_xn(c, &tmXN, xn, B, T, pair ? bi2::HALF : bi::NCOL))) return rc;
+#else
   if ((rc = make_tmap_xn(c, &tmXN, xn, B, T, bi::NCOL))) return rc;
+#endif
   BlockInParams p{};
   p.b_in = L.in_bf; p.cw = L.sc_w; p.cb = L.sc_b;
   p.B = B; p.T = T; p.trace = trace; p.vx_f16 = vx_f16 ? 1 : 0;
   p.vx_scale = vx_f16 ? L.vx_scale : nullptr;   // fp16 rows carry a[ch] * v*x1 (undone by the conv's output scale)
   p.tiles_per_seq = (T + bi::BT - 1) / bi::BT;
   p.num_tiles = B * p.tiles_per_seq;
+#ifdef CLM_EXPERIMENTS
+  if (pair) {   // CTA pairs (cta_group::2): one tile per pair, each CTA half of the channels and half of the token rows
+    if (int rc_attr = ensure_smem_attr(c, (const void*)(block_in2_kernel), (int)(bi2::SMEM_TOTAL2))) return rc_attr;
+    const int grid2 = 2 * std::min(p.num_tiles, c->num_sms / 2);
+    block_in2_kernel<<<grid2, bi::THREADS, bi2::SMEM_TOTAL2, st>>>(L.tm_inf, tmVX, tmX0, tmXN, p);
+    CLM_LAUNCH_CHECK(c, "block_in2");
+    return 0;
+  }
+#endif
   const int grid = std::min(p.num_tiles, c->num_sms);
   block_in_kernel<<<grid, bi::THREADS, bi::SMEM_TOTAL, st>>>(L.tm_inf, tmVX, tmX0, tmXN, p);
   CLM_LAUNCH_CHECK(c, "block_in");
@@ -1467,11 +1483,12 @@ int clm_set_option(clm_ctx* c, const char* name, int value) {
   else if (n == "fused_in") c->fused_in = value != 0;
 #ifdef CLM_EXPERIMENTS
   else if (n == "fast_conv") c->fast_conv = value != 0;
+  else if (n == "in_2cta") c->in_2cta = value != 0;
   else if (n == "mlp_2cta") c->mlp_2cta = value != 0;
   else if (n == "mlp_epi16") c->mlp_epi16 = value != 0;
   else if (n == "mlp_pp") c->mlp_pp = value != 0;
 #else
-  else if (n == "fast_conv" || n == "mlp_2cta" || n == "mlp_epi16" || n == "mlp_pp")
+  else if (n == "fast_conv" || n == "in_2cta" || n == "mlp_2cta" || n == "mlp_epi16" || n == "mlp_pp")
     return fail(c, CLM_ERR_INVALID, "clm_set_option: '%s' selects an experiment kernel that is not compiled in (build with -DCLM_EXPERIMENTS)", name);
 #endif
   else if (n == "tc_conv") c->tc_conv = value != 0;
@@ -1482,6 +1499,7 @@ int clm_set_option(clm_ctx* c, const char* name, int value) {
   else if (n == "y_channel_major") c->y_channel_major = value != 0;
   else if (n == "mlp_grid") c->mlp_grid = value;
   else if (n == "skip_dead_res") c->skip_dead_res = value != 0;
+
   else if (n == "tc_scale_shift") {   // test hook: move the calibrated input scale of the tensor-core conv by 2^value
     if (!c->finalized) return fail(c, CLM_ERR_STATE, "clm_set_option(tc_scale_shift) before clm_finalize");
     CLM_CUDA(c, cudaDeviceSynchronize());

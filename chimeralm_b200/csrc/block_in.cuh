@@ -273,6 +273,7 @@ block_in_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
         }
         ptx::fence_proxy_async_smem();
         ptx::bar_sync(2, EPI_THREADS);
+        if (tr) stamp(1);   // x0 staged
         if (issuer) {
 #pragma unroll
           for (int hh = 0; hh < 2; ++hh) ptx::tma_store_3d(&tmX0, smem + OFF_STAGE + hh * STAGE_BOX, t0 + hh * 64, h * 128, b);
@@ -281,6 +282,7 @@ block_in_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
         // ---- set B: v * x1
         ptx::mbar_wait(&acc_full[1], pass & 1);
         ptx::tc_fence_after_sync();
+        if (tr) stamp(1);   // set B accumulated
         halo(1);
         halo(2);
 #pragma unroll 1
@@ -294,8 +296,10 @@ block_in_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
             if (lane == 0) ptx::mbar_arrive(&acc_free[1]);
           }
           if (s == 0) {   // the staging buffers are being read by the x0 store of this pass (long since issued)
+            if (tr) stamp(1);   // first half of set B convolved
             if (issuer) ptx::tma_store_wait_read<0>();
             ptx::bar_sync(1, EPI_THREADS);
+            if (tr) stamp(1);   // staging free again
           }
 #pragma unroll
           for (int k = 0; k < 4; ++k) {

@@ -23,7 +23,8 @@ for _ in range(2):
     torch.cuda.synchronize()
 t = tr.cpu()
 t0 = int(t[t > 0].min())
-print("per tile - mma: [tile start, xn_full seen, (acc_free seen, pass issued) x2]; epilogue: [tile start, xn_free seen, LN done, (pass start, acc_full seen, pass done) x2]")
+print("per tile - mma: [tile start, xn_full seen, (acc_free[0] seen, pass issued) x2]; epilogue: [tile start, (pass start = staging free, set A accumulated, "
+      "x0 staged, set B accumulated, first half of set B convolved, staging free again, pass done) x2]")
 for role, name in ((0, "mma"), (1, "epilogue(warp2)")):
     v = [int(x) - t0 for x in t[role] if x > 0]
     print(name, len(v))

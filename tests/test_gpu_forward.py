@@ -281,7 +281,7 @@ def test_full_size_batch_permutation_invariance(state_dict):
 
 @pytest.mark.parametrize("option,T", [("fused_score_pool", 1500), ("fused_head", 1500), ("tc_conv", 8193), ("tc_chunked", 9000),
                                       ("fused_mlp", 700), ("fused_in", 700), ("fast_conv", 700), ("mlp_epi16", 1500), ("mlp_pp", 8193), ("mlp_early_res", 8193), ("mlp_fc2_lag", 8193),
-                                      ("skip_dead_res", 700)])
+                                      ("skip_dead_res", 700), ("in_2cta", 700), ("in_2cta", 8193)])
 def test_kernel_variants_agree(state_dict, option, T):
     """Every `clm_set_option` switch selects a different kernel for the same math (fused vs unfused, tensor-core vs fp32 FFT,
     8 vs 16 epilogue warps): flipping it must not move the logits by more than the parity tolerance."""
@@ -294,7 +294,7 @@ def test_kernel_variants_agree(state_dict, option, T):
     try:
         ids = _ids(B, T, seed=T, pad_left=T // 4).to(torch.uint8).cuda()
         base = eng.forward(ids).clone()
-        default_on = option not in ("mlp_epi16", "mlp_pp")
+        default_on = option not in ("mlp_epi16", "mlp_pp", "in_2cta")
         try:
             eng.set_option(option, {"mlp_fc2_lag": 2}.get(option, 0 if default_on else 1))
         except ChimeraLMNativeError as e:
