@@ -46,6 +46,8 @@ struct clm_bam {
   FILE* f = nullptr;
   int n_threads = 1;
   size_t chunk_bytes = size_t(16) << 20;
+  size_t ramp_bytes = size_t(1) << 20;   // the first loads are short (1, 4, 16 MiB): the first reads come out after a 1 MiB
+                                         // inflate instead of a 16 MiB one (~0.1 s of start-up latency for the predict loop)
   std::string err;
   std::vector<uint8_t> cbuf;  // compressed bytes read but not yet inflated (partial block carry)
   bool file_eof = false;
@@ -68,10 +70,12 @@ Chunk clm_bam::load_chunk() {
   Chunk out;
   if (!file_eof) {
     size_t have = cbuf.size();
-    cbuf.resize(have + chunk_bytes);
-    size_t got = fread(cbuf.data() + have, 1, chunk_bytes, f);
+    const size_t want = std::min(chunk_bytes, ramp_bytes);
+    ramp_bytes = std::min(chunk_bytes, ramp_bytes * 4);
+    cbuf.resize(have + want);
+    size_t got = fread(cbuf.data() + have, 1, want, f);
     cbuf.resize(have + got);
-    if (got < chunk_bytes) {
+    if (got < want) {
       if (ferror(f)) {
         out.err = "read error";
         return out;
