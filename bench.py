@@ -266,9 +266,15 @@ def run_k2(args, eng, D, sampler):
         ev[2].record()
         return ev
 
-    # ---- `e2e`: through the C-ABI host entry point, H2D + D2H inside.  Measured FIRST, `value` right after it, the profiled
-    # pass last: the three share one clock / power state as far as a bench can arrange it (boxes at their power cap drift
-    # a few percent over the first seconds of load)
+    def settle():
+        # The board reaches its power cap within a few tenths of a second of this load and then drops from 1 965 MHz to
+        # 1 700-1 850 MHz (profiles/r2_e2e_gap.txt).  Every timed pass therefore starts from the same state: one second of
+        # idle, then the W warm-up steps - otherwise whichever pass happens to run first gets the higher clock.
+        torch.cuda.synchronize()
+        time.sleep(1.0)
+
+    # ---- `e2e`: through the C-ABI host entry point, H2D + D2H inside
+    settle()
     for i in range(args.warmup):
         step_resident(i)
     e2e_pipelined(eng, [(host_batches[i % N_DISTINCT], offsets_p, T, B) for i in range(args.warmup)], B)
@@ -282,12 +288,16 @@ def run_k2(args, eng, D, sampler):
         sampler.mark_end("k2_e2e")
     # and the plain synchronous call, one batch at a time (what a caller without a pipeline gets)
     lo = torch.empty(B, 2, dtype=torch.float32).pin_memory()
+    settle()
+    for i in range(args.warmup):
+        eng.predict_host(host_batches[i % N_DISTINCT], offsets_p, T, logits_out=lo, **ENC)
     D.barrier()
     t0 = time.perf_counter()
     for i in range(args.steps):
         eng.predict_host(host_batches[i % N_DISTINCT], offsets_p, T, logits_out=lo, **ENC)
     e2e_sync_s = time.perf_counter() - t0
     # ---- `value`: device-resident, un-profiled
+    settle()
     for i in range(args.warmup):
         step_resident(i)
     D.all_gather(torch.zeros(args.steps * B, dtype=torch.uint8, device=D.dev))   # NCCL's first collective of this shape is not a step
@@ -304,6 +314,9 @@ def run_k2(args, eng, D, sampler):
     assert eng.forward_status() is None
 
     # ---- second pass with per-launch CUDA events: kernel times for the roofline (not part of `value`)
+    settle()
+    for i in range(args.warmup):
+        step_resident(i)
     D.barrier()
     eng.profile_reset()
     eng.profile(True)
