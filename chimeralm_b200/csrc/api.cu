@@ -121,6 +121,9 @@ struct clm_ctx {
   int n_split = 1;
   // e2e staging
   cudaStream_t own_stream = nullptr;
+  // copies of the host entry points run on their own streams, so that batch k + 1's H2D and batch k - 1's D2H overlap
+  // batch k's kernels (one stream per direction: a D2H waits for its forward and must not hold the next H2D back)
+  cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
   // Staging of the host entry points: HOST_SLOTS independent sets, so that clm_predict_host_submit can copy and enqueue
   // batch k + 1 (and k + 2) while batch k is still running; slot 0's buffers double as the calibration forward's.
   static constexpr int HOST_SLOTS = 3;
@@ -130,7 +133,7 @@ struct clm_ctx {
     uint8_t* ids = nullptr;
     float* logits = nullptr;
     uint8_t* labels = nullptr;
-    cudaEvent_t done = nullptr;
+    cudaEvent_t done = nullptr, h2d_done = nullptr, fwd_done = nullptr;
     bool busy = false;
     long long seq = 0;
     int B = 0, T = 0;
@@ -821,6 +824,8 @@ int clm_create(const clm_config* cfg, int device, clm_ctx** out) {
   if (!fn || qres != cudaDriverEntryPointSuccess) return fail(c, CLM_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
   c->encode_tiled = reinterpret_cast<EncodeTiledFn>(fn);
   CLM_CUDA(c, cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+  CLM_CUDA(c, cudaStreamCreateWithFlags(&c->h2d_stream, cudaStreamNonBlocking));
+  CLM_CUDA(c, cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking));
   uint8_t lut[256];
   memset(lut, 6, sizeof lut);  // [UNK]
   lut['A'] = 7; lut['C'] = 8; lut['G'] = 9; lut['T'] = 10; lut['N'] = 11;
@@ -844,9 +849,12 @@ void clm_destroy(clm_ctx* c) {
     if (p) cudaFree(p);
   for (cudaEvent_t e : c->prof_pool) cudaEventDestroy(e);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
+  if (c->h2d_stream) cudaStreamDestroy(c->h2d_stream);
+  if (c->d2h_stream) cudaStreamDestroy(c->d2h_stream);
   if (c->h_status) cudaFreeHost(c->h_status);
   for (auto& sl : c->slot)
-    if (sl.done) cudaEventDestroy(sl.done);
+    for (cudaEvent_t e : {sl.done, sl.h2d_done, sl.fwd_done})
+      if (e) cudaEventDestroy(e);
   delete c;
 }
 
@@ -1160,7 +1168,8 @@ int clm_reserve_tokens(clm_ctx* c, int max_B, int max_T, long long max_tokens) {
     if ((rc = dev_alloc(c, &sl.logits, (size_t)max_B * 2))) return rc;
     if ((rc = dev_alloc(c, &sl.labels, (size_t)max_B))) return rc;
     if ((rc = dev_alloc(c, &sl.bases, M))) return rc;   // a read contributes at most one base per token
-    if (!sl.done) CLM_CUDA(c, cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
+    for (cudaEvent_t* e : {&sl.done, &sl.h2d_done, &sl.fwd_done})
+      if (!*e) CLM_CUDA(c, cudaEventCreateWithFlags(e, cudaEventDisableTiming));
   }
   c->st_bases_cap = M;
   c->max_B = max_B; c->max_T = max_T; c->Tp_max = Tp;   // only now: every workspace exists
@@ -1415,15 +1424,19 @@ int clm_predict_host_submit(clm_ctx* c, const uint8_t* h_bases, const int64_t* h
   clm_ctx::HostSlot& sl = c->slot[c->next_slot];
   if (sl.busy) return fail(c, CLM_ERR_STATE, "clm_predict_host_submit: %d batches are already in flight; call clm_predict_host_wait", clm_ctx::HOST_SLOTS);
   cudaStream_t st = c->own_stream;
-  CLM_CUDA(c, cudaMemcpyAsync(sl.bases, h_bases, nbytes, cudaMemcpyHostToDevice, st));
-  CLM_CUDA(c, cudaMemcpyAsync(sl.offsets, h_offsets, (size_t)(B + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+  CLM_CUDA(c, cudaMemcpyAsync(sl.bases, h_bases, nbytes, cudaMemcpyHostToDevice, c->h2d_stream));
+  CLM_CUDA(c, cudaMemcpyAsync(sl.offsets, h_offsets, (size_t)(B + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, c->h2d_stream));
+  CLM_CUDA(c, cudaEventRecord(sl.h2d_done, c->h2d_stream));
+  CLM_CUDA(c, cudaStreamWaitEvent(st, sl.h2d_done, 0));
   int rc = clm_encode_batch(c, sl.bases, sl.offsets, B, T_pad, add_cls, add_sep, pad_left, max_bases, sl.ids, nullptr, st);
   if (rc) return rc;
   rc = clm_forward(c, sl.ids, CLM_U8, B, T_pad, sl.logits, sl.labels, st);
   if (rc) return rc;
-  CLM_CUDA(c, cudaMemcpyAsync(h_logits, sl.logits, (size_t)B * 2 * sizeof(float), cudaMemcpyDeviceToHost, st));
-  if (h_labels) CLM_CUDA(c, cudaMemcpyAsync(h_labels, sl.labels, (size_t)B, cudaMemcpyDeviceToHost, st));
-  CLM_CUDA(c, cudaEventRecord(sl.done, st));
+  CLM_CUDA(c, cudaEventRecord(sl.fwd_done, st));
+  CLM_CUDA(c, cudaStreamWaitEvent(c->d2h_stream, sl.fwd_done, 0));
+  CLM_CUDA(c, cudaMemcpyAsync(h_logits, sl.logits, (size_t)B * 2 * sizeof(float), cudaMemcpyDeviceToHost, c->d2h_stream));
+  if (h_labels) CLM_CUDA(c, cudaMemcpyAsync(h_labels, sl.labels, (size_t)B, cudaMemcpyDeviceToHost, c->d2h_stream));
+  CLM_CUDA(c, cudaEventRecord(sl.done, c->d2h_stream));
   sl.busy = true; sl.seq = c->fwd_seq; sl.B = B; sl.T = T_pad; sl.h_logits = h_logits; sl.h_labels = h_labels;
   *ticket = c->next_slot;
   c->next_slot = (c->next_slot + 1) % clm_ctx::HOST_SLOTS;
