@@ -601,3 +601,29 @@ def test_bucketed_predict_flow_matches_per_read_forward(tmp_path, state_dict):
             assert [preds[n] for n in names] == logits.argmax(1).tolist()
     finally:
         model.engine.close()
+
+
+def test_single_sequence_predictor(state_dict):
+    """`ChimeraLMPredictor.predict` (reference chimeralm/ui.py:36-79 without Gradio): validation messages, and the
+    probabilities of one sequence against softmax(oracle logits) on the reference's tokenisation of it (max_length 32 768:
+    the web path keeps 32 767 bases + [SEP])."""
+    from chimeralm_b200.model import ClassificationLit
+    from chimeralm_b200.predictor import ChimeraLMPredictor
+    from oracle import hyena_oracle as O
+    from oracle import tokenizer_oracle as TO
+
+    model = ClassificationLit(state_dict, device=0, max_batch=1, max_tokens=32769)
+    try:
+        pr = ChimeraLMPredictor(model)
+        assert pr.predict("  ")[0] == "Please enter a DNA sequence"
+        assert pr.predict("ACGTX")[0].startswith("Invalid characters")
+        g = torch.Generator().manual_seed(3)
+        seq = "".join("ACGTN"[int(x)] for x in torch.randint(0, 5, (1500,), generator=g)).lower()
+        name, conf, breakdown = pr.predict(seq)
+        ids = torch.tensor([TO.encode(seq.upper(), max_length=32768, add_cls=False)])
+        ref = torch.softmax(O.forward(state_dict, ids, CFG), dim=-1)[0]
+        assert name == ["Biological", "Chimeric Artifact"][int(ref.argmax())]
+        assert abs(conf - ref.max().item()) <= 1e-3
+        assert breakdown == {"Biological": f"{ref[0].item():.3f}", "Chimeric Artifact": f"{ref[1].item():.3f}"}
+    finally:
+        model.engine.close()
