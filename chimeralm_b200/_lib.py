@@ -22,7 +22,9 @@ class clm_config(C.Structure):
     _fields_ = [(n, C.c_int) for n in (
         "d_model", "n_layer", "d_inner", "vocab_rows", "max_seq_len", "filter_order", "emb_dim",
         "short_filter_order", "num_inner_mlps", "head_hidden", "num_classes")] + [
-        ("layer_norm_eps", C.c_float), ("filter_shift", C.c_float)]
+        ("layer_norm_eps", C.c_float), ("filter_shift", C.c_float), ("pooling", C.c_int)]
+
+POOLING = {"attention": 0, "mean": 1, "max": 2, "cls": 3}
 
 
 class ChimeraLMNativeError(RuntimeError):

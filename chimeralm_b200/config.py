@@ -40,6 +40,9 @@ class HyenaConfig:
     head_hidden: int = 512
     head_num_layers: int = 2
     num_classes: int = 2
+    # BinarySequenceClassifier.pooling_type (components/hyena.py:22): "attention" is what ChimeraLM uses (lm.py:46-55);
+    # "mean", "max" and "cls" are the head's other modes (no scorer weights in the state dict then)
+    pooling_type: str = "attention"
 
     @property
     def vocab_rows(self) -> int:

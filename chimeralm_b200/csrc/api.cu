@@ -790,6 +790,7 @@ void clm_default_config(clm_config* cfg) {
   cfg->filter_order = 64; cfg->emb_dim = 5; cfg->short_filter_order = 3; cfg->num_inner_mlps = 2;
   cfg->head_hidden = 512; cfg->num_classes = 2;
   cfg->layer_norm_eps = 1e-5f; cfg->filter_shift = 0.05f;
+  cfg->pooling = 0;
 }
 
 const char* clm_version(void) { return "chimeralm_b200 0.1 (sm_100a)"; }
@@ -804,7 +805,7 @@ int clm_create(const clm_config* cfg, int device, clm_ctx** out) {
   // The kernels are specialised for the named architecture; refuse anything else loudly.
   if (cfg->d_model != 256 || cfg->d_inner != 1024 || cfg->head_hidden != 512 || cfg->num_classes != 2 ||
       cfg->short_filter_order != 3 || cfg->filter_order > 64 || cfg->num_inner_mlps != 2 || cfg->n_layer < 1 ||
-      cfg->vocab_rows < 1 || cfg->vocab_rows > 16)
+      cfg->vocab_rows < 1 || cfg->vocab_rows > 16 || cfg->pooling < 0 || cfg->pooling > 3)
     return CLM_ERR_INVALID;
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return CLM_ERR_CUDA;
@@ -1052,11 +1053,20 @@ int clm_finalize(clm_ctx* c) {
   c->head_base = 0;
   // head
   const float *a0w, *a2b;
-  NEED(HD + "attention.0.weight", (int64_t)D * D, &a0w);
-  NEED(HD + "attention.0.bias", D, &c->att0_b);
-  NEED(HD + "attention.2.weight", D, &c->att2_w);
-  NEED(HD + "attention.2.bias", 1, &a2b);
-  CLM_CUDA(c, cudaMemcpy(&c->att2_b, a2b, sizeof(float), cudaMemcpyDeviceToHost));
+  if (g.pooling == 0) {
+    NEED(HD + "attention.0.weight", (int64_t)D * D, &a0w);
+    NEED(HD + "attention.0.bias", D, &c->att0_b);
+    NEED(HD + "attention.2.weight", D, &c->att2_w);
+    NEED(HD + "attention.2.bias", 1, &a2b);
+    CLM_CUDA(c, cudaMemcpy(&c->att2_b, a2b, sizeof(float), cudaMemcpyDeviceToHost));
+  } else {
+    // mean / max / cls pooling: the module has no scorer (components/hyena.py:50-53); the kernels still run the scorer
+    // GEMM on zero weights and ignore its scores, so the one fused tail serves every pooling type
+    float* z = nullptr;
+    if ((rc = dev_alloc(c, &z, (size_t)D * D + 2 * D))) return rc;
+    CLM_CUDA(c, cudaMemset(z, 0, ((size_t)D * D + 2 * D) * sizeof(float)));
+    a0w = z; c->att0_b = z + (size_t)D * D; c->att2_w = z + (size_t)D * D + D; c->att2_b = 0.f;
+  }
   if ((rc = to_bf16(c, a0w, (int64_t)D * D, &c->att0_w))) return rc;
   if ((rc = make_tmap_bf16_2d(c, &c->tm_att0, c->att0_w, D, D, 256))) return rc;
   {
@@ -1324,6 +1334,7 @@ int clm_forward(clm_ctx* c, const void* d_ids, int ids_dtype, int B, int T, floa
     sp_.b0 = c->att0_bf; sp_.w2 = c->att2_w; sp_.b2 = c->att2_b; sp_.g = c->lnf_g; sp_.beta = c->lnf_b;
     sp_.score = c->score; sp_.part = c->part; sp_.B = B; sp_.T = T;
     sp_.tiles_per_seq = (T + sp::BM - 1) / sp::BM; sp_.num_tiles = B * sp_.tiles_per_seq;
+    sp_.pool_mode = g.pooling;
     n_split = sp_.tiles_per_seq;
     score_pool_kernel<<<std::min(sp_.num_tiles, c->num_sms), sp::THREADS, sp::SMEM_TOTAL, st>>>(tmA, c->tm_att0f, sp_);
     CLM_LAUNCH_CHECK(c, "score_pool");
@@ -1347,7 +1358,7 @@ int clm_forward(clm_ctx* c, const void* d_ids, int ids_dtype, int B, int T, floa
     layernorm_bf16_kernel<<<rows32, 256, 0, st>>>(c->R, c->ones, c->zeros, c->XN, M, g.layer_norm_eps);
     CLM_LAUNCH_CHECK(c, "normalize_for_pool");
   }
-  pool_partial_kernel<<<dim3(c->n_split, B), 256, 0, st>>>(c->XN, c->score, c->lnf_g, c->lnf_b, c->part, T, c->n_split);
+  pool_partial_kernel<<<dim3(c->n_split, B), 256, 0, st>>>(c->XN, c->score, c->lnf_g, c->lnf_b, c->part, T, c->n_split, g.pooling);
   CLM_LAUNCH_CHECK(c, "pool_partial"); }
   STOP_AFTER(NL, 12);
   }
@@ -1362,7 +1373,7 @@ int clm_forward(clm_ctx* c, const void* d_ids, int ids_dtype, int B, int T, floa
       hf.wo = hp.wo; hf.bo = hp.bo;
       hf.pooled = c->pooled; hf.h0 = c->hbuf[0]; hf.h1 = c->hbuf[1]; hf.h2 = c->hbuf[2]; hf.h3 = c->hbuf[3];
       hf.logits = d_logits; hf.labels = d_labels; hf.counter = c->head_counter; hf.base = c->head_base; hf.B = B;
-      hf.err = c->d_err; hf.status_out = status_slot; hf.status_tag = status_tag;
+      hf.err = c->d_err; hf.status_out = status_slot; hf.status_tag = status_tag; hf.pool_mode = g.pooling;
       const int grid = H / 8;
       void* args[] = {&hf};
       constexpr size_t head_smem = (size_t)HEAD_BT * 512 * sizeof(float);
@@ -1373,7 +1384,7 @@ int clm_forward(clm_ctx* c, const void* d_ids, int ids_dtype, int B, int T, floa
       // a rejected launch must not move the host's idea of the counter ahead of the device's.
       c->head_base += 5u * (unsigned)grid;
     } else {
-    pool_merge_kernel<<<B, 256, 0, st>>>(c->part, n_split, c->pooled);
+    pool_merge_kernel<<<B, 256, 0, st>>>(c->part, n_split, c->pooled, g.pooling);
     CLM_LAUNCH_CHECK(c, "pool_merge");
     head_layer_kernel<256, true, false, false><<<dim3(H / 8, (B + 31) / 32), 256, 0, st>>>(hp.w0, hp.b0, c->pooled, nullptr, c->hbuf[0], nullptr, B, H);
     CLM_LAUNCH_CHECK(c, "head_l0");

@@ -245,7 +245,7 @@ __global__ void __launch_bounds__(256) transpose_ct_kernel(const __nv_bfloat16* 
 __global__ void __launch_bounds__(256) pool_partial_kernel(const __nv_bfloat16* __restrict__ XN, const float* __restrict__ score,
                                                            const float* __restrict__ g, const float* __restrict__ bta,
                                                            float* __restrict__ part,  // [B][S][2+D]
-                                                           int T, int n_split) {
+                                                           int T, int n_split, int pool_mode) {
   // XN = (r - mean) * rstd of the final residual (bf16, token-major, emitted by the last block or the LayerNorm
   // kernel with unit affine); ln_f's gamma/beta are applied ONCE to the pooled sum: sum_t w_t (xn_t g + b) =
   // g * sum_t w_t xn_t + b * sum_t w_t.  One warp per token row (512 contiguous bytes), 8 bf16 per lane.
@@ -262,8 +262,27 @@ __global__ void __launch_bounds__(256) pool_partial_kernel(const __nv_bfloat16* 
   for (int t = tb + warp; t < te; t += 8) {
     const long long row = (long long)b * T + t;
     const uint4 raw = __ldg(reinterpret_cast<const uint4*>(XN + row * D) + lane);
-    const float sc = __ldg(score + row);
+    float sc = __ldg(score + row);
+    if (pool_mode == 1) sc = 0.f;                                  // mean: uniform weights
+    else if (pool_mode == 3) {                                     // cls: position 0 only
+      if (t != 0) continue;
+      sc = 0.f;
+    }
     const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+    if (pool_mode == 2) {   // max: acc[] carries the running max, m/l are unused; negative gammas are handled by the caller's
+                            // sign trick below (max of gamma * x = gamma * (gamma >= 0 ? max x : min x)) - here per element
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int c0 = lane * 8 + 2 * i;
+        const float g0 = __ldg(g + c0), g1 = __ldg(g + c0 + 1);
+        const float h0 = g0 * __uint_as_float(w[i] << 16), h1 = g1 * __uint_as_float(w[i] & 0xffff0000u);
+        acc[2 * i] = (l == 0.f) ? h0 : fmaxf(acc[2 * i], h0);
+        acc[2 * i + 1] = (l == 0.f) ? h1 : fmaxf(acc[2 * i + 1], h1);
+      }
+      l = 1.f;
+      m = 0.f;
+      continue;
+    }
     const float mn = fmaxf(m, sc);
     const float corr = __expf(m - mn);  // exp(-inf) = 0 on the first step
     const float pw = __expf(sc - mn);
@@ -288,6 +307,14 @@ __global__ void __launch_bounds__(256) pool_partial_kernel(const __nv_bfloat16* 
     const float f = (sm_m[w] == -INFINITY) ? 0.f : __expf(sm_m[w] - M);
     a += sm_acc[w][d] * f;
     L += sm_l[w] * f;
+  }
+  if (pool_mode == 2) {   // max over the warps' running maxima of gamma * xn; + beta
+    float mx = -INFINITY;
+    for (int w = 0; w < 8; ++w)
+      if (sm_l[w] > 0.f) mx = fmaxf(mx, sm_acc[w][d]);
+    out[2 + d] = mx + __ldg(bta + d);
+    if (d == 0) { out[0] = 0.f; out[1] = mx == -INFINITY ? 0.f : 1.f; }
+    return;
   }
   out[2 + d] = a * __ldg(g + d) + L * __ldg(bta + d);   // ln_f affine applied to the (unnormalised) weighted sum
   if (d == 0) { out[0] = M; out[1] = L; }
@@ -336,10 +363,18 @@ __device__ __forceinline__ float gelu_erf_h(float x) { return 0.5f * x * (1.0f +
 // Head as a chain of small kernels in which every weight row is read ONCE for the whole batch (a one-CTA-per-read
 // head streamed all 4 MB of head weights per read; at batch 32 that is 128 MB through L2).  Unfused path; the fused
 // head_fused_kernel below is what clm_forward launches.
-__global__ void __launch_bounds__(256) pool_merge_kernel(const float* __restrict__ part, int n_split, float* __restrict__ pooled) {
+__global__ void __launch_bounds__(256) pool_merge_kernel(const float* __restrict__ part, int n_split, float* __restrict__ pooled,
+                                                         int pool_mode) {
   constexpr int D = 256;
   const int b = blockIdx.x, d = threadIdx.x;
   const float* pp = part + (long long)b * n_split * (2 + D);
+  if (pool_mode == 2) {   // max pooling: the partials hold per-slice maxima
+    float mx = -INFINITY;
+    for (int s = 0; s < n_split; ++s)
+      if (pp[s * (2 + D) + 1] > 0.f) mx = fmaxf(mx, pp[s * (2 + D) + 2 + d]);
+    pooled[(long long)b * D + d] = mx;
+    return;
+  }
   float M = -INFINITY;
   for (int s = 0; s < n_split; ++s) M = fmaxf(M, pp[s * (2 + D)]);
   float a = 0.f, L = 0.f;
@@ -404,6 +439,7 @@ struct HeadFusedParams {
   unsigned int* counter;
   unsigned int base;  // counter value before this launch
   int B;
+  int pool_mode;      // 2 = max pooling (the partials are maxima); otherwise softmax-weighted sums
   int* err;           // status word of the forward in flight (may be null)
   int* status_out;    // mapped host slot that receives (status_tag | *err) when the forward is complete (may be null)
   int status_tag;     // forward sequence number << 8
@@ -487,6 +523,13 @@ __global__ void __launch_bounds__(256) head_fused_kernel(HeadFusedParams p) {
   for (int b = blockIdx.x; b < p.B; b += G) {
     const int d = threadIdx.x;
     const float* pp = p.part + (long long)b * p.n_split * (2 + D);
+    if (p.pool_mode == 2) {   // max pooling: the partials hold per-tile maxima
+      float mx = -INFINITY;
+      for (int s = 0; s < p.n_split; ++s)
+        if (pp[s * (2 + D) + 1] > 0.f) mx = fmaxf(mx, pp[s * (2 + D) + 2 + d]);
+      p.pooled[(long long)b * D + d] = mx;
+      continue;
+    }
     float M = -INFINITY;
     for (int s = 0; s < p.n_split; ++s) M = fmaxf(M, pp[s * (2 + D)]);
     float a = 0.f, L = 0.f;

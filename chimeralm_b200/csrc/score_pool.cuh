@@ -24,6 +24,11 @@ struct ScorePoolParams {
   float* score;        // [B*T] (kept for clm_attention_weights and debugging)
   float* part;         // [B][tiles_per_seq][2 + 256]: (m, l, v)
   int B, T, tiles_per_seq, num_tiles;
+  // Pooling of BinarySequenceClassifier (chimeralm/models/components/hyena.py:97-136, mask == None): 0 attention (what
+  // ChimeraLM uses, lm.py:46-55), 1 mean = uniform weights, 2 max over the sequence per channel, 3 cls = position 0 only.
+  // Mean and cls are the attention machinery with fixed scores; max keeps (max, min) per channel because ln_f's gamma may
+  // be negative.
+  int pool_mode;
 };
 
 namespace sp {
@@ -178,10 +183,20 @@ score_pool_kernel(const __grid_constant__ CUtensorMap tmXN, const __grid_constan
         s1 = 32 + lane < valid ? x1 : -INFINITY;
         s2 = 64 + lane < valid ? x2 : -INFINITY;
         s3 = 96 + lane < valid ? x3 : -INFINITY;
+        if (p.pool_mode == 1 || p.pool_mode == 2) {          // mean (and the bookkeeping of max): every position weighs the same
+          s0 = lane < valid ? 0.f : -INFINITY;
+          s1 = 32 + lane < valid ? 0.f : -INFINITY;
+          s2 = 64 + lane < valid ? 0.f : -INFINITY;
+          s3 = 96 + lane < valid ? 0.f : -INFINITY;
+        } else if (p.pool_mode == 3) {                        // cls: only position 0 of the read
+          s0 = (t0 == 0 && lane == 0) ? 0.f : -INFINITY;
+          s1 = s2 = s3 = -INFINITY;
+        }
       }
       float m = fmaxf(fmaxf(s0, s1), fmaxf(s2, s3));
       for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-      const float p0 = __expf(s0 - m), p1 = __expf(s1 - m), p2 = __expf(s2 - m), p3 = __expf(s3 - m);   // exp(-inf) = 0
+      const float mz = (m == -INFINITY) ? 0.f : m;   // a tile with no weight at all (cls, tiles after the first): p = 0, l = 0
+      const float p0 = __expf(s0 - mz), p1 = __expf(s1 - mz), p2 = __expf(s2 - mz), p3 = __expf(s3 - mz);   // exp(-inf) = 0
       float l = (p0 + p1) + (p2 + p3);
       for (int o = 16; o; o >>= 1) l += __shfl_xor_sync(0xffffffffu, l, o);
       if (e == 0) {
@@ -198,15 +213,27 @@ score_pool_kernel(const __grid_constant__ CUtensorMap tmXN, const __grid_constan
         const int c = tid, kb = c >> 6, cc = c & 63;
         const uint8_t* base = smem + OFF_A + kb * A_KB + (cc & 7) * 2;
         const uint32_t chunk = uint32_t(cc >> 3);
-        float v = 0.f;
-#pragma unroll 8
-        for (int t = 0; t < BM; ++t) {
-          const unsigned short h = *reinterpret_cast<const unsigned short*>(base + t * 128 + ((chunk ^ uint32_t(t & 7)) << 4));
-          v = fmaf(s_p[t], __uint_as_float(uint32_t(h) << 16), v);
-        }
         float* out = p.part + ((long long)b * p.tiles_per_seq + ts) * (2 + D);
-        out[2 + c] = v * gam + l * bet;
-        if (c == 0) { out[0] = m; out[1] = l; }
+        if (p.pool_mode == 2) {   // max over the tile's valid positions of ln_f(x)[c] = gamma xn + beta
+          float hi = -INFINITY, lo = INFINITY;
+          for (int t = 0; t < valid; ++t) {
+            const unsigned short h = *reinterpret_cast<const unsigned short*>(base + t * 128 + ((chunk ^ uint32_t(t & 7)) << 4));
+            const float x = __uint_as_float(uint32_t(h) << 16);
+            hi = fmaxf(hi, x);
+            lo = fminf(lo, x);
+          }
+          out[2 + c] = (gam >= 0.f ? hi : lo) * gam + bet;
+          if (c == 0) { out[0] = 0.f; out[1] = 1.f; }
+        } else {
+          float v = 0.f;
+#pragma unroll 8
+          for (int t = 0; t < BM; ++t) {
+            const unsigned short h = *reinterpret_cast<const unsigned short*>(base + t * 128 + ((chunk ^ uint32_t(t & 7)) << 4));
+            v = fmaf(s_p[t], __uint_as_float(uint32_t(h) << 16), v);
+          }
+          out[2 + c] = v * gam + l * bet;
+          if (c == 0) { out[0] = m; out[1] = l; }
+        }
       }
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(a_empty);   // tile and s_part / s_p may be overwritten

@@ -42,6 +42,9 @@ class Engine:
         ccfg.short_filter_order, ccfg.num_inner_mlps = cfg.short_filter_order, cfg.num_inner_mlps
         ccfg.head_hidden, ccfg.num_classes = cfg.head_hidden, cfg.num_classes
         ccfg.layer_norm_eps, ccfg.filter_shift = cfg.layer_norm_epsilon, cfg.shift
+        if cfg.pooling_type not in _lib.POOLING:
+            raise ValueError(f"Unsupported pooling type: {cfg.pooling_type}")   # the reference's message (components/hyena.py:135)
+        ccfg.pooling = _lib.POOLING[cfg.pooling_type]
         self.ctx = C.c_void_p()
         rc = self.lib.clm_create(C.byref(ccfg), self.device.index or 0, C.byref(self.ctx))
         if rc < 0:

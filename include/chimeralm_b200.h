@@ -41,6 +41,10 @@ typedef struct {
   int filter_order, emb_dim, short_filter_order, num_inner_mlps;
   int head_hidden, num_classes;
   float layer_norm_eps, filter_shift;
+  /* pooling of the head (BinarySequenceClassifier.pooling_type, chimeralm/models/components/hyena.py:22,97-136; no mask on
+   * the predict path): 0 attention (what ChimeraLM uses, chimeralm/models/lm.py:46-55), 1 mean, 2 max, 3 cls.  With a
+   * pooling other than attention the `net.head.attention.*` tensors are not required. */
+  int pooling;
 } clm_config;
 
 void clm_default_config(clm_config* cfg);

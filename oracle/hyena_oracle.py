@@ -103,7 +103,8 @@ def backbone(sd, input_ids: torch.Tensor, cfg) -> torch.Tensor:
     return F.layer_norm(h, (cfg.d_model,), sd[BB + "ln_f.weight"], sd[BB + "ln_f.bias"], cfg.layer_norm_epsilon)
 
 
-def head(sd, hidden: torch.Tensor, return_attention: bool = False, return_features: bool = False):
+def head(sd, hidden: torch.Tensor, return_attention: bool = False, return_features: bool = False,
+         pooling: str = "attention"):
     """BinarySequenceClassifier.forward(hidden, attention_mask=None), attention pooling.
 
     components/hyena.py:117-132: scores = Linear(256->1)(GELU(Linear(256->256)(h)));
@@ -112,11 +113,21 @@ def head(sd, hidden: torch.Tensor, return_attention: bool = False, return_featur
     ResidualBlock(512) then output_layer Lin(512,2); dropouts are identity in eval.
     GELU here is the exact-erf flavour (nn.GELU default).
     """
-    a = F.linear(hidden, sd[HD + "attention.0.weight"], sd[HD + "attention.0.bias"])
-    a = F.gelu(a)
-    s = F.linear(a, sd[HD + "attention.2.weight"], sd[HD + "attention.2.bias"])  # [B,T,1]
-    w = torch.softmax(s, dim=1)
-    pooled = (hidden * w).sum(dim=1)
+    w = None
+    if pooling == "attention":
+        a = F.linear(hidden, sd[HD + "attention.0.weight"], sd[HD + "attention.0.bias"])
+        a = F.gelu(a)
+        s = F.linear(a, sd[HD + "attention.2.weight"], sd[HD + "attention.2.bias"])  # [B,T,1]
+        w = torch.softmax(s, dim=1)
+        pooled = (hidden * w).sum(dim=1)
+    elif pooling == "mean":      # components/hyena.py:97-106 with attention_mask None
+        pooled = hidden.mean(dim=1)
+    elif pooling == "max":       # :107-115
+        pooled = hidden.max(dim=1)[0]
+    elif pooling == "cls":       # :134-136: the FIRST position
+        pooled = hidden[:, 0, :]
+    else:
+        raise ValueError(f"Unsupported pooling type: {pooling}")
     x = F.gelu(F.linear(pooled, sd[HD + "classifier.0.weight"], sd[HD + "classifier.0.bias"]))
     x = F.gelu(F.linear(x, sd[HD + "classifier.3.weight"], sd[HD + "classifier.3.bias"]))
     r = F.linear(x, sd[HD + "classifier.6.layers.0.weight"], sd[HD + "classifier.6.layers.0.bias"])
@@ -136,9 +147,10 @@ def forward(sd, input_ids: torch.Tensor, cfg, return_hidden: bool = False, retur
     """ClassificationLit.forward (basic_module.py:67-77) -> logits [B,2] float32."""
     input_ids = input_ids.long()
     h = backbone(sd, input_ids, cfg)
+    pooling = getattr(cfg, "pooling_type", "attention")
     if return_features:
-        return head(sd, h, return_features=True)
-    logits = head(sd, h)
+        return head(sd, h, return_features=True, pooling=pooling)
+    logits = head(sd, h, pooling=pooling)
     if return_hidden:
         return logits, h
     return logits

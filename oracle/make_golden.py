@@ -94,6 +94,16 @@ def head_golden():
         out[f"{tag}_shape"] = np.array(shape)
         out[f"{tag}_logits"] = logits.numpy()
         out[f"{tag}_attn"] = head.attention_weights.squeeze(-1).numpy()
+    # the head's other pooling modes (components/hyena.py:97-115,134-136): no scorer in the module, same classifier weights
+    for pooling in ("mean", "max", "cls"):
+        alt = m.BinarySequenceClassifier(input_dim=256, hidden_dim=512, num_layers=2, dropout=0.1, pooling_type=pooling,
+                                         activation="gelu", use_residual=True).eval()
+        sd = perturb_norms(make_state_dict(0), 1)
+        hsd = {k[len(HEAD_PREFIX):]: v for k, v in sd.items() if k.startswith(HEAD_PREFIX) and ".attention." not in k}
+        alt.load_state_dict(hsd, strict=True)
+        hidden = torch.randn((3, 37, 256), generator=torch.Generator().manual_seed(100))
+        with torch.inference_mode():
+            out[f"a_logits_{pooling}"] = alt(hidden, None).numpy()
     out["head_param_count"] = np.array(sum(p.numel() for p in head.parameters()))
     out["head_keys"] = np.array(sorted(head.state_dict().keys()))
     return out

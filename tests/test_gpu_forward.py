@@ -627,3 +627,34 @@ def test_single_sequence_predictor(state_dict):
         assert breakdown == {"Biological": f"{ref[0].item():.3f}", "Chimeric Artifact": f"{ref[1].item():.3f}"}
     finally:
         model.engine.close()
+
+
+@pytest.mark.parametrize("pooling", ["mean", "max", "cls"])
+@pytest.mark.parametrize("fused", [True, False])
+def test_other_pooling_modes(state_dict, pooling, fused):
+    """`BinarySequenceClassifier.pooling_type` other than attention (components/hyena.py:97-115,134-136, mask None): mean over
+    all positions, max over the sequence, the first position.  The oracle head is pinned on the reference class for each
+    mode; the state dict carries no scorer weights then.  Both the fused tail and the unfused path."""
+    import dataclasses
+
+    from chimeralm_b200.engine import Engine
+    from oracle import hyena_oracle as O
+
+    cfg = dataclasses.replace(CFG, pooling_type=pooling)
+    sd = {k: v for k, v in state_dict.items() if ".head.attention." not in k}
+    B, T = 3, 1000
+    ids = _ids(B, T, seed=13, pad_left=300)
+    ref = O.forward(sd, ids, cfg)
+    eng = Engine(sd, device=0, cfg=cfg, max_batch=B, max_tokens=T)
+    try:
+        if not fused:
+            eng.set_option("fused_score_pool", 0)
+            eng.set_option("fused_head", 0)
+        logits = eng.forward(ids.to(torch.uint8).cuda(), check=True).cpu()
+        err = (logits - ref).abs().max().item()
+        print(f"pooling={pooling} fused={fused}: logits max|err| {err:.3e}")
+        assert err <= LOGIT_TOL, err   # measured 1.3e-4 (mean), 3.6e-4 (max: ONE bf16-rounded position per channel), 2.2e-4 (cls)
+    finally:
+        eng.close()
+    with pytest.raises(ValueError):
+        Engine(sd, device=0, cfg=dataclasses.replace(CFG, pooling_type="median"), max_batch=1, max_tokens=64)
