@@ -49,6 +49,7 @@ struct LayerW {
   __nv_bfloat16* in_wf = nullptr;
   float* in_bf = nullptr;
   CUtensorMap tm_inf;
+  CUtensorMap tm_inf_h;   // same buffer, one k-block (128 rows) per box: the CTA-pair kernel's 16 KB slots
   // block_mlp operands, pre-tiled [N/rt][K/64][rt][64] so that every 32 KB ring slot is one TMA box
   __nv_bfloat16 *out_wt = nullptr, *fc1_wt = nullptr, *fc2_wt = nullptr;
   CUtensorMap tm_out_t, tm_fc1_t, tm_fc2_t;
@@ -426,7 +427,7 @@ int launch_block_in(clm_ctx* c, int layer, const __nv_bfloat16* xn, int B, int T
   if (pair) {   // CTA pairs (cta_group::2): one tile per pair, each CTA half of the channels and half of the token rows
     if (int rc_attr = ensure_smem_attr(c, (const void*)(block_in2_kernel), (int)(bi2::SMEM_TOTAL2))) return rc_attr;
     const int grid2 = 2 * std::min(p.num_tiles, c->num_sms / 2);
-    block_in2_kernel<<<grid2, bi::THREADS, bi2::SMEM_TOTAL2, st>>>(L.tm_inf, tmVX, tmX0, tmXN, p);
+    block_in2_kernel<<<grid2, bi::THREADS, bi2::SMEM_TOTAL2, st>>>(L.tm_inf_h, tmVX, tmX0, tmXN, p);
     CLM_LAUNCH_CHECK(c, "block_in2");
     return 0;
   }
@@ -957,6 +958,9 @@ int clm_finalize(clm_ctx* c) {
       fold_ln_kernel<<<3 * D, 256>>>(in_w, L.in_b, L.ln1_g, L.ln1_b, wf, L.in_bf, D);
       CLM_LAUNCH_CHECK(c, "fold_ln");
       if ((rc = retile(c, wf, 3 * D, D, 128, &L.in_wf, &L.tm_inf))) return rc;
+#ifdef CLM_EXPERIMENTS
+      if ((rc = make_tmap_retiled(c, &L.tm_inf_h, L.in_wf, (long long)3 * D * D / 64, 128))) return rc;
+#endif
     }
     if ((rc = make_tmap_bf16_2d(c, &L.tm_out, L.out_w, D, D, 128))) return rc;
     if ((rc = make_tmap_bf16_2d(c, &L.tm_fc1, L.fc1_w, g.d_inner, D, 128))) return rc;

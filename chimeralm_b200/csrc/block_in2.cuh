@@ -28,12 +28,18 @@ constexpr int HALF = NCOL / 2;                                  // 72 token rows
 constexpr int KB_HALF_BYTES = HALF * 128;                       // 9216: one k-block of this CTA's rows
 constexpr int XN_HALF_BYTES = 4 * KB_HALF_BYTES;                // 36864
 constexpr int NXN = 2;                                          // token tile double-buffered
-constexpr int NSLOT2 = 3;
+// Weight ring: SEVEN slots of ONE k-block (16 KB: this CTA's 128 channels x 64 k).  The pair's slot round trip (both CTAs'
+// TMA -> leader's barrier -> MMA -> multicast commit -> both producers) is longer than a single CTA's: with 3 x 32 KB the
+// tile's 48 MMAs took 7-8 K cycles to issue, with 4 x 32 KB 3.9 K (profiles/r2_trace_block_in.txt); 4 x 32 KB does not fit
+// next to two token buffers, 7 x 16 KB does.
+constexpr int SLOT2_BYTES = 128 * 64 * 2;                       // 16 KB
+constexpr int NSLOT2 = 7;
 constexpr int OFF_XN2 = 0;
 constexpr int OFF_W2 = OFF_XN2 + NXN * XN_HALF_BYTES;           // 73728
-constexpr int OFF_STAGE2 = OFF_W2 + NSLOT2 * SLOT_BYTES;        // 172032
-constexpr int OFF_BAR2 = OFF_STAGE2 + 2 * STAGE_BOX;            // 204800
+constexpr int OFF_STAGE2 = OFF_W2 + NSLOT2 * SLOT2_BYTES;       // 188416
+constexpr int OFF_BAR2 = OFF_STAGE2 + 2 * STAGE_BOX;            // 221184
 constexpr int SMEM_TOTAL2 = OFF_BAR2 + 256;
+static_assert(SMEM_TOTAL2 <= 232448, "shared memory budget");
 static_assert(KB_HALF_BYTES % 1024 == 0 && OFF_W2 % 1024 == 0 && OFF_STAGE2 % 1024 == 0, "swizzled tiles need 1 KB alignment");
 }  // namespace bi2
 
@@ -71,12 +77,12 @@ block_in2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
   if ((ptx::smem_u32(smem) & 1023u) != 0) __trap();
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR2);
   uint64_t* w_full = bars;          // [NSLOT2] leader's copy is the live one (tx bytes from both CTAs)
-  uint64_t* w_empty = bars + 4;     // [NSLOT2] per CTA, released by the leader's multicast commit
-  uint64_t* xn_full = bars + 8;     // [NXN]   leader's copy (both halves' bytes)
-  uint64_t* xn_free = bars + 10;    // [NXN]   per CTA (multicast commit)
-  uint64_t* acc_full = bars + 12;   // [2]     per CTA (multicast commit): set A (x0) / set B (x1, v) accumulated
-  uint64_t* acc_free = bars + 14;   // [2]     leader's copy, 16 warp arrivals
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 16);
+  uint64_t* w_empty = bars + 8;     // [NSLOT2] per CTA, released by the leader's multicast commit
+  uint64_t* xn_full = bars + 16;    // [NXN]   leader's copy (both halves' bytes)
+  uint64_t* xn_free = bars + 18;    // [NXN]   per CTA (multicast commit)
+  uint64_t* acc_full = bars + 20;   // [2]     per CTA (multicast commit): set A (x0) / set B (x1, v) accumulated
+  uint64_t* acc_free = bars + 22;   // [2]     leader's copy, 16 warp arrivals
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 24);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t cr = ptx::cluster_ctarank();
@@ -120,12 +126,12 @@ block_in2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
                                   t0 - HALO + HALF * (int)cr, b);
         }
         for (int g = 0; g < 3; ++g)
-          for (int kp = 0; kp < 2; ++kp) {   // this CTA's 128 channels of group g, k-blocks (2 kp, 2 kp + 1): one 32 KB box
+          for (int kb = 0; kb < 4; ++kb) {   // this CTA's 128 channels of group g, k-block kb: one 16 KB box
             const uint32_t s = wi % NSLOT2, ph = (wi / NSLOT2) & 1;
             ptx::mbar_wait(&w_empty[s], ph ^ 1);
-            if (leader) ptx::mbar_expect_tx(&w_full[s], 2 * SLOT_BYTES);
-            ptx::tma_load_2d_2cta(smem + OFF_W2 + s * SLOT_BYTES, &tmW, ptx::mapa(ptx::smem_u32(&w_full[s]), 0), 0,
-                                  ((g * 2 + (int)cr) * 4 + 2 * kp) * 128);
+            if (leader) ptx::mbar_expect_tx(&w_full[s], 2 * SLOT2_BYTES);
+            ptx::tma_load_2d_2cta(smem + OFF_W2 + s * SLOT2_BYTES, &tmW, ptx::mapa(ptx::smem_u32(&w_full[s]), 0), 0,
+                                  ((g * 2 + (int)cr) * 4 + kb) * 128);
             ++wi;
           }
       }
@@ -147,19 +153,15 @@ block_in2_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
             ptx::tc_fence_after_sync();
             if (g == 0) stamp(0);
           }
-          for (int kp = 0; kp < 2; ++kp) {
+          for (int kb = 0; kb < 4; ++kb) {
             const uint32_t s = wi % NSLOT2, ph = (wi / NSLOT2) & 1;
             ptx::mbar_wait_cluster(&w_full[s], ph);
             ptx::tc_fence_after_sync();
+            const uint64_t da = ptx::smem_desc_k_sw128(sW + s * SLOT2_BYTES);
+            const uint64_t db = ptx::smem_desc_k_sw128(sXN + buf * XN_HALF_BYTES + kb * KB_HALF_BYTES);
 #pragma unroll
-            for (int q2 = 0; q2 < 2; ++q2) {
-              const int kb = 2 * kp + q2;
-              const uint64_t da = ptx::smem_desc_k_sw128(sW + s * SLOT_BYTES + q2 * (SLOT_BYTES / 2));
-              const uint64_t db = ptx::smem_desc_k_sw128(sXN + buf * XN_HALF_BYTES + kb * KB_HALF_BYTES);
-#pragma unroll
-              for (int k = 0; k < 4; ++k)
-                ptx::umma_f16_2cta_e(tmem_base + g * GCOLS, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
-            }
+            for (int k = 0; k < 4; ++k)
+              ptx::umma_f16_2cta_e(tmem_base + g * GCOLS, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
             ptx::umma_commit_2cta_e(&w_empty[s]);
             ++wi;
           }
