@@ -1378,15 +1378,17 @@ int clm_forward(clm_ctx* c, const void* d_ids, int ids_dtype, int B, int T, floa
       hf.pooled = c->pooled; hf.h0 = c->hbuf[0]; hf.h1 = c->hbuf[1]; hf.h2 = c->hbuf[2]; hf.h3 = c->hbuf[3];
       hf.logits = d_logits; hf.labels = d_labels; hf.counter = c->head_counter; hf.base = c->head_base; hf.B = B;
       hf.err = c->d_err; hf.status_out = status_slot; hf.status_tag = status_tag; hf.pool_mode = g.pooling;
-      const int grid = H / 8;
+      // (H / 8) neuron groups x up to 4 read slices of whole 32-read tiles; 256 CTAs of 64 KB are co-resident on 148 SMs
+      const int slices = std::max(1, std::min(4, (B + HEAD_BT - 1) / HEAD_BT));
+      const dim3 grid(H / 8, slices);
       void* args[] = {&hf};
       constexpr size_t head_smem = (size_t)HEAD_BT * 512 * sizeof(float);
       if (int rc_attr = ensure_smem_attr(c, (const void*)(head_fused_kernel), (int)((int)head_smem))) return rc_attr;
-      CLM_CUDA(c, cudaLaunchCooperativeKernel((const void*)head_fused_kernel, dim3(grid), dim3(256), args, head_smem, st));
+      CLM_CUDA(c, cudaLaunchCooperativeKernel((const void*)head_fused_kernel, grid, dim3(256), args, head_smem, st));
       CLM_LAUNCH_CHECK(c, "head_fused");
-      // five grid barriers per launch; the device counter is never reset.  Advanced only once the launch was accepted:
-      // a rejected launch must not move the host's idea of the counter ahead of the device's.
-      c->head_base += 5u * (unsigned)grid;
+      // five grid barriers + one final arrival per CTA and launch; the device counter is never reset.  Advanced only once
+      // the launch was accepted: a rejected launch must not move the host's idea of the counter ahead of the device's.
+      c->head_base += 6u * (unsigned)(grid.x * grid.y);
     } else {
     pool_merge_kernel<<<B, 256, 0, st>>>(c->part, n_split, c->pooled, g.pooling);
     CLM_LAUNCH_CHECK(c, "pool_merge");

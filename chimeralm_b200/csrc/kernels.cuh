@@ -477,7 +477,7 @@ constexpr int HEAD_BT = 32;   // reads per shared-memory tile of the layer input
 // the CTA needs all of it; from global memory each warp would pull B x IN floats through L2 again).
 template <int IN, bool GELU, bool SKIP>
 __device__ __forceinline__ void head_fused_layer(const float* __restrict__ W, const float* __restrict__ bias, const float* x,
-                                                 const float* skip, float* y, int o, int OUT, int B, float* xs) {
+                                                 const float* skip, float* y, int o, int OUT, int b_lo, int B, float* xs) {
   const int lane = threadIdx.x & 31;
   constexpr int V = IN / 128;
   float4 w[V];
@@ -487,7 +487,7 @@ __device__ __forceinline__ void head_fused_layer(const float* __restrict__ W, co
     for (int v = 0; v < V; ++v) w[v] = __ldg(reinterpret_cast<const float4*>(W + (long long)o * IN) + lane + 32 * v);
     bo = __ldg(bias + o);
   }
-  for (int b0 = 0; b0 < B; b0 += HEAD_BT) {
+  for (int b0 = b_lo; b0 < B; b0 += HEAD_BT) {   // this CTA's reads [b_lo, B)
     const int nb = min(HEAD_BT, B - b0);
     __syncthreads();   // previous tile fully consumed
     for (int i = threadIdx.x; i < nb * (IN / 4); i += blockDim.x)
@@ -518,9 +518,15 @@ __global__ void __launch_bounds__(256) head_fused_kernel(HeadFusedParams p) {
   constexpr int D = 256, H = 512;
   extern __shared__ __align__(16) float head_xs[];   // HEAD_BT x 512 fp32
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const unsigned int G = gridDim.x;
+  // grid = (H / 8 neuron groups, read slices): every weight row is still read once per slice (<= 4 slices), and a batch of
+  // 255 short reads no longer walks eight 32-read tiles through one CTA per neuron group (0.41 ms at B = 255,
+  // profiles/r2_length_sweep.txt)
+  const unsigned int G = gridDim.x * gridDim.y;
+  const unsigned int cta = blockIdx.y * gridDim.x + blockIdx.x;
+  const int per = ((p.B + (int)gridDim.y - 1) / (int)gridDim.y + HEAD_BT - 1) / HEAD_BT * HEAD_BT;   // reads per slice, whole tiles
+  const int b_lo = (int)blockIdx.y * per, b_hi = min(p.B, b_lo + per);
   // phase 0: merge the pooling partials of each read (pool_merge_kernel)
-  for (int b = blockIdx.x; b < p.B; b += G) {
+  for (int b = cta; b < p.B; b += G) {
     const int d = threadIdx.x;
     const float* pp = p.part + (long long)b * p.n_split * (2 + D);
     if (p.pool_mode == 2) {   // max pooling: the partials hold per-tile maxima
@@ -542,21 +548,28 @@ __global__ void __launch_bounds__(256) head_fused_kernel(HeadFusedParams p) {
     p.pooled[(long long)b * D + d] = a / L;
   }
   grid_barrier(p.counter, p.base + 1 * G);
-  const int o = blockIdx.x * 8 + warp;   // G * 8 == H
-  head_fused_layer<D, true, false>(p.w0, p.b0, p.pooled, nullptr, p.h0, o, H, p.B, head_xs);
+  const int o = blockIdx.x * 8 + warp;   // gridDim.x * 8 == H
+  head_fused_layer<D, true, false>(p.w0, p.b0, p.pooled, nullptr, p.h0, o, H, b_lo, b_hi, head_xs);
   grid_barrier(p.counter, p.base + 2 * G);
-  head_fused_layer<H, true, false>(p.w1, p.b1, p.h0, nullptr, p.h1, o, H, p.B, head_xs);
+  head_fused_layer<H, true, false>(p.w1, p.b1, p.h0, nullptr, p.h1, o, H, b_lo, b_hi, head_xs);
   grid_barrier(p.counter, p.base + 3 * G);
-  head_fused_layer<H, true, false>(p.wr0, p.br0, p.h1, nullptr, p.h2, o, H, p.B, head_xs);
+  head_fused_layer<H, true, false>(p.wr0, p.br0, p.h1, nullptr, p.h2, o, H, b_lo, b_hi, head_xs);
   grid_barrier(p.counter, p.base + 4 * G);
-  head_fused_layer<H, false, true>(p.wr1, p.br1, p.h2, p.h1, p.h3, o, H, p.B, head_xs);
+  head_fused_layer<H, false, true>(p.wr1, p.br1, p.h2, p.h1, p.h3, o, H, b_lo, b_hi, head_xs);
   grid_barrier(p.counter, p.base + 5 * G);
-  if (blockIdx.x == 0) {
-    head_fused_layer<H, false, false>(p.wo, p.bo, p.h3, nullptr, p.logits, warp, 2, p.B, head_xs);
+  if (blockIdx.x == 0) {   // output layer: one CTA per read slice
+    head_fused_layer<H, false, false>(p.wo, p.bo, p.h3, nullptr, p.logits, warp, 2, b_lo, b_hi, head_xs);
     __syncthreads();
     if (p.labels && warp == 0)
-      for (int b = lane; b < p.B; b += 32) p.labels[b] = (p.logits[b * 2 + 1] > p.logits[b * 2]) ? 1 : 0;   // ties -> 0
-    if (threadIdx.x == 0) publish_status(p.err, p.status_out, p.status_tag);
+      for (int b = b_lo + lane; b < b_hi; b += 32) p.labels[b] = (p.logits[b * 2 + 1] > p.logits[b * 2]) ? 1 : 0;   // ties -> 0
+  }
+  // The status word is handed to the host by the last CTA to get here (one more arrival on the barrier counter: the host
+  // accounts for 6 G per launch), after every slice has written its logits.
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned int prev = atomicAdd(p.counter, 1u);
+    if (prev == p.base + 6 * G - 1) publish_status(p.err, p.status_out, p.status_tag);
   }
 }
 
