@@ -16,3 +16,17 @@ for k in block_mlp_kernel longconv_tc_kernel block_in_kernel score_pool_kernel; 
       python bench.py --steps 2 --warmup 1 $K2ONLY > gpurun_out/${TAG}_ncu_$k.log 2>&1
 done
 tail -c 400 gpurun_out/${TAG}_bench.json
+# the chunked form of the tensor-core conv (reads longer than 8 200 tokens): a forward of 16 x 32 769 tokens only
+cat > gpurun_out/_long_fwd.py <<'PY'
+import sys, torch
+sys.path.insert(0, ".")
+from chimeralm_b200.engine import Engine
+from chimeralm_b200.weights import make_state_dict
+eng = Engine(make_state_dict(0), device=0, max_batch=16, max_tokens=32769)
+ids = torch.randint(7, 11, (16, 32769), dtype=torch.uint8, device="cuda")
+for _ in range(3):
+    eng.forward(ids)
+torch.cuda.synchronize()
+PY
+python gpurun_out/_long_fwd.py && ncu --set full --clock-control none --import-source on -k regex:longconv_tc_kernel --launch-skip 5 -c 1 -f \
+    -o gpurun_out/${TAG}_longconv_tc_chunked python gpurun_out/_long_fwd.py > gpurun_out/${TAG}_ncu_longconv_tc_chunked.log 2>&1
