@@ -661,7 +661,7 @@ int launch_longconv(clm_ctx* c, int layer, const __nv_bfloat16* vx, const __nv_b
   return fail(c, CLM_ERR_INVALID, "longconv: no plan for T=%d", T);
 }
 
-// Reads of 4097..8200 tokens (the N = 16384 transform class).  Below 8192 tokens the input rows past T are zero
+// Reads of 2057..8200 tokens (the N = 16384 transform class).  Below 8192 tokens the input rows past T are zero
 // filled (TMA bounds + block_in writes zeros for t in [T, Tp)), so the same kernel serves them.
 struct TcPlan { int nc, nt; };   // transforms (chunks of 8192 tokens) per read, tail tokens finished by direct products
 TcPlan tc_plan(int T) {
@@ -672,7 +672,10 @@ TcPlan tc_plan(int T) {
 size_t tc_scratch_per_cta(int nc) { return nc > 1 ? (size_t)(nc - 1) * tc::N + 2 * tc::C : 0; }   // floats (parked spectra are fp16 pairs)
 
 bool tc_conv_applies(const clm_ctx* c, int T) {
-  if (!c->tc_conv || T <= tc::C / 2 || c->layers[0].gtc == nullptr) return false;
+  // Below 2 057 tokens the fp32 FFT kernels win (N = 4 096: ~8.3 K cycles per item); from there on one tensor-core item
+  // (13.4-14.6 K cycles for two reads of up to 8 192 tokens, the rows past T are zeros) beats the N = 8 192 fp32 transform
+  // (~16 K cycles per item; profiles/r2_length_sweep.txt)
+  if (!c->tc_conv || T <= tc::C / 4 + LONGCONV_TAIL_MAX || c->layers[0].gtc == nullptr) return false;
   const TcPlan pl = tc_plan(T);
   return pl.nc == 1 || (c->tc_chunked && pl.nc <= std::min(c->tc_nseg, 4));   // the kernel's segment loop is unrolled for <= 4 chunks
 }

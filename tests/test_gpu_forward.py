@@ -77,7 +77,7 @@ def test_stagewise_residual_stream(engine, state_dict, B, T):
     assert (logits - logits_ref).abs().max().item() <= LOGIT_TOL
 
 
-@pytest.mark.parametrize("B,T", [(1, 64), (4, 2049), (2, 8193), (3, 5000)])
+@pytest.mark.parametrize("B,T", [(1, 64), (4, 2049), (2, 8193), (3, 5000), (3, 3000)])
 def test_logits_and_labels(engine, state_dict, B, T):
     from oracle import hyena_oracle as O
 

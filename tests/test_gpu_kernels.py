@@ -85,7 +85,7 @@ def test_longconv(engine, state_dict, T):
     assert err <= 1e-2 * max(1.0, scale), (T, err, scale)
 
 
-@pytest.mark.parametrize("T,B", [(8192, 2), (8193, 3), (8200, 5), (4097, 2), (5000, 3), (8191, 2),
+@pytest.mark.parametrize("T,B", [(8192, 2), (8193, 3), (8200, 5), (4097, 2), (5000, 3), (8191, 2), (2057, 3), (3073, 2), (4096, 1),
                                  (8201, 2), (12000, 3), (16384, 2), (16385, 3), (20000, 2), (24583, 1), (32768, 2), (32769, 3)])
 def test_longconv_tensor_core(engine, state_dict, T, B):
     """Tensor-core FFT conv (fp16 operands, fp32 accumulate) vs the oracle's fp32 rFFT conv: max error within 1e-2 of
