@@ -157,7 +157,7 @@ struct clm_ctx {
   bool fused_in = true;   // LN1+in_proj+short conv+gate in one kernel
   bool fast_conv = true;  // tuned single-chunk long convolution
   int mlp_stagger = 0;    // block_mlp: CTA phase stagger in cycles (0 = off)
-  bool tc_conv = true;    // tensor-core FFT long convolution for reads of 8192..8200 tokens (needs fused_in)
+  bool tc_conv = true;    // tensor-core FFT long convolution for reads of more than 2 056 tokens (needs fused_in)
   __half* tc_S = nullptr; // shared-memory image of the DFT constant stack (longconv_tc)
   bool fused_head = true;         // pooling merge + classifier layers in one cooperative launch
   unsigned int* head_counter = nullptr;

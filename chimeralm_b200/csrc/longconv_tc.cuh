@@ -1,7 +1,7 @@
 // Long convolution on the tensor cores: a 16384-point FFT as two 128-point DFT matrix products
 // (Monarch / four-step decomposition, N = 128 x 128), all four matrix stages on tcgen05 with fp16
 // operands and fp32 accumulation in TMEM.  Same math as longconv_fast_kernel<14> for reads of
-// 8192..8200 tokens: y = causal_conv(vx, k) + bias * vx (bias folded into tap 0), out = y * x0;
+// 2057..8200 tokens (longer reads: chunked form below): y = causal_conv(vx, k) + bias * vx (bias folded into tap 0), out = y * x0;
 // replaces fftconv() (reference chimeralm/models/components/hyena.py via HF modeling_hyena.fftconv,
 // SURVEY.md A.5).
 //

@@ -282,7 +282,7 @@ class Engine:
         return out
 
     def longconv_tc(self, layer: int, vx_f16: torch.Tensor, x0: torch.Tensor, T: int):
-        """Tensor-core FFT long conv (8192 <= T <= 8200): vx fp16 [B,D,Tp], x0 bf16 -> bf16 [B,D,Tp]."""
+        """Tensor-core FFT long conv (2057 <= T <= 32769; zeros past T): vx fp16 [B,D,Tp], x0 bf16 -> bf16 [B,D,Tp]."""
         if vx_f16.dtype != torch.float16 or x0.dtype != torch.bfloat16:
             raise TypeError("longconv_tc takes fp16 vx and bf16 x0")
         B, D, Tp = vx_f16.shape

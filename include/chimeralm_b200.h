@@ -174,7 +174,7 @@ int clm_longconv(clm_ctx* ctx, int layer, const void* d_vx, const void* d_x0, vo
  * `save_attention=True` / `BinarySequenceClassifier.attention_weights` (chimeralm/models/components/hyena.py:129-130,
  * chimeralm/models/lm.py:14,30). */
 int clm_attention_weights(clm_ctx* ctx, float* d_out, int B, int T, void* stream);
-/* Tensor-core FFT long convolution (reads of 8192..8200 tokens): same contract as clm_longconv except
+/* Tensor-core FFT long convolution (reads of 2 057 .. 32 769 tokens; rows past T must be zero below 8 192 tokens, Tp a multiple of 128): same contract as clm_longconv except
  * that d_vx holds fp16 values (what the fused in_proj kernel emits when this kernel follows). */
 int clm_longconv_tc(clm_ctx* ctx, int layer, const void* d_vx_f16, const void* d_x0, void* d_out, int B, int T, int Tp,
                     void* stream);
