@@ -68,6 +68,8 @@ def bucket_batches(lengths: np.ndarray, batch: int, n_special: int = 1, max_toke
         if max_tokens_per_batch is not None:
             while j > i + 1 and (j - i) * (int(lengths[order[j - 1]]) + n_special) > max_tokens_per_batch:
                 j -= 1
+        if (j - i) > 1 and (j - i) % 2 == 1 and j < n:
+            j -= 1   # even batches: the long convolution carries TWO reads per transform (real and imaginary part)
         out.append(order[i:j])
         i = j
     return out
