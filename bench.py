@@ -327,7 +327,34 @@ def run_k2(args, eng, D, sampler):
     ms_prof = evp[0].elapsed_time(evp[2])
     kernel_sum = sum(v[0] for v in prof.values())
 
-    per_rank = D.gather_floats([ms, gather_ms, ms_prof, kernel_sum, e2e_s * 1e3, e2e_sync_s * 1e3])
+    # ---- the same two measurements in the STEADY state: ~1.5 s of the same load first, so the board is at its power cap
+    # (1 700-1 850 MHz) when the K timed steps run.  `value` / `e2e` above start one second after idle and see boost clocks;
+    # an 8-GPU box runs every rank at the capped clock from the start, so the scaling of the steady-state figures is the
+    # like-for-like one.
+    def preheat(seconds):
+        t_end = time.perf_counter() + seconds
+        i = 0
+        while time.perf_counter() < t_end:
+            for _ in range(8):
+                step_resident(i)
+                i += 1
+            torch.cuda.synchronize()
+
+    preheat(args.preheat)
+    D.barrier()
+    if sampler:
+        sampler.mark_start("k2_steady")
+    evs = timed_pass()
+    D.barrier()
+    if sampler:
+        sampler.mark_end("k2_steady")
+    ms_steady = evs[0].elapsed_time(evs[2])
+    preheat(args.preheat / 3)
+    D.barrier()
+    t0 = time.perf_counter()
+    e2e_pipelined(eng, [(host_batches[i % N_DISTINCT], offsets_p, T, B) for i in range(args.steps)], B)
+    e2e_steady_s = time.perf_counter() - t0
+    per_rank = D.gather_floats([ms, gather_ms, ms_prof, kernel_sum, e2e_s * 1e3, e2e_sync_s * 1e3, ms_steady, e2e_steady_s * 1e3])
     return {"B": B, "L": L, "T": T, "prof": prof, "launches": launches, "per_rank": per_rank}
 
 
@@ -545,6 +572,7 @@ def main():
     ap.add_argument("--k3-reads", type=int, default=24576, help="reads of the K3 stream in the k3 sub-record (0 = skip)")
     ap.add_argument("--k5-steps", type=int, default=16, help="timed K5 batches per GPU (0 = skip)")
     ap.add_argument("--k5-batch", type=int, default=64)
+    ap.add_argument("--preheat", type=float, default=1.5, help="seconds of load before the steady-state passes")
     ap.add_argument("--no-labels", action="store_true", help="skip the label-agreement pass")
     ap.add_argument("--no-cli", action="store_true", help="skip the 2-GPU CLI check (only runs at --gpus 2)")
     args = ap.parse_args()
@@ -584,8 +612,10 @@ def main():
     D.barrier()
     clocks = sampler.stop()
     ck = clocks.get("k2", {})
+    cs = clocks.get("k2_steady", {})
     clocks_per_rank = D.gather_floats([ck.get("sm_mhz") or 0.0, ck.get("sm_mhz_min") or 0.0, ck.get("power_w_max") or 0.0,
-                                       float("sw_power_cap" in ck.get("reasons", []))])
+                                       float("sw_power_cap" in ck.get("reasons", [])), cs.get("sm_mhz") or 0.0,
+                                       cs.get("power_w_max") or 0.0])
     D.close()
     if rank != 0:
         return
@@ -678,11 +708,18 @@ def main():
         "kernel_ms_per_step_note": "rank 0, from the second (profiled) pass; `value` comes from the first, un-profiled pass",
         "ms_per_rank": [r[0] / args.steps for r in per_rank],
         "compute_ms_per_rank": [(r[0] - r[1]) / args.steps for r in per_rank],   # the same region without the final gather
-        "clocks_per_rank": [{"sm_mhz": c[0], "sm_mhz_min": c[1], "power_w_max": c[2], "sw_power_cap": bool(c[3])} for c in clocks_per_rank],
+        "clocks_per_rank": [{"sm_mhz": c[0], "sm_mhz_min": c[1], "power_w_max": c[2], "sw_power_cap": bool(c[3]),
+                             "steady_sm_mhz": c[4], "steady_power_w_max": c[5]} for c in clocks_per_rank],
         "gather_ms_per_rank": [r[1] for r in per_rank],
         "slowest_rank": {"rank": slow, "ms_per_step": per_rank[slow][0] / args.steps,
                          "kernel_sum_ms_per_step": per_rank[slow][3] / args.steps,
                          "profiled_pass_ms_per_step": per_rank[slow][2] / args.steps},
+        "steady_state": {"value": world * B * args.steps / (max(r[6] for r in per_rank) / 1e3), "unit": "reads/s",
+                         "e2e": world * B * args.steps / (max(r[7] for r in per_rank) / 1e3),
+                         "ms_per_step": max(r[6] for r in per_rank) / args.steps, "ms_per_rank": [r[6] / args.steps for r in per_rank],
+                         "preheat_s": args.preheat, "clocks": clocks.get("k2_steady"),
+                         "note": "same K steps after ~1.5 s of the same load: the board is at its power cap; `value` / `e2e` start "
+                                 "one second after idle (boost clocks), like round 1's numbers"},
         "label_agreement": labels.get("label_agreement") if labels else None,
         "n_reads": labels.get("n_reads") if labels else None,
         "logit_max_err": labels.get("logit_max_err") if labels else None,

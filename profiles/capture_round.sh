@@ -4,7 +4,7 @@
 # Every ncu pass runs only after the same command has exited 0 without ncu; numbers printed under ncu are never bench values.
 # usage (on the box): bash profiles/capture_round.sh r2_v1
 TAG=${1:-round}
-K2ONLY="--k3-reads 0 --k5-steps 0 --no-labels --cpu-sample 0"
+K2ONLY="--k3-reads 0 --k5-steps 0 --no-labels --cpu-sample 0 --preheat 0"
 mkdir -p gpurun_out
 python bench.py --steps 40 --warmup 5 > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err || exit 1
 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/${TAG}_bench_reference.json 2>> gpurun_out/${TAG}_bench.err
