@@ -7,7 +7,8 @@ sd = make_state_dict(0)
 side = torch.cuda.Stream()
 host = torch.empty(128 << 20, dtype=torch.uint8).pin_memory()
 dev = torch.empty(128 << 20, dtype=torch.uint8, device="cuda")
-for B, T, n in ((32, 8193, 600), (16, 16385, 200), (8, 32769, 100), (31, 5000, 300), (3, 8200, 300), (64, 4097, 200)):
+for B, T, n in ((32, 8193, 600), (16, 16385, 200), (8, 32769, 100), (31, 5000, 300), (3, 8200, 300), (64, 4097, 200), (85, 3073, 200),
+                (255, 1025, 200), (127, 2049, 200)):
     eng = Engine(sd, device=0, max_batch=B, max_tokens=T)
     ids = torch.randint(7, 11, (B, T), dtype=torch.uint8, device="cuda")
     first = eng.forward(ids).clone()
@@ -20,5 +21,6 @@ for B, T, n in ((32, 8193, 600), (16, 16385, 200), (8, 32769, 100), (31, 5000, 3
         if i % 20 == 19 and not torch.equal(out, first):
             bad += 1
     torch.cuda.synchronize()
+    eng.forward_status()   # the last forward's status word: raises on a token-range / fp16-range flag
     print(f"B={B} T={T}: {n} forwards, conv={eng.longconv_variant(T)}, mismatches={bad}")
     eng.close()
