@@ -27,6 +27,7 @@
 #include "longconv.cuh"
 #include "longconv_fast.cuh"
 #include "longconv_tc.cuh"
+#include "longconv_tc2.cuh"
 #include "score_pool.cuh"
 
 using namespace clm;
@@ -158,6 +159,7 @@ struct clm_ctx {
   bool fast_conv = true;  // tuned single-chunk long convolution
   int mlp_stagger = 0;    // block_mlp: CTA phase stagger in cycles (0 = off)
   bool tc_conv = true;    // tensor-core FFT long convolution for reads of more than 2 056 tokens (needs fused_in)
+  bool tc_pipe = true;    // single-transform reads (<= 8 200 tokens): two items in flight per SM (longconv_tc2_kernel)
   __half* tc_S = nullptr; // shared-memory image of the DFT constant stack (longconv_tc)
   bool fused_head = true;         // pooling merge + classifier layers in one cooperative launch
   unsigned int* head_counter = nullptr;
@@ -692,6 +694,8 @@ int launch_longconv_tc(clm_ctx* c, int layer, const __half* vx, const __nv_bfloa
   const cuuint64_t n_rows = (cuuint64_t)(whole_rows ? std::min(64, Tp / 128) : Tp / 128);   // 128-token rows per channel
   if (int rc_attr = ensure_smem_attr(c, (const void*)(longconv_tc_kernel<false>), (int)(tc::SMEM_TOTAL))) return rc_attr;
   if (int rc_attr = ensure_smem_attr(c, (const void*)(longconv_tc_kernel<true>), (int)(tc::SMEM_TOTAL))) return rc_attr;
+  if (int rc_attr = ensure_smem_attr(c, (const void*)(longconv_tc2_kernel<false>), (int)(tc2::SMEM2_TOTAL))) return rc_attr;
+  if (int rc_attr = ensure_smem_attr(c, (const void*)(longconv_tc2_kernel<true>), (int)(tc2::SMEM2_TOTAL))) return rc_attr;
   if (tc_scratch_per_cta(pl.nc) * c->num_sms > c->tc_scratch_floats)
     return fail(c, CLM_ERR_STATE, "longconv_tc: scratch too small for T=%d; call clm_reserve with max_T >= %d", T, T);
   LayerW& L = c->layers[layer];
@@ -737,8 +741,10 @@ int launch_longconv_tc(clm_ctx* c, int layer, const __half* vx, const __nv_bfloa
   p.rel = L.tc_rel; p.err = (unit_scale || osc_override) ? c->d_err + 1 : c->d_err;
   const int grid = std::min(p.n_items, c->num_sms);
   if (pl.nc > 1) longconv_tc_kernel<true><<<grid, tc::THREADS_CH, tc::SMEM_TOTAL, st>>>(tm, tmo, tmg, p);
+  else if (c->tc_pipe && trace) longconv_tc2_kernel<true><<<grid, tc2::THREADS2, tc2::SMEM2_TOTAL, st>>>(tm, tmo, tmg, p);
+  else if (c->tc_pipe) longconv_tc2_kernel<false><<<grid, tc2::THREADS2, tc2::SMEM2_TOTAL, st>>>(tm, tmo, tmg, p);
   else longconv_tc_kernel<false><<<grid, tc::THREADS, tc::SMEM_TOTAL, st>>>(tm, tmo, tmg, p);
-  CLM_LAUNCH_CHECK(c, pl.nc > 1 ? "longconv_tc_chunked" : "longconv_tc");
+  CLM_LAUNCH_CHECK(c, pl.nc > 1 ? "longconv_tc_chunked" : (c->tc_pipe ? "longconv_tc2" : "longconv_tc"));
   return 0;
 }
 
@@ -1526,6 +1532,7 @@ int clm_set_option(clm_ctx* c, const char* name, int value) {
 #endif
   else if (n == "tc_conv") c->tc_conv = value != 0;
   else if (n == "tc_chunked") c->tc_chunked = value != 0;
+  else if (n == "tc_pipe") c->tc_pipe = value != 0;
   else if (n == "fused_score_pool") c->fused_score_pool = value != 0;
   else if (n == "fused_head") c->fused_head = value != 0;
   else if (n == "mlp_stagger") c->mlp_stagger = value;
