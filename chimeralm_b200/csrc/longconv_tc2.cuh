@@ -19,8 +19,8 @@
 // longer cost an extra output row in step 7: F[k1][64] = (-1)^k1, so their transform part is an alternating sum over BT,
 // done together with the direct products by an otherwise idle warp, which also issues the gate-tile loads.
 //
-// Warps: 0 = TMA producer (z tiles, output stores), 1 = MMA issuer, 2 = gate loads + tail tokens, 3 idle, 4..11 = epilogue
-// (TMEM lane quarter = warp % 4, index half = (warp - 4) / 4); `setmaxnreg` moves registers to the epilogue warpgroups.
+// Warps: 0..7 = epilogue (TMEM lane quarter = warp % 4, index half = warp / 4), 8 = TMA producer (z tiles, output stores),
+// 9 = MMA issuer, 10 = gate loads, 11 = tail tokens; `setmaxnreg` moves registers to the epilogue warpgroups.
 #pragma once
 #include "longconv_tc.cuh"
 
@@ -37,7 +37,10 @@ constexpr int OFF2_BAR = OFF2_BT + BT_BYTES;      // 229376
 constexpr int SMEM2_TOTAL = OFF2_BAR + 512;
 constexpr int THREADS2 = 384;
 constexpr int FRE = 0, FIM = 128;                 // row blocks of the constant stack
-constexpr int EPI2_W0 = 4;
+constexpr int EPI2_W0 = 0;                        // epilogue warps 0..7
+// The helper warps take the HIGHEST warp ids: the warp scheduler favours higher ids, and the MMA issuer (a few instructions
+// per 64-cycle MMA) must not queue behind the two epilogue warps of its scheduler.
+constexpr int W_PROD = 8, W_MMA = 9, W_AUX = 10, W_TAIL = 11;
 
 // kind::f16 instruction descriptor, fp16 x fp16 -> fp32, M = 128, optional negation of the A / B operand (bits 13 / 14)
 __host__ __device__ constexpr uint32_t idesc2(uint32_t n, bool a_mn, bool b_mn, bool a_neg, bool b_neg) {
@@ -89,7 +92,7 @@ longconv_tc2_kernel(const __grid_constant__ CUtensorMap tmVX, const __grid_const
       dst[i] = __ldg(p.S + pnl * (S_PANEL / 16) + 128 * 8 + off);
     }
   }
-  if (warp == 0 && lane == 0) {
+  if (warp == W_PROD && lane == 0) {
     ptx::prefetch_tmap(&tmVX); ptx::prefetch_tmap(&tmOut); ptx::prefetch_tmap(&tmX0);
     for (int i = 0; i < 3; ++i) { ptx::mbar_init(&z_full[i], 1); ptx::mbar_init(&g_full[i], 1); ptx::mbar_init(&out_ready[i], 8); }
     for (int t = 0; t < 2; ++t) {
@@ -100,7 +103,7 @@ longconv_tc2_kernel(const __grid_constant__ CUtensorMap tmVX, const __grid_const
     }
     ptx::mbar_init(imd, 8); ptx::mbar_init(bdr, 8);
     ptx::fence_mbar_init();
-  } else if (warp == 1) {
+  } else if (warp == W_MMA) {
     ptx::tmem_alloc<512>(tmem_ptr);
   }
   ptx::fence_proxy_async_smem();
@@ -110,7 +113,7 @@ longconv_tc2_kernel(const __grid_constant__ CUtensorMap tmVX, const __grid_const
   const uint32_t tmem_base = *tmem_ptr;
   const uint32_t U0 = tmem_base, U1 = tmem_base + 128, U2 = tmem_base + 256, U3 = tmem_base + 384;
 
-  if (warp == 0) {
+  if (warp == W_PROD) {
     // =========================== TMA producer (z loads, output stores) ===========================
     ptx::setmaxnreg_dec<104>();
     if (lane == 0) {
@@ -140,7 +143,7 @@ longconv_tc2_kernel(const __grid_constant__ CUtensorMap tmVX, const __grid_const
       }
       ptx::tma_store_wait<0>();
     }
-  } else if (warp == 1) {
+  } else if (warp == W_MMA) {
     // =========================== MMA issuer (whole warp, uniform control flow; one elected lane issues) ===========
     // Steps 3 and 5 (data from TMEM x constants) share one rolled loop, steps 1 and 7 (constants x data / data x constants
     // from shared memory) another: ~300 instructions, so that this warp's code stays resident in the instruction cache.
@@ -158,10 +161,10 @@ longconv_tc2_kernel(const __grid_constant__ CUtensorMap tmVX, const __grid_const
 #pragma unroll 1
     for (int s = 0; s < n_slots; ++s) {
       const int j = s & 7, k2x = (s >> 3) * 2;
-      // slot order: M1 A, M7 B-, M3 A, M1 B, M5 A, M3 B, M7 A, M5 B
-      const int it = k2x + ((j == 1) ? -1 : ((j == 3 || j == 5 || j == 7) ? 1 : 0));
+      // slot order: M1 A, M7 B-, M3 A, M1 B, M5 A, M3 B, M7 A, M5 B   (item offset + 1 in 2 bits, step in 4 bits per slot)
+      const int it = k2x + int((0x9991u >> (2 * j)) & 3u) - 1;
       if (it < 0 || it >= n) continue;
-      const int step = (j == 0 || j == 3) ? 1 : ((j == 2 || j == 5) ? 3 : ((j == 4 || j == 7) ? 5 : 7));
+      const int step = int((0x57351371u >> (4 * j)) & 7u);
       const uint32_t type = it & 1, k = it >> 1, ph = k & 1;
       if constexpr (TR) stamp(0);
       if (step == 3 || step == 5) {
@@ -227,36 +230,40 @@ longconv_tc2_kernel(const __grid_constant__ CUtensorMap tmVX, const __grid_const
         }
         ptx::tc_fence_after_sync();
         if constexpr (TR) stamp(0);
-        const int nhq = is7 ? 2 : 1;
 #pragma unroll 1
         for (uint32_t op = 0; op < 4; ++op) {             // (output half o, input part: z re / im rows, or BT's B_re / B_im rows)
           const uint32_t o = op >> 1, part = op & 1;
           const int rows = (o ^ part) ? FIM : FRE;
           const bool neg = (o == is7) && (part != is7);   // step 1: -Fim Zim in A_re; step 7: -Bre Fim in z_im
-          const uint32_t id = is7 ? (neg ? id7n : id7) : (neg ? id1n : id1);
           const uint32_t dst = o ? d1 : d0;
-          uint64_t dc = s_desc(rows, 0), dd = dD + (uint64_t)((part * 16384) >> 4);
-#pragma unroll 1
-          for (int hq = 0; hq < nhq; ++hq) {             // 64 K rows (one panel of the constants) per pass
+          const uint64_t dc = s_desc(rows, 0), dd = dD + (uint64_t)((part * 16384) >> 4);
+          if (!is7) {   // 64 K rows: one pass
+            const uint32_t id = neg ? id1n : id1;
 #pragma unroll
-            for (int jj = 0; jj < 4; ++jj)
-              ptx::umma_f16_e(dst, is7 ? dd + 128 * jj : dc + 2 * jj, is7 ? dc + 2 * jj : dd + 128 * jj, id, (part | hq | jj) != 0);
-            dc += S2_PANEL >> 4; dd += 512;
+            for (int jj = 0; jj < 4; ++jj) ptx::umma_f16_e(dst, dc + 2 * jj, dd + 128 * jj, id, (part | jj) != 0);
+          } else {      // 128 K rows: both panels of the constants
+            const uint32_t id = neg ? id7n : id7;
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj)
+              ptx::umma_f16_e(dst, dd + 128 * jj, dc + (jj >> 2) * (S2_PANEL >> 4) + 2 * (jj & 3), id, (part | jj) != 0);
           }
         }
         ptx::umma_commit_e(is7 ? &o_full[type] : &x_full[type]);
       }
       if constexpr (TR) stamp(0);
     }
-  } else if (warp == 2) {
-    // =========================== gate-tile loads + tail tokens ===========================
+  } else if (warp == W_AUX || warp == W_TAIL) {
+    // =========================== gate-tile loads (warp W_AUX) / tail tokens (warp W_TAIL) ===========================
+    // (two warps on two schedulers: whatever a helper warp executes is taken from the two epilogue warps it shares a
+    // scheduler with, and the slowest epilogue warp sets the pace of every barrier)
     ptx::setmaxnreg_dec<104>();
-    for (int k = 0; 2 * k <= n; ++k) {
+    const bool gate_warp = warp == W_AUX;
+    for (int k = (gate_warp || nt > 0) ? 0 : n; 2 * k <= n; ++k) {
 #pragma unroll 1
       for (int sub = 0; sub < 4; ++sub) {
-        // order of the events this warp follows: x_full(A_k), bt_full(B_k-1), x_full(B_k), bt_full(A_k)
+        // order of the events: x_full(A_k) [gate], bt_full(B_k-1) [tail], x_full(B_k) [gate], bt_full(A_k) [tail]
         const int it = 2 * k + (sub == 1 ? -1 : (sub == 2 ? 1 : 0));
-        if (it < 0 || it >= n) continue;
+        if (it < 0 || it >= n || ((sub & 1) == 0) != gate_warp) continue;
         const uint32_t type = it & 1, ph = (it >> 1) & 1;
         const int item = item0 + it;
         const int ch = item / p.n_pairs, pr = item % p.n_pairs;
@@ -297,17 +304,18 @@ longconv_tc2_kernel(const __grid_constant__ CUtensorMap tmVX, const __grid_const
           // n2 = 0..7 is 16-byte chunk 0 of atom 0, stored at chunk position k1 & 7 of its 128-byte row
           float sre = 0.f, sim = 0.f;
           {
-            const int r0 = (lane >> 3) * 32;
+            // lane group g = lane >> 3 takes rows k1 = 4 i + g: the four groups of one load hit four different chunk
+            // positions (k1 & 7), i.e. different banks; the sign (-1)^k1 = (-1)^g is a per-lane constant
+            const int g4 = lane >> 3;
             const uint8_t* base = smem + OFF2_BT + jl * 2;
 #pragma unroll 2
             for (int i = 0; i < 32; ++i) {
-              const int rr = r0 + i;
+              const int rr = 4 * i + g4;
               const uint8_t* rowp = base + rr * 128 + ((rr & 7) << 4);
-              const float vr = __half2float(*reinterpret_cast<const __half*>(rowp));
-              const float vi = __half2float(*reinterpret_cast<const __half*>(rowp + 128 * 128));
-              sre += (i & 1) ? -vr : vr;
-              sim += (i & 1) ? -vi : vi;
+              sre += __half2float(*reinterpret_cast<const __half*>(rowp));
+              sim += __half2float(*reinterpret_cast<const __half*>(rowp + 128 * 128));
             }
+            if (g4 & 1) { sre = -sre; sim = -sim; }
           }
           sre += __shfl_xor_sync(0xffffffffu, sre, 8);
           sim += __shfl_xor_sync(0xffffffffu, sim, 8);
@@ -319,8 +327,6 @@ longconv_tc2_kernel(const __grid_constant__ CUtensorMap tmVX, const __grid_const
         }
       }
     }
-  } else if (warp == 3) {
-    ptx::setmaxnreg_dec<104>();
   } else {
     // =========================== epilogue warps ===========================
     ptx::setmaxnreg_inc<200>();
@@ -338,15 +344,15 @@ longconv_tc2_kernel(const __grid_constant__ CUtensorMap tmVX, const __grid_const
     float2 seed1[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) sincospif(-2.0f * float((r * col12(u)) % N) / float(N), &seed1[u].y, &seed1[u].x);
-    const bool tr = TR && trace && warp == EPI2_W0 && lane == 0;
+    const bool tr = TR && trace && lane == 0;   // every epilogue warp records its own row (1 + warp)
     const float2 w2 = make_float2(wstep.x * wstep.x - wstep.y * wstep.y, 2.0f * wstep.x * wstep.y);
     const int n_slots = 8 * (n / 2 + 1);
     // channel of local item `it` without a division per slot (a CTA's items span at most a few channels)
     const int ch0 = item0 / p.n_pairs, pr0 = item0 % p.n_pairs;
+    // (items per CTA <= 256 n_pairs / 148 + 1, so pr0 + it < 3 n_pairs + 1)
     auto ch_of = [&](int it) {
-      int c = ch0, x = pr0 + it;
-      while (x >= p.n_pairs) { x -= p.n_pairs; ++c; }
-      return c;
+      const int x = pr0 + it, np = p.n_pairs;
+      return ch0 + (x >= np) + (x >= 2 * np) + (x >= 3 * np);
     };
     // spectrum-table lines of this thread: uint4 (4 consecutive k2) at (((ch * 4 + k1 / 32) * 2 + k2 / 64) * 16 + (k2 % 64) / 4) * 32
     // + k1 % 32; an index half of this warp (k2 = 64 h + 32 hf + 0..31) is 8 uint4, 32 apart.  The first half of the NEXT E2
@@ -359,12 +365,12 @@ longconv_tc2_kernel(const __grid_constant__ CUtensorMap tmVX, const __grid_const
 #pragma unroll 1
     for (int s = 0; s < n_slots; ++s) {
       const int j = s & 7, k2x = (s >> 3) * 2;
-      // slot order: E3 B-, E1 A, E4 B-, E2 A, E1 B, E3 A, E2 B, E4 A
-      const int it = k2x + ((j == 0 || j == 2) ? -1 : ((j == 4 || j == 6) ? 1 : 0));
+      // slot order: E3 B-, E1 A, E4 B-, E2 A, E1 B, E3 A, E2 B, E4 A   (item offset + 1 in 2 bits, phase in 4 bits per slot)
+      const int it = k2x + int((0x6644u >> (2 * j)) & 3u) - 1;
       if (it < 0 || it >= n) continue;
-      const int phase = (j == 1 || j == 4) ? 1 : ((j == 3 || j == 6) ? 2 : ((j == 0 || j == 5) ? 3 : 4));
+      const int phase = int((0x42312413u >> (4 * j)) & 7u);
       const uint32_t type = it & 1, ph = (it >> 1) & 1;
-      if constexpr (TR) { if (tr) stamp(1); }
+      if constexpr (TR) { if (tr) stamp(1 + warp - EPI2_W0); }
       // Twiddle seeds are re-materialised per phase: without the barrier ptxas precomputes all 256 twiddle values of the
       // thread once and keeps them in LOCAL memory (an L2 round trip per use with this shared-memory carve-out).
       float2 ws = wstep;
@@ -380,7 +386,7 @@ longconv_tc2_kernel(const __grid_constant__ CUtensorMap tmVX, const __grid_const
         const uint32_t t_im = (type ? U2 : U1) + lane_addr, t_re = U0 + lane_addr;
         ptx::mbar_wait(&x_full[type], ph);
         ptx::tc_fence_after_sync();
-        if constexpr (TR) { if (tr) stamp(1); }
+        if constexpr (TR) { if (tr) stamp(1 + warp - EPI2_W0); }
         uint32_t xi[4][16];
 #pragma unroll
         for (int u = 0; u < 4; ++u) tmem_ld16(t_im + col12(u), xi[u]);
@@ -388,7 +394,7 @@ longconv_tc2_kernel(const __grid_constant__ CUtensorMap tmVX, const __grid_const
         if (type == 1) {   // the A-type partner's step 5 writes its first half into this unit
           ptx::tc_fence_before_sync();
           __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(imd);
+          ptx::mbar_arrive_lane0(imd, lane);
         }
         float2 sc[4];
 #pragma unroll
@@ -427,7 +433,7 @@ longconv_tc2_kernel(const __grid_constant__ CUtensorMap tmVX, const __grid_const
           ptx::tmem_st_wait();   // an index half is complete
           ptx::tc_fence_before_sync();
           __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(&p1_full[2 * type + h]);
+          ptx::mbar_arrive_lane0(&p1_full[2 * type + h], lane);
 #pragma unroll
           for (int uu = 0; uu < 2; ++uu) {
             sc[uu] = sc[2 + uu];
@@ -453,7 +459,7 @@ longconv_tc2_kernel(const __grid_constant__ CUtensorMap tmVX, const __grid_const
         }
         ptx::mbar_wait(&y_full[type], ph);
         ptx::tc_fence_after_sync();
-        if constexpr (TR) { if (tr) stamp(1); }
+        if constexpr (TR) { if (tr) stamp(1 + warp - EPI2_W0); }
 #pragma unroll 1
         for (int h = 0; h < 2; ++h) {
           uint32_t xr2[2][16], xi2[2][16];
@@ -487,7 +493,7 @@ longconv_tc2_kernel(const __grid_constant__ CUtensorMap tmVX, const __grid_const
           ptx::tmem_st_wait();
           ptx::tc_fence_before_sync();
           __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(&p2_full[2 * type + h]);
+          ptx::mbar_arrive_lane0(&p2_full[2 * type + h], lane);
 #pragma unroll
           for (int v = 0; v < 8; ++v) g[v] = g2[v];
         }
@@ -502,7 +508,7 @@ longconv_tc2_kernel(const __grid_constant__ CUtensorMap tmVX, const __grid_const
         }
         ptx::mbar_wait(&x2_full[type], ph);
         ptx::tc_fence_after_sync();
-        if constexpr (TR) { if (tr) stamp(1); }
+        if constexpr (TR) { if (tr) stamp(1 + warp - EPI2_W0); }
         uint32_t xr[4][16];
 #pragma unroll
         for (int u = 0; u < 4; ++u) tmem_ld16(t_bre + 16 * u, xr[u]);
@@ -510,7 +516,7 @@ longconv_tc2_kernel(const __grid_constant__ CUtensorMap tmVX, const __grid_const
         if (type == 0) {   // the B-type partner's step 3 writes S_im into this unit
           ptx::tc_fence_before_sync();
           __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(bdr);
+          ptx::mbar_arrive_lane0(bdr, lane);
         }
         if (nt > 0 && it >= 1) ptx::mbar_wait(&bt_read[type ^ 1], ((it - 1) >> 1) & 1);   // the tail warp is done with BT
         float2 sc[4];
@@ -563,7 +569,7 @@ longconv_tc2_kernel(const __grid_constant__ CUtensorMap tmVX, const __grid_const
         ptx::fence_proxy_async_smem();
         ptx::tc_fence_before_sync();
         __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&bt_full[type]);
+        ptx::mbar_arrive_lane0(&bt_full[type], lane);
       } else {
         // ------------------------------------------------ E4: out = z' * x0, in place over the gate tile, TMA store
         const int buf = it % NZ;
@@ -578,7 +584,7 @@ longconv_tc2_kernel(const __grid_constant__ CUtensorMap tmVX, const __grid_const
         }
         ptx::mbar_wait(&o_full[type], ph);
         ptx::tc_fence_after_sync();
-        if constexpr (TR) { if (tr) stamp(1); }
+        if constexpr (TR) { if (tr) stamp(1 + warp - EPI2_W0); }
         uint32_t zr[2][16], zi[2][16];
 #pragma unroll
         for (int h2 = 0; h2 < 2; ++h2) {
@@ -588,25 +594,36 @@ longconv_tc2_kernel(const __grid_constant__ CUtensorMap tmVX, const __grid_const
         ptx::tmem_ld_wait();
         ptx::tc_fence_before_sync();
         __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&e4_done[type]);   // the unit is free for the next same-type item's step 1
+        ptx::mbar_arrive_lane0(&e4_done[type], lane);   // the unit is free for the next same-type item's step 1
         ptx::mbar_wait(&g_full[buf], (it / NZ) & 1);
         // [n1][n2] bf16, 256 B per n1 row: gate in, product out
         unsigned short* st0 = reinterpret_cast<unsigned short*>(zb) + r + 32 * hf * 128;
         // One output per thread is enough for the range check: an overflow in P1 / P2 reaches every output of the item, one
         // in BT reaches every output of its row n2 - and a row is a thread here.
         const float chk = fmaf(__uint_as_float(zr[0][0]), 0.f, __uint_as_float(zi[0][0]) * 0.f);
+        // two n1 rows per packed multiply; bf16 -> fp32 of the gate by byte permute (ALU pipe: the FMA pipe is the busy one)
+        const f2t OSC = f2_pack(osc, osc);
+        auto gate2 = [&](const unsigned short* g) {
+          return f2_packu(__byte_perm(uint32_t(g[0]), 0u, 0x1044), __byte_perm(uint32_t(g[128]), 0u, 0x1044));
+        };
+        auto put2 = [&](unsigned short* g, f2t v) {   // one rounding, fp32 -> bf16, as before
+          float lo, hi;
+          f2_unpack(v, lo, hi);
+          const __nv_bfloat162 pk = __floats2bfloat162_rn(lo, hi);
+          const uint32_t u = *reinterpret_cast<const uint32_t*>(&pk);
+          g[0] = (unsigned short)u;
+          g[128] = (unsigned short)(u >> 16);
+        };
 #pragma unroll 1
         for (int h2 = 0; h2 < 2; ++h2) {
 #pragma unroll
-          for (int e = 0; e < 16; ++e) {
-            const float va = __uint_as_float(zr[0][e]) * osc, vb = __uint_as_float(zi[0][e]) * osc;
-            const float ga = __uint_as_float(uint32_t(st0[e * 128]) << 16);
-            const __nv_bfloat16 oa = __float2bfloat16(va * ga);
-            st0[e * 128] = *reinterpret_cast<const unsigned short*>(&oa);
+          for (int e = 0; e < 16; e += 2) {
             // (an odd batch's last item has no second read: that half of the buffer is neither loaded nor stored)
-            const float gb = __uint_as_float(uint32_t(st0[8192 + e * 128]) << 16);
-            const __nv_bfloat16 ob = __float2bfloat16(vb * gb);
-            st0[8192 + e * 128] = *reinterpret_cast<const unsigned short*>(&ob);
+            unsigned short* ga = st0 + e * 128;
+            unsigned short* gb = ga + 8192;
+            const f2t GA = gate2(ga), GB = gate2(gb);
+            put2(ga, f2_mul(f2_mul(f2_packu(zr[0][e], zr[0][e + 1]), OSC), GA));
+            put2(gb, f2_mul(f2_mul(f2_packu(zi[0][e], zi[0][e + 1]), OSC), GB));
           }
           st0 += 16 * 128;
 #pragma unroll
@@ -615,14 +632,14 @@ longconv_tc2_kernel(const __grid_constant__ CUtensorMap tmVX, const __grid_const
         if (chk != chk) atomicOr(p.err, 2);   // an fp16 operand overflowed somewhere in this item: the launch is reported
         ptx::fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&out_ready[buf]);
+        ptx::mbar_arrive_lane0(&out_ready[buf], lane);
       }
-      if constexpr (TR) { if (tr) stamp(1); }
+      if constexpr (TR) { if (tr) stamp(1 + warp - EPI2_W0); }
     }
   }
   ptx::tc_fence_before_sync();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == W_MMA) {
     ptx::tc_fence_after_sync();
     ptx::tmem_dealloc<512>(tmem_base);
   }

@@ -115,6 +115,34 @@ def test_longconv_tensor_core(engine, state_dict, T, B):
         assert rel <= 2e-3, (T, layer, rel)
 
 
+@pytest.mark.parametrize("T,B", [(8193, 7), (8200, 4), (8192, 1), (2057, 2), (6000, 33)])
+def test_longconv_tensor_core_two_in_flight_matches_one_item_kernel(engine, T, B):
+    """longconv_tc2_kernel (two items in flight per SM, default) against longconv_tc_kernel<false> (one item per SM,
+    option tc_pipe=0) on the same inputs: the same fp16 operands go through the same products, so the two differ by fp32
+    summation order of the tail tokens only.  Odd and large batches exercise the CTA item ranges (1 .. many items, with
+    and without a B-type partner for the last item)."""
+    D = CFG.d_model
+    Tp = (T + 127) // 128 * 128
+    g = torch.Generator().manual_seed(1000 + T + B)
+    vx = torch.zeros(B, D, Tp, dtype=torch.float16)
+    x0 = torch.zeros(B, D, Tp, dtype=torch.bfloat16)
+    vx[..., :T] = _rand_bf16((B, D, T), g).to(torch.float16)
+    x0[..., :T] = _rand_bf16((B, D, T), g)
+    vx, x0 = vx.cuda(), x0.cuda()
+    try:
+        outs = []
+        for pipe in (1, 0):
+            engine.set_option("tc_pipe", pipe)
+            outs.append(engine.longconv_tc(2, vx, x0, T)[..., :T].float().clone())
+        torch.cuda.synchronize()
+    finally:
+        engine.set_option("tc_pipe", 1)
+    d = (outs[0] - outs[1]).abs()
+    scale = outs[1].abs().max().item()
+    assert torch.equal(outs[0][..., : min(T, 8192)], outs[1][..., : min(T, 8192)]), d.max().item()
+    assert d.max().item() <= 1e-2 * max(1.0, scale)
+
+
 def _range_case(name, B, D, T, g):
     """v * x1 inputs far from N(0, 1): what a trained checkpoint (or a [PAD]-heavy batch) can feed the convolution."""
     x = torch.randn(B, D, T, generator=g)
