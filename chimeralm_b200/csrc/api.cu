@@ -64,6 +64,16 @@ struct LayerW {
   // longconv_tc dynamic-range factors (powers of two, see LongConvTcParams): table exponents, and two sets of
   // output/input factors - `cal` for the forward (input scale from the calibration draw), `unit` for a = 1 (raw fp16 entry)
   int* gexp = nullptr;                               // [n_seg][D]
+  // four-reads-per-item form (reads of <= 4096 tokens): spectrum table of the filter truncated to 4096 taps, its exponents,
+  // and 2^(gexp[0] - gexp4) per channel (applied on top of whichever output scale the launch uses)
+  __half2* gtc4 = nullptr;
+  int* gexp4 = nullptr;
+  float* tc_adj4 = nullptr;
+  // chunked two-in-flight form (reads longer than 8 200 tokens): V-form tables H_j = FFT([k_j | k_{j-1}]) (see
+  // tc::spectrum_kernel), their exponents and 2^(e[0] - e[j]).  H_0 = G_0, so the output scale is the same as gtc's.
+  __half2* gtcH = nullptr;
+  int* gexpH = nullptr;
+  float* tc_relH = nullptr;
   float *vx_scale = nullptr, *tc_osc = nullptr, *tc_inva = nullptr, *tc_rel = nullptr;
   float *unit_scale = nullptr, *unit_osc = nullptr, *unit_inva = nullptr;
   unsigned int* vx_amax = nullptr;                   // [D] float bits, calibration forward
@@ -160,6 +170,8 @@ struct clm_ctx {
   int mlp_stagger = 0;    // block_mlp: CTA phase stagger in cycles (0 = off)
   bool tc_conv = true;    // tensor-core FFT long convolution for reads of more than 2 056 tokens (needs fused_in)
   bool tc_pipe = true;    // single-transform reads (<= 8 200 tokens): two items in flight per SM (longconv_tc2_kernel)
+  bool tc_pack4 = true;   // reads of 2 049 .. 4 096 tokens: four reads per transform (needs tc_pipe)
+  bool tc_pipe_chunked = true;   // reads longer than 8 200 tokens on the two-in-flight kernel (V-form tables, no carry)
   __half* tc_S = nullptr; // shared-memory image of the DFT constant stack (longconv_tc)
   bool fused_head = true;         // pooling merge + classifier layers in one cooperative launch
   unsigned int* head_counter = nullptr;
@@ -673,11 +685,22 @@ TcPlan tc_plan(int T) {
 }
 size_t tc_scratch_per_cta(int nc) { return nc > 1 ? (size_t)(nc - 1) * tc::N + 2 * tc::C : 0; }   // floats (parked spectra are fp16 pairs)
 
+// Four reads per item (longconv_tc2_kernel<., true>), reads of 2 049 .. 4 096 tokens: one item costs what a two-read item
+// costs (~13.5 K cycles at the capped clock: the epilogue phases set the pace, the extra step-7 MMAs hide under them), so
+// the conv time of these buckets halves (profiles/r2_v3_length_sweep.txt: 4 096 tokens 1.53 -> 0.92 ms per batch,
+// 3 073 tokens 2.06 -> 1.19).  Up to 2 048 tokens the N = 4 096 fp32 transform is still cheaper per read (1 537 tokens:
+// 1.92 ms against 2.18).
+bool tc_pack4_applies(const clm_ctx* c, int T) {
+  return c->tc_conv && c->tc_pipe && c->tc_pack4 && c->layers[0].gtc4 != nullptr && T > tc::C / 4 && T <= tc::C / 2;
+}
+
 bool tc_conv_applies(const clm_ctx* c, int T) {
   // Below 2 057 tokens the fp32 FFT kernels win (N = 4 096: ~8.3 K cycles per item); from there on one tensor-core item
   // (13.4-14.6 K cycles for two reads of up to 8 192 tokens, the rows past T are zeros) beats the N = 8 192 fp32 transform
   // (~16 K cycles per item; profiles/r2_length_sweep.txt)
-  if (!c->tc_conv || T <= tc::C / 4 + LONGCONV_TAIL_MAX || c->layers[0].gtc == nullptr) return false;
+  if (!c->tc_conv || c->layers[0].gtc == nullptr) return false;
+  if (tc_pack4_applies(c, T)) return true;
+  if (T <= tc::C / 4 + LONGCONV_TAIL_MAX) return false;
   const TcPlan pl = tc_plan(T);
   return pl.nc == 1 || (c->tc_chunked && pl.nc <= std::min(c->tc_nseg, 4));   // the kernel's segment loop is unrolled for <= 4 chunks
 }
@@ -694,8 +717,15 @@ int launch_longconv_tc(clm_ctx* c, int layer, const __half* vx, const __nv_bfloa
   const cuuint64_t n_rows = (cuuint64_t)(whole_rows ? std::min(64, Tp / 128) : Tp / 128);   // 128-token rows per channel
   if (int rc_attr = ensure_smem_attr(c, (const void*)(longconv_tc_kernel<false>), (int)(tc::SMEM_TOTAL))) return rc_attr;
   if (int rc_attr = ensure_smem_attr(c, (const void*)(longconv_tc_kernel<true>), (int)(tc::SMEM_TOTAL))) return rc_attr;
-  if (int rc_attr = ensure_smem_attr(c, (const void*)(longconv_tc2_kernel<false>), (int)(tc2::SMEM2_TOTAL))) return rc_attr;
-  if (int rc_attr = ensure_smem_attr(c, (const void*)(longconv_tc2_kernel<true>), (int)(tc2::SMEM2_TOTAL))) return rc_attr;
+  {
+    const void* k2[] = {(const void*)(longconv_tc2_kernel<false, false, false>), (const void*)(longconv_tc2_kernel<true, false, false>),
+                        (const void*)(longconv_tc2_kernel<false, true, false>),  (const void*)(longconv_tc2_kernel<true, true, false>),
+                        (const void*)(longconv_tc2_kernel<false, false, true>),  (const void*)(longconv_tc2_kernel<true, false, true>)};
+    for (const void* f : k2)
+      if (int rc_attr = ensure_smem_attr(c, f, (int)(tc2::SMEM2_TOTAL))) return rc_attr;
+  }
+  const bool pack4 = tc_pack4_applies(c, T);   // four reads per item: 32-row boxes (one read's 4096 tokens) instead of 64
+  const cuuint32_t box_rows = pack4 ? 32 : 64;
   if (tc_scratch_per_cta(pl.nc) * c->num_sms > c->tc_scratch_floats)
     return fail(c, CLM_ERR_STATE, "longconv_tc: scratch too small for T=%d; call clm_reserve with max_T >= %d", T, T);
   LayerW& L = c->layers[layer];
@@ -704,7 +734,7 @@ int launch_longconv_tc(clm_ctx* c, int layer, const __half* vx, const __nv_bfloa
   {
     cuuint64_t dims[3] = {128, n_rows, (cuuint64_t)B * D};
     cuuint64_t strides[2] = {256, (cuuint64_t)Tp * 2};
-    cuuint32_t box[3] = {64, 64, 1}, estr[3] = {1, 1, 1};
+    cuuint32_t box[3] = {64, box_rows, 1}, estr[3] = {1, 1, 1};
     CUresult r = c->encode_tiled(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<__half*>(vx), dims, strides, box, estr,
                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -714,7 +744,7 @@ int launch_longconv_tc(clm_ctx* c, int layer, const __half* vx, const __nv_bfloa
   {
     cuuint64_t dims[3] = {128, n_rows, (cuuint64_t)B * D};
     cuuint64_t strides[2] = {256, (cuuint64_t)Tp * 2};
-    cuuint32_t box[3] = {128, 64, 1}, estr[3] = {1, 1, 1};
+    cuuint32_t box[3] = {128, box_rows, 1}, estr[3] = {1, 1, 1};
     CUresult r = c->encode_tiled(&tmo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, out, dims, strides, box, estr,
                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -724,7 +754,7 @@ int launch_longconv_tc(clm_ctx* c, int layer, const __half* vx, const __nv_bfloa
   {
     cuuint64_t dims[3] = {128, n_rows, (cuuint64_t)B * D};
     cuuint64_t strides[2] = {256, (cuuint64_t)Tp * 2};
-    cuuint32_t box[3] = {128, 64, 1}, estr[3] = {1, 1, 1};
+    cuuint32_t box[3] = {128, box_rows, 1}, estr[3] = {1, 1, 1};
     CUresult r = c->encode_tiled(&tmg, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<__nv_bfloat16*>(x0), dims, strides, box, estr,
                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -733,16 +763,27 @@ int launch_longconv_tc(clm_ctx* c, int layer, const __half* vx, const __nv_bfloa
   LongConvTcParams p{};
   p.T = T; p.vx = vx; p.k = L.k; p.dbias = L.fbias; p.Lk = c->Lk;
   p.x0 = x0; p.out = out; p.S = reinterpret_cast<const uint4*>(c->tc_S); p.G = reinterpret_cast<const uint4*>(L.gtc);
-  p.B = B; p.D = D; p.Tp = Tp; p.n_pairs = (B + 1) / 2; p.n_items = D * p.n_pairs; p.trace = trace;
+  p.B = B; p.D = D; p.Tp = Tp; p.n_pairs = pack4 ? (B + 3) / 4 : (B + 1) / 2; p.n_items = D * p.n_pairs; p.trace = trace;
+  if (pack4) { p.G = reinterpret_cast<const uint4*>(L.gtc4); p.osc_adj = L.tc_adj4; }
+  // chunked reads on the two-in-flight kernel: V-form tables (H_0 = G_0, so the output scale is unchanged)
+  const bool pipe_ch = pl.nc > 1 && c->tc_pipe && c->tc_pipe_chunked && L.gtcH != nullptr;
   p.n_chunks = pl.nc; p.nt = pl.nt; p.scratch = c->tc_scratch; p.scratch_per_cta = (long long)tc_scratch_per_cta(pl.nc);
   p.g_seg_stride = (long long)D * (tc::N / 4);
   p.osc = osc_override ? osc_override : (unit_scale ? L.unit_osc : L.tc_osc);
   p.inva = inva_override ? inva_override : (unit_scale ? L.unit_inva : L.tc_inva);
   p.rel = L.tc_rel; p.err = (unit_scale || osc_override) ? c->d_err + 1 : c->d_err;
   const int grid = std::min(p.n_items, c->num_sms);
-  if (pl.nc > 1) longconv_tc_kernel<true><<<grid, tc::THREADS_CH, tc::SMEM_TOTAL, st>>>(tm, tmo, tmg, p);
-  else if (c->tc_pipe && trace) longconv_tc2_kernel<true><<<grid, tc2::THREADS2, tc2::SMEM2_TOTAL, st>>>(tm, tmo, tmg, p);
-  else if (c->tc_pipe) longconv_tc2_kernel<false><<<grid, tc2::THREADS2, tc2::SMEM2_TOTAL, st>>>(tm, tmo, tmg, p);
+  if (pipe_ch) {
+    p.G = reinterpret_cast<const uint4*>(L.gtcH);
+    p.rel = L.tc_relH;
+    if (trace) longconv_tc2_kernel<true, false, true><<<grid, tc2::THREADS2, tc2::SMEM2_TOTAL, st>>>(tm, tmo, tmg, p);
+    else longconv_tc2_kernel<false, false, true><<<grid, tc2::THREADS2, tc2::SMEM2_TOTAL, st>>>(tm, tmo, tmg, p);
+  }
+  else if (pl.nc > 1) longconv_tc_kernel<true><<<grid, tc::THREADS_CH, tc::SMEM_TOTAL, st>>>(tm, tmo, tmg, p);
+  else if (pack4 && trace) longconv_tc2_kernel<true, true, false><<<grid, tc2::THREADS2, tc2::SMEM2_TOTAL, st>>>(tm, tmo, tmg, p);
+  else if (pack4) longconv_tc2_kernel<false, true, false><<<grid, tc2::THREADS2, tc2::SMEM2_TOTAL, st>>>(tm, tmo, tmg, p);
+  else if (c->tc_pipe && trace) longconv_tc2_kernel<true, false, false><<<grid, tc2::THREADS2, tc2::SMEM2_TOTAL, st>>>(tm, tmo, tmg, p);
+  else if (c->tc_pipe) longconv_tc2_kernel<false, false, false><<<grid, tc2::THREADS2, tc2::SMEM2_TOTAL, st>>>(tm, tmo, tmg, p);
   else longconv_tc_kernel<false><<<grid, tc::THREADS, tc::SMEM_TOTAL, st>>>(tm, tmo, tmg, p);
   CLM_LAUNCH_CHECK(c, pl.nc > 1 ? "longconv_tc_chunked" : (c->tc_pipe ? "longconv_tc2" : "longconv_tc"));
   return 0;
@@ -1056,6 +1097,21 @@ int clm_finalize(clm_ctx* c) {
       tc::scales_kernel<<<(D + 255) / 256, 256>>>(L.gexp, nullptr, L.unit_scale, L.unit_osc, L.unit_inva, L.tc_rel, D, c->tc_nseg, 0);
       tc::scales_kernel<<<(D + 255) / 256, 256>>>(L.gexp, nullptr, L.vx_scale, L.tc_osc, L.tc_inva, L.tc_rel, D, c->tc_nseg, 0);
       CLM_LAUNCH_CHECK(c, "tc_scales");
+      // the same filter truncated to its first 4096 taps (all a read of <= 4096 tokens can see): four reads per transform
+      if ((rc = dev_alloc(c, &L.gtc4, (size_t)D * tc::N))) return rc;
+      if ((rc = dev_alloc(c, &L.gexp4, (size_t)D))) return rc;
+      if ((rc = dev_alloc(c, &L.tc_adj4, (size_t)D))) return rc;
+      tc::spectrum_kernel<<<dim3(D, 1), 256, tc::N * sizeof(float2)>>>(L.k, c->Lk, std::min(c->cfg.max_seq_len, tc::C / 2), L.fbias, L.gtc4, L.gexp4);
+      tc::exp_adj_kernel<<<(D + 255) / 256, 256>>>(L.gexp, L.gexp4, L.tc_adj4, D);
+      CLM_LAUNCH_CHECK(c, "tc_spectrum4");
+      if (c->tc_nseg > 1) {
+        if ((rc = dev_alloc(c, &L.gtcH, (size_t)c->tc_nseg * D * tc::N))) return rc;
+        if ((rc = dev_alloc(c, &L.gexpH, (size_t)c->tc_nseg * D))) return rc;
+        if ((rc = dev_alloc(c, &L.tc_relH, (size_t)c->tc_nseg * D))) return rc;
+        tc::spectrum_kernel<<<dim3(D, c->tc_nseg), 256, tc::N * sizeof(float2)>>>(L.k, c->Lk, c->cfg.max_seq_len, L.fbias, L.gtcH, L.gexpH, 1);
+        tc::rel_kernel<<<(D + 255) / 256, 256>>>(L.gexpH, L.tc_relH, D, c->tc_nseg);
+        CLM_LAUNCH_CHECK(c, "tc_spectrumH");
+      }
     }
   }
   if ((rc = dev_alloc(c, &c->tc_S, (size_t)tc::S_BYTES / 2))) return rc;
@@ -1533,6 +1589,8 @@ int clm_set_option(clm_ctx* c, const char* name, int value) {
   else if (n == "tc_conv") c->tc_conv = value != 0;
   else if (n == "tc_chunked") c->tc_chunked = value != 0;
   else if (n == "tc_pipe") c->tc_pipe = value != 0;
+  else if (n == "tc_pack4") c->tc_pack4 = value != 0;
+  else if (n == "tc_pipe_chunked") c->tc_pipe_chunked = value != 0;
   else if (n == "fused_score_pool") c->fused_score_pool = value != 0;
   else if (n == "fused_head") c->fused_head = value != 0;
   else if (n == "mlp_stagger") c->mlp_stagger = value;

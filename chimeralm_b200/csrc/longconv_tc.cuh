@@ -64,6 +64,7 @@ struct LongConvTcParams {
   const float* osc;          // [D]
   const float* inva;         // [D]
   const float* rel;          // [n_seg][D]
+  const float* osc_adj;      // [D] four-reads-per-item form only: 2^(e[0][ch] - e4[ch]), e4 = exponent of the 4096-tap table
   int* err;                  // status word: bit 1 (value 2) is set when an output is not finite (fp16 range exceeded)
   long long* trace;          // optional [2][64] clock64 stamps of CTA 0: row 0 = MMA issuer, row 1 = epilogue warp 2
 };
@@ -137,9 +138,14 @@ __global__ void build_s_kernel(__half* __restrict__ img) {
 // {re(k2, k2+1), im(k2, k2+1), re(k2+2, k2+3), im(k2+2, k2+3)} at uint4 index
 //   (((ch * 4 + k1 / 32) * 2 + k2 / 64) * 16 + (k2 % 64) / 4) * 32 + k1 % 32
 // so that a warp of 32 consecutive k1 reads 512 contiguous bytes per 16-byte load.
+// vform: the table of segment j also carries segment j - 1 in the SECOND half of the 16384-point window,
+//   H_j = FFT([k_j | k_{j-1}]) = G_j + (-1)^k G_{j-1}.
+// With these tables the overlap-add over chunks needs no carry: the output chunk m is the FIRST half of
+// IFFT(sum_c S_c H_{m-c}), because the second half of x_c * k_j (which belongs to chunk c + j + 1) is the first half of
+// the same product shifted by half a period, i.e. of S_c G_j (-1)^k (longconv_tc2_kernel, chunked form).
 __global__ void __launch_bounds__(256) spectrum_kernel(const float* __restrict__ k, long long Lk, int n_taps,
                                                        const float* __restrict__ dbias, __half2* __restrict__ G_all,
-                                                       int* __restrict__ gexp) {
+                                                       int* __restrict__ gexp, int vform = 0) {
   extern __shared__ float2 sm_a[];            // A[k1][n2], 128 KB
   __shared__ float2 w128[128];
   __shared__ float red[8];
@@ -165,6 +171,16 @@ __global__ void __launch_bounds__(256) spectrum_kernel(const float* __restrict__
       const float2 w = w128[(k1 * n1) & 127];
       ar = fmaf(v, w.x, ar);
       ai = fmaf(v, w.y, ai);
+    }
+    if (vform && seg > 0) {   // second half of the window: the previous segment (all of its C taps exist; tap 0 of the
+      const float* kp = kc - C;   // filter, with the bias skip, sits at the start of segment 0)
+      for (int n1 = 64; n1 < 128; ++n1) {
+        const int t = 128 * (n1 - 64) + n2;
+        const float v = kp[t] + ((seg == 1 && t == 0) ? dbias[ch] : 0.f);
+        const float2 w = w128[(k1 * n1) & 127];
+        ar = fmaf(v, w.x, ar);
+        ai = fmaf(v, w.y, ai);
+      }
     }
     float s, c;
     sincospif(-2.0f * float((k1 * n2) % N) / float(N), &s, &c);
@@ -267,6 +283,19 @@ __global__ void scales_kernel(const int* __restrict__ gexp, const unsigned int* 
   inva[ch] = ldexpf(1.0f, -ea);
   osc[ch] = ldexpf(1.0f, -e0 - ea - 11);    // 1 / (2^e0 * a * N * S1), N * S1 = 2048
   for (int j = 0; j < n_seg; ++j) rel[j * D + ch] = ldexpf(1.0f, max(-120, min(120, e0 - gexp[j * D + ch])));
+}
+
+// rel[j][ch] = 2^(e[0][ch] - e[j][ch]) for a table set of its own (the V-form tables of the chunked two-in-flight kernel)
+__global__ void rel_kernel(const int* __restrict__ gexp, float* __restrict__ rel, int D, int n_seg) {
+  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ch >= D) return;
+  for (int j = 0; j < n_seg; ++j) rel[j * D + ch] = ldexpf(1.0f, max(-120, min(120, gexp[ch] - gexp[j * D + ch])));
+}
+
+// adj[ch] = 2^(e[ch] - e4[ch]): brings the output scale of the full-filter table to the 4096-tap table's exponent
+__global__ void exp_adj_kernel(const int* __restrict__ gexp, const int* __restrict__ gexp4, float* __restrict__ adj, int D) {
+  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ch < D) adj[ch] = ldexpf(1.0f, max(-120, min(120, gexp[ch] - gexp4[ch])));
 }
 
 // bf16 -> fp16 with the per-channel input scale and zeros past T (what block_in emits in the forward)

@@ -34,7 +34,7 @@ constexpr int OFF2_S = 0;
 constexpr int OFF2_Z = OFF2_S + S2_BYTES;
 constexpr int OFF2_BT = OFF2_Z + NZ * Z_BYTES;
 constexpr int OFF2_BAR = OFF2_BT + BT_BYTES;      // 229376
-constexpr int SMEM2_TOTAL = OFF2_BAR + 512;
+constexpr int SMEM2_TOTAL = OFF2_BAR + 1024;
 constexpr int THREADS2 = 384;
 constexpr int FRE = 0, FIM = 128;                 // row blocks of the constant stack
 constexpr int EPI2_W0 = 0;                        // epilogue warps 0..7
@@ -49,7 +49,21 @@ __host__ __device__ constexpr uint32_t idesc2(uint32_t n, bool a_mn, bool b_mn, 
 }
 }  // namespace tc2
 
-template <bool TR>   // TR: record the clock trace of CTA 0 (clm_longconv_tc_trace); the product launch carries no stamps
+// TR: record the clock trace of CTA 0 (clm_longconv_tc_trace); the product launch carries no stamps.
+// P4: reads of at most 4096 tokens, FOUR reads per item.  A causal convolution of a T-token read needs taps 0..T-1 only,
+// so with the filter truncated to 4096 taps (its own spectrum table) a 16384-point transform has room for two reads per
+// real sequence: [read 0 | 4096 zeros | read 1 | 4096 zeros] convolves to [out 0 (8192) | out 1 (8192)] without overlap.
+// z = (reads 4q, 4q+1) + i (reads 4q+2, 4q+3).  The nonzero input rows are n1 in [0,32) and [64,96) (still K = 64 in step 1:
+// the constants' K slices jump to the second panel), the wanted output rows are the same two runs (step 7: two N = 32
+// groups per half instead of one N = 64), and the gate / output tile holds 32 rows of each of the four reads.  Everything
+// between (steps 3 and 5, E1-E3) is unchanged, so the conv cost per read halves for the short-read buckets.
+// CH: reads longer than 8 200 tokens, overlap-add over chunks of 8 192 tokens in the frequency domain.  A work unit is
+// (item, chunk); the two units in flight are consecutive chunks of one item (or the last / first of two).  Chunk c's
+// spectrum S_c is parked (fp16 pairs, per-CTA scratch, each thread re-reads only what it wrote) and E2 forms
+//   V_c = sum_{j <= c} S_{c-j} H_j,   H_j = FFT([k_j | k_{j-1}])   (V-form tables, tc::spectrum_kernel)
+// so that the chunk's outputs are the FIRST half of one inverse transform: no second output half, no carry between chunks,
+// and steps 1 / 7, E1, E3, E4 are exactly the single-transform ones.  Tail tokens (t >= NC C): see the tail warp.
+template <bool TR, bool P4, bool CH>
 __global__ void __launch_bounds__(tc2::THREADS2, 1)
 longconv_tc2_kernel(const __grid_constant__ CUtensorMap tmVX, const __grid_constant__ CUtensorMap tmOut,
                     const __grid_constant__ CUtensorMap tmX0, LongConvTcParams p) {
@@ -76,8 +90,13 @@ longconv_tc2_kernel(const __grid_constant__ CUtensorMap tmVX, const __grid_const
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int per = (p.n_items + gridDim.x - 1) / gridDim.x;
   const int item0 = blockIdx.x * per, item1 = min(p.n_items, item0 + per);
-  const int n = max(0, item1 - item0);
+  const int NC = CH ? p.n_chunks : 1;
+  const int n = max(0, item1 - item0) * NC;   // work units of this CTA: (local item, chunk), chunk fastest
+  const int inv_nc = 65536 / NC + 1;          // u / NC = (u * inv_nc) >> 16 for u < 4096, NC <= 4
+  auto u_item = [&](int u) { return CH ? (u * inv_nc) >> 16 : u; };
+  auto u_chunk = [&](int u) { return CH ? u - ((u * inv_nc) >> 16) * NC : 0; };
   const int nt = p.nt;
+  float* tailF = reinterpret_cast<float*>(bars + 48);   // [NZ][2 reads][8]: first-row outputs of a unit, for the tail warp (CH)
   long long* trace = (TR && p.trace && blockIdx.x == 0) ? p.trace : nullptr;
   int trace_n = 0;
   auto stamp = [&](int role) {
@@ -118,23 +137,36 @@ longconv_tc2_kernel(const __grid_constant__ CUtensorMap tmVX, const __grid_const
     ptx::setmaxnreg_dec<104>();
     if (lane == 0) {
       auto load_z = [&](int it) {
-        const int buf = it % NZ, item = item0 + it;
+        const int buf = it % NZ, item = item0 + u_item(it), c = u_chunk(it);
         const int ch = item / p.n_pairs, pr = item % p.n_pairs;
         uint8_t* z = smem + OFF2_Z + buf * Z_BYTES;
         ptx::mbar_expect_tx(&z_full[buf], Z_BYTES);
         for (int part = 0; part < 2; ++part) {
-          const int row = (2 * pr + part) * p.D + ch;    // reads past B are out of bounds -> zero filled
-          for (int a = 0; a < 2; ++a) ptx::tma_load_3d(z + part * 16384 + a * 8192, &tmVX, &z_full[buf], 64 * a, 0, row);
+          if constexpr (P4) {   // K rows 0..31: first read of the part (n1 = 0..31), K rows 32..63: second read (n1 = 64..95)
+            for (int sl = 0; sl < 2; ++sl) {
+              const int row = (4 * pr + 2 * part + sl) * p.D + ch;   // reads past B are out of bounds -> zero filled
+              for (int a = 0; a < 2; ++a)
+                ptx::tma_load_3d(z + part * 16384 + a * 8192 + sl * 4096, &tmVX, &z_full[buf], 64 * a, 0, row);
+            }
+          } else {
+            const int row = (2 * pr + part) * p.D + ch;    // reads past B are out of bounds -> zero filled
+            for (int a = 0; a < 2; ++a) ptx::tma_load_3d(z + part * 16384 + a * 8192, &tmVX, &z_full[buf], 64 * a, 64 * c, row);
+          }
         }
       };
       for (int it = 0; it < min(n, NZ); ++it) load_z(it);
       for (int j = 0; j < n; ++j) {
-        const int buf = j % NZ, item = item0 + j;
+        const int buf = j % NZ, item = item0 + u_item(j), c = u_chunk(j);
         const int ch = item / p.n_pairs, pr = item % p.n_pairs;
         uint8_t* z = smem + OFF2_Z + buf * Z_BYTES;
         ptx::mbar_wait(&out_ready[buf], (j / NZ) & 1);
-        ptx::tma_store_3d(&tmOut, z, 0, 0, 2 * pr * p.D + ch);
-        if (2 * pr + 1 < p.B) ptx::tma_store_3d(&tmOut, z + 16384, 0, 0, (2 * pr + 1) * p.D + ch);
+        if constexpr (P4) {   // 32 rows of each of the four reads (stores of reads past B are clipped)
+          for (int q4 = 0; q4 < 4; ++q4)
+            ptx::tma_store_3d(&tmOut, z + (q4 >> 1) * 16384 + (q4 & 1) * 8192, 0, 0, (4 * pr + q4) * p.D + ch);
+        } else {
+          ptx::tma_store_3d(&tmOut, z, 0, 64 * c, 2 * pr * p.D + ch);
+          if (2 * pr + 1 < p.B) ptx::tma_store_3d(&tmOut, z + 16384, 0, 64 * c, (2 * pr + 1) * p.D + ch);
+        }
         ptx::tma_store_commit();
         if (j + NZ < n) {
           ptx::tma_store_wait_read<0>();
@@ -150,7 +182,7 @@ longconv_tc2_kernel(const __grid_constant__ CUtensorMap tmVX, const __grid_const
     ptx::setmaxnreg_dec<104>();
     constexpr uint32_t id1 = idesc2(128, false, true, false, false), id1n = idesc2(128, false, true, true, false);
     constexpr uint32_t id35 = idesc2(128, false, false, false, false), id35n = idesc2(128, false, false, false, true);
-    constexpr uint32_t id7 = idesc2(64, true, false, false, false), id7n = idesc2(64, true, false, false, true);
+    constexpr uint32_t id7 = idesc2(P4 ? 32 : 64, true, false, false, false), id7n = idesc2(P4 ? 32 : 64, true, false, false, true);
     const uint32_t sS = ptx::smem_u32(smem + OFF2_S), sBT = ptx::smem_u32(smem + OFF2_BT);
     const uint64_t dS = ptx::smem_desc_k_sw128(sS);
     auto s_desc = [&](int row0, int kk) -> uint64_t {    // constant rows row0.., K index kk (multiple of 16)
@@ -240,12 +272,23 @@ longconv_tc2_kernel(const __grid_constant__ CUtensorMap tmVX, const __grid_const
           if (!is7) {   // 64 K rows: one pass
             const uint32_t id = neg ? id1n : id1;
 #pragma unroll
-            for (int jj = 0; jj < 4; ++jj) ptx::umma_f16_e(dst, dc + 2 * jj, dd + 128 * jj, id, (part | jj) != 0);
+            for (int jj = 0; jj < 4; ++jj)   // P4: input rows n1 = 0..31 and 64..95 -> K slices 0, 16 of panel 0 and of panel 1
+              ptx::umma_f16_e(dst, P4 ? dc + (jj >> 1) * (S2_PANEL >> 4) + 2 * (jj & 1) : dc + 2 * jj, dd + 128 * jj, id, (part | jj) != 0);
           } else {      // 128 K rows: both panels of the constants
             const uint32_t id = neg ? id7n : id7;
+            if constexpr (P4) {   // output rows n1 = 0..31 -> columns [0,32) of the half, n1 = 64..95 -> columns [32,64)
+#pragma unroll 1
+              for (int g = 0; g < 2; ++g) {
+                const uint64_t dcg = dc + (uint64_t)((g * 64 * 128) >> 4);
 #pragma unroll
-            for (int jj = 0; jj < 8; ++jj)
-              ptx::umma_f16_e(dst, dd + 128 * jj, dc + (jj >> 2) * (S2_PANEL >> 4) + 2 * (jj & 3), id, (part | jj) != 0);
+                for (int jj = 0; jj < 8; ++jj)
+                  ptx::umma_f16_e(dst + 32 * g, dd + 128 * jj, dcg + (jj >> 2) * (S2_PANEL >> 4) + 2 * (jj & 3), id, (part | jj) != 0);
+              }
+            } else {
+#pragma unroll
+              for (int jj = 0; jj < 8; ++jj)
+                ptx::umma_f16_e(dst, dd + 128 * jj, dc + (jj >> 2) * (S2_PANEL >> 4) + 2 * (jj & 3), id, (part | jj) != 0);
+            }
           }
         }
         ptx::umma_commit_e(is7 ? &o_full[type] : &x_full[type]);
@@ -258,14 +301,15 @@ longconv_tc2_kernel(const __grid_constant__ CUtensorMap tmVX, const __grid_const
     // scheduler with, and the slowest epilogue warp sets the pace of every barrier)
     ptx::setmaxnreg_dec<104>();
     const bool gate_warp = warp == W_AUX;
-    for (int k = (gate_warp || nt > 0) ? 0 : n; 2 * k <= n; ++k) {
+    float a_prev = 0.f, b_prev = 0.f;   // tail recurrence over the chunks of an item (chunked form)
+    for (int k = (gate_warp || (!P4 && nt > 0)) ? 0 : n; 2 * k <= n; ++k) {
 #pragma unroll 1
       for (int sub = 0; sub < 4; ++sub) {
         // order of the events: x_full(A_k) [gate], bt_full(B_k-1) [tail], x_full(B_k) [gate], bt_full(A_k) [tail]
         const int it = 2 * k + (sub == 1 ? -1 : (sub == 2 ? 1 : 0));
         if (it < 0 || it >= n || ((sub & 1) == 0) != gate_warp) continue;
         const uint32_t type = it & 1, ph = (it >> 1) & 1;
-        const int item = item0 + it;
+        const int item = item0 + u_item(it), cc = u_chunk(it);
         const int ch = item / p.n_pairs, pr = item % p.n_pairs;
         const int b0 = 2 * pr, b1 = 2 * pr + 1;
         const bool has1 = b1 < p.B;
@@ -274,32 +318,48 @@ longconv_tc2_kernel(const __grid_constant__ CUtensorMap tmVX, const __grid_const
             const int buf = it % NZ;
             uint8_t* zb = smem + OFF2_Z + buf * Z_BYTES;
             ptx::mbar_wait(&x_full[type], ph);
-            ptx::mbar_expect_tx(&g_full[buf], has1 ? Z_BYTES : Z_BYTES / 2);
-            ptx::tma_load_3d(zb, &tmX0, &g_full[buf], 0, 0, b0 * p.D + ch);
-            if (has1) ptx::tma_load_3d(zb + 16384, &tmX0, &g_full[buf], 0, 0, b1 * p.D + ch);
+            if constexpr (P4) {   // 32 rows of each of the four reads (reads past B: zero filled)
+              ptx::mbar_expect_tx(&g_full[buf], Z_BYTES);
+              for (int q4 = 0; q4 < 4; ++q4)
+                ptx::tma_load_3d(zb + (q4 >> 1) * 16384 + (q4 & 1) * 8192, &tmX0, &g_full[buf], 0, 0, (4 * pr + q4) * p.D + ch);
+            } else {
+              ptx::mbar_expect_tx(&g_full[buf], has1 ? Z_BYTES : Z_BYTES / 2);
+              ptx::tma_load_3d(zb, &tmX0, &g_full[buf], 0, 64 * cc, b0 * p.D + ch);
+              if (has1) ptx::tma_load_3d(zb + 16384, &tmX0, &g_full[buf], 0, 64 * cc, b1 * p.D + ch);
+            }
           }
           __syncwarp();
         } else if (nt > 0) {
-          // Tail tokens t = C + j (j < nt): output C + j of the transform = sum_k1 (-1)^k1 BT[k1][n2 = j] (row n1 = 64 of
-          // step 7: conj(F)[k1][64] = (-1)^k1), which holds the taps 0..8191 part; the <= 2 (j + 1) products with the taps
-          // the transform wraps around are added directly: x[i] k'[C + j - i] (a = 0) and x[C + i] k'[j - i] (a = 1), i <= j.
-          // Lane = (j = lane & 7, a = bit 3, read = bit 4) for the products, (j, k1 quarter = lane >> 3) for the BT sums.
-          const int jl = lane & 7, a = (lane >> 3) & 1, rd = lane >> 4;
+          // Tail tokens t = NC C + j (j < nt <= 8).  Row n1 = 64 of a unit's inverse transform - an alternating sum over BT,
+          // conj(F)[k1][64] = (-1)^k1 - is the value at C + j of that transform.  Single transform (NC = 1): that is the
+          // taps 0..8191 part of output C + j, and the <= 2 (j + 1) products the transform wraps around are added directly:
+          // x[a C + i] k'[(NC - a) C + j - i], a = 0..NC, i <= j.  Chunked: with the V-form tables unit m's transform is
+          // w_m + shift(w_{m-1}), w_m = IFFT(sum_{c+s=m} S_c G_s), so its first-row outputs are F_m = a_m + b_{m-1} and its
+          // row 64 is R_m = b_m + a_{m-1} (a / b = value j of the first / second half of w_m); the recurrence
+          // a_m = F_m - b_{m-1}, b_m = R_m - a_{m-1} over the item's units yields b_{NC-1}, the pairs c + s = NC - 1, and
+          // the pairs c + s = NC are the same direct products.  F_m comes from the E4 thread that owns it (tailF).
+          // Lane = (j = lane & 7, a parity = bit 3, read = bit 4) for the products, (j, k1 mod 4 = lane >> 3) for the BT sums.
+          const int jl = lane & 7, abit = (lane >> 3) & 1, rd = lane >> 4;
           const bool live = jl < nt && (rd == 0 || has1);
+          const bool last = cc == NC - 1;
           const long long rowb = ((long long)(rd ? b1 : b0) * p.D + ch) * p.Tp;
-          const float* kq = p.k + (long long)ch * p.Lk + (a ? 0 : C);
-          const __half* xq = p.vx + rowb + (a ? C : 0);
-          float tcv = 0.f;
-#pragma unroll 1
-          for (int i = 0; i < nt; ++i)   // rolled (code size); nt = 1 for a maximum-length read
-            if (live && i <= jl) {
-              float kv = __ldg(kq + (jl - i));
-              if (a == 1 && i == jl) kv += __ldg(p.dbias + ch);   // tap 0 carries the bias skip
-              tcv = fmaf(__half2float(xq[i]), kv, tcv);
-            }
-          tcv += __shfl_xor_sync(0xffffffffu, tcv, 8);
           const float inva = __ldg(p.inva + ch), osc = __ldg(p.osc + ch);
-          const float tx = live ? __bfloat162float(p.x0[rowb + C + jl]) : 0.f;
+          float tcv = 0.f, tx = 0.f;
+          if (last) {
+            const float* kq = p.k + (long long)ch * p.Lk;
+#pragma unroll 1
+            for (int a = abit; a <= NC; a += 2)
+#pragma unroll 1
+              for (int i = 0; i < nt; ++i)   // rolled (code size); nt = 1 for a maximum-length read
+                if (live && i <= jl) {
+                  const int tap = (NC - a) * C + jl - i;
+                  float kv = __ldg(kq + tap);
+                  if (tap == 0) kv += __ldg(p.dbias + ch);   // tap 0 carries the bias skip
+                  tcv = fmaf(__half2float(p.vx[rowb + (long long)a * C + i]), kv, tcv);
+                }
+            if (live) tx = __bfloat162float(p.x0[rowb + (long long)NC * C + jl]);
+          }
+          tcv += __shfl_xor_sync(0xffffffffu, tcv, 8);
           ptx::mbar_wait(&bt_full[type], ph);
           // n2 = 0..7 is 16-byte chunk 0 of atom 0, stored at chunk position k1 & 7 of its 128-byte row
           float sre = 0.f, sim = 0.f;
@@ -323,7 +383,18 @@ longconv_tc2_kernel(const __grid_constant__ CUtensorMap tmVX, const __grid_const
           sim += __shfl_xor_sync(0xffffffffu, sim, 16);
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive(&bt_read[type]);
-          if (live && a == 0) p.out[rowb + C + jl] = __float2bfloat16(((rd ? sim : sre) * osc + tcv * inva) * tx);
+          float tail = (rd ? sim : sre) * osc;
+          if constexpr (CH) {
+            const int buf = it % NZ;
+            ptx::mbar_wait(&out_ready[buf], (it / NZ) & 1);   // E4 of this unit has published F_m
+            const float F = tailF[(buf * 2 + rd) * 8 + jl];
+            if (cc == 0) { a_prev = 0.f; b_prev = 0.f; }
+            const float a_m = F - b_prev, b_m = tail - a_prev;
+            a_prev = a_m;
+            b_prev = b_m;
+            tail = b_m;
+          }
+          if (last && live && abit == 0) p.out[rowb + (long long)NC * C + jl] = __float2bfloat16((tail + tcv * inva) * tx);
         }
       }
     }
@@ -357,7 +428,14 @@ longconv_tc2_kernel(const __grid_constant__ CUtensorMap tmVX, const __grid_const
     // spectrum-table lines of this thread: uint4 (4 consecutive k2) at (((ch * 4 + k1 / 32) * 2 + k2 / 64) * 16 + (k2 % 64) / 4) * 32
     // + k1 % 32; an index half of this warp (k2 = 64 h + 32 hf + 0..31) is 8 uint4, 32 apart.  The first half of the NEXT E2
     // is fetched during the phase before it (E3 or E4: the L2 round trip would otherwise open every E2).
-    auto g_ptr = [&](int it, int h) { return p.G + ((((size_t)ch_of(it) * 4 + q) * 2) * 16 + 16 * h + 8 * hf) * 32 + lane; };
+    // (`it` = work unit; chunked form: table of filter segment `seg`, the unit's own chunk always takes segment 0)
+    auto g_ptr = [&](int it, int h, int seg = 0) {
+      return p.G + (CH ? (size_t)seg * p.g_seg_stride : 0) + ((((size_t)ch_of(u_item(it)) * 4 + q) * 2) * 16 + 16 * h + 8 * hf) * 32 + lane;
+    };
+    // chunked form: this CTA's parked spectra, chunk c at uint4 [c * 4096, (c + 1) * 4096): run (h, uu), uint4 v of thread
+    // tid_e at ((h * 2 + uu) * 4 + v) * 256 + tid_e (fp16 pairs in the spectrum-table layout)
+    uint4* park = reinterpret_cast<uint4*>(p.scratch + (long long)blockIdx.x * p.scratch_per_cta);
+    const int tid_e = (warp - EPI2_W0) * 32 + lane;
     uint4 gpre[8];
     int gpre_it = -1;
 #pragma unroll
@@ -446,9 +524,11 @@ longconv_tc2_kernel(const __grid_constant__ CUtensorMap tmVX, const __grid_const
         const uint32_t t_re = U1 + lane_addr, t_im = U3 + lane_addr;
         uint4 g[8], g2[8];
         {
-          const uint4* g1 = g_ptr(it, 1);
+          if constexpr (!CH) {   // (chunked form: the second half's table lines are fetched between the halves - registers)
+            const uint4* g1 = g_ptr(it, 1);
 #pragma unroll
-          for (int v = 0; v < 8; ++v) g2[v] = __ldg(g1 + v * 32);
+            for (int v = 0; v < 8; ++v) g2[v] = __ldg(g1 + v * 32);
+          }
           if (gpre_it != it) {   // first item of the CTA: nothing ran before this E2
             const uint4* g0 = g_ptr(it, 0);
 #pragma unroll
@@ -460,21 +540,40 @@ longconv_tc2_kernel(const __grid_constant__ CUtensorMap tmVX, const __grid_const
         ptx::mbar_wait(&y_full[type], ph);
         ptx::tc_fence_after_sync();
         if constexpr (TR) { if (tr) stamp(1 + warp - EPI2_W0); }
+        const int cc = u_chunk(it);
 #pragma unroll 1
         for (int h = 0; h < 2; ++h) {
           uint32_t xr2[2][16], xi2[2][16];
+          if constexpr (!CH) {
 #pragma unroll
-          for (int uu = 0; uu < 2; ++uu) {
-            tmem_ld16(t_re + 64 * h + 32 * hf + 16 * uu, xr2[uu]);
-            tmem_ld16(t_im + 64 * h + 32 * hf + 16 * uu, xi2[uu]);
+            for (int uu = 0; uu < 2; ++uu) {
+              tmem_ld16(t_re + 64 * h + 32 * hf + 16 * uu, xr2[uu]);
+              tmem_ld16(t_im + 64 * h + 32 * hf + 16 * uu, xi2[uu]);
+            }
+            ptx::tmem_ld_wait();
           }
-          ptx::tmem_ld_wait();
 #pragma unroll
           for (int uu = 0; uu < 2; ++uu) {
             uint32_t w[16];
+            uint4 gq[4], sq[4];   // chunked form: operands of the first extra product, requested before anything else of the run
+            const size_t slot = (size_t)((h * 2 + uu) * 4) * 256 + tid_e;
+            if constexpr (CH) {   // one run at a time: the segment sum below needs the registers
+              if (cc > 0) {
+                const uint4* gj = g_ptr(it, h, 1) + (4 * uu) * 32;
+#pragma unroll
+                for (int v = 0; v < 4; ++v) {
+                  gq[v] = __ldg(gj + v * 32);
+                  sq[v] = park[(size_t)(cc - 1) * 4096 + slot + (size_t)v * 256];
+                }
+              }
+              tmem_ld16(t_re + 64 * h + 32 * hf + 16 * uu, xr2[uu]);
+              tmem_ld16(t_im + 64 * h + 32 * hf + 16 * uu, xi2[uu]);
+              ptx::tmem_ld_wait();
+            }
             const uint32_t (&xr)[16] = xr2[uu];
             const uint32_t (&xi)[16] = xi2[uu];
             const uint32_t col = 64 * h + 32 * hf + 16 * uu;
+            f2t ar[8], ai[8];   // products for elements (2 m, 2 m + 1)
 #pragma unroll
             for (int v = 0; v < 4; ++v) {
               const uint32_t gw[4] = {g[4 * uu + v].x, g[4 * uu + v].y, g[4 * uu + v].z, g[4 * uu + v].w};
@@ -483,9 +582,56 @@ longconv_tc2_kernel(const __grid_constant__ CUtensorMap tmVX, const __grid_const
                 const int idx = 4 * v + 2 * hp;
                 const f2t GR = h2_to_f2(gw[2 * hp]), GI = h2_to_f2(gw[2 * hp + 1]);
                 const f2t XR = f2_packu(xr[idx], xr[idx + 1]), XI = f2_packu(xi[idx], xi[idx + 1]);
-                w[idx / 2] = f2_to_h2(f2_sub(f2_mul(XR, GR), f2_mul(XI, GI)));
-                w[8 + idx / 2] = f2_to_h2(f2_fma(XR, GI, f2_mul(XI, GR)));
+                ar[idx / 2] = f2_sub(f2_mul(XR, GR), f2_mul(XI, GI));
+                ai[idx / 2] = f2_fma(XR, GI, f2_mul(XI, GR));
               }
+            }
+            if constexpr (CH) {
+              // park this chunk's spectrum for the later chunks (fp16: the sum below is rounded to fp16 anyway), then add the
+              // earlier chunks' spectra times the later V-form tables: V_c = sum_j S_{c-j} H_j; the loads of product j + 1
+              // fly while product j is accumulated
+              if (cc < NC - 1) {
+#pragma unroll
+                for (int v = 0; v < 4; ++v)
+                  park[(size_t)cc * 4096 + slot + (size_t)v * 256] =
+                      make_uint4(pack_f16(__uint_as_float(xr[4 * v]), __uint_as_float(xr[4 * v + 1])),
+                                 pack_f16(__uint_as_float(xi[4 * v]), __uint_as_float(xi[4 * v + 1])),
+                                 pack_f16(__uint_as_float(xr[4 * v + 2]), __uint_as_float(xr[4 * v + 3])),
+                                 pack_f16(__uint_as_float(xi[4 * v + 2]), __uint_as_float(xi[4 * v + 3])));
+              }
+              if (cc > 0) {
+#pragma unroll 1
+                for (int j = 1; j <= cc; ++j) {
+                  if (j > 1) {   // (product 1 was requested at the top of the run)
+                    const uint4* gj = g_ptr(it, h, j) + (4 * uu) * 32;
+#pragma unroll
+                    for (int v = 0; v < 4; ++v) {
+                      gq[v] = __ldg(gj + v * 32);
+                      sq[v] = park[(size_t)(cc - j) * 4096 + slot + (size_t)v * 256];
+                    }
+                  }
+                  const float relj = __ldg(p.rel + j * p.D + ch_of(u_item(it)));   // 2^(e_0 - e_j): table j -> table 0's scale
+                  const f2t REL = f2_pack(relj, relj);
+#pragma unroll
+                  for (int v = 0; v < 4; ++v) {
+                    const uint32_t gw[4] = {gq[v].x, gq[v].y, gq[v].z, gq[v].w};
+                    const uint32_t sw[4] = {sq[v].x, sq[v].y, sq[v].z, sq[v].w};
+#pragma unroll
+                    for (int hp = 0; hp < 2; ++hp) {
+                      const int m = 2 * v + hp;   // elements 2 m, 2 m + 1
+                      const f2t GR = f2_mul(h2_to_f2(gw[2 * hp]), REL), GI = f2_mul(h2_to_f2(gw[2 * hp + 1]), REL);
+                      const f2t XR = h2_to_f2(sw[2 * hp]), XI = h2_to_f2(sw[2 * hp + 1]);
+                      ar[m] = f2_sub(f2_fma(XR, GR, ar[m]), f2_mul(XI, GI));
+                      ai[m] = f2_fma(XI, GR, f2_fma(XR, GI, ai[m]));
+                    }
+                  }
+                }
+              }
+            }
+#pragma unroll
+            for (int m = 0; m < 8; ++m) {
+              w[m] = f2_to_h2(ar[m]);
+              w[8 + m] = f2_to_h2(ai[m]);
             }
             tmem_st8(t_re + col, w);
             tmem_st8(t_re + col + 8, w + 8);
@@ -494,8 +640,16 @@ longconv_tc2_kernel(const __grid_constant__ CUtensorMap tmVX, const __grid_const
           ptx::tc_fence_before_sync();
           __syncwarp();
           ptx::mbar_arrive_lane0(&p2_full[2 * type + h], lane);
+          if constexpr (CH) {
+            if (h == 0) {
+              const uint4* g1 = g_ptr(it, 1);
 #pragma unroll
-          for (int v = 0; v < 8; ++v) g[v] = g2[v];
+              for (int v = 0; v < 8; ++v) g[v] = __ldg(g1 + v * 32);
+            }
+          } else {
+#pragma unroll
+            for (int v = 0; v < 8; ++v) g[v] = g2[v];
+          }
         }
       } else if (phase == 3) {
         // ------------------------------------------------ E3: BT = fp16(conj(tw) .* B), shared memory
@@ -574,7 +728,8 @@ longconv_tc2_kernel(const __grid_constant__ CUtensorMap tmVX, const __grid_const
         // ------------------------------------------------ E4: out = z' * x0, in place over the gate tile, TMA store
         const int buf = it % NZ;
         uint8_t* zb = smem + OFF2_Z + buf * Z_BYTES;
-        const float osc = __ldg(p.osc + ch_of(it));   // output scale of this channel (exact power of two)
+        // output scale of this channel (exact power of two; P4: times 2^(e - e4), the 4096-tap table has its own exponent)
+        const float osc = P4 ? __ldg(p.osc + ch_of(it)) * __ldg(p.osc_adj + ch_of(it)) : __ldg(p.osc + ch_of(u_item(it)));
         const uint32_t t_z = (type ? U2 : U0) + lane_addr + 32 * hf;
         if (type == 1 && it + 1 < n) {   // E4 of a B-type item: the next phase is E2 of item it + 1
           const uint4* g0 = g_ptr(it + 1, 0);
@@ -601,6 +756,12 @@ longconv_tc2_kernel(const __grid_constant__ CUtensorMap tmVX, const __grid_const
         // One output per thread is enough for the range check: an overflow in P1 / P2 reaches every output of the item, one
         // in BT reaches every output of its row n2 - and a row is a thread here.
         const float chk = fmaf(__uint_as_float(zr[0][0]), 0.f, __uint_as_float(zi[0][0]) * 0.f);
+        if constexpr (CH) {   // first-row outputs (n1 = 0, n2 = r < 8) before the gate: F_m of the tail recurrence
+          if (nt > 0 && hf == 0 && r < 8) {
+            tailF[(buf * 2 + 0) * 8 + r] = __uint_as_float(zr[0][0]) * osc;
+            tailF[(buf * 2 + 1) * 8 + r] = __uint_as_float(zi[0][0]) * osc;
+          }
+        }
         // two n1 rows per packed multiply; bf16 -> fp32 of the gate by byte permute (ALU pipe: the FMA pipe is the busy one)
         const f2t OSC = f2_pack(osc, osc);
         auto gate2 = [&](const unsigned short* g) {

@@ -11,7 +11,7 @@ python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/${TAG}_bench_
 python bench.py --steps 2 --warmup 1 $K2ONLY > gpurun_out/${TAG}_bench_short.json 2>> gpurun_out/${TAG}_bench.err || exit 1
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/${TAG}_launches.csv \
     python bench.py --steps 2 --warmup 1 $K2ONLY > gpurun_out/${TAG}_ncu_launches.log 2>&1
-for k in block_mlp_kernel longconv_tc_kernel block_in_kernel score_pool_kernel; do
+for k in block_mlp_kernel longconv_tc2_kernel block_in_kernel score_pool_kernel; do
   ncu --set full --clock-control none --import-source on -k regex:$k --launch-skip 6 -c 1 -f -o gpurun_out/${TAG}_$k \
       python bench.py --steps 2 --warmup 1 $K2ONLY > gpurun_out/${TAG}_ncu_$k.log 2>&1
 done

@@ -12,7 +12,7 @@ from chimeralm_b200.weights import make_state_dict  # noqa: E402
 BUDGET = 32 * 8193
 eng = Engine(make_state_dict(0), device=0, max_batch=256, max_tokens=32769, token_budget=BUDGET)
 print(f"{'T':>6s} {'B':>4s} {'conv kernel':>16s} {'ms/batch':>9s} {'Mtok/s':>8s}   kernel ms per batch")
-for T in (1025, 2049, 3073, 4097, 5121, 6145, 8193, 8201, 12289, 16385, 20481, 24577, 32769):
+for T in (tuple(int(a) for a in sys.argv[1:]) or (1025, 1100, 1537, 2049, 3073, 4096, 4097, 5121, 6145, 8193, 8201, 12289, 16385, 20481, 24577, 32769)):
     B = max(1, min(256, BUDGET // T))
     ids = torch.randint(7, 11, (B, T), dtype=torch.uint8, device="cuda")
     for _ in range(3):

@@ -86,7 +86,9 @@ def test_longconv(engine, state_dict, T):
 
 
 @pytest.mark.parametrize("T,B", [(8192, 2), (8193, 3), (8200, 5), (4097, 2), (5000, 3), (8191, 2), (2057, 3), (3073, 2), (4096, 1),
-                                 (8201, 2), (12000, 3), (16384, 2), (16385, 3), (20000, 2), (24583, 1), (32768, 2), (32769, 3)])
+                                 (8201, 2), (12000, 3), (16384, 2), (16385, 3), (20000, 2), (24583, 1), (32768, 2), (32769, 3),
+                                 # four reads per transform (2 049 .. 4 096 tokens): every B mod 4, odd row counts
+                                 (2049, 1), (2500, 5), (2056, 4), (3500, 8), (3000, 6), (4096, 7), (4000, 10), (2100, 37)])
 def test_longconv_tensor_core(engine, state_dict, T, B):
     """Tensor-core FFT conv (fp16 operands, fp32 accumulate) vs the oracle's fp32 rFFT conv: max error within 1e-2 of
     the output scale (same bar as the fp32 kernels) and relative L2 error <= 2e-3 (bf16 output rounding alone is ~1e-3)."""
@@ -130,6 +132,7 @@ def test_longconv_tensor_core_two_in_flight_matches_one_item_kernel(engine, T, B
     x0[..., :T] = _rand_bf16((B, D, T), g)
     vx, x0 = vx.cuda(), x0.cuda()
     try:
+        engine.set_option("tc_pack4", 0)   # (reads of <= 4 096 tokens would otherwise take the four-reads-per-item form)
         outs = []
         for pipe in (1, 0):
             engine.set_option("tc_pipe", pipe)
@@ -137,10 +140,36 @@ def test_longconv_tensor_core_two_in_flight_matches_one_item_kernel(engine, T, B
         torch.cuda.synchronize()
     finally:
         engine.set_option("tc_pipe", 1)
+        engine.set_option("tc_pack4", 1)
     d = (outs[0] - outs[1]).abs()
     scale = outs[1].abs().max().item()
     assert torch.equal(outs[0][..., : min(T, 8192)], outs[1][..., : min(T, 8192)]), d.max().item()
     assert d.max().item() <= 1e-2 * max(1.0, scale)
+
+
+@pytest.mark.parametrize("T,B", [(3000, 5), (4096, 4), (2100, 9)])
+def test_longconv_tensor_core_four_reads_per_item_matches_two(engine, T, B):
+    """Reads of 2 057 .. 4 096 tokens: the four-reads-per-item form (filter truncated to 4 096 taps, option tc_pack4=1,
+    default) against the two-reads-per-item form (full 8 192-tap spectrum) - the same convolution up to fp16 rounding of
+    two different spectrum tables."""
+    D = CFG.d_model
+    Tp = (T + 127) // 128 * 128
+    g = torch.Generator().manual_seed(77 + T + B)
+    vx = torch.zeros(B, D, Tp, dtype=torch.float16)
+    x0 = torch.zeros(B, D, Tp, dtype=torch.bfloat16)
+    vx[..., :T] = _rand_bf16((B, D, T), g).to(torch.float16)
+    x0[..., :T] = _rand_bf16((B, D, T), g)
+    vx, x0 = vx.cuda(), x0.cuda()
+    try:
+        outs = []
+        for pack in (1, 0):
+            engine.set_option("tc_pack4", pack)
+            outs.append(engine.longconv_tc(1, vx, x0, T)[..., :T].float().clone())
+        torch.cuda.synchronize()
+    finally:
+        engine.set_option("tc_pack4", 1)
+    rel = ((outs[0] - outs[1]).norm() / outs[1].norm()).item()
+    assert rel <= 3e-3, rel   # two bf16 roundings of nearly equal values
 
 
 def _range_case(name, B, D, T, g):
