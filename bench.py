@@ -663,11 +663,11 @@ def main():
     roof["traffic_source"] = traffic_src
     rooflines = {k: roofline_of(k, v[0], v[1]) for k, v in prof.items() if k in ("longconv", "block_mlp", "block_in", "gemm_score")}
     if "longconv" in rooflines and conv_variant == "fft_tensor_core":
-        # Monarch FFT on tcgen05 (csrc/longconv_tc.cuh): per item (one channel of two reads) 16 MMAs 128x128x16 + 2 x 16 MMAs
-        # 128x256x16 + 32 MMAs 128xN7x16 (N7 = 80 when T > 8192, else 64); 256 * ceil(B / 2) items per launch.  These are
-        # EXECUTED fp16 tensor FLOPs (22x the algorithmic FFT count): a pipe-utilisation figure, not a roofline fraction.
-        n7 = 80 if T > 8192 else 64
-        item_flop = 2 * 16 * (16 * 128 * 128 + 2 * 16 * 128 * 256 + 32 * 128 * n7)
+        # Monarch FFT on tcgen05 (csrc/longconv_tc2.cuh, two items in flight per SM): per item (one channel of two reads) 16
+        # MMAs 128x128x16 (step 1) + 2 x 32 MMAs 128x128x16 (steps 3, 5 as N = 128 halves) + 32 MMAs 128x64x16 (step 7; the
+        # tail token's row no longer costs an output row); 256 * ceil(B / 2) items per launch.  These are EXECUTED fp16
+        # tensor FLOPs (22x the algorithmic FFT count): a pipe-utilisation figure, not a roofline fraction.
+        item_flop = 2 * 16 * (16 * 128 * 128 + 2 * 32 * 128 * 128 + 32 * 128 * 64)
         sec = rooflines["longconv"]["avg_launch_ms"] / 1e3
         rooflines["longconv"]["tensor_pipe_executed_tflops"] = item_flop * 256 * ((B + 1) // 2) / sec / 1e12
     dense_tflops = F_TOK * (reads_per_s / world) * T / 1e12

@@ -54,6 +54,7 @@ struct BlockMlpParams {
   // pooling consume the normalised xn rows) - 128 KB of stores per tile less on the SM's ~30 B/clk store path
   int skip_res_store;
   int stagger_cycles;    // CTA b starts (b % 4) * stagger_cycles late (0 = off)
+  int helpers_high;      // 1: the helper warps (producer, MMA issuer) take the highest warp ids, the epilogue warps 0..7
   long long* trace;      // optional [3][64] clock64 stamps written by CTA 0 (null in production)
 };
 
@@ -150,7 +151,11 @@ block_mlp_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 20);
   float (*s_part)[2][BM] = reinterpret_cast<float (*)[2][BM]>(smem + OFF_PART);  // [half][sum|sumsq][row]
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // `warp` is the ROLE index (0 producer, 1 MMA issuer, 2-3 idle, 4..11 epilogue).  With helpers_high the roles 0..3 sit on the
+  // physical warps 8..11: the warp scheduler favours higher warp ids, and the MMA issuer shares its scheduler with two
+  // epilogue warps.  The TMEM lane quarter (physical warp % 4) is the same either way.
+  const int pwarp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = p.helpers_high ? (pwarp + 4) % 12 : pwarp;
   // Each CTA walks the 8 fc1/fc2 hidden chunks starting at a different one, so the 148 CTAs do
   // not all pull the same weight tile out of L2 at the same moment.
   const int rot = blockIdx.x & (NCHUNK - 1);
@@ -478,7 +483,7 @@ block_mlp_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
       }
       s_part[hf][0][r] = s1;
       s_part[hf][1][r] = s2;
-      if (threadIdx.x == EPI_TID0) ptx::tma_store_wait_read<0>();   // previous tile's xn store has finished reading HB
+      if (warp == EPI_WARP0 && lane == 0) ptx::tma_store_wait_read<0>();   // previous tile's xn store has finished reading HB
       ptx::bar_sync(1, EPI_THREADS);
       const float ts1 = s_part[0][0][r] + s_part[1][0][r];
       const float ts2 = s_part[0][1][r] + s_part[1][1][r];
@@ -633,7 +638,7 @@ block_mlp_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
       if (lane == 0) ptx::mbar_arrive(r_free);
       if (p.write_xn) {
         ptx::bar_sync(1, EPI_THREADS);
-        if (threadIdx.x == EPI_TID0) {
+        if (warp == EPI_WARP0 && lane == 0) {
           int xb, xt0;
           if (p.y_cm) { xb = tile / p.tiles_per_seq; xt0 = (tile % p.tiles_per_seq) * BM; }
           else { xb = 0; xt0 = tile * BM; }
@@ -644,7 +649,7 @@ block_mlp_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
       }
       if (tr) stamp(2);
     }
-    if (threadIdx.x == EPI_TID0) ptx::tma_store_wait<0>();
+    if (warp == EPI_WARP0 && lane == 0) ptx::tma_store_wait<0>();
   }
   ptx::tc_fence_before_sync();
   __syncthreads();

@@ -187,7 +187,9 @@ int clm_longconv_tc_auto(clm_ctx* ctx, int layer, const void* d_vx_bf16, const v
 /* Which long-convolution kernel clm_forward uses for reads of T tokens: 0 = first fp32 FFT kernel, 1 = tuned fp32
  * FFT kernel, 2 = tensor-core FFT kernel; -1 before clm_finalize. */
 int clm_longconv_variant(const clm_ctx* ctx, int T);
-/* Same, and CTA 0 writes clock64() stamps into d_trace[2][64] (row 0 MMA issuer, row 1 epilogue warp). */
+/* Same, and CTA 0 writes clock64() stamps into d_trace (int64, zero-filled by the caller): the two-items-in-flight kernel
+ * (default) fills [9][64] - row 0 the MMA issuer (start / barrier passed / end per slot), rows 1..8 the epilogue warps; the
+ * one-item kernels (options tc_pipe=0, tc_pipe_chunked=0) fill [2][64]. */
 int clm_longconv_tc_trace(clm_ctx* ctx, int layer, const void* d_vx_f16, const void* d_x0, void* d_out, int B, int T,
                           int Tp, long long* d_trace, void* stream);
 int clm_get_filter(clm_ctx* ctx, int layer, float* d_out, int L, void* stream);

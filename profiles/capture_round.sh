@@ -28,5 +28,5 @@ for _ in range(3):
     eng.forward(ids)
 torch.cuda.synchronize()
 PY
-python gpurun_out/_long_fwd.py && ncu --set full --clock-control none --import-source on -k regex:longconv_tc_kernel --launch-skip 5 -c 1 -f \
+python gpurun_out/_long_fwd.py && ncu --set full --clock-control none --import-source on -k regex:longconv_tc2_kernel --launch-skip 5 -c 1 -f \
     -o gpurun_out/${TAG}_longconv_tc_chunked python gpurun_out/_long_fwd.py > gpurun_out/${TAG}_ncu_longconv_tc_chunked.log 2>&1

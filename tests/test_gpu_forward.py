@@ -280,6 +280,8 @@ def test_full_size_batch_permutation_invariance(state_dict):
 
 
 @pytest.mark.parametrize("option,T", [("fused_score_pool", 1500), ("fused_head", 1500), ("tc_conv", 8193), ("tc_chunked", 9000),
+                                      ("tc_pipe", 8193), ("tc_pack4", 3000), ("tc_pipe_chunked", 16385), ("tc_pipe_chunked", 20000),
+                                      ("mlp_helpers_high", 700),
                                       ("fused_mlp", 700), ("fused_in", 700), ("fast_conv", 700), ("mlp_epi16", 1500), ("mlp_pp", 8193), ("mlp_early_res", 8193), ("mlp_fc2_lag", 8193),
                                       ("skip_dead_res", 700), ("in_2cta", 700), ("in_2cta", 8193)])
 def test_kernel_variants_agree(state_dict, option, T):
@@ -294,7 +296,7 @@ def test_kernel_variants_agree(state_dict, option, T):
     try:
         ids = _ids(B, T, seed=T, pad_left=T // 4).to(torch.uint8).cuda()
         base = eng.forward(ids).clone()
-        default_on = option not in ("mlp_epi16", "mlp_pp", "in_2cta")
+        default_on = option not in ("mlp_epi16", "mlp_pp", "in_2cta", "mlp_helpers_high")
         try:
             eng.set_option(option, {"mlp_fc2_lag": 2}.get(option, 0 if default_on else 1))
         except ChimeraLMNativeError as e:
