@@ -541,6 +541,15 @@ longconv_tc2_kernel(const __grid_constant__ CUtensorMap tmVX, const __grid_const
         ptx::tc_fence_after_sync();
         if constexpr (TR) { if (tr) stamp(1 + warp - EPI2_W0); }
         const int cc = u_chunk(it);
+        // table scale factors of the later filter segments (chunked form), fetched once per phase: a load inside the segment
+        // loop put an L2 round trip in front of every product
+        float rel1 = 1.f, rel2 = 1.f, rel3 = 1.f;
+        if constexpr (CH) {
+          const float* relp = p.rel + ch_of(u_item(it));
+          if (cc >= 1) rel1 = __ldg(relp + p.D);
+          if (cc >= 2) rel2 = __ldg(relp + 2 * p.D);
+          if (cc >= 3) rel3 = __ldg(relp + 3 * p.D);
+        }
 #pragma unroll 1
         for (int h = 0; h < 2; ++h) {
           uint32_t xr2[2][16], xi2[2][16];
@@ -610,7 +619,7 @@ longconv_tc2_kernel(const __grid_constant__ CUtensorMap tmVX, const __grid_const
                       sq[v] = park[(size_t)(cc - j) * 4096 + slot + (size_t)v * 256];
                     }
                   }
-                  const float relj = __ldg(p.rel + j * p.D + ch_of(u_item(it)));   // 2^(e_0 - e_j): table j -> table 0's scale
+                  const float relj = j == 1 ? rel1 : (j == 2 ? rel2 : rel3);   // 2^(e_0 - e_j): table j -> table 0's scale
                   const f2t REL = f2_pack(relj, relj);
 #pragma unroll
                   for (int v = 0; v < 4; ++v) {
