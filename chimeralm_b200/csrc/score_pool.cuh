@@ -116,6 +116,13 @@ score_pool_kernel(const __grid_constant__ CUtensorMap tmXN, const __grid_constan
         ptx::mbar_wait(a_empty, (it & 1) ^ 1);
         ptx::mbar_expect_tx(a_full, 4 * A_KB);
         for (int kb = 0; kb < 4; ++kb) ptx::tma_load_3d(smem + OFF_A + kb * A_KB, &tmXN, a_full, kb * BK, t0, b);   // rows >= T: zeros
+        // the tile buffer is single (the resident weights take the rest of shared memory), so the next tile's load can only be
+        // issued once this one has been pooled: have it wait in L2 by then
+        const int nxt = tile + gridDim.x;
+        if (nxt < p.num_tiles) {
+          const int nb = nxt / p.tiles_per_seq, nt0 = (nxt % p.tiles_per_seq) * BM;
+          for (int kb = 0; kb < 4; ++kb) ptx::tma_prefetch_3d(&tmXN, kb * BK, nt0, nb);
+        }
       }
     }
   } else if (warp == 1) {
