@@ -184,6 +184,7 @@ struct clm_ctx {
   bool mlp_2cta = false;  // CTA-pair (cta_group::2) version of the fused block tail
   bool mlp_epi16 = false; // fused block tail with 16 epilogue warps (block_mlp16.cuh)
   int mlp_helpers_high = 0;
+  int in_prefetch = 0;    // block_in: next token tile prefetched into L2 (measured: no effect, 0.667 vs 0.665 ms/step interleaved)
   int mlp_early_res = 33; // block_mlp: float4 of the next tile's residual half-row loaded before E3 (0, 16, 32; 33 = spread over E3)
   int mlp_fc2_lag = 1;    // block_mlp: fc2 of chunk j - lag is issued after fc1 of chunk j (2: recorded experiment, no faster)
   int mlp_grid = 0;       // block_mlp: cap on the number of CTAs (0 = one per SM); diagnostic
@@ -436,6 +437,7 @@ int launch_block_in(clm_ctx* c, int layer, const __nv_bfloat16* xn, int B, int T
   p.b_in = L.in_bf; p.cw = L.sc_w; p.cb = L.sc_b;
   p.B = B; p.T = T; p.trace = trace; p.vx_f16 = vx_f16 ? 1 : 0;
   p.vx_scale = vx_f16 ? L.vx_scale : nullptr;   // fp16 rows carry a[ch] * v*x1 (undone by the conv's output scale)
+  p.prefetch_xn = c->in_prefetch;
   p.tiles_per_seq = (T + bi::BT - 1) / bi::BT;
   p.num_tiles = B * p.tiles_per_seq;
 #ifdef CLM_EXPERIMENTS
@@ -1612,6 +1614,7 @@ int clm_set_option(clm_ctx* c, const char* name, int value) {
   else if (n == "mlp_fc2_lag") c->mlp_fc2_lag = value;
   else if (n == "mlp_early_res") c->mlp_early_res = value;
   else if (n == "mlp_helpers_high") c->mlp_helpers_high = value;
+  else if (n == "in_prefetch") c->in_prefetch = value;
   else return fail(c, CLM_ERR_INVALID, "clm_set_option: unknown option '%s'", name);
   return 0;
 }

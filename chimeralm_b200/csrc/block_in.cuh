@@ -46,6 +46,7 @@ struct BlockInParams {
   const float* vx_scale;  // [256] power-of-two factor a[ch] on v * x1 when vx_f16 (nullptr = 1): keeps the fp16 rows and every
                           // fp16 intermediate of the tensor-core FFT in range for weights of any magnitude (longconv_tc.cuh)
   long long* trace;     // optional [2][64] clock64 stamps of CTA 0 (row 0 = MMA issuer, row 1 = epilogue warp 2)
+  int prefetch_xn;      // 1: the producer prefetches the next token tile into L2 (option in_prefetch)
 };
 
 namespace bi {
@@ -120,6 +121,16 @@ block_in_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
           ptx::mbar_wait(xn_free, (it & 1) ^ 1);
           ptx::mbar_expect_tx(xn_full, XN_BYTES);
           for (int kb = 0; kb < 4; ++kb) ptx::tma_load_3d(smem + OFF_XN + kb * KB_ROWS_BYTES, &tmXN, xn_full, kb * 64, t0 - HALO, b);
+          // The token tile is single-buffered (72 KB next to the weight ring), so this load is issued only when the previous
+          // tile's MMAs are done and its 3.5-4 K cycles were fully exposed (profiles/r2_trace_block_in.txt) - most of it HBM
+          // time for activations the previous kernel wrote.  Ask for the NEXT tile now: by the time it is loaded it sits in L2.
+          if (p.prefetch_xn) {
+            const int nxt = tile + gridDim.x;
+            if (nxt < p.num_tiles) {
+              const int nb = nxt / p.tiles_per_seq, nt0 = (nxt % p.tiles_per_seq) * BT;
+              for (int kb = 0; kb < 4; ++kb) ptx::tma_prefetch_3d(&tmXN, kb * 64, nt0 - HALO, nb);
+            }
+          }
         }
         for (int h = 0; h < 2; ++h)
           for (int g = 0; g < 3; ++g)
