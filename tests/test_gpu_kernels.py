@@ -190,15 +190,15 @@ def _range_case(name, B, D, T, g):
     return x.to(torch.bfloat16)
 
 
-@pytest.mark.parametrize("T", [8193, 20000, 32769])
+@pytest.mark.parametrize("T,B", [(8193, 2), (20000, 2), (32769, 2), (3000, 5)])   # plain, chunked (V-form tables), four reads per item
 @pytest.mark.parametrize("case", ["large", "dc", "tiny", "mixed", "pad_prefix"])
-def test_longconv_tensor_core_dynamic_range(engine, state_dict, case, T):
+def test_longconv_tensor_core_dynamic_range(engine, state_dict, case, T, B):
     """The fp16 tensor-core convolution with per-channel power-of-two input scaling (from the data here, from the
     calibration draw in the forward) and per-(segment, channel) spectrum scaling, against the oracle's fp32 rFFT
     convolution, per channel: relative L2 error <= 3e-3 for every channel (bf16 output rounding alone is ~1.5e-3)."""
     from oracle import hyena_oracle as O
 
-    B, D = 2, CFG.d_model
+    D = CFG.d_model
     Tp = (T + 127) // 128 * 128
     g = torch.Generator().manual_seed(T + len(case))
     vx = torch.zeros(B, D, Tp, dtype=torch.bfloat16)
