@@ -170,6 +170,7 @@ struct clm_ctx {
   int mlp_stagger = 0;    // block_mlp: CTA phase stagger in cycles (0 = off)
   bool tc_conv = true;    // tensor-core FFT long convolution for reads of more than 2 056 tokens (needs fused_in)
   bool tc_pipe = true;    // single-transform reads (<= 8 200 tokens): two items in flight per SM (longconv_tc2_kernel)
+  int tc_helpers_low = 0; // longconv_tc2: helper warps on the lowest warp ids (A/B switch)
   bool tc_pack4 = true;   // reads of 2 049 .. 4 096 tokens: four reads per transform (needs tc_pipe)
   bool tc_pipe_chunked = true;   // reads longer than 8 200 tokens on the two-in-flight kernel (V-form tables, no carry)
   __half* tc_S = nullptr; // shared-memory image of the DFT constant stack (longconv_tc)
@@ -769,6 +770,7 @@ int launch_longconv_tc(clm_ctx* c, int layer, const __half* vx, const __nv_bfloa
   p.x0 = x0; p.out = out; p.S = reinterpret_cast<const uint4*>(c->tc_S); p.G = reinterpret_cast<const uint4*>(L.gtc);
   p.B = B; p.D = D; p.Tp = Tp; p.n_pairs = pack4 ? (B + 3) / 4 : (B + 1) / 2; p.n_items = D * p.n_pairs; p.trace = trace;
   if (pack4) { p.G = reinterpret_cast<const uint4*>(L.gtc4); p.osc_adj = L.tc_adj4; }
+  p.helpers_low = c->tc_helpers_low;
   // chunked reads on the two-in-flight kernel: V-form tables (H_0 = G_0, so the output scale is unchanged)
   const bool pipe_ch = pl.nc > 1 && c->tc_pipe && c->tc_pipe_chunked && L.gtcH != nullptr;
   p.n_chunks = pl.nc; p.nt = pl.nt; p.scratch = c->tc_scratch; p.scratch_per_cta = (long long)tc_scratch_per_cta(pl.nc);
@@ -1594,6 +1596,7 @@ int clm_set_option(clm_ctx* c, const char* name, int value) {
   else if (n == "tc_chunked") c->tc_chunked = value != 0;
   else if (n == "tc_pipe") c->tc_pipe = value != 0;
   else if (n == "tc_pack4") c->tc_pack4 = value != 0;
+  else if (n == "tc_helpers_low") c->tc_helpers_low = value;
   else if (n == "tc_pipe_chunked") c->tc_pipe_chunked = value != 0;
   else if (n == "fused_score_pool") c->fused_score_pool = value != 0;
   else if (n == "fused_head") c->fused_head = value != 0;

@@ -64,6 +64,7 @@ struct LongConvTcParams {
   const float* osc;          // [D]
   const float* inva;         // [D]
   const float* rel;          // [n_seg][D]
+  int helpers_low;           // longconv_tc2_kernel, A/B switch: 1 = helper warps on the LOWEST warp ids (default 0: highest)
   const float* osc_adj;      // [D] four-reads-per-item form only: 2^(e[0][ch] - e4[ch]), e4 = exponent of the 4096-tap table
   int* err;                  // status word: bit 1 (value 2) is set when an output is not finite (fp16 range exceeded)
   long long* trace;          // optional [2][64] clock64 stamps of CTA 0: row 0 = MMA issuer, row 1 = epilogue warp 2

@@ -87,7 +87,9 @@ longconv_tc2_kernel(const __grid_constant__ CUtensorMap tmVX, const __grid_const
   uint64_t* bt_read = bars + 31;     // [type] the tail warp has finished reading BT
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 40);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // `warp` is the ROLE index (0..7 epilogue, 8..11 helpers); the TMEM lane quarter (physical warp % 4) equals role % 4 either way
+  const int pwarp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = p.helpers_low ? (pwarp + 8) % 12 : pwarp;
   const int per = (p.n_items + gridDim.x - 1) / gridDim.x;
   const int item0 = blockIdx.x * per, item1 = min(p.n_items, item0 + per);
   const int NC = CH ? p.n_chunks : 1;
@@ -436,10 +438,10 @@ longconv_tc2_kernel(const __grid_constant__ CUtensorMap tmVX, const __grid_const
     // tid_e at ((h * 2 + uu) * 4 + v) * 256 + tid_e (fp16 pairs in the spectrum-table layout)
     uint4* park = reinterpret_cast<uint4*>(p.scratch + (long long)blockIdx.x * p.scratch_per_cta);
     const int tid_e = (warp - EPI2_W0) * 32 + lane;
-    uint4 gpre[8];
+    uint4 g[8];        // table lines of the index half E2 works on next (lives across the phases: fetched one phase ahead)
     int gpre_it = -1;
 #pragma unroll
-    for (int v = 0; v < 8; ++v) gpre[v] = make_uint4(0u, 0u, 0u, 0u);
+    for (int v = 0; v < 8; ++v) g[v] = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll 1
     for (int s = 0; s < n_slots; ++s) {
       const int j = s & 7, k2x = (s >> 3) * 2;
@@ -522,7 +524,7 @@ longconv_tc2_kernel(const __grid_constant__ CUtensorMap tmVX, const __grid_const
       } else if (phase == 2) {
         // ------------------------------------------------ E2: P2 = fp16(S .* G'), packed in place over S_re (U1)
         const uint32_t t_re = U1 + lane_addr, t_im = U3 + lane_addr;
-        uint4 g[8], g2[8];
+        uint4 g2[8];
         {
           if constexpr (!CH) {   // (chunked form: the second half's table lines are fetched between the halves - registers)
             const uint4* g1 = g_ptr(it, 1);
@@ -532,10 +534,8 @@ longconv_tc2_kernel(const __grid_constant__ CUtensorMap tmVX, const __grid_const
           if (gpre_it != it) {   // first item of the CTA: nothing ran before this E2
             const uint4* g0 = g_ptr(it, 0);
 #pragma unroll
-            for (int v = 0; v < 8; ++v) gpre[v] = __ldg(g0 + v * 32);
+            for (int v = 0; v < 8; ++v) g[v] = __ldg(g0 + v * 32);
           }
-#pragma unroll
-          for (int v = 0; v < 8; ++v) g[v] = gpre[v];
         }
         ptx::mbar_wait(&y_full[type], ph);
         ptx::tc_fence_after_sync();
@@ -666,7 +666,7 @@ longconv_tc2_kernel(const __grid_constant__ CUtensorMap tmVX, const __grid_const
         if (type == 0 && it + 1 < n) {   // E3 of an A-type item: the next phase is E2 of its partner, item it + 1
           const uint4* g0 = g_ptr(it + 1, 0);
 #pragma unroll
-          for (int v = 0; v < 8; ++v) gpre[v] = __ldg(g0 + v * 32);
+          for (int v = 0; v < 8; ++v) g[v] = __ldg(g0 + v * 32);
           gpre_it = it + 1;
         }
         ptx::mbar_wait(&x2_full[type], ph);
@@ -743,7 +743,7 @@ longconv_tc2_kernel(const __grid_constant__ CUtensorMap tmVX, const __grid_const
         if (type == 1 && it + 1 < n) {   // E4 of a B-type item: the next phase is E2 of item it + 1
           const uint4* g0 = g_ptr(it + 1, 0);
 #pragma unroll
-          for (int v = 0; v < 8; ++v) gpre[v] = __ldg(g0 + v * 32);
+          for (int v = 0; v < 8; ++v) g[v] = __ldg(g0 + v * 32);
           gpre_it = it + 1;
         }
         ptx::mbar_wait(&o_full[type], ph);
