@@ -3,10 +3,14 @@
 //   score[t] = w2 . gelu_erf(W0' xn[t] + b0') + b2            (BinarySequenceClassifier attention branch,
 //   per 128-token tile: m = max score, p[t] = exp(score[t] - m),       components/hyena.py:79-95,117-132; ln_f's affine is
 //   l = sum p, v[c] = sum_t p[t] xn[t][c]                               folded into W0', b0' and applied to v at the end)
-// The scorer weights (128 KB bf16) stay resident in shared memory; each token tile is read ONCE from HBM (the unfused
-// pair streamed the weights from L2 for every tile and read the tokens twice), the tcgen05 accumulator is drained by
+// Each token tile is read ONCE from HBM (the unfused pair read the tokens twice), the tcgen05 accumulator is drained by
 // 8 epilogue warps (the exact-erf GELU is the expensive part) and the softmax-weighted sum is taken from the same
 // shared-memory tile the MMA consumed.  pool_merge_kernel combines the per-tile partials of a read.
+// Pipelining (round 2): the first version kept the scorer weights (128 KB) resident, which left room for ONE token tile, so
+// load -> MMA -> GELU -> softmax -> pooling of a tile ran strictly in series (17 K cycles per tile, 16 % of the HBM roofline).
+// Now the weights stream through a two-slot ring (32 KB k-blocks, L2 hits: 128 KB per tile and SM), the token tile and the
+// accumulator are double-buffered (2 x 64 KB, 2 x 256 TMEM columns), and tile i + 1 is loaded and multiplied while the
+// epilogue warps score and pool tile i.
 #pragma once
 #include <cuda_bf16.h>
 
@@ -35,9 +39,11 @@ namespace sp {
 constexpr int D = 256, BM = 128, BK = 64;
 constexpr int W_KB = D * BK * 2;            // 32 KB: [256 n x 64 k]
 constexpr int A_KB = BM * BK * 2;           // 16 KB: [128 tokens x 64 k]
+constexpr int NW = 2;                       // weight ring slots (one 64-wide k-block of all 256 outputs each)
+constexpr int A_TILE = 4 * A_KB;            // 64 KB
 constexpr int OFF_W = 0;
-constexpr int OFF_A = OFF_W + 4 * W_KB;     // 131072
-constexpr int OFF_BAR = OFF_A + 4 * A_KB;   // 196608
+constexpr int OFF_A = OFF_W + NW * W_KB;    // 65536; two tile buffers
+constexpr int OFF_BAR = OFF_A + 2 * A_TILE; // 196608
 constexpr int OFF_F = OFF_BAR + 128;        // s_part[2][128], p[128], red[16]
 constexpr int OFF_C = OFF_F + (2 * 128 + 128 + 16) * 4;   // b0[256], w2[256]: with ~200 KB of shared memory carved out the L1 is a
 constexpr int SMEM_TOTAL = OFF_C + 512 * 4;               // few KB and warp-uniform __ldg loads go to L2 every time
@@ -81,12 +87,13 @@ score_pool_kernel(const __grid_constant__ CUtensorMap tmXN, const __grid_constan
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((ptx::smem_u32(smem) & 1023u) != 0) __trap();
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
-  uint64_t* w_full = bars;        // scorer weights landed (once)
-  uint64_t* a_full = bars + 1;    // token tile landed
-  uint64_t* a_empty = bars + 2;   // pooling finished reading the tile (8 warp arrivals)
-  uint64_t* acc_full = bars + 3;  // accumulator complete
-  uint64_t* acc_free = bars + 4;  // accumulator drained (8 warp arrivals)
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 6);
+  uint64_t* w_full = bars;        // [NW] weight k-block landed
+  uint64_t* w_empty = bars + 2;   // [NW] its MMAs are done
+  uint64_t* a_full = bars + 4;    // [2] token tile landed
+  uint64_t* a_empty = bars + 6;   // [2] pooling finished reading the tile (8 warp arrivals)
+  uint64_t* acc_full = bars + 8;  // [2] accumulator complete
+  uint64_t* acc_free = bars + 10; // [2] accumulator drained (8 warp arrivals)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 12);
   float* s_part = reinterpret_cast<float*>(smem + OFF_F);   // [2][128]
   float* s_p = s_part + 256;                                // [128]
   float* s_c = reinterpret_cast<float*>(smem + OFF_C);      // b0 | w2
@@ -95,11 +102,14 @@ score_pool_kernel(const __grid_constant__ CUtensorMap tmXN, const __grid_constan
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmXN); ptx::prefetch_tmap(&tmW);
-    ptx::mbar_init(w_full, 1); ptx::mbar_init(a_full, 1); ptx::mbar_init(a_empty, 8);
-    ptx::mbar_init(acc_full, 1); ptx::mbar_init(acc_free, 8);
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&w_full[i], 1); ptx::mbar_init(&w_empty[i], 1);
+      ptx::mbar_init(&a_full[i], 1); ptx::mbar_init(&a_empty[i], 8);
+      ptx::mbar_init(&acc_full[i], 1); ptx::mbar_init(&acc_free[i], 8);
+    }
     ptx::fence_mbar_init();
   } else if (warp == 1) {
-    ptx::tmem_alloc<256>(tmem_ptr);
+    ptx::tmem_alloc<512>(tmem_ptr);
   }
   ptx::tc_fence_before_sync();
   __syncthreads();
@@ -108,20 +118,19 @@ score_pool_kernel(const __grid_constant__ CUtensorMap tmXN, const __grid_constan
 
   if (warp == 0) {
     if (lane == 0) {
-      ptx::mbar_expect_tx(w_full, 4 * W_KB);
-      for (int kb = 0; kb < 4; ++kb) ptx::tma_load_2d(smem + OFF_W + kb * W_KB, &tmW, w_full, kb * BK, 0);
-      uint32_t it = 0;
+      uint32_t it = 0, wi = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
         const int b = tile / p.tiles_per_seq, t0 = (tile % p.tiles_per_seq) * BM;
-        ptx::mbar_wait(a_empty, (it & 1) ^ 1);
-        ptx::mbar_expect_tx(a_full, 4 * A_KB);
-        for (int kb = 0; kb < 4; ++kb) ptx::tma_load_3d(smem + OFF_A + kb * A_KB, &tmXN, a_full, kb * BK, t0, b);   // rows >= T: zeros
-        // the tile buffer is single (the resident weights take the rest of shared memory), so the next tile's load can only be
-        // issued once this one has been pooled: have it wait in L2 by then
-        const int nxt = tile + gridDim.x;
-        if (nxt < p.num_tiles) {
-          const int nb = nxt / p.tiles_per_seq, nt0 = (nxt % p.tiles_per_seq) * BM;
-          for (int kb = 0; kb < 4; ++kb) ptx::tma_prefetch_3d(&tmXN, kb * BK, nt0, nb);
+        const uint32_t buf = it & 1;
+        ptx::mbar_wait(&a_empty[buf], ((it >> 1) & 1) ^ 1);
+        ptx::mbar_expect_tx(&a_full[buf], A_TILE);
+        for (int kb = 0; kb < 4; ++kb)   // rows >= T: zeros
+          ptx::tma_load_3d(smem + OFF_A + buf * A_TILE + kb * A_KB, &tmXN, &a_full[buf], kb * BK, t0, b);
+        for (int kb = 0; kb < 4; ++kb, ++wi) {   // the scorer weights again, k-block by k-block (L2 hits)
+          const uint32_t sl = wi % NW;
+          ptx::mbar_wait(&w_empty[sl], ((wi / NW) & 1) ^ 1);
+          ptx::mbar_expect_tx(&w_full[sl], W_KB);
+          ptx::tma_load_2d(smem + OFF_W + sl * W_KB, &tmW, &w_full[sl], kb * BK, 0);
         }
       }
     }
@@ -129,32 +138,37 @@ score_pool_kernel(const __grid_constant__ CUtensorMap tmXN, const __grid_constan
     if (lane == 0) {
       constexpr uint32_t idesc = ptx::idesc_bf16_f32(BM, D);
       const uint32_t sA = ptx::smem_u32(smem + OFF_A), sW = ptx::smem_u32(smem + OFF_W);
-      ptx::mbar_wait(w_full, 0);
-      uint32_t it = 0;
+      uint32_t it = 0, wi = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
-        ptx::mbar_wait(a_full, it & 1);
-        ptx::mbar_wait(acc_free, (it & 1) ^ 1);
+        const uint32_t buf = it & 1, bph = (it >> 1) & 1;
+        ptx::mbar_wait(&a_full[buf], bph);
+        ptx::mbar_wait(&acc_free[buf], bph ^ 1);
         ptx::tc_fence_after_sync();
+        for (int kb = 0; kb < 4; ++kb, ++wi) {
+          const uint32_t sl = wi % NW;
+          ptx::mbar_wait(&w_full[sl], (wi / NW) & 1);
+          ptx::tc_fence_after_sync();
+          const uint64_t da = ptx::smem_desc_k_sw128(sA + buf * A_TILE + kb * A_KB), db = ptx::smem_desc_k_sw128(sW + sl * W_KB);
 #pragma unroll
-        for (int kb = 0; kb < 4; ++kb) {
-          const uint64_t da = ptx::smem_desc_k_sw128(sA + kb * A_KB), db = ptx::smem_desc_k_sw128(sW + kb * W_KB);
-#pragma unroll
-          for (int k = 0; k < 4; ++k) ptx::umma_f16(tmem_base, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+          for (int k = 0; k < 4; ++k) ptx::umma_f16(tmem_base + buf * 256, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+          ptx::umma_commit(&w_empty[sl]);
         }
-        ptx::umma_commit(acc_full);
+        ptx::umma_commit(&acc_full[buf]);
       }
     }
   } else {
     const int e = warp - 2, q = warp & 3, hf = e >> 2;
     const int r = q * 32 + lane;            // token row inside the tile (scores); also used as lane index below
     const int tid = threadIdx.x - 64;       // 0..255: channel for the pooling sum
-    const uint32_t lane_addr = tmem_base + (uint32_t(q * 32) << 16);
+    const uint32_t lane_addr0 = tmem_base + (uint32_t(q * 32) << 16);
     const float gam = __ldg(p.g + tid), bet = __ldg(p.beta + tid);
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
       const int b = tile / p.tiles_per_seq, ts = tile % p.tiles_per_seq, t0 = ts * BM;
       const int valid = min(BM, p.T - t0);
-      ptx::mbar_wait(acc_full, it & 1);
+      const uint32_t buf = it & 1, bph = (it >> 1) & 1;
+      const uint32_t lane_addr = lane_addr0 + buf * 256;
+      ptx::mbar_wait(&acc_full[buf], bph);
       ptx::tc_fence_after_sync();
       // ---- scores: this thread's 128 of the 256 scorer outputs of row r
       f2t sc2 = f2_pack(0.f, 0.f);
@@ -176,7 +190,7 @@ score_pool_kernel(const __grid_constant__ CUtensorMap tmXN, const __grid_constan
       }
       ptx::tc_fence_before_sync();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(acc_free);   // the accumulator may be overwritten by the next tile
+      if (lane == 0) ptx::mbar_arrive(&acc_free[buf]);   // the accumulator may be overwritten by the tile after next
       float sc_lo, sc_hi;
       f2_unpack(sc2, sc_lo, sc_hi);
       s_part[hf * 128 + r] = sc_lo + sc_hi;
@@ -218,7 +232,7 @@ score_pool_kernel(const __grid_constant__ CUtensorMap tmXN, const __grid_constan
       // ---- pooling: v[c] = sum_t p[t] xn[t][c] from the swizzled K-major tile the MMA just consumed
       {
         const int c = tid, kb = c >> 6, cc = c & 63;
-        const uint8_t* base = smem + OFF_A + kb * A_KB + (cc & 7) * 2;
+        const uint8_t* base = smem + OFF_A + buf * A_TILE + kb * A_KB + (cc & 7) * 2;
         const uint32_t chunk = uint32_t(cc >> 3);
         float* out = p.part + ((long long)b * p.tiles_per_seq + ts) * (2 + D);
         if (p.pool_mode == 2) {   // max over the tile's valid positions of ln_f(x)[c] = gamma xn + beta
@@ -243,14 +257,14 @@ score_pool_kernel(const __grid_constant__ CUtensorMap tmXN, const __grid_constan
         }
       }
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(a_empty);   // tile and s_part / s_p may be overwritten
+      if (lane == 0) ptx::mbar_arrive(&a_empty[buf]);   // the tile buffer may be overwritten (s_part / s_p: the epilogue's own)
     }
   }
   ptx::tc_fence_before_sync();
   __syncthreads();
   if (warp == 1) {
     ptx::tc_fence_after_sync();
-    ptx::tmem_dealloc<256>(tmem_base);
+    ptx::tmem_dealloc<512>(tmem_base);
   }
 }
 
