@@ -185,6 +185,7 @@ struct clm_ctx {
   bool mlp_2cta = false;  // CTA-pair (cta_group::2) version of the fused block tail
   bool mlp_epi16 = false; // fused block tail with 16 epilogue warps (block_mlp16.cuh)
   int mlp_helpers_high = 0;
+  int mlp_store_a = 0;    // block_mlp: residual column groups stored in the statistics sweep of the output epilogue
   int in_prefetch = 0;    // block_in: next token tile prefetched into L2 (measured: no effect, 0.667 vs 0.665 ms/step interleaved)
   int mlp_early_res = 33; // block_mlp: float4 of the next tile's residual half-row loaded before E3 (0, 16, 32; 33 = spread over E3)
   int mlp_fc2_lag = 1;    // block_mlp: fc2 of chunk j - lag is issued after fc1 of chunk j (2: recorded experiment, no faster)
@@ -482,6 +483,7 @@ int launch_block_mlp(clm_ctx* c, int layer, const __nv_bfloat16* y, float* res, 
   p.trace = trace;
   p.stagger_cycles = c->mlp_stagger;
   p.helpers_high = c->mlp_helpers_high;
+  p.store_a = c->mlp_store_a;
   p.skip_res_store = (skip_res_store && xn_out) ? 1 : 0;
   if (B > 0) {
     p.y_cm = 1; p.T = T; p.tiles_per_seq = (T + bm::BM - 1) / bm::BM; p.num_tiles = B * p.tiles_per_seq;
@@ -1617,6 +1619,7 @@ int clm_set_option(clm_ctx* c, const char* name, int value) {
   else if (n == "mlp_fc2_lag") c->mlp_fc2_lag = value;
   else if (n == "mlp_early_res") c->mlp_early_res = value;
   else if (n == "mlp_helpers_high") c->mlp_helpers_high = value;
+  else if (n == "mlp_store_a") c->mlp_store_a = value;
   else if (n == "in_prefetch") c->in_prefetch = value;
   else return fail(c, CLM_ERR_INVALID, "clm_set_option: unknown option '%s'", name);
   return 0;

@@ -54,6 +54,7 @@ struct BlockMlpParams {
   // pooling consume the normalised xn rows) - 128 KB of stores per tile less on the SM's ~30 B/clk store path
   int skip_res_store;
   int stagger_cycles;    // CTA b starts (b % 4) * stagger_cycles late (0 = off)
+  int store_a;           // 0..4: column groups (of 4) whose residual stores are issued in E3's statistics sweep
   int helpers_high;      // 1: the helper warps (producer, MMA issuer) take the highest warp ids, the epilogue warps 0..7
   long long* trace;      // optional [3][64] clock64 stamps written by CTA 0 (null in production)
 };
@@ -576,11 +577,22 @@ block_mlp_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
           uint32_t a[32];
           ptx::tmem_ld_32x32b_x32(lane_addr + TM_R + col, a);
           ptx::tmem_ld_wait();
+          // store_a: the residual stores of the first `store_a` column groups are issued HERE, in the statistics sweep, where
+          // the store path would otherwise idle (the values are final; only the normalised copy needs the row statistics):
+          // 128 KB per tile at ~30 B/clk/SM is the floor of this epilogue, and sweep B alone carried all of it
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             const float v = __uint_as_float(a[j]) + lc.b2[col + j];
             o1 += v;
             o2 = fmaf(v, v, o2);
+          }
+          if (ci < p.store_a && row_ok && !p.skip_res_store) {
+            float* dst = p.res + ptx::r32_off(row, col);   // column chunks of a row are 128 floats apart in the R32 layout
+#pragma unroll
+            for (int g = 0; g < 8; ++g)
+              *reinterpret_cast<float4*>(dst + g * 128) =
+                  make_float4(__uint_as_float(a[4 * g]) + lc.b2[col + 4 * g], __uint_as_float(a[4 * g + 1]) + lc.b2[col + 4 * g + 1],
+                              __uint_as_float(a[4 * g + 2]) + lc.b2[col + 4 * g + 2], __uint_as_float(a[4 * g + 3]) + lc.b2[col + 4 * g + 3]);
           }
           if constexpr (EARLY_RES == 33) load_res_dyn(pf_row, pf_ok, 8 + 4 * ci, 4);
         }
@@ -604,7 +616,7 @@ block_mlp_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
             float x[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) x[j] = __uint_as_float(a[g * 8 + j]) + lc.b2[col + g * 8 + j];
-            if (row_ok && !p.skip_res_store) {
+            if (ci >= p.store_a && row_ok && !p.skip_res_store) {
               *reinterpret_cast<float4*>(p.res + ptx::r32_off(row, col + g * 8)) = make_float4(x[0], x[1], x[2], x[3]);
               *reinterpret_cast<float4*>(p.res + ptx::r32_off(row, col + g * 8 + 4)) = make_float4(x[4], x[5], x[6], x[7]);
             }
