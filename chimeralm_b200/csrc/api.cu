@@ -15,6 +15,7 @@
 
 #include "../../include/chimeralm_b200.h"
 #include "block_in.cuh"
+#include "embed_in.cuh"
 #include "block_mlp.cuh"
 #ifdef CLM_EXPERIMENTS   // recorded-slower variants of the block tail and the first long-convolution kernel: not in the product build
 #include "block_in2.cuh"
@@ -49,6 +50,7 @@ struct LayerW {
   // LayerNorm1 affine folded into in_proj (block_in kernel): W' = W diag(gamma), b' = b + W beta
   __nv_bfloat16* in_wf = nullptr;
   float* in_bf = nullptr;
+  float* in_wf32 = nullptr;   // folded in_proj weights in fp32 (source of the bf16 tiles; layer 0's feed embed_in_table_kernel)
   CUtensorMap tm_inf;
   CUtensorMap tm_inf_h;   // same buffer, one k-block (128 rows) per box: the CTA-pair kernel's 16 KB slots
   // block_mlp operands, pre-tiled [N/rt][K/64][rt][64] so that every 32 KB ring slot is one TMA box
@@ -185,6 +187,11 @@ struct clm_ctx {
   bool mlp_2cta = false;  // CTA-pair (cta_group::2) version of the fused block tail
   bool mlp_epi16 = false; // fused block tail with 16 epilogue warps (block_mlp16.cuh)
   int mlp_helpers_high = 0;
+  bool embed_in = true;   // block 0's first half by table lookup over the token ids (embed_in.cuh) instead of block_in_kernel
+  float* u_tab0 = nullptr;   // [768][16] in_proj output of block 0 per vocabulary row
+  bool mlp_gather_tails = true;   // block_mlp: reads ending in a <= 64-token partial tile share gathered tiles (BlockMlpParams::gather_L)
+  __nv_bfloat16* YG = nullptr;    // gathered tail columns of Y, channel-major [D][128 x gathered tiles]
+  size_t yg_elems = 0;
   int mlp_store_a = 0;    // block_mlp: residual column groups stored in the statistics sweep of the output epilogue
   int in_prefetch = 0;    // block_in: next token tile prefetched into L2 (measured: no effect, 0.667 vs 0.665 ms/step interleaved)
   int mlp_early_res = 33; // block_mlp: float4 of the next tile's residual half-row loaded before E3 (0, 16, 32; 33 = spread over E3)
@@ -457,6 +464,29 @@ int launch_block_in(clm_ctx* c, int layer, const __nv_bfloat16* xn, int B, int T
   return 0;
 }
 
+// block 0's first half straight from the token ids (embed_in.cuh)
+int launch_embed_in(clm_ctx* c, const void* d_ids, int ids_dtype, int B, int T, int Tp, void* vx, __nv_bfloat16* x0,
+                    cudaStream_t st, bool vx_f16) {
+  LayerW& L = c->layers[0];
+  EmbedInParams p{};
+  p.ids = d_ids; p.U = c->u_tab0; p.cw = L.sc_w; p.cb = L.sc_b;
+  p.vx_scale = vx_f16 ? L.vx_scale : nullptr;
+  p.x0 = x0; p.vx = vx; p.B = B; p.T = T; p.Tp = Tp; p.vx_f16 = vx_f16 ? 1 : 0; p.rows = c->cfg.vocab_rows;
+  const dim3 grid((unsigned)((Tp + ei::BLOCK_TOK - 1) / ei::BLOCK_TOK), ei::D / ei::CG, (unsigned)B);
+#define CLM_EI_LAUNCH(IdT)                                                          \
+  if (vx_f16) embed_in_kernel<IdT, true><<<grid, ei::THREADS, 0, st>>>(p);           \
+  else embed_in_kernel<IdT, false><<<grid, ei::THREADS, 0, st>>>(p)
+  switch (ids_dtype) {
+    case CLM_U8: CLM_EI_LAUNCH(uint8_t); break;
+    case CLM_I32: CLM_EI_LAUNCH(int32_t); break;
+    case CLM_I64: CLM_EI_LAUNCH(int64_t); break;
+    default: return fail(c, CLM_ERR_INVALID, "embed_in: ids dtype %d not supported", ids_dtype);
+  }
+#undef CLM_EI_LAUNCH
+  CLM_LAUNCH_CHECK(c, "embed_in");
+  return 0;
+}
+
 // y token-major [M,256] when B == 0; channel-major [B][256][Tp] (M == B*T) otherwise
 int launch_block_mlp(clm_ctx* c, int layer, const __nv_bfloat16* y, float* res, int M, cudaStream_t st,
                      long long* trace = nullptr, int B = 0, int T = 0, int Tp = 0, __nv_bfloat16* xn_out = nullptr,
@@ -487,6 +517,36 @@ int launch_block_mlp(clm_ctx* c, int layer, const __nv_bfloat16* y, float* res, 
   p.skip_res_store = (skip_res_store && xn_out) ? 1 : 0;
   if (B > 0) {
     p.y_cm = 1; p.T = T; p.tiles_per_seq = (T + bm::BM - 1) / bm::BM; p.num_tiles = B * p.tiles_per_seq;
+  }
+  p.n_full_tiles = p.num_tiles; p.B = B; p.xn = xn_out;
+  CUtensorMap tmYG = tmY;
+#ifdef CLM_EXPERIMENTS
+  const bool gather_ok = !(c->mlp_2cta && !trace) && !c->mlp_pp && !c->mlp_epi16;
+#else
+  const bool gather_ok = true;
+#endif
+  if (B > 1 && c->mlp_gather_tails && gather_ok && c->YG) {
+    // tails of 1..64 tokens: 128 / L of them per gathered tile instead of one partial tile each (BlockMlpParams::gather_L)
+    const int Lt = T % bm::BM;
+    const int P = Lt > 0 ? bm::BM / Lt : 0;
+    const int n_g = P >= 2 ? (B + P - 1) / P : 0;
+    const int D = c->cfg.d_model;
+    const size_t TG = (size_t)n_g * bm::BM;
+    if (n_g > 0 && n_g < B && TG * D <= c->yg_elems) {
+      gather_tails_kernel<<<(unsigned)((TG * D + 255) / 256), 256, 0, st>>>(y, c->YG, B, D, Tp, (int)TG, T - Lt, Lt, P);
+      CLM_LAUNCH_CHECK(c, "gather_tails");
+      cuuint64_t dims[3] = {(cuuint64_t)TG, (cuuint64_t)D, 1};
+      cuuint64_t strides[2] = {(cuuint64_t)TG * 2, (cuuint64_t)TG * D * 2};
+      cuuint32_t box[3] = {64, 64, 1}, estr[3] = {1, 1, 1};
+      CUresult r = c->encode_tiled(&tmYG, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, c->YG, dims, strides, box, estr,
+                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) return fail(c, CLM_ERR_CUDA, "cuTensorMapEncodeTiled(gathered tails) failed with CUresult %d", (int)r);
+      p.gather_L = Lt; p.gather_P = P;
+      p.tiles_per_seq = T / bm::BM;
+      p.n_full_tiles = B * p.tiles_per_seq;
+      p.num_tiles = p.n_full_tiles + n_g;
+    }
   }
   CUtensorMap tmXN = tmY;
   if (xn_out) {
@@ -521,7 +581,7 @@ int launch_block_mlp(clm_ctx* c, int layer, const __nv_bfloat16* y, float* res, 
 #define CLM_MLP_LAUNCH(E, LAG)                                                                                             \
   {                                                                                                                        \
     if (int rc_attr = ensure_smem_attr(c, (const void*)(block_mlp_kernel<E, LAG>), (int)(bm::SMEM_TOTAL))) return rc_attr;  \
-    block_mlp_kernel<E, LAG><<<grid, bm::THREADS_WG, bm::SMEM_TOTAL, st>>>(tmY, L.tm_out_t, L.tm_fc1_t, L.tm_fc2_t, tmXN, p); \
+    block_mlp_kernel<E, LAG><<<grid, bm::THREADS_WG, bm::SMEM_TOTAL, st>>>(tmY, L.tm_out_t, L.tm_fc1_t, L.tm_fc2_t, tmXN, tmYG, p); \
   }
   if (c->mlp_fc2_lag >= 2) CLM_MLP_LAUNCH(33, 2)
   else if (c->mlp_early_res >= 33) CLM_MLP_LAUNCH(33, 1)
@@ -1016,6 +1076,7 @@ int clm_finalize(clm_ctx* c) {
       fold_ln_kernel<<<3 * D, 256>>>(in_w, L.in_b, L.ln1_g, L.ln1_b, wf, L.in_bf, D);
       CLM_LAUNCH_CHECK(c, "fold_ln");
       if ((rc = retile(c, wf, 3 * D, D, 128, &L.in_wf, &L.tm_inf))) return rc;
+      L.in_wf32 = wf;
 #ifdef CLM_EXPERIMENTS
       if ((rc = make_tmap_retiled(c, &L.tm_inf_h, L.in_wf, (long long)3 * D * D / 64, 128))) return rc;
 #endif
@@ -1157,6 +1218,11 @@ int clm_finalize(clm_ctx* c) {
     if ((rc = dev_alloc(c, &c->emb_norm, (size_t)g.vocab_rows * D))) return rc;
     embed_norm_table_kernel<<<g.vocab_rows, 32>>>(c->emb, c->emb_norm, g.vocab_rows, g.layer_norm_eps);
     CLM_LAUNCH_CHECK(c, "embed_norm_table");
+    if (g.n_layer > 0 && g.vocab_rows <= ei::NV && D == ei::D && c->layers[0].in_wf32) {
+      if ((rc = dev_alloc(c, &c->u_tab0, (size_t)3 * D * ei::NV))) return rc;
+      embed_in_table_kernel<<<3 * D, 32>>>(c->layers[0].in_wf32, c->layers[0].in_bf, c->emb_norm, c->u_tab0, g.vocab_rows);
+      CLM_LAUNCH_CHECK(c, "embed_in_table");
+    }
     std::vector<float> h1(D, 1.0f);
     if ((rc = dev_alloc(c, &c->ones, (size_t)D))) return rc;
     if ((rc = dev_alloc(c, &c->zeros, (size_t)D))) return rc;
@@ -1198,10 +1264,10 @@ int clm_reserve_tokens(clm_ctx* c, int max_B, int max_T, long long max_tokens) {
   // fit), the context is left with no workspaces and max_B = max_T = 0, so every later forward is refused until a
   // smaller clm_reserve succeeds - never a launch on freed memory.
   c->max_B = c->max_T = c->Tp_max = 0;
-  c->max_tokens = 0; c->ct_elems = 0;
+  c->max_tokens = 0; c->ct_elems = 0; c->yg_elems = 0;
   c->scratch_bytes = 0; c->tc_scratch_floats = 0; c->st_bases_cap = 0;
   dev_release(c, &c->R); dev_release(c, &c->XN); dev_release(c, &c->U); dev_release(c, &c->VX); dev_release(c, &c->X0);
-  dev_release(c, &c->Y); dev_release(c, &c->YT); dev_release(c, &c->score); dev_release(c, &c->part);
+  dev_release(c, &c->Y); dev_release(c, &c->YG); dev_release(c, &c->YT); dev_release(c, &c->score); dev_release(c, &c->part);
   dev_release(c, &c->pooled); dev_release(c, &c->scratch); dev_release(c, &c->tc_scratch);
   for (auto& sl : c->slot) {
     dev_release(c, &sl.bases); dev_release(c, &sl.offsets); dev_release(c, &sl.ids); dev_release(c, &sl.logits);
@@ -1222,6 +1288,11 @@ int clm_reserve_tokens(clm_ctx* c, int max_B, int max_T, long long max_tokens) {
   if ((rc = dev_alloc(c, &c->VX, CT))) return rc;
   if ((rc = dev_alloc(c, &c->X0, CT))) return rc;
   if ((rc = dev_alloc(c, &c->Y, CT))) return rc;
+  {   // at most ceil(max_B / 2) gathered tiles of 128 columns
+    const size_t yg = (size_t)D * bm::BM * ((size_t)(max_B + 1) / 2);
+    if ((rc = dev_alloc(c, &c->YG, yg))) return rc;
+    c->yg_elems = yg;
+  }
   if ((rc = dev_alloc(c, &c->YT, M * D))) return rc;
   if ((rc = dev_alloc(c, &c->score, M))) return rc;
   c->n_split = std::max(1, std::min(64, (2 * c->num_sms + max_B - 1) / max_B));
@@ -1306,11 +1377,14 @@ int clm_forward(clm_ctx* c, const void* d_ids, int ids_dtype, int B, int T, floa
 #define STOP_AFTER(layer, stage) \
   if (c->dbg_layer == (layer) && c->dbg_stage == (stage)) return 0
 
+  // block 0's first half reads the ids directly (table lookup), so nobody consumes the embedding's xn rows
+  const bool ei0 = c->embed_in && c->u_tab0 && c->fused_in && c->dbg_layer != 0 && g.n_layer > 0 && B <= 65535;
+  __nv_bfloat16* const emb_xn = ei0 ? nullptr : c->XN;
   { ProfScope ps_(c, PC_EMBED, st);
   switch (ids_dtype) {
-    case CLM_U8: embed_kernel<uint8_t><<<rows32e, 256, 0, st>>>((const uint8_t*)d_ids, c->emb, c->emb_norm, c->R, c->XN, M, D, g.vocab_rows, c->d_err); break;
-    case CLM_I32: embed_kernel<int32_t><<<rows32e, 256, 0, st>>>((const int32_t*)d_ids, c->emb, c->emb_norm, c->R, c->XN, M, D, g.vocab_rows, c->d_err); break;
-    case CLM_I64: embed_kernel<int64_t><<<rows32e, 256, 0, st>>>((const int64_t*)d_ids, c->emb, c->emb_norm, c->R, c->XN, M, D, g.vocab_rows, c->d_err); break;
+    case CLM_U8: embed_kernel<uint8_t><<<rows32e, 256, 0, st>>>((const uint8_t*)d_ids, c->emb, c->emb_norm, c->R, emb_xn, M, D, g.vocab_rows, c->d_err); break;
+    case CLM_I32: embed_kernel<int32_t><<<rows32e, 256, 0, st>>>((const int32_t*)d_ids, c->emb, c->emb_norm, c->R, emb_xn, M, D, g.vocab_rows, c->d_err); break;
+    case CLM_I64: embed_kernel<int64_t><<<rows32e, 256, 0, st>>>((const int64_t*)d_ids, c->emb, c->emb_norm, c->R, emb_xn, M, D, g.vocab_rows, c->d_err); break;
     default: return fail(c, CLM_ERR_INVALID, "clm_forward: ids dtype %d not supported", ids_dtype);
   }
   CLM_LAUNCH_CHECK(c, "embed"); }
@@ -1328,7 +1402,9 @@ int clm_forward(clm_ctx* c, const void* d_ids, int ids_dtype, int B, int T, floa
       }
       ProfScope ps_(c, PC_BLOCK_IN, st);
       use_tc = tc_conv_applies(c, T);
-      if ((rc = launch_block_in(c, l, c->XN, B, T, Tp, c->VX, c->X0, st, nullptr, use_tc))) return rc;
+      if (l == 0 && ei0) rc = launch_embed_in(c, d_ids, ids_dtype, B, T, Tp, c->VX, c->X0, st, use_tc);
+      else rc = launch_block_in(c, l, c->XN, B, T, Tp, c->VX, c->X0, st, nullptr, use_tc);
+      if (rc) return rc;
       if (c->calibrating && !use_tc && L.vx_amax) {
         tc::amax_cm_kernel<<<dim3(D, B), 256, 0, st>>>(c->VX, D, Tp, T, L.vx_amax);
         CLM_LAUNCH_CHECK(c, "vx_amax");
@@ -1620,6 +1696,8 @@ int clm_set_option(clm_ctx* c, const char* name, int value) {
   else if (n == "mlp_early_res") c->mlp_early_res = value;
   else if (n == "mlp_helpers_high") c->mlp_helpers_high = value;
   else if (n == "mlp_store_a") c->mlp_store_a = value;
+  else if (n == "embed_in") c->embed_in = value != 0;
+  else if (n == "mlp_gather_tails") c->mlp_gather_tails = value != 0;
   else if (n == "in_prefetch") c->in_prefetch = value;
   else return fail(c, CLM_ERR_INVALID, "clm_set_option: unknown option '%s'", name);
   return 0;

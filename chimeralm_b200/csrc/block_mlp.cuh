@@ -47,6 +47,14 @@ struct BlockMlpParams {
   // y_cm == 1: y is channel-major [B][256][Tp] (tmY 3-D {t, c, b}); tiles are 128 tokens of ONE read,
   //            fed to out_proj as an MN-major A operand, so no transpose pass is needed.
   int y_cm, T, tiles_per_seq;
+  // Tail gathering (y_cm only; gather_L == 0: off).  A read of T = 128 f + L tokens with 1 <= L <= 64 would end in a tile
+  // with L valid rows that costs as much as a full one (B of them per launch: K2's 8 193-token reads pay 2 080 tiles =
+  // 15 waves for 2 048 tiles of work).  Instead tiles_per_seq = f, tiles [0, n_full_tiles) are the full ones, and the tails
+  // of gather_P = 128 / L reads share each of the remaining tiles: row r of gathered tile g is token 128 f + r % L of read
+  // g P + r / L.  Their y operand comes from yg (tmYG: channel-major [256][gathered tiles x 128], written by
+  // gather_tails_kernel), their normalised rows go to xn by plain stores.
+  int gather_L, gather_P, n_full_tiles, B;
+  __nv_bfloat16* xn;     // xn rows [B*T][256] (gathered tiles only; the full tiles use tmXN)
   // write_xn: the output epilogue also emits xn = (out - mean) * rstd as bf16 [B][T][256] (tmXN, 3-D {col, t, b}):
   // the next consumer's LayerNorm (affine folded into its weights) without another pass over the residual.
   int write_xn;
@@ -121,6 +129,16 @@ __device__ __forceinline__ uint32_t gelu_tanh_bf16x2(f2t h) {
 }
 }  // namespace bm
 
+// y [B][D][Tp] channel-major -> yg [D][TG]: column 128 g + r = token t0 + r % L of read g P + r / L (zero where there is none)
+__global__ void gather_tails_kernel(const __nv_bfloat16* __restrict__ y, __nv_bfloat16* __restrict__ yg, int B, int D, int Tp,
+                                    int TG, int t0, int L, int P) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= D * TG) return;
+  const int c = idx / TG, col = idx - c * TG;
+  const int g = col >> 7, r = col & 127, jj = r / L, l = r - jj * L, j = g * P + jj;
+  yg[idx] = (jj < P && j < B) ? y[((size_t)j * D + c) * Tp + t0 + l] : __float2bfloat16(0.f);
+}
+
 // EARLY_RES: the next tile's residual half-row is loaded into registers BEFORE the output epilogue (E3) of this tile
 // instead of after it, so the loads (per-SM outstanding-miss bound: ~6.5 K cycles for 128 KB even from L2) complete
 // under E3's stores instead of in front of E1.
@@ -134,7 +152,7 @@ template <int EARLY_RES, int LAG = 1>   // EARLY_RES: number of the 32 float4 lo
 __global__ void __launch_bounds__(bm::THREADS_WG, 1)
 block_mlp_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmWout,
                  const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2,
-                 const __grid_constant__ CUtensorMap tmXN, BlockMlpParams p) {
+                 const __grid_constant__ CUtensorMap tmXN, const __grid_constant__ CUtensorMap tmYG, BlockMlpParams p) {
   using namespace bm;
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((ptx::smem_u32(smem) & 1023u) != 0) __trap();  // swizzled UMMA/TMA tiles need 1 KB alignment
@@ -169,7 +187,7 @@ block_mlp_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmY); ptx::prefetch_tmap(&tmWout); ptx::prefetch_tmap(&tmW1); ptx::prefetch_tmap(&tmW2);
-    ptx::prefetch_tmap(&tmXN);
+    ptx::prefetch_tmap(&tmXN); ptx::prefetch_tmap(&tmYG);
     for (int i = 0; i < NSLOT; ++i) { ptx::mbar_init(&w_full[i], 1); ptx::mbar_init(&w_empty[i], 1); }
     ptx::mbar_init(g1_done, 1);
     ptx::mbar_init(xn_full, 8);
@@ -213,9 +231,12 @@ block_mlp_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
           for (int q = 0; q < 2; ++q) {
             const int kb = 2 * kp + q;
             if (p.y_cm) {
-              const int b = tile / p.tiles_per_seq, t0 = (tile % p.tiles_per_seq) * BM;
+              const bool gt = tile >= p.n_full_tiles;   // gathered tails: same box, from yg
+              const CUtensorMap* tm = gt ? &tmYG : &tmY;
+              const int b = gt ? 0 : tile / p.tiles_per_seq;
+              const int t0 = gt ? (tile - p.n_full_tiles) * BM : (tile % p.tiles_per_seq) * BM;
               for (int hh = 0; hh < 2; ++hh)   // k-block = 64 channels; two 64-token halves of 8 KB each
-                ptx::tma_load_3d(s + q * KB_BYTES + hh * (KB_BYTES / 2), &tmY, fb, t0 + hh * 64, kb * BK, b);
+                ptx::tma_load_3d(s + q * KB_BYTES + hh * (KB_BYTES / 2), tm, fb, t0 + hh * 64, kb * BK, b);
             } else {
               ptx::tma_load_2d(s + q * KB_BYTES, &tmY, fb, kb * BK, tile * BM);
             }
@@ -411,46 +432,42 @@ block_mlp_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
           rs[j] = ok ? *reinterpret_cast<const float4*>(p.res + ptx::r32_off(lrow, hf * 128 + 4 * j))
                      : make_float4(0.f, 0.f, 0.f, 0.f);
     };
+    // residual / xn row of this thread in `tile`
+    auto tile_row = [&](int tile, long long& row, bool& ok) {
+      if (p.y_cm) {
+        if (tile < p.n_full_tiles) {
+          const int t = (tile % p.tiles_per_seq) * BM + r;
+          row = (long long)(tile / p.tiles_per_seq) * p.T + t;
+          ok = t < p.T;
+        } else {
+          const int jj = r / p.gather_L, j = (tile - p.n_full_tiles) * p.gather_P + jj;
+          row = (long long)j * p.T + (p.T - p.gather_L) + (r - jj * p.gather_L);
+          ok = jj < p.gather_P && j < p.B;
+        }
+      } else {
+        row = (long long)tile * BM + r;
+        ok = row < p.M;
+      }
+    };
     using I0 = std::integral_constant<int, 0>;
     using IE = std::integral_constant<int, (EARLY_RES > 32 ? 32 : EARLY_RES)>;
     using I32 = std::integral_constant<int, 32>;
     if (EARLY_RES && (int)blockIdx.x < p.num_tiles) {
-      if (p.y_cm) {
-        const int t = ((int)blockIdx.x % p.tiles_per_seq) * BM + r;
-        load_res((long long)((int)blockIdx.x / p.tiles_per_seq) * p.T + t, t < p.T, I0{}, IE{});
-      } else {
-        load_res((long long)blockIdx.x * BM + r, (long long)blockIdx.x * BM + r < p.M, I0{}, IE{});
-      }
+      long long row0;
+      bool ok0;
+      tile_row((int)blockIdx.x, row0, ok0);
+      load_res(row0, ok0, I0{}, IE{});
     }
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
       const uint32_t tph = it & 1;
       const uint32_t TM_R = tph ? 256u : 0u, TM_XN = tph ? 0u : 256u, TM_H = tph ? 128u : 384u;
       long long row;
       bool row_ok;
-      if (p.y_cm) {
-        const int b = tile / p.tiles_per_seq, t = (tile % p.tiles_per_seq) * BM + r;
-        row = (long long)b * p.T + t;
-        row_ok = t < p.T;
-      } else {
-        row = (long long)tile * BM + r;
-        row_ok = row < p.M;
-      }
+      tile_row(tile, row, row_ok);
       // row of this thread in the NEXT tile of this CTA (for the residual L2 prefetch)
       long long pf_row = 0;
       bool pf_ok = false;
-      {
-        const int nt_ = tile + gridDim.x;
-        if (nt_ < p.num_tiles) {
-          if (p.y_cm) {
-            const int t = (nt_ % p.tiles_per_seq) * BM + r;
-            pf_row = (long long)(nt_ / p.tiles_per_seq) * p.T + t;
-            pf_ok = t < p.T;
-          } else {
-            pf_row = (long long)nt_ * BM + r;
-            pf_ok = pf_row < p.M;
-          }
-        }
-      }
+      if (tile + (int)gridDim.x < p.num_tiles) tile_row(tile + (int)gridDim.x, pf_row, pf_ok);
       // ------------------------------------------------ E1: r1, LayerNorm2 -> xn (TMEM)
       // The residual half-row (128 fp32) is fetched into registers BEFORE waiting for the
       // out_proj accumulator, so its DRAM latency hides behind the y-tile load and G1.
@@ -650,7 +667,20 @@ block_mlp_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
       if (lane == 0) ptx::mbar_arrive(r_free);
       if (p.write_xn) {
         ptx::bar_sync(1, EPI_THREADS);
-        if (warp == EPI_WARP0 && lane == 0) {
+        if (tile >= p.n_full_tiles) {   // (n_full_tiles == num_tiles unless tails are gathered)
+          // rows of different reads: no TMA box.  Every thread copies its own staged half-row (the bytes it wrote above) to
+          // the xn row, 16 B at a time; the generic-proxy reads are done before the next tile's first HB write (program order).
+          if (row_ok) {
+            uint4* dst = reinterpret_cast<uint4*>(p.xn + row * D + hf * 128);
+#pragma unroll 1
+            for (int k = 0; k < 16; ++k) {   // 16-byte chunk k of the half-row: k-block 2 hf + k / 8, chunk k % 8 (swizzled)
+              const uint32_t a_ = sHB + (2 * hf + (k >> 3)) * KB_BYTES + r * 128 + ((uint32_t(k & 7) ^ swz) << 4);
+              uint4 v;
+              asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a_));
+              dst[k] = v;
+            }
+          }
+        } else if (warp == EPI_WARP0 && lane == 0) {
           int xb, xt0;
           if (p.y_cm) { xb = tile / p.tiles_per_seq; xt0 = (tile % p.tiles_per_seq) * BM; }
           else { xb = 0; xt0 = tile * BM; }

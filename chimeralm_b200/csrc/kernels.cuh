@@ -93,7 +93,7 @@ __global__ void __launch_bounds__(256) embed_kernel(const IdT* __restrict__ ids,
   for (int k = 0; k < 4; ++k) {
     const int rr = warp * 4 + k;
     const long long row = row0 + rr;
-    if (row < M) reinterpret_cast<uint4*>(XN + row * D)[lane] = __ldg(reinterpret_cast<const uint4*>(En + (long long)s_id[rr] * D) + lane);
+    if (XN && row < M) reinterpret_cast<uint4*>(XN + row * D)[lane] = __ldg(reinterpret_cast<const uint4*>(En + (long long)s_id[rr] * D) + lane);
   }
 }
 

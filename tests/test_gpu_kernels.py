@@ -303,9 +303,11 @@ def test_block_in_fused(engine, state_dict, B, T):
     assert e_vx <= 2e-2 * max(1.0, vx_ref.abs().max().item()), (e_vx, vx_ref.abs().max().item())
 
 
-@pytest.mark.parametrize("B,T", [(1, 128), (2, 300), (3, 1025)])
+@pytest.mark.parametrize("B,T", [(1, 128), (2, 300), (3, 1025), (4, 60), (7, 130), (5, 2112), (3, 1500)])
 def test_block_mlp_channel_major_operand(engine, state_dict, B, T):
-    """Same fused block tail, fed the conv output channel-major (MN-major UMMA A operand)."""
+    """Same fused block tail, fed the conv output channel-major (MN-major UMMA A operand).  Reads ending in a partial tile of
+    1..64 tokens share gathered tiles (300 -> 44-token tails, two per tile; 1025 -> 128 per tile; 60: no full tile at all;
+    2112 -> 64-token tails); 1500 (92-token tails) and B = 1 keep one partial tile per read."""
     from oracle import hyena_oracle as O
 
     layer = 0
