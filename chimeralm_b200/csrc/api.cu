@@ -189,6 +189,8 @@ struct clm_ctx {
   int mlp_helpers_high = 0;
   bool embed_in = true;   // block 0's first half by table lookup over the token ids (embed_in.cuh) instead of block_in_kernel
   float* u_tab0 = nullptr;   // [768][16] in_proj output of block 0 per vocabulary row
+  float* emb_r32 = nullptr;  // embedding rows as a 32-row R32 table: block 0's residual input is looked up by token id
+  bool embed_res = true;     // with embed_in: no embedding kernel at all (block_mlp of block 0 reads emb_r32)
   bool mlp_gather_tails = true;   // block_mlp: reads ending in a <= 64-token partial tile share gathered tiles (BlockMlpParams::gather_L)
   __nv_bfloat16* YG = nullptr;    // gathered tail columns of Y, channel-major [D][128 x gathered tiles]
   size_t yg_elems = 0;
@@ -472,6 +474,7 @@ int launch_embed_in(clm_ctx* c, const void* d_ids, int ids_dtype, int B, int T, 
   p.ids = d_ids; p.U = c->u_tab0; p.cw = L.sc_w; p.cb = L.sc_b;
   p.vx_scale = vx_f16 ? L.vx_scale : nullptr;
   p.x0 = x0; p.vx = vx; p.B = B; p.T = T; p.Tp = Tp; p.vx_f16 = vx_f16 ? 1 : 0; p.rows = c->cfg.vocab_rows;
+  p.err = c->d_err;
   const dim3 grid((unsigned)((Tp + ei::BLOCK_TOK - 1) / ei::BLOCK_TOK), ei::D / ei::CG, (unsigned)B);
 #define CLM_EI_LAUNCH(IdT)                                                          \
   if (vx_f16) embed_in_kernel<IdT, true><<<grid, ei::THREADS, 0, st>>>(p);           \
@@ -490,7 +493,7 @@ int launch_embed_in(clm_ctx* c, const void* d_ids, int ids_dtype, int B, int T, 
 // y token-major [M,256] when B == 0; channel-major [B][256][Tp] (M == B*T) otherwise
 int launch_block_mlp(clm_ctx* c, int layer, const __nv_bfloat16* y, float* res, int M, cudaStream_t st,
                      long long* trace = nullptr, int B = 0, int T = 0, int Tp = 0, __nv_bfloat16* xn_out = nullptr,
-                     bool skip_res_store = false) {
+                     bool skip_res_store = false, const void* ids = nullptr, int ids_dtype = 0) {
   if (int rc_c = bind_constants(c, st)) return rc_c;
   LayerW& L = c->layers[layer];
   CUtensorMap tmY;
@@ -519,6 +522,7 @@ int launch_block_mlp(clm_ctx* c, int layer, const __nv_bfloat16* y, float* res, 
     p.y_cm = 1; p.T = T; p.tiles_per_seq = (T + bm::BM - 1) / bm::BM; p.num_tiles = B * p.tiles_per_seq;
   }
   p.n_full_tiles = p.num_tiles; p.B = B; p.xn = xn_out;
+  if (ids) { p.res_tab = c->emb_r32; p.ids = ids; p.ids_dtype = ids_dtype; p.vocab_rows = c->cfg.vocab_rows; }
   CUtensorMap tmYG = tmY;
 #ifdef CLM_EXPERIMENTS
   const bool gather_ok = !(c->mlp_2cta && !trace) && !c->mlp_pp && !c->mlp_epi16;
@@ -1222,6 +1226,9 @@ int clm_finalize(clm_ctx* c) {
       if ((rc = dev_alloc(c, &c->u_tab0, (size_t)3 * D * ei::NV))) return rc;
       embed_in_table_kernel<<<3 * D, 32>>>(c->layers[0].in_wf32, c->layers[0].in_bf, c->emb_norm, c->u_tab0, g.vocab_rows);
       CLM_LAUNCH_CHECK(c, "embed_in_table");
+      if ((rc = dev_alloc(c, &c->emb_r32, (size_t)32 * D))) return rc;
+      embed_r32_table_kernel<<<32, 256>>>(c->emb, c->emb_r32, g.vocab_rows);
+      CLM_LAUNCH_CHECK(c, "embed_r32_table");
     }
     std::vector<float> h1(D, 1.0f);
     if ((rc = dev_alloc(c, &c->ones, (size_t)D))) return rc;
@@ -1380,7 +1387,14 @@ int clm_forward(clm_ctx* c, const void* d_ids, int ids_dtype, int B, int T, floa
   // block 0's first half reads the ids directly (table lookup), so nobody consumes the embedding's xn rows
   const bool ei0 = c->embed_in && c->u_tab0 && c->fused_in && c->dbg_layer != 0 && g.n_layer > 0 && B <= 65535;
   __nv_bfloat16* const emb_xn = ei0 ? nullptr : c->XN;
-  { ProfScope ps_(c, PC_EMBED, st);
+#ifdef CLM_EXPERIMENTS
+  const bool mlp_product = !c->mlp_2cta && !c->mlp_pp && !c->mlp_epi16;
+#else
+  const bool mlp_product = true;
+#endif
+  // ... and block 0's second half looks its residual input up by token id: no embedding kernel at all
+  const bool ei_res = ei0 && c->embed_res && c->emb_r32 && c->fused_mlp && mlp_product;
+  if (!ei_res) { ProfScope ps_(c, PC_EMBED, st);
   switch (ids_dtype) {
     case CLM_U8: embed_kernel<uint8_t><<<rows32e, 256, 0, st>>>((const uint8_t*)d_ids, c->emb, c->emb_norm, c->R, emb_xn, M, D, g.vocab_rows, c->d_err); break;
     case CLM_I32: embed_kernel<int32_t><<<rows32e, 256, 0, st>>>((const int32_t*)d_ids, c->emb, c->emb_norm, c->R, emb_xn, M, D, g.vocab_rows, c->d_err); break;
@@ -1440,8 +1454,9 @@ int clm_forward(clm_ctx* c, const void* d_ids, int ids_dtype, int B, int T, floa
       ProfScope ps_(c, PC_BLOCK_MLP, st);
       // the last block's residual has no reader on the folded tail (scorer + pooling read xn); any debug stop keeps it
       const bool dead_res = l == g.n_layer - 1 && c->dbg_layer < 0 && c->skip_dead_res;
-      if (c->y_channel_major) rc = launch_block_mlp(c, l, c->Y, c->R, (int)M, st, nullptr, B, T, Tp, c->XN, dead_res);
-      else rc = launch_block_mlp(c, l, c->YT, c->R, (int)M, st, nullptr, 0, 0, 0, c->XN, dead_res);
+      const void* tab_ids = (l == 0 && ei_res) ? d_ids : nullptr;
+      if (c->y_channel_major) rc = launch_block_mlp(c, l, c->Y, c->R, (int)M, st, nullptr, B, T, Tp, c->XN, dead_res, tab_ids, ids_dtype);
+      else rc = launch_block_mlp(c, l, c->YT, c->R, (int)M, st, nullptr, 0, 0, 0, c->XN, dead_res, tab_ids, ids_dtype);
       if (rc) return rc;
       xn_valid = true;
     } else {
@@ -1697,6 +1712,7 @@ int clm_set_option(clm_ctx* c, const char* name, int value) {
   else if (n == "mlp_helpers_high") c->mlp_helpers_high = value;
   else if (n == "mlp_store_a") c->mlp_store_a = value;
   else if (n == "embed_in") c->embed_in = value != 0;
+  else if (n == "embed_res") c->embed_res = value != 0;
   else if (n == "mlp_gather_tails") c->mlp_gather_tails = value != 0;
   else if (n == "in_prefetch") c->in_prefetch = value;
   else return fail(c, CLM_ERR_INVALID, "clm_set_option: unknown option '%s'", name);

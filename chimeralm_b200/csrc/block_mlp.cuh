@@ -55,6 +55,12 @@ struct BlockMlpParams {
   // gather_tails_kernel), their normalised rows go to xn by plain stores.
   int gather_L, gather_P, n_full_tiles, B;
   __nv_bfloat16* xn;     // xn rows [B*T][256] (gathered tiles only; the full tiles use tmXN)
+  // res_tab != nullptr (block 0): the residual INPUT of row i is the embedding row of token id ids[i], read from a 32-row table
+  // in the R32 layout (L2-resident) - the embedding kernel and its 1 KB per token of HBM writes and reads disappear.  The
+  // output still goes to res.
+  const float* res_tab;
+  const void* ids;       // [M] token ids, element type ids_dtype (2 = u8, 3 = i32, 4 = i64: clm_dtype)
+  int ids_dtype, vocab_rows;
   // write_xn: the output epilogue also emits xn = (out - mean) * rstd as bf16 [B][T][256] (tmXN, 3-D {col, t, b}):
   // the next consumer's LayerNorm (affine folded into its weights) without another pass over the residual.
   int write_xn;
@@ -418,10 +424,20 @@ block_mlp_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
     const bool tr = trace && warp == EPI_WARP0 && lane == 0;
     uint32_t it = 0;
     float4 rs[32];
+    const float* const res_in = p.res_tab ? p.res_tab : p.res;
+    // row of the residual INPUT: the row itself, or (block 0) the token id's row of the embedding table
+    auto src_row = [&](long long row, bool ok) -> long long {
+      if (!p.res_tab || !ok) return row;
+      long long id;
+      if (p.ids_dtype == 2) id = reinterpret_cast<const uint8_t*>(p.ids)[row];
+      else if (p.ids_dtype == 3) id = reinterpret_cast<const int32_t*>(p.ids)[row];
+      else id = reinterpret_cast<const long long*>(p.ids)[row];
+      return (id < 0 || id >= p.vocab_rows) ? 0 : id;   // out-of-range ids are flagged by embed_in_kernel; same substitution
+    };
     auto load_res = [&](long long lrow, bool ok, auto j0_, auto j1_) {
 #pragma unroll
       for (int j = decltype(j0_)::value; j < decltype(j1_)::value; ++j)
-        rs[j] = ok ? *reinterpret_cast<const float4*>(p.res + ptx::r32_off(lrow, hf * 128 + 4 * j))
+        rs[j] = ok ? *reinterpret_cast<const float4*>(res_in + ptx::r32_off(lrow, hf * 128 + 4 * j))
                    : make_float4(0.f, 0.f, 0.f, 0.f);
     };
     // (lo, n) become constants once the calling loop is fully unrolled, so rs[] stays in registers
@@ -429,7 +445,7 @@ block_mlp_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
 #pragma unroll
       for (int j = 0; j < 32; ++j)
         if (j >= lo && j < lo + n)
-          rs[j] = ok ? *reinterpret_cast<const float4*>(p.res + ptx::r32_off(lrow, hf * 128 + 4 * j))
+          rs[j] = ok ? *reinterpret_cast<const float4*>(res_in + ptx::r32_off(lrow, hf * 128 + 4 * j))
                      : make_float4(0.f, 0.f, 0.f, 0.f);
     };
     // residual / xn row of this thread in `tile`
@@ -456,7 +472,7 @@ block_mlp_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
       long long row0;
       bool ok0;
       tile_row((int)blockIdx.x, row0, ok0);
-      load_res(row0, ok0, I0{}, IE{});
+      load_res(src_row(row0, ok0), ok0, I0{}, IE{});
     }
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
       const uint32_t tph = it & 1;
@@ -468,10 +484,12 @@ block_mlp_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
       long long pf_row = 0;
       bool pf_ok = false;
       if (tile + (int)gridDim.x < p.num_tiles) tile_row(tile + (int)gridDim.x, pf_row, pf_ok);
+      // from here on pf_row is the SOURCE row of the next tile's residual (the id load is issued a whole tile before its use)
+      pf_row = src_row(pf_row, pf_ok);
       // ------------------------------------------------ E1: r1, LayerNorm2 -> xn (TMEM)
       // The residual half-row (128 fp32) is fetched into registers BEFORE waiting for the
       // out_proj accumulator, so its DRAM latency hides behind the y-tile load and G1.
-      load_res(row, row_ok, IE{}, I32{});
+      if (IE::value < 32) load_res(src_row(row, row_ok), row_ok, IE{}, I32{});
       ptx::mbar_wait(g1_done, tph);
       ptx::tc_fence_after_sync();
       if (tr) stamp(2);
@@ -540,7 +558,7 @@ block_mlp_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
         ptx::tc_fence_before_sync();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(hacc_free);   // the accumulator is in registers: fc1 of the next chunk may start
-        if (j < 4 && pf_ok) {
+        if (j < 4 && pf_ok && !p.res_tab) {
           // next tile's residual half-row (512 B per thread, 32 float4 at 512 B stride): pull 8 of them towards L2 per
           // chunk so that E1 of the next tile does not start with a 19 MB chip-wide HBM burst
 #pragma unroll

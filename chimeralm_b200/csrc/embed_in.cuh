@@ -57,7 +57,14 @@ struct EmbedInParams {
   __nv_bfloat16* x0;      // [B][256][Tp]
   void* vx;               // [B][256][Tp] bf16, or fp16 when vx_f16
   int B, T, Tp, vx_f16, rows;
+  int* err;               // bit 0 raised for an id outside [0, rows) (the embedding kernel's check, when that kernel is not run)
 };
+
+// E [rows][256] -> the first 32-row group of an R32 residual buffer (rows >= `rows` zero): block_mlp's table for block 0
+__global__ void __launch_bounds__(256) embed_r32_table_kernel(const float* __restrict__ E, float* __restrict__ out, int rows) {
+  const int v = blockIdx.x, col = threadIdx.x;
+  out[ptx::r32_off(v, col)] = v < rows ? E[v * ei::D + col] : 0.f;
+}
 
 __device__ __forceinline__ float lds_f32(uint32_t addr) {
   float v;
@@ -98,7 +105,10 @@ __global__ void __launch_bounds__(ei::THREADS) embed_in_kernel(EmbedInParams p) 
     if (t < 0) v = NV;                                   // before the read: the zero slot
     else if (t < p.T) {
       v = (long long)row[t];
-      if (v < 0 || v >= p.rows) v = 0;                   // flagged by the embedding kernel; same substitution here
+      if (v < 0 || v >= p.rows) {                        // nn.Embedding would raise: flag it, substitute row 0
+        if (p.err && blockIdx.y == 0 && k >= 2) atomicOr(p.err, 1);
+        v = 0;
+      }
     }
     ia[k] = su0 + (uint32_t)v * 4u;
   }
