@@ -46,7 +46,10 @@ from chimeralm_b200 import synth  # noqa: E402
 READ_LEN = 8192          # K2: fixed 8 kb reads
 BATCH = 32               # K2: batch 32
 N_DISTINCT = 8           # distinct synthetic batches rotated through the timed region
-F_TOK = 6_423_040        # dense FLOP/token
+F_TOK = 6_423_040        # dense FLOP/token of the reference's graph
+# ... of which block 0's in_proj (2 x 256 x 768) is NOT executed as a GEMM here: its input is one of 16 embedding rows, so the
+# product is a table lookup (csrc/embed_in.cuh).  The dense_tensor_* figures count executed tensor work only.
+F_TOK_EXEC = F_TOK - 2 * 256 * 768
 CONV_BYTES_TOK_LAYER = 1536  # long-conv algorithmic bytes/token/layer (vx in, x0 in, y*x0 out; 2 B each x 256 channels)
 K3_TOKEN_CAP = BATCH * (READ_LEN + 1)   # padded tokens per bucketed batch: the K2 step's size
 K3_MAX_READS = 256
@@ -409,7 +412,7 @@ def run_k5(args, eng, D, sampler):
             "reads_per_s": reads_s, "bases_per_s": reads_s * L, "tokens_per_s": reads_s * T, "ms_per_step": ms_max / args.k5_steps,
             "ms_per_rank": [r[0] for r in per_rank],
             "e2e_reads_per_s": D.world * B / (max(r[1] for r in per_rank) / 1e3),
-            "dense_tensor_frac_of_burst_peak": F_TOK * reads_s / D.world * T / 1e12 / peaks()["tflops_burst"],
+            "dense_tensor_frac_of_burst_peak": F_TOK_EXEC * reads_s / D.world * T / 1e12 / peaks()["tflops_burst"],
             "longconv_kernel": eng.longconv_variant(T),
             "kernel_ms_per_step": {k: v[0] / 2 for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])}}
 
@@ -488,7 +491,7 @@ def run_k3(args, eng, D, sampler):
             "tokens_per_rank": tokens, "reads_per_rank": [r[3] for r in per_rank],
             "token_imbalance_max_over_mean": max(tokens) / (sum(tokens) / len(tokens)),
             "cost_imbalance_max_over_mean": max(r[6] for r in per_rank) / (sum(r[6] for r in per_rank) / len(per_rank)),
-            "dense_tensor_frac_of_burst_peak": F_TOK * sum(tokens) / D.world / (ms_max / 1e3) / 1e12 / peaks()["tflops_burst"]}
+            "dense_tensor_frac_of_burst_peak": F_TOK_EXEC * sum(tokens) / D.world / (ms_max / 1e3) / 1e12 / peaks()["tflops_burst"]}
 
 
 def run_label_agreement(device):
@@ -635,6 +638,7 @@ def main():
                     "block_mlp": 2 * 256 * 256 + 2 * 256 * 1024 + 2 * 1024 * 256}
     bytes_per_tok = {"longconv": CONV_BYTES_TOK_LAYER, "layernorm": 1024 + 512, "shortconv_gate": 1536 + 1024,
                      "transpose": 1024, "pool": 516, "embed": 1 + 1024 + 512, "encode": 2, "head": 0,
+                     "embed_in": 1 + 1024,   # block 0's first half by table lookup: 1 id byte in, x0 + v*x1 (2 x 256 x 2 B) out
                      "gemm_score": 512}   # fused scorer + pooling: the normalised tokens are read once (bf16)
     traffic, traffic_src = {}, None
     for name in ("r2_traffic.json", "r1_traffic.json"):
@@ -661,7 +665,7 @@ def main():
     roof["peak_source"] = pk["src"] + ("; burst bf16 figure: the timed region is a fraction of a second, not a power-capped long step"
                                        if roof["bound"] == "tensor" else "")
     roof["traffic_source"] = traffic_src
-    rooflines = {k: roofline_of(k, v[0], v[1]) for k, v in prof.items() if k in ("longconv", "block_mlp", "block_in", "gemm_score")}
+    rooflines = {k: roofline_of(k, v[0], v[1]) for k, v in prof.items() if k in ("longconv", "block_mlp", "block_in", "gemm_score", "embed_in")}
     if "longconv" in rooflines and conv_variant == "fft_tensor_core":
         # Monarch FFT on tcgen05 (csrc/longconv_tc2.cuh, two items in flight per SM): per item (one channel of two reads) 16
         # MMAs 128x128x16 (step 1) + 2 x 32 MMAs 128x128x16 (steps 3, 5 as N = 128 halves) + 32 MMAs 128x64x16 (step 7; the
@@ -670,7 +674,7 @@ def main():
         item_flop = 2 * 16 * (16 * 128 * 128 + 2 * 32 * 128 * 128 + 32 * 128 * 64)
         sec = rooflines["longconv"]["avg_launch_ms"] / 1e3
         rooflines["longconv"]["tensor_pipe_executed_tflops"] = item_flop * 256 * ((B + 1) // 2) / sec / 1e12
-    dense_tflops = F_TOK * (reads_per_s / world) * T / 1e12
+    dense_tflops = (F_TOK_EXEC if "embed_in" in prof else F_TOK) * (reads_per_s / world) * T / 1e12
 
     cpu = None
     if args.cpu_sample > 0:
@@ -695,6 +699,8 @@ def main():
         "dense_tensor_tflops_per_gpu": dense_tflops,
         "dense_tensor_frac_of_burst_peak": dense_tflops / pk["tflops_burst"],
         "dense_tensor_frac_of_sustained_peak": dense_tflops / pk["tflops_sustained"],
+        "dense_tensor_note": "executed tensor-core FLOPs only: block 0's in_proj is a lookup over the 16 token ids (embed_in), "
+                             "so 393 216 of the graph's 6 423 040 FLOP/token are not counted",
         "e2e": {"value": world * B * args.steps / e2e_s, "unit": "reads/s", "h2d_bytes_per_step": B * L + (B + 1) * 8,
                 "d2h_bytes_per_step": B * 2 * 4 + B,
                 "api": "clm_predict_host_submit / clm_predict_host_wait (C-ABI, pinned host buffers, up to 3 batches in flight)",

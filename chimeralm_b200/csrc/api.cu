@@ -177,6 +177,7 @@ struct clm_ctx {
   bool tc_pipe_chunked = true;   // reads longer than 8 200 tokens on the two-in-flight kernel (V-form tables, no carry)
   __half* tc_S = nullptr; // shared-memory image of the DFT constant stack (longconv_tc)
   bool fused_head = true;         // pooling merge + classifier layers in one cooperative launch
+  bool head_coop = true;          // 0: plain launch of the same kernel (A/B of the cooperative launch's own cost; <= 256 CTAs of 64 KB)
   unsigned int* head_counter = nullptr;
   unsigned int head_base = 0;
   bool fused_score_pool = true;   // scorer GEMM + pooling partials in one persistent kernel (needs the folded tail)
@@ -864,10 +865,10 @@ int launch_longconv_tc(clm_ctx* c, int layer, const __half* vx, const __nv_bfloa
 int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
 enum ProfCat { PC_ENCODE = 0, PC_EMBED, PC_LN, PC_GEMM_IN, PC_SHORTCONV, PC_LONGCONV, PC_TRANSPOSE, PC_GEMM_OUT,
-               PC_GEMM_FC1, PC_GEMM_FC2, PC_SCORE, PC_POOL, PC_HEAD, PC_BLOCK_MLP, PC_BLOCK_IN, PC_COUNT };
+               PC_GEMM_FC1, PC_GEMM_FC2, PC_SCORE, PC_POOL, PC_HEAD, PC_BLOCK_MLP, PC_BLOCK_IN, PC_EMBED_IN, PC_COUNT };
 const char* kProfNames[PC_COUNT] = {"encode", "embed", "layernorm", "gemm_in_proj", "shortconv_gate", "longconv",
                                     "transpose", "gemm_out_proj", "gemm_fc1", "gemm_fc2", "gemm_score", "pool",
-                                    "head", "block_mlp", "block_in"};
+                                    "head", "block_mlp", "block_in", "embed_in"};
 
 struct ProfScope {
   clm_ctx* c;
@@ -1414,7 +1415,7 @@ int clm_forward(clm_ctx* c, const void* d_ids, int ids_dtype, int B, int T, floa
         layernorm_bf16_kernel<<<rows32, 256, 0, st>>>(c->R, c->ones, c->zeros, c->XN, M, g.layer_norm_eps);
         CLM_LAUNCH_CHECK(c, "normalize");
       }
-      ProfScope ps_(c, PC_BLOCK_IN, st);
+      ProfScope ps_(c, (l == 0 && ei0) ? PC_EMBED_IN : PC_BLOCK_IN, st);
       use_tc = tc_conv_applies(c, T);
       if (l == 0 && ei0) rc = launch_embed_in(c, d_ids, ids_dtype, B, T, Tp, c->VX, c->X0, st, use_tc);
       else rc = launch_block_in(c, l, c->XN, B, T, Tp, c->VX, c->X0, st, nullptr, use_tc);
@@ -1548,7 +1549,8 @@ int clm_forward(clm_ctx* c, const void* d_ids, int ids_dtype, int B, int T, floa
       void* args[] = {&hf};
       constexpr size_t head_smem = (size_t)HEAD_BT * 512 * sizeof(float);
       if (int rc_attr = ensure_smem_attr(c, (const void*)(head_fused_kernel), (int)((int)head_smem))) return rc_attr;
-      CLM_CUDA(c, cudaLaunchCooperativeKernel((const void*)head_fused_kernel, grid, dim3(256), args, head_smem, st));
+      if (c->head_coop) CLM_CUDA(c, cudaLaunchCooperativeKernel((const void*)head_fused_kernel, grid, dim3(256), args, head_smem, st));
+      else head_fused_kernel<<<grid, 256, head_smem, st>>>(hf);
       CLM_LAUNCH_CHECK(c, "head_fused");
       // five grid barriers + one final arrival per CTA and launch; the device counter is never reset.  Advanced only once
       // the launch was accepted: a rejected launch must not move the host's idea of the counter ahead of the device's.
@@ -1693,6 +1695,7 @@ int clm_set_option(clm_ctx* c, const char* name, int value) {
   else if (n == "tc_pipe_chunked") c->tc_pipe_chunked = value != 0;
   else if (n == "fused_score_pool") c->fused_score_pool = value != 0;
   else if (n == "fused_head") c->fused_head = value != 0;
+  else if (n == "head_coop") c->head_coop = value != 0;
   else if (n == "mlp_stagger") c->mlp_stagger = value;
   else if (n == "y_channel_major") c->y_channel_major = value != 0;
   else if (n == "mlp_grid") c->mlp_grid = value;

@@ -475,25 +475,42 @@ constexpr int HEAD_BT = 32;   // reads per shared-memory tile of the layer input
 
 // One layer for output neuron o (one warp), all reads: the layer input is staged in shared memory tile by tile (every warp of
 // the CTA needs all of it; from global memory each warp would pull B x IN floats through L2 again).
-template <int IN, bool GELU, bool SKIP>
-__device__ __forceinline__ void head_fused_layer(const float* __restrict__ W, const float* __restrict__ bias, const float* x,
-                                                 const float* skip, float* y, int o, int OUT, int b_lo, int B, float* xs) {
+// weight row and bias of output neuron o: loaded BEFORE the grid barrier in front of the layer (they do not depend on it), so
+// the L2 round trip overlaps the barrier instead of following it
+template <int IN>
+__device__ __forceinline__ void head_load_w(const float* __restrict__ W, const float* __restrict__ bias, int o, int OUT,
+                                            float4 (&w)[4], float& bo) {
   const int lane = threadIdx.x & 31;
-  constexpr int V = IN / 128;
-  float4 w[V];
-  float bo = 0.f;
+  bo = 0.f;
   if (o < OUT) {
 #pragma unroll
-    for (int v = 0; v < V; ++v) w[v] = __ldg(reinterpret_cast<const float4*>(W + (long long)o * IN) + lane + 32 * v);
+    for (int v = 0; v < IN / 128; ++v) w[v] = __ldg(reinterpret_cast<const float4*>(W + (long long)o * IN) + lane + 32 * v);
     bo = __ldg(bias + o);
   }
+}
+
+template <int IN, bool GELU, bool SKIP>
+__device__ __forceinline__ uint32_t head_fused_layer(const float4 (&w)[4], float bo, const float* x,
+                                                 const float* skip, float* y, int o, int OUT, int b_lo, int B, float* xs,
+                                                 uint64_t* bar, uint32_t phase) {
+  const int lane = threadIdx.x & 31;
+  constexpr int V = IN / 128;
   for (int b0 = b_lo; b0 < B; b0 += HEAD_BT) {   // this CTA's reads [b_lo, B)
     const int nb = min(HEAD_BT, B - b0);
     __syncthreads();   // previous tile fully consumed
-    for (int i = threadIdx.x; i < nb * (IN / 4); i += blockDim.x)
-      reinterpret_cast<float4*>(xs)[i] = reinterpret_cast<const float4*>(x + (long long)b0 * IN)[i];   // coherent load
-    __syncthreads();
+    // One bulk copy (<= 64 KB) by the TMA engine instead of 64 dependent 16-byte loads per thread: the staging was ~5 us of
+    // each layer's ~15.  The rows were written by other CTAs before the grid barrier (generic proxy, fenced there); the
+    // proxy fence orders this thread's acquire of that barrier before the async-proxy read.
+    if (threadIdx.x == 0) {
+      ptx::fence_proxy_async_all();
+      ptx::mbar_expect_tx(bar, (uint32_t)(nb * IN * 4));
+      ptx::bulk_load_1d(xs, x + (long long)b0 * IN, (uint32_t)(nb * IN * 4), bar);
+    }
+    ptx::mbar_wait(bar, phase & 1);
+    ++phase;
     if (o < OUT) {
+      static_assert(HEAD_BT == 32, "one read of the tile per lane in the layer epilogue");
+      float mine = 0.f;   // lane b keeps read b's dot product: bias, GELU, skip and the store then run once, 32 reads wide
 #pragma unroll 4
       for (int b = 0; b < nb; ++b) {
         float a = 0.f;
@@ -503,15 +520,17 @@ __device__ __forceinline__ void head_fused_layer(const float* __restrict__ W, co
           a += w[v].x * xv.x + w[v].y * xv.y + w[v].z * xv.z + w[v].w * xv.w;
         }
         for (int s2 = 16; s2 > 0; s2 >>= 1) a += __shfl_xor_sync(0xffffffffu, a, s2);
-        if (lane == 0) {
-          a += bo;
-          if (GELU) a = gelu_erf_h(a);
-          if (SKIP) a += skip[(long long)(b0 + b) * OUT + o];
-          y[(long long)(b0 + b) * OUT + o] = a;
-        }
+        if (b == lane) mine = a;
+      }
+      if (lane < nb) {
+        float a = mine + bo;
+        if (GELU) a = gelu_erf_h(a);
+        if (SKIP) a += skip[(long long)(b0 + lane) * OUT + o];
+        y[(long long)(b0 + lane) * OUT + o] = a;
       }
     }
   }
+  return phase;
 }
 
 __global__ void __launch_bounds__(256) head_fused_kernel(HeadFusedParams p) {
@@ -525,40 +544,72 @@ __global__ void __launch_bounds__(256) head_fused_kernel(HeadFusedParams p) {
   const unsigned int cta = blockIdx.y * gridDim.x + blockIdx.x;
   const int per = ((p.B + (int)gridDim.y - 1) / (int)gridDim.y + HEAD_BT - 1) / HEAD_BT * HEAD_BT;   // reads per slice, whole tiles
   const int b_lo = (int)blockIdx.y * per, b_hi = min(p.B, b_lo + per);
-  // phase 0: merge the pooling partials of each read (pool_merge_kernel)
+  __shared__ uint64_t head_bar;
+  uint32_t phase = 0;
+  if (threadIdx.x == 0) {
+    ptx::mbar_init(&head_bar, 1);
+    ptx::fence_mbar_init();
+  }
+  // phase 0: merge the pooling partials of each read (pool_merge_kernel).  The per-slice maxima and sums are staged in
+  // shared memory first, so that the long loop over slices carries only independent loads (the sums are accumulated in the
+  // same order as before: bit-identical results)
   for (int b = cta; b < p.B; b += G) {
     const int d = threadIdx.x;
     const float* pp = p.part + (long long)b * p.n_split * (2 + D);
     if (p.pool_mode == 2) {   // max pooling: the partials hold per-tile maxima
       float mx = -INFINITY;
-      for (int s = 0; s < p.n_split; ++s)
-        if (pp[s * (2 + D) + 1] > 0.f) mx = fmaxf(mx, pp[s * (2 + D) + 2 + d]);
+#pragma unroll 8
+      for (int s = 0; s < p.n_split; ++s) {
+        const float cnt = pp[s * (2 + D) + 1], v = pp[s * (2 + D) + 2 + d];
+        if (cnt > 0.f) mx = fmaxf(mx, v);
+      }
       p.pooled[(long long)b * D + d] = mx;
       continue;
     }
+    float* s_m = head_xs;                 // [n_split] slice maxima, then the factors exp(m_s - M)
+    float* s_l = head_xs + p.n_split;     // [n_split] slice sums
+    __syncthreads();
+    for (int s = threadIdx.x; s < p.n_split; s += blockDim.x) {
+      s_m[s] = pp[s * (2 + D)];
+      s_l[s] = pp[s * (2 + D) + 1];
+    }
+    __syncthreads();
     float M = -INFINITY;
-    for (int s = 0; s < p.n_split; ++s) M = fmaxf(M, pp[s * (2 + D)]);
+    for (int s = 0; s < p.n_split; ++s) M = fmaxf(M, s_m[s]);
+    __syncthreads();
+    for (int s = threadIdx.x; s < p.n_split; s += blockDim.x) {
+      const float ms = s_m[s];
+      s_m[s] = (ms == -INFINITY) ? 0.f : __expf(ms - M);
+    }
+    __syncthreads();
     float a = 0.f, L = 0.f;
+#pragma unroll 8
     for (int s = 0; s < p.n_split; ++s) {
-      const float ms = pp[s * (2 + D)];
-      const float f = (ms == -INFINITY) ? 0.f : __expf(ms - M);
+      const float f = s_m[s];
       a += pp[s * (2 + D) + 2 + d] * f;
-      L += pp[s * (2 + D) + 1] * f;
+      L += s_l[s] * f;
     }
     p.pooled[(long long)b * D + d] = a / L;
   }
-  grid_barrier(p.counter, p.base + 1 * G);
   const int o = blockIdx.x * 8 + warp;   // gridDim.x * 8 == H
-  head_fused_layer<D, true, false>(p.w0, p.b0, p.pooled, nullptr, p.h0, o, H, b_lo, b_hi, head_xs);
+  float4 w[4];
+  float bo;
+  head_load_w<D>(p.w0, p.b0, o, H, w, bo);
+  grid_barrier(p.counter, p.base + 1 * G);
+  phase = head_fused_layer<D, true, false>(w, bo, p.pooled, nullptr, p.h0, o, H, b_lo, b_hi, head_xs, &head_bar, phase);
+  head_load_w<H>(p.w1, p.b1, o, H, w, bo);
   grid_barrier(p.counter, p.base + 2 * G);
-  head_fused_layer<H, true, false>(p.w1, p.b1, p.h0, nullptr, p.h1, o, H, b_lo, b_hi, head_xs);
+  phase = head_fused_layer<H, true, false>(w, bo, p.h0, nullptr, p.h1, o, H, b_lo, b_hi, head_xs, &head_bar, phase);
+  head_load_w<H>(p.wr0, p.br0, o, H, w, bo);
   grid_barrier(p.counter, p.base + 3 * G);
-  head_fused_layer<H, true, false>(p.wr0, p.br0, p.h1, nullptr, p.h2, o, H, b_lo, b_hi, head_xs);
+  phase = head_fused_layer<H, true, false>(w, bo, p.h1, nullptr, p.h2, o, H, b_lo, b_hi, head_xs, &head_bar, phase);
+  head_load_w<H>(p.wr1, p.br1, o, H, w, bo);
   grid_barrier(p.counter, p.base + 4 * G);
-  head_fused_layer<H, false, true>(p.wr1, p.br1, p.h2, p.h1, p.h3, o, H, b_lo, b_hi, head_xs);
+  phase = head_fused_layer<H, false, true>(w, bo, p.h2, p.h1, p.h3, o, H, b_lo, b_hi, head_xs, &head_bar, phase);
+  if (blockIdx.x == 0) head_load_w<H>(p.wo, p.bo, warp, 2, w, bo);
   grid_barrier(p.counter, p.base + 5 * G);
   if (blockIdx.x == 0) {   // output layer: one CTA per read slice
-    head_fused_layer<H, false, false>(p.wo, p.bo, p.h3, nullptr, p.logits, warp, 2, b_lo, b_hi, head_xs);
+    phase = head_fused_layer<H, false, false>(w, bo, p.h3, nullptr, p.logits, warp, 2, b_lo, b_hi, head_xs, &head_bar, phase);
     __syncthreads();
     if (p.labels && warp == 0)
       for (int b = b_lo + lane; b < b_hi; b += 32) p.labels[b] = (p.logits[b * 2 + 1] > p.logits[b * 2]) ? 1 : 0;   // ties -> 0
