@@ -196,6 +196,7 @@ struct clm_ctx {
   __nv_bfloat16* YG = nullptr;    // gathered tail columns of Y, channel-major [D][128 x gathered tiles]
   size_t yg_elems = 0;
   int mlp_store_a = 0;    // block_mlp: residual column groups stored in the statistics sweep of the output epilogue
+  bool in_ext_tail = true;   // block_in: a read's tail of <= 16 tokens rides on its last full tile (BlockInParams::ext_L)
   int in_prefetch = 0;    // block_in: next token tile prefetched into L2 (measured: no effect, 0.667 vs 0.665 ms/step interleaved)
   int mlp_early_res = 33; // block_mlp: float4 of the next tile's residual half-row loaded before E3 (0, 16, 32; 33 = spread over E3)
   int mlp_fc2_lag = 1;    // block_mlp: fc2 of chunk j - lag is issued after fc1 of chunk j (2: recorded experiment, no faster)
@@ -452,6 +453,19 @@ int launch_block_in(clm_ctx* c, int layer, const __nv_bfloat16* xn, int B, int T
   p.prefetch_xn = c->in_prefetch;
   p.tiles_per_seq = (T + bi::BT - 1) / bi::BT;
   p.num_tiles = B * p.tiles_per_seq;
+  CUtensorMap tmXNE = tmXN;
+#ifdef CLM_EXPERIMENTS
+  const bool ext_ok = !pair;
+#else
+  const bool ext_ok = true;
+#endif
+  if (ext_ok && c->in_ext_tail && T >= bi::BT && T % bi::BT >= 1 && T % bi::BT <= bi::EXT) {
+    // tails of 1..16 tokens ride on the read's last full tile (BlockInParams::ext_L) instead of being a tile of their own
+    if ((rc = make_tmap_xn(c, &tmXNE, xn, B, T, bi::NCOL_EXT))) return rc;
+    p.ext_L = T % bi::BT;
+    p.tiles_per_seq = T / bi::BT;
+    p.num_tiles = B * p.tiles_per_seq;
+  }
 #ifdef CLM_EXPERIMENTS
   if (pair) {   // CTA pairs (cta_group::2): one tile per pair, each CTA half of the channels and half of the token rows
     if (int rc_attr = ensure_smem_attr(c, (const void*)(block_in2_kernel), (int)(bi2::SMEM_TOTAL2))) return rc_attr;
@@ -462,7 +476,7 @@ int launch_block_in(clm_ctx* c, int layer, const __nv_bfloat16* xn, int B, int T
   }
 #endif
   const int grid = std::min(p.num_tiles, c->num_sms);
-  block_in_kernel<<<grid, bi::THREADS, bi::SMEM_TOTAL, st>>>(L.tm_inf, tmVX, tmX0, tmXN, p);
+  block_in_kernel<<<grid, bi::THREADS, bi::SMEM_TOTAL, st>>>(L.tm_inf, tmVX, tmX0, tmXN, tmXNE, p);
   CLM_LAUNCH_CHECK(c, "block_in");
   return 0;
 }
@@ -1718,6 +1732,7 @@ int clm_set_option(clm_ctx* c, const char* name, int value) {
   else if (n == "embed_res") c->embed_res = value != 0;
   else if (n == "mlp_gather_tails") c->mlp_gather_tails = value != 0;
   else if (n == "in_prefetch") c->in_prefetch = value;
+  else if (n == "in_ext_tail") c->in_ext_tail = value != 0;
   else return fail(c, CLM_ERR_INVALID, "clm_set_option: unknown option '%s'", name);
   return 0;
 }

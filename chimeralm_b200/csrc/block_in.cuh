@@ -47,12 +47,19 @@ struct BlockInParams {
                           // fp16 intermediate of the tensor-core FFT in range for weights of any magnitude (longconv_tc.cuh)
   long long* trace;     // optional [2][64] clock64 stamps of CTA 0 (row 0 = MMA issuer, row 1 = epilogue warp 2)
   int prefetch_xn;      // 1: the producer prefetches the next token tile into L2 (option in_prefetch)
+  // ext_L > 0 (reads of 128 f + L tokens, 1 <= L <= 16): tiles_per_seq = f and the LAST tile of every read also computes the
+  // L tail tokens - N = 160 token columns instead of 144, 16 more output columns for the second token half's warps, one more
+  // store round that also zero-fills the rest of the read's last 128-token row.  The tail would otherwise be a tile of its
+  // own that streams the same 384 KB of weights for L tokens (K2's 8 193-token reads: 2 080 tiles = 15 waves for 14 of work).
+  int ext_L;
 };
 
 namespace bi {
 constexpr int D = 256, BT = 128, HALO = 16, NCOL = BT + HALO;   // 144 token columns per tile
+constexpr int EXT = 16, NCOL_EXT = NCOL + EXT;                  // 160 columns in a read's last tile when it carries the tail (ext_L)
 constexpr int KB_ROWS_BYTES = NCOL * 128;                       // one k-block of xn: 144 rows x 128 B
-constexpr int XN_BYTES = 4 * KB_ROWS_BYTES;                     // 73728
+constexpr int KB_ROWS_BYTES_EXT = NCOL_EXT * 128;               // ... 160 rows
+constexpr int XN_BYTES = 4 * KB_ROWS_BYTES_EXT;                 // 81920 (room for the extended tile)
 constexpr int SLOT_BYTES = 2 * 128 * 64 * 2;                    // 32 KB: two k-blocks of [128 channels x 64 k], ONE TMA box
 constexpr int NSLOT = 3;                                        // ring depth x 32 KB is what hides the TMA latency: with 2 slots
                                                                 // (one of look-ahead) a pass took 4.4-5.9 K cycles to issue 3.5 K of MMAs
@@ -63,7 +70,7 @@ constexpr int OFF_STAGE = OFF_W + NSLOT * SLOT_BYTES;           // 139264
 constexpr int OFF_BAR = OFF_STAGE + 2 * STAGE_BOX;              // staging: ONE tensor at a time (x0, then v * x1), two token halves
 constexpr int SMEM_TOTAL = OFF_BAR + 256;
 constexpr int THREADS = 320, EPI_THREADS = 256;
-constexpr int GCOLS = NCOL;                                     // TMEM columns per channel group
+constexpr int GCOLS = NCOL_EXT;                                 // TMEM columns per channel group (3 x 160 <= 512)
 }  // namespace bi
 
 __device__ __forceinline__ void tmem_ld_32x32b_x2(uint32_t taddr, uint32_t& a, uint32_t& b) {
@@ -72,7 +79,8 @@ __device__ __forceinline__ void tmem_ld_32x32b_x2(uint32_t taddr, uint32_t& a, u
 
 __global__ void __launch_bounds__(bi::THREADS, 1)
 block_in_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmVX,
-                const __grid_constant__ CUtensorMap tmX0, const __grid_constant__ CUtensorMap tmXN, BlockInParams p) {
+                const __grid_constant__ CUtensorMap tmX0, const __grid_constant__ CUtensorMap tmXN,
+                const __grid_constant__ CUtensorMap tmXNE, BlockInParams p) {
   using namespace bi;
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((ptx::smem_u32(smem) & 1023u) != 0) __trap();
@@ -96,6 +104,7 @@ block_in_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmW); ptx::prefetch_tmap(&tmVX); ptx::prefetch_tmap(&tmX0); ptx::prefetch_tmap(&tmXN);
+    ptx::prefetch_tmap(&tmXNE);
     for (int i = 0; i < NSLOT; ++i) { ptx::mbar_init(&w_full[i], 1); ptx::mbar_init(&w_empty[i], 1); }
     ptx::mbar_init(xn_full, 1); ptx::mbar_init(xn_free, 1);
     for (int i = 0; i < 2; ++i) { ptx::mbar_init(&acc_full[i], 1); ptx::mbar_init(&acc_free[i], 8); }
@@ -118,9 +127,11 @@ block_in_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
         {  // B operand: normalised tokens [t0 - 16, t0 + 128) of read b, 4 k-blocks of [144 rows x 64]; rows
            // outside [0, T) are zero-filled by TMA (their products are discarded by the epilogue)
           const int b = tile / p.tiles_per_seq, t0 = (tile % p.tiles_per_seq) * BT;
+          const bool ext = p.ext_L > 0 && (tile % p.tiles_per_seq) == p.tiles_per_seq - 1;   // 160-row box (tmXNE)
+          const int kbb = ext ? KB_ROWS_BYTES_EXT : KB_ROWS_BYTES;
           ptx::mbar_wait(xn_free, (it & 1) ^ 1);
-          ptx::mbar_expect_tx(xn_full, XN_BYTES);
-          for (int kb = 0; kb < 4; ++kb) ptx::tma_load_3d(smem + OFF_XN + kb * KB_ROWS_BYTES, &tmXN, xn_full, kb * 64, t0 - HALO, b);
+          ptx::mbar_expect_tx(xn_full, 4 * kbb);
+          for (int kb = 0; kb < 4; ++kb) ptx::tma_load_3d(smem + OFF_XN + kb * kbb, ext ? &tmXNE : &tmXN, xn_full, kb * 64, t0 - HALO, b);
           // The token tile is single-buffered (72 KB next to the weight ring), so this load is issued only when the previous
           // tile's MMAs are done and its 3.5-4 K cycles were fully exposed (profiles/r2_trace_block_in.txt) - most of it HBM
           // time for activations the previous kernel wrote.  Ask for the NEXT tile now: by the time it is loaded it sits in L2.
@@ -146,13 +157,16 @@ block_in_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
   } else if (warp == 1) {
     // =========================== MMA issuer ===========================
     {   // whole warp, uniform control flow; one elected lane issues (ptx::umma_f16_e)
-      constexpr uint32_t idesc = ptx::idesc_bf16_f32(128, NCOL);
+      constexpr uint32_t idesc_n = ptx::idesc_bf16_f32(128, NCOL), idesc_e = ptx::idesc_bf16_f32(128, NCOL_EXT);
       const uint32_t sXN = ptx::smem_u32(smem + OFF_XN), sW = ptx::smem_u32(smem + OFF_W);
       uint32_t wi = 0, it = 0, pass = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
         stamp(0);
         ptx::mbar_wait(xn_full, it & 1);
         stamp(0);
+        const bool ext = p.ext_L > 0 && (tile % p.tiles_per_seq) == p.tiles_per_seq - 1;
+        const uint32_t idesc = ext ? idesc_e : idesc_n;
+        const uint32_t kbb = ext ? KB_ROWS_BYTES_EXT : KB_ROWS_BYTES;
         for (int h = 0; h < 2; ++h, ++pass) {
           for (int g = 0; g < 3; ++g) {
             if (g < 2) {   // g == 0 starts set A, g == 1 starts set B
@@ -168,7 +182,7 @@ block_in_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
               for (int q2 = 0; q2 < 2; ++q2) {
                 const int kb = 2 * kp + q2;
                 const uint64_t da = ptx::smem_desc_k_sw128(sW + s * SLOT_BYTES + q2 * (SLOT_BYTES / 2));
-                const uint64_t db = ptx::smem_desc_k_sw128(sXN + kb * KB_ROWS_BYTES);
+                const uint64_t db = ptx::smem_desc_k_sw128(sXN + kb * kbb);
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
                   ptx::umma_f16_e(tmem_base + g * GCOLS, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
@@ -214,6 +228,7 @@ block_in_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
       const int b = tile / p.tiles_per_seq;
       const int t0 = (tile % p.tiles_per_seq) * BT;
+      const bool ext = p.ext_L > 0 && (tile % p.tiles_per_seq) == p.tiles_per_seq - 1;   // this tile also carries the read's tail
       const bool tr = trace && warp == 2 && lane == 0;
       if (tr) stamp(1);
       // ------------------------------------------------ two passes of conv + gate epilogue
@@ -260,6 +275,68 @@ block_in_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
           hm2[g] = um2;
           hm1[g] = um1;
         };
+        // the 16 extra columns [144, 160) of an extended tile: they follow the second token half's last sub-block, so its
+        // warps carry on with their filter state; tokens past the end of the read come out as ZERO
+        auto conv_ext = [&](int g, float (&out)[EXT]) {
+          uint32_t a[8], c8[8];
+          ptx::tmem_ld_32x32b_x8(lane_addr + g * GCOLS + NCOL, a);
+          ptx::tmem_ld_32x32b_x8(lane_addr + g * GCOLS + NCOL + 8, c8);
+          ptx::tmem_ld_wait();
+          float um2 = hm2[g], um1 = hm1[g];
+#pragma unroll
+          for (int j = 0; j < EXT; ++j) {
+            const float u = __uint_as_float(j < 8 ? a[j] : c8[j - 8]) + bia[g];
+            out[j] = fmaf(w0[g], um2, fmaf(w1[g], um1, fmaf(w2[g], u, cbv[g])));
+            um2 = um1;
+            um1 = u;
+          }
+        };
+        // store round of an extended tile: tokens [t0 + 128, t0 + 256) = the read's last 128-token row.  The second half's
+        // warps filter and stage the 16 tail columns (zeros from ext_L on) and zeros up to 64, the first half's warps the
+        // all-zero second box.  The tail columns are read from TMEM HERE, after the tile's main store was issued - the values
+        // live in registers only inside this round; the accumulator set is released to the next pass afterwards (one short
+        // tensor-pipe stall per pass of a read's last tile, 32 of K2's 2 048 tiles).
+        auto store_ext = [&](int which) {   // 0: x0 (set A), 1: v * x1 (set B)
+          float val[EXT];
+          if (hf == 1) {
+            if (which == 0) {
+              conv_ext(0, val);
+            } else {
+              float x1e[EXT];
+              conv_ext(1, x1e);
+              conv_ext(2, val);
+#pragma unroll
+              for (int j = 0; j < EXT; ++j) val[j] *= x1e[j];
+            }
+          }
+          ptx::tc_fence_before_sync();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&acc_free[which]);
+          const bool as_f16 = which == 1 && p.vx_f16;
+          if (issuer) ptx::tma_store_wait_read<0>();
+          ptx::bar_sync(1, EPI_THREADS);
+          const uint32_t rowaddr = sST + hf * STAGE_BOX + rowoff;   // hf 1 -> box 1 (tail + zeros), hf 0 -> box 0 (zeros)
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            uint32_t q0 = 0, q1 = 0, q2 = 0, q3 = 0;
+            if (hf == 1 && k < 2) {
+              float m[8];
+#pragma unroll
+              for (int e8 = 0; e8 < 8; ++e8) m[e8] = (k * 8 + e8 < p.ext_L) ? val[k * 8 + e8] : 0.f;
+              if (as_f16) { q0 = pack_f16(m[0], m[1]); q1 = pack_f16(m[2], m[3]); q2 = pack_f16(m[4], m[5]); q3 = pack_f16(m[6], m[7]); }
+              else { q0 = pack_bf16(m[0], m[1]); q1 = pack_bf16(m[2], m[3]); q2 = pack_bf16(m[4], m[5]); q3 = pack_bf16(m[6], m[7]); }
+            }
+            ptx::st_shared_v4(rowaddr + ((uint32_t(k) ^ swz) << 4), q0, q1, q2, q3);
+          }
+          ptx::fence_proxy_async_smem();
+          ptx::bar_sync(2, EPI_THREADS);
+          if (issuer) {
+            const CUtensorMap* tm = which == 0 ? &tmX0 : &tmVX;
+            ptx::tma_store_3d(tm, smem + OFF_STAGE + STAGE_BOX, t0 + BT, h * 128, b);   // staged by the hf == 1 warps
+            ptx::tma_store_3d(tm, smem + OFF_STAGE, t0 + BT + 64, h * 128, b);         // zeros
+            ptx::tma_store_commit();
+          }
+        };
         // ---- set A: x0
         ptx::mbar_wait(&acc_full[0], pass & 1);
         ptx::tc_fence_after_sync();
@@ -269,7 +346,7 @@ block_in_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
         for (int s = 0; s < 2; ++s) {
           float x0v[32];
           conv_sub(0, s, x0v);
-          if (s == 1) {                      // set A is in registers: the next pass may overwrite it
+          if (s == 1 && !ext) {              // set A is in registers: the next pass may overwrite it
             ptx::tc_fence_before_sync();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(&acc_free[0]);
@@ -290,6 +367,7 @@ block_in_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
           for (int hh = 0; hh < 2; ++hh) ptx::tma_store_3d(&tmX0, smem + OFF_STAGE + hh * STAGE_BOX, t0 + hh * 64, h * 128, b);
           ptx::tma_store_commit();
         }
+        if (ext) store_ext(0);
         // ---- set B: v * x1
         ptx::mbar_wait(&acc_full[1], pass & 1);
         ptx::tc_fence_after_sync();
@@ -301,7 +379,7 @@ block_in_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
           float x1v[32], vv[32];
           conv_sub(1, s, x1v);
           conv_sub(2, s, vv);
-          if (s == 1) {
+          if (s == 1 && !ext) {
             ptx::tc_fence_before_sync();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(&acc_free[1]);
@@ -338,6 +416,7 @@ block_in_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
           for (int hh = 0; hh < 2; ++hh) ptx::tma_store_3d(&tmVX, smem + OFF_STAGE + hh * STAGE_BOX, t0 + hh * 64, h * 128, b);
           ptx::tma_store_commit();
         }
+        if (ext) store_ext(1);
         if (tr) stamp(1);
       }
     }

@@ -279,9 +279,10 @@ def test_block_mlp_fused(engine, state_dict, M):
     assert err <= 2e-2, (M, err)
 
 
-@pytest.mark.parametrize("B,T", [(1, 70), (2, 300), (3, 1025), (2, 8193)])
+@pytest.mark.parametrize("B,T", [(1, 70), (2, 300), (3, 1025), (2, 8193), (2, 272), (3, 140), (2, 8200), (2, 145)])
 def test_block_in_fused(engine, state_dict, B, T):
-    """Fused LN1+in_proj+short conv+gate vs fp32 torch (oracle ops), channel-major outputs."""
+    """Fused LN1+in_proj+short conv+gate vs fp32 torch (oracle ops), channel-major outputs.  Tails of 1..16 tokens (1025, 8193,
+    272, 140, 8200) ride on the read's last full tile (160 token columns); 145 (17-token tail) and 70 keep a tile of their own."""
     from oracle import hyena_oracle as O
 
     layer = 1
