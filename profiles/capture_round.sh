@@ -11,9 +11,11 @@ python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/${TAG}_bench_
 python bench.py --steps 2 --warmup 1 $K2ONLY > gpurun_out/${TAG}_bench_short.json 2>> gpurun_out/${TAG}_bench.err || exit 1
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/${TAG}_launches.csv \
     python bench.py --steps 2 --warmup 1 $K2ONLY > gpurun_out/${TAG}_ncu_launches.log 2>&1
-for k in block_mlp_kernel longconv_tc2_kernel block_in_kernel score_pool_kernel; do
+for k in block_mlp_kernel longconv_tc2_kernel block_in_kernel score_pool_kernel embed_in_kernel; do
   ncu --set full --clock-control none --import-source on -k regex:$k --launch-skip 6 -c 1 -f -o gpurun_out/${TAG}_$k \
       python bench.py --steps 2 --warmup 1 $K2ONLY > gpurun_out/${TAG}_ncu_$k.log 2>&1
+  # summarise on the box and drop the 12-14 MB report: gpurun brings back at most 64 MiB
+  python profiles/ncu_summary.py gpurun_out/${TAG}_$k.ncu-rep > gpurun_out/${TAG}_$k.txt 2>&1 && rm -f gpurun_out/${TAG}_$k.ncu-rep
 done
 tail -c 400 gpurun_out/${TAG}_bench.json
 # the chunked form of the tensor-core conv (reads longer than 8 200 tokens): a forward of 16 x 32 769 tokens only
@@ -30,3 +32,4 @@ torch.cuda.synchronize()
 PY
 python gpurun_out/_long_fwd.py && ncu --set full --clock-control none --import-source on -k regex:longconv_tc2_kernel --launch-skip 5 -c 1 -f \
     -o gpurun_out/${TAG}_longconv_tc_chunked python gpurun_out/_long_fwd.py > gpurun_out/${TAG}_ncu_longconv_tc_chunked.log 2>&1
+python profiles/ncu_summary.py gpurun_out/${TAG}_longconv_tc_chunked.ncu-rep > gpurun_out/${TAG}_longconv_tc2_chunked.txt 2>&1 && rm -f gpurun_out/${TAG}_longconv_tc_chunked.ncu-rep

@@ -11,7 +11,7 @@ rows = [r for r in csv.reader(open(sys.argv[1])) if len(r) > 14 and r[0].isdigit
 bench = json.load(open(sys.argv[2]))
 STEP = {"block_mlp_kernel": "block_mlp", "longconv_tc2_kernel": "longconv", "longconv_tc_kernel": "longconv", "longconv_fast_kernel": "longconv",
         "block_in_kernel": "block_in", "score_pool_kernel": "gemm_score", "head_fused_kernel": "head", "embed_kernel": "embed",
-        "encode_kernel": "encode"}
+        "encode_kernel": "encode", "embed_in_kernel": "embed_in", "gather_tails_kernel": "block_mlp"}
 agg = collections.OrderedDict()
 for r in rows:
     name = re.sub(r"^void ", "", r[4]).replace("clm::", "")

@@ -8,7 +8,8 @@ side = torch.cuda.Stream()
 host = torch.empty(128 << 20, dtype=torch.uint8).pin_memory()
 dev = torch.empty(128 << 20, dtype=torch.uint8, device="cuda")
 for B, T, n in ((32, 8193, 600), (16, 16385, 200), (8, 32769, 100), (31, 5000, 300), (3, 8200, 300), (64, 4097, 200), (85, 3073, 200),
-                (255, 1025, 200), (127, 2049, 200), (102, 2560, 200), (21, 12289, 200), (13, 20000, 100), (64, 4096, 200), (5, 32769, 100)):
+                (255, 1025, 200), (127, 2049, 200), (102, 2560, 200), (21, 12289, 200), (13, 20000, 100), (64, 4096, 200), (5, 32769, 100),
+                (40, 3000, 200), (9, 2064, 200), (70, 200, 200)):   # 56-token tails (gathered only), 16-token tails, short reads
     eng = Engine(sd, device=0, max_batch=B, max_tokens=T)
     ids = torch.randint(7, 11, (B, T), dtype=torch.uint8, device="cuda")
     first = eng.forward(ids).clone()
