@@ -743,4 +743,21 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    # stdout carries exactly ONE line, the JSON record: libraries that write to fd 1 on their own (NCCL prints its version
+    # line there when NCCL_DEBUG is set in the environment) are sent to stderr for the duration of the run
+    sys.stdout.flush()
+    _real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        import contextlib
+        import io
+
+        _buf = io.StringIO()
+        with contextlib.redirect_stdout(_buf):
+            main()
+    finally:
+        sys.stdout.flush()
+        os.dup2(_real_stdout, 1)
+        os.close(_real_stdout)
+    sys.stdout.write(_buf.getvalue())
+    sys.stdout.flush()
