@@ -164,7 +164,12 @@ int clm_block_mlp_trace(clm_ctx* ctx, int layer, const void* d_y, float* d_res, 
  * workspace) with the optional clock trace (d_trace may be NULL). */
 int clm_block_mlp_cm_trace(clm_ctx* ctx, int layer, const void* d_y_cm, float* d_res, int B, int T, int Tp, int write_xn,
                            long long* d_trace, void* stream);
-/* Runtime switches: "fused_mlp" / "fused_in" (default 1) select the fused block kernels in clm_forward. */
+/* Runtime switches: "fused_mlp" / "fused_in" (default 1) select the fused block kernels in clm_forward.  Others select a
+ * different kernel for the same math (A/B partners and test hooks; every one of them is held to the logit tolerance by
+ * tests/test_gpu_forward.py::test_kernel_variants_agree): "tc_conv", "tc_pipe", "tc_pack4", "tc_chunked",
+ * "tc_pipe_chunked" (forms of the long convolution), "fused_score_pool", "fused_head", "head_coop", "skip_dead_res",
+ * "embed_in" / "embed_res" (block 0's first half and residual input by table lookup over the token ids, default 1),
+ * "mlp_gather_tails" / "in_ext_tail" (tail tokens share tiles, default 1), "y_channel_major".  Unknown names are an error. */
 int clm_set_option(clm_ctx* ctx, const char* name, int value);
 /* out = (causal_long_conv(vx, k_layer) + bias_layer * vx) * x0 on channel-major bf16 [B][D][Tp]. */
 int clm_longconv(clm_ctx* ctx, int layer, const void* d_vx, const void* d_x0, void* d_out, int B, int T, int Tp,
