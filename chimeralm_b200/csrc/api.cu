@@ -188,6 +188,9 @@ struct clm_ctx {
   bool mlp_2cta = false;  // CTA-pair (cta_group::2) version of the fused block tail
   bool mlp_epi16 = false; // fused block tail with 16 epilogue warps (block_mlp16.cuh)
   int mlp_helpers_high = 0;
+  bool pdl = true;        // programmatic dependent launch of the step's kernels (launch_k)
+  bool pdl_now = false;   // ... for the forward being issued: only when EVERY kernel between the embedding and the head takes part
+                          // (the tensor-core conv; with the fp32 FFT conv in the chain the step measured 2.7 % slower, profiles/r2_ab_interleaved.txt)
   bool embed_in = true;   // block 0's first half by table lookup over the token ids (embed_in.cuh) instead of block_in_kernel
   float* u_tab0 = nullptr;   // [768][16] in_proj output of block 0 per vocabulary row
   float* emb_r32 = nullptr;  // embedding rows as a 32-row R32 table: block 0's residual input is looked up by token id
@@ -259,6 +262,20 @@ int bind_constants(clm_ctx* c, cudaStream_t st) {
   CLM_CUDA(c, cudaMemcpyToSymbolAsync(bm::c_mlp, c->h_mlp.data(), c->h_mlp.size() * sizeof(bm::LayerConsts), 0, cudaMemcpyHostToDevice, st));
   g_const_owner[dev] = c;
   return 0;
+}
+
+// Launch with (c->pdl) or without programmatic stream serialization: every kernel launched through here calls
+// ptx::griddep_wait() before it touches anything its predecessors wrote, so its prologue may overlap their tail.
+template <typename... Params, typename... Args>
+cudaError_t launch_k(clm_ctx* c, void (*kern)(Params...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at{};
+  at.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at.val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = &at;
+  cfg.numAttrs = (c->pdl_now && !c->prof_on) ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<Params>(args)...);
 }
 
 int ensure_smem_attr(clm_ctx* c, const void* func, int bytes) {
@@ -476,7 +493,7 @@ int launch_block_in(clm_ctx* c, int layer, const __nv_bfloat16* xn, int B, int T
   }
 #endif
   const int grid = std::min(p.num_tiles, c->num_sms);
-  block_in_kernel<<<grid, bi::THREADS, bi::SMEM_TOTAL, st>>>(L.tm_inf, tmVX, tmX0, tmXN, tmXNE, p);
+  launch_k(c, block_in_kernel, dim3(grid), dim3(bi::THREADS), bi::SMEM_TOTAL, st, L.tm_inf, tmVX, tmX0, tmXN, tmXNE, p);
   CLM_LAUNCH_CHECK(c, "block_in");
   return 0;
 }
@@ -492,8 +509,8 @@ int launch_embed_in(clm_ctx* c, const void* d_ids, int ids_dtype, int B, int T, 
   p.err = c->d_err;
   const dim3 grid((unsigned)((Tp + ei::BLOCK_TOK - 1) / ei::BLOCK_TOK), ei::D / ei::CG, (unsigned)B);
 #define CLM_EI_LAUNCH(IdT)                                                          \
-  if (vx_f16) embed_in_kernel<IdT, true><<<grid, ei::THREADS, 0, st>>>(p);           \
-  else embed_in_kernel<IdT, false><<<grid, ei::THREADS, 0, st>>>(p)
+  if (vx_f16) launch_k(c, embed_in_kernel<IdT, true>, grid, dim3(ei::THREADS), 0, st, p);           \
+  else launch_k(c, embed_in_kernel<IdT, false>, grid, dim3(ei::THREADS), 0, st, p)
   switch (ids_dtype) {
     case CLM_U8: CLM_EI_LAUNCH(uint8_t); break;
     case CLM_I32: CLM_EI_LAUNCH(int32_t); break;
@@ -552,7 +569,7 @@ int launch_block_mlp(clm_ctx* c, int layer, const __nv_bfloat16* y, float* res, 
     const int D = c->cfg.d_model;
     const size_t TG = (size_t)n_g * bm::BM;
     if (n_g > 0 && n_g < B && TG * D <= c->yg_elems) {
-      gather_tails_kernel<<<(unsigned)((TG * D + 255) / 256), 256, 0, st>>>(y, c->YG, B, D, Tp, (int)TG, T - Lt, Lt, P);
+      launch_k(c, gather_tails_kernel, dim3((unsigned)((TG * D + 255) / 256)), dim3(256), 0, st, y, c->YG, B, D, Tp, (int)TG, T - Lt, Lt, P);
       CLM_LAUNCH_CHECK(c, "gather_tails");
       cuuint64_t dims[3] = {(cuuint64_t)TG, (cuuint64_t)D, 1};
       cuuint64_t strides[2] = {(cuuint64_t)TG * 2, (cuuint64_t)TG * D * 2};
@@ -600,7 +617,7 @@ int launch_block_mlp(clm_ctx* c, int layer, const __nv_bfloat16* y, float* res, 
 #define CLM_MLP_LAUNCH(E, LAG)                                                                                             \
   {                                                                                                                        \
     if (int rc_attr = ensure_smem_attr(c, (const void*)(block_mlp_kernel<E, LAG>), (int)(bm::SMEM_TOTAL))) return rc_attr;  \
-    block_mlp_kernel<E, LAG><<<grid, bm::THREADS_WG, bm::SMEM_TOTAL, st>>>(tmY, L.tm_out_t, L.tm_fc1_t, L.tm_fc2_t, tmXN, tmYG, p); \
+    launch_k(c, block_mlp_kernel<E, LAG>, dim3(grid), dim3(bm::THREADS_WG), bm::SMEM_TOTAL, st, tmY, L.tm_out_t, L.tm_fc1_t, L.tm_fc2_t, tmXN, tmYG, p); \
   }
   if (c->mlp_fc2_lag >= 2) CLM_MLP_LAUNCH(33, 2)
   else if (c->mlp_early_res >= 33) CLM_MLP_LAUNCH(33, 1)
@@ -864,13 +881,13 @@ int launch_longconv_tc(clm_ctx* c, int layer, const __half* vx, const __nv_bfloa
     p.G = reinterpret_cast<const uint4*>(L.gtcH);
     p.rel = L.tc_relH;
     if (trace) longconv_tc2_kernel<true, false, true><<<grid, tc2::THREADS2, tc2::SMEM2_TOTAL, st>>>(tm, tmo, tmg, p);
-    else longconv_tc2_kernel<false, false, true><<<grid, tc2::THREADS2, tc2::SMEM2_TOTAL, st>>>(tm, tmo, tmg, p);
+    else launch_k(c, longconv_tc2_kernel<false, false, true>, dim3(grid), dim3(tc2::THREADS2), tc2::SMEM2_TOTAL, st, tm, tmo, tmg, p);
   }
   else if (pl.nc > 1) longconv_tc_kernel<true><<<grid, tc::THREADS_CH, tc::SMEM_TOTAL, st>>>(tm, tmo, tmg, p);
   else if (pack4 && trace) longconv_tc2_kernel<true, true, false><<<grid, tc2::THREADS2, tc2::SMEM2_TOTAL, st>>>(tm, tmo, tmg, p);
-  else if (pack4) longconv_tc2_kernel<false, true, false><<<grid, tc2::THREADS2, tc2::SMEM2_TOTAL, st>>>(tm, tmo, tmg, p);
+  else if (pack4) launch_k(c, longconv_tc2_kernel<false, true, false>, dim3(grid), dim3(tc2::THREADS2), tc2::SMEM2_TOTAL, st, tm, tmo, tmg, p);
   else if (c->tc_pipe && trace) longconv_tc2_kernel<true, false, false><<<grid, tc2::THREADS2, tc2::SMEM2_TOTAL, st>>>(tm, tmo, tmg, p);
-  else if (c->tc_pipe) longconv_tc2_kernel<false, false, false><<<grid, tc2::THREADS2, tc2::SMEM2_TOTAL, st>>>(tm, tmo, tmg, p);
+  else if (c->tc_pipe) launch_k(c, longconv_tc2_kernel<false, false, false>, dim3(grid), dim3(tc2::THREADS2), tc2::SMEM2_TOTAL, st, tm, tmo, tmg, p);
   else longconv_tc_kernel<false><<<grid, tc::THREADS, tc::SMEM_TOTAL, st>>>(tm, tmo, tmg, p);
   CLM_LAUNCH_CHECK(c, pl.nc > 1 ? "longconv_tc_chunked" : (c->tc_pipe ? "longconv_tc2" : "longconv_tc"));
   return 0;
@@ -1399,6 +1416,9 @@ int clm_forward(clm_ctx* c, const void* d_ids, int ids_dtype, int B, int T, floa
 #define STOP_AFTER(layer, stage) \
   if (c->dbg_layer == (layer) && c->dbg_stage == (stage)) return 0
 
+  c->pdl_now = c->pdl && c->fused_in && c->fused_mlp && c->tc_pipe && c->dbg_layer < 0 && tc_conv_applies(c, T) &&
+               (tc_plan(T).nc == 1 || c->tc_pipe_chunked);
+  struct PdlReset { clm_ctx* c; ~PdlReset() { c->pdl_now = false; } } pdl_reset_{c};
   // block 0's first half reads the ids directly (table lookup), so nobody consumes the embedding's xn rows
   const bool ei0 = c->embed_in && c->u_tab0 && c->fused_in && c->dbg_layer != 0 && g.n_layer > 0 && B <= 65535;
   __nv_bfloat16* const emb_xn = ei0 ? nullptr : c->XN;
@@ -1519,7 +1539,7 @@ int clm_forward(clm_ctx* c, const void* d_ids, int ids_dtype, int B, int T, floa
     sp_.tiles_per_seq = (T + sp::BM - 1) / sp::BM; sp_.num_tiles = B * sp_.tiles_per_seq;
     sp_.pool_mode = g.pooling;
     n_split = sp_.tiles_per_seq;
-    score_pool_kernel<<<std::min(sp_.num_tiles, c->num_sms), sp::THREADS, sp::SMEM_TOTAL, st>>>(tmA, c->tm_att0f, sp_);
+    launch_k(c, score_pool_kernel, dim3(std::min(sp_.num_tiles, c->num_sms)), dim3(sp::THREADS), sp::SMEM_TOTAL, st, tmA, c->tm_att0f, sp_);
     CLM_LAUNCH_CHECK(c, "score_pool");
   } else {
   {
@@ -1729,6 +1749,7 @@ int clm_set_option(clm_ctx* c, const char* name, int value) {
   else if (n == "mlp_helpers_high") c->mlp_helpers_high = value;
   else if (n == "mlp_store_a") c->mlp_store_a = value;
   else if (n == "embed_in") c->embed_in = value != 0;
+  else if (n == "pdl") c->pdl = value != 0;
   else if (n == "embed_res") c->embed_res = value != 0;
   else if (n == "mlp_gather_tails") c->mlp_gather_tails = value != 0;
   else if (n == "in_prefetch") c->in_prefetch = value;

@@ -84,6 +84,7 @@ block_in_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
   using namespace bi;
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((ptx::smem_u32(smem) & 1023u) != 0) __trap();
+  ptx::griddep_launch();
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
   uint64_t* w_full = bars;          // [NSLOT]
   uint64_t* w_empty = bars + 4;     // [NSLOT] (NSLOT <= 4)
@@ -116,6 +117,7 @@ block_in_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
   __syncthreads();
   ptx::tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_ptr;
+  ptx::griddep_wait();   // xn comes from the kernel before this one
 
   if (warp == 0) {
     // =========================== TMA producer: 12 weight slots (2 k-blocks each) per tile ===========

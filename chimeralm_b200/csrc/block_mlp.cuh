@@ -138,6 +138,8 @@ __device__ __forceinline__ uint32_t gelu_tanh_bf16x2(f2t h) {
 // y [B][D][Tp] channel-major -> yg [D][TG]: column 128 g + r = token t0 + r % L of read g P + r / L (zero where there is none)
 __global__ void gather_tails_kernel(const __nv_bfloat16* __restrict__ y, __nv_bfloat16* __restrict__ yg, int B, int D, int Tp,
                                     int TG, int t0, int L, int P) {
+  ptx::griddep_launch();
+  ptx::griddep_wait();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= D * TG) return;
   const int c = idx / TG, col = idx - c * TG;
@@ -162,6 +164,7 @@ block_mlp_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
   using namespace bm;
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((ptx::smem_u32(smem) & 1023u) != 0) __trap();  // swizzled UMMA/TMA tiles need 1 KB alignment
+  ptx::griddep_launch();
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
   uint64_t* w_full = bars;                 // [NSLOT]
   uint64_t* w_empty = bars + 5;            // [NSLOT]
@@ -208,6 +211,7 @@ block_mlp_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
   __syncthreads();
   ptx::tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_ptr;
+  ptx::griddep_wait();   // y, the residual and (gathered tiles) yg come from the kernels before this one
   // All CTAs run the same tile schedule in lockstep, so their residual reads (E1) and writes (E3) would hit HBM as
   // chip-wide bursts while the tensor pipes idle.  Starting the CTAs in `stagger` phase groups spreads that traffic.
   if (p.stagger_cycles > 0) {

@@ -81,6 +81,7 @@ __global__ void __launch_bounds__(ei::THREADS) embed_in_kernel(EmbedInParams p) 
   // [group][channel][id], 17 words per channel: slot 16 holds 0 = "before the read" (the causal zero padding), so the
   // lookup needs no select; lanes of a warp read <= 17 consecutive words of one channel: no bank conflicts
   constexpr int NS = NV + 1;
+  ptx::griddep_launch();
   __shared__ float s_u[3][CG][NS];
   __shared__ __align__(16) float4 s_c[3][CG];   // (w0, w1, w2, cb) per group and channel; the v group carries vx_scale
   const int b = blockIdx.z, c0 = blockIdx.y * CG;
@@ -94,6 +95,7 @@ __global__ void __launch_bounds__(ei::THREADS) embed_in_kernel(EmbedInParams p) 
     s_c[g][i - g * CG] = make_float4(__ldg(p.cw + ch * 3) * a, __ldg(p.cw + ch * 3 + 1) * a, __ldg(p.cw + ch * 3 + 2) * a,
                                      __ldg(p.cb + ch) * a);
   }
+  ptx::griddep_wait();   // the ids come from the encode kernel (the tables above are constants)
   const int t0 = blockIdx.x * BLOCK_TOK + threadIdx.x * TOK;
   // shared-memory byte address of s_u[0][cl][id] for tokens t0 - 2 .. t0 + 7, bumped by one channel per iteration (the group
   // offset is an immediate): one LDS per lookup and 10 adds per channel instead of per-lookup address arithmetic

@@ -70,6 +70,7 @@ longconv_tc2_kernel(const __grid_constant__ CUtensorMap tmVX, const __grid_const
   using namespace tc2;
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((ptx::smem_u32(smem) & 1023u) != 0) __trap();
+  ptx::griddep_launch();
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF2_BAR);
   uint64_t* z_full = bars;           // [3] z tile landed (TMA)
   uint64_t* g_full = bars + 3;       // [3] x0 gate tile landed in the z buffer
@@ -133,6 +134,7 @@ longconv_tc2_kernel(const __grid_constant__ CUtensorMap tmVX, const __grid_const
   ptx::tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_ptr;
   const uint32_t U0 = tmem_base, U1 = tmem_base + 128, U2 = tmem_base + 256, U3 = tmem_base + 384;
+  ptx::griddep_wait();   // vx and x0 come from the kernel before this one (the 64 KB constant stack above does not)
 
   if (warp == W_PROD) {
     // =========================== TMA producer (z loads, output stores) ===========================

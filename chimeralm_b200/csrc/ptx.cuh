@@ -85,6 +85,15 @@ __device__ __forceinline__ void tc_fence_after_sync() {
 }
 
 // ------------------------------------------------------------------ TMA
+// Programmatic dependent launch: a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start while its
+// predecessor in the stream is still draining (its CTAs take the SMs the predecessor's CTAs have left); everything before
+// this wait (barrier init, TMEM allocation, tensor-map prefetch, constants into shared memory) overlaps that tail and the
+// launch latency.  After the wait all of the predecessor's memory operations are visible.  A no-op in a plain launch.
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// ... and the other half: once every CTA of THIS grid has issued it (or exited), the next kernel's CTAs may be placed on SMs as
+// they become free.  Issued at the top of a kernel: the dependents still wait (griddep_wait) for this grid to complete.
+__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // 1-D bulk copy global -> shared (TMA engine, no tensor map): 16-byte aligned addresses, size a multiple of 16
 __device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),

@@ -86,6 +86,7 @@ score_pool_kernel(const __grid_constant__ CUtensorMap tmXN, const __grid_constan
   using namespace sp;
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((ptx::smem_u32(smem) & 1023u) != 0) __trap();
+  ptx::griddep_launch();
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
   uint64_t* w_full = bars;        // [NW] weight k-block landed
   uint64_t* w_empty = bars + 2;   // [NW] its MMAs are done
@@ -115,6 +116,7 @@ score_pool_kernel(const __grid_constant__ CUtensorMap tmXN, const __grid_constan
   __syncthreads();
   ptx::tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_ptr;
+  ptx::griddep_wait();   // the normalised rows come from the last block's kernel
 
   if (warp == 0) {
     if (lane == 0) {

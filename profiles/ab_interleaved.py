@@ -9,6 +9,11 @@ sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
 from chimeralm_b200.engine import Engine  # noqa: E402
 from chimeralm_b200.weights import make_state_dict  # noqa: E402
 
+# --noprof: no per-kernel events between the launches (they serialise the stream and switch programmatic dependent launch off):
+# the step time alone
+NOPROF = "--noprof" in sys.argv
+if NOPROF:
+    sys.argv.remove("--noprof")
 opt = sys.argv[1]
 B, T = (int(sys.argv[2]), int(sys.argv[3])) if len(sys.argv) > 3 else (32, 8193)
 eng = Engine(make_state_dict(0), max_batch=B, max_tokens=T)
@@ -22,16 +27,19 @@ for rep in range(4):
         eng.set_option(opt, val)
         for _ in range(3):
             eng.forward(ids)
-        eng.profile(True)
-        eng.profile_reset()
+        if not NOPROF:
+            eng.profile(True)
+            eng.profile_reset()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(n):
             eng.forward(ids)
         e1.record()
         torch.cuda.synchronize()
-        prof = {k: v[0] / n for k, v in eng.profile_read().items()}
-        eng.profile(False)
+        prof = {}
+        if not NOPROF:
+            prof = {k: v[0] / n for k, v in eng.profile_read().items()}
+            eng.profile(False)
         prof["step"] = e0.elapsed_time(e1) / n
         res[val].append(prof)
 for val in (1, 0):

@@ -285,6 +285,7 @@ def test_full_size_batch_permutation_invariance(state_dict):
                                       ("mlp_gather_tails", 40),
                                       ("embed_in", 8193), ("embed_in", 700), ("embed_in", 40), ("embed_in", 3000), ("embed_in", 9000),
                                       ("in_ext_tail", 8193), ("in_ext_tail", 1296), ("in_ext_tail", 2060), ("in_ext_tail", 9000),
+                                      ("pdl", 8193), ("pdl", 700), ("pdl", 20000),
                                       ("embed_res", 8193), ("embed_res", 700), ("embed_res", 40), ("embed_res", 1281),
                                       ("fused_mlp", 700), ("fused_in", 700), ("fast_conv", 700), ("mlp_epi16", 1500), ("mlp_pp", 8193), ("mlp_early_res", 8193), ("mlp_fc2_lag", 8193),
                                       ("skip_dead_res", 700), ("in_2cta", 700), ("in_2cta", 8193)])
