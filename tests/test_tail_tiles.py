@@ -119,3 +119,43 @@ def test_k2_block_in_tile_count():
     assert block_in_plan(32, 8193) == (64, 2048, 1)
     assert block_in_plan(32, 8193, ext=False) == (65, 2080, 0)
     assert block_in_plan(2, 145)[2] == 0             # 17-token tail: a tile of its own
+
+
+def test_block0_table_lookup_equals_the_oracle_ops():
+    """DESIGN.md 4.3a in the oracle's own arithmetic (fp32, CPU): block 0's LayerNorm1 + in_proj depend on the token id alone, so
+    a 16-row table U[id] followed by the causal 3-tap filter and the gate gives exactly what the oracle's embedding ->
+    layer_norm -> linear -> conv1d -> split -> gate gives (chimeralm_b200/csrc/embed_in.cuh restated with torch ops; the
+    identity, not the CUDA kernel, is what this pins - the kernel is held to the oracle by tests/test_gpu_forward.py)."""
+    import torch
+    import torch.nn.functional as F
+
+    from chimeralm_b200.config import DEFAULT_CONFIG as cfg
+    from chimeralm_b200.weights import make_state_dict, perturb_norms
+    from oracle import hyena_oracle as O
+
+    sd = {k: torch.as_tensor(v) for k, v in make_state_dict(3).items()}
+    perturb_norms(sd, seed=4)   # non-trivial LayerNorm affines
+    p = f"{O.BB}layers.0."
+    D = cfg.d_model
+    E = sd[O.BB + "embeddings.word_embeddings.weight"]
+    g = torch.Generator().manual_seed(11)
+    ids = torch.randint(0, 16, (3, 301), generator=g)
+    ids[0, :40] = 4   # a [PAD] prefix like a left-padded batch
+    # the oracle's path (hyena_oracle.block / hyena_operator up to the first gate)
+    x = F.layer_norm(F.embedding(ids, E).float(), (D,), sd[p + "norm1.weight"], sd[p + "norm1.bias"], cfg.layer_norm_epsilon)
+    u = F.linear(x, sd[p + "mixer.in_proj.weight"], sd[p + "mixer.in_proj.bias"]).transpose(1, 2)
+    uc = F.conv1d(u, sd[p + "mixer.short_filter.weight"], sd[p + "mixer.short_filter.bias"], padding=2, groups=3 * D)[..., :ids.shape[1]]
+    x0_ref, x1_ref, v_ref = uc.split(D, dim=1)
+    # the table form: U[id][ch], u = 0 before the read, out = w0 u[t-2] + w1 u[t-1] + w2 u[t] + cb
+    U = F.linear(F.layer_norm(E[:16].float(), (D,), sd[p + "norm1.weight"], sd[p + "norm1.bias"], cfg.layer_norm_epsilon),
+                 sd[p + "mixer.in_proj.weight"], sd[p + "mixer.in_proj.bias"])          # [16, 768]
+    w = sd[p + "mixer.short_filter.weight"].reshape(3 * D, 3)
+    cb = sd[p + "mixer.short_filter.bias"]
+    ut = U[ids]                                                                           # [B, T, 768]
+    z = torch.zeros_like(ut[:, :1])
+    um1 = torch.cat([z, ut[:, :-1]], 1)
+    um2 = torch.cat([z, z, ut[:, :-2]], 1)
+    out = (w[:, 0] * um2 + w[:, 1] * um1 + w[:, 2] * ut + cb).transpose(1, 2)
+    x0, x1, v = out.split(D, dim=1)
+    assert (x0 - x0_ref).abs().max().item() <= 1e-5
+    assert (v * x1 - v_ref * x1_ref).abs().max().item() <= 1e-5
