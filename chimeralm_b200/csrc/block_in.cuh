@@ -19,6 +19,10 @@
 // Per tile two passes (channel halves); each pass accumulates the x0/x1/v blocks of the same
 // 128 channels in TMEM columns [0,144) [144,288) [288,432).
 //
+// A read's tail of 1..16 tokens (T = 128 f + L) rides on its last full tile: N = 160 columns, TMEM groups at a stride of 160
+// (BlockInParams::ext_L).  Block 0 does not run this kernel at all: its input is one of 16 embedding rows, so
+// in_proj is a table (embed_in.cuh).
+//
 // LayerNorm's affine is folded offline (clm_finalize): W' = W_in * diag(gamma),
 // b' = b_in + W_in beta, so the kernel only normalises.
 //

@@ -9,6 +9,10 @@
 // 1024-wide hidden activations on chip: per token the kernel reads 512 B (y, bf16) + 1 KB
 // (res) and writes 1 KB (res), instead of ~9.2 KB for the unfused sequence.
 //
+// Round 2 additions: reads that end in a partial tile of <= 64 tokens share GATHERED tiles (rows are
+// independent in all three GEMMs: BlockMlpParams::gather_L, gather_tails_kernel), and block 0 reads its residual input from the
+// embedding table by token id (BlockMlpParams::res_tab) - there is no embedding kernel on the product path.
+//
 // One CTA per SM loops over tiles of 128 tokens.  All three GEMMs run on tcgen05 with the
 // accumulators in TMEM:
 //   (the two 256-column halves swap roles every tile)
